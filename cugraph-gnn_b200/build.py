@@ -1,0 +1,76 @@
+"""Builds libwholegraph_b200.so (the C-ABI drop-in for the hot path) for sm_100a, in-tree.
+
+    python cugraph-gnn_b200/build.py [--force] [-v]
+
+Every csrc/*.cu is compiled to an object in csrc/build/ (in parallel, only when stale) and
+linked into cugraph-gnn_b200/lib/libwholegraph_b200.so.  nvcc cross-compiles without a GPU.
+"""
+import concurrent.futures
+import glob
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(CSRC, "build")
+LIBDIR = os.path.join(HERE, "lib")
+LIB = os.path.join(LIBDIR, "libwholegraph_b200.so")
+
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-ccbin", HOST_CXX,
+    "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
+    "--expt-relaxed-constexpr", "--extended-lambda",
+    "-I", os.path.join(ROOT, "include"),
+    "-I", CSRC,
+    "-DWGB_BUILDING_LIB",
+]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def _compile(src, verbose):
+    obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "wholememory", "*.h"))
+    if _stale(obj, [src] + headers + [__file__]):
+        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj, True
+    return obj, False
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    if force:
+        for f in glob.glob(os.path.join(OBJ, "*.o")):
+            os.remove(f)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(lambda s: _compile(s, verbose), srcs))
+    objs = [o for o, _ in results]
+    if force or any(changed for _, changed in results) or _stale(LIB, objs):
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-ccbin", HOST_CXX, "-lrt", "-lpthread", "-ldl",
+                                                      "-Xlinker", "--no-undefined"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

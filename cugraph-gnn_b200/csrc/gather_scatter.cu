@@ -1,0 +1,435 @@
+// G1 / G2: row gather and scatter over a WholeMemory table (sm_100a).
+//
+// Replaces the reference's gather_func_kernel / gather_func_sub_warp_kernel / scatter_func_kernel
+// (cpp/src/wholememory_ops/functions/gather_scatter_func.cuh:243-365, 509-587) and, for tables
+// striped over the GPUs of one NVSwitch box, the whole NCCL bucket / all-to-all pipeline of
+// cpp/src/wholememory_ops/gather_op_impl_nccl.cu:23-171: remote rows are read (or written) with
+// plain ld.global / st.global on peer-mapped pointers from inside this kernel.
+//
+// Design: the dense side (gather output / scatter input) is viewed as a flat
+// sequence of 16-byte vectors; thread t moves vectors t, t+T, t+2T, t+3T of a 4*T window, all four
+// loads issued before the first store, so every warp keeps 4 x 512 B in flight and both sides are
+// fully coalesced for any row width (one warp-wide access = 512 contiguous bytes of one or more
+// rows).  No shared-memory bounce, no per-access divide: the row of a vector comes from a
+// multiply-shift, the owning rank from a compare chain over <= 7 chunk boundaries that live in
+// the kernel parameter block.
+
+#include "wm_common.cuh"
+
+namespace wgb {
+
+template <int BYTES>
+struct vec_of;
+template <>
+struct vec_of<1> { using type = unsigned char; };
+template <>
+struct vec_of<2> { using type = unsigned short; };
+template <>
+struct vec_of<4> { using type = unsigned int; };
+template <>
+struct vec_of<8> { using type = uint2; };
+template <>
+struct vec_of<16> { using type = uint4; };
+
+// streaming loads/stores: every byte is touched once per call, keep L1 for the index vector.
+template <typename V>
+__device__ __forceinline__ V ld_stream(const V* p)
+{
+  return *p;
+}
+template <>
+__device__ __forceinline__ uint4 ld_stream<uint4>(const uint4* p)
+{
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+template <>
+__device__ __forceinline__ uint2 ld_stream<uint2>(const uint2* p)
+{
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+struct RowDiv {  // q = n / d for n < 2^31 via multiply-shift
+  unsigned int mul;
+  unsigned int shift;
+  unsigned int d;
+  __device__ __forceinline__ unsigned int div(unsigned int n) const
+  {
+    return (unsigned int)(((unsigned long long)n * mul) >> shift);
+  }
+};
+
+static RowDiv make_row_div(unsigned int d)
+{
+  RowDiv r;
+  r.d   = d;
+  int l = 0;
+  while ((1u << l) < d)
+    l++;
+  r.shift = 31 + l;
+  r.mul   = (unsigned int)(((1ULL << r.shift) + d - 1) / d);
+  return r;
+}
+
+constexpr int kBlock  = 256;
+constexpr int kUnroll = 4;
+
+// ---- same-dtype path: pure byte movement ---------------------------------------------------------
+// SCATTER=false: dense[i, :] = table[idx[i], :]      SCATTER=true: table[idx[i], :] = dense[i, :]
+template <typename IdxT, int VEC, bool CHUNKED, bool SCATTER>
+__global__ void __launch_bounds__(kBlock) rows_copy_kernel(ChunkRef table,
+                                                           unsigned long long table_off_bytes,
+                                                           unsigned long long row_stride_bytes,
+                                                           const IdxT* __restrict__ idx,
+                                                           unsigned int total_vecs,
+                                                           RowDiv vpr,
+                                                           char* __restrict__ dense,
+                                                           unsigned long long dense_stride_bytes)
+{
+  using V                   = typename vec_of<VEC>::type;
+  const unsigned int window = kBlock * kUnroll;
+  for (unsigned int base = blockIdx.x * window; base < total_vecs; base += gridDim.x * window) {
+    V val[kUnroll];
+    char* tptr[kUnroll];
+    char* dptr[kUnroll];
+    bool ok[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      unsigned int j   = base + u * kBlock + threadIdx.x;
+      ok[u]            = j < total_vecs;
+      unsigned int row = vpr.div(ok[u] ? j : 0);
+      unsigned int c   = (ok[u] ? j : 0) - row * vpr.d;
+      long long r      = ok[u] ? (long long)idx[row] : -1;
+      ok[u]            = ok[u] && r >= 0;
+      unsigned long long off = table_off_bytes + (unsigned long long)(r < 0 ? 0 : r) * row_stride_bytes;
+      tptr[u] = table.at<CHUNKED>(off) + (unsigned long long)c * VEC;
+      dptr[u] = dense + (unsigned long long)row * dense_stride_bytes + (unsigned long long)c * VEC;
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      if (ok[u]) val[u] = ld_stream(reinterpret_cast<const V*>(SCATTER ? dptr[u] : tptr[u]));
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      if (ok[u]) *reinterpret_cast<V*>(SCATTER ? tptr[u] : dptr[u]) = val[u];
+    }
+  }
+}
+
+// ---- converting path -----------------------------------------------------------------------------
+// element conversion as the reference does it (gather_scatter_func.cuh:150-197): half / bf16 go
+// through float, everything else is a static_cast.
+template <typename T>
+struct via { using type = T; };
+template <>
+struct via<__half> { using type = float; };
+template <>
+struct via<__nv_bfloat16> { using type = float; };
+
+template <typename From, typename To>
+__device__ __forceinline__ To convert_elt(From x)
+{
+  typename via<From>::type a = static_cast<typename via<From>::type>(x);
+  typename via<To>::type b   = static_cast<typename via<To>::type>(a);
+  return static_cast<To>(b);
+}
+
+template <typename T, int N>
+struct alignas(sizeof(T) * N) elt_pack {
+  T v[N];
+};
+
+template <typename TableT, typename DenseT, typename IdxT, int ALIGN, bool SCATTER>
+__global__ void __launch_bounds__(kBlock) rows_convert_kernel(ChunkRef table,
+                                                              unsigned long long table_off_elts,
+                                                              unsigned long long row_stride_elts,
+                                                              const IdxT* __restrict__ idx,
+                                                              unsigned int total_vecs,
+                                                              RowDiv vpr,
+                                                              DenseT* __restrict__ dense,
+                                                              unsigned long long dense_stride_elts)
+{
+  using TP = elt_pack<TableT, ALIGN>;
+  using DP = elt_pack<DenseT, ALIGN>;
+  for (unsigned int j = blockIdx.x * kBlock + threadIdx.x; j < total_vecs; j += gridDim.x * kBlock) {
+    unsigned int row = vpr.div(j);
+    unsigned int c   = j - row * vpr.d;
+    long long r      = (long long)idx[row];
+    if (r < 0) continue;
+    unsigned long long off = (table_off_elts + (unsigned long long)r * row_stride_elts) * sizeof(TableT);
+    TP* tp = reinterpret_cast<TP*>(table.at<true>(off)) + c;
+    DP* dp = reinterpret_cast<DP*>(dense + (unsigned long long)row * dense_stride_elts) + c;
+    if (!SCATTER) {
+      TP in = *tp;
+      DP out;
+#pragma unroll
+      for (int k = 0; k < ALIGN; k++)
+        out.v[k] = convert_elt<TableT, DenseT>(in.v[k]);
+      *dp = out;
+    } else {
+      DP in = *dp;
+      TP out;
+#pragma unroll
+      for (int k = 0; k < ALIGN; k++)
+        out.v[k] = convert_elt<DenseT, TableT>(in.v[k]);
+      *tp = out;
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+struct RowsOpArgs {
+  ChunkRef table;
+  wholememory_matrix_description_t table_desc;
+  const void* idx;
+  wholememory_dtype_t idx_dtype;
+  int64_t n;
+  void* dense;  // already offset-free base pointer
+  wholememory_matrix_description_t dense_desc;
+  bool scatter;
+  int sms;
+  cudaStream_t stream;
+};
+
+static int largest_pow2_alignment(std::initializer_list<unsigned long long> values, int cap)
+{
+  int a = cap;
+  for (; a > 1; a /= 2) {
+    bool ok = true;
+    for (auto v : values)
+      if (v % (unsigned long long)a != 0) ok = false;
+    if (ok) break;
+  }
+  return a;
+}
+
+static int grid_for(unsigned long long work_items, int per_block, int sms_limit)
+{
+  unsigned long long blocks = (work_items + per_block - 1) / per_block;
+  int sms                   = num_sms();
+  unsigned long long cap    = (unsigned long long)(sms_limit > 0 ? std::min(sms_limit, sms) : sms) * 8ULL;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+template <typename IdxT, int VEC, bool SCATTER>
+static void launch_copy(const RowsOpArgs& a, int64_t row0, int64_t rows, unsigned int vpr)
+{
+  size_t elt                    = dtype_size(a.table_desc.dtype);
+  unsigned long long total      = (unsigned long long)rows * vpr;
+  RowDiv rd                     = make_row_div(vpr);
+  const IdxT* idx               = static_cast<const IdxT*>(a.idx) + row0;
+  unsigned long long dstride    = (unsigned long long)a.dense_desc.stride * elt;
+  char* dense                   = static_cast<char*>(a.dense) + (unsigned long long)a.dense_desc.storage_offset * elt + (unsigned long long)row0 * dstride;
+  unsigned long long toff       = (unsigned long long)a.table_desc.storage_offset * elt;
+  unsigned long long tstride    = (unsigned long long)a.table_desc.stride * elt;
+  int grid                      = grid_for(total, kBlock * kUnroll, a.sms);
+  if (a.table.world > 1)
+    rows_copy_kernel<IdxT, VEC, true, SCATTER><<<grid, kBlock, 0, a.stream>>>(a.table, toff, tstride, idx, (unsigned int)total, rd, dense, dstride);
+  else
+    rows_copy_kernel<IdxT, VEC, false, SCATTER><<<grid, kBlock, 0, a.stream>>>(a.table, toff, tstride, idx, (unsigned int)total, rd, dense, dstride);
+  WGB_CUDA_TRY(cudaGetLastError());
+}
+
+template <typename IdxT, bool SCATTER>
+static void run_copy(const RowsOpArgs& a)
+{
+  size_t elt = dtype_size(a.table_desc.dtype);
+  unsigned long long row_bytes = (unsigned long long)a.table_desc.sizes[1] * elt;
+  unsigned long long dense_addr = reinterpret_cast<unsigned long long>(a.dense) + (unsigned long long)a.dense_desc.storage_offset * elt;
+  unsigned long long base_or = 0;
+  for (int r = 0; r < a.table.world; r++)
+    base_or |= reinterpret_cast<unsigned long long>(a.table.base[r]) | (r > 0 ? a.table.start[r] : 0ULL);
+  int vec = largest_pow2_alignment({row_bytes, (unsigned long long)a.table_desc.stride * elt,
+                                    (unsigned long long)a.table_desc.storage_offset * elt, dense_addr,
+                                    (unsigned long long)a.dense_desc.stride * elt, base_or},
+                                   16);
+  if ((size_t)vec < elt) vec = (int)elt;  // element alignment is guaranteed by construction
+  unsigned int vpr = (unsigned int)(row_bytes / vec);
+  // keep every launch below 2^31 vectors so the kernel can use 32-bit index math
+  int64_t rows_per_launch = std::max<int64_t>(1, (int64_t)((1ULL << 31) - kBlock * kUnroll) / vpr);
+  for (int64_t row0 = 0; row0 < a.n; row0 += rows_per_launch) {
+    int64_t rows = std::min(rows_per_launch, a.n - row0);
+    switch (vec) {
+      case 16: launch_copy<IdxT, 16, SCATTER>(a, row0, rows, vpr); break;
+      case 8: launch_copy<IdxT, 8, SCATTER>(a, row0, rows, vpr); break;
+      case 4: launch_copy<IdxT, 4, SCATTER>(a, row0, rows, vpr); break;
+      case 2: launch_copy<IdxT, 2, SCATTER>(a, row0, rows, vpr); break;
+      default: launch_copy<IdxT, 1, SCATTER>(a, row0, rows, vpr); break;
+    }
+  }
+}
+
+template <typename TableT, typename DenseT, typename IdxT, bool SCATTER>
+static void run_convert(const RowsOpArgs& a)
+{
+  unsigned long long dense_addr = reinterpret_cast<unsigned long long>(a.dense) / sizeof(DenseT) + (unsigned long long)a.dense_desc.storage_offset;
+  unsigned long long tbase_or = 0;
+  for (int r = 0; r < a.table.world; r++)
+    tbase_or |= reinterpret_cast<unsigned long long>(a.table.base[r]) / sizeof(TableT) | (r > 0 ? a.table.start[r] / sizeof(TableT) : 0ULL);
+  int align = largest_pow2_alignment({(unsigned long long)a.table_desc.sizes[1], (unsigned long long)a.table_desc.stride,
+                                      (unsigned long long)a.table_desc.storage_offset, dense_addr,
+                                      (unsigned long long)a.dense_desc.stride, tbase_or},
+                                     4);
+  if (align == 2) align = 1;
+  unsigned int vpr        = (unsigned int)(a.table_desc.sizes[1] / align);
+  int64_t rows_per_launch = std::max<int64_t>(1, (int64_t)((1ULL << 31) - kBlock) / vpr);
+  RowDiv rd               = make_row_div(vpr);
+  for (int64_t row0 = 0; row0 < a.n; row0 += rows_per_launch) {
+    int64_t rows             = std::min(rows_per_launch, a.n - row0);
+    unsigned long long total = (unsigned long long)rows * vpr;
+    const IdxT* idx          = static_cast<const IdxT*>(a.idx) + row0;
+    DenseT* dense            = static_cast<DenseT*>(a.dense) + a.dense_desc.storage_offset + row0 * a.dense_desc.stride;
+    int grid                 = grid_for(total, kBlock, a.sms);
+    if (align == 4)
+      rows_convert_kernel<TableT, DenseT, IdxT, 4, SCATTER><<<grid, kBlock, 0, a.stream>>>(
+        a.table, (unsigned long long)a.table_desc.storage_offset, (unsigned long long)a.table_desc.stride, idx,
+        (unsigned int)total, rd, dense, (unsigned long long)a.dense_desc.stride);
+    else
+      rows_convert_kernel<TableT, DenseT, IdxT, 1, SCATTER><<<grid, kBlock, 0, a.stream>>>(
+        a.table, (unsigned long long)a.table_desc.storage_offset, (unsigned long long)a.table_desc.stride, idx,
+        (unsigned int)total, rd, dense, (unsigned long long)a.dense_desc.stride);
+    WGB_CUDA_TRY(cudaGetLastError());
+  }
+}
+
+template <typename F>
+static void for_float_type(wholememory_dtype_t dt, F&& f)
+{
+  switch (dt) {
+    case WHOLEMEMORY_DT_FLOAT: f(float{}); break;
+    case WHOLEMEMORY_DT_HALF: f(__half{}); break;
+    case WHOLEMEMORY_DT_DOUBLE: f(double{}); break;
+    case WHOLEMEMORY_DT_BF16: f(__nv_bfloat16{}); break;
+    default: throw logic_error("not a floating dtype");
+  }
+}
+template <typename F>
+static void for_int_type(wholememory_dtype_t dt, F&& f)
+{
+  switch (dt) {
+    case WHOLEMEMORY_DT_INT: f(int32_t{}); break;
+    case WHOLEMEMORY_DT_INT64: f(int64_t{}); break;
+    case WHOLEMEMORY_DT_INT16: f(int16_t{}); break;
+    case WHOLEMEMORY_DT_INT8: f(int8_t{}); break;
+    default: throw logic_error("not an integer dtype");
+  }
+}
+
+template <typename IdxT, bool SCATTER>
+static void run_rows_op_typed(const RowsOpArgs& a)
+{
+  if (a.table_desc.dtype == a.dense_desc.dtype) {
+    run_copy<IdxT, SCATTER>(a);
+    return;
+  }
+  if (wholememory_dtype_is_floating_number(a.table_desc.dtype)) {
+    for_float_type(a.table_desc.dtype, [&](auto t) {
+      for_float_type(a.dense_desc.dtype, [&](auto d) {
+        using T = decltype(t);
+        using D = decltype(d);
+        if constexpr (!std::is_same<T, D>::value) run_convert<T, D, IdxT, SCATTER>(a);
+      });
+    });
+  } else {
+    for_int_type(a.table_desc.dtype, [&](auto t) {
+      for_int_type(a.dense_desc.dtype, [&](auto d) {
+        using T = decltype(t);
+        using D = decltype(d);
+        if constexpr (!std::is_same<T, D>::value) run_convert<T, D, IdxT, SCATTER>(a);
+      });
+    });
+  }
+}
+
+// Validation shared by gather and scatter; mirrors cpp/src/wholememory_ops/gather_op.cpp:12-70 and
+// functions/gather_func.cu:53-66 (same error codes for the same mistakes).
+static wholememory_error_code_t rows_op(wholememory_tensor_t wm_tensor, wholememory_tensor_t indices_tensor,
+                                        wholememory_tensor_t dense_tensor, void* stream, int sms, bool scatter)
+{
+  if (!wm_tensor || !indices_tensor || !dense_tensor) return WHOLEMEMORY_INVALID_INPUT;
+  wholememory_tensor_description_t td = *wholememory_tensor_get_tensor_description(wm_tensor);
+  if (td.dim != 1 && td.dim != 2) {
+    log_msg(LEVEL_ERROR, "wholememory_tensor should be 1D or 2D tensor.");
+    return WHOLEMEMORY_INVALID_INPUT;
+  }
+  if (td.dim == 1 && !wholememory_unsqueeze_tensor(&td, 1)) return WHOLEMEMORY_LOGIC_ERROR;
+  wholememory_matrix_description_t table_desc;
+  if (!wholememory_convert_tensor_desc_to_matrix(&table_desc, &td)) return WHOLEMEMORY_LOGIC_ERROR;
+  wholememory_tensor_description_t* id = wholememory_tensor_get_tensor_description(indices_tensor);
+  if (id->dim != 1) {
+    log_msg(LEVEL_ERROR, "indices tensor should be 1D tensor");
+    return WHOLEMEMORY_INVALID_INPUT;
+  }
+  if (id->dtype != WHOLEMEMORY_DT_INT && id->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
+  wholememory_tensor_description_t dd = *wholememory_tensor_get_tensor_description(dense_tensor);
+  if (dd.dim != wholememory_tensor_get_tensor_description(wm_tensor)->dim) {
+    log_msg(LEVEL_ERROR, "%s tensor should be same dim as wholememory_tensor.", scatter ? "input" : "output");
+    return WHOLEMEMORY_INVALID_INPUT;
+  }
+  if (dd.dim == 1 && !wholememory_unsqueeze_tensor(&dd, 1)) return WHOLEMEMORY_LOGIC_ERROR;
+  wholememory_matrix_description_t dense_desc;
+  if (!wholememory_convert_tensor_desc_to_matrix(&dense_desc, &dd)) return WHOLEMEMORY_INVALID_INPUT;
+  wholememory_array_description_t idx_desc;
+  if (!wholememory_convert_tensor_desc_to_array(&idx_desc, id)) return WHOLEMEMORY_INVALID_INPUT;
+
+  return guarded(scatter ? "wholememory_scatter" : "wholememory_gather", [&] {
+    bool tf = wholememory_dtype_is_floating_number(table_desc.dtype);
+    bool df = wholememory_dtype_is_floating_number(dense_desc.dtype);
+    WGB_EXPECTS(tf || wholememory_dtype_is_integer_number(table_desc.dtype), "bad embedding dtype");
+    WGB_EXPECTS(df || wholememory_dtype_is_integer_number(dense_desc.dtype), "bad output dtype");
+    WGB_EXPECTS(tf == df, "embedding and output should be same number type, e.g. floating number or integer number.");
+    WGB_EXPECTS(dense_desc.sizes[1] == table_desc.sizes[1], "embedding dim of table and output differ");
+    WGB_EXPECTS(dense_desc.sizes[0] >= idx_desc.size, "output has fewer rows than indices");
+    if (idx_desc.size == 0 || table_desc.sizes[1] == 0) return;
+    wholememory_tensor_t dense_root = wholememory_tensor_get_root(dense_tensor);
+    WGB_EXPECTS(!dense_root->is_wholememory, "indices/output must not be WholeMemory tensors");
+    wholememory_tensor_t idx_root = wholememory_tensor_get_root(indices_tensor);
+    WGB_EXPECTS(!idx_root->is_wholememory, "indices must not be a WholeMemory tensor");
+    RowsOpArgs a;
+    a.table      = make_chunk_ref(wm_tensor);
+    a.table_desc = table_desc;
+    a.idx        = static_cast<const char*>(idx_root->storage_ptr) + idx_desc.storage_offset * dtype_size(idx_desc.dtype);
+    a.idx_dtype  = idx_desc.dtype;
+    a.n          = idx_desc.size;
+    a.dense      = dense_root->storage_ptr;
+    a.dense_desc = dense_desc;
+    a.scatter    = scatter;
+    a.sms        = sms;
+    a.stream     = as_stream(stream);
+    if (idx_desc.dtype == WHOLEMEMORY_DT_INT) {
+      if (scatter) run_rows_op_typed<int32_t, true>(a);
+      else run_rows_op_typed<int32_t, false>(a);
+    } else {
+      if (scatter) run_rows_op_typed<int64_t, true>(a);
+      else run_rows_op_typed<int64_t, false>(a);
+    }
+  });
+}
+
+}  // namespace wgb
+
+extern "C" {
+
+wholememory_error_code_t wholememory_gather(wholememory_tensor_t wholememory_tensor,
+                                            wholememory_tensor_t indices_tensor,
+                                            wholememory_tensor_t output_tensor,
+                                            wholememory_env_func_t* /*p_env_fns*/, void* stream, int gather_sms)
+{
+  return wgb::rows_op(wholememory_tensor, indices_tensor, output_tensor, stream, gather_sms, false);
+}
+
+wholememory_error_code_t wholememory_scatter(wholememory_tensor_t input_tensor, wholememory_tensor_t indices_tensor,
+                                             wholememory_tensor_t wholememory_tensor,
+                                             wholememory_env_func_t* /*p_env_fns*/, void* stream, int scatter_sms)
+{
+  return wgb::rows_op(wholememory_tensor, indices_tensor, input_tensor, stream, scatter_sms, true);
+}
+
+}  // extern "C"

@@ -1,0 +1,248 @@
+"""TEST INFRASTRUCTURE ONLY: numpy/ctypes front-end of the CPU oracle (oracle/wg_oracle.cpp).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs may import this module; the product package (``cugraph-gnn_b200/``) never does.
+Every function is a thin typed wrapper; the algorithm and its reference citations live in
+``wg_oracle.cpp``.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+DT_FLOAT, DT_HALF, DT_DOUBLE, DT_BF16, DT_INT, DT_INT64, DT_INT16, DT_INT8 = range(1, 9)
+
+_NP2DT = {
+    np.dtype(np.float32): DT_FLOAT,
+    np.dtype(np.float16): DT_HALF,
+    np.dtype(np.float64): DT_DOUBLE,
+    np.dtype(np.int32): DT_INT,
+    np.dtype(np.int64): DT_INT64,
+    np.dtype(np.int16): DT_INT16,
+    np.dtype(np.int8): DT_INT8,
+}
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libwg_oracle.so")
+    src = os.path.join(_HERE, "wg_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.wgo_multihop_sample.restype = ctypes.c_void_p
+        _LIB.wgo_multihop_num_edges.restype = ctypes.c_int64
+        _LIB.wgo_multihop_num_nodes.restype = ctypes.c_int64
+        _LIB.wgo_hop_seed.restype = ctypes.c_uint64
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _dt(a, bf16=False):
+    if bf16:
+        return DT_BF16
+    return _NP2DT[a.dtype]
+
+
+def num_threads():
+    return int(lib().wgo_num_threads())
+
+
+def pcg32_reference_stream(initstate, initseq, n):
+    out = np.empty(n, dtype=np.uint32)
+    lib().wgo_pcg32_reference_stream(ctypes.c_uint64(initstate), ctypes.c_uint64(initseq), _p(out), ctypes.c_int(n))
+    return out
+
+
+def generate_random_positive_int(seed, subsequence, n, dtype=np.int32):
+    out = np.empty(n, dtype=dtype)
+    fn = lib().wgo_generate_random_positive_int if dtype == np.int32 else lib().wgo_generate_random_positive_int64
+    fn(ctypes.c_int64(seed), ctypes.c_int64(subsequence), _p(out), ctypes.c_int64(n))
+    return out
+
+
+def generate_exponential_distribution_negative_float(seed, subsequence, n):
+    out = np.empty(n, dtype=np.float32)
+    lib().wgo_generate_exponential_distribution_negative_float(
+        ctypes.c_int64(seed), ctypes.c_int64(subsequence), _p(out), ctypes.c_int64(n)
+    )
+    return out
+
+
+def sample_offsets(row_ptr, centers, max_sample_count):
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    centers = np.ascontiguousarray(centers)
+    n = centers.shape[0]
+    off = np.empty(n + 1, dtype=np.int32)
+    lib().wgo_sample_offsets(_p(row_ptr), _p(centers), _dt(centers), ctypes.c_int64(n), ctypes.c_int(max_sample_count), _p(off))
+    return off
+
+
+def unweighted_sample(row_ptr, col, centers, max_sample_count, seed):
+    """Returns (sample_offset int32[n+1], dest col-dtype[total], center_localid int32[total], edge_gid int64[total])."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col)
+    centers = np.ascontiguousarray(centers)
+    n = centers.shape[0]
+    off = sample_offsets(row_ptr, centers, max_sample_count)
+    total = int(off[n])
+    dest = np.empty(total, dtype=col.dtype)
+    lid = np.empty(total, dtype=np.int32)
+    gid = np.empty(total, dtype=np.int64)
+    rc = lib().wgo_unweighted_sample(
+        _p(row_ptr), _p(col), _dt(col), _p(centers), _dt(centers), ctypes.c_int64(n),
+        ctypes.c_int(max_sample_count), ctypes.c_uint64(seed), _p(off), _p(dest), _p(lid), _p(gid),
+    )
+    if rc != 0:
+        raise ValueError("oracle: unsupported max_sample_count")
+    return off, dest, lid, gid
+
+
+def weighted_sample(row_ptr, col, weights, centers, max_sample_count, seed, return_keys=False):
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col)
+    weights = np.ascontiguousarray(weights)
+    centers = np.ascontiguousarray(centers)
+    n = centers.shape[0]
+    off = sample_offsets(row_ptr, centers, max_sample_count)
+    total = int(off[n])
+    dest = np.empty(total, dtype=col.dtype)
+    lid = np.empty(total, dtype=np.int32)
+    gid = np.empty(total, dtype=np.int64)
+    keys = np.empty(total, dtype=np.float32)
+    rc = lib().wgo_weighted_sample(
+        _p(row_ptr), _p(col), _dt(col), _p(weights), _dt(weights), _p(centers), _dt(centers), ctypes.c_int64(n),
+        ctypes.c_int(max_sample_count), ctypes.c_uint64(seed), _p(off), _p(dest), _p(lid), _p(gid), _p(keys),
+    )
+    if rc != 0:
+        raise ValueError("oracle: unsupported max_sample_count")
+    if return_keys:
+        return off, dest, lid, gid, keys
+    return off, dest, lid, gid
+
+
+def weighted_row_keys(row_ptr, weights, v, b, max_sample_count, seed):
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    weights = np.ascontiguousarray(weights)
+    deg = int(row_ptr[v + 1] - row_ptr[v])
+    keys = np.empty(deg, dtype=np.float32)
+    lib().wgo_weighted_row_keys(_p(row_ptr), _p(weights), _dt(weights), ctypes.c_int64(v), ctypes.c_int64(b),
+                                ctypes.c_int(max_sample_count), ctypes.c_uint64(seed), _p(keys))
+    return keys
+
+
+def append_unique(targets, neighbors):
+    targets = np.ascontiguousarray(targets)
+    neighbors = np.ascontiguousarray(neighbors, dtype=targets.dtype)
+    T, N = targets.shape[0], neighbors.shape[0]
+    uniq = np.empty(T + N, dtype=targets.dtype)
+    cnt = np.zeros(1, dtype=np.int32)
+    r2u = np.empty(N, dtype=np.int32)
+    lib().wgo_append_unique(_p(targets), ctypes.c_int64(T), _p(neighbors), ctypes.c_int64(N), _dt(targets), _p(uniq), _p(cnt), _p(r2u))
+    return uniq[: int(cnt[0])].copy(), r2u
+
+
+def gather(table, indices, out_dtype=None, dim=None, stride=None, storage_offset=0, table_bf16=False, out_bf16=False,
+           out=None, out_stride=None):
+    """table: 2-D (or flat with explicit dim/stride) numpy array; bf16 tables are passed as uint16 + table_bf16."""
+    indices = np.ascontiguousarray(indices)
+    n = indices.shape[0]
+    if dim is None:
+        dim = table.shape[1] if table.ndim == 2 else 1
+    if stride is None:
+        stride = table.shape[1] if table.ndim == 2 else 1
+    table = np.ascontiguousarray(table)
+    tdt = DT_BF16 if table_bf16 else _dt(table)
+    if out is None:
+        odt_np = np.dtype(out_dtype) if out_dtype is not None else table.dtype
+        if out_bf16:
+            odt_np = np.dtype(np.uint16)
+        out_stride = dim if out_stride is None else out_stride
+        out = np.zeros((n, out_stride), dtype=odt_np)
+    else:
+        out_stride = out.shape[1] if out_stride is None else out_stride
+    odt = DT_BF16 if out_bf16 else _dt(out)
+    rc = lib().wgo_gather(_p(table), tdt, ctypes.c_int64(dim), ctypes.c_int64(stride), ctypes.c_int64(storage_offset),
+                          _p(indices), _dt(indices), ctypes.c_int64(n), _p(out), odt, ctypes.c_int64(out_stride), ctypes.c_int64(0))
+    if rc != 0:
+        raise ValueError("oracle: embedding and output must both be floating or both integer")
+    return out
+
+
+def scatter(inp, indices, table, dim=None, stride=None, storage_offset=0, in_bf16=False, table_bf16=False):
+    indices = np.ascontiguousarray(indices)
+    inp = np.ascontiguousarray(inp)
+    n = indices.shape[0]
+    if dim is None:
+        dim = inp.shape[1] if inp.ndim == 2 else 1
+    if stride is None:
+        stride = table.shape[1] if table.ndim == 2 else 1
+    in_stride = inp.shape[1] if inp.ndim == 2 else 1
+    idt = DT_BF16 if in_bf16 else _dt(inp)
+    tdt = DT_BF16 if table_bf16 else _dt(table)
+    rc = lib().wgo_scatter(_p(inp), idt, ctypes.c_int64(dim), ctypes.c_int64(in_stride), ctypes.c_int64(0), _p(indices), _dt(indices),
+                           ctypes.c_int64(n), _p(table), tdt, ctypes.c_int64(stride), ctypes.c_int64(storage_offset))
+    if rc != 0:
+        raise ValueError("oracle: dtype class mismatch")
+    return table
+
+
+def csr_aggregate(indptr, indices, x, mean=True):
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n_dst = indptr.shape[0] - 1
+    dim = x.shape[1]
+    out = np.empty((n_dst, dim), dtype=np.float64)
+    lib().wgo_csr_aggregate(_p(indptr), _p(indices), ctypes.c_int64(n_dst), _p(x), ctypes.c_int64(dim), ctypes.c_int64(dim), ctypes.c_int(1 if mean else 0), _p(out))
+    return out
+
+
+def hop_seed(random_state, hop):
+    return int(lib().wgo_hop_seed(ctypes.c_uint64(random_state), ctypes.c_int(hop)))
+
+
+def multihop_sample(row_ptr, col, seeds, label_offsets, fanout, random_state, weights=None, edge_ids=None):
+    """pylibcugraph-shaped multi-hop sample (COO). Returns a dict of numpy arrays."""
+    row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    col = np.ascontiguousarray(col)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    label_offsets = np.ascontiguousarray(label_offsets, dtype=np.int64)
+    fanout = np.ascontiguousarray(fanout, dtype=np.int32)
+    if weights is not None:
+        weights = np.ascontiguousarray(weights)
+    if edge_ids is not None:
+        edge_ids = np.ascontiguousarray(edge_ids, dtype=np.int64)
+    B = label_offsets.shape[0] - 1
+    L = fanout.shape[0]
+    h = lib().wgo_multihop_sample(
+        _p(row_ptr), _p(col), _dt(col), _p(weights), (_dt(weights) if weights is not None else 0), _p(edge_ids),
+        _p(seeds), _p(label_offsets), ctypes.c_int64(B), _p(fanout), ctypes.c_int(L), ctypes.c_uint64(random_state),
+    )
+    h = ctypes.c_void_p(h)
+    ne = int(lib().wgo_multihop_num_edges(h))
+    nn = int(lib().wgo_multihop_num_nodes(h))
+    out = {
+        "majors": np.empty(ne, dtype=np.int32),
+        "minors": np.empty(ne, dtype=np.int32),
+        "edge_id": np.empty(ne, dtype=np.int64),
+        "label_hop_offsets": np.empty(B * L + 1, dtype=np.int64),
+        "renumber_map": np.empty(nn, dtype=np.int64),
+        "renumber_map_offsets": np.empty(B + 1, dtype=np.int64),
+    }
+    lib().wgo_multihop_copy(h, _p(out["majors"]), _p(out["minors"]), _p(out["edge_id"]), _p(out["label_hop_offsets"]),
+                            _p(out["renumber_map"]), _p(out["renumber_map_offsets"]))
+    lib().wgo_multihop_free(h)
+    return out

@@ -1,0 +1,319 @@
+"""CPU tests of the oracle: known-answer vectors, the reference's pinned expectations, and an
+independent pure-Python restatement of the sampler for cross-checking the C++ one."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from graphs import karate_csr, random_csr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PINS = json.load(open(os.path.join(HERE, "golden", "reference_pins.json")))
+
+MASK64 = (1 << 64) - 1
+MULT = 6364136223846793005
+
+
+class PyPcg:
+    """Line-by-line python twin of the PCG restatement (oracle/wg_oracle.cpp)."""
+
+    def __init__(self, seed, subsequence, offset):
+        self.state = 0
+        self.inc = ((subsequence << 1) | 1) & MASK64
+        self.next_u32()
+        self.state = (self.state + seed) & MASK64
+        self.next_u32()
+        # skip-ahead, Brown's algorithm
+        G, h, C, f = 1, MULT, 0, self.inc
+        while offset:
+            if offset & 1:
+                G = (G * h) & MASK64
+                C = (C * h + f) & MASK64
+            f = (f * (h + 1)) & MASK64
+            h = (h * h) & MASK64
+            offset >>= 1
+        self.state = (self.state * G + C) & MASK64
+
+    def next_u32(self):
+        old = self.state
+        self.state = (old * MULT + self.inc) & MASK64
+        xs = (((old >> 18) ^ old) >> 27) & 0xFFFFFFFF
+        rot = old >> 59
+        return ((xs >> rot) | (xs << ((-rot) & 31))) & 0xFFFFFFFF
+
+    def next_i32(self):
+        return self.next_u32() & 0x7FFFFFFF
+
+
+def py_uniform_sample(row_ptr, col, centers, M, seed):
+    """cpp/tests/wholegraph_ops/graph_sampling_test_utils.cu:312-401, in plain python."""
+    tabs = PINS["sampler_launch_tables"]
+    out_dest, out_lid, out_gid, offs = [], [], [], [0]
+    for b, v in enumerate(centers):
+        start, end = int(row_ptr[v]), int(row_ptr[v + 1])
+        N = end - start
+        if N <= 0:
+            picks = []
+        elif M <= 0 or N <= M:
+            picks = list(range(N))
+        else:
+            T = tabs["warp_count"][(M - 1) // 32] * 32
+            ipt = tabs["items_per_thread"][(M - 1) // 32]
+            r = [N] * (T * ipt)
+            for j in range(T):
+                g = PyPcg(seed, b * T + j, b * T + j)
+                for k in range(ipt):
+                    idx = k * T + j
+                    x = g.next_i32()
+                    r[idx] = x % (N - idx) if idx < M else N
+            Q = list(range(N))
+            picks = []
+            for i in range(M):
+                picks.append(Q[r[i]])
+                Q[r[i]] = Q[N - i - 1]
+        for a in picks:
+            out_dest.append(int(col[start + a]))
+            out_lid.append(b)
+            out_gid.append(start + a)
+        offs.append(len(out_dest))
+    return np.array(offs), np.array(out_dest), np.array(out_lid), np.array(out_gid)
+
+
+def test_pcg32_matches_published_vector(oracle):
+    kat = PINS["pcg32_published_kat"]
+    got = oracle.pcg32_reference_stream(kat["initstate"], kat["initseq"], len(kat["outputs_hex"]))
+    assert ["%08x" % x for x in got] == kat["outputs_hex"]
+    g = PyPcg(kat["initstate"], kat["initseq"], 0)
+    assert ["%08x" % g.next_u32() for _ in kat["outputs_hex"]] == kat["outputs_hex"]
+
+
+@pytest.mark.parametrize("subseq", [0, 1, 31, 32, 1000, 123456789])
+def test_raft_stream_twin(oracle, subseq):
+    got = oracle.generate_random_positive_int(62, subseq, 5)
+    g = PyPcg(62, subseq, subseq)
+    assert got.tolist() == [g.next_i32() for _ in range(5)]
+    assert (got >= 0).all()
+
+
+def test_exponential_keys_are_negative_log2_uniform(oracle):
+    keys = oracle.generate_exponential_distribution_negative_float(7, 3, 4096)
+    assert (keys <= 0).all() and np.isfinite(keys).all()
+    # -log2(U) has mean 1/ln2
+    assert abs(-keys.mean() - 1.0 / np.log(2.0)) < 0.08
+
+
+@pytest.mark.parametrize("M", [5, 1, 32, 33, 50, 100, 300])
+def test_uniform_sampler_karate_two_restatements_agree(oracle, M):
+    """C1: karate, 1 hop -- C++ oracle == python restatement, bit exact and in order."""
+    row_ptr, col = karate_csr()
+    centers = np.arange(34, dtype=np.int64)
+    off, dest, lid, gid = oracle.unweighted_sample(row_ptr, col, centers, M, 62)
+    poff, pdest, plid, pgid = py_uniform_sample(row_ptr, col, centers, M, 62)
+    assert off.tolist() == poff.tolist()
+    assert dest.tolist() == pdest.tolist()
+    assert lid.tolist() == plid.tolist()
+    assert gid.tolist() == pgid.tolist()
+
+
+def test_uniform_sampler_properties(oracle):
+    row_ptr, col = random_csr(2000, 60000, seed=1)
+    centers = np.random.default_rng(0).integers(0, 2000, 700)
+    for M in (10, 25, 64):
+        off, dest, lid, gid = oracle.unweighted_sample(row_ptr, col, centers, M, 1234)
+        deg = row_ptr[centers + 1] - row_ptr[centers]
+        assert (np.diff(off) == np.minimum(deg, M)).all()
+        assert (col[gid] == dest).all()
+        for b in range(len(centers)):
+            g = gid[off[b]:off[b + 1]]
+            assert len(set(g.tolist())) == len(g)  # without replacement
+            assert ((g >= row_ptr[centers[b]]) & (g < row_ptr[centers[b] + 1])).all()
+            assert (lid[off[b]:off[b + 1]] == b).all()
+
+
+def test_sample_all_is_csr_order(oracle):
+    row_ptr, col = karate_csr(np.int64)
+    centers = np.array([0, 33, 11, 0], dtype=np.int32)
+    off, dest, lid, gid = oracle.unweighted_sample(row_ptr, col, centers, -1, 0)
+    exp = np.concatenate([np.arange(row_ptr[c], row_ptr[c + 1]) for c in centers])
+    assert gid.tolist() == exp.tolist()
+    assert dest.tolist() == col[exp].tolist()
+
+
+def test_weighted_sampler_zero_weight_never_sampled(oracle):
+    """biased sampling pin: an edge of weight 0 is never chosen while enough positive ones exist
+    (python/cugraph-pyg/cugraph_pyg/tests/loader/test_neighbor_loader.py:99-133)."""
+    row_ptr, col = random_csr(300, 9000, seed=5)
+    rng = np.random.default_rng(3)
+    w = rng.uniform(1.0, 20.0, 9000).astype(np.float32)
+    zero = rng.random(9000) < 0.3
+    w[zero] = 0.0
+    centers = np.arange(300)
+    off, dest, lid, gid = oracle.weighted_sample(row_ptr, col, w, centers, 4, 99)
+    for b in range(300):
+        s, e = row_ptr[b], row_ptr[b + 1]
+        pos = int((w[s:e] > 0).sum())
+        if e - s > 4 and pos >= 4:
+            assert (w[gid[off[b]:off[b + 1]]] > 0).all()
+
+
+def test_weighted_sampler_is_top_m_of_keys(oracle):
+    row_ptr, col = random_csr(200, 8000, seed=8)
+    w = np.random.default_rng(1).uniform(1, 20, 8000)
+    centers = np.array([3, 50, 50, 199, 7])
+    M = 10
+    off, dest, lid, gid, keys = oracle.weighted_sample(row_ptr, col, w, centers, M, 5, return_keys=True)
+    for b, v in enumerate(centers):
+        deg = int(row_ptr[v + 1] - row_ptr[v])
+        if deg <= M:
+            continue
+        allk = oracle.weighted_row_keys(row_ptr, w, int(v), b, M, 5)
+        top = np.sort(np.argsort(-allk, kind="stable")[:M] + row_ptr[v])
+        assert np.sort(gid[off[b]:off[b + 1]]).tolist() == top.tolist()
+
+
+def test_append_unique_reference_example(oracle):
+    pin = PINS["append_unique_docstring_example"]
+    t = np.array(pin["targets"], dtype=np.int64)
+    n = np.array(pin["neighbors"], dtype=np.int64)
+    uniq, r2u = oracle.append_unique(t, n)
+    assert uniq[: len(t)].tolist() == pin["unique_prefix"]
+    assert sorted(uniq[len(t):].tolist()) == pin["unique_tail_sorted"]
+    assert (uniq[r2u] == n).all()
+    # first-occurrence order
+    assert uniq[len(t):].tolist() == [4, 5, 6, 9]
+
+
+@pytest.mark.parametrize("T,N,dtype", [(3, 10, np.int32), (53, 123, np.int32), (57, 1235, np.int64), (0, 17, np.int64), (9, 0, np.int32)])
+def test_append_unique_matrix(oracle, T, N, dtype):
+    """sizes from cpp/tests/graph_ops/append_unique_tests.cu:219-231 (+ empty edge cases)."""
+    rng = np.random.default_rng(T * 1000 + N)
+    t = rng.permutation(4 * (T + N) + 8)[:T].astype(dtype)
+    n = rng.integers(0, 2 * (T + N) + 8, N).astype(dtype)
+    uniq, r2u = oracle.append_unique(t, n)
+    assert uniq[:T].tolist() == t.tolist()
+    assert len(set(uniq.tolist())) == len(uniq)
+    assert set(uniq.tolist()) == set(t.tolist()) | set(n.tolist())
+    if N:
+        assert (uniq[r2u] == n).all()
+
+
+def test_gather_closed_form(oracle):
+    """table[i][d] = i + d  (test_wholegraph_gather_scatter.py:16-31)."""
+    rows, dim = 1000, 33
+    table = (np.arange(rows)[:, None] + np.arange(dim)[None, :]).astype(np.float32)
+    idx = np.random.default_rng(0).integers(0, rows, 257).astype(np.int64)
+    out = oracle.gather(table, idx)
+    assert (out == idx[:, None] + np.arange(dim)[None, :]).all()
+    out16 = oracle.gather(table, idx, out_dtype=np.float16)
+    assert (out16 == (idx[:, None] + np.arange(dim)[None, :]).astype(np.float16)).all()
+    # negative indices leave the output row untouched
+    idx2 = idx.copy()
+    idx2[::3] = -1
+    out2 = oracle.gather(table, idx2)
+    assert (out2[::3] == 0).all()
+
+
+def test_half_conversion_matches_numpy(oracle):
+    x = np.random.default_rng(0).standard_normal(20000).astype(np.float32) * np.float32(300.0)
+    x = np.concatenate([x, np.array([0.0, -0.0, 65504.0, 65519.9, 65520.0, 1e-8, 6e-8, 5.96e-8, 2.98e-8, 1e-5, np.inf, -np.inf], dtype=np.float32)])
+    table = x.reshape(-1, 1)
+    out = oracle.gather(table, np.arange(len(x)), out_dtype=np.float16)
+    assert (out.view(np.uint16).ravel() == x.astype(np.float16).view(np.uint16)).all()
+    back = oracle.gather(out, np.arange(len(x)), out_dtype=np.float32)
+    assert (back.ravel().view(np.uint32) == x.astype(np.float16).astype(np.float32).view(np.uint32)).all()
+
+
+def test_scatter_then_gather_roundtrip(oracle):
+    table = np.zeros((500, 16), dtype=np.float32)
+    idx = np.random.default_rng(1).permutation(500)[:200].astype(np.int32)
+    rows = np.random.default_rng(2).standard_normal((200, 16)).astype(np.float32)
+    oracle.scatter(rows, idx, table)
+    assert (oracle.gather(table, idx) == rows).all()
+
+
+def test_csr_aggregate_against_numpy(oracle):
+    rng = np.random.default_rng(0)
+    n_dst, n_src, dim = 50, 80, 12
+    deg = rng.integers(0, 7, n_dst)
+    indptr = np.concatenate([[0], np.cumsum(deg)])
+    indices = rng.integers(0, n_src, indptr[-1])
+    x = rng.standard_normal((n_src, dim)).astype(np.float32)
+    for mean in (True, False):
+        got = oracle.csr_aggregate(indptr, indices, x, mean=mean)
+        for i in range(n_dst):
+            rows = x[indices[indptr[i]:indptr[i + 1]]].astype(np.float64)
+            exp = rows.sum(0) if rows.size else np.zeros(dim)
+            if mean and rows.shape[0]:
+                exp = exp / rows.shape[0]
+            assert np.allclose(got[i], exp, rtol=1e-12, atol=1e-12)
+
+
+def _check_multihop_structure(res, row_ptr, col, seeds, label_offsets, fanout):
+    B, L = len(label_offsets) - 1, len(fanout)
+    lho, rmo = res["label_hop_offsets"], res["renumber_map_offsets"]
+    assert lho[0] == 0 and lho[-1] == len(res["majors"])
+    for l in range(B):
+        m = res["renumber_map"][rmo[l]:rmo[l + 1]]
+        s = seeds[label_offsets[l]:label_offsets[l + 1]]
+        assert m[: len(s)].tolist() == list(s)  # retain_seeds: seeds first, in order
+        assert len(set(m.tolist())) == len(m)
+        seen_sources = 0
+        prev_nodes = len(s)
+        for h in range(L):
+            a, b = lho[l * L + h], lho[l * L + h + 1]
+            mj, mn, eid = res["majors"][a:b], res["minors"][a:b], res["edge_id"][a:b]
+            # every edge exists in the graph: edge_id is the CSR position
+            assert (m[mn] == col[eid]).all()
+            src = m[mj]
+            assert ((eid >= row_ptr[src]) & (eid < row_ptr[src + 1])).all()
+            if len(mj):
+                # hop-monotone renumbering (sampler.py:570-575, 676-687)
+                assert mj.min() >= seen_sources and mj.max() < prev_nodes
+                assert (np.diff(mj) >= 0).all()
+            seen_sources = prev_nodes
+            if len(mn):
+                prev_nodes = max(prev_nodes, int(mn.max()) + 1)
+        assert prev_nodes == len(m)
+
+
+def test_multihop_structure_and_fanout_all(oracle):
+    row_ptr, col = random_csr(500, 6000, seed=11, col_dtype=np.int64)
+    rng = np.random.default_rng(4)
+    seeds = np.concatenate([rng.permutation(500)[:7], rng.permutation(500)[:5], rng.permutation(500)[:9]])
+    lo = np.array([0, 7, 12, 21])
+    for fanout in ([3, 2], [-1, 2], [4, 0, 3], [25, 10]):
+        res = oracle.multihop_sample(row_ptr, col, seeds, lo, fanout, 62)
+        _check_multihop_structure(res, row_ptr, col, seeds, lo, fanout)
+    # fanout -1 is fully deterministic: hop 0 edges are exactly the adjacency of the seeds
+    res = oracle.multihop_sample(row_ptr, col, seeds, lo, [-1], 1)
+    for l in range(3):
+        s = seeds[lo[l]:lo[l + 1]]
+        a, b = res["label_hop_offsets"][l], res["label_hop_offsets"][l + 1]
+        exp = np.concatenate([np.arange(row_ptr[v], row_ptr[v + 1]) for v in s])
+        assert res["edge_id"][a:b].tolist() == exp.tolist()
+
+
+def test_multihop_reference_hetero_pin_homogeneous_projection(oracle):
+    """The reference's only fully deterministic multi-hop expectation
+    (test_distributed_sampler.py:19-150, fanout -1): projected on each edge type separately it pins
+    hop sizes, edge ids and endpoints of a 2-hop take-all expansion from seeds [4, 5]."""
+    pin = PINS["hetero_fanout_all"]
+    srcs, dsts, eids, etps = (np.array(pin[k]) for k in ("srcs", "dsts", "eids", "etps"))
+    # build one CSR by source over both edge types (take-all sampling follows out-edges of src)
+    order = np.lexsort((np.arange(len(srcs)), srcs))
+    row_ptr = np.zeros(11, dtype=np.int64)
+    np.cumsum(np.bincount(srcs, minlength=10), out=row_ptr[1:])
+    col = dsts[order].astype(np.int64)
+    res = oracle.multihop_sample(row_ptr, col, np.array(pin["seeds"]), np.array([0, 2]), [-1, -1], 0)
+    m = res["renumber_map"]
+    lho = res["label_hop_offsets"]
+    for hop in (0, 1):
+        a, b = lho[hop], lho[hop + 1]
+        pos = order[res["edge_id"][a:b]]
+        for et in (0, 1):
+            sel = etps[pos] == et
+            exp = pin["expect"]["etype%d_hop%d" % (et, hop)]
+            assert sorted(eids[pos][sel].tolist()) == exp["eids"]
+            assert sorted(m[res["majors"][a:b]][sel].tolist()) == exp["srcs"]
+            assert sorted(m[res["minors"][a:b]][sel].tolist()) == exp["dsts"]
