@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Hot-path benchmark: multi-hop neighbour sampling + renumbering -> feature gather.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the CPU implementation of the same path)
+
+Workload (BASELINE.json configs[1], "C2"): synthetic RMAT |V| = 10 M, |E| = 160 M (a,b,c,d = .57,.19,.19,.05,
+seed 42), CSR by destination, int64 row_ptr / int32 col_idx; features fp32 [|V|, 128] with the closed form
+table[i][d] = (i + d) & 0xFFFF; fan-out [25, 10]; sampler seed 62.
+
+One step = one call group of 64 mini-batches ("labels") x 1024 seeds per GPU, i.e. what
+cugraph_pyg.sampler.DistributedNeighborSampler hands to the native sampler in one call
+(python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:877-908) followed by the feature fetch of
+every mini-batch (sampler/sampler.py:51-165 -> FeatureStore -> WholeMemoryEmbedding.gather):
+    1. fused multi-hop sampler: per label, hop 1 samples 25 neighbours of the seeds, hop 2 samples 10 neighbours
+       of the vertices new in hop 1; per-label renumbering (seeds first, first-occurrence order); COO output
+    2. gather the feature row of every vertex of every sampled sub-graph (the concatenated renumber maps).
+Every step uses a different seed set; the feature table (5.1 GB) and the bytes gathered per step exceed L2.
+
+metric = sampled edges / s for the whole step (sampling + renumbering + feature gather), whole job over all GPUs.
+Extra keys: gather_gbs (reference definition: gathered output bytes / gather time,
+cpp/bench/wholememory_ops/gather_scatter_bench.cu:352-355), stages (per-stage device times), roofline
+(dominant kernel = the gather), cpu_baseline (the oracle on the host cores, bounded sample).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cugraph-gnn_b200"))
+
+NUM_NODES = 10_000_000
+NUM_EDGES = 160_000_000
+FEAT_DIM = 128
+FANOUT = [25, 10]
+BATCH = 1024
+LABELS_PER_STEP = 64
+SAMPLER_SEED = 62
+RMAT = (0.57, 0.19, 0.19, 0.05)
+WORKLOAD = "C2 synthetic RMAT |V|=10M |E|=160M fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"
+METRIC = "sampled_edges_per_sec (multi-hop sample + renumber + feature gather, fanout [25,10])"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def rmat_csr(torch, num_nodes, num_edges, seed, device):
+    """RMAT edge list generated on `device`, folded into [0, num_nodes), returned as CSR by destination."""
+    scale = max(1, (num_nodes - 1).bit_length())
+    a, b, c, d = RMAT
+    g = torch.Generator(device=device).manual_seed(seed)
+    chunk = 1 << 24
+    keys = torch.empty(num_edges, dtype=torch.int64, device=device)
+    for lo in range(0, num_edges, chunk):
+        n = min(chunk, num_edges - lo)
+        src = torch.zeros(n, dtype=torch.int64, device=device)
+        dst = torch.zeros(n, dtype=torch.int64, device=device)
+        for _ in range(scale):
+            r = torch.rand(n, device=device, generator=g)
+            src_bit = (r >= a + b).to(torch.int64)  # quadrants c, d
+            dst_bit = (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)  # quadrants b, d
+            src = (src << 1) | src_bit
+            dst = (dst << 1) | dst_bit
+        src %= num_nodes
+        dst %= num_nodes
+        keys[lo:lo + n] = (dst << 32) | src
+        del src, dst
+    keys, _ = torch.sort(keys)
+    rows = keys >> 32
+    col = (keys & 0xFFFFFFFF).to(torch.int32)
+    del keys
+    row_ptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=device)
+    row_ptr[1:] = torch.bincount(rows, minlength=num_nodes).cumsum(0)
+    return row_ptr, col
+
+
+def seed_sets(torch, num_sets, labels, rank=0):
+    """num_sets call groups of `labels` mini-batches of BATCH distinct seeds (int64, like NodeLoader's randperm)."""
+    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    out = []
+    for _ in range(num_sets):
+        out.append(torch.randperm(NUM_NODES, generator=g)[: labels * BATCH].contiguous())
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+            time.sleep(0.3)
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.1)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+
+        def num(x):
+            try:
+                return float(x)
+            except Exception:
+                return None
+
+        sm = sorted(v for v in (num(r[0]) for r in self.rows if r) if v is not None)
+        mx = [v for v in (num(r[1]) for r in self.rows if len(r) > 1) if v is not None]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for k, nm in enumerate(names):
+                if len(r) > 4 + k and r[4 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import pylibwholegraph.binding.wholememory_binding as wmb
+    import pylibwholegraph.torch as wgth
+
+    wgth.init(rank, world, local_rank, world)
+    comm = wgth.get_global_communicator()
+    launch_count = wmb.native_symbol("wholememory_b200_kernel_launch_count")
+    launch_count.restype = ctypes.c_ulonglong
+
+    t0 = time.time()
+    row_ptr, col = rmat_csr(torch, NUM_NODES, NUM_EDGES, 42, dev)
+    torch.cuda.synchronize()
+    log("[rank %d] RMAT CSR built in %.1fs, |E|=%d, max degree %d" % (rank, time.time() - t0, col.numel(), int((row_ptr[1:] - row_ptr[:-1]).max())))
+
+    # graph: replicated per GPU (720 MB); features: striped over the GPUs of the box and read by P2P
+    one = wgth.create_group_communicator(1, 1) if world > 1 else comm
+    wm_rp = wgth.create_wholememory_tensor(one, "chunked", "cuda", [NUM_NODES + 1], torch.int64, [1])
+    wm_rp.get_local_tensor()[0].copy_(row_ptr)
+    wm_col = wgth.create_wholememory_tensor(one, "chunked", "cuda", [col.numel()], torch.int32, [1])
+    wm_col.get_local_tensor()[0].copy_(col)
+    del col
+    emb = wgth.create_embedding(comm, "chunked", "cuda", torch.float32, [NUM_NODES, FEAT_DIM])
+    local, start = emb.get_embedding_tensor().get_local_tensor()
+    ar = torch.arange(FEAT_DIM, device=dev)[None, :]
+    for lo in range(0, local.shape[0], 1 << 20):
+        hi = min(local.shape[0], lo + (1 << 20))
+        local[lo:hi] = ((torch.arange(start + lo, start + hi, device=dev)[:, None] + ar) & 0xFFFF).float()
+    comm.barrier()
+    sampler = wgth.MultiHopSampler()
+    labels = args.labels
+    label_offsets = (torch.arange(labels + 1, dtype=torch.int64) * BATCH).to(dev)
+
+    n_sets = args.steps + args.warmup
+    host_seeds = [s.pin_memory() for s in seed_sets(torch, n_sets, labels, rank)]
+
+    def step(seeds_dev, seed, ev=None):
+        if ev:
+            ev[0].record()
+        res = sampler.sample(wm_rp, wm_col, seeds_dev, label_offsets, FANOUT, seed)
+        if ev:
+            ev[1].record()
+        x = emb.gather(res["renumber_map"])
+        if ev:
+            ev[2].record()
+        return int(res["minors"].numel()), int(res["renumber_map"].numel()), x, res
+
+    def e2e_step(k):
+        sd = host_seeds[k].to(dev, non_blocking=True)  # H2D of the step's input, from pinned memory
+        e, n, x, res = step(sd, SAMPLER_SEED + 7 * k)
+        # the step's result as the reference's loader reads it back: per-batch sizes + a checksum of the features
+        metric = torch.cat([res["label_hop_offsets"].double(), res["renumber_map_offsets"].double(), x.sum(dtype=torch.float64).reshape(1)])
+        host = metric.cpu()
+        return e, n, host.numel() * 8
+
+    dev_seeds = [s.to(dev) for s in host_seeds]
+    torch.cuda.synchronize()
+    for w in range(args.warmup):
+        step(dev_seeds[w], SAMPLER_SEED + 7 * w)
+        e2e_step(w)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+    # ---- device-resident timing: `value` -------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = int(launch_count())
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_begin.record()
+    tot_edges = tot_nodes = 0
+    for k in range(args.steps):
+        e, n, x, _ = step(dev_seeds[args.warmup + k], SAMPLER_SEED + 7 * (args.warmup + k), evs[k])
+        tot_edges += e
+        tot_nodes += n
+    t_end.record()
+    torch.cuda.synchronize()
+    launches = int(launch_count()) - launches0
+    ms_total = t_begin.elapsed_time(t_end)
+    sample_ms = sum(ev[0].elapsed_time(ev[1]) for ev in evs)
+    gather_ms = sum(ev[1].elapsed_time(ev[2]) for ev in evs)
+
+    # ---- end-to-end: pinned host seeds in, per-batch sizes + feature checksum out, every step -----------
+    if world > 1:
+        dist.barrier()
+    e_begin, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_edges = 0
+    d2h_bytes = 0
+    torch.cuda.synchronize()
+    e_begin.record()
+    for k in range(args.steps):
+        e, n, d2h_bytes = e2e_step(args.warmup + k)
+        e2e_edges += e
+    e_end.record()
+    torch.cuda.synchronize()
+    e2e_ms = e_begin.elapsed_time(e_end)
+    clock_info = clocks.stop() if rank == 0 else None
+
+    stats = torch.tensor([ms_total, e2e_ms, sample_ms, gather_ms], dtype=torch.float64, device=dev)
+    counts = torch.tensor([tot_edges, tot_nodes, e2e_edges], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms, sample_ms, gather_ms = stats.tolist()
+    tot_edges, tot_nodes, e2e_edges = counts.tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        row_bytes = FEAT_DIM * 4
+        rows_per_rank = tot_nodes / world
+        gather_alg_bytes = (2 * row_bytes + 8) * rows_per_rank  # per rank, all steps
+        gather_achieved = gather_alg_bytes / (gather_ms * 1e-3) / 1e9
+        # sampler algorithmic bytes (BASELINE.md §3, int32 ids out / int64 edge ids): per edge col 4 + minor 4 + major 4 + edge id 8,
+        # per frontier vertex id 8 + row_ptr 16
+        sample_alg_bytes = (20.0 * tot_edges + 24.0 * tot_nodes) / world
+        out = {
+            "metric": METRIC,
+            "value": tot_edges / (ms_total * 1e-3),
+            "unit": "edges/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "int64/int32 ids, fp32 features",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "labels_per_step_per_gpu": labels, "seeds_per_label": BATCH,
+                       "l2": "inputs larger than L2 (5.1 GB table, >1 GB gathered per step); new seed set every step",
+                       "graph": "replicated per GPU", "features": "chunked over %d GPU(s), in-kernel P2P gather" % world},
+            "gather_gbs": row_bytes * tot_nodes / (gather_ms * 1e-3) / 1e9,
+            "stages": {
+                "sample_renumber_ms_per_step": sample_ms / args.steps,
+                "gather_ms_per_step": gather_ms / args.steps,
+                "edges_per_step_per_gpu": tot_edges / args.steps / world,
+                "nodes_gathered_per_step_per_gpu": tot_nodes / args.steps / world,
+                "sample_stage_edges_per_sec_per_gpu": tot_edges / world / (sample_ms * 1e-3),
+                "sample_stage_alg_gbs": sample_alg_bytes / (sample_ms * 1e-3) / 1e9,
+            },
+            "roofline": {"kernel": "rows_copy_kernel (feature gather)", "bound": "hbm", "achieved": gather_achieved, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": gather_achieved / hbm_peak, "traffic": None, "peak_source": peak_src},
+            "e2e": {"value": e2e_edges / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": labels * BATCH * 8, "d2h_bytes_per_step": d2h_bytes,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": launches,
+            "clocks": clock_info,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(row_ptr.cpu().numpy(), wm_col.get_local_tensor()[0].cpu().numpy(), budget_s=15.0)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (a C++/OpenMP restatement of the reference's own host reference algorithms; the
+# reference's implementation cannot be compiled or installed here -- SURVEY.md §8c) on the host cores.
+# ----------------------------------------------------------------------------------------------------
+def cpu_baseline(row_ptr, col, budget_s=15.0, labels=4, steps=None):
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import wg_oracle as oracle
+
+    table = None
+    try:
+        table = np.empty((NUM_NODES, FEAT_DIM), dtype=np.float32)
+        for lo in range(0, NUM_NODES, 1 << 20):
+            hi = min(NUM_NODES, lo + (1 << 20))
+            table[lo:hi] = (np.arange(lo, hi, dtype=np.int64)[:, None] + np.arange(FEAT_DIM)[None, :]) & 0xFFFF
+    except MemoryError:
+        table = None
+
+    def feat(ids):
+        if table is not None:
+            return oracle.gather(table, ids)
+        return ((ids[:, None] + np.arange(FEAT_DIM)[None, :]) & 0xFFFF).astype(np.float32)
+
+    rng = np.random.default_rng(0)
+    lo = (np.arange(labels + 1) * BATCH).astype(np.int64)
+    edges, busy, n_steps = 0, 0.0, 0
+    t0 = time.time()
+    while True:
+        seeds = rng.permutation(NUM_NODES)[: labels * BATCH].astype(np.int64)
+        t1 = time.time()
+        res = oracle.multihop_sample(row_ptr, col, seeds, lo, FANOUT, SAMPLER_SEED + n_steps)
+        feat(res["renumber_map"])
+        dt = time.time() - t1
+        if n_steps > 0:  # first pass warms the page cache / OpenMP pool
+            edges += int(res["minors"].shape[0])
+            busy += dt
+        n_steps += 1
+        if steps is not None:
+            if n_steps > steps:
+                break
+        elif time.time() - t0 > budget_s and n_steps >= 3:
+            break
+    return {"value": edges / busy, "unit": "edges/s", "cores": oracle.num_threads(), "kind": "port",
+            "sample": "%d timed steps of %d labels x %d seeds (same graph, fan-out, seed rule; 1 untimed warm-up step)" % (n_steps - 1, labels, BATCH)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    row_ptr, col = rmat_csr(torch, NUM_NODES, NUM_EDGES, 42, dev)  # input generation only; nothing timed runs on the GPU
+    row_ptr, col = row_ptr.cpu().numpy(), col.cpu().numpy()
+    t0 = time.time()
+    base = cpu_baseline(row_ptr, col, steps=args.steps + args.warmup - 1, labels=4)
+    wall = time.time() - t0
+    out = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": base["value"], "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / max(1, args.steps + args.warmup), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64/int32 ids, fp32 features", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "labels_per_step": 4, "seeds_per_label": BATCH},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--labels", type=int, default=LABELS_PER_STEP)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

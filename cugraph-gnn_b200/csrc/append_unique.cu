@@ -124,19 +124,19 @@ static void append_unique_typed(const KeyT* targets, int T, const KeyT* neighbor
   int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sms * 8));
   if (total > 0) {
     uniq_insert_kernel<KeyT><<<grid, 256, 0, stream>>>(table, slots - 1, targets, T, neighbors, Nn, slot_of);
-    WGB_CUDA_TRY(cudaGetLastError());
+    WGB_CHECK_LAUNCH();
   }
   auto* state  = static_cast<unsigned long long*>(st);
   auto* ticket = reinterpret_cast<unsigned int*>(state + tiles);
   uniq_rank_kernel<<<tiles, kScanBlock, 0, stream>>>(table, slot_of, T, Nn, rank, state, ticket);
-  WGB_CUDA_TRY(cudaGetLastError());
+  WGB_CHECK_LAUNCH();
   int new_count = 0;
   WGB_CUDA_TRY(cudaMemcpyAsync(&new_count, rank + Nn, sizeof(int), cudaMemcpyDeviceToHost, stream));
   WGB_CUDA_TRY(cudaStreamSynchronize(stream));
   auto* unique_out = static_cast<KeyT*>(output_alloc(env, unique_ctx, (int64_t)T + new_count, dt));
   if (total > 0) {
     uniq_finalize_kernel<KeyT><<<grid, 256, 0, stream>>>(table, slot_of, targets, T, neighbors, Nn, rank, unique_out, raw_to_unique);
-    WGB_CUDA_TRY(cudaGetLastError());
+    WGB_CHECK_LAUNCH();
   }
   // temp buffers are released by the callbacks when this scope ends; with stream-ordered or
   // caching allocators (torch) that is safe without another sync.

@@ -234,7 +234,7 @@ static void launch_copy(const RowsOpArgs& a, int64_t row0, int64_t rows, unsigne
     rows_copy_kernel<IdxT, VEC, true, SCATTER><<<grid, kBlock, 0, a.stream>>>(a.table, toff, tstride, idx, (unsigned int)total, rd, dense, dstride);
   else
     rows_copy_kernel<IdxT, VEC, false, SCATTER><<<grid, kBlock, 0, a.stream>>>(a.table, toff, tstride, idx, (unsigned int)total, rd, dense, dstride);
-  WGB_CUDA_TRY(cudaGetLastError());
+  WGB_CHECK_LAUNCH();
 }
 
 template <typename IdxT, bool SCATTER>
@@ -295,7 +295,7 @@ static void run_convert(const RowsOpArgs& a)
       rows_convert_kernel<TableT, DenseT, IdxT, 1, SCATTER><<<grid, kBlock, 0, a.stream>>>(
         a.table, (unsigned long long)a.table_desc.storage_offset, (unsigned long long)a.table_desc.stride, idx,
         (unsigned int)total, rd, dense, (unsigned long long)a.dense_desc.stride);
-    WGB_CUDA_TRY(cudaGetLastError());
+    WGB_CHECK_LAUNCH();
   }
 }
 
@@ -369,7 +369,9 @@ static wholememory_error_code_t rows_op(wholememory_tensor_t wm_tensor, wholemem
   }
   if (id->dtype != WHOLEMEMORY_DT_INT && id->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
   wholememory_tensor_description_t dd = *wholememory_tensor_get_tensor_description(dense_tensor);
-  if (dd.dim != wholememory_tensor_get_tensor_description(wm_tensor)->dim) {
+  // the reference compares against the (already unsqueezed) table description, i.e. a 1-D table takes an
+  // [n, 1] output (gather_op.cpp:33-52); a plain 1-D output is accepted as well.
+  if (dd.dim != td.dim && !(dd.dim == 1 && wholememory_tensor_get_tensor_description(wm_tensor)->dim == 1)) {
     log_msg(LEVEL_ERROR, "%s tensor should be same dim as wholememory_tensor.", scatter ? "input" : "output");
     return WHOLEMEMORY_INVALID_INPUT;
   }

@@ -30,6 +30,7 @@
 namespace wgb {
 
 int g_log_level = LEVEL_WARN;
+unsigned long long g_kernel_launches = 0;
 
 void log_msg(int level, const char* fmt, ...)
 {
@@ -470,6 +471,8 @@ bool wholememory_is_intranode_communicator(wholememory_comm_t) { return true; }
 bool wholememory_is_intra_mnnvl_communicator(wholememory_comm_t) { return false; }
 bool wholememory_is_build_with_nvshmem() { return false; }
 
+unsigned long long wholememory_b200_kernel_launch_count() { return wgb::g_kernel_launches; }
+
 int fork_get_device_count()
 {
   // count devices in a child so that the caller never creates a CUDA context
@@ -852,7 +855,10 @@ wholememory_error_code_t wholememory_make_tensor_from_pointer(wholememory_tensor
 {
   if (!tensor || !desc) return WHOLEMEMORY_INVALID_INPUT;
   if (desc->dim < 0 || desc->dim > 2) return WHOLEMEMORY_INVALID_INPUT;
-  if (desc->dim >= 1 && desc->strides[desc->dim - 1] != 1) {
+  bool empty = false;
+  for (int i = 0; i < desc->dim; i++)
+    if (desc->sizes[i] == 0) empty = true;
+  if (!empty && desc->dim >= 1 && desc->strides[desc->dim - 1] != 1) {
     log_msg(LEVEL_ERROR, "last stride must be 1");
     return WHOLEMEMORY_INVALID_INPUT;
   }

@@ -87,7 +87,7 @@ static void launch_count_scan(const SampleArgs& a, void* tile_state_mem)
     count_scan_kernel<IdT, true><<<tiles, kScanBlock, 0, a.stream>>>(a.row_ptr, a.row_ptr_off, static_cast<const IdT*>(a.centers), a.n, a.M, a.offsets, state, ticket);
   else
     count_scan_kernel<IdT, false><<<tiles, kScanBlock, 0, a.stream>>>(a.row_ptr, a.row_ptr_off, static_cast<const IdT*>(a.centers), a.n, a.M, a.offsets, state, ticket);
-  WGB_CUDA_TRY(cudaGetLastError());
+  WGB_CHECK_LAUNCH();
 }
 
 template <typename IdT, typename ColT, bool CHUNKED>
@@ -115,7 +115,7 @@ static void launch_uniform(const SampleArgs& a)
     int grid          = std::max(1, std::min(a.n, sms * 16));
     uniform_general_kernel<IdT, ColT, CHUNKED><<<grid, kGeneralBlock, 0, a.stream>>>(a.row_ptr, a.row_ptr_off, a.col, a.col_off, centers, a.n, a.M, a.seed, a.offsets, out, a.out_lid, a.out_gid, tab);
   }
-  WGB_CUDA_TRY(cudaGetLastError());
+  WGB_CHECK_LAUNCH();
 }
 
 template <typename IdT, typename ColT, typename WT, bool CHUNKED>
@@ -135,7 +135,7 @@ static void launch_weighted(const SampleArgs& a)
     else
       weighted_kernel<IdT, ColT, WT, 256, CHUNKED><<<grid, 256, 0, a.stream>>>(a.row_ptr, a.row_ptr_off, a.col, a.col_off, a.wgt, a.wgt_off, centers, a.n, a.M, a.seed, a.offsets, out, a.out_lid, a.out_gid, tab);
   }
-  WGB_CUDA_TRY(cudaGetLastError());
+  WGB_CHECK_LAUNCH();
 }
 
 template <typename IdT, typename ColT>

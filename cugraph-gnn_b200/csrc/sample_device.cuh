@@ -136,8 +136,11 @@ template <typename IdT, bool CHUNKED>
 __global__ void __launch_bounds__(kScanBlock) count_scan_kernel(ChunkRef row_ptr, unsigned long long row_ptr_off,
                                                                  const IdT* __restrict__ centers, int n, int M,
                                                                  int* __restrict__ offsets,
-                                                                 unsigned long long* state, unsigned int* ticket)
+                                                                 unsigned long long* state, unsigned int* ticket,
+                                                                 const int* __restrict__ n_dev = nullptr,
+                                                                 int* __restrict__ total_out = nullptr)
 {
+  if (n_dev) n = *n_dev;  // frontier size produced on the device by the previous hop
   const int tile = take_ticket(ticket);
   const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
   unsigned int v[kScanItems];
@@ -162,6 +165,7 @@ __global__ void __launch_bounds__(kScanBlock) count_scan_kernel(ChunkRef row_ptr
   for (int k = 0; k < kScanItems; k++) {
     long long i = base + k;
     if (i <= n) offsets[i] = (int)(prefix + v[k]);
+    if (i == n && total_out) *total_out = (int)(prefix + v[k]);
   }
 }
 
@@ -170,8 +174,10 @@ template <typename IdT, typename ColT, bool CHUNKED>
 __global__ void __launch_bounds__(256) sample_all_kernel(ChunkRef row_ptr, unsigned long long row_ptr_off, ChunkRef col,
                                                          unsigned long long col_off, const IdT* __restrict__ centers,
                                                          int n, const int* __restrict__ offsets, ColT* __restrict__ out,
-                                                         int* __restrict__ lid, long long* __restrict__ gid)
+                                                         int* __restrict__ lid, long long* __restrict__ gid,
+                                                         const int* __restrict__ n_dev = nullptr)
 {
+  if (n_dev) n = *n_dev;
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * 8;
   for (int b = blockIdx.x * 8 + (threadIdx.x >> 5); b < n; b += nwarps) {
@@ -232,8 +238,10 @@ __global__ void __launch_bounds__(256) uniform_small_kernel(ChunkRef row_ptr, un
                                                             const IdT* __restrict__ centers, int n, int M,
                                                             unsigned long long seed, const int* __restrict__ offsets,
                                                             ColT* __restrict__ out, int* __restrict__ lid,
-                                                            long long* __restrict__ gid, const Affine* __restrict__ tab)
+                                                            long long* __restrict__ gid, const Affine* __restrict__ tab,
+                                                            const int* __restrict__ n_dev = nullptr)
 {
+  if (n_dev) n = *n_dev;
   constexpr int GPW = 32 / G;
   __shared__ int W[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -322,8 +330,10 @@ template <typename IdT, typename ColT, bool CHUNKED>
 __global__ void __launch_bounds__(kGeneralBlock) uniform_general_kernel(
   ChunkRef row_ptr, unsigned long long row_ptr_off, ChunkRef col, unsigned long long col_off,
   const IdT* __restrict__ centers, int n, int M, unsigned long long seed, const int* __restrict__ offsets,
-  ColT* __restrict__ out, int* __restrict__ lid, long long* __restrict__ gid, const Affine* __restrict__ tab)
+  ColT* __restrict__ out, int* __restrict__ lid, long long* __restrict__ gid, const Affine* __restrict__ tab,
+  const int* __restrict__ n_dev = nullptr)
 {
+  if (n_dev) n = *n_dev;
   __shared__ unsigned long long keys[1024];
   __shared__ int xs[1024];
   __shared__ int prev[1024];
@@ -441,8 +451,10 @@ __global__ void __launch_bounds__(BLOCK) weighted_kernel(ChunkRef row_ptr, unsig
                                                          int n, int M, unsigned long long seed,
                                                          const int* __restrict__ offsets, ColT* __restrict__ out,
                                                          int* __restrict__ lid, long long* __restrict__ gid,
-                                                         const Affine* __restrict__ tab)
+                                                         const Affine* __restrict__ tab,
+                                                         const int* __restrict__ n_dev = nullptr)
 {
+  if (n_dev) n = *n_dev;
   constexpr int C = 2048;
   __shared__ unsigned long long cand[C];
   __shared__ int s_cnt;

@@ -49,6 +49,15 @@ void log_msg(int level, const char* fmt, ...);
     }                                                                                          \
   } while (0)
 
+// every kernel launch of this library goes through this check; the counter backs bench.py's
+// "gpu_launches" claim (wholememory_b200_kernel_launch_count()).
+extern unsigned long long g_kernel_launches;
+#define WGB_CHECK_LAUNCH()                   \
+  do {                                       \
+    ++::wgb::g_kernel_launches;              \
+    WGB_CUDA_TRY(cudaGetLastError());        \
+  } while (0)
+
 #define WGB_EXPECTS(cond, msg)                                                                 \
   do {                                                                                         \
     if (!(cond)) throw ::wgb::logic_error(std::string(msg) + " [" #cond "]");                  \

@@ -28,3 +28,4 @@ from .tensor import (
     destroy_wholememory_tensor,
 )
 from . import wholememory_ops, wholegraph_ops, graph_ops
+from .multihop import MultiHopSampler, multihop_neighbor_sample

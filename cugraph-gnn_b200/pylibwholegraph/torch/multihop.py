@@ -1,0 +1,96 @@
+"""Fused multi-hop, multi-label neighbour sampler (B200 extension, include/wholememory/b200_ops.h).
+
+One native call replaces the reference's per-hop python loop of sample + append_unique
+(pylibwholegraph/torch/graph_structure.py:136-196) and produces the pylibcugraph-shaped result that
+cugraph-pyg's readers decode (cugraph_pyg/sampler/sampler.py:525-740).
+"""
+import ctypes
+from typing import List, Optional
+
+import pylibwholegraph.binding.wholememory_binding as wmb
+from pylibwholegraph.utils.imports import import_optional
+from .wholegraph_env import get_stream, TorchMemoryContext, get_wholegraph_env_fns, wrap_torch_tensor
+
+torch = import_optional("torch")
+
+FLAG_CSR = 1
+FLAG_INT64_IDS = 2
+
+_vp = ctypes.c_void_p
+_create = wmb.native_symbol("wholegraph_create_multihop_sampler")
+_create.restype = ctypes.c_int
+_create.argtypes = [ctypes.POINTER(_vp)]
+_destroy = wmb.native_symbol("wholegraph_destroy_multihop_sampler")
+_destroy.restype = ctypes.c_int
+_destroy.argtypes = [_vp]
+_sample = wmb.native_symbol("wholegraph_multihop_neighbor_sample")
+_sample.restype = ctypes.c_int
+_sample.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_ulonglong,
+                    ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+
+
+def _handle(t):
+    """wholememory_tensor_t of a WholeMemoryTensor / PyWholeMemoryTensor / torch tensor / None (+ keep-alive)."""
+    if t is None:
+        return None, None
+    if hasattr(t, "wmb_tensor"):
+        return t.wmb_tensor.get_c_handle(), t
+    if hasattr(t, "get_c_handle"):
+        return t.get_c_handle(), t
+    w = wrap_torch_tensor(t)
+    return w.get_c_handle(), (w, t)
+
+
+class MultiHopSampler(object):
+    """Owns the persistent device scratch of the fused sampler; reuse one instance per loader."""
+
+    def __init__(self):
+        h = _vp()
+        wmb.check_wholememory_error_code(_create(ctypes.byref(h)))
+        self._h = h.value
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _destroy(self._h)
+            self._h = None
+
+    def sample(self, csr_row_ptr, csr_col, seeds: "torch.Tensor", label_offsets: "torch.Tensor", fanout: List[int],
+               random_state: int, *, csr_weight=None, csr_edge_id=None, compression: str = "COO",
+               int64_ids: bool = False):
+        """Returns a dict with majors|major_offsets, minors, edge_id, label_hop_offsets, renumber_map,
+        renumber_map_offsets (all CUDA tensors)."""
+        assert seeds.is_cuda and seeds.dim() == 1 and seeds.dtype in (torch.int32, torch.int64)
+        label_offsets = label_offsets.to(device=seeds.device, dtype=torch.int64)
+        assert compression in ("COO", "CSR")
+        csr = compression == "CSR"
+        flags = (FLAG_CSR if csr else 0) | (FLAG_INT64_IDS if int64_ids else 0)
+        names = ["majors", "minors", "edge_id", "label_hop_offsets", "renumber_map", "renumber_map_offsets", "major_offsets"]
+        ctx = {n: TorchMemoryContext() for n in names}
+        keep = []
+        handles = []
+        for t in (csr_row_ptr, csr_col, csr_weight, csr_edge_id, seeds, label_offsets):
+            h, k = _handle(t)
+            handles.append(h)
+            keep.append(k)
+        fan = (ctypes.c_int * len(fanout))(*[int(f) for f in fanout])
+        err = _sample(
+            self._h, *handles, fan, len(fanout), ctypes.c_ulonglong(random_state & 0xFFFFFFFFFFFFFFFF), flags,
+            None if csr else ctx["majors"].get_c_context(), ctx["minors"].get_c_context(), ctx["edge_id"].get_c_context(),
+            ctx["label_hop_offsets"].get_c_context(), ctx["renumber_map"].get_c_context(),
+            ctx["renumber_map_offsets"].get_c_context(), ctx["major_offsets"].get_c_context() if csr else None,
+            get_wholegraph_env_fns(), get_stream(),
+        )
+        wmb.check_wholememory_error_code(err)
+        out = {n: ctx[n].get_tensor() for n in names if ctx[n].get_tensor() is not None}
+        return out
+
+
+_default_sampler: Optional[MultiHopSampler] = None
+
+
+def multihop_neighbor_sample(csr_row_ptr, csr_col, seeds, label_offsets, fanout, random_state, **kwargs):
+    """Functional form using a process-wide sampler object."""
+    global _default_sampler
+    if _default_sampler is None:
+        _default_sampler = MultiHopSampler()
+    return _default_sampler.sample(csr_row_ptr, csr_col, seeds, label_offsets, fanout, random_state, **kwargs)

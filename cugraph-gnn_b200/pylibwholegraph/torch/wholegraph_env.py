@@ -119,6 +119,14 @@ def wrap_torch_tensor(t: Union["torch.Tensor", None]) -> wmb.WrappedLocalTensor:
         return wrapped.wrap_tensor(desc, 0)
     desc.set_dtype(torch_dtype_to_wholememory_dtype(t.dtype))
     desc.set_shape(tuple(t.shape))
-    desc.set_stride(tuple(t.stride()))
+    # empty tensors may report arbitrary strides (numpy gives 0): describe them as contiguous
+    if t.numel() > 0:
+        desc.set_stride(tuple(t.stride()))
+    else:
+        dense, acc = [], 1
+        for s in reversed(t.shape):
+            dense.insert(0, acc)
+            acc *= max(int(s), 1)
+        desc.set_stride(tuple(dense))
     desc.set_storage_offset(0)
     return wrapped.wrap_tensor(desc, t.data_ptr())

@@ -1,0 +1,84 @@
+/*
+ * B200-native extensions of the C ABI: entry points that have no counterpart in libwholegraph's
+ * headers because the reference reaches the same functionality through other libraries
+ * (pylibcugraph's multi-hop sampler, torch_geometric's aggregation) or not at all.
+ * Plain handles, pointers and sizes only.
+ */
+#pragma once
+
+#include <wholememory/env_func_ptrs.h>
+#include <wholememory/wholememory.h>
+#include <wholememory/wholememory_tensor.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+unsigned long long wholememory_b200_kernel_launch_count();
+
+/* ---------------------------------------------------------------------------------------------
+ * S0: multi-hop, multi-label ("batch") neighbour sampling with renumbering in ONE call.
+ *
+ * Replaces the call cugraph-pyg makes into the un-vendored libcugraph,
+ *   pylibcugraph.homogeneous_{uniform,biased}_neighbor_sample(..., renumber=True, retain_seeds=True,
+ *   deduplicate_sources=True, prior_sources_behavior="exclude", return_hops=True, compression=COO|CSR)
+ *   (/root/reference/python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:784-819, 888-902)
+ * and the per-hop python loop of the in-repo path
+ *   (/root/reference/python/pylibwholegraph/pylibwholegraph/torch/graph_structure.py:136-196).
+ *
+ * The sampler object owns the persistent scratch (hash table keyed (label, vertex), frontier and edge
+ * buffers); it is bound to the CUDA device that was current when it was created and must be used from
+ * one stream at a time.
+ *
+ *   csr_row_ptr   int64 [V+1]           WholeMemory or local tensor (peer chunks are read by P2P)
+ *   csr_col       int32|int64 [E]
+ *   csr_weight    fp32|fp64 [E] or NULL  non-NULL selects weight-biased (A-Res) sampling
+ *   csr_edge_id   int64 [E] or NULL      value reported as edge id (NULL: the CSR position)
+ *   seeds         int32|int64 [S]        device; seeds of label l are seeds[label_offsets[l] : label_offsets[l+1]]
+ *   label_offsets int64 [B+1]            device
+ *   fanout[h]     > 0 sample, -1 take all, 0 skip the hop;  random_state: hop h uses random_state + h*0x9E3779B97F4A7C15
+ *
+ * Outputs (allocated through p_env_fns->output_fns, contexts as in wholegraph_op.h):
+ *   majors / minors        int32 (int64 with WHOLEGRAPH_MULTIHOP_INT64_IDS) [E_s] label-local ids, grouped by
+ *                          label then hop; local ids: seeds first, then vertices in first-occurrence order
+ *   edge_id                int64 [E_s]
+ *   label_hop_offsets      int64 [B*L+1]   COO: edge offsets.  CSR: offsets into major_offsets
+ *   renumber_map           int64 [N_s]     global id of every local id, labels concatenated
+ *   renumber_map_offsets   int64 [B+1]
+ *   major_offsets          int64 [R+1]     only with WHOLEGRAPH_MULTIHOP_CSR (majors is then not produced)
+ * One host synchronisation per call (to size the outputs); take-all hops add one each.
+ */
+typedef struct wholegraph_multihop_sampler_* wholegraph_multihop_sampler_t;
+
+#define WHOLEGRAPH_MULTIHOP_COO 0
+#define WHOLEGRAPH_MULTIHOP_CSR 1
+#define WHOLEGRAPH_MULTIHOP_INT64_IDS 2
+
+wholememory_error_code_t wholegraph_create_multihop_sampler(wholegraph_multihop_sampler_t* sampler);
+wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop_sampler_t sampler);
+
+wholememory_error_code_t wholegraph_multihop_neighbor_sample(wholegraph_multihop_sampler_t sampler,
+                                                             wholememory_tensor_t csr_row_ptr,
+                                                             wholememory_tensor_t csr_col,
+                                                             wholememory_tensor_t csr_weight,
+                                                             wholememory_tensor_t csr_edge_id,
+                                                             wholememory_tensor_t seeds,
+                                                             wholememory_tensor_t label_offsets,
+                                                             const int* fanout,
+                                                             int num_hops,
+                                                             unsigned long long random_state,
+                                                             int flags,
+                                                             void* out_majors_ctx,
+                                                             void* out_minors_ctx,
+                                                             void* out_edge_id_ctx,
+                                                             void* out_label_hop_offsets_ctx,
+                                                             void* out_renumber_map_ctx,
+                                                             void* out_renumber_map_offsets_ctx,
+                                                             void* out_major_offsets_ctx,
+                                                             wholememory_env_func_t* p_env_fns,
+                                                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
