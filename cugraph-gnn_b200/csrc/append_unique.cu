@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kScanBlock) uniq_rank_kernel(const UniqSlot* _
                                                                int T, int Nn, int* __restrict__ rank,
                                                                unsigned long long* state, unsigned int* ticket)
 {
-  const int tile       = take_ticket(ticket);
+  const int tile       = blockIdx.x;
   const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
   unsigned int v[kScanItems];
 #pragma unroll

@@ -10,12 +10,15 @@
 // B200-first design:
 //  * no host synchronisation until every hop is done: frontier sizes and edge counts stay on the device,
 //    kernels are launched over host-known upper bounds (|frontier| * fanout) and read the true sizes from
-//    device memory; a single 32-byte D2H copy at the end sizes the outputs.
+//    device memory; a single 24-byte D2H copy at the end sizes the outputs.
 //  * per hop: count+scan (single pass) -> sample (sub-warp per row) -> hash insert with atomicMin of the
 //    first edge position -> single-pass flag+scan+compact that emits the next frontier in first-occurrence
 //    order and assigns local ids.  The next frontier of a label is exactly the vertices new in this hop.
-//  * one open-addressing table keyed (label, vertex) for the whole call group, persistent across calls in
-//    the sampler object; slots are invalidated by an 8-bit epoch in the key instead of a memset.
+//  * one open-addressing table keyed (label, vertex) for the whole call group.  Its allocation covers the
+//    worst case, but every hop only uses the first `nslots` slots, chosen ON THE DEVICE from the true
+//    counts (2 x (known vertices + this hop's edges)), so the working set stays L2-resident (126 MB) even
+//    though the worst-case bound is ~10x larger.  Each hop runs in a new 8-bit epoch (no memset): the
+//    vertices numbered so far are re-inserted (cheap: earlier hops are an order of magnitude smaller).
 //  * the final pass scatters (major, minor, edge id) from hop-major scratch to the label-major / hop-minor
 //    layout the decoders expect (sampler/sampler.py:525-740) and turns hash slots into local ids, so
 //    renumbering costs no extra pass over the edges.
@@ -38,9 +41,12 @@ constexpr int kMaxHops = 16;
 
 struct MhSlot {
   unsigned long long key;  // epoch(8) | label * V + vertex (56)
-  unsigned long long aux;  // (255 - epoch)(8) | t(23) | index(32) | is_tag(1): see tag()/fin()
+  unsigned long long aux;  // (255 - epoch)(8) | t(23) | index(32) | is_tag(1): see mh_tag()/mh_fin()
 };
 
+// "first position" race: tag(t, e) while hop t-1 is being inserted, replaced by fin(t, rank) once the
+// first occurrence has been ranked.  fin(t, .) < tag(t', .) for t < t', so a vertex numbered in an earlier
+// step always wins the atomicMin against edges of later hops.
 __host__ __device__ __forceinline__ unsigned long long mh_tag(unsigned int t, unsigned int e)
 {
   return ((unsigned long long)t << 33) | ((unsigned long long)e << 1) | 1ULL;
@@ -61,85 +67,225 @@ __device__ __forceinline__ unsigned long long mh_mix(unsigned long long x)
   return x;
 }
 
-// claim-or-find the slot of `item` (= label * V + vertex) in the current epoch
-__device__ __forceinline__ unsigned int mh_find_or_insert(MhSlot* table, unsigned int mask, unsigned long long item,
-                                                          unsigned long long epoch)
+// Open addressing with GROUP probing: the probe sequence of an item is the 4-slot (64-byte) aligned groups
+// starting at its home group; one probe step loads the four keys of a group with independent loads (one L2
+// round trip) and scans them in order, so a lookup costs ~1 round trip at load factor 0.5 instead of one
+// dependent round trip per slot.  nslots is always a multiple of 4.
+constexpr unsigned int kGroup = 4;
+
+__device__ __forceinline__ unsigned int mh_home(unsigned long long item, unsigned int nslots)
+{
+  // fast range over the groups (any group count), returns the first slot of the home group
+  return (unsigned int)(((mh_mix(item) >> 32) * (unsigned long long)(nslots / kGroup)) >> 32) * kGroup;
+}
+
+struct MhGroupKeys {
+  unsigned long long k[kGroup];
+};
+__device__ __forceinline__ MhGroupKeys mh_load_group(const MhSlot* table, unsigned int g)
+{
+  MhGroupKeys r;
+#pragma unroll
+  for (unsigned int j = 0; j < kGroup; j++)
+    r.k[j] = ld_relaxed_u64(&table[g + j].key);
+  return r;
+}
+
+// claim-or-find the slot of `item` (= label * V + vertex) in the current epoch, starting at group `g`
+// whose keys have already been loaded into `cur` (lets callers batch the first, random, access)
+__device__ __forceinline__ unsigned int mh_find_or_insert_from(MhSlot* table, unsigned int nslots, unsigned long long item,
+                                                               unsigned long long epoch, unsigned int g, MhGroupKeys cur)
 {
   const unsigned long long key = (epoch << 56) | item;
-  unsigned int slot            = (unsigned int)mh_mix(item) & mask;
   while (true) {
-    unsigned long long cur = ld_relaxed_u64(&table[slot].key);
-    if (cur == key) return slot;
-    if ((cur >> 56) != epoch) {  // stale or never used: try to claim
-      unsigned long long prev = atomicCAS(&table[slot].key, cur, key);
-      if (prev == cur || prev == key) return slot;
-      continue;  // somebody else claimed it for another key: re-inspect this slot
+#pragma unroll
+    for (unsigned int j = 0; j < kGroup; j++) {
+      unsigned long long c = cur.k[j];
+      if (c == key) return g + j;
+      if ((c >> 56) != epoch) {  // stale or never used: try to claim
+        unsigned long long prev = atomicCAS(&table[g + j].key, c, key);
+        if (prev == c || prev == key) return g + j;
+        // somebody else claimed it for another key of this epoch: move on to the next slot
+      }
     }
-    slot = (slot + 1) & mask;
+    g   = g + kGroup >= nslots ? 0u : g + kGroup;
+    cur = mh_load_group(table, g);
   }
 }
 
-// label of every seed: slabel[s] = l such that label_offsets[l] <= s < label_offsets[l+1]
-__global__ void __launch_bounds__(256) mh_seed_label_kernel(const long long* __restrict__ label_offsets, int B, int S,
-                                                            int* __restrict__ slabel)
+__device__ __forceinline__ void mh_race_first(MhSlot* table, unsigned int slot, unsigned long long mine)
 {
+  // hub vertices are reached by many edges of one label: read first, only an edge that can still lower
+  // the first position pays for the same-address atomic
+  if (ld_relaxed_u64(&table[slot].aux) > mine) atomicMin(&table[slot].aux, mine);
+}
+
+// ---- step 0: seeds ------------------------------------------------------------------------------------
+// label of seed s by binary search in label_offsets, insert (label, seed), race for the first position
+template <typename SeedT>
+__global__ void __launch_bounds__(256) mh_seed_insert_kernel(MhSlot* table, const unsigned int* __restrict__ nslots_dev,
+                                                             unsigned long long epoch, unsigned long long V,
+                                                             const SeedT* __restrict__ seeds, int S,
+                                                             const long long* __restrict__ label_offsets, int B,
+                                                             int* __restrict__ slabel, unsigned int* __restrict__ slot_of)
+{
+  const unsigned int nslots          = *nslots_dev;
+  const unsigned long long inv_epoch = (255ULL - epoch) << 56;
   for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
-    int lo = 0, hi = B;  // find the last l with label_offsets[l] <= s
+    int lo = 0, hi = B;  // last l with label_offsets[l] <= s
     while (hi - lo > 1) {
       int mid = (lo + hi) >> 1;
       if (label_offsets[mid] <= s) lo = mid;
       else hi = mid;
     }
-    slabel[s] = lo;
+    slabel[s]               = lo;
+    unsigned long long item = (unsigned long long)lo * V + (unsigned long long)seeds[s];
+    unsigned int home       = mh_home(item, nslots);
+    unsigned int slot       = mh_find_or_insert_from(table, nslots, item, epoch, home, mh_load_group(table, home));
+    mh_race_first(table, slot, inv_epoch | mh_tag(0u, (unsigned int)s));
+    slot_of[s] = slot;
   }
 }
 
-// K3: insert the endpoints discovered in this hop; remember their slot and race for "first position"
-// SEEDS=true : item e is seed e, label from slabel;  SEEDS=false: item e is an edge, label = flabel[erow[e]]
-template <typename VT, bool SEEDS>
-__global__ void __launch_bounds__(256) mh_insert_kernel(MhSlot* table, unsigned int mask, unsigned long long epoch,
-                                                        unsigned long long V, unsigned int t,
+// ---- K3: insert the neighbours sampled in this hop -------------------------------------------------------
+// 4 edges per thread, staged so that the dependent memory round trips of the four edges overlap:
+//   A  load the home group of each edge (4 x 4 independent loads)
+//   B  scan the loaded keys (no memory)
+//   C  one optimistic CAS per edge that has to claim a slot (4 in flight)
+//   D  resolve; the rare losers (CAS lost to another key, or a full home group) take the generic probe loop
+//   E  race for the first position: a freshly claimed slot holds a stale (= worst) aux, so the claimer sends
+//      its atomicMin without reading; edges that found their vertex read aux first and usually skip the atomic
+constexpr int kInsertIlp = 4;
+template <typename VT>
+__global__ void __launch_bounds__(256) mh_insert_kernel(MhSlot* table, const unsigned int* __restrict__ nslots_dev,
+                                                        unsigned long long epoch, unsigned long long V, unsigned int t,
                                                         const VT* __restrict__ vertices, const int* __restrict__ n_dev,
                                                         const int* __restrict__ erow, const int* __restrict__ flabel,
                                                         unsigned int* __restrict__ slot_of)
 {
-  const int n = *n_dev;
+  const int n                        = *n_dev;
+  const unsigned int nslots          = *nslots_dev;
   const unsigned long long inv_epoch = (255ULL - epoch) << 56;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    int label               = SEEDS ? flabel[e] : flabel[erow[e]];
-    unsigned long long item = (unsigned long long)label * V + (unsigned long long)vertices[e];
-    unsigned int slot       = mh_find_or_insert(table, mask, item, epoch);
-    atomicMin(&table[slot].aux, inv_epoch | mh_tag(t, (unsigned int)e));
-    slot_of[e] = slot;
+  const int stride                   = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * kInsertIlp) {
+    int row[kInsertIlp];
+    unsigned long long item[kInsertIlp];
+    MhGroupKeys cur[kInsertIlp];
+    unsigned int slot[kInsertIlp];
+    unsigned long long prev[kInsertIlp], expect[kInsertIlp];
+    int state[kInsertIlp];  // 0 found, 1 CAS issued, 2 group full -> slow path, -1 inactive
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++) {
+      int e  = base + k * stride;
+      row[k] = e < n ? erow[e] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++) {
+      int e   = base + k * stride;
+      item[k] = e < n ? (unsigned long long)flabel[row[k]] * V + (unsigned long long)vertices[e] : 0ULL;
+    }
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++) {  // A
+      int e   = base + k * stride;
+      slot[k] = mh_home(item[k], nslots);
+      if (e < n) cur[k] = mh_load_group(table, slot[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++) {  // B
+      int e    = base + k * stride;
+      state[k] = -1;
+      if (e < n) {
+        const unsigned long long key = (epoch << 56) | item[k];
+        state[k]                     = 2;
+#pragma unroll
+        for (int j = (int)kGroup - 1; j >= 0; j--) {  // descending: the lowest matching / stale index wins
+          if ((cur[k].k[j] >> 56) != epoch) {
+            state[k]  = 1;
+            expect[k] = cur[k].k[j];
+            prev[k]   = (unsigned long long)j;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < (int)kGroup; j++) {
+          // a match only counts if it sits before the first stale slot (probe order); keys are unique per epoch,
+          // so a match after a stale slot cannot exist
+          if (cur[k].k[j] == key) {
+            state[k] = 0;
+            prev[k]  = (unsigned long long)j;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++) {  // C
+      if (state[k] == 1) {
+        slot[k] += (unsigned int)prev[k];
+        prev[k] = atomicCAS(&table[slot[k]].key, expect[k], (epoch << 56) | item[k]);
+      } else if (state[k] == 0) {
+        slot[k] += (unsigned int)prev[k];
+      }
+    }
+    bool fresh[kInsertIlp];
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++) {  // D
+      fresh[k] = false;
+      if (state[k] == 1) {
+        const unsigned long long key = (epoch << 56) | item[k];
+        if (prev[k] == expect[k]) {
+          fresh[k] = true;
+        } else if (prev[k] != key) {
+          unsigned int g = slot[k] & ~(kGroup - 1);
+          slot[k]        = mh_find_or_insert_from(table, nslots, item[k], epoch, g, mh_load_group(table, g));
+        }
+      } else if (state[k] == 2) {
+        unsigned int g = slot[k] + kGroup >= nslots ? 0u : slot[k] + kGroup;
+        slot[k]        = mh_find_or_insert_from(table, nslots, item[k], epoch, g, mh_load_group(table, g));
+      }
+    }
+    unsigned long long aux[kInsertIlp];
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++)  // E
+      aux[k] = (state[k] >= 0 && !fresh[k]) ? ld_relaxed_u64(&table[slot[k]].aux) : ~0ULL;
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++) {
+      int e = base + k * stride;
+      if (state[k] >= 0) {
+        const unsigned long long mine = inv_epoch | mh_tag(t, (unsigned int)e);
+        if (aux[k] > mine) atomicMin(&table[slot[k]].aux, mine);
+        slot_of[e] = slot[k];
+      }
+    }
   }
 }
 
-// K4: flag first occurrences, scan, compact into the next frontier (first-occurrence order), assign ranks
+// ---- K4: flag first occurrences, scan, compact into the next frontier, assign ranks ------------------------
 template <typename VT, bool SEEDS>
 __global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(MhSlot* table, unsigned long long epoch, unsigned int t,
                                                                 const VT* __restrict__ vertices,
-                                                                const int* __restrict__ n_dev,
+                                                                const int* __restrict__ n_dev, int n_host,
                                                                 const int* __restrict__ erow,
                                                                 const int* __restrict__ flabel,
                                                                 const unsigned int* __restrict__ slot_of,
                                                                 long long* __restrict__ next_frontier,
                                                                 int* __restrict__ next_flabel, int* __restrict__ next_n,
-                                                                unsigned long long* state, unsigned int* ticket)
+                                                                unsigned long long* state)
 {
-  const int n          = *n_dev;
-  const int tile       = take_ticket(ticket);
-  const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
+  const int n    = n_dev ? *n_dev : n_host;
+  const int tile = blockIdx.x;
+  if ((long long)tile * kScanTile > n) return;  // grid is sized from the host-side upper bound
+  const long long base               = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
   const unsigned long long inv_epoch = (255ULL - epoch) << 56;
   unsigned int v[kScanItems];
   unsigned int slot[kScanItems];
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
     long long e = base + k;
-    v[k]        = 0;
-    if (e < n) {
-      slot[k] = slot_of[e];
-      v[k]    = (table[slot[k]].aux & kAuxMask) == mh_tag(t, (unsigned int)e) ? 1u : 0u;
-    }
+    slot[k]     = e < n ? slot_of[e] : 0u;
+  }
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) {
+    long long e = base + k;
+    v[k]        = (e < n && (ld_relaxed_u64(&table[slot[k]].aux) & kAuxMask) == mh_tag(t, (unsigned int)e)) ? 1u : 0u;
   }
   unsigned int flags = 0;
 #pragma unroll
@@ -160,32 +306,75 @@ __global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(MhSlot* table, u
   }
 }
 
-// fr_off[l] = first frontier row of label l (flabel is non-decreasing), fr_off[B] = n
-__global__ void __launch_bounds__(256) mh_label_bounds_kernel(const int* __restrict__ flabel, const int* __restrict__ n_dev, int B,
-                                                              int* __restrict__ fr_off)
+// fr_off[l] = first frontier row of label l (flabel is non-decreasing), fr_off[B] = n.
+// One thread per frontier row; a row writes the offsets of every label that starts at it.
+__global__ void __launch_bounds__(256) mh_label_bounds_kernel(const int* __restrict__ flabel, const int* __restrict__ n_dev,
+                                                              int B, int* __restrict__ fr_off)
 {
   const int n = *n_dev;
-  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= B; l += gridDim.x * blockDim.x) {
-    int lo = 0, hi = n;  // first index with flabel[idx] >= l
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (flabel[mid] < l) lo = mid + 1;
-      else hi = mid;
-    }
-    fr_off[l] = lo;
+  if (n == 0) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= B; l += gridDim.x * blockDim.x)
+      fr_off[l] = 0;
+    return;
+  }
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const int l    = flabel[r];
+    const int prev = r > 0 ? flabel[r - 1] : -1;
+    for (int x = prev + 1; x <= l; x++)
+      fr_off[x] = r;
+    if (r == n - 1)
+      for (int x = l + 1; x <= B; x++)
+        fr_off[x] = n;
   }
 }
 
-// per-label bookkeeping after the last hop
+// slots used by the hop that is about to be inserted: 2 x (vertices numbered so far + its edges)
+__global__ void mh_plan_hop_kernel(const int* __restrict__ n_rows, int h, const int* __restrict__ n_edges_h,
+                                   unsigned int capacity, unsigned int* __restrict__ nslots_out)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long items = (unsigned long long)*n_edges_h;
+    for (int t = 0; t <= h; t++)
+      items += (unsigned long long)n_rows[t];
+    unsigned long long want = 2 * items + 1024;  // load factor <= 0.5
+    if (want > capacity) want = capacity;
+    *nslots_out = (unsigned int)(want & ~3ULL);
+  }
+}
+
+// vertices numbered in steps 0..h enter the new epoch with their final (step, rank)
+struct MhFrontiers {
+  const long long* frontier[kMaxHops + 1];
+  const int* flabel[kMaxHops + 1];
+};
+__global__ void __launch_bounds__(256) mh_reinsert_kernel(MhSlot* table, const unsigned int* __restrict__ nslots_dev,
+                                                          unsigned long long epoch, unsigned long long V,
+                                                          MhFrontiers fr, const int* __restrict__ n_rows)
+{
+  const unsigned int t               = blockIdx.y;
+  const int n                        = n_rows[t];
+  const unsigned int nslots          = *nslots_dev;
+  const unsigned long long inv_epoch = (255ULL - epoch) << 56;
+  const long long* __restrict__ frontier = fr.frontier[t];
+  const int* __restrict__ flabel         = fr.flabel[t];
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+    unsigned long long item = (unsigned long long)flabel[f] * V + (unsigned long long)frontier[f];
+    unsigned int home       = mh_home(item, nslots);
+    unsigned int slot       = mh_find_or_insert_from(table, nslots, item, epoch, home, mh_load_group(table, home));
+    table[slot].aux         = inv_epoch | mh_fin(t, (unsigned int)f);
+  }
+}
+
+// ---- per-label bookkeeping after the last hop ------------------------------------------------------------
 struct MhMeta {
   const int* fr_off[kMaxHops + 1];  // [t][B+1]
-  const int* off[kMaxHops];         // [h][ub_frontier+1] sample offsets (null when the hop is skipped)
+  const int* off[kMaxHops];         // [h] sample offsets over the frontier rows (null: hop skipped)
   int L;
   int B;
 };
 
 // counts[0 .. B*L)           edges of (label, hop)
-// counts[B*L .. B*L+B)       nodes of label
+// counts[B*L .. B*L+B)       vertices of label
 // counts[B*L+B .. B*L+2B)    source rows of label (CSR major rows)
 // base[t*B + l]              local id of the first vertex label l discovered at step t
 __global__ void __launch_bounds__(256) mh_meta_kernel(MhMeta m, long long* __restrict__ counts, int* __restrict__ base)
@@ -197,7 +386,6 @@ __global__ void __launch_bounds__(256) mh_meta_kernel(MhMeta m, long long* __res
       acc += m.fr_off[t][l + 1] - m.fr_off[t][l];
       if (t == m.L - 1) rows = acc;
     }
-    if (m.L == 0) rows = 0;
     for (int h = 0; h < m.L; h++) {
       long long e = 0;
       if (m.off[h]) e = (long long)m.off[h][m.fr_off[h][l + 1]] - (long long)m.off[h][m.fr_off[h][l]];
@@ -208,18 +396,26 @@ __global__ void __launch_bounds__(256) mh_meta_kernel(MhMeta m, long long* __res
   }
 }
 
-// single-block exclusive scan of `n` int64 values (n is small: B*L, B); writes n+1 outputs
-__global__ void __launch_bounds__(1024) mh_scan_i64_kernel(const long long* __restrict__ in, long long n,
-                                                           long long* __restrict__ out, long long* __restrict__ total_out)
+// three exclusive scans (blockIdx.x selects the array), each by one block; writes n+1 outputs + the total
+struct MhScan3 {
+  const long long* in[3];
+  long long* out[3];
+  long long n[3];
+  long long* totals;
+};
+__global__ void __launch_bounds__(1024) mh_scan3_kernel(MhScan3 a)
 {
   __shared__ long long s_warp[32];
   __shared__ long long s_carry;
+  const long long* __restrict__ in = a.in[blockIdx.x];
+  long long* __restrict__ out      = a.out[blockIdx.x];
+  const long long n                = a.n[blockIdx.x];
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (long long base = 0; base < n; base += blockDim.x) {
-    long long i = base + threadIdx.x;
-    long long x = i < n ? in[i] : 0;
+    long long i   = base + threadIdx.x;
+    long long x   = i < n ? in[i] : 0;
     long long inc = x;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -238,50 +434,75 @@ __global__ void __launch_bounds__(1024) mh_scan_i64_kernel(const long long* __re
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    out[n] = s_carry;
-    if (total_out) *total_out = s_carry;
+    out[n]               = s_carry;
+    a.totals[blockIdx.x] = s_carry;
   }
 }
 
-// final pass over the edges of one hop: scratch (hop-major) -> outputs (label-major, hop-minor)
+// after the hop's first occurrences are ranked: replace every edge's slot index by the (step, rank) of its
+// endpoint, packed step(4) | rank(28).  The table is re-hashed by the next hop, slot indices would dangle.
+__global__ void __launch_bounds__(256) mh_resolve_kernel(const MhSlot* __restrict__ table, const int* __restrict__ n_dev,
+                                                         unsigned int* __restrict__ slot_to_ref)
+{
+  const int n = *n_dev;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const unsigned long long aux = table[slot_to_ref[e]].aux & kAuxMask;
+    slot_to_ref[e]               = ((unsigned int)(aux >> 33) << 28) | ((unsigned int)(aux >> 1) & 0x0FFFFFFFu);
+  }
+}
+
+// ---- final pass -------------------------------------------------------------------------------------------
+struct MhHopBufs {
+  const int* off[kMaxHops];
+  const int* erow[kMaxHops];
+  const unsigned int* slot[kMaxHops];
+  const long long* gid[kMaxHops];
+};
+
+// edges of hop blockIdx.y: scratch (hop-major) -> outputs (label-major, hop-minor), (step, rank) -> local ids
 template <typename OutT, bool CHUNKED>
-__global__ void __launch_bounds__(256) mh_emit_edges_kernel(const MhSlot* __restrict__ table, int h, int L, int B,
-                                                            const int* __restrict__ n_edges_dev,
-                                                            const int* __restrict__ off_h, const int* __restrict__ erow,
-                                                            const unsigned int* __restrict__ slot_of,
-                                                            const long long* __restrict__ gid,
-                                                            const int* __restrict__ flabel_h, MhMeta m,
-                                                            const int* __restrict__ base, const long long* __restrict__ lho,
-                                                            ChunkRef edge_id_ref, unsigned long long edge_id_off, bool has_edge_id,
+__global__ void __launch_bounds__(256) mh_emit_edges_kernel(int L, int B,
+                                                            const int* __restrict__ n_edges, MhHopBufs hb, MhFrontiers fr,
+                                                            MhMeta m, const int* __restrict__ base,
+                                                            const long long* __restrict__ lho, ChunkRef edge_id_ref,
+                                                            unsigned long long edge_id_off, bool has_edge_id,
                                                             OutT* __restrict__ majors, OutT* __restrict__ minors,
                                                             long long* __restrict__ edge_id_out)
 {
-  const int n = *n_edges_dev;
+  const int h = blockIdx.y;
+  const int n = n_edges[h];
+  const int* __restrict__ off_h            = hb.off[h];
+  const int* __restrict__ erow             = hb.erow[h];
+  const unsigned int* __restrict__ slot_of = hb.slot[h];
+  const long long* __restrict__ gid        = hb.gid[h];
+  const int* __restrict__ flabel_h         = fr.flabel[h];
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const int f       = erow[e];
-    const int l       = flabel_h[f];
-    const int f0      = m.fr_off[h][l];
-    const long long p = lho[(long long)l * L + h] + (long long)(e - off_h[f0]);
-    unsigned long long aux = table[slot_of[e]].aux & kAuxMask;
-    const unsigned int t   = (unsigned int)(aux >> 33);
-    const unsigned int rk  = (unsigned int)(aux >> 1);
+    const unsigned int ref       = slot_of[e];  // step(4) | rank(28), see mh_resolve_kernel
+    const int f                  = erow[e];
+    long long g                  = gid[e];
+    const int l                  = flabel_h[f];
+    const int f0                 = m.fr_off[h][l];
+    const long long p            = lho[(long long)l * L + h] + (long long)(e - off_h[f0]);
+    const unsigned int t         = ref >> 28;
+    const unsigned int rk        = ref & 0x0FFFFFFFu;
     if (majors) majors[p] = (OutT)(base[h * B + l] + (f - f0));
     minors[p] = (OutT)(base[t * B + l] + (int)(rk - (unsigned int)m.fr_off[t][l]));
-    long long g = gid[e];
     if (has_edge_id) g = load_i64<CHUNKED>(edge_id_ref, edge_id_off + (unsigned long long)g);
     edge_id_out[p] = g;
   }
 }
 
-// final pass over the frontier rows of step t: renumber map (+ CSR major offsets for t < L)
-__global__ void __launch_bounds__(256) mh_emit_rows_kernel(int t, int L, int B, const int* __restrict__ n_rows_dev,
-                                                           const long long* __restrict__ frontier,
-                                                           const int* __restrict__ flabel, MhMeta m,
-                                                           const int* __restrict__ base, const long long* __restrict__ rmo,
-                                                           const long long* __restrict__ lho, const long long* __restrict__ rbase,
+// frontier rows of step blockIdx.y: renumber map (+ CSR major offsets for steps < L)
+__global__ void __launch_bounds__(256) mh_emit_rows_kernel(int L, int B, const int* __restrict__ n_rows, MhFrontiers fr,
+                                                           MhMeta m, const int* __restrict__ base,
+                                                           const long long* __restrict__ rmo, const long long* __restrict__ lho,
+                                                           const long long* __restrict__ rbase,
                                                            long long* __restrict__ map_out, long long* __restrict__ major_offsets)
 {
-  const int n = *n_rows_dev;
+  const int t = blockIdx.y;
+  const int n = n_rows[t];
+  const long long* __restrict__ frontier = fr.frontier[t];
+  const int* __restrict__ flabel         = fr.flabel[t];
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
     const int l     = flabel[f];
     const int f0    = m.fr_off[t][l];
@@ -313,28 +534,6 @@ __global__ void __launch_bounds__(256) mh_csr_label_hop_kernel(int L, int B, con
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256) mh_seeds_to_i64_kernel(const T* __restrict__ in, int n, long long* __restrict__ out)
-{
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    out[i] = (long long)in[i];
-}
-
-// re-insert already numbered vertices after the table had to grow (take-all hops only)
-__global__ void __launch_bounds__(256) mh_reinsert_kernel(MhSlot* table, unsigned int mask, unsigned long long epoch,
-                                                          unsigned long long V, unsigned int t,
-                                                          const long long* __restrict__ frontier,
-                                                          const int* __restrict__ flabel, const int* __restrict__ n_dev)
-{
-  const int n = *n_dev;
-  const unsigned long long inv_epoch = (255ULL - epoch) << 56;
-  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
-    unsigned long long item = (unsigned long long)flabel[f] * V + (unsigned long long)frontier[f];
-    unsigned int slot       = mh_find_or_insert(table, mask, item, epoch);
-    table[slot].aux         = inv_epoch | mh_fin(t, (unsigned int)f);
-  }
-}
-
 }  // namespace wgb
 
 // ---------------------------------------------------------------------------------------------------
@@ -346,9 +545,9 @@ struct wholegraph_multihop_sampler_ {
     size_t n = 0;
   };
   Buf table;
-  unsigned int table_slots = 0;
-  int epoch                = 0;
-  Buf slabel, scan_state, small_i32, small_i64, counts;
+  unsigned int table_slots = 0;  // allocated capacity
+  int epoch                = 0;  // last epoch handed out (0: table must be initialised)
+  Buf slabel, scan_state, small_i32, small_i64, counts, seed_slot;
   Buf frontier[wgb::kMaxHops + 1], flabel[wgb::kMaxHops + 1], fr_off[wgb::kMaxHops + 1];
   Buf off[wgb::kMaxHops], dest[wgb::kMaxHops], erow[wgb::kMaxHops], gid[wgb::kMaxHops], slot[wgb::kMaxHops];
   Buf base;
@@ -365,11 +564,11 @@ static void* ensure(wholegraph_multihop_sampler_::Buf& b, size_t bytes)
     if (b.p) WGB_CUDA_TRY(cudaFree(b.p));
     b.p = nullptr;
     b.n = 0;
-    size_t want = bytes + bytes / 8;  // a little slack so that slowly growing call groups do not realloc every call
+    size_t want = bytes + bytes / 8;  // slack so that slowly growing call groups do not realloc every call
     cudaError_t e = cudaMalloc(&b.p, want);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      e = cudaMalloc(&b.p, bytes);
+      e    = cudaMalloc(&b.p, bytes);
       want = bytes;
       if (e != cudaSuccess) {
         cudaGetLastError();
@@ -454,120 +653,115 @@ static void multihop_run(MhCall& c)
   bool bounded = true;
   ub_rows[0]   = S;
   for (int h = 0; h < L; h++) {
-    if (c.fanout[h] > 0 && bounded) {
-      ub_edges[h] = ub_rows[h] * c.fanout[h];
-    } else if (c.fanout[h] == 0) {
+    if (c.fanout[h] == 0) {
       ub_edges[h] = 0;
+    } else if (c.fanout[h] > 0 && bounded) {
+      ub_edges[h] = ub_rows[h] * c.fanout[h];
     } else {
       bounded     = false;
       ub_edges[h] = -1;  // known only after the hop's count (host sync)
     }
     ub_rows[h + 1] = ub_edges[h];
   }
+  WGB_EXPECTS(S < (1 << 28), "too many seeds for one call (2^28)");
+  long long known_items = S;  // seeds + every hop whose edge bound is known before the call starts
+  for (int h = 0; h < L && ub_edges[h] >= 0; h++)
+    known_items += ub_edges[h];
 
-  // small per-call arrays
-  int* small_i32 = static_cast<int*>(ensure(sp->small_i32, sizeof(int) * (size_t)(2 * (kMaxHops + 2))));
-  int* n_rows_dev  = small_i32;                   // [L+1] frontier sizes
-  int* n_edges_dev = small_i32 + (kMaxHops + 1);  // [L]   edge counts
+  // ---- table capacity and epochs ---------------------------------------------------------------------
+  auto ensure_capacity = [&](long long items) {
+    unsigned long long want = (unsigned long long)std::max<long long>(2 * items, 2048);
+    if (want > 0xFFFFFFF0ULL) throw logic_error("call group too large for one multi-hop call; split the seeds into more calls");
+    if (sp->table_slots < want) {
+      ensure(sp->table, (size_t)want * sizeof(MhSlot));
+      sp->table_slots = (unsigned int)(std::min<unsigned long long>(sp->table.n / sizeof(MhSlot), 0xFFFFFFF0ULL) & ~3ULL);
+      sp->epoch       = 0;
+    }
+  };
+  auto next_epoch = [&]() -> unsigned long long {
+    if (sp->epoch == 0 || sp->epoch >= 253) {
+      // all-ones = "stale key, worst possible aux"; everything alive is re-inserted by the caller afterwards
+      WGB_CUDA_TRY(cudaMemsetAsync(sp->table.p, 0xFF, (size_t)sp->table_slots * sizeof(MhSlot), st));
+      sp->epoch = 0;
+    }
+    return (unsigned long long)(++sp->epoch);
+  };
+  ensure_capacity(known_items);
+  MhSlot* table = static_cast<MhSlot*>(sp->table.p);
+
+  // ---- small per-call device arrays -------------------------------------------------------------------
+  int* small_i32     = static_cast<int*>(ensure(sp->small_i32, sizeof(int) * (size_t)(4 * (kMaxHops + 2))));
+  int* n_rows_dev    = small_i32;                                                          // [L+1] frontier sizes
+  int* n_edges_dev   = small_i32 + (kMaxHops + 1);                                         // [L]   edge counts
+  unsigned int* nslots_dev = reinterpret_cast<unsigned int*>(small_i32 + 2 * (kMaxHops + 1));  // [L+1] slots in use per step
   int* slabel = static_cast<int*>(ensure(sp->slabel, sizeof(int) * (size_t)std::max(S, 1)));
   for (int t = 0; t <= L; t++)
     ensure(sp->fr_off[t], sizeof(int) * (size_t)(B + 1));
   ensure(sp->base, sizeof(int) * (size_t)(L + 1) * (size_t)std::max(B, 1));
+  WGB_CUDA_TRY(cudaMemsetAsync(n_edges_dev, 0, sizeof(int) * kMaxHops, st));
 
-  // scan states: one slice per single-pass scan of the call (seed compaction + 2 per hop)
-  auto tiles_for = [](long long n) { return (int)((n + kScanTile) / kScanTile); };
-  auto grow_table = [&](long long items_needed, int upto_t) {
-    unsigned long long want = 1024;
-    while ((long long)want < 2 * items_needed)
-      want <<= 1;
-    if (want > (1ULL << 31)) throw logic_error("call group too large for one multi-hop call (hash table > 2^31 slots); split the seeds");
-    if (sp->table_slots >= want && sp->epoch >= 1 && sp->epoch < 254 && upto_t < 0) {
-      sp->epoch++;
-      return;
-    }
-    if (sp->table_slots < want) {
-      ensure(sp->table, (size_t)want * sizeof(MhSlot));
-      sp->table_slots = (unsigned int)want;
-      sp->epoch       = 0;
-    }
-    if (sp->epoch == 0 || sp->epoch >= 254 || upto_t >= 0) {
-      // fresh table (or epoch wrap, or growth in the middle of a call): all-ones = "stale key, worst aux"
-      WGB_CUDA_TRY(cudaMemsetAsync(sp->table.p, 0xFF, (size_t)sp->table_slots * sizeof(MhSlot), st));
-      if (upto_t < 0) sp->epoch = 1;
-      else if (sp->epoch == 0 || sp->epoch >= 254) sp->epoch = 1;
-      for (int t = 0; t <= upto_t; t++) {  // re-insert what is already numbered
-        mh_reinsert_kernel<<<grid_over(ub_rows[t], sms), 256, 0, st>>>(
-          static_cast<MhSlot*>(sp->table.p), sp->table_slots - 1, (unsigned long long)sp->epoch, c.V, (unsigned int)t,
-          static_cast<long long*>(sp->frontier[t].p), static_cast<int*>(sp->flabel[t].p), n_rows_dev + t);
-        WGB_CHECK_LAUNCH();
-      }
-    }
-  };
-
-  long long known_items = S;  // seeds + every hop whose edge bound is known before the call starts
-  for (int h = 0; h < L && ub_edges[h] >= 0; h++)
-    known_items += ub_edges[h];
-  grow_table(known_items, -1);
-  MhSlot* table = static_cast<MhSlot*>(sp->table.p);
-  unsigned long long epoch = (unsigned long long)sp->epoch;
-
-  // ---- step 0: seeds -> frontier_0 (dedup per label, first occurrence keeps the id) --------------------
-  long long* seeds64 = static_cast<long long*>(ensure(sp->dest[kMaxHops - 1], sizeof(long long) * (size_t)std::max(S, 1)));
-  if (c.seed_dtype == WHOLEMEMORY_DT_INT)
-    mh_seeds_to_i64_kernel<int><<<grid_over(S, sms), 256, 0, st>>>(static_cast<const int*>(c.seeds), S, seeds64);
-  else
-    mh_seeds_to_i64_kernel<long long><<<grid_over(S, sms), 256, 0, st>>>(static_cast<const long long*>(c.seeds), S, seeds64);
-  WGB_CHECK_LAUNCH();
-  mh_seed_label_kernel<<<grid_over(S, sms), 256, 0, st>>>(c.label_offsets, B, S, slabel);
-  WGB_CHECK_LAUNCH();
-  // scan-state arena: sized generously per use, zeroed once per use (tiny)
   auto scan_slice = [&](long long n_items) {
-    int tiles     = tiles_for(n_items);
-    size_t bytes  = scan_state_bytes(tiles);
-    void* p       = ensure(sp->scan_state, bytes);
+    int tiles    = (int)((n_items + kScanTile) / kScanTile);
+    size_t bytes = scan_state_bytes(tiles);
+    void* p      = ensure(sp->scan_state, bytes);
     WGB_CUDA_TRY(cudaMemsetAsync(p, 0, bytes, st));
     return std::make_pair(static_cast<unsigned long long*>(p), tiles);
   };
-  int* n_seeds_dev = small_i32 + 2 * (kMaxHops + 1);
-  WGB_CUDA_TRY(cudaMemcpyAsync(n_seeds_dev, &S, sizeof(int), cudaMemcpyHostToDevice, st));
-  unsigned int* slot0 = static_cast<unsigned int*>(ensure(sp->slot[kMaxHops - 1], sizeof(unsigned int) * (size_t)std::max(S, 1)));
-  long long* frontier0 = static_cast<long long*>(ensure(sp->frontier[0], sizeof(long long) * (size_t)std::max(S, 1)));
-  int* flabel0         = static_cast<int*>(ensure(sp->flabel[0], sizeof(int) * (size_t)std::max(S, 1)));
-  mh_insert_kernel<long long, true><<<grid_over(S, sms), 256, 0, st>>>(table, sp->table_slots - 1, epoch, c.V, 0u, seeds64, n_seeds_dev, nullptr, slabel, slot0);
-  WGB_CHECK_LAUNCH();
-  {
-    auto ss = scan_slice(S);
-    mh_compact_kernel<long long, true><<<ss.second, kScanBlock, 0, st>>>(table, epoch, 0u, seeds64, n_seeds_dev, nullptr, slabel, slot0, frontier0, flabel0, n_rows_dev + 0, ss.first, reinterpret_cast<unsigned int*>(ss.first + ss.second));
-    WGB_CHECK_LAUNCH();
-  }
-  mh_label_bounds_kernel<<<grid_over(B + 1, sms), 256, 0, st>>>(flabel0, n_rows_dev + 0, B, static_cast<int*>(sp->fr_off[0].p));
-  WGB_CHECK_LAUNCH();
 
-  // ---- hops ---------------------------------------------------------------------------------------------
+  MhFrontiers fr;
   MhMeta meta;
+  MhHopBufs hb;
+  memset(&fr, 0, sizeof(fr));
   memset(&meta, 0, sizeof(meta));
+  memset(&hb, 0, sizeof(hb));
   meta.L = L;
   meta.B = B;
-  meta.fr_off[0] = static_cast<int*>(sp->fr_off[0].p);
+
+  // ---- step 0: seeds -> frontier_0 (dedup per label, first occurrence keeps the id) --------------------
+  {
+    unsigned int nslots0 = (unsigned int)(std::min<unsigned long long>(sp->table_slots, (unsigned long long)S * 2 + 1024) & ~3ULL);
+    WGB_CUDA_TRY(cudaMemcpyAsync(nslots_dev, &nslots0, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
+    unsigned long long epoch = next_epoch();
+    unsigned int* slot0  = static_cast<unsigned int*>(ensure(sp->seed_slot, sizeof(unsigned int) * (size_t)std::max(S, 1)));
+    long long* frontier0 = static_cast<long long*>(ensure(sp->frontier[0], sizeof(long long) * (size_t)std::max(S, 1)));
+    int* flabel0         = static_cast<int*>(ensure(sp->flabel[0], sizeof(int) * (size_t)std::max(S, 1)));
+    auto ss              = scan_slice(S);
+    if (c.seed_dtype == WHOLEMEMORY_DT_INT) {
+      mh_seed_insert_kernel<int><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const int*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
+      WGB_CHECK_LAUNCH();
+      mh_compact_kernel<int, true><<<ss.second, kScanBlock, 0, st>>>(table, epoch, 0u, static_cast<const int*>(c.seeds), nullptr, S, nullptr, slabel, slot0, frontier0, flabel0, n_rows_dev, ss.first);
+    } else {
+      mh_seed_insert_kernel<long long><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const long long*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
+      WGB_CHECK_LAUNCH();
+      mh_compact_kernel<long long, true><<<ss.second, kScanBlock, 0, st>>>(table, epoch, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, frontier0, flabel0, n_rows_dev, ss.first);
+    }
+    WGB_CHECK_LAUNCH();
+    mh_label_bounds_kernel<<<grid_over(std::max(S, B + 1), sms), 256, 0, st>>>(flabel0, n_rows_dev, B, static_cast<int*>(sp->fr_off[0].p));
+    WGB_CHECK_LAUNCH();
+    fr.frontier[0]  = frontier0;
+    fr.flabel[0]    = flabel0;
+    meta.fr_off[0]  = static_cast<int*>(sp->fr_off[0].p);
+  }
+
+  // ---- hops ---------------------------------------------------------------------------------------------
   for (int h = 0; h < L; h++) {
     const long long rows_ub = ub_rows[h];
     const int M             = c.fanout[h];
     long long* frontier     = static_cast<long long*>(sp->frontier[h].p);
     int* flabel             = static_cast<int*>(sp->flabel[h].p);
-    int* off                = static_cast<int*>(ensure(sp->off[h], sizeof(int) * (size_t)(rows_ub + 1 + kScanTile)));
-    meta.off[h]             = nullptr;
+    int* off                = static_cast<int*>(ensure(sp->off[h], sizeof(int) * (size_t)(std::max<long long>(rows_ub, 0) + 1 + kScanTile)));
     long long edges_ub      = ub_edges[h];
+    meta.off[h]             = nullptr;
     if (M != 0 && rows_ub > 0) {
       // K1: counts + scan over the frontier
       auto ss = scan_slice(rows_ub);
-      count_scan_kernel<long long, CHUNKED><<<ss.second, kScanBlock, 0, st>>>(c.row_ptr, c.row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, reinterpret_cast<unsigned int*>(ss.first + ss.second), n_rows_dev + h, n_edges_dev + h);
+      count_scan_kernel<long long, CHUNKED><<<ss.second, kScanBlock, 0, st>>>(c.row_ptr, c.row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, nullptr, n_rows_dev + h, n_edges_dev + h);
       WGB_CHECK_LAUNCH();
       meta.off[h] = off;
       if (edges_ub < 0) {
         // take-all hop: the edge count is data dependent -> one extra host sync to size the scratch
-        int e_host = 0, r_host = 0;
+        int e_host = 0;
         WGB_CUDA_TRY(cudaMemcpyAsync(&e_host, n_edges_dev + h, sizeof(int), cudaMemcpyDeviceToHost, st));
-        WGB_CUDA_TRY(cudaMemcpyAsync(&r_host, n_rows_dev + h, sizeof(int), cudaMemcpyDeviceToHost, st));
         WGB_CUDA_TRY(cudaStreamSynchronize(st));
         WGB_EXPECTS(e_host >= 0, "edge count of a take-all hop overflowed int32");
         edges_ub = e_host;
@@ -581,40 +775,54 @@ static void multihop_run(MhCall& c)
           ub_rows[hh + 1] = ub_edges[hh];
           known_items += ub_edges[hh];
         }
-        if ((unsigned long long)(2 * known_items) > sp->table_slots) {
-          grow_table(known_items, h);
-          table = static_cast<MhSlot*>(sp->table.p);
-          epoch = (unsigned long long)sp->epoch;
-        }
+        ensure_capacity(known_items);  // may reallocate: everything alive is re-inserted below anyway
+        table = static_cast<MhSlot*>(sp->table.p);
       }
     } else {
-      WGB_CUDA_TRY(cudaMemsetAsync(n_edges_dev + h, 0, sizeof(int), st));
       edges_ub       = 0;
       ub_edges[h]    = 0;
       ub_rows[h + 1] = 0;
     }
-    WGB_EXPECTS(edges_ub < (1LL << 31) - kScanTile, "too many edges in one hop for one call; split the seeds into more calls");
-    ColT* dest     = static_cast<ColT*>(ensure(sp->dest[h], sizeof(ColT) * (size_t)std::max<long long>(edges_ub, 1)));
-    int* erow      = static_cast<int*>(ensure(sp->erow[h], sizeof(int) * (size_t)std::max<long long>(edges_ub, 1)));
-    long long* gid = static_cast<long long*>(ensure(sp->gid[h], sizeof(long long) * (size_t)std::max<long long>(edges_ub, 1)));
-    unsigned int* slot = static_cast<unsigned int*>(ensure(sp->slot[h], sizeof(unsigned int) * (size_t)std::max<long long>(edges_ub, 1)));
-    long long* next_frontier = static_cast<long long*>(ensure(sp->frontier[h + 1], sizeof(long long) * (size_t)std::max<long long>(edges_ub, 1)));
-    int* next_flabel         = static_cast<int*>(ensure(sp->flabel[h + 1], sizeof(int) * (size_t)std::max<long long>(edges_ub, 1)));
+    WGB_EXPECTS(edges_ub < (1LL << 28), "too many edges in one hop for one call (2^28); split the seeds into more calls");
+    const size_t ecap = (size_t)std::max<long long>(edges_ub, 1);
+    ColT* dest               = static_cast<ColT*>(ensure(sp->dest[h], sizeof(ColT) * ecap));
+    int* erow                = static_cast<int*>(ensure(sp->erow[h], sizeof(int) * ecap));
+    long long* gid           = static_cast<long long*>(ensure(sp->gid[h], sizeof(long long) * ecap));
+    unsigned int* slot       = static_cast<unsigned int*>(ensure(sp->slot[h], sizeof(unsigned int) * ecap));
+    long long* next_frontier = static_cast<long long*>(ensure(sp->frontier[h + 1], sizeof(long long) * ecap));
+    int* next_flabel         = static_cast<int*>(ensure(sp->flabel[h + 1], sizeof(int) * ecap));
+    hb.off[h]  = off;
+    hb.erow[h] = erow;
+    hb.slot[h] = slot;
+    hb.gid[h]  = gid;
     if (edges_ub > 0) {
+      // new epoch for this hop: pick the slot count on the device, re-insert what is numbered so far
+      unsigned long long epoch = next_epoch();
+      mh_plan_hop_kernel<<<1, 32, 0, st>>>(n_rows_dev, h, n_edges_dev + h, sp->table_slots, nslots_dev + h + 1);
+      WGB_CHECK_LAUNCH();
+      long long max_rows = 1;
+      for (int t = 0; t <= h; t++)
+        max_rows = std::max(max_rows, ub_rows[t]);
+      mh_reinsert_kernel<<<dim3(grid_over(max_rows, sms), h + 1), 256, 0, st>>>(table, nslots_dev + h + 1, epoch, c.V, fr, n_rows_dev);
+      WGB_CHECK_LAUNCH();
       // K2: sample
       launch_hop_sample<ColT, CHUNKED>(c, frontier, n_rows_dev + h, rows_ub, M, c.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL, off, dest, erow, gid);
       // K3: insert (label, neighbour)
-      mh_insert_kernel<ColT, false><<<grid_over(edges_ub, sms), 256, 0, st>>>(table, sp->table_slots - 1, epoch, c.V, (unsigned int)(h + 1), dest, n_edges_dev + h, erow, flabel, slot);
+      mh_insert_kernel<ColT><<<grid_over((edges_ub + kInsertIlp - 1) / kInsertIlp, sms), 256, 0, st>>>(table, nslots_dev + h + 1, epoch, c.V, (unsigned int)(h + 1), dest, n_edges_dev + h, erow, flabel, slot);
       WGB_CHECK_LAUNCH();
       // K4: first occurrences -> next frontier
       auto ss = scan_slice(edges_ub);
-      mh_compact_kernel<ColT, false><<<ss.second, kScanBlock, 0, st>>>(table, epoch, (unsigned int)(h + 1), dest, n_edges_dev + h, erow, flabel, slot, next_frontier, next_flabel, n_rows_dev + h + 1, ss.first, reinterpret_cast<unsigned int*>(ss.first + ss.second));
+      mh_compact_kernel<ColT, false><<<ss.second, kScanBlock, 0, st>>>(table, epoch, (unsigned int)(h + 1), dest, n_edges_dev + h, 0, erow, flabel, slot, next_frontier, next_flabel, n_rows_dev + h + 1, ss.first);
+      WGB_CHECK_LAUNCH();
+      mh_resolve_kernel<<<grid_over(edges_ub, sms), 256, 0, st>>>(table, n_edges_dev + h, slot);
       WGB_CHECK_LAUNCH();
     } else {
       WGB_CUDA_TRY(cudaMemsetAsync(n_rows_dev + h + 1, 0, sizeof(int), st));
     }
-    mh_label_bounds_kernel<<<grid_over(B + 1, sms), 256, 0, st>>>(next_flabel, n_rows_dev + h + 1, B, static_cast<int*>(sp->fr_off[h + 1].p));
+    mh_label_bounds_kernel<<<grid_over(std::max<long long>(edges_ub, B + 1), sms), 256, 0, st>>>(next_flabel, n_rows_dev + h + 1, B, static_cast<int*>(sp->fr_off[h + 1].p));
     WGB_CHECK_LAUNCH();
+    fr.frontier[h + 1] = next_frontier;
+    fr.flabel[h + 1]   = next_flabel;
     meta.fr_off[h + 1] = static_cast<int*>(sp->fr_off[h + 1].p);
   }
 
@@ -622,18 +830,19 @@ static void multihop_run(MhCall& c)
   const long long n_counts = (long long)B * L + 2LL * B;
   long long* counts = static_cast<long long*>(ensure(sp->counts, sizeof(long long) * (size_t)(n_counts + 1)));
   long long* scans  = static_cast<long long*>(ensure(sp->small_i64, sizeof(long long) * (size_t)(n_counts + 8)));
-  long long* lho    = scans;                        // B*L + 1
+  long long* lho    = scans;                         // B*L + 1
   long long* rmo    = scans + (long long)B * L + 1;  // B + 1
   long long* rbase  = rmo + B + 1;                   // B + 1
   long long* totals = rbase + B + 1;                 // 3
   int* base         = static_cast<int*>(sp->base.p);
   mh_meta_kernel<<<grid_over(B, sms), 256, 0, st>>>(meta, counts, base);
   WGB_CHECK_LAUNCH();
-  mh_scan_i64_kernel<<<1, 1024, 0, st>>>(counts, (long long)B * L, lho, totals + 0);
-  WGB_CHECK_LAUNCH();
-  mh_scan_i64_kernel<<<1, 1024, 0, st>>>(counts + (long long)B * L, B, rmo, totals + 1);
-  WGB_CHECK_LAUNCH();
-  mh_scan_i64_kernel<<<1, 1024, 0, st>>>(counts + (long long)B * L + B, B, rbase, totals + 2);
+  MhScan3 sc;
+  sc.in[0] = counts;                           sc.out[0] = lho;   sc.n[0] = (long long)B * L;
+  sc.in[1] = counts + (long long)B * L;        sc.out[1] = rmo;   sc.n[1] = B;
+  sc.in[2] = counts + (long long)B * L + B;    sc.out[2] = rbase; sc.n[2] = B;
+  sc.totals = totals;
+  mh_scan3_kernel<<<3, 1024, 0, st>>>(sc);
   WGB_CHECK_LAUNCH();
   // ---- the one host sync of the call: output sizes ------------------------------------------------------------
   WGB_CUDA_TRY(cudaMemcpyAsync(sp->h_totals, totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -643,8 +852,8 @@ static void multihop_run(MhCall& c)
   const bool csr    = (c.flags & WHOLEGRAPH_MULTIHOP_CSR) != 0;
   const bool idx64  = (c.flags & WHOLEGRAPH_MULTIHOP_INT64_IDS) != 0;
   const wholememory_dtype_t idx_dt = idx64 ? WHOLEMEMORY_DT_INT64 : WHOLEMEMORY_DT_INT;
-  void* out_minors  = output_alloc(c.env, c.ctx_minors, n_edges, idx_dt);
-  void* out_majors  = (!csr && c.ctx_majors) ? output_alloc(c.env, c.ctx_majors, n_edges, idx_dt) : nullptr;
+  void* out_minors   = output_alloc(c.env, c.ctx_minors, n_edges, idx_dt);
+  void* out_majors   = (!csr && c.ctx_majors) ? output_alloc(c.env, c.ctx_majors, n_edges, idx_dt) : nullptr;
   long long* out_eid = static_cast<long long*>(output_alloc(c.env, c.ctx_edge_id, n_edges, WHOLEMEMORY_DT_INT64));
   long long* out_lho = static_cast<long long*>(output_alloc(c.env, c.ctx_lho, (long long)B * L + 1, WHOLEMEMORY_DT_INT64));
   long long* out_map = static_cast<long long*>(output_alloc(c.env, c.ctx_map, n_nodes, WHOLEMEMORY_DT_INT64));
@@ -662,18 +871,22 @@ static void multihop_run(MhCall& c)
     WGB_CHECK_LAUNCH();
   }
   // ---- final pass: edges and rows to their label-major places ---------------------------------------------------
-  for (int h = 0; h < L; h++) {
-    if (ub_edges[h] <= 0) continue;
-    int grid = grid_over(ub_edges[h], sms);
+  long long max_edges = 0, max_rows = 1;
+  for (int h = 0; h < L; h++)
+    max_edges = std::max(max_edges, ub_edges[h]);
+  for (int t = 0; t <= L; t++)
+    max_rows = std::max(max_rows, ub_rows[t]);
+  if (n_edges > 0 && max_edges > 0) {
+    // tighter than the upper bound: no hop has more edges than the call has in total
+    dim3 grid(grid_over(std::min(max_edges, n_edges), sms), L);
     if (idx64)
-      mh_emit_edges_kernel<long long, CHUNKED><<<grid, 256, 0, st>>>(table, h, L, B, n_edges_dev + h, static_cast<int*>(sp->off[h].p), static_cast<int*>(sp->erow[h].p), static_cast<unsigned int*>(sp->slot[h].p), static_cast<long long*>(sp->gid[h].p), static_cast<int*>(sp->flabel[h].p), meta, base, lho, c.eid, c.eid_off, c.has_eid, static_cast<long long*>(out_majors), static_cast<long long*>(out_minors), out_eid);
+      mh_emit_edges_kernel<long long, CHUNKED><<<grid, 256, 0, st>>>(L, B, n_edges_dev, hb, fr, meta, base, lho, c.eid, c.eid_off, c.has_eid, static_cast<long long*>(out_majors), static_cast<long long*>(out_minors), out_eid);
     else
-      mh_emit_edges_kernel<int, CHUNKED><<<grid, 256, 0, st>>>(table, h, L, B, n_edges_dev + h, static_cast<int*>(sp->off[h].p), static_cast<int*>(sp->erow[h].p), static_cast<unsigned int*>(sp->slot[h].p), static_cast<long long*>(sp->gid[h].p), static_cast<int*>(sp->flabel[h].p), meta, base, lho, c.eid, c.eid_off, c.has_eid, static_cast<int*>(out_majors), static_cast<int*>(out_minors), out_eid);
+      mh_emit_edges_kernel<int, CHUNKED><<<grid, 256, 0, st>>>(L, B, n_edges_dev, hb, fr, meta, base, lho, c.eid, c.eid_off, c.has_eid, static_cast<int*>(out_majors), static_cast<int*>(out_minors), out_eid);
     WGB_CHECK_LAUNCH();
   }
-  for (int t = 0; t <= L; t++) {
-    if (ub_rows[t] <= 0) continue;
-    mh_emit_rows_kernel<<<grid_over(ub_rows[t], sms), 256, 0, st>>>(t, L, B, n_rows_dev + t, static_cast<long long*>(sp->frontier[t].p), static_cast<int*>(sp->flabel[t].p), meta, base, rmo, lho, rbase, out_map, out_moff);
+  if (n_nodes > 0) {
+    mh_emit_rows_kernel<<<dim3(grid_over(std::min(max_rows, n_nodes), sms), L + 1), 256, 0, st>>>(L, B, n_rows_dev, fr, meta, base, rmo, lho, rbase, out_map, out_moff);
     WGB_CHECK_LAUNCH();
   }
 }
@@ -701,7 +914,7 @@ wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop
     b.p = nullptr;
   };
   cudaDeviceSynchronize();
-  drop(s->table); drop(s->slabel); drop(s->scan_state); drop(s->small_i32); drop(s->small_i64); drop(s->counts); drop(s->base);
+  drop(s->table); drop(s->seed_slot); drop(s->slabel); drop(s->scan_state); drop(s->small_i32); drop(s->small_i64); drop(s->counts); drop(s->base);
   for (int i = 0; i <= wgb::kMaxHops; i++) {
     drop(s->frontier[i]); drop(s->flabel[i]); drop(s->fr_off[i]);
   }

@@ -141,7 +141,11 @@ __global__ void __launch_bounds__(kScanBlock) count_scan_kernel(ChunkRef row_ptr
                                                                  int* __restrict__ total_out = nullptr)
 {
   if (n_dev) n = *n_dev;  // frontier size produced on the device by the previous hop
-  const int tile = take_ticket(ticket);
+  // tiles are processed in blockIdx order (CTAs are dispatched in increasing index order, so every
+  // predecessor is resident or finished); tiles past the one holding index n have nothing to do -- the
+  // grid is sized from a host-side upper bound when n lives on the device.
+  const int tile = blockIdx.x;
+  if ((long long)tile * kScanTile > n) return;
   const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
   unsigned int v[kScanItems];
 #pragma unroll
@@ -211,6 +215,9 @@ __device__ __forceinline__ int resolve_chain_group(int x, bool valid, int g, int
   unsigned int m   = __match_any_sync(gmask, key);
   unsigned int low = m & ((1u << lane) - 1u);
   bool has_prev    = valid && low != 0;
+  // fast path (the common case when N >> M): no two steps read the same position and no step reads one of
+  // the M tail positions that get copied -> Q is still the identity wherever it is read, a[i] = r[i].
+  if (!__any_sync(gmask, has_prev || (valid && x >= N - M))) return x;
   int jstar        = has_prev ? (31 - __clz(low)) - sub * G : 0;
   Wg[g]            = -1;
   __syncwarp(gmask);
