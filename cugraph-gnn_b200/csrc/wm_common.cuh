@@ -148,7 +148,9 @@ struct wholememory_handle_ {
   size_t chunk_start[wgb::kMaxWorld + 1] = {};  // byte offsets
   void** d_ptrs                          = nullptr;  // device copies for wholememory_gref_t
   size_t* d_offsets                      = nullptr;
-  bool vmm                               = false;    // CONTINUOUS with a flat VA mapping
+  bool vmm                               = false;    // chunks are cuMem allocations mapped with cuMemMap
+  unsigned long long vmm_handle[wgb::kMaxWorld] = {};
+  size_t vmm_size[wgb::kMaxWorld]        = {};
   void* flat_ptr                         = nullptr;
 };
 

@@ -495,6 +495,8 @@ class DeviceArrayView:
     def __init__(self, ptr, shape, dtype, strides_elts=None, owner=None):
         es = _DT_SIZE[int(dtype)]
         self.owner = owner
+        self.wm_dtype = int(dtype)
+        self.strides_elts = None if strides_elts is None else tuple(int(x) for x in strides_elts)
         self.is_bf16 = int(dtype) == WholeMemoryDataType.DtBF16
         self.__cuda_array_interface__ = {
             "shape": tuple(shape),

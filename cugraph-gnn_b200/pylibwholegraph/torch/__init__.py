@@ -29,3 +29,4 @@ from .tensor import (
 )
 from . import wholememory_ops, wholegraph_ops, graph_ops
 from .multihop import MultiHopSampler, multihop_neighbor_sample
+from .aggregate import csr_aggregate, csr_aggregate_forward, SAGEConv

@@ -79,6 +79,41 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample(wholegraph_multihop
                                                              wholememory_env_func_t* p_env_fns,
                                                              void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * A1: CSR neighbourhood aggregation of the sampled block (the SpMM that consumes the sampler output).
+ *
+ * The reference has no such kernel; its models use torch_geometric SAGEConv/GCNConv message passing over
+ * the COO block (/root/reference/python/cugraph-pyg/cugraph_pyg/examples/gcn_dist_mnmg.py:239,
+ * /root/reference/python/pylibwholegraph/pylibwholegraph/torch/gnn_model.py:119-125).
+ *
+ *   out[i, :] = reduce_{e in [indptr[i], indptr[i+1])} x[ map[indices[e]], : ]     (fp32 accumulate and output)
+ *
+ *   indptr     int32|int64 [n_dst+1]   local device tensor (the sampler's major_offsets)
+ *   indices    int32|int64 [nnz]       local device tensor (the sampler's minors)
+ *   gather_map int64 [*] or NULL       NULL: indices address rows of x directly.  Non-NULL (the renumber map):
+ *                                      x is the full feature table and the gather is fused into the aggregation
+ *   x          fp32|fp16|bf16 [n, F]   local or WholeMemory tensor (peer rows are read by P2P), rows 16-byte aligned
+ *   out        fp32 [n_dst, F]         local device tensor
+ * wholegraph_csr_aggregate_backward adds grad_out[i,:] (* 1/deg_i for mean) into grad_x[indices[e],:].
+ */
+#define WHOLEGRAPH_AGG_SUM 0
+#define WHOLEGRAPH_AGG_MEAN 1
+
+wholememory_error_code_t wholegraph_csr_aggregate(wholememory_tensor_t indptr,
+                                                  wholememory_tensor_t indices,
+                                                  wholememory_tensor_t gather_map,
+                                                  wholememory_tensor_t x,
+                                                  int reduce,
+                                                  wholememory_tensor_t out,
+                                                  void* stream);
+
+wholememory_error_code_t wholegraph_csr_aggregate_backward(wholememory_tensor_t indptr,
+                                                           wholememory_tensor_t indices,
+                                                           wholememory_tensor_t grad_out,
+                                                           int reduce,
+                                                           wholememory_tensor_t grad_x,
+                                                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

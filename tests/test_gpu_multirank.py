@@ -1,0 +1,135 @@
+"""(e) Multi-GPU path on whatever devices exist: world_size-2 with one process per rank.  With a single
+visible GPU both ranks share device 0 -- cudaIpc mapping, the chunk partition plan and the in-kernel
+address translation are exactly those of two GPUs (peer loads then stay on one device)."""
+import functools
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _setup(rank, world):
+    for p in (os.path.join(ROOT, "cugraph-gnn_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+
+    torch.cuda.set_device(rank % torch.cuda.device_count())
+    return torch
+
+
+def _comm(uid, rank, world):
+    import pylibwholegraph.binding.wholememory_binding as wmb
+    import pylibwholegraph.torch as wgth
+
+    wgth.init(rank, world, rank, world)
+    return wgth, wgth.WholeMemoryCommunicator(wmb.create_communicator(wmb.PyWholeMemoryUniqueID(uid), rank, world))
+
+
+def _gather_scatter_worker(rank, world, uid, partition):
+    torch = _setup(rank, world)
+    wgth, comm = _comm(uid, rank, world)
+    rows, dim = 10007, 128
+    part = None
+    if partition == "uneven":
+        part = [rows // 3, rows - rows // 3] if world == 2 else None
+    emb = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [rows, dim], torch.float32, [dim, 1], part)
+    local, start = emb.get_local_tensor()
+    # reference partition plan: ceil(N / W) rows per rank (memory_handle.cpp:1597-1629)
+    if part is None:
+        per = (rows + world - 1) // world
+        assert start == min(rank * per, rows) and local.shape[0] == min((rank + 1) * per, rows) - start
+    else:
+        assert start == sum(part[:rank]) and local.shape[0] == part[rank]
+    ids = torch.arange(start, start + local.shape[0], device="cuda")
+    local.copy_(((ids[:, None] * 7 + torch.arange(dim, device="cuda")[None, :]) % 4096).float())
+    torch.cuda.synchronize()
+    comm.barrier()
+    g = torch.Generator().manual_seed(5)  # same indices on every rank: both read local AND remote rows
+    idx = torch.randint(0, rows, (5000,), generator=g)
+    idx[::11] = -1
+    got = emb.gather(idx.cuda())
+    exp = ((idx[:, None] * 7 + torch.arange(dim)[None, :]) % 4096).float()
+    keep = idx >= 0
+    assert torch.equal(got.cpu()[keep], exp[keep]), "rank %d: chunked gather mismatch" % rank
+    # int32 indices + fp16 output over the remote chunk only
+    other = (rank + 1) % world
+    lo = start if other == rank else (0 if rank == 1 else local.shape[0])
+    remote_idx = torch.arange(lo, lo + 100, dtype=torch.int32)
+    got16 = emb.gather(remote_idx.cuda(), force_dtype=torch.float16)
+    assert torch.equal(got16.cpu(), ((remote_idx.long()[:, None] * 7 + torch.arange(dim)[None, :]) % 4096).half())
+    comm.barrier()
+    # scatter: rank 0 writes rows that live on every rank, owners verify their local memory
+    new_rows = torch.arange(0, rows, 97)
+    if rank == 0:
+        emb.scatter(torch.full((new_rows.shape[0], dim), -3.0).cuda(), new_rows.cuda())
+        torch.cuda.synchronize()
+    comm.barrier()
+    mine = new_rows[(new_rows >= start) & (new_rows < start + local.shape[0])] - start
+    assert bool((local[mine.cuda()] == -3.0).all()), "rank %d: scattered rows did not arrive" % rank
+    # per-rank views of every chunk are P2P mapped
+    chunks, starts = emb.get_all_chunked_tensor()
+    assert len(chunks) == world and starts[rank] == start
+    assert float(chunks[other][0, 0]) == float(chunks[other][0, 0])
+    comm.barrier()
+    wgth.destroy_wholememory_tensor(emb)
+
+
+def _sampler_worker(rank, world, uid):
+    torch = _setup(rank, world)
+    wgth, comm = _comm(uid, rank, world)
+    import wg_oracle as oracle
+    from graphs import random_csr
+    from pylibwholegraph.torch import wholegraph_ops
+
+    nodes, edges = 9703, 104323
+    row_ptr, col = random_csr(nodes, edges, seed=77)
+    # CSR striped over the ranks by element range, as the reference's tests do
+    # (cpp/tests/wholegraph_ops/wholegraph_csr_unweighted_sample_without_replacement_tests.cu:182-195)
+    def striped(arr):
+        t = torch.from_numpy(arr)
+        wm = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [arr.shape[0]], t.dtype, [1])
+        local, start = wm.get_local_tensor()
+        local.copy_(t[start:start + local.shape[0]].cuda())
+        return wm
+
+    wm_rp, wm_col = striped(row_ptr), striped(col)
+    torch.cuda.synchronize()
+    comm.barrier()
+    centers = np.random.default_rng(rank).integers(0, nodes, 700).astype(np.int64)
+    for M in (10, 25, 50, -1):
+        off, dest, lid, gid = wholegraph_ops.unweighted_sample_without_replacement(
+            wm_rp.wmb_tensor, wm_col.wmb_tensor, torch.from_numpy(centers).cuda(), M, 1234 + rank, True, True)
+        eoff, edest, elid, egid = oracle.unweighted_sample(row_ptr, col, centers, M, 1234 + rank)
+        assert np.array_equal(off.cpu().numpy(), eoff) and np.array_equal(gid.cpu().numpy(), egid)
+        assert np.array_equal(dest.cpu().numpy(), edest)
+    # fused multi-hop sampler over the striped graph
+    sampler = wgth.MultiHopSampler()
+    seeds = np.random.default_rng(10 + rank).permutation(nodes)[:300].astype(np.int64)
+    lo = np.array([0, 100, 300], dtype=np.int64)
+    got = sampler.sample(wm_rp, wm_col, torch.from_numpy(seeds).cuda(), torch.from_numpy(lo).cuda(), [5, 3], 99)
+    exp = oracle.multihop_sample(row_ptr, col, seeds, lo, [5, 3], 99)
+    for k in ("majors", "minors", "edge_id", "renumber_map", "label_hop_offsets"):
+        assert np.array_equal(got[k].cpu().numpy(), exp[k]), k
+    comm.barrier()
+
+
+def _run(fn, **kw):
+    import pylibwholegraph.binding.wholememory_binding as wmb
+    from pylibwholegraph.utils.multiprocess import multiprocess_run
+
+    uid = wmb.create_unique_id().get_bytes()
+    multiprocess_run(2, functools.partial(fn, uid=uid, **kw))
+
+
+@pytest.mark.parametrize("partition", ["equal", "uneven"])
+def test_chunked_gather_scatter_two_ranks(partition):
+    _run(_gather_scatter_worker, partition=partition)
+
+
+def test_chunked_csr_sampling_two_ranks():
+    _run(_sampler_worker)
