@@ -595,7 +595,7 @@ struct MhCall {
   unsigned long long V;
   unsigned long long random_state;
   int flags;
-  void *ctx_majors, *ctx_minors, *ctx_edge_id, *ctx_lho, *ctx_map, *ctx_rmo, *ctx_major_offsets;
+  void *ctx_majors, *ctx_minors, *ctx_edge_id, *ctx_lho, *ctx_map, *ctx_rmo, *ctx_major_offsets, *ctx_step_counts;
   wholememory_env_func_t* env;
   cudaStream_t stream;
 };
@@ -863,6 +863,13 @@ static void multihop_run(MhCall& c)
     WGB_EXPECTS(c.ctx_major_offsets != nullptr, "CSR compression needs a major_offsets output context");
     out_moff = static_cast<long long*>(output_alloc(c.env, c.ctx_major_offsets, n_srcrows + 1, WHOLEMEMORY_DT_INT64));
   }
+  if (c.ctx_step_counts) {
+    // vertices label l discovered at step t (t = 0: its seeds): base[(t+1)*B + l] - base[t*B + l]; handed out as
+    // the [L+1, B] table of first local ids plus the per-label totals so that readers never have to reduce
+    // over the edge arrays (the reference's decoders do, with a host sync per hop: sampler.py:570-575)
+    int* out_sc = static_cast<int*>(output_alloc(c.env, c.ctx_step_counts, (long long)(L + 1) * B, WHOLEMEMORY_DT_INT));
+    WGB_CUDA_TRY(cudaMemcpyAsync(out_sc, base, sizeof(int) * (size_t)(L + 1) * (size_t)B, cudaMemcpyDeviceToDevice, st));
+  }
   WGB_CUDA_TRY(cudaMemcpyAsync(out_rmo, rmo, sizeof(long long) * (size_t)(B + 1), cudaMemcpyDeviceToDevice, st));
   if (!csr) {
     WGB_CUDA_TRY(cudaMemcpyAsync(out_lho, lho, sizeof(long long) * (size_t)((long long)B * L + 1), cudaMemcpyDeviceToDevice, st));
@@ -933,6 +940,7 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample(
   wholememory_tensor_t label_offsets, const int* fanout, int num_hops, unsigned long long random_state, int flags,
   void* out_majors_ctx, void* out_minors_ctx, void* out_edge_id_ctx, void* out_label_hop_offsets_ctx,
   void* out_renumber_map_ctx, void* out_renumber_map_offsets_ctx, void* out_major_offsets_ctx,
+  void* out_label_step_base_ctx,
   wholememory_env_func_t* p_env_fns, void* stream)
 {
   using namespace wgb;
@@ -1004,6 +1012,7 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample(
     c.ctx_map           = out_renumber_map_ctx;
     c.ctx_rmo           = out_renumber_map_offsets_ctx;
     c.ctx_major_offsets = out_major_offsets_ctx;
+    c.ctx_step_counts   = out_label_step_base_ctx;
     c.env               = p_env_fns;
     c.stream            = as_stream(stream);
     if (cd->dtype == WHOLEMEMORY_DT_INT) {

@@ -1,0 +1,174 @@
+"""Call-group batching around the native sampler (role of the reference's
+cugraph_pyg/sampler/distributed_sampler.py:25-908, node path).
+
+A "call group" is the set of mini-batches handed to ONE native call; its size is `local_seeds_per_call`
+(default: the reference's memory heuristic, clamped to what one fused call accepts).  Each rank samples its own
+seeds from its own (replicated) CSR, so no collective is issued while sampling; the only collectives are the
+ones that keep uneven ranks in step (all_reduce of the call-group count), as in the reference (:301-329).
+"""
+from functools import reduce
+from math import ceil
+from typing import Dict, Iterator, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+import pylibcugraph
+from .sampler_utils import verify_metadata
+
+TensorType = Union[torch.Tensor, np.ndarray, list]
+
+
+class BaseDistributedSampler:
+    def __init__(self, graph, local_seeds_per_call: int, retain_original_seeds: bool = False):
+        self.__graph = graph
+        self.__local_seeds_per_call = int(local_seeds_per_call)
+        self.__handle = None
+        self.__retain_original_seeds = retain_original_seeds
+
+    def sample_batches(self, seeds, seed_times, batch_id_offsets, random_state: int = 0, metadata=None) -> Dict[str, torch.Tensor]:
+        raise NotImplementedError("Must be implemented by subclass")
+
+    @property
+    def is_multi_gpu(self) -> bool:
+        return isinstance(self.__graph, pylibcugraph.MGGraph)
+
+    @property
+    def _local_seeds_per_call(self) -> int:
+        return self.__local_seeds_per_call
+
+    @property
+    def _graph(self):
+        return self.__graph
+
+    @property
+    def _resource_handle(self):
+        if self.__handle is None:
+            self.__handle = pylibcugraph.ResourceHandle()
+        return self.__handle
+
+    @property
+    def _retain_original_seeds(self) -> bool:
+        return self.__retain_original_seeds
+
+    def get_start_batch_offset(self, local_num_batches: int, assume_equal_input_size: bool = False) -> Tuple[int, bool]:
+        """First global batch id of this rank, and whether every rank has the same number of batches."""
+        if not (self.is_multi_gpu and torch.distributed.is_initialized()):
+            return 0, True
+        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        if assume_equal_input_size:
+            return rank * local_num_batches, True
+        t = torch.empty((world,), dtype=torch.int64, device="cuda")
+        torch.distributed.all_gather_into_tensor(t, torch.tensor([local_num_batches], dtype=torch.int64, device="cuda"))
+        counts = t.tolist()
+        return int(sum(counts[:rank])), len(set(counts)) == 1
+
+    def _call_group(self, seeds: torch.Tensor, index: torch.Tensor, batch_id_start: int, batch_size: int,
+                    random_state: int, metadata) -> Tuple[Dict[str, torch.Tensor], int, int]:
+        n = int(seeds.numel())
+        num_full, last = divmod(n, batch_size)
+        sizes = [batch_size] * num_full + ([last] if last else [])
+        input_offsets = torch.tensor([0] + sizes, dtype=torch.int64).cumsum(0)
+        out = self.sample_batches(seeds=seeds, seed_times=None, batch_id_offsets=input_offsets.cuda(non_blocking=True),
+                                  random_state=random_state, metadata=metadata)
+        out["input_index"] = index.cuda(non_blocking=True)
+        out["input_offsets"] = input_offsets  # host: readers slice with python ints
+        out["map"] = out.pop("renumber_map")
+        out = {k: v for k, v in out.items() if v is not None}
+        return out, batch_id_start, batch_id_start + len(sizes) - 1
+
+    def sample_from_nodes(self, nodes: TensorType, *, batch_size: int = 16, random_state: int = 62,
+                          assume_equal_input_size: bool = False, input_id: Optional[TensorType] = None,
+                          input_time: Optional[TensorType] = None, metadata=None
+                          ) -> Iterator[Tuple[Dict[str, torch.Tensor], int, int]]:
+        """Lazily yields (raw call-group dict, first batch id, last batch id)."""
+        verify_metadata(metadata)
+        if input_time is not None:
+            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+        nodes = torch.as_tensor(nodes).cuda()
+        num_seeds = int(nodes.numel())
+        input_id = torch.arange(num_seeds, dtype=torch.int64) if input_id is None else torch.as_tensor(input_id).cpu()
+        batches_per_call = max(1, self._local_seeds_per_call // batch_size)
+        seeds_per_call = batches_per_call * batch_size
+        local_num_batches = int(ceil(num_seeds / batch_size))
+        batch_id_start, equal = self.get_start_batch_offset(local_num_batches, assume_equal_input_size)
+        seed_groups = list(torch.split(nodes, seeds_per_call))
+        index_groups = list(torch.split(input_id, seeds_per_call))
+        if self.is_multi_gpu and torch.distributed.is_initialized() and not equal:
+            # every rank makes the same number of calls (uneven ranks sample empty groups)
+            t = torch.tensor([len(seed_groups)], dtype=torch.int32, device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            pad = int(t) - len(seed_groups)
+            seed_groups += [nodes[:0]] * pad
+            index_groups += [input_id[:0]] * pad
+
+        def gen():
+            start = batch_id_start
+            for call_id, (s, ix) in enumerate(zip(seed_groups, index_groups)):
+                raw, first, last = self._call_group(s, ix, start, batch_size, random_state + call_id, metadata)
+                start = last + 1
+                yield raw, first, last
+
+        return gen()
+
+    def sample_from_edges(self, *args, **kwargs):
+        raise NotImplementedError("link-prediction sampling is outside the B200 hot path (SURVEY.md §8f row 2)")
+
+
+class DistributedNeighborSampler(BaseDistributedSampler):
+    BASE_VERTICES_PER_BYTE = 0.1107662486009992  # reference heuristic ("based on benchmarking", :755-757)
+    UNKNOWN_VERTICES_DEFAULT = 32768
+    MAX_EDGES_PER_HOP = (1 << 28) - 1  # one fused call packs (step, rank) references in 32 bits
+
+    def __init__(self, graph, *, local_seeds_per_call: Optional[int] = None, retain_original_seeds: bool = False,
+                 fanout: List[int] = [-1], prior_sources_behavior: str = "exclude", deduplicate_sources: bool = True,
+                 compression: str = "COO", compress_per_hop: bool = False, with_replacement: bool = False,
+                 disjoint: bool = False, biased: bool = False, heterogeneous: bool = False, temporal: bool = False,
+                 temporal_comparison: Optional[str] = None, vertex_type_offsets=None, num_edge_types: int = 1):
+        if heterogeneous or num_edge_types > 1:
+            raise NotImplementedError("heterogeneous sampling is not built yet (SURVEY.md §8e C5)")
+        if temporal:
+            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+        self.__fanout = [int(f) for f in np.asarray(fanout).reshape(-1)]
+        self.__func = pylibcugraph.homogeneous_biased_neighbor_sample if biased else pylibcugraph.homogeneous_uniform_neighbor_sample
+        self.__func_kwargs = {
+            "h_fan_out": np.asarray(self.__fanout, dtype="int32"),
+            "prior_sources_behavior": prior_sources_behavior,
+            "retain_seeds": retain_original_seeds,
+            "deduplicate_sources": deduplicate_sources,
+            "compress_per_hop": compress_per_hop,
+            "compression": compression,
+            "with_replacement": with_replacement,
+            "disjoint_sampling": disjoint,
+        }
+        super().__init__(graph, self.__calc_local_seeds_per_call(local_seeds_per_call), retain_original_seeds)
+
+    def __calc_local_seeds_per_call(self, local_seeds_per_call: Optional[int]) -> int:
+        if local_seeds_per_call is not None:
+            return int(local_seeds_per_call)
+        if any(f <= 0 for f in self.__fanout):
+            return DistributedNeighborSampler.UNKNOWN_VERTICES_DEFAULT
+        total_memory = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+        prod = reduce(lambda x, y: x * y, self.__fanout)
+        by_memory = int(DistributedNeighborSampler.BASE_VERTICES_PER_BYTE * total_memory / prod)
+        return max(1, min(by_memory, DistributedNeighborSampler.MAX_EDGES_PER_HOP // prod))
+
+    def sample_batches(self, seeds, seed_times, batch_id_offsets, random_state: int = 0, metadata=None) -> Dict[str, torch.Tensor]:
+        rank = torch.distributed.get_rank() if (self.is_multi_gpu and torch.distributed.is_initialized()) else 0
+        kwargs = {
+            "resource_handle": self._resource_handle,
+            "input_graph": self._graph,
+            "start_vertex_list": seeds,
+            "starting_vertex_label_offsets": batch_id_offsets,
+            "renumber": True,
+            "return_hops": True,
+            "do_expensive_check": False,
+            "random_state": random_state + rank,
+        }
+        kwargs.update(self.__func_kwargs)
+        out = self.__func(**kwargs)
+        out["fanout"] = torch.tensor(self.__fanout, dtype=torch.int32)
+        out["rank"] = rank
+        if metadata is not None:
+            out.update(metadata)
+        return out

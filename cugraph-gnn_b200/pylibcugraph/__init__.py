@@ -1,0 +1,218 @@
+"""pylibcugraph-shaped entry points on top of the B200 fused sampler.
+
+cugraph-pyg's only use of pylibcugraph on the hot path is: build an SGGraph/MGGraph from COO arrays and
+call ``{homogeneous,heterogeneous}_{uniform,biased}_neighbor_sample`` once per call group
+(reference call sites: python/cugraph-pyg/cugraph_pyg/data/graph_store.py:263-329,
+python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:53-94, 784-819, 888-902).
+libcugraph itself is not vendored in the reference tree; this module keeps the call signature and the
+result dictionary so that code written against pylibcugraph runs unchanged, and routes the work to
+``wholegraph_multihop_neighbor_sample`` (include/wholememory/b200_ops.h).
+
+Differences that callers can observe:
+  * arrays are torch CUDA tensors (the reference converts cupy -> torch right after the call anyway);
+  * the random stream is this project's (S1/S2 geometry per hop), not libcugraph's -- unverifiable either way;
+  * with_replacement=True, disjoint_sampling=True, temporal and heterogeneous sampling raise NotImplementedError.
+"""
+from typing import Optional
+
+import numpy as np
+import torch
+
+__version__ = "26.10.00+b200"
+
+
+class ResourceHandle:
+    """Placeholder for pylibcugraph.ResourceHandle (streams come from torch's current stream)."""
+
+    def __init__(self, handle_ptr=None):
+        self.handle_ptr = handle_ptr
+
+
+class GraphProperties:
+    def __init__(self, is_symmetric: bool = False, is_multigraph: bool = False):
+        self.is_symmetric = is_symmetric
+        self.is_multigraph = is_multigraph
+
+
+def _as_cuda(a, dtype=None):
+    if a is None:
+        return None
+    t = torch.as_tensor(a)
+    if not t.is_cuda:
+        t = t.cuda()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+class SGGraph:
+    """CSR by cuGraph source, resident on this GPU.
+
+    The sampler follows out-edges of a seed, so rows are sources and columns destinations; cugraph-pyg passes
+    src = PyG edge_index[1], dst = PyG edge_index[0] (graph_store.py:509-533), i.e. rows end up being PyG
+    destinations and the sampled neighbours PyG sources (in-edges)."""
+
+    def __init__(self, resource_handle, graph_properties, src_or_offset_array, dst_or_index_array, weight_array=None,
+                 store_transposed=False, renumber=False, do_expensive_check=False, edge_id_array=None,
+                 edge_type_array=None, input_array_format="COO", vertices_array=None, drop_self_loops=False,
+                 drop_multi_edges=False, symmetrize=False, edge_start_time_array=None, edge_end_time_array=None,
+                 num_vertices: Optional[int] = None):
+        if edge_start_time_array is not None or edge_end_time_array is not None:
+            raise NotImplementedError("temporal graphs are outside the B200 hot path")
+        if drop_self_loops or drop_multi_edges or symmetrize or renumber or store_transposed:
+            raise NotImplementedError("graph transformations are not supported; pass the final COO")
+        self.properties = graph_properties
+        if input_array_format == "CSR":
+            row_ptr = _as_cuda(src_or_offset_array, torch.int64)
+            col = _as_cuda(dst_or_index_array)
+            order = None
+        elif input_array_format == "COO":
+            src = _as_cuda(src_or_offset_array, torch.int64)
+            dst = _as_cuda(dst_or_index_array, torch.int64)
+            if num_vertices is None:
+                if vertices_array is not None:
+                    num_vertices = int(torch.as_tensor(vertices_array).max()) + 1 if len(vertices_array) else 0
+                else:
+                    num_vertices = int(max(src.max(), dst.max())) + 1 if src.numel() else 0
+            order = torch.argsort(src, stable=True)
+            col = dst[order]
+            row_ptr = torch.zeros(num_vertices + 1, dtype=torch.int64, device=src.device)
+            if src.numel():
+                row_ptr[1:] = torch.bincount(src, minlength=num_vertices).cumsum(0)
+        else:
+            raise ValueError("input_array_format must be 'COO' or 'CSR'")
+        self.num_vertices = int(row_ptr.numel() - 1)
+        self.row_ptr = row_ptr
+        # 32-bit columns halve the sampler's random-read traffic whenever the ids fit
+        self.col = col.to(torch.int32) if self.num_vertices < 2**31 - 1 else col.to(torch.int64)
+        pick = (lambda a, dt=None: None if a is None else (_as_cuda(a, dt)[order] if order is not None else _as_cuda(a, dt)))
+        self.edge_id = pick(edge_id_array, torch.int64)
+        if self.edge_id is None and order is not None:
+            self.edge_id = order  # position in the caller's COO
+        self.edge_type = pick(edge_type_array, torch.int32)
+        self.weight = pick(weight_array)
+        if self.weight is not None and self.weight.dtype not in (torch.float32, torch.float64):
+            self.weight = self.weight.float()
+        self._sampler = None
+
+    def _get_sampler(self):
+        if self._sampler is None:
+            from pylibwholegraph.torch.multihop import MultiHopSampler
+
+            self._sampler = MultiHopSampler()
+        return self._sampler
+
+
+class MGGraph(SGGraph):
+    """Multi-GPU graph: every rank contributes its edge partition, the CSR is REPLICATED on every GPU of the box
+    (all-gather of the edge lists at construction).  Seeds are sharded by the callers, so sampling needs no
+    communication at all; graphs that do not fit one B200 (180 GB) can be striped with WholeMemory tensors and
+    sampled through pylibwholegraph.torch.MultiHopSampler directly."""
+
+    def __init__(self, resource_handle, graph_properties, src_array, dst_array, weight_array=None, store_transposed=False,
+                 do_expensive_check=False, edge_id_array=None, edge_type_array=None, vertices_array=None, num_arrays=1,
+                 size=None, **kwargs):
+        import torch.distributed as dist
+
+        def gather(a, dtype=None):
+            if a is None:
+                return None
+            if isinstance(a, (list, tuple)):
+                a = torch.cat([_as_cuda(x, dtype) for x in a]) if len(a) else torch.empty(0, dtype=dtype)
+            t = _as_cuda(a, dtype)
+            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+                return t
+            n = torch.tensor([t.numel()], device=t.device, dtype=torch.int64)
+            sizes = [torch.zeros_like(n) for _ in range(dist.get_world_size())]
+            dist.all_gather(sizes, n)
+            mx = int(max(int(s) for s in sizes))
+            pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
+            pad[: t.numel()] = t
+            out = [torch.empty_like(pad) for _ in range(dist.get_world_size())]
+            dist.all_gather(out, pad)
+            return torch.cat([o[: int(s)] for o, s in zip(out, sizes)])
+
+        nv = None
+        if vertices_array is not None:
+            v = gather(vertices_array, torch.int64)
+            nv = int(v.max()) + 1 if v.numel() else 0
+        super().__init__(resource_handle, graph_properties, gather(src_array, torch.int64), gather(dst_array, torch.int64),
+                         weight_array=gather(weight_array), edge_id_array=gather(edge_id_array, torch.int64),
+                         edge_type_array=gather(edge_type_array, torch.int32), num_vertices=nv, **kwargs)
+
+
+def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, biased, *,
+                     with_replacement=False, do_expensive_check=False, prior_sources_behavior=None,
+                     deduplicate_sources=False, return_hops=False, renumber=False, retain_seeds=False,
+                     compression="COO", compress_per_hop=False, random_state=None, disjoint_sampling=False,
+                     return_dict=True, **unused):
+    if with_replacement:
+        raise NotImplementedError("sampling with replacement is not on the B200 hot path")
+    if disjoint_sampling:
+        raise NotImplementedError("disjoint sampling is not on the B200 hot path")
+    if compress_per_hop:
+        raise NotImplementedError("compress_per_hop=True is not supported")
+    if not renumber:
+        raise NotImplementedError("the fused sampler always renumbers (cugraph-pyg calls with renumber=True)")
+    if prior_sources_behavior not in (None, "exclude") or (prior_sources_behavior is None and deduplicate_sources is False and len(h_fan_out) > 1):
+        # the fused sampler implements exactly deduplicate_sources=True + prior_sources_behavior="exclude"
+        raise NotImplementedError("only deduplicate_sources=True with prior_sources_behavior='exclude' is supported")
+    if biased and input_graph.weight is None:
+        raise ValueError("biased sampling needs a graph with edge weights")
+    seeds = _as_cuda(start_vertex_list)
+    if seeds.dtype not in (torch.int32, torch.int64):
+        seeds = seeds.long()
+    if starting_vertex_label_offsets is None:
+        offsets = torch.tensor([0, seeds.numel()], dtype=torch.int64, device=seeds.device)
+    else:
+        offsets = _as_cuda(starting_vertex_label_offsets, torch.int64)
+    fanout = [int(f) for f in np.asarray(h_fan_out).reshape(-1)]
+    if random_state is None:
+        random_state = int(np.random.randint(0, 2**62))
+    res = input_graph._get_sampler().sample(
+        input_graph.row_ptr, input_graph.col, seeds, offsets, fanout, int(random_state),
+        csr_weight=input_graph.weight if biased else None, csr_edge_id=input_graph.edge_id,
+        compression=compression, int64_ids=True,
+    )
+    out = {
+        "majors": res.get("majors"),
+        "minors": res["minors"],
+        "major_offsets": res.get("major_offsets"),
+        "edge_id": res["edge_id"],
+        "edge_type": None,
+        "weight": None,
+        "hop_id": None,
+        "renumber_map": res["renumber_map"],
+        "renumber_map_offsets": res["renumber_map_offsets"],
+        "label_hop_offsets": res["label_hop_offsets"],
+        # extension: [L+1, B] first local id of the vertices each label discovered at step t (0 = seeds)
+        "label_step_base": res["label_step_base"],
+    }
+    return out
+
+
+def homogeneous_uniform_neighbor_sample(resource_handle, input_graph, start_vertex_list, starting_vertex_label_offsets,
+                                        h_fan_out, **kwargs):
+    return _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, False, **kwargs)
+
+
+def homogeneous_biased_neighbor_sample(resource_handle, input_graph, start_vertex_list, starting_vertex_label_offsets,
+                                       h_fan_out, **kwargs):
+    return _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, True, **kwargs)
+
+
+def _not_on_path(name):
+    def fn(*args, **kwargs):
+        raise NotImplementedError(f"pylibcugraph.{name} is outside the B200 hot path (SURVEY.md §8: homogeneous node sampling)")
+
+    fn.__name__ = name
+    return fn
+
+
+heterogeneous_uniform_neighbor_sample = _not_on_path("heterogeneous_uniform_neighbor_sample")
+heterogeneous_biased_neighbor_sample = _not_on_path("heterogeneous_biased_neighbor_sample")
+homogeneous_uniform_temporal_neighbor_sample = _not_on_path("homogeneous_uniform_temporal_neighbor_sample")
+homogeneous_biased_temporal_neighbor_sample = _not_on_path("homogeneous_biased_temporal_neighbor_sample")
+heterogeneous_uniform_temporal_neighbor_sample = _not_on_path("heterogeneous_uniform_temporal_neighbor_sample")
+heterogeneous_biased_temporal_neighbor_sample = _not_on_path("heterogeneous_biased_temporal_neighbor_sample")
+negative_sampling = _not_on_path("negative_sampling")

@@ -26,7 +26,7 @@ _destroy.argtypes = [_vp]
 _sample = wmb.native_symbol("wholegraph_multihop_neighbor_sample")
 _sample.restype = ctypes.c_int
 _sample.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_ulonglong,
-                    ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+                    ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
 
 
 def _handle(t):
@@ -64,7 +64,8 @@ class MultiHopSampler(object):
         assert compression in ("COO", "CSR")
         csr = compression == "CSR"
         flags = (FLAG_CSR if csr else 0) | (FLAG_INT64_IDS if int64_ids else 0)
-        names = ["majors", "minors", "edge_id", "label_hop_offsets", "renumber_map", "renumber_map_offsets", "major_offsets"]
+        names = ["majors", "minors", "edge_id", "label_hop_offsets", "renumber_map", "renumber_map_offsets", "major_offsets",
+                 "label_step_base"]
         ctx = {n: TorchMemoryContext() for n in names}
         keep = []
         handles = []
@@ -78,10 +79,13 @@ class MultiHopSampler(object):
             None if csr else ctx["majors"].get_c_context(), ctx["minors"].get_c_context(), ctx["edge_id"].get_c_context(),
             ctx["label_hop_offsets"].get_c_context(), ctx["renumber_map"].get_c_context(),
             ctx["renumber_map_offsets"].get_c_context(), ctx["major_offsets"].get_c_context() if csr else None,
+            ctx["label_step_base"].get_c_context(),
             get_wholegraph_env_fns(), get_stream(),
         )
         wmb.check_wholememory_error_code(err)
         out = {n: ctx[n].get_tensor() for n in names if ctx[n].get_tensor() is not None}
+        # [L+1, B]: first local id of the vertices each label discovered at step t (0 = seeds)
+        out["label_step_base"] = out["label_step_base"].view(len(fanout) + 1, -1)
         return out
 
 

@@ -47,6 +47,8 @@ unsigned long long wholememory_b200_kernel_launch_count();
  *   renumber_map           int64 [N_s]     global id of every local id, labels concatenated
  *   renumber_map_offsets   int64 [B+1]
  *   major_offsets          int64 [R+1]     only with WHOLEGRAPH_MULTIHOP_CSR (majors is then not produced)
+ *   label_step_base        int32 [(L+1)*B] optional (ctx may be NULL): label_step_base[t*B + l] = first local id of the
+ *                                          vertices label l discovered at step t (t = 0: seeds, t = h+1: hop h)
  * One host synchronisation per call (to size the outputs); take-all hops add one each.
  */
 typedef struct wholegraph_multihop_sampler_* wholegraph_multihop_sampler_t;
@@ -76,6 +78,7 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample(wholegraph_multihop
                                                              void* out_renumber_map_ctx,
                                                              void* out_renumber_map_offsets_ctx,
                                                              void* out_major_offsets_ctx,
+                                                             void* out_label_step_base_ctx,
                                                              wholememory_env_func_t* p_env_fns,
                                                              void* stream);
 

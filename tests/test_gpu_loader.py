@@ -1,0 +1,139 @@
+"""cugraph_pyg layer on the GPU: GraphStore / FeatureStore / NeighborLoader invariants taken from the reference's
+own tests (python/cugraph-pyg/cugraph_pyg/tests/loader/test_neighbor_loader.py:20-97, data/test_feature_store.py,
+sampler/test_distributed_sampler.py) plus exact agreement of the loader's mini-batches with the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from graphs import karate_csr, random_csr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pyg():
+    import torch
+
+    torch.cuda.set_device(0)
+    os.environ.setdefault("LOCAL_WORLD_SIZE", "1")
+    import cugraph_pyg
+    from cugraph_pyg.data import GraphStore, FeatureStore
+    from cugraph_pyg.loader import NeighborLoader
+
+    return torch, GraphStore, FeatureStore, NeighborLoader
+
+
+def _karate_edge_index(torch):
+    row_ptr, col = karate_csr(np.int64)
+    dst = np.repeat(np.arange(34), np.diff(row_ptr))
+    # PyG convention: edge_index[0] = source, edge_index[1] = destination; CSR rows are destinations
+    return torch.from_numpy(np.stack([col, dst]))
+
+
+def test_neighbor_loader_karate_features_follow_n_id(pyg):
+    """reference: test_neighbor_loader (:20-49): feat[n_id] == batch.feat for every batch."""
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    ei = _karate_edge_index(torch)
+    graph_store = GraphStore()
+    graph_store.put_edge_index(ei, ("person", "knows", "person"), "coo", False, (34, 34))
+    feature_store = FeatureStore()
+    feat = torch.randint(128, (34, 16))
+    feature_store["person", "feat", None] = feat
+    loader = NeighborLoader((feature_store, graph_store), [5, 5], input_nodes=torch.arange(34))
+    n_batches = 0
+    for batch in loader:
+        n_batches += 1
+        assert (feature_store["person", "feat", None][batch.n_id].cpu() == batch.feat.cpu()).all()
+        assert torch.equal(batch.feat.cpu(), feat[batch.n_id.cpu()])
+        # every sampled edge exists: PyG edge (src -> dst) with src = n_id[row], dst = n_id[col]
+        src = batch.n_id[batch.edge_index[0]].cpu()
+        dst = batch.n_id[batch.edge_index[1]].cpu()
+        have = set(zip(ei[0].tolist(), ei[1].tolist()))
+        assert all((int(s), int(d)) in have for s, d in zip(src, dst))
+        assert batch.batch_size == batch.input_id.numel() <= 16
+        assert int(batch.num_sampled_nodes.sum()) == batch.n_id.numel()
+        assert int(batch.num_sampled_edges.sum()) == batch.edge_index.shape[1]
+        assert torch.equal(batch.n_id[: batch.batch_size].cpu(), batch.batch.cpu())
+    assert n_batches == len(loader) == 3
+
+
+def test_neighbor_loader_len(pyg):
+    """reference: test_neighbor_loader_len (:52-96)."""
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    src, dst = torch.tensor([1, 2, 3, 4]), torch.tensor([0, 1, 2, 3])
+    graph_store = GraphStore()
+    graph_store.put_edge_index(torch.stack([src, dst]), ("person", "knows", "person"), "coo", False, (5, 5))
+    feature_store = FeatureStore()
+    feature_store["person", "feat", None] = torch.randint(128, (5, 16))
+    assert len(NeighborLoader((feature_store, graph_store), [1], input_nodes=torch.arange(5), batch_size=2)) == 3
+    assert len(NeighborLoader((feature_store, graph_store), [1], input_nodes=torch.arange(5), batch_size=2, drop_last=True)) == 2
+    with pytest.raises(ValueError, match="input_nodes"):
+        len(NeighborLoader((feature_store, graph_store), [1], input_nodes="person", batch_size=2))
+
+
+@pytest.mark.parametrize("compression", ["CSR", "COO"])
+def test_neighbor_loader_matches_oracle(pyg, oracle, compression):
+    """Loader mini-batches == oracle multihop on the same seeds / seed / fan-out, through every python layer."""
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    import cugraph_pyg.loader.node_loader as nl
+
+    nodes, edges, dim = 5003, 60000, 32
+    row_ptr, col = random_csr(nodes, edges, seed=29, col_dtype=np.int64)
+    dst = np.repeat(np.arange(nodes), np.diff(row_ptr))
+    ei = torch.from_numpy(np.stack([col, dst]))
+    graph_store = GraphStore()
+    graph_store[("n", "e", "n"), "coo", False, (nodes, nodes)] = ei
+    feature_store = FeatureStore(location="cuda")
+    x = torch.randn((nodes, dim))
+    y = torch.randint(0, 10, (nodes,))
+    feature_store["n", "x", None] = x
+    feature_store["n", "y", None] = y
+    seeds = torch.from_numpy(np.random.default_rng(0).permutation(nodes)[:1000])
+    nl.generate_seed = lambda: 4321  # pin the per-iterator seed
+    loader = NeighborLoader((feature_store, graph_store), [10, 5], input_nodes=seeds, batch_size=128,
+                            compression=compression, local_seeds_per_call=384)  # 3 batches per call group
+    lo = np.concatenate([np.arange(0, 1000, 128), [1000]])
+    batches = list(loader)
+    assert len(batches) == 8
+    for b, batch in enumerate(batches):
+        group, within = divmod(b, 3)
+        g_lo = lo[group * 3: min(group * 3 + 3, 8) + 1] - lo[group * 3]
+        g_seeds = seeds.numpy()[lo[group * 3]: lo[min(group * 3 + 3, 8)]]
+        exp = oracle.multihop_sample(row_ptr, col, g_seeds, g_lo, [10, 5], 4321 + group)
+        a, e = exp["label_hop_offsets"][within * 2], exp["label_hop_offsets"][within * 2 + 2]
+        m0, m1 = exp["renumber_map_offsets"][within], exp["renumber_map_offsets"][within + 1]
+        assert np.array_equal(batch.n_id.cpu().numpy(), exp["renumber_map"][m0:m1])
+        assert np.array_equal(batch.edge_index[0].cpu().numpy(), exp["minors"][a:e])
+        assert np.array_equal(batch.edge_index[1].cpu().numpy(), exp["majors"][a:e])
+        # the CSR was built from (src sorted stable) so CSR position == position after the store's sort
+        assert np.array_equal(np.sort(batch.e_id.cpu().numpy()), np.sort(exp["edge_id"][a:e]))
+        assert batch.num_sampled_edges.tolist() == np.diff(exp["label_hop_offsets"][within * 2: within * 2 + 3]).tolist()
+        assert torch.equal(batch.x.cpu(), x[batch.n_id.cpu()])
+        assert torch.equal(batch.y.cpu(), y[batch.n_id.cpu()])
+        assert torch.equal(batch.input_id.cpu(), torch.arange(lo[b], lo[b + 1]))
+        if compression == "CSR":
+            assert batch.csr_indptr[-1] == batch.edge_index.shape[1]
+
+
+def test_feature_store_roundtrip_and_graph_store_layouts(pyg):
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    fs = FeatureStore()
+    a = torch.randn((100, 8))
+    fs["v", "a", None] = a
+    assert torch.equal(fs["v", "a", None].get_local_tensor().cpu(), a)       # index=None returns the DistEmbedding itself
+    assert torch.equal(fs["v", "a", torch.tensor([5, 1, 99])].cpu(), a[[5, 1, 99]])
+    assert fs.get_tensor_size("v", "a") == (100, 8)
+    assert [(t.group_name, t.attr_name) for t in fs.get_all_tensor_attrs()] == [("v", "a")]
+    del fs["v", "a", None]
+    assert fs.get_all_tensor_attrs() == []
+    gs = GraphStore()
+    ei = torch.tensor([[0, 1, 1, 2], [1, 0, 2, 1]])
+    gs.put_edge_index(ei, ("v", "e", "v"), "coo", False, (3, 3))
+    row, col = gs.get_edge_index(("v", "e", "v"), "coo")
+    assert torch.equal(torch.stack([row, col]).cpu(), ei)
+    assert gs.is_homogeneous and gs._vertex_offsets == {"v": 0}
+    assert gs._graph.num_vertices == 3
+    gs.finalize()
+    with pytest.raises(RuntimeError):
+        gs.finalize()
