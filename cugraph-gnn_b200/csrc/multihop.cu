@@ -34,6 +34,10 @@
 #include <wholememory/b200_ops.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
+#include <utility>
+#include <vector>
 
 namespace wgb {
 
@@ -67,57 +71,87 @@ __device__ __forceinline__ unsigned long long mh_mix(unsigned long long x)
   return x;
 }
 
-// Open addressing with GROUP probing: the probe sequence of an item is the 4-slot (64-byte) aligned groups
-// starting at its home group; one probe step loads the four keys of a group with independent loads (one L2
-// round trip) and scans them in order, so a lookup costs ~1 round trip at load factor 0.5 instead of one
-// dependent round trip per slot.  nslots is always a multiple of 4.
-constexpr unsigned int kGroup = 4;
+// Open addressing over BUCKETS of two 16-byte slots = one 32-byte sector.  What bounds these kernels is the number
+// of L2 REQUESTS per edge (random 8..32-byte accesses cost one request each, ~10^11 requests/s chip-wide), not
+// bytes, so the table is built to need as few as possible:
+//   * one 256-bit load (LDG.256) returns both keys AND both aux words of a bucket;
+//   * a new key is installed together with its first position by ONE 128-bit CAS (ATOMG.CAS.128) on the slot;
+//   * an edge that finds its vertex already has the current aux from the bucket load and only sends an atomicMin
+//     if it can still lower it.
+// => ~2 requests for a new vertex, ~1 for a repeated one (the previous 64-bit design: 4 key loads + CAS + aux
+// load + atomicMin).  nslots is always a multiple of 4.
+constexpr unsigned int kBucket = 2;
 
 __device__ __forceinline__ unsigned int mh_home(unsigned long long item, unsigned int nslots)
 {
-  // fast range over the groups (any group count), returns the first slot of the home group
-  return (unsigned int)(((mh_mix(item) >> 32) * (unsigned long long)(nslots / kGroup)) >> 32) * kGroup;
+  // fast range over the buckets (any bucket count), returns the first slot of the home bucket
+  return (unsigned int)(((mh_mix(item) >> 32) * (unsigned long long)(nslots / kBucket)) >> 32) * kBucket;
 }
 
-struct MhGroupKeys {
-  unsigned long long k[kGroup];
+struct MhBucket {
+  unsigned long long k[kBucket], a[kBucket];
 };
-__device__ __forceinline__ MhGroupKeys mh_load_group(const MhSlot* table, unsigned int g)
+__device__ __forceinline__ MhBucket mh_load_bucket(const MhSlot* table, unsigned int g)
 {
-  MhGroupKeys r;
-#pragma unroll
-  for (unsigned int j = 0; j < kGroup; j++)
-    r.k[j] = ld_relaxed_u64(&table[g + j].key);
+  MhBucket r;
+  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(r.k[0]), "=l"(r.a[0]), "=l"(r.k[1]), "=l"(r.a[1])
+               : "l"(table + g)
+               : "memory");
   return r;
 }
 
-// claim-or-find the slot of `item` (= label * V + vertex) in the current epoch, starting at group `g`
-// whose keys have already been loaded into `cur` (lets callers batch the first, random, access)
-__device__ __forceinline__ unsigned int mh_find_or_insert_from(MhSlot* table, unsigned int nslots, unsigned long long item,
-                                                               unsigned long long epoch, unsigned int g, MhGroupKeys cur)
+// 128-bit compare-and-swap of a whole slot; returns the previous contents
+__device__ __forceinline__ void mh_cas_slot(MhSlot* p, unsigned long long ek, unsigned long long ea, unsigned long long nk,
+                                            unsigned long long na, unsigned long long& ok, unsigned long long& oa)
+{
+  asm volatile(
+    "{\n .reg .b128 c, s, d;\n mov.b128 c, {%2, %3};\n mov.b128 s, {%4, %5};\n"
+    " atom.relaxed.gpu.global.cas.b128 d, [%6], c, s;\n mov.b128 {%0, %1}, d;\n}"
+    : "=l"(ok), "=l"(oa)
+    : "l"(ek), "l"(ea), "l"(nk), "l"(na), "l"(p)
+    : "memory");
+}
+
+// Claim-or-find the slot of `item` (= label * V + vertex) in the current epoch, starting at bucket `g` whose
+// contents have already been loaded into `cur` (lets callers batch the first, random, access of several items).
+// A new key is installed with aux = `mine`; *seen = the aux this thread knows the slot to hold afterwards
+// (`mine` if it installed the key, else the value read) -- callers race with atomicMin only if *seen > mine.
+__device__ __forceinline__ unsigned int mh_upsert_from(MhSlot* table, unsigned int nslots, unsigned long long item,
+                                                       unsigned long long epoch, unsigned long long mine, unsigned int g,
+                                                       MhBucket cur, unsigned long long* seen)
 {
   const unsigned long long key = (epoch << 56) | item;
   while (true) {
 #pragma unroll
-    for (unsigned int j = 0; j < kGroup; j++) {
-      unsigned long long c = cur.k[j];
-      if (c == key) return g + j;
-      if ((c >> 56) != epoch) {  // stale or never used: try to claim
-        unsigned long long prev = atomicCAS(&table[g + j].key, c, key);
-        if (prev == c || prev == key) return g + j;
-        // somebody else claimed it for another key of this epoch: move on to the next slot
+    for (unsigned int j = 0; j < kBucket; j++) {
+      unsigned long long ck = cur.k[j], ca = cur.a[j];
+      if (ck != key && (ck >> 56) != epoch) {  // stale or never used: try to claim it, key and aux at once
+        unsigned long long ok, oa;
+        mh_cas_slot(&table[g + j], ck, ca, key, mine, ok, oa);
+        if (ok == ck && oa == ca) {
+          *seen = mine;
+          return g + j;
+        }
+        ck = ok;  // somebody else got there first: look at what the slot holds now
+        ca = oa;
       }
+      if (ck == key) {
+        *seen = ca;
+        return g + j;
+      }
+      // another key of this epoch: move on
     }
-    g   = g + kGroup >= nslots ? 0u : g + kGroup;
-    cur = mh_load_group(table, g);
+    g   = g + kBucket >= nslots ? 0u : g + kBucket;
+    cur = mh_load_bucket(table, g);
   }
 }
 
-__device__ __forceinline__ void mh_race_first(MhSlot* table, unsigned int slot, unsigned long long mine)
+__device__ __forceinline__ void mh_race_first(MhSlot* table, unsigned int slot, unsigned long long seen, unsigned long long mine)
 {
-  // hub vertices are reached by many edges of one label: read first, only an edge that can still lower
-  // the first position pays for the same-address atomic
-  if (ld_relaxed_u64(&table[slot].aux) > mine) atomicMin(&table[slot].aux, mine);
+  // hub vertices are reached by many edges of one label: only an edge that can still lower the first position
+  // pays for the same-address atomic
+  if (seen > mine) atomicMin(&table[slot].aux, mine);
 }
 
 // ---- step 0: seeds ------------------------------------------------------------------------------------
@@ -138,24 +172,21 @@ __global__ void __launch_bounds__(256) mh_seed_insert_kernel(MhSlot* table, cons
       if (label_offsets[mid] <= s) lo = mid;
       else hi = mid;
     }
-    slabel[s]               = lo;
-    unsigned long long item = (unsigned long long)lo * V + (unsigned long long)seeds[s];
-    unsigned int home       = mh_home(item, nslots);
-    unsigned int slot       = mh_find_or_insert_from(table, nslots, item, epoch, home, mh_load_group(table, home));
-    mh_race_first(table, slot, inv_epoch | mh_tag(0u, (unsigned int)s));
+    slabel[s]                     = lo;
+    const unsigned long long item = (unsigned long long)lo * V + (unsigned long long)seeds[s];
+    const unsigned long long mine = inv_epoch | mh_tag(0u, (unsigned int)s);
+    const unsigned int home       = mh_home(item, nslots);
+    unsigned long long seen;
+    const unsigned int slot = mh_upsert_from(table, nslots, item, epoch, mine, home, mh_load_bucket(table, home), &seen);
+    mh_race_first(table, slot, seen, mine);
     slot_of[s] = slot;
   }
 }
 
 // ---- K3: insert the neighbours sampled in this hop -------------------------------------------------------
-// 4 edges per thread, staged so that the dependent memory round trips of the four edges overlap:
-//   A  load the home group of each edge (4 x 4 independent loads)
-//   B  scan the loaded keys (no memory)
-//   C  one optimistic CAS per edge that has to claim a slot (4 in flight)
-//   D  resolve; the rare losers (CAS lost to another key, or a full home group) take the generic probe loop
-//   E  race for the first position: a freshly claimed slot holds a stale (= worst) aux, so the claimer sends
-//      its atomicMin without reading; edges that found their vertex read aux first and usually skip the atomic
-constexpr int kInsertIlp = 4;
+// kInsertIlp edges per thread: the bucket loads of all of them are issued before the first dependent CAS, so
+// the random round trips of the edges overlap.
+constexpr int kInsertIlp = 1;  // measured (profiles/micro/insert_probe.cu): the CAS chains serialise per thread, more warps beat more ILP
 template <typename VT>
 __global__ void __launch_bounds__(256) mh_insert_kernel(MhSlot* table, const unsigned int* __restrict__ nslots_dev,
                                                         unsigned long long epoch, unsigned long long V, unsigned int t,
@@ -170,10 +201,8 @@ __global__ void __launch_bounds__(256) mh_insert_kernel(MhSlot* table, const uns
   for (int base = blockIdx.x * blockDim.x + threadIdx.x; base < n; base += stride * kInsertIlp) {
     int row[kInsertIlp];
     unsigned long long item[kInsertIlp];
-    MhGroupKeys cur[kInsertIlp];
-    unsigned int slot[kInsertIlp];
-    unsigned long long prev[kInsertIlp], expect[kInsertIlp];
-    int state[kInsertIlp];  // 0 found, 1 CAS issued, 2 group full -> slow path, -1 inactive
+    unsigned int home[kInsertIlp];
+    MhBucket cur[kInsertIlp];
 #pragma unroll
     for (int k = 0; k < kInsertIlp; k++) {
       int e  = base + k * stride;
@@ -185,73 +214,23 @@ __global__ void __launch_bounds__(256) mh_insert_kernel(MhSlot* table, const uns
       item[k] = e < n ? (unsigned long long)flabel[row[k]] * V + (unsigned long long)vertices[e] : 0ULL;
     }
 #pragma unroll
-    for (int k = 0; k < kInsertIlp; k++) {  // A
+    for (int k = 0; k < kInsertIlp; k++) {
       int e   = base + k * stride;
-      slot[k] = mh_home(item[k], nslots);
-      if (e < n) cur[k] = mh_load_group(table, slot[k]);
+      home[k] = mh_home(item[k], nslots);
+      if (e < n) cur[k] = mh_load_bucket(table, home[k]);
     }
-#pragma unroll
-    for (int k = 0; k < kInsertIlp; k++) {  // B
-      int e    = base + k * stride;
-      state[k] = -1;
-      if (e < n) {
-        const unsigned long long key = (epoch << 56) | item[k];
-        state[k]                     = 2;
-#pragma unroll
-        for (int j = (int)kGroup - 1; j >= 0; j--) {  // descending: the lowest matching / stale index wins
-          if ((cur[k].k[j] >> 56) != epoch) {
-            state[k]  = 1;
-            expect[k] = cur[k].k[j];
-            prev[k]   = (unsigned long long)j;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < (int)kGroup; j++) {
-          // a match only counts if it sits before the first stale slot (probe order); keys are unique per epoch,
-          // so a match after a stale slot cannot exist
-          if (cur[k].k[j] == key) {
-            state[k] = 0;
-            prev[k]  = (unsigned long long)j;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kInsertIlp; k++) {  // C
-      if (state[k] == 1) {
-        slot[k] += (unsigned int)prev[k];
-        prev[k] = atomicCAS(&table[slot[k]].key, expect[k], (epoch << 56) | item[k]);
-      } else if (state[k] == 0) {
-        slot[k] += (unsigned int)prev[k];
-      }
-    }
-    bool fresh[kInsertIlp];
-#pragma unroll
-    for (int k = 0; k < kInsertIlp; k++) {  // D
-      fresh[k] = false;
-      if (state[k] == 1) {
-        const unsigned long long key = (epoch << 56) | item[k];
-        if (prev[k] == expect[k]) {
-          fresh[k] = true;
-        } else if (prev[k] != key) {
-          unsigned int g = slot[k] & ~(kGroup - 1);
-          slot[k]        = mh_find_or_insert_from(table, nslots, item[k], epoch, g, mh_load_group(table, g));
-        }
-      } else if (state[k] == 2) {
-        unsigned int g = slot[k] + kGroup >= nslots ? 0u : slot[k] + kGroup;
-        slot[k]        = mh_find_or_insert_from(table, nslots, item[k], epoch, g, mh_load_group(table, g));
-      }
-    }
-    unsigned long long aux[kInsertIlp];
-#pragma unroll
-    for (int k = 0; k < kInsertIlp; k++)  // E
-      aux[k] = (state[k] >= 0 && !fresh[k]) ? ld_relaxed_u64(&table[slot[k]].aux) : ~0ULL;
+    unsigned int slot[kInsertIlp];
+    unsigned long long seen[kInsertIlp];
 #pragma unroll
     for (int k = 0; k < kInsertIlp; k++) {
       int e = base + k * stride;
-      if (state[k] >= 0) {
-        const unsigned long long mine = inv_epoch | mh_tag(t, (unsigned int)e);
-        if (aux[k] > mine) atomicMin(&table[slot[k]].aux, mine);
+      if (e < n) slot[k] = mh_upsert_from(table, nslots, item[k], epoch, inv_epoch | mh_tag(t, (unsigned int)e), home[k], cur[k], &seen[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kInsertIlp; k++) {
+      int e = base + k * stride;
+      if (e < n) {
+        mh_race_first(table, slot[k], seen[k], inv_epoch | mh_tag(t, (unsigned int)e));
         slot_of[e] = slot[k];
       }
     }
@@ -259,13 +238,23 @@ __global__ void __launch_bounds__(256) mh_insert_kernel(MhSlot* table, const uns
 }
 
 // ---- K4: flag first occurrences, scan, compact into the next frontier, assign ranks ------------------------
+// The table is only READ here (one random 8-byte access per edge): every edge turns its slot index into a
+// reference to its endpoint, packed step(4) | index(28):
+//   * endpoint numbered in an earlier step t' < t:   t'  | rank          (final)
+//   * endpoint new in this step, first seen at e':    15  | e'            (pending), and rank_of[e'] = its rank
+// Pending references are resolved by the final pass through rank_of (a dense array a few MB large), so neither a
+// random write-back of the ranks into the table nor a second random pass over it is needed; the table itself is
+// re-hashed by the next hop anyway.
+constexpr unsigned int kRefPending = 15u;
+
 template <typename VT, bool SEEDS>
-__global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(MhSlot* table, unsigned long long epoch, unsigned int t,
+__global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(const MhSlot* __restrict__ table, unsigned int t,
                                                                 const VT* __restrict__ vertices,
                                                                 const int* __restrict__ n_dev, int n_host,
                                                                 const int* __restrict__ erow,
                                                                 const int* __restrict__ flabel,
-                                                                const unsigned int* __restrict__ slot_of,
+                                                                unsigned int* __restrict__ slot_to_ref,
+                                                                unsigned int* __restrict__ rank_of,
                                                                 long long* __restrict__ next_frontier,
                                                                 int* __restrict__ next_flabel, int* __restrict__ next_n,
                                                                 unsigned long long* state)
@@ -273,34 +262,45 @@ __global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(MhSlot* table, u
   const int n    = n_dev ? *n_dev : n_host;
   const int tile = blockIdx.x;
   if ((long long)tile * kScanTile > n) return;  // grid is sized from the host-side upper bound
-  const long long base               = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
-  const unsigned long long inv_epoch = (255ULL - epoch) << 56;
+  const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
   unsigned int v[kScanItems];
   unsigned int slot[kScanItems];
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
     long long e = base + k;
-    slot[k]     = e < n ? slot_of[e] : 0u;
+    slot[k]     = e < n ? slot_to_ref[e] : 0u;
   }
+  unsigned long long aux[kScanItems];
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
     long long e = base + k;
-    v[k]        = (e < n && (ld_relaxed_u64(&table[slot[k]].aux) & kAuxMask) == mh_tag(t, (unsigned int)e)) ? 1u : 0u;
+    aux[k]      = e < n ? (ld_relaxed_u64(&table[slot[k]].aux) & kAuxMask) : 0ULL;
   }
   unsigned int flags = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++)
+  for (int k = 0; k < kScanItems; k++) {
+    long long e = base + k;
+    v[k]        = (e < n && aux[k] == mh_tag(t, (unsigned int)e)) ? 1u : 0u;
     flags |= v[k] << k;
+  }
   unsigned int agg          = block_scan_items(v);
   unsigned long long prefix = scan_tile_prefix(state, tile, agg);
 #pragma unroll
   for (int k = 0; k < kScanItems; k++) {
     long long e = base + k;
-    if (e < n && ((flags >> k) & 1u)) {
-      unsigned int rank   = (unsigned int)(prefix + v[k]);
-      next_frontier[rank] = (long long)vertices[e];
-      next_flabel[rank]   = SEEDS ? flabel[e] : flabel[erow[e]];
-      table[slot[k]].aux  = inv_epoch | mh_fin(t, rank);
+    if (e < n) {
+      if ((flags >> k) & 1u) {
+        unsigned int rank   = (unsigned int)(prefix + v[k]);
+        next_frontier[rank] = (long long)vertices[e];
+        next_flabel[rank]   = SEEDS ? flabel[e] : flabel[erow[e]];
+        if (!SEEDS) rank_of[e] = rank;
+      }
+      if (!SEEDS) {
+        // tag(t, e'): bit 0 set, e' in bits 1..32;  fin(t', rank): bit 0 clear
+        const unsigned int idx = (unsigned int)(aux[k] >> 1) & 0x0FFFFFFFu;
+        const unsigned int st  = (aux[k] & 1ULL) ? kRefPending : (unsigned int)(aux[k] >> 33);
+        slot_to_ref[e]         = (st << 28) | idx;
+      }
     }
     if (e == n) *next_n = (int)(prefix + v[k]);
   }
@@ -360,8 +360,9 @@ __global__ void __launch_bounds__(256) mh_reinsert_kernel(MhSlot* table, const u
   for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
     unsigned long long item = (unsigned long long)flabel[f] * V + (unsigned long long)frontier[f];
     unsigned int home       = mh_home(item, nslots);
-    unsigned int slot       = mh_find_or_insert_from(table, nslots, item, epoch, home, mh_load_group(table, home));
-    table[slot].aux         = inv_epoch | mh_fin(t, (unsigned int)f);
+    unsigned long long seen;
+    // (label, vertex) pairs of the frontiers are distinct: always a fresh claim, installed with its final aux
+    mh_upsert_from(table, nslots, item, epoch, inv_epoch | mh_fin(t, (unsigned int)f), home, mh_load_bucket(table, home), &seen);
   }
 }
 
@@ -439,23 +440,12 @@ __global__ void __launch_bounds__(1024) mh_scan3_kernel(MhScan3 a)
   }
 }
 
-// after the hop's first occurrences are ranked: replace every edge's slot index by the (step, rank) of its
-// endpoint, packed step(4) | rank(28).  The table is re-hashed by the next hop, slot indices would dangle.
-__global__ void __launch_bounds__(256) mh_resolve_kernel(const MhSlot* __restrict__ table, const int* __restrict__ n_dev,
-                                                         unsigned int* __restrict__ slot_to_ref)
-{
-  const int n = *n_dev;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const unsigned long long aux = table[slot_to_ref[e]].aux & kAuxMask;
-    slot_to_ref[e]               = ((unsigned int)(aux >> 33) << 28) | ((unsigned int)(aux >> 1) & 0x0FFFFFFFu);
-  }
-}
-
 // ---- final pass -------------------------------------------------------------------------------------------
 struct MhHopBufs {
   const int* off[kMaxHops];
   const int* erow[kMaxHops];
-  const unsigned int* slot[kMaxHops];
+  const unsigned int* slot[kMaxHops];     // per edge: reference to its endpoint, see mh_compact_kernel
+  const unsigned int* rank_of[kMaxHops];  // per edge that is a first occurrence: rank of its endpoint in the next frontier
   const long long* gid[kMaxHops];
 };
 
@@ -477,7 +467,8 @@ __global__ void __launch_bounds__(256) mh_emit_edges_kernel(int L, int B,
   const long long* __restrict__ gid        = hb.gid[h];
   const int* __restrict__ flabel_h         = fr.flabel[h];
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
-    const unsigned int ref       = slot_of[e];  // step(4) | rank(28), see mh_resolve_kernel
+    unsigned int ref             = slot_of[e];  // step(4) | index(28), see mh_compact_kernel
+    if ((ref >> 28) == kRefPending) ref = ((unsigned int)(h + 1) << 28) | hb.rank_of[h][ref & 0x0FFFFFFFu];
     const int f                  = erow[e];
     long long g                  = gid[e];
     const int l                  = flabel_h[f];
@@ -549,10 +540,33 @@ struct wholegraph_multihop_sampler_ {
   int epoch                = 0;  // last epoch handed out (0: table must be initialised)
   Buf slabel, scan_state, small_i32, small_i64, counts, seed_slot;
   Buf frontier[wgb::kMaxHops + 1], flabel[wgb::kMaxHops + 1], fr_off[wgb::kMaxHops + 1];
-  Buf off[wgb::kMaxHops], dest[wgb::kMaxHops], erow[wgb::kMaxHops], gid[wgb::kMaxHops], slot[wgb::kMaxHops];
+  Buf off[wgb::kMaxHops], dest[wgb::kMaxHops], erow[wgb::kMaxHops], gid[wgb::kMaxHops], slot[wgb::kMaxHops], rank_of[wgb::kMaxHops];
   Buf base;
   long long* h_totals = nullptr;  // pinned
   int device          = -1;
+  // a call between _begin and _finish
+  struct Pending {
+    bool active = false;
+    int B = 0, L = 0, flags = 0;
+    bool has_eid = false, chunked = false;
+    wgb::ChunkRef eid;
+    unsigned long long eid_off = 0;
+    long long ub_rows[wgb::kMaxHops + 1];
+    long long ub_edges[wgb::kMaxHops];
+    wgb::MhFrontiers fr;
+    wgb::MhMeta meta;
+    wgb::MhHopBufs hb;
+    long long *lho = nullptr, *rmo = nullptr, *rbase = nullptr;
+    int *base = nullptr, *n_rows_dev = nullptr, *n_edges_dev = nullptr;
+  } pending;
+  cudaEvent_t ready = nullptr;  // recorded after the output sizes have been copied to h_totals
+  // WGB_MH_TIMING=1: per-stage device times (cudaEvents between launches), averaged, printed at destroy
+  bool timing = false;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  size_t marks_used = 0;
+  std::vector<std::pair<std::string, std::pair<double, long long>>> stage_stats;
+  long long timed_calls = 0;
+  int warm_calls        = 0;
 };
 
 namespace wgb {
@@ -580,6 +594,66 @@ static void* ensure(wholegraph_multihop_sampler_::Buf& b, size_t bytes)
   return b.p;
 }
 
+static void mh_mark(wholegraph_multihop_sampler_* sp, const char* name, cudaStream_t st)
+{
+  if (!sp->timing) return;
+  if (sp->marks_used == sp->marks.size()) {
+    cudaEvent_t e;
+    WGB_CUDA_TRY(cudaEventCreate(&e));
+    sp->marks.emplace_back(name, e);
+  }
+  sp->marks[sp->marks_used].first = name;
+  WGB_CUDA_TRY(cudaEventRecord(sp->marks[sp->marks_used].second, st));
+  sp->marks_used++;
+}
+
+static const char* hop_stage(wholegraph_multihop_sampler_* sp, int h, const char* stage)
+{
+  if (!sp->timing) return stage;
+  static std::vector<std::string*> pool;  // leaked on purpose: names must outlive the marks
+  std::string want = "hop" + std::to_string(h) + " " + stage;
+  for (auto* p : pool)
+    if (*p == want) return p->c_str();
+  pool.push_back(new std::string(want));
+  return pool.back()->c_str();
+}
+
+// called when the stream is known to be idle past the last mark
+static void mh_collect_marks(wholegraph_multihop_sampler_* sp)
+{
+  if (!sp->timing || sp->marks_used < 2) return;
+  WGB_CUDA_TRY(cudaEventSynchronize(sp->marks[sp->marks_used - 1].second));
+  if (sp->warm_calls++ < 3) {  // the first calls allocate scratch while the device waits
+    sp->marks_used = 0;
+    return;
+  }
+  for (size_t i = 1; i < sp->marks_used; i++) {
+    float ms = 0.f;
+    WGB_CUDA_TRY(cudaEventElapsedTime(&ms, sp->marks[i - 1].second, sp->marks[i].second));
+    std::string name = sp->marks[i].first;
+    size_t k = 0;
+    for (; k < sp->stage_stats.size(); k++)
+      if (sp->stage_stats[k].first == name) break;
+    if (k == sp->stage_stats.size()) sp->stage_stats.push_back({name, {0.0, 0}});
+    sp->stage_stats[k].second.first += ms;
+    sp->stage_stats[k].second.second++;
+  }
+  sp->timed_calls++;
+  sp->marks_used = 0;
+}
+
+static void mh_print_marks(wholegraph_multihop_sampler_* sp)
+{
+  if (!sp->timing || sp->timed_calls == 0) return;
+  double total = 0;
+  fprintf(stderr, "[wgb multihop] per-call device time by stage, %lld calls\n", sp->timed_calls);
+  for (auto& s : sp->stage_stats) {
+    fprintf(stderr, "  %-28s %9.2f us  (%lld marks)\n", s.first.c_str(), 1e3 * s.second.first / (double)sp->timed_calls, s.second.second);
+    total += s.second.first;
+  }
+  fprintf(stderr, "  %-28s %9.2f us\n", "total", 1e3 * total / (double)sp->timed_calls);
+}
+
 static int grid_over(long long n, int sms) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)sms * 8)); }
 
 struct MhCall {
@@ -595,8 +669,6 @@ struct MhCall {
   unsigned long long V;
   unsigned long long random_state;
   int flags;
-  void *ctx_majors, *ctx_minors, *ctx_edge_id, *ctx_lho, *ctx_map, *ctx_rmo, *ctx_major_offsets, *ctx_step_counts;
-  wholememory_env_func_t* env;
   cudaStream_t stream;
 };
 
@@ -640,9 +712,11 @@ static void launch_hop_sample(const MhCall& c, const long long* frontier, const 
 }
 
 template <typename ColT, bool CHUNKED>
-static void multihop_run(MhCall& c)
+static void multihop_begin(MhCall& c)
 {
   auto* sp        = c.sp;
+  sp->pending.active = false;  // a call that was begun but never finished is abandoned: its scratch is reused below
+  sp->marks_used = 0;
   const int sms   = num_sms();
   const int B     = c.B, L = c.L, S = c.S;
   cudaStream_t st = c.stream;
@@ -717,6 +791,7 @@ static void multihop_run(MhCall& c)
   meta.L = L;
   meta.B = B;
 
+  mh_mark(sp, "start", st);
   // ---- step 0: seeds -> frontier_0 (dedup per label, first occurrence keeps the id) --------------------
   {
     unsigned int nslots0 = (unsigned int)(std::min<unsigned long long>(sp->table_slots, (unsigned long long)S * 2 + 1024) & ~3ULL);
@@ -729,15 +804,16 @@ static void multihop_run(MhCall& c)
     if (c.seed_dtype == WHOLEMEMORY_DT_INT) {
       mh_seed_insert_kernel<int><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const int*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
       WGB_CHECK_LAUNCH();
-      mh_compact_kernel<int, true><<<ss.second, kScanBlock, 0, st>>>(table, epoch, 0u, static_cast<const int*>(c.seeds), nullptr, S, nullptr, slabel, slot0, frontier0, flabel0, n_rows_dev, ss.first);
+      mh_compact_kernel<int, true><<<ss.second, kScanBlock, 0, st>>>(table, 0u, static_cast<const int*>(c.seeds), nullptr, S, nullptr, slabel, slot0, nullptr, frontier0, flabel0, n_rows_dev, ss.first);
     } else {
       mh_seed_insert_kernel<long long><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const long long*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
       WGB_CHECK_LAUNCH();
-      mh_compact_kernel<long long, true><<<ss.second, kScanBlock, 0, st>>>(table, epoch, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, frontier0, flabel0, n_rows_dev, ss.first);
+      mh_compact_kernel<long long, true><<<ss.second, kScanBlock, 0, st>>>(table, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, nullptr, frontier0, flabel0, n_rows_dev, ss.first);
     }
     WGB_CHECK_LAUNCH();
     mh_label_bounds_kernel<<<grid_over(std::max(S, B + 1), sms), 256, 0, st>>>(flabel0, n_rows_dev, B, static_cast<int*>(sp->fr_off[0].p));
     WGB_CHECK_LAUNCH();
+    mh_mark(sp, "seeds", st);
     fr.frontier[0]  = frontier0;
     fr.flabel[0]    = flabel0;
     meta.fr_off[0]  = static_cast<int*>(sp->fr_off[0].p);
@@ -757,6 +833,7 @@ static void multihop_run(MhCall& c)
       auto ss = scan_slice(rows_ub);
       count_scan_kernel<long long, CHUNKED><<<ss.second, kScanBlock, 0, st>>>(c.row_ptr, c.row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, nullptr, n_rows_dev + h, n_edges_dev + h);
       WGB_CHECK_LAUNCH();
+      mh_mark(sp, hop_stage(sp, h, "count+scan"), st);
       meta.off[h] = off;
       if (edges_ub < 0) {
         // take-all hop: the edge count is data dependent -> one extra host sync to size the scratch
@@ -789,11 +866,13 @@ static void multihop_run(MhCall& c)
     int* erow                = static_cast<int*>(ensure(sp->erow[h], sizeof(int) * ecap));
     long long* gid           = static_cast<long long*>(ensure(sp->gid[h], sizeof(long long) * ecap));
     unsigned int* slot       = static_cast<unsigned int*>(ensure(sp->slot[h], sizeof(unsigned int) * ecap));
+    unsigned int* rank_of    = static_cast<unsigned int*>(ensure(sp->rank_of[h], sizeof(unsigned int) * ecap));
     long long* next_frontier = static_cast<long long*>(ensure(sp->frontier[h + 1], sizeof(long long) * ecap));
     int* next_flabel         = static_cast<int*>(ensure(sp->flabel[h + 1], sizeof(int) * ecap));
     hb.off[h]  = off;
     hb.erow[h] = erow;
     hb.slot[h] = slot;
+    hb.rank_of[h] = rank_of;
     hb.gid[h]  = gid;
     if (edges_ub > 0) {
       // new epoch for this hop: pick the slot count on the device, re-insert what is numbered so far
@@ -805,22 +884,25 @@ static void multihop_run(MhCall& c)
         max_rows = std::max(max_rows, ub_rows[t]);
       mh_reinsert_kernel<<<dim3(grid_over(max_rows, sms), h + 1), 256, 0, st>>>(table, nslots_dev + h + 1, epoch, c.V, fr, n_rows_dev);
       WGB_CHECK_LAUNCH();
+      mh_mark(sp, hop_stage(sp, h, "plan+reinsert"), st);
       // K2: sample
       launch_hop_sample<ColT, CHUNKED>(c, frontier, n_rows_dev + h, rows_ub, M, c.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL, off, dest, erow, gid);
+      mh_mark(sp, hop_stage(sp, h, "sample"), st);
       // K3: insert (label, neighbour)
-      mh_insert_kernel<ColT><<<grid_over((edges_ub + kInsertIlp - 1) / kInsertIlp, sms), 256, 0, st>>>(table, nslots_dev + h + 1, epoch, c.V, (unsigned int)(h + 1), dest, n_edges_dev + h, erow, flabel, slot);
+      mh_insert_kernel<ColT><<<std::max(1, (int)std::min<long long>((edges_ub + 255) / 256, (long long)sms * 16)), 256, 0, st>>>(table, nslots_dev + h + 1, epoch, c.V, (unsigned int)(h + 1), dest, n_edges_dev + h, erow, flabel, slot);
       WGB_CHECK_LAUNCH();
+      mh_mark(sp, hop_stage(sp, h, "insert"), st);
       // K4: first occurrences -> next frontier
       auto ss = scan_slice(edges_ub);
-      mh_compact_kernel<ColT, false><<<ss.second, kScanBlock, 0, st>>>(table, epoch, (unsigned int)(h + 1), dest, n_edges_dev + h, 0, erow, flabel, slot, next_frontier, next_flabel, n_rows_dev + h + 1, ss.first);
+      mh_compact_kernel<ColT, false><<<ss.second, kScanBlock, 0, st>>>(table, (unsigned int)(h + 1), dest, n_edges_dev + h, 0, erow, flabel, slot, rank_of, next_frontier, next_flabel, n_rows_dev + h + 1, ss.first);
       WGB_CHECK_LAUNCH();
-      mh_resolve_kernel<<<grid_over(edges_ub, sms), 256, 0, st>>>(table, n_edges_dev + h, slot);
-      WGB_CHECK_LAUNCH();
+      mh_mark(sp, hop_stage(sp, h, "compact"), st);
     } else {
       WGB_CUDA_TRY(cudaMemsetAsync(n_rows_dev + h + 1, 0, sizeof(int), st));
     }
     mh_label_bounds_kernel<<<grid_over(std::max<long long>(edges_ub, B + 1), sms), 256, 0, st>>>(next_flabel, n_rows_dev + h + 1, B, static_cast<int*>(sp->fr_off[h + 1].p));
     WGB_CHECK_LAUNCH();
+    mh_mark(sp, hop_stage(sp, h, "label bounds"), st);
     fr.frontier[h + 1] = next_frontier;
     fr.flabel[h + 1]   = next_flabel;
     meta.fr_off[h + 1] = static_cast<int*>(sp->fr_off[h + 1].p);
@@ -844,30 +926,67 @@ static void multihop_run(MhCall& c)
   sc.totals = totals;
   mh_scan3_kernel<<<3, 1024, 0, st>>>(sc);
   WGB_CHECK_LAUNCH();
-  // ---- the one host sync of the call: output sizes ------------------------------------------------------------
+  // ---- output sizes travel to pinned memory; _finish waits for `ready`, not for the stream ----------------------
   WGB_CUDA_TRY(cudaMemcpyAsync(sp->h_totals, totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
-  WGB_CUDA_TRY(cudaStreamSynchronize(st));
+  WGB_CUDA_TRY(cudaEventRecord(sp->ready, st));
+  mh_mark(sp, "meta+scan3", st);
+  auto& pd = sp->pending;
+  pd.B = B; pd.L = L; pd.flags = c.flags; pd.has_eid = c.has_eid; pd.chunked = CHUNKED;
+  pd.eid = c.eid; pd.eid_off = c.eid_off;
+  for (int t = 0; t <= L; t++) pd.ub_rows[t] = ub_rows[t];
+  for (int h = 0; h < L; h++) pd.ub_edges[h] = ub_edges[h];
+  pd.fr = fr; pd.meta = meta; pd.hb = hb;
+  pd.lho = lho; pd.rmo = rmo; pd.rbase = rbase; pd.base = base;
+  pd.n_rows_dev = n_rows_dev; pd.n_edges_dev = n_edges_dev;
+  pd.active = true;
+}
+
+struct MhOutCtx {
+  void *majors, *minors, *edge_id, *lho, *map, *rmo, *major_offsets, *step_counts;
+  wholememory_env_func_t* env;
+  cudaStream_t stream;
+};
+
+// second half of a call: wait for the sizes, allocate the outputs, scatter scratch -> outputs
+static void multihop_finish(wholegraph_multihop_sampler_* sp, const MhOutCtx& c)
+{
+  WGB_EXPECTS(sp->pending.active, "no call in flight on this sampler object");
+  auto& pd        = sp->pending;
+  pd.active       = false;
+  const int sms   = num_sms();
+  const int B = pd.B, L = pd.L;
+  cudaStream_t st = c.stream;
+  const MhFrontiers& fr = pd.fr;
+  const MhMeta& meta    = pd.meta;
+  const MhHopBufs& hb   = pd.hb;
+  long long *lho = pd.lho, *rmo = pd.rmo, *rbase = pd.rbase;
+  int *base = pd.base, *n_rows_dev = pd.n_rows_dev, *n_edges_dev = pd.n_edges_dev;
+  const long long* ub_rows  = pd.ub_rows;
+  const long long* ub_edges = pd.ub_edges;
+  // ---- the one host wait of the call ------------------------------------------------------------------------------
+  WGB_CUDA_TRY(cudaEventSynchronize(sp->ready));
+  WGB_CUDA_TRY(cudaStreamWaitEvent(st, sp->ready, 0));  // no-op on the stream the call was begun on
   const long long n_edges = sp->h_totals[0], n_nodes = sp->h_totals[1], n_srcrows = sp->h_totals[2];
 
-  const bool csr    = (c.flags & WHOLEGRAPH_MULTIHOP_CSR) != 0;
-  const bool idx64  = (c.flags & WHOLEGRAPH_MULTIHOP_INT64_IDS) != 0;
+  const bool csr    = (pd.flags & WHOLEGRAPH_MULTIHOP_CSR) != 0;
+  const bool idx64  = (pd.flags & WHOLEGRAPH_MULTIHOP_INT64_IDS) != 0;
   const wholememory_dtype_t idx_dt = idx64 ? WHOLEMEMORY_DT_INT64 : WHOLEMEMORY_DT_INT;
-  void* out_minors   = output_alloc(c.env, c.ctx_minors, n_edges, idx_dt);
-  void* out_majors   = (!csr && c.ctx_majors) ? output_alloc(c.env, c.ctx_majors, n_edges, idx_dt) : nullptr;
-  long long* out_eid = static_cast<long long*>(output_alloc(c.env, c.ctx_edge_id, n_edges, WHOLEMEMORY_DT_INT64));
-  long long* out_lho = static_cast<long long*>(output_alloc(c.env, c.ctx_lho, (long long)B * L + 1, WHOLEMEMORY_DT_INT64));
-  long long* out_map = static_cast<long long*>(output_alloc(c.env, c.ctx_map, n_nodes, WHOLEMEMORY_DT_INT64));
-  long long* out_rmo = static_cast<long long*>(output_alloc(c.env, c.ctx_rmo, B + 1, WHOLEMEMORY_DT_INT64));
+  void* out_minors   = output_alloc(c.env, c.minors, n_edges, idx_dt);
+  void* out_majors   = (!csr && c.majors) ? output_alloc(c.env, c.majors, n_edges, idx_dt) : nullptr;
+  long long* out_eid = static_cast<long long*>(output_alloc(c.env, c.edge_id, n_edges, WHOLEMEMORY_DT_INT64));
+  long long* out_lho = static_cast<long long*>(output_alloc(c.env, c.lho, (long long)B * L + 1, WHOLEMEMORY_DT_INT64));
+  long long* out_map = static_cast<long long*>(output_alloc(c.env, c.map, n_nodes, WHOLEMEMORY_DT_INT64));
+  long long* out_rmo = static_cast<long long*>(output_alloc(c.env, c.rmo, B + 1, WHOLEMEMORY_DT_INT64));
   long long* out_moff = nullptr;
   if (csr) {
-    WGB_EXPECTS(c.ctx_major_offsets != nullptr, "CSR compression needs a major_offsets output context");
-    out_moff = static_cast<long long*>(output_alloc(c.env, c.ctx_major_offsets, n_srcrows + 1, WHOLEMEMORY_DT_INT64));
+    WGB_EXPECTS(c.major_offsets != nullptr, "CSR compression needs a major_offsets output context");
+    out_moff = static_cast<long long*>(output_alloc(c.env, c.major_offsets, n_srcrows + 1, WHOLEMEMORY_DT_INT64));
   }
-  if (c.ctx_step_counts) {
+  if (c.step_counts) {
     // vertices label l discovered at step t (t = 0: its seeds): base[(t+1)*B + l] - base[t*B + l]; handed out as
     // the [L+1, B] table of first local ids plus the per-label totals so that readers never have to reduce
     // over the edge arrays (the reference's decoders do, with a host sync per hop: sampler.py:570-575)
-    int* out_sc = static_cast<int*>(output_alloc(c.env, c.ctx_step_counts, (long long)(L + 1) * B, WHOLEMEMORY_DT_INT));
+    int* out_sc = static_cast<int*>(output_alloc(c.env, c.step_counts, (long long)(L + 1) * B, WHOLEMEMORY_DT_INT));
     WGB_CUDA_TRY(cudaMemcpyAsync(out_sc, base, sizeof(int) * (size_t)(L + 1) * (size_t)B, cudaMemcpyDeviceToDevice, st));
   }
   WGB_CUDA_TRY(cudaMemcpyAsync(out_rmo, rmo, sizeof(long long) * (size_t)(B + 1), cudaMemcpyDeviceToDevice, st));
@@ -886,16 +1005,26 @@ static void multihop_run(MhCall& c)
   if (n_edges > 0 && max_edges > 0) {
     // tighter than the upper bound: no hop has more edges than the call has in total
     dim3 grid(grid_over(std::min(max_edges, n_edges), sms), L);
-    if (idx64)
-      mh_emit_edges_kernel<long long, CHUNKED><<<grid, 256, 0, st>>>(L, B, n_edges_dev, hb, fr, meta, base, lho, c.eid, c.eid_off, c.has_eid, static_cast<long long*>(out_majors), static_cast<long long*>(out_minors), out_eid);
-    else
-      mh_emit_edges_kernel<int, CHUNKED><<<grid, 256, 0, st>>>(L, B, n_edges_dev, hb, fr, meta, base, lho, c.eid, c.eid_off, c.has_eid, static_cast<int*>(out_majors), static_cast<int*>(out_minors), out_eid);
+    auto emit = [&](auto out_tag, auto chunk_tag) {
+      using OutT                = decltype(out_tag);
+      constexpr bool kChunkedId = decltype(chunk_tag)::value;
+      mh_emit_edges_kernel<OutT, kChunkedId><<<grid, 256, 0, st>>>(L, B, n_edges_dev, hb, fr, meta, base, lho, pd.eid, pd.eid_off, pd.has_eid, static_cast<OutT*>(out_majors), static_cast<OutT*>(out_minors), out_eid);
+    };
+    if (idx64) {
+      if (pd.chunked) emit((long long)0, std::true_type{});
+      else emit((long long)0, std::false_type{});
+    } else {
+      if (pd.chunked) emit((int)0, std::true_type{});
+      else emit((int)0, std::false_type{});
+    }
     WGB_CHECK_LAUNCH();
   }
   if (n_nodes > 0) {
     mh_emit_rows_kernel<<<dim3(grid_over(std::min(max_rows, n_nodes), sms), L + 1), 256, 0, st>>>(L, B, n_rows_dev, fr, meta, base, rmo, lho, rbase, out_map, out_moff);
     WGB_CHECK_LAUNCH();
   }
+  mh_mark(sp, "emit", st);
+  mh_collect_marks(sp);
 }
 
 }  // namespace wgb
@@ -909,6 +1038,9 @@ wholememory_error_code_t wholegraph_create_multihop_sampler(wholegraph_multihop_
     auto* s = new wholegraph_multihop_sampler_();
     WGB_CUDA_TRY(cudaGetDevice(&s->device));
     WGB_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&s->h_totals), 8 * sizeof(long long)));
+    WGB_CUDA_TRY(cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
+    const char* t = getenv("WGB_MH_TIMING");
+    s->timing     = t && atoi(t) > 0;
     *sampler = s;
   });
 }
@@ -926,27 +1058,27 @@ wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop
     drop(s->frontier[i]); drop(s->flabel[i]); drop(s->fr_off[i]);
   }
   for (int i = 0; i < wgb::kMaxHops; i++) {
-    drop(s->off[i]); drop(s->dest[i]); drop(s->erow[i]); drop(s->gid[i]); drop(s->slot[i]);
+    drop(s->off[i]); drop(s->dest[i]); drop(s->erow[i]); drop(s->gid[i]); drop(s->slot[i]); drop(s->rank_of[i]);
   }
   if (s->h_totals) cudaFreeHost(s->h_totals);
+  if (s->ready) cudaEventDestroy(s->ready);
+  wgb::mh_print_marks(s);
+  for (auto& m : s->marks)
+    cudaEventDestroy(m.second);
   cudaGetLastError();
   delete s;
   return WHOLEMEMORY_SUCCESS;
 }
 
-wholememory_error_code_t wholegraph_multihop_neighbor_sample(
+wholememory_error_code_t wholegraph_multihop_neighbor_sample_begin(
   wholegraph_multihop_sampler_t sampler, wholememory_tensor_t csr_row_ptr, wholememory_tensor_t csr_col,
   wholememory_tensor_t csr_weight, wholememory_tensor_t csr_edge_id, wholememory_tensor_t seeds,
   wholememory_tensor_t label_offsets, const int* fanout, int num_hops, unsigned long long random_state, int flags,
-  void* out_majors_ctx, void* out_minors_ctx, void* out_edge_id_ctx, void* out_label_hop_offsets_ctx,
-  void* out_renumber_map_ctx, void* out_renumber_map_offsets_ctx, void* out_major_offsets_ctx,
-  void* out_label_step_base_ctx,
-  wholememory_env_func_t* p_env_fns, void* stream)
+  void* stream)
 {
   using namespace wgb;
-  if (!sampler || !csr_row_ptr || !csr_col || !seeds || !label_offsets || !fanout || !p_env_fns) return WHOLEMEMORY_INVALID_INPUT;
+  if (!sampler || !csr_row_ptr || !csr_col || !seeds || !label_offsets || !fanout) return WHOLEMEMORY_INVALID_INPUT;
   if (num_hops < 1 || num_hops >= kMaxHops - 1) return WHOLEMEMORY_INVALID_INPUT;
-  if (!out_minors_ctx || !out_edge_id_ctx || !out_label_hop_offsets_ctx || !out_renumber_map_ctx || !out_renumber_map_offsets_ctx) return WHOLEMEMORY_INVALID_INPUT;
   auto* rd = wholememory_tensor_get_tensor_description(csr_row_ptr);
   auto* cd = wholememory_tensor_get_tensor_description(csr_col);
   auto* sd = wholememory_tensor_get_tensor_description(seeds);
@@ -966,7 +1098,7 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample(
     auto* ed = wholememory_tensor_get_tensor_description(csr_edge_id);
     if (ed->dim != 1 || ed->sizes[0] != cd->sizes[0] || ed->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
   }
-  return guarded("wholegraph_multihop_neighbor_sample", [&] {
+  return guarded("wholegraph_multihop_neighbor_sample_begin", [&] {
     WGB_EXPECTS(sd->sizes[0] < (1LL << 31) - kScanTile, "too many seeds for one call");
     WGB_EXPECTS(ld->sizes[0] - 1 < (1LL << 23), "too many labels for one call");
     MhCall c;
@@ -1005,24 +1137,58 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample(
     WGB_EXPECTS((long double)c.V * (long double)std::max(c.B, 1) < 72057594037927936.0L, "labels x vertices must stay below 2^56");
     c.random_state      = random_state;
     c.flags             = flags;
-    c.ctx_majors        = out_majors_ctx;
-    c.ctx_minors        = out_minors_ctx;
-    c.ctx_edge_id       = out_edge_id_ctx;
-    c.ctx_lho           = out_label_hop_offsets_ctx;
-    c.ctx_map           = out_renumber_map_ctx;
-    c.ctx_rmo           = out_renumber_map_offsets_ctx;
-    c.ctx_major_offsets = out_major_offsets_ctx;
-    c.ctx_step_counts   = out_label_step_base_ctx;
-    c.env               = p_env_fns;
     c.stream            = as_stream(stream);
     if (cd->dtype == WHOLEMEMORY_DT_INT) {
-      if (c.chunked) multihop_run<int, true>(c);
-      else multihop_run<int, false>(c);
+      if (c.chunked) multihop_begin<int, true>(c);
+      else multihop_begin<int, false>(c);
     } else {
-      if (c.chunked) multihop_run<long long, true>(c);
-      else multihop_run<long long, false>(c);
+      if (c.chunked) multihop_begin<long long, true>(c);
+      else multihop_begin<long long, false>(c);
     }
   });
+}
+
+wholememory_error_code_t wholegraph_multihop_neighbor_sample_finish(
+  wholegraph_multihop_sampler_t sampler, void* out_majors_ctx, void* out_minors_ctx, void* out_edge_id_ctx,
+  void* out_label_hop_offsets_ctx, void* out_renumber_map_ctx, void* out_renumber_map_offsets_ctx,
+  void* out_major_offsets_ctx, void* out_label_step_base_ctx, wholememory_env_func_t* p_env_fns, void* stream)
+{
+  using namespace wgb;
+  if (!sampler || !p_env_fns) return WHOLEMEMORY_INVALID_INPUT;
+  if (!out_minors_ctx || !out_edge_id_ctx || !out_label_hop_offsets_ctx || !out_renumber_map_ctx || !out_renumber_map_offsets_ctx) return WHOLEMEMORY_INVALID_INPUT;
+  return guarded("wholegraph_multihop_neighbor_sample_finish", [&] {
+    MhOutCtx o;
+    o.majors        = out_majors_ctx;
+    o.minors        = out_minors_ctx;
+    o.edge_id       = out_edge_id_ctx;
+    o.lho           = out_label_hop_offsets_ctx;
+    o.map           = out_renumber_map_ctx;
+    o.rmo           = out_renumber_map_offsets_ctx;
+    o.major_offsets = out_major_offsets_ctx;
+    o.step_counts   = out_label_step_base_ctx;
+    o.env           = p_env_fns;
+    o.stream        = as_stream(stream);
+    multihop_finish(sampler, o);
+  });
+}
+
+wholememory_error_code_t wholegraph_multihop_neighbor_sample(
+  wholegraph_multihop_sampler_t sampler, wholememory_tensor_t csr_row_ptr, wholememory_tensor_t csr_col,
+  wholememory_tensor_t csr_weight, wholememory_tensor_t csr_edge_id, wholememory_tensor_t seeds,
+  wholememory_tensor_t label_offsets, const int* fanout, int num_hops, unsigned long long random_state, int flags,
+  void* out_majors_ctx, void* out_minors_ctx, void* out_edge_id_ctx, void* out_label_hop_offsets_ctx,
+  void* out_renumber_map_ctx, void* out_renumber_map_offsets_ctx, void* out_major_offsets_ctx,
+  void* out_label_step_base_ctx,
+  wholememory_env_func_t* p_env_fns, void* stream)
+{
+  if (!p_env_fns) return WHOLEMEMORY_INVALID_INPUT;
+  if (!out_minors_ctx || !out_edge_id_ctx || !out_label_hop_offsets_ctx || !out_renumber_map_ctx || !out_renumber_map_offsets_ctx) return WHOLEMEMORY_INVALID_INPUT;
+  wholememory_error_code_t e = wholegraph_multihop_neighbor_sample_begin(sampler, csr_row_ptr, csr_col, csr_weight, csr_edge_id, seeds,
+                                                                         label_offsets, fanout, num_hops, random_state, flags, stream);
+  if (e != WHOLEMEMORY_SUCCESS) return e;
+  return wholegraph_multihop_neighbor_sample_finish(sampler, out_majors_ctx, out_minors_ctx, out_edge_id_ctx, out_label_hop_offsets_ctx,
+                                                    out_renumber_map_ctx, out_renumber_map_offsets_ctx, out_major_offsets_ctx,
+                                                    out_label_step_base_ctx, p_env_fns, stream);
 }
 
 }  // extern "C"

@@ -23,10 +23,16 @@ _create.argtypes = [ctypes.POINTER(_vp)]
 _destroy = wmb.native_symbol("wholegraph_destroy_multihop_sampler")
 _destroy.restype = ctypes.c_int
 _destroy.argtypes = [_vp]
-_sample = wmb.native_symbol("wholegraph_multihop_neighbor_sample")
-_sample.restype = ctypes.c_int
-_sample.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_ulonglong,
-                    ctypes.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+_begin = wmb.native_symbol("wholegraph_multihop_neighbor_sample_begin")
+_begin.restype = ctypes.c_int
+_begin.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_ulonglong,
+                   ctypes.c_int, _vp]
+_finish = wmb.native_symbol("wholegraph_multihop_neighbor_sample_finish")
+_finish.restype = ctypes.c_int
+_finish.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+
+_OUT_NAMES = ("majors", "minors", "edge_id", "label_hop_offsets", "renumber_map", "renumber_map_offsets", "major_offsets",
+              "label_step_base")
 
 
 def _handle(t):
@@ -54,19 +60,17 @@ class MultiHopSampler(object):
             _destroy(self._h)
             self._h = None
 
-    def sample(self, csr_row_ptr, csr_col, seeds: "torch.Tensor", label_offsets: "torch.Tensor", fanout: List[int],
-               random_state: int, *, csr_weight=None, csr_edge_id=None, compression: str = "COO",
-               int64_ids: bool = False):
-        """Returns a dict with majors|major_offsets, minors, edge_id, label_hop_offsets, renumber_map,
-        renumber_map_offsets (all CUDA tensors)."""
+    def sample_async(self, csr_row_ptr, csr_col, seeds: "torch.Tensor", label_offsets: "torch.Tensor", fanout: List[int],
+                     random_state: int, *, csr_weight=None, csr_edge_id=None, compression: str = "COO",
+                     int64_ids: bool = False) -> "PendingSample":
+        """Enqueues every hop on the current stream and returns at once; ``.result()`` of the returned object waits
+        for the output sizes only and yields the dict ``sample`` returns.  One call may be pending per sampler
+        object -- loaders alternate between two objects to keep the device busy (cugraph_pyg.sampler)."""
         assert seeds.is_cuda and seeds.dim() == 1 and seeds.dtype in (torch.int32, torch.int64)
         label_offsets = label_offsets.to(device=seeds.device, dtype=torch.int64)
         assert compression in ("COO", "CSR")
         csr = compression == "CSR"
         flags = (FLAG_CSR if csr else 0) | (FLAG_INT64_IDS if int64_ids else 0)
-        names = ["majors", "minors", "edge_id", "label_hop_offsets", "renumber_map", "renumber_map_offsets", "major_offsets",
-                 "label_step_base"]
-        ctx = {n: TorchMemoryContext() for n in names}
         keep = []
         handles = []
         for t in (csr_row_ptr, csr_col, csr_weight, csr_edge_id, seeds, label_offsets):
@@ -74,8 +78,37 @@ class MultiHopSampler(object):
             handles.append(h)
             keep.append(k)
         fan = (ctypes.c_int * len(fanout))(*[int(f) for f in fanout])
-        err = _sample(
-            self._h, *handles, fan, len(fanout), ctypes.c_ulonglong(random_state & 0xFFFFFFFFFFFFFFFF), flags,
+        err = _begin(self._h, *handles, fan, len(fanout), ctypes.c_ulonglong(random_state & 0xFFFFFFFFFFFFFFFF), flags,
+                     get_stream())
+        wmb.check_wholememory_error_code(err)
+        return PendingSample(self, keep, csr, len(fanout))
+
+    def sample(self, csr_row_ptr, csr_col, seeds: "torch.Tensor", label_offsets: "torch.Tensor", fanout: List[int],
+               random_state: int, *, csr_weight=None, csr_edge_id=None, compression: str = "COO",
+               int64_ids: bool = False):
+        """Returns a dict with majors|major_offsets, minors, edge_id, label_hop_offsets, renumber_map,
+        renumber_map_offsets, label_step_base (all CUDA tensors)."""
+        return self.sample_async(csr_row_ptr, csr_col, seeds, label_offsets, fanout, random_state, csr_weight=csr_weight,
+                                 csr_edge_id=csr_edge_id, compression=compression, int64_ids=int64_ids).result()
+
+
+class PendingSample(object):
+    """A call group whose hops are running on the device (MultiHopSampler.sample_async)."""
+
+    def __init__(self, sampler: MultiHopSampler, keep, csr: bool, hops: int):
+        self._sampler = sampler
+        self._keep = keep  # inputs stay alive until the outputs exist
+        self._csr = csr
+        self._hops = hops
+        self._out = None
+
+    def result(self):
+        if self._out is not None:
+            return self._out
+        ctx = {n: TorchMemoryContext() for n in _OUT_NAMES}
+        csr = self._csr
+        err = _finish(
+            self._sampler._h,
             None if csr else ctx["majors"].get_c_context(), ctx["minors"].get_c_context(), ctx["edge_id"].get_c_context(),
             ctx["label_hop_offsets"].get_c_context(), ctx["renumber_map"].get_c_context(),
             ctx["renumber_map_offsets"].get_c_context(), ctx["major_offsets"].get_c_context() if csr else None,
@@ -83,9 +116,11 @@ class MultiHopSampler(object):
             get_wholegraph_env_fns(), get_stream(),
         )
         wmb.check_wholememory_error_code(err)
-        out = {n: ctx[n].get_tensor() for n in names if ctx[n].get_tensor() is not None}
+        out = {n: ctx[n].get_tensor() for n in _OUT_NAMES if ctx[n].get_tensor() is not None}
         # [L+1, B]: first local id of the vertices each label discovered at step t (0 = seeds)
-        out["label_step_base"] = out["label_step_base"].view(len(fanout) + 1, -1)
+        out["label_step_base"] = out["label_step_base"].view(self._hops + 1, -1)
+        self._out = out
+        self._keep = None
         return out
 
 

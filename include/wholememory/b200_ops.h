@@ -82,6 +82,39 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample(wholegraph_multihop
                                                              wholememory_env_func_t* p_env_fns,
                                                              void* stream);
 
+/* The same call in two halves, so that a loader can keep the GPU busy across call groups:
+ *   _begin   enqueues every hop on `stream` and returns without waiting for the device;
+ *   _finish  waits until the output sizes have reached the host (an event recorded by _begin, NOT the whole
+ *            stream), allocates the outputs through the callbacks and enqueues the final scatter on `stream`.
+ * Work enqueued between the two (e.g. _begin of the next call group on another sampler object, or the feature
+ * gather of the previous one) overlaps the host wait.  One call may be in flight per sampler object; the graph
+ * tensors must stay alive until _finish returns, seeds/label_offsets until the stream has run _begin's kernels
+ * (stream-ordered frees, such as torch's caching allocator on the same stream, are fine). */
+wholememory_error_code_t wholegraph_multihop_neighbor_sample_begin(wholegraph_multihop_sampler_t sampler,
+                                                                   wholememory_tensor_t csr_row_ptr,
+                                                                   wholememory_tensor_t csr_col,
+                                                                   wholememory_tensor_t csr_weight,
+                                                                   wholememory_tensor_t csr_edge_id,
+                                                                   wholememory_tensor_t seeds,
+                                                                   wholememory_tensor_t label_offsets,
+                                                                   const int* fanout,
+                                                                   int num_hops,
+                                                                   unsigned long long random_state,
+                                                                   int flags,
+                                                                   void* stream);
+
+wholememory_error_code_t wholegraph_multihop_neighbor_sample_finish(wholegraph_multihop_sampler_t sampler,
+                                                                    void* out_majors_ctx,
+                                                                    void* out_minors_ctx,
+                                                                    void* out_edge_id_ctx,
+                                                                    void* out_label_hop_offsets_ctx,
+                                                                    void* out_renumber_map_ctx,
+                                                                    void* out_renumber_map_offsets_ctx,
+                                                                    void* out_major_offsets_ctx,
+                                                                    void* out_label_step_base_ctx,
+                                                                    wholememory_env_func_t* p_env_fns,
+                                                                    void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * A1: CSR neighbourhood aggregation of the sampled block (the SpMM that consumes the sampler output).
  *

@@ -234,3 +234,37 @@ def test_multihop_c1_karate_and_large_properties(env, oracle):
         h0 = lho[2 * b + 1]
         assert mj[a:h0].max() < per and (mj[h0:e].min() >= per if e > h0 else True)
         assert mn[a:e].max() + 1 == len(mm)
+
+
+def test_multihop_async_two_samplers_interleaved(env, oracle):
+    """sample_async on two sampler objects, begun back to back and finished out of phase (the loader's software
+    pipeline), gives exactly the synchronous results; an abandoned pending call does not poison the object."""
+    import torch
+
+    wgth, comm, sampler = env
+    other = wgth.MultiHopSampler()
+    row_ptr, col = random_csr(4001, 52000, seed=21)
+    wm_rp, wm_col = _wm(wgth, comm, row_ptr), _wm(wgth, comm, col)
+    calls = []
+    rng = np.random.default_rng(5)
+    for k in range(6):
+        seeds, lo = _labels(rng, 4001, [40, 17, 0, 90])
+        calls.append((seeds, lo, 700 + k))
+    objs = [sampler, other]
+    pend = objs[0].sample_async(wm_rp, wm_col, torch.from_numpy(calls[0][0]).cuda(), torch.from_numpy(calls[0][1]).cuda(), [7, 5], calls[0][2])
+    for k in range(6):
+        nxt = None
+        if k + 1 < 6:
+            s, l, seed = calls[k + 1]
+            nxt = objs[(k + 1) & 1].sample_async(wm_rp, wm_col, torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda(), [7, 5], seed)
+        got = pend.result()
+        assert pend.result() is got  # idempotent
+        _assert_equal_coo(got, oracle.multihop_sample(row_ptr, col, calls[k][0], calls[k][1], [7, 5], calls[k][2]))
+        pend = nxt
+    # abandoned call, then a normal one on the same object
+    s, l, seed = calls[0]
+    other.sample_async(wm_rp, wm_col, torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda(), [7, 5], seed)
+    got = other.sample(wm_rp, wm_col, torch.from_numpy(s).cuda(), torch.from_numpy(l).cuda(), [7, 5], seed, compression="CSR")
+    exp = oracle.multihop_sample(row_ptr, col, s, l, [7, 5], seed)
+    assert np.array_equal(got["renumber_map"].cpu().numpy(), exp["renumber_map"])
+    assert np.array_equal(got["minors"].cpu().numpy(), exp["minors"])
