@@ -23,6 +23,7 @@ cpp/bench/wholememory_ops/gather_scatter_bench.cu:352-355), stages (per-stage de
 (dominant kernel = the gather), cpu_baseline (the oracle on the host cores, bounded sample).
 """
 import argparse
+import contextlib
 import ctypes
 import json
 import os
@@ -217,16 +218,21 @@ def run_ours(args):
         sd = host_seeds[k].to(dev, non_blocking=True)  # H2D of the step's input, from pinned memory
         return samplers[k & 1].sample_async(wm_rp, wm_col, sd, label_offsets, FANOUT, SAMPLER_SEED + 7 * k)
 
+    side = torch.cuda.Stream(device=dev) if args.gather_stream else None
+
     def e2e_end(pending):
         res = pending.result()
-        x = emb.gather(res["renumber_map"])
-        first = x.index_select(0, res["renumber_map_offsets"][:-1])  # [labels, F]
-        metric = torch.cat([res["label_hop_offsets"].double(), res["renumber_map_offsets"].double(), first.double().reshape(-1)])
-        host = torch.empty(metric.shape, dtype=metric.dtype, pin_memory=True)
-        host.copy_(metric, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
-        return int(res["minors"].numel()), host, ev
+        if side is not None:  # feature fetch on its own stream: overlaps the next call group's sampling kernels
+            side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            x = emb.gather(res["renumber_map"])
+            first = x.index_select(0, res["renumber_map_offsets"][:-1])  # [labels, F]
+            metric = torch.cat([res["label_hop_offsets"].double(), res["renumber_map_offsets"].double(), first.double().reshape(-1)])
+            host = torch.empty(metric.shape, dtype=metric.dtype, pin_memory=True)
+            host.copy_(metric, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        return int(res["minors"].numel()), (host, res, x), ev
 
     def e2e_loop(first_k, n):
         """n call groups, one sampler call in flight ahead of the gather; returns (edges, d2h bytes per step)."""
@@ -241,12 +247,12 @@ def run_ours(args):
             if len(done) > 1:  # read the previous step's result on the host while this one runs
                 h0, ev0 = done.pop(0)
                 ev0.synchronize()
-                nbytes = h0.numel() * 8
-                assert h0[0] == 0.0
+                nbytes = h0[0].numel() * 8
+                assert h0[0][0] == 0.0
             pend = nxt
         for h0, ev0 in done:
             ev0.synchronize()
-            nbytes = h0.numel() * 8
+            nbytes = h0[0].numel() * 8
         return edges, nbytes
 
     dev_seeds = [s.to(dev) for s in host_seeds]
@@ -308,6 +314,14 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         row_bytes = FEAT_DIM * 4
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes of the gather kernel from the committed ncu --set full capture, scaled to this run's rows per launch
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r1_gather_traffic.json")))
+            per_row = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["rows_in_launch"]
+            traffic = per_row * (tot_nodes / world / args.steps)
+            traffic_src = "ncu dram__bytes_read+write per row (%s) x rows per launch of this run" % cap["source"]
+        except Exception:
+            pass
         rows_per_rank = tot_nodes / world
         gather_alg_bytes = (2 * row_bytes + 8) * rows_per_rank  # per rank, all steps
         gather_achieved = gather_alg_bytes / (gather_ms * 1e-3) / 1e9
@@ -340,7 +354,8 @@ def run_ours(args):
                 "sample_stage_alg_gbs": sample_alg_bytes / (sample_ms * 1e-3) / 1e9,
             },
             "roofline": {"kernel": "rows_copy_kernel (feature gather)", "bound": "hbm", "achieved": gather_achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": gather_achieved / hbm_peak, "traffic": None, "peak_source": peak_src},
+                         "unit": "GB/s", "frac": gather_achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": gather_alg_bytes / args.steps, "peak_source": peak_src},
             "e2e": {"value": e2e_edges / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": labels * BATCH * 8, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
@@ -434,6 +449,7 @@ def main():
     ap.add_argument("--labels", type=int, default=LABELS_PER_STEP)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather-stream", type=int, default=0, help="e2e: run the feature gather on a second stream (1) or in line (0)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

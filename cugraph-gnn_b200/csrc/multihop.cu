@@ -247,6 +247,12 @@ __global__ void __launch_bounds__(256) mh_insert_kernel(MhSlot* table, const uns
 // re-hashed by the next hop anyway.
 constexpr unsigned int kRefPending = 15u;
 
+// Striped arrangement: item k of thread x is edge tile_base + k * 256 + x, so every global access of a warp is
+// coalesced (a blocked arrangement makes lanes stride by 4 * items bytes).  Flags are single bits, so the
+// tile-wide exclusive scan is ballots + popcounts per (stripe, warp) and ONE 64-entry scan in shared memory.
+constexpr int kCompactItems = 8;
+constexpr int kCompactTile  = kScanBlock * kCompactItems;
+
 template <typename VT, bool SEEDS>
 __global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(const MhSlot* __restrict__ table, unsigned int t,
                                                                 const VT* __restrict__ vertices,
@@ -257,61 +263,99 @@ __global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(const MhSlot* __
                                                                 unsigned int* __restrict__ rank_of,
                                                                 long long* __restrict__ next_frontier,
                                                                 int* __restrict__ next_flabel, int* __restrict__ next_n,
-                                                                unsigned long long* state)
+                                                                unsigned long long* state, unsigned int* ticket)
 {
+  constexpr int kWarps = kScanBlock / 32;
+  __shared__ unsigned int s_cnt[kCompactItems * kWarps];  // [stripe][warp] counts -> exclusive prefixes
+  __shared__ unsigned int s_total;
   const int n    = n_dev ? *n_dev : n_host;
-  const int tile = blockIdx.x;
-  if ((long long)tile * kScanTile > n) return;  // grid is sized from the host-side upper bound
-  const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
-  unsigned int v[kScanItems];
-  unsigned int slot[kScanItems];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  // persistent CTAs take tiles by ticket (in order, so the look-back never waits for a tile that has not started);
+  // the grid is sized from the resident CTA count, not from the host-side upper bound of n
+  while (true) {
+    const int tile = take_ticket(ticket);
+    if ((long long)tile * kCompactTile > n) return;
+    const long long base = (long long)tile * kCompactTile + threadIdx.x;
+    unsigned int slot[kCompactItems];
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    long long e = base + k;
-    slot[k]     = e < n ? slot_to_ref[e] : 0u;
-  }
-  unsigned long long aux[kScanItems];
+    for (int k = 0; k < kCompactItems; k++) {
+      long long e = base + k * kScanBlock;
+      slot[k]     = e < n ? slot_to_ref[e] : 0u;
+    }
+    unsigned long long aux[kCompactItems];
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    long long e = base + k;
-    aux[k]      = e < n ? (ld_relaxed_u64(&table[slot[k]].aux) & kAuxMask) : 0ULL;
-  }
-  unsigned int flags = 0;
+    for (int k = 0; k < kCompactItems; k++) {
+      long long e = base + k * kScanBlock;
+      aux[k]      = e < n ? (ld_relaxed_u64(&table[slot[k]].aux) & kAuxMask) : 0ULL;
+    }
+    unsigned int flags = 0;
+    unsigned int within[kCompactItems];  // flagged items before this one in its (stripe, warp)
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    long long e = base + k;
-    v[k]        = (e < n && aux[k] == mh_tag(t, (unsigned int)e)) ? 1u : 0u;
-    flags |= v[k] << k;
-  }
-  unsigned int agg          = block_scan_items(v);
-  unsigned long long prefix = scan_tile_prefix(state, tile, agg);
+    for (int k = 0; k < kCompactItems; k++) {
+      long long e          = base + k * kScanBlock;
+      const bool f         = e < n && aux[k] == mh_tag(t, (unsigned int)e);
+      const unsigned int b = __ballot_sync(0xffffffffu, f);
+      within[k]            = __popc(b & ((1u << lane) - 1u));
+      flags |= (f ? 1u : 0u) << k;
+      if (lane == 0) s_cnt[k * kWarps + wid] = __popc(b);
+    }
+    if (!SEEDS) {
+      // references do not depend on the scan: written while the tile prefix is being looked up
+      // tag(t, e'): bit 0 set, e' in bits 1..32;  fin(t', rank): bit 0 clear
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    long long e = base + k;
-    if (e < n) {
+      for (int k = 0; k < kCompactItems; k++) {
+        long long e            = base + k * kScanBlock;
+        const unsigned int idx = (unsigned int)(aux[k] >> 1) & 0x0FFFFFFFu;
+        const unsigned int st  = (aux[k] & 1ULL) ? kRefPending : (unsigned int)(aux[k] >> 33);
+        if (e < n) slot_to_ref[e] = (st << 28) | idx;
+      }
+    }
+    __syncthreads();
+    if (wid == 0) {  // exclusive scan of the kCompactItems * kWarps (= 64) counts, two per lane
+      static_assert(kCompactItems * kWarps == 64, "scan below assumes 64 counters");
+      unsigned int a = s_cnt[2 * lane], b = s_cnt[2 * lane + 1];
+      unsigned int inc = a + b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      s_cnt[2 * lane]     = inc - a - b;
+      s_cnt[2 * lane + 1] = inc - b;
+      if (lane == 31) s_total = inc;
+    }
+    __syncthreads();
+    const unsigned int agg    = s_total;
+    unsigned long long prefix = scan_tile_prefix(state, tile, agg);
+#pragma unroll
+    for (int k = 0; k < kCompactItems; k++) {
+      long long e = base + k * kScanBlock;
       if ((flags >> k) & 1u) {
-        unsigned int rank   = (unsigned int)(prefix + v[k]);
+        unsigned int rank   = (unsigned int)prefix + s_cnt[k * kWarps + wid] + within[k];
         next_frontier[rank] = (long long)vertices[e];
         next_flabel[rank]   = SEEDS ? flabel[e] : flabel[erow[e]];
         if (!SEEDS) rank_of[e] = rank;
       }
-      if (!SEEDS) {
-        // tag(t, e'): bit 0 set, e' in bits 1..32;  fin(t', rank): bit 0 clear
-        const unsigned int idx = (unsigned int)(aux[k] >> 1) & 0x0FFFFFFFu;
-        const unsigned int st  = (aux[k] & 1ULL) ? kRefPending : (unsigned int)(aux[k] >> 33);
-        slot_to_ref[e]         = (st << 28) | idx;
-      }
     }
-    if (e == n) *next_n = (int)(prefix + v[k]);
+    if (n >= (long long)tile * kCompactTile && n < (long long)(tile + 1) * kCompactTile && threadIdx.x == 0)
+      *next_n = (int)(prefix + agg);  // the tile that holds index n is the last one: every flagged item precedes n
+    __syncthreads();  // s_cnt is rewritten by the next tile
   }
 }
 
-// fr_off[l] = first frontier row of label l (flabel is non-decreasing), fr_off[B] = n.
-// One thread per frontier row; a row writes the offsets of every label that starts at it.
-__global__ void __launch_bounds__(256) mh_label_bounds_kernel(const int* __restrict__ flabel, const int* __restrict__ n_dev,
-                                                              int B, int* __restrict__ fr_off)
+// fr_off[t][l] = first frontier row of label l at step t (flabel is non-decreasing), fr_off[t][B] = n_t.
+// One thread per frontier row; a row writes the offsets of every label that starts at it.  Nothing on the hop
+// chain reads these, so one launch (blockIdx.y = step) after the last hop does all steps.
+struct MhLabelBounds {
+  const int* flabel[kMaxHops + 1];
+  int* fr_off[kMaxHops + 1];
+};
+__global__ void __launch_bounds__(256) mh_label_bounds_kernel(MhLabelBounds a, const int* __restrict__ n_rows, int B)
 {
-  const int n = *n_dev;
+  const int t                    = blockIdx.y;
+  const int n                    = n_rows[t];
+  const int* __restrict__ flabel = a.flabel[t];
+  int* __restrict__ fr_off       = a.fr_off[t];
   if (n == 0) {
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l <= B; l += gridDim.x * blockDim.x)
       fr_off[l] = 0;
@@ -774,13 +818,15 @@ static void multihop_begin(MhCall& c)
   ensure(sp->base, sizeof(int) * (size_t)(L + 1) * (size_t)std::max(B, 1));
   WGB_CUDA_TRY(cudaMemsetAsync(n_edges_dev, 0, sizeof(int) * kMaxHops, st));
 
-  auto scan_slice = [&](long long n_items) {
-    int tiles    = (int)((n_items + kScanTile) / kScanTile);
+  auto scan_slice = [&](long long n_items, int tile_items = kScanTile) {
+    int tiles    = (int)((n_items + tile_items) / tile_items);
     size_t bytes = scan_state_bytes(tiles);
     void* p      = ensure(sp->scan_state, bytes);
     WGB_CUDA_TRY(cudaMemsetAsync(p, 0, bytes, st));
     return std::make_pair(static_cast<unsigned long long*>(p), tiles);
   };
+  auto scan_grid = [&](int tiles) { return std::min(tiles, sms * 8); };
+  auto ticket_of = [](std::pair<unsigned long long*, int> ss) { return reinterpret_cast<unsigned int*>(ss.first + ss.second); };
 
   MhFrontiers fr;
   MhMeta meta;
@@ -800,18 +846,16 @@ static void multihop_begin(MhCall& c)
     unsigned int* slot0  = static_cast<unsigned int*>(ensure(sp->seed_slot, sizeof(unsigned int) * (size_t)std::max(S, 1)));
     long long* frontier0 = static_cast<long long*>(ensure(sp->frontier[0], sizeof(long long) * (size_t)std::max(S, 1)));
     int* flabel0         = static_cast<int*>(ensure(sp->flabel[0], sizeof(int) * (size_t)std::max(S, 1)));
-    auto ss              = scan_slice(S);
+    auto ss              = scan_slice(S, kCompactTile);
     if (c.seed_dtype == WHOLEMEMORY_DT_INT) {
       mh_seed_insert_kernel<int><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const int*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
       WGB_CHECK_LAUNCH();
-      mh_compact_kernel<int, true><<<ss.second, kScanBlock, 0, st>>>(table, 0u, static_cast<const int*>(c.seeds), nullptr, S, nullptr, slabel, slot0, nullptr, frontier0, flabel0, n_rows_dev, ss.first);
+      mh_compact_kernel<int, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const int*>(c.seeds), nullptr, S, nullptr, slabel, slot0, nullptr, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
     } else {
       mh_seed_insert_kernel<long long><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const long long*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
       WGB_CHECK_LAUNCH();
-      mh_compact_kernel<long long, true><<<ss.second, kScanBlock, 0, st>>>(table, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, nullptr, frontier0, flabel0, n_rows_dev, ss.first);
+      mh_compact_kernel<long long, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, nullptr, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
     }
-    WGB_CHECK_LAUNCH();
-    mh_label_bounds_kernel<<<grid_over(std::max(S, B + 1), sms), 256, 0, st>>>(flabel0, n_rows_dev, B, static_cast<int*>(sp->fr_off[0].p));
     WGB_CHECK_LAUNCH();
     mh_mark(sp, "seeds", st);
     fr.frontier[0]  = frontier0;
@@ -831,7 +875,7 @@ static void multihop_begin(MhCall& c)
     if (M != 0 && rows_ub > 0) {
       // K1: counts + scan over the frontier
       auto ss = scan_slice(rows_ub);
-      count_scan_kernel<long long, CHUNKED><<<ss.second, kScanBlock, 0, st>>>(c.row_ptr, c.row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, nullptr, n_rows_dev + h, n_edges_dev + h);
+      count_scan_kernel<long long, CHUNKED><<<scan_grid(ss.second), kScanBlock, 0, st>>>(c.row_ptr, c.row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, ticket_of(ss), n_rows_dev + h, n_edges_dev + h);
       WGB_CHECK_LAUNCH();
       mh_mark(sp, hop_stage(sp, h, "count+scan"), st);
       meta.off[h] = off;
@@ -893,16 +937,13 @@ static void multihop_begin(MhCall& c)
       WGB_CHECK_LAUNCH();
       mh_mark(sp, hop_stage(sp, h, "insert"), st);
       // K4: first occurrences -> next frontier
-      auto ss = scan_slice(edges_ub);
-      mh_compact_kernel<ColT, false><<<ss.second, kScanBlock, 0, st>>>(table, (unsigned int)(h + 1), dest, n_edges_dev + h, 0, erow, flabel, slot, rank_of, next_frontier, next_flabel, n_rows_dev + h + 1, ss.first);
+      auto ss = scan_slice(edges_ub, kCompactTile);
+      mh_compact_kernel<ColT, false><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, (unsigned int)(h + 1), dest, n_edges_dev + h, 0, erow, flabel, slot, rank_of, next_frontier, next_flabel, n_rows_dev + h + 1, ss.first, ticket_of(ss));
       WGB_CHECK_LAUNCH();
       mh_mark(sp, hop_stage(sp, h, "compact"), st);
     } else {
       WGB_CUDA_TRY(cudaMemsetAsync(n_rows_dev + h + 1, 0, sizeof(int), st));
     }
-    mh_label_bounds_kernel<<<grid_over(std::max<long long>(edges_ub, B + 1), sms), 256, 0, st>>>(next_flabel, n_rows_dev + h + 1, B, static_cast<int*>(sp->fr_off[h + 1].p));
-    WGB_CHECK_LAUNCH();
-    mh_mark(sp, hop_stage(sp, h, "label bounds"), st);
     fr.frontier[h + 1] = next_frontier;
     fr.flabel[h + 1]   = next_flabel;
     meta.fr_off[h + 1] = static_cast<int*>(sp->fr_off[h + 1].p);
@@ -917,6 +958,17 @@ static void multihop_begin(MhCall& c)
   long long* rbase  = rmo + B + 1;                   // B + 1
   long long* totals = rbase + B + 1;                 // 3
   int* base         = static_cast<int*>(sp->base.p);
+  {
+    MhLabelBounds lb;
+    long long most = B + 1;
+    for (int t = 0; t <= L; t++) {
+      lb.flabel[t] = fr.flabel[t];
+      lb.fr_off[t] = static_cast<int*>(sp->fr_off[t].p);
+      most         = std::max(most, ub_rows[t]);
+    }
+    mh_label_bounds_kernel<<<dim3(grid_over(most, sms), L + 1), 256, 0, st>>>(lb, n_rows_dev, B);
+    WGB_CHECK_LAUNCH();
+  }
   mh_meta_kernel<<<grid_over(B, sms), 256, 0, st>>>(meta, counts, base);
   WGB_CHECK_LAUNCH();
   MhScan3 sc;

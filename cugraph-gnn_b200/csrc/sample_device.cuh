@@ -85,12 +85,13 @@ __device__ __forceinline__ unsigned long long scan_tile_prefix(unsigned long lon
 
 // block-wide exclusive scan of kScanItems values per thread (blocked arrangement);
 // returns the block aggregate, rewrites v[] with exclusive prefixes inside the tile.
-__device__ __forceinline__ unsigned int block_scan_items(unsigned int (&v)[kScanItems])
+template <int ITEMS>
+__device__ __forceinline__ unsigned int block_scan_items(unsigned int (&v)[ITEMS])
 {
   __shared__ unsigned int s_warp[kScanBlock / 32];
   unsigned int tsum = 0;
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
+  for (int k = 0; k < ITEMS; k++) {
     unsigned int x = v[k];
     v[k]           = tsum;
     tsum += x;
@@ -114,7 +115,7 @@ __device__ __forceinline__ unsigned int block_scan_items(unsigned int (&v)[kScan
   __syncthreads();
   unsigned int tbase = wbase + inc - tsum;
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++)
+  for (int k = 0; k < ITEMS; k++)
     v[k] += tbase;
   return total;
 }
@@ -141,35 +142,37 @@ __global__ void __launch_bounds__(kScanBlock) count_scan_kernel(ChunkRef row_ptr
                                                                  int* __restrict__ total_out = nullptr)
 {
   if (n_dev) n = *n_dev;  // frontier size produced on the device by the previous hop
-  // tiles are processed in blockIdx order (CTAs are dispatched in increasing index order, so every
-  // predecessor is resident or finished); tiles past the one holding index n have nothing to do -- the
-  // grid is sized from a host-side upper bound when n lives on the device.
-  const int tile = blockIdx.x;
-  if ((long long)tile * kScanTile > n) return;
-  const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
-  unsigned int v[kScanItems];
+  // persistent CTAs take tiles by ticket: tiles start in increasing order, so every predecessor a tile looks back
+  // at is resident or finished, and the grid can be sized from the resident CTA count instead of from n (which
+  // may only be known as a host-side upper bound when it lives on the device).
+  while (true) {
+    const int tile = take_ticket(ticket);
+    if ((long long)tile * kScanTile > n) return;
+    const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
+    unsigned int v[kScanItems];
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    long long i = base + k;
-    unsigned int c = 0;
-    if (i < n) {
-      unsigned long long node = (unsigned long long)centers[i];
-      long long s = load_i64<CHUNKED>(row_ptr, row_ptr_off + node);
-      long long e = load_i64<CHUNKED>(row_ptr, row_ptr_off + node + 1);
-      long long d = e - s;
-      if (d < 0) d = 0;
-      if (M > 0 && d > M) d = M;
-      c = (unsigned int)d;
+    for (int k = 0; k < kScanItems; k++) {
+      long long i = base + k;
+      unsigned int c = 0;
+      if (i < n) {
+        unsigned long long node = (unsigned long long)centers[i];
+        long long s = load_i64<CHUNKED>(row_ptr, row_ptr_off + node);
+        long long e = load_i64<CHUNKED>(row_ptr, row_ptr_off + node + 1);
+        long long d = e - s;
+        if (d < 0) d = 0;
+        if (M > 0 && d > M) d = M;
+        c = (unsigned int)d;
+      }
+      v[k] = c;
     }
-    v[k] = c;
-  }
-  unsigned int agg = block_scan_items(v);
-  unsigned long long prefix = scan_tile_prefix(state, tile, agg);
+    unsigned int agg = block_scan_items(v);
+    unsigned long long prefix = scan_tile_prefix(state, tile, agg);
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    long long i = base + k;
-    if (i <= n) offsets[i] = (int)(prefix + v[k]);
-    if (i == n && total_out) *total_out = (int)(prefix + v[k]);
+    for (int k = 0; k < kScanItems; k++) {
+      long long i = base + k;
+      if (i <= n) offsets[i] = (int)(prefix + v[k]);
+      if (i == n && total_out) *total_out = (int)(prefix + v[k]);
+    }
   }
 }
 
