@@ -569,6 +569,180 @@ __global__ void __launch_bounds__(256) mh_csr_label_hop_kernel(int L, int B, con
   }
 }
 
+
+// ---- heterogeneous graphs -------------------------------------------------------------------------------------
+// T edge types, each with its own CSR over the GLOBAL vertex id space; Vt vertex types own contiguous id ranges.
+// A hop samples the whole frontier once per edge type (fan-out [hop * T + etype]); the hop's edge list is ordered
+// (frontier row, edge type, slot), so it stays label-major and insert / compact above run unchanged over it.
+// Everything type-specific is bookkeeping around them: where (row, type) starts in the hop's edge list, and local ids
+// that restart per (label, vertex type).  The descriptor lives in device memory (too large for a parameter block).
+constexpr int kMaxEdgeTypes   = 16;
+constexpr int kMaxVertexTypes = 16;
+
+struct MhHeteroDesc {
+  int T, Vt, L, B;
+  long long vto[kMaxVertexTypes + 1];              // vertex type vt owns global ids [vto[vt], vto[vt+1])
+  const int* off[kMaxHops][kMaxEdgeTypes];         // [h][t][f]: exclusive scan over frontier rows of the type's counts (null: skipped)
+  const int* pos[kMaxHops][kMaxEdgeTypes];         // [h][t][f]: first edge of (row f, type t) in the hop's edge list
+  const int* tcnt[kMaxHops + 1][kMaxVertexTypes];  // [s][vt][r]: rows r' < r of step s whose vertex has type vt
+  int* typed_local[kMaxHops + 1];                  // [s][r]: local id of frontier row r inside (label, vertex type)
+  ChunkRef eid[kMaxEdgeTypes];
+  unsigned long long eid_off[kMaxEdgeTypes];
+  int has_eid[kMaxEdgeTypes];
+};
+
+__device__ __forceinline__ int mh_vtype_of(const MhHeteroDesc* __restrict__ d, long long v)
+{
+  int vt = 0;
+  for (int i = 1; i < d->Vt; i++)
+    vt += v >= d->vto[i] ? 1 : 0;
+  return vt;
+}
+
+// pos[t][f] = sum_t' off[t'][f] + sum_{t' < t} (off[t'][f+1] - off[t'][f]);  *n_edges = sum_t off[t][n]
+struct MhCombine {
+  const int* off[kMaxEdgeTypes];
+  int* pos[kMaxEdgeTypes];
+  int T;
+};
+__global__ void __launch_bounds__(256) mh_combine_types_kernel(MhCombine a, const int* __restrict__ n_dev, int* __restrict__ n_edges)
+{
+  const int n = *n_dev;
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f <= n; f += gridDim.x * blockDim.x) {
+    int run = 0;
+    for (int t = 0; t < a.T; t++)
+      run += a.off[t] ? a.off[t][f] : 0;
+    if (f == n) *n_edges = run;
+    for (int t = 0; t < a.T; t++) {
+      a.pos[t][f] = run;
+      if (f < n && a.off[t]) run += a.off[t][f + 1] - a.off[t][f];
+    }
+  }
+}
+
+// tcnt[s][vt][r] for every (step, vertex type) slice = blockIdx.y; persistent ticketed scan per slice
+struct MhVtypeScan {
+  int* tcnt[(kMaxHops + 1)];  // [s] -> Vt arrays of (cap_s + 1) ints, back to back
+  long long cap[(kMaxHops + 1)];
+  unsigned long long* state;  // per slice: tiles_max words + 2 (ticket)
+  long long state_stride;
+};
+__global__ void __launch_bounds__(kScanBlock) mh_vtype_scan_kernel(const MhHeteroDesc* __restrict__ d, MhFrontiers fr,
+                                                                   const int* __restrict__ n_rows, MhVtypeScan a)
+{
+  const int s = blockIdx.y / d->Vt, vt = blockIdx.y % d->Vt;
+  const int n = n_rows[s];
+  const long long* __restrict__ frontier = fr.frontier[s];
+  int* __restrict__ out                  = a.tcnt[s] + (long long)vt * (a.cap[s] + 1);
+  unsigned long long* state              = a.state + (long long)blockIdx.y * a.state_stride;
+  unsigned int* ticket                   = reinterpret_cast<unsigned int*>(state + a.state_stride - 2);
+  const long long lo = d->vto[vt], hi = d->vto[vt + 1];
+  while (true) {
+    const int tile = take_ticket(ticket);
+    if ((long long)tile * kScanTile > n) return;
+    const long long base = (long long)tile * kScanTile + (long long)threadIdx.x * kScanItems;
+    unsigned int v[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      long long r = base + k;
+      long long x = r < n ? frontier[r] : -1;
+      v[k]        = (x >= lo && x < hi) ? 1u : 0u;
+    }
+    unsigned int agg          = block_scan_items(v);
+    unsigned long long prefix = scan_tile_prefix(state, tile, agg);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      long long r = base + k;
+      if (r <= n) out[r] = (int)(prefix + v[k]);
+    }
+  }
+}
+
+// per label: first typed local id of every (step, vertex type), node counts per (label, vtype), edge counts per
+// (label, edge type, hop)
+__global__ void __launch_bounds__(256) mh_hetero_meta_kernel(const MhHeteroDesc* __restrict__ d, MhMeta m,
+                                                             long long* __restrict__ edge_counts,
+                                                             long long* __restrict__ node_counts, int* __restrict__ tbase)
+{
+  const int T = d->T, Vt = d->Vt, L = d->L, B = d->B;
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < B; l += gridDim.x * blockDim.x) {
+    for (int vt = 0; vt < Vt; vt++) {
+      int acc = 0;
+      for (int s = 0; s <= L; s++) {
+        tbase[((long long)s * Vt + vt) * B + l] = acc;
+        const int* c = d->tcnt[s][vt];
+        acc += c[m.fr_off[s][l + 1]] - c[m.fr_off[s][l]];
+      }
+      node_counts[(long long)l * Vt + vt] = acc;
+    }
+    for (int t = 0; t < T; t++)
+      for (int h = 0; h < L; h++) {
+        const int* o = d->off[h][t];
+        edge_counts[((long long)l * T + t) * L + h] = o ? (long long)o[m.fr_off[h][l + 1]] - (long long)o[m.fr_off[h][l]] : 0;
+      }
+  }
+}
+
+// frontier rows of step blockIdx.y: typed local id + renumber map
+__global__ void __launch_bounds__(256) mh_hetero_rows_kernel(const MhHeteroDesc* __restrict__ d, MhFrontiers fr, MhMeta m,
+                                                             const int* __restrict__ n_rows, const int* __restrict__ tbase,
+                                                             const long long* __restrict__ rmo, long long* __restrict__ map_out)
+{
+  const int s = blockIdx.y;
+  const int n = n_rows[s];
+  const int Vt = d->Vt, B = d->B;
+  const long long* __restrict__ frontier = fr.frontier[s];
+  const int* __restrict__ flabel         = fr.flabel[s];
+  int* __restrict__ typed                = d->typed_local[s];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    const long long v = frontier[r];
+    const int l       = flabel[r];
+    const int vt      = mh_vtype_of(d, v);
+    const int* c      = d->tcnt[s][vt];
+    const int tl      = tbase[((long long)s * Vt + vt) * B + l] + c[r] - c[m.fr_off[s][l]];
+    typed[r]          = tl;
+    map_out[rmo[(long long)l * Vt + vt] + tl] = v;
+  }
+}
+
+// edges of hop blockIdx.y -> [label][edge type][hop] groups
+template <typename OutT, bool CHUNKED>
+__global__ void __launch_bounds__(256) mh_hetero_emit_edges_kernel(const MhHeteroDesc* __restrict__ d,
+                                                                   const int* __restrict__ n_edges, MhHopBufs hb, MhFrontiers fr,
+                                                                   MhMeta m, const long long* __restrict__ lto,
+                                                                   OutT* __restrict__ majors, OutT* __restrict__ minors,
+                                                                   long long* __restrict__ edge_id, int* __restrict__ edge_type,
+                                                                   long long* __restrict__ edge_renumber_map)
+{
+  const int h = blockIdx.y;
+  const int n = n_edges[h];
+  const int T = d->T, L = d->L;
+  const int* __restrict__ erow             = hb.erow[h];
+  const unsigned int* __restrict__ slot_of = hb.slot[h];
+  const long long* __restrict__ gid        = hb.gid[h];
+  const int* __restrict__ flabel_h         = fr.flabel[h];
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    unsigned int ref = slot_of[e];
+    if ((ref >> 28) == kRefPending) ref = ((unsigned int)(h + 1) << 28) | hb.rank_of[h][ref & 0x0FFFFFFFu];
+    const int f  = erow[e];
+    const int l  = flabel_h[f];
+    const int f0 = m.fr_off[h][l];
+    int t        = 0;
+    for (int i = 1; i < T; i++)
+      t += d->pos[h][i][f] <= e ? 1 : 0;  // pos is non-decreasing in the type for a fixed row
+    const long long group = lto[((long long)l * T + t) * L];
+    const long long p     = lto[((long long)l * T + t) * L + h] + (long long)(e - d->pos[h][t][f]) +
+                        (long long)(d->off[h][t][f] - d->off[h][t][f0]);
+    majors[p]    = (OutT)d->typed_local[h][f];
+    minors[p]    = (OutT)d->typed_local[ref >> 28][ref & 0x0FFFFFFFu];
+    edge_type[p] = t;
+    edge_id[p]   = p - group;
+    long long g  = gid[e];
+    if (d->has_eid[t]) g = load_i64<CHUNKED>(d->eid[t], d->eid_off[t] + (unsigned long long)g);
+    edge_renumber_map[p] = g;
+  }
+}
+
 }  // namespace wgb
 
 // ---------------------------------------------------------------------------------------------------
@@ -586,6 +760,9 @@ struct wholegraph_multihop_sampler_ {
   Buf frontier[wgb::kMaxHops + 1], flabel[wgb::kMaxHops + 1], fr_off[wgb::kMaxHops + 1];
   Buf off[wgb::kMaxHops], dest[wgb::kMaxHops], erow[wgb::kMaxHops], gid[wgb::kMaxHops], slot[wgb::kMaxHops], rank_of[wgb::kMaxHops];
   Buf base;
+  // heterogeneous calls only
+  Buf pos[wgb::kMaxHops], tcnt[wgb::kMaxHops + 1], typed[wgb::kMaxHops + 1], vscan_state, tbase, desc_dev;
+  wgb::MhHeteroDesc desc_host;
   long long* h_totals = nullptr;  // pinned
   int device          = -1;
   // a call between _begin and _finish
@@ -602,6 +779,9 @@ struct wholegraph_multihop_sampler_ {
     wgb::MhHopBufs hb;
     long long *lho = nullptr, *rmo = nullptr, *rbase = nullptr;
     int *base = nullptr, *n_rows_dev = nullptr, *n_edges_dev = nullptr;
+    bool hetero = false;  // typed outputs ([label][edge type][hop], ids per (label, vertex type))
+    int T = 1, Vt = 1;
+    int* tbase = nullptr;
   } pending;
   cudaEvent_t ready = nullptr;  // recorded after the output sizes have been copied to h_totals
   // WGB_MH_TIMING=1: per-stage device times (cudaEvents between launches), averaged, printed at destroy
@@ -700,16 +880,25 @@ static void mh_print_marks(wholegraph_multihop_sampler_* sp)
 
 static int grid_over(long long n, int sms) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)sms * 8)); }
 
+struct MhTypeCsr {
+  ChunkRef row_ptr, col, wgt, eid;
+  unsigned long long row_ptr_off = 0, col_off = 0, wgt_off = 0, eid_off = 0;
+  bool has_eid = false;
+};
+
 struct MhCall {
   wholegraph_multihop_sampler_* sp;
-  ChunkRef row_ptr, col, wgt, eid;
-  unsigned long long row_ptr_off, col_off, wgt_off, eid_off;
+  int T  = 1;                        // edge types (one CSR each)
+  int Vt = 1;                        // vertex types
+  bool hetero = false;               // typed outputs
+  MhTypeCsr csr[kMaxEdgeTypes];
+  long long vto[kMaxVertexTypes + 1];
   wholememory_dtype_t col_dtype, wgt_dtype, seed_dtype;
-  bool weighted, has_eid, chunked;
+  bool weighted, chunked;
   const void* seeds;
   const long long* label_offsets;  // device
   int S, B, L;
-  int fanout[kMaxHops];
+  int fanout[kMaxHops * kMaxEdgeTypes];  // [h * T + t]
   unsigned long long V;
   unsigned long long random_state;
   int flags;
@@ -717,40 +906,40 @@ struct MhCall {
 };
 
 template <typename ColT, bool CHUNKED>
-static void launch_hop_sample(const MhCall& c, const long long* frontier, const int* n_dev, long long ub_rows, int M,
-                              unsigned long long seed, const int* off, ColT* dest, int* erow, long long* gid)
+static void launch_hop_sample(const MhCall& c, const MhTypeCsr& g, const long long* frontier, const int* n_dev, long long ub_rows,
+                              int M, unsigned long long seed, const int* off, ColT* dest, int* erow, long long* gid)
 {
   int sms           = num_sms();
   const Affine* tab = skip_table_device();
   int n_ub          = (int)ub_rows;
   if (M <= 0) {
     int grid = std::max(1, std::min((n_ub + 7) / 8, sms * 8));
-    sample_all_kernel<long long, ColT, CHUNKED><<<grid, 256, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, frontier, n_ub, off, dest, erow, gid, n_dev);
+    sample_all_kernel<long long, ColT, CHUNKED><<<grid, 256, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, frontier, n_ub, off, dest, erow, gid, n_dev);
   } else if (c.weighted) {
     int grid = std::max(1, std::min(n_ub, sms * 8));
     if (c.wgt_dtype == WHOLEMEMORY_DT_FLOAT) {
       if (M <= 256)
-        weighted_kernel<long long, ColT, float, 128, CHUNKED><<<grid, 128, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, c.wgt, c.wgt_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
+        weighted_kernel<long long, ColT, float, 128, CHUNKED><<<grid, 128, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, g.wgt, g.wgt_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
       else
-        weighted_kernel<long long, ColT, float, 256, CHUNKED><<<grid, 256, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, c.wgt, c.wgt_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
+        weighted_kernel<long long, ColT, float, 256, CHUNKED><<<grid, 256, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, g.wgt, g.wgt_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
     } else {
       if (M <= 256)
-        weighted_kernel<long long, ColT, double, 128, CHUNKED><<<grid, 128, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, c.wgt, c.wgt_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
+        weighted_kernel<long long, ColT, double, 128, CHUNKED><<<grid, 128, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, g.wgt, g.wgt_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
       else
-        weighted_kernel<long long, ColT, double, 256, CHUNKED><<<grid, 256, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, c.wgt, c.wgt_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
+        weighted_kernel<long long, ColT, double, 256, CHUNKED><<<grid, 256, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, g.wgt, g.wgt_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
     }
   } else if (M <= 32) {
     int batches = (n_ub + 31) / 32;
     int grid    = std::max(1, std::min((batches + 7) / 8, sms * 8));
     if (M <= 8)
-      uniform_small_kernel<long long, ColT, 8, CHUNKED><<<grid, 256, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
+      uniform_small_kernel<long long, ColT, 8, CHUNKED><<<grid, 256, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
     else if (M <= 16)
-      uniform_small_kernel<long long, ColT, 16, CHUNKED><<<grid, 256, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
+      uniform_small_kernel<long long, ColT, 16, CHUNKED><<<grid, 256, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
     else
-      uniform_small_kernel<long long, ColT, 32, CHUNKED><<<grid, 256, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
+      uniform_small_kernel<long long, ColT, 32, CHUNKED><<<grid, 256, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
   } else {
     int grid = std::max(1, std::min(n_ub, sms * 16));
-    uniform_general_kernel<long long, ColT, CHUNKED><<<grid, kGeneralBlock, 0, c.stream>>>(c.row_ptr, c.row_ptr_off, c.col, c.col_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
+    uniform_general_kernel<long long, ColT, CHUNKED><<<grid, kGeneralBlock, 0, c.stream>>>(g.row_ptr, g.row_ptr_off, g.col, g.col_off, frontier, n_ub, M, seed, off, dest, erow, gid, tab, n_dev);
   }
   WGB_CHECK_LAUNCH();
 }
@@ -768,13 +957,24 @@ static void multihop_begin(MhCall& c)
   // ---- host-side bounds ---------------------------------------------------------------------------
   long long ub_rows[kMaxHops + 1];
   long long ub_edges[kMaxHops];
+  const int T = c.T;
+  // per-hop sum of the positive fan-outs over the edge types; -1: some type takes all neighbours
+  auto hop_fanout_sum = [&](int h) -> long long {
+    long long sum = 0;
+    for (int t = 0; t < T; t++) {
+      if (c.fanout[h * T + t] < 0) return -1;
+      sum += c.fanout[h * T + t];
+    }
+    return sum;
+  };
   bool bounded = true;
   ub_rows[0]   = S;
   for (int h = 0; h < L; h++) {
-    if (c.fanout[h] == 0) {
+    const long long fs = hop_fanout_sum(h);
+    if (fs == 0) {
       ub_edges[h] = 0;
-    } else if (c.fanout[h] > 0 && bounded) {
-      ub_edges[h] = ub_rows[h] * c.fanout[h];
+    } else if (fs > 0 && bounded) {
+      ub_edges[h] = ub_rows[h] * fs;
     } else {
       bounded     = false;
       ub_edges[h] = -1;  // known only after the hop's count (host sync)
@@ -808,7 +1008,8 @@ static void multihop_begin(MhCall& c)
   MhSlot* table = static_cast<MhSlot*>(sp->table.p);
 
   // ---- small per-call device arrays -------------------------------------------------------------------
-  int* small_i32     = static_cast<int*>(ensure(sp->small_i32, sizeof(int) * (size_t)(4 * (kMaxHops + 2))));
+  int* small_i32     = static_cast<int*>(ensure(sp->small_i32, sizeof(int) * (size_t)(4 * (kMaxHops + 2) + kMaxHops * kMaxEdgeTypes)));
+  int* n_edges_t_dev = small_i32 + 4 * (kMaxHops + 2);  // [L][T] edge counts per type (T > 1)
   int* n_rows_dev    = small_i32;                                                          // [L+1] frontier sizes
   int* n_edges_dev   = small_i32 + (kMaxHops + 1);                                         // [L]   edge counts
   unsigned int* nslots_dev = reinterpret_cast<unsigned int*>(small_i32 + 2 * (kMaxHops + 1));  // [L+1] slots in use per step
@@ -817,6 +1018,17 @@ static void multihop_begin(MhCall& c)
     ensure(sp->fr_off[t], sizeof(int) * (size_t)(B + 1));
   ensure(sp->base, sizeof(int) * (size_t)(L + 1) * (size_t)std::max(B, 1));
   WGB_CUDA_TRY(cudaMemsetAsync(n_edges_dev, 0, sizeof(int) * kMaxHops, st));
+  MhHeteroDesc& desc = sp->desc_host;
+  if (c.hetero) {
+    memset(&desc, 0, sizeof(desc));
+    desc.T = T; desc.Vt = c.Vt; desc.L = L; desc.B = B;
+    for (int v = 0; v <= c.Vt; v++) desc.vto[v] = c.vto[v];
+    for (int t = 0; t < T; t++) {
+      desc.eid[t]     = c.csr[t].eid;
+      desc.eid_off[t] = c.csr[t].eid_off;
+      desc.has_eid[t] = c.csr[t].has_eid ? 1 : 0;
+    }
+  }
 
   auto scan_slice = [&](long long n_items, int tile_items = kScanTile) {
     int tiles    = (int)((n_items + tile_items) / tile_items);
@@ -866,19 +1078,44 @@ static void multihop_begin(MhCall& c)
   // ---- hops ---------------------------------------------------------------------------------------------
   for (int h = 0; h < L; h++) {
     const long long rows_ub = ub_rows[h];
-    const int M             = c.fanout[h];
     long long* frontier     = static_cast<long long*>(sp->frontier[h].p);
     int* flabel             = static_cast<int*>(sp->flabel[h].p);
-    int* off                = static_cast<int*>(ensure(sp->off[h], sizeof(int) * (size_t)(std::max<long long>(rows_ub, 0) + 1 + kScanTile)));
+    const size_t off_stride = (size_t)(std::max<long long>(rows_ub, 0) + 1 + kScanTile);
+    int* off_all            = static_cast<int*>(ensure(sp->off[h], sizeof(int) * off_stride * (size_t)T));
+    int* pos_all            = T > 1 ? static_cast<int*>(ensure(sp->pos[h], sizeof(int) * off_stride * (size_t)T)) : nullptr;
     long long edges_ub      = ub_edges[h];
+    const long long fs      = hop_fanout_sum(h);
     meta.off[h]             = nullptr;
-    if (M != 0 && rows_ub > 0) {
-      // K1: counts + scan over the frontier
-      auto ss = scan_slice(rows_ub);
-      count_scan_kernel<long long, CHUNKED><<<scan_grid(ss.second), kScanBlock, 0, st>>>(c.row_ptr, c.row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, ticket_of(ss), n_rows_dev + h, n_edges_dev + h);
-      WGB_CHECK_LAUNCH();
+    const int* off_t[kMaxEdgeTypes];  // null: the type is skipped in this hop
+    const int* pos_t[kMaxEdgeTypes];
+    for (int t = 0; t < T; t++)
+      off_t[t] = pos_t[t] = nullptr;
+    if (fs != 0 && rows_ub > 0) {
+      // K1: counts + scan over the frontier, once per edge type
+      for (int t = 0; t < T; t++) {
+        const int M = c.fanout[h * T + t];
+        if (M == 0) continue;
+        int* off = off_all + (size_t)t * off_stride;
+        auto ss  = scan_slice(rows_ub);
+        count_scan_kernel<long long, CHUNKED><<<scan_grid(ss.second), kScanBlock, 0, st>>>(c.csr[t].row_ptr, c.csr[t].row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, ticket_of(ss), n_rows_dev + h, T > 1 ? n_edges_t_dev + h * T + t : n_edges_dev + h);
+        WGB_CHECK_LAUNCH();
+        off_t[t] = off;
+      }
+      if (T > 1) {
+        MhCombine cb;
+        cb.T = T;
+        for (int t = 0; t < T; t++) {
+          cb.off[t] = off_t[t];
+          cb.pos[t] = pos_all + (size_t)t * off_stride;
+          pos_t[t]  = cb.pos[t];
+        }
+        mh_combine_types_kernel<<<grid_over(rows_ub + 1, sms), 256, 0, st>>>(cb, n_rows_dev + h, n_edges_dev + h);
+        WGB_CHECK_LAUNCH();
+      } else {
+        pos_t[0] = off_t[0];
+      }
       mh_mark(sp, hop_stage(sp, h, "count+scan"), st);
-      meta.off[h] = off;
+      meta.off[h] = off_t[0];
       if (edges_ub < 0) {
         // take-all hop: the edge count is data dependent -> one extra host sync to size the scratch
         int e_host = 0;
@@ -890,9 +1127,9 @@ static void multihop_begin(MhCall& c)
         ub_edges[h]    = edges_ub;
         ub_rows[h + 1] = edges_ub;
         for (int hh = h + 1; hh < L; hh++) {  // later bounded hops can now be bounded too
-          if (c.fanout[hh] > 0) ub_edges[hh] = ub_rows[hh] * c.fanout[hh];
-          else if (c.fanout[hh] == 0) ub_edges[hh] = 0;
-          else break;
+          const long long fs2 = hop_fanout_sum(hh);
+          if (fs2 < 0) break;
+          ub_edges[hh]    = ub_rows[hh] * fs2;
           ub_rows[hh + 1] = ub_edges[hh];
           known_items += ub_edges[hh];
         }
@@ -904,6 +1141,11 @@ static void multihop_begin(MhCall& c)
       ub_edges[h]    = 0;
       ub_rows[h + 1] = 0;
     }
+    if (c.hetero)
+      for (int t = 0; t < T; t++) {
+        desc.off[h][t] = off_t[t];
+        desc.pos[h][t] = pos_t[t];
+      }
     WGB_EXPECTS(edges_ub < (1LL << 28), "too many edges in one hop for one call (2^28); split the seeds into more calls");
     const size_t ecap = (size_t)std::max<long long>(edges_ub, 1);
     ColT* dest               = static_cast<ColT*>(ensure(sp->dest[h], sizeof(ColT) * ecap));
@@ -913,7 +1155,7 @@ static void multihop_begin(MhCall& c)
     unsigned int* rank_of    = static_cast<unsigned int*>(ensure(sp->rank_of[h], sizeof(unsigned int) * ecap));
     long long* next_frontier = static_cast<long long*>(ensure(sp->frontier[h + 1], sizeof(long long) * ecap));
     int* next_flabel         = static_cast<int*>(ensure(sp->flabel[h + 1], sizeof(int) * ecap));
-    hb.off[h]  = off;
+    hb.off[h]  = off_t[0];
     hb.erow[h] = erow;
     hb.slot[h] = slot;
     hb.rank_of[h] = rank_of;
@@ -929,8 +1171,13 @@ static void multihop_begin(MhCall& c)
       mh_reinsert_kernel<<<dim3(grid_over(max_rows, sms), h + 1), 256, 0, st>>>(table, nslots_dev + h + 1, epoch, c.V, fr, n_rows_dev);
       WGB_CHECK_LAUNCH();
       mh_mark(sp, hop_stage(sp, h, "plan+reinsert"), st);
-      // K2: sample
-      launch_hop_sample<ColT, CHUNKED>(c, frontier, n_rows_dev + h, rows_ub, M, c.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL, off, dest, erow, gid);
+      // K2: sample, once per edge type; type t writes its edges of row f at pos_t[f]
+      const unsigned long long hop_seed = c.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL;
+      for (int t = 0; t < T; t++) {
+        if (!off_t[t]) continue;
+        launch_hop_sample<ColT, CHUNKED>(c, c.csr[t], frontier, n_rows_dev + h, rows_ub, c.fanout[h * T + t],
+                                         hop_seed + (unsigned long long)t * 0xD1B54A32D192ED03ULL, pos_t[t], dest, erow, gid);
+      }
       mh_mark(sp, hop_stage(sp, h, "sample"), st);
       // K3: insert (label, neighbour)
       mh_insert_kernel<ColT><<<std::max(1, (int)std::min<long long>((edges_ub + 255) / 256, (long long)sms * 16)), 256, 0, st>>>(table, nslots_dev + h + 1, epoch, c.V, (unsigned int)(h + 1), dest, n_edges_dev + h, erow, flabel, slot);
@@ -950,14 +1197,18 @@ static void multihop_begin(MhCall& c)
   }
 
   // ---- per-label bookkeeping + offsets ---------------------------------------------------------------------
-  const long long n_counts = (long long)B * L + 2LL * B;
+  const int Vt             = c.Vt;
+  const long long n_groups = c.hetero ? (long long)B * T * L : (long long)B * L;  // edge groups
+  const long long n_maps   = c.hetero ? (long long)B * Vt : (long long)B;          // renumber map segments
+  const long long n_counts = n_groups + n_maps + B;
   long long* counts = static_cast<long long*>(ensure(sp->counts, sizeof(long long) * (size_t)(n_counts + 1)));
   long long* scans  = static_cast<long long*>(ensure(sp->small_i64, sizeof(long long) * (size_t)(n_counts + 8)));
-  long long* lho    = scans;                         // B*L + 1
-  long long* rmo    = scans + (long long)B * L + 1;  // B + 1
-  long long* rbase  = rmo + B + 1;                   // B + 1
-  long long* totals = rbase + B + 1;                 // 3
+  long long* lho    = scans;                 // n_groups + 1
+  long long* rmo    = scans + n_groups + 1;  // n_maps + 1
+  long long* rbase  = rmo + n_maps + 1;      // B + 1 (homogeneous CSR only)
+  long long* totals = rbase + B + 1;         // 3
   int* base         = static_cast<int*>(sp->base.p);
+  int* tbase        = nullptr;
   {
     MhLabelBounds lb;
     long long most = B + 1;
@@ -969,12 +1220,41 @@ static void multihop_begin(MhCall& c)
     mh_label_bounds_kernel<<<dim3(grid_over(most, sms), L + 1), 256, 0, st>>>(lb, n_rows_dev, B);
     WGB_CHECK_LAUNCH();
   }
-  mh_meta_kernel<<<grid_over(B, sms), 256, 0, st>>>(meta, counts, base);
-  WGB_CHECK_LAUNCH();
   MhScan3 sc;
-  sc.in[0] = counts;                           sc.out[0] = lho;   sc.n[0] = (long long)B * L;
-  sc.in[1] = counts + (long long)B * L;        sc.out[1] = rmo;   sc.n[1] = B;
-  sc.in[2] = counts + (long long)B * L + B;    sc.out[2] = rbase; sc.n[2] = B;
+  if (!c.hetero) {
+    mh_meta_kernel<<<grid_over(B, sms), 256, 0, st>>>(meta, counts, base);
+    WGB_CHECK_LAUNCH();
+    sc.in[0] = counts;                           sc.out[0] = lho;   sc.n[0] = (long long)B * L;
+    sc.in[1] = counts + (long long)B * L;        sc.out[1] = rmo;   sc.n[1] = B;
+    sc.in[2] = counts + (long long)B * L + B;    sc.out[2] = rbase; sc.n[2] = B;
+  } else {
+    // per (step, vertex type): exclusive counts over the frontier rows, one launch for all slices
+    MhVtypeScan vs;
+    long long tiles_max = 1;
+    for (int t = 0; t <= L; t++) {
+      const long long cap = std::max<long long>(ub_rows[t], 0);
+      vs.cap[t]           = cap;
+      vs.tcnt[t]          = static_cast<int*>(ensure(sp->tcnt[t], sizeof(int) * (size_t)(cap + 1) * (size_t)Vt));
+      desc.typed_local[t] = static_cast<int*>(ensure(sp->typed[t], sizeof(int) * (size_t)std::max<long long>(cap, 1)));
+      for (int vt = 0; vt < Vt; vt++)
+        desc.tcnt[t][vt] = vs.tcnt[t] + (long long)vt * (cap + 1);
+      tiles_max = std::max(tiles_max, (cap + kScanTile) / kScanTile);
+    }
+    vs.state_stride   = tiles_max + 2;
+    const size_t vbytes = sizeof(unsigned long long) * (size_t)vs.state_stride * (size_t)((L + 1) * Vt);
+    vs.state          = static_cast<unsigned long long*>(ensure(sp->vscan_state, vbytes));
+    WGB_CUDA_TRY(cudaMemsetAsync(vs.state, 0, vbytes, st));
+    MhHeteroDesc* desc_dev = static_cast<MhHeteroDesc*>(ensure(sp->desc_dev, sizeof(MhHeteroDesc)));
+    WGB_CUDA_TRY(cudaMemcpyAsync(desc_dev, &desc, sizeof(MhHeteroDesc), cudaMemcpyHostToDevice, st));
+    mh_vtype_scan_kernel<<<dim3((unsigned int)std::min<long long>(tiles_max, (long long)sms * 4), (L + 1) * Vt), kScanBlock, 0, st>>>(desc_dev, fr, n_rows_dev, vs);
+    WGB_CHECK_LAUNCH();
+    tbase = static_cast<int*>(ensure(sp->tbase, sizeof(int) * (size_t)(L + 1) * (size_t)Vt * (size_t)std::max(B, 1)));
+    mh_hetero_meta_kernel<<<grid_over(B, sms), 256, 0, st>>>(desc_dev, meta, counts, counts + n_groups, tbase);
+    WGB_CHECK_LAUNCH();
+    sc.in[0] = counts;            sc.out[0] = lho;   sc.n[0] = n_groups;
+    sc.in[1] = counts + n_groups; sc.out[1] = rmo;   sc.n[1] = n_maps;
+    sc.in[2] = counts;            sc.out[2] = rbase; sc.n[2] = 0;
+  }
   sc.totals = totals;
   mh_scan3_kernel<<<3, 1024, 0, st>>>(sc);
   WGB_CHECK_LAUNCH();
@@ -983,8 +1263,9 @@ static void multihop_begin(MhCall& c)
   WGB_CUDA_TRY(cudaEventRecord(sp->ready, st));
   mh_mark(sp, "meta+scan3", st);
   auto& pd = sp->pending;
-  pd.B = B; pd.L = L; pd.flags = c.flags; pd.has_eid = c.has_eid; pd.chunked = CHUNKED;
-  pd.eid = c.eid; pd.eid_off = c.eid_off;
+  pd.B = B; pd.L = L; pd.flags = c.flags; pd.has_eid = c.csr[0].has_eid; pd.chunked = CHUNKED;
+  pd.eid = c.csr[0].eid; pd.eid_off = c.csr[0].eid_off;
+  pd.hetero = c.hetero; pd.T = T; pd.Vt = Vt; pd.tbase = tbase;
   for (int t = 0; t <= L; t++) pd.ub_rows[t] = ub_rows[t];
   for (int h = 0; h < L; h++) pd.ub_edges[h] = ub_edges[h];
   pd.fr = fr; pd.meta = meta; pd.hb = hb;
@@ -995,6 +1276,7 @@ static void multihop_begin(MhCall& c)
 
 struct MhOutCtx {
   void *majors, *minors, *edge_id, *lho, *map, *rmo, *major_offsets, *step_counts;
+  void *edge_type = nullptr, *edge_renumber_map = nullptr, *edge_renumber_map_offsets = nullptr;  // heterogeneous calls
   wholememory_env_func_t* env;
   cudaStream_t stream;
 };
@@ -1023,6 +1305,57 @@ static void multihop_finish(wholegraph_multihop_sampler_* sp, const MhOutCtx& c)
   const bool csr    = (pd.flags & WHOLEGRAPH_MULTIHOP_CSR) != 0;
   const bool idx64  = (pd.flags & WHOLEGRAPH_MULTIHOP_INT64_IDS) != 0;
   const wholememory_dtype_t idx_dt = idx64 ? WHOLEMEMORY_DT_INT64 : WHOLEMEMORY_DT_INT;
+  if (pd.hetero) {
+    const int T = pd.T, Vt = pd.Vt;
+    WGB_EXPECTS(!csr, "CSR compression is not defined for heterogeneous sampling (as in the reference)");
+    WGB_EXPECTS(c.majors && c.edge_type && c.edge_renumber_map && c.edge_renumber_map_offsets, "heterogeneous call finished through the homogeneous entry point");
+    void* out_majors    = output_alloc(c.env, c.majors, n_edges, idx_dt);
+    void* out_minors    = output_alloc(c.env, c.minors, n_edges, idx_dt);
+    long long* out_eid  = static_cast<long long*>(output_alloc(c.env, c.edge_id, n_edges, WHOLEMEMORY_DT_INT64));
+    int* out_etype      = static_cast<int*>(output_alloc(c.env, c.edge_type, n_edges, WHOLEMEMORY_DT_INT));
+    long long* out_lto  = static_cast<long long*>(output_alloc(c.env, c.lho, (long long)B * T * L + 1, WHOLEMEMORY_DT_INT64));
+    long long* out_map  = static_cast<long long*>(output_alloc(c.env, c.map, n_nodes, WHOLEMEMORY_DT_INT64));
+    long long* out_rmo  = static_cast<long long*>(output_alloc(c.env, c.rmo, (long long)B * Vt + 1, WHOLEMEMORY_DT_INT64));
+    long long* out_emap = static_cast<long long*>(output_alloc(c.env, c.edge_renumber_map, n_edges, WHOLEMEMORY_DT_INT64));
+    long long* out_ermo = static_cast<long long*>(output_alloc(c.env, c.edge_renumber_map_offsets, (long long)B * T + 1, WHOLEMEMORY_DT_INT64));
+    if (c.step_counts) {
+      int* out_sc = static_cast<int*>(output_alloc(c.env, c.step_counts, (long long)(L + 1) * Vt * B, WHOLEMEMORY_DT_INT));
+      WGB_CUDA_TRY(cudaMemcpyAsync(out_sc, pd.tbase, sizeof(int) * (size_t)(L + 1) * (size_t)Vt * (size_t)B, cudaMemcpyDeviceToDevice, st));
+    }
+    WGB_CUDA_TRY(cudaMemcpyAsync(out_rmo, rmo, sizeof(long long) * (size_t)((long long)B * Vt + 1), cudaMemcpyDeviceToDevice, st));
+    WGB_CUDA_TRY(cudaMemcpyAsync(out_lto, lho, sizeof(long long) * (size_t)((long long)B * T * L + 1), cudaMemcpyDeviceToDevice, st));
+    // edge_renumber_map_offsets[l*T + t] = label_type_hop_offsets[(l*T + t) * L]
+    WGB_CUDA_TRY(cudaMemcpy2DAsync(out_ermo, sizeof(long long), lho, sizeof(long long) * (size_t)L, sizeof(long long), (size_t)((long long)B * T + 1), cudaMemcpyDeviceToDevice, st));
+    const MhHeteroDesc* desc_dev = static_cast<const MhHeteroDesc*>(sp->desc_dev.p);
+    long long max_edges = 0, max_rows = 1;
+    for (int h = 0; h < L; h++)
+      max_edges = std::max(max_edges, ub_edges[h]);
+    for (int t = 0; t <= L; t++)
+      max_rows = std::max(max_rows, ub_rows[t]);
+    if (n_nodes > 0) {
+      mh_hetero_rows_kernel<<<dim3(grid_over(std::min(max_rows, n_nodes), sms), L + 1), 256, 0, st>>>(desc_dev, fr, meta, n_rows_dev, pd.tbase, rmo, out_map);
+      WGB_CHECK_LAUNCH();
+    }
+    if (n_edges > 0 && max_edges > 0) {
+      dim3 grid(grid_over(std::min(max_edges, n_edges), sms), L);
+      auto emit = [&](auto out_tag, auto chunk_tag) {
+        using OutT                = decltype(out_tag);
+        constexpr bool kChunkedId = decltype(chunk_tag)::value;
+        mh_hetero_emit_edges_kernel<OutT, kChunkedId><<<grid, 256, 0, st>>>(desc_dev, n_edges_dev, hb, fr, meta, lho, static_cast<OutT*>(out_majors), static_cast<OutT*>(out_minors), out_eid, out_etype, out_emap);
+      };
+      if (idx64) {
+        if (pd.chunked) emit((long long)0, std::true_type{});
+        else emit((long long)0, std::false_type{});
+      } else {
+        if (pd.chunked) emit((int)0, std::true_type{});
+        else emit((int)0, std::false_type{});
+      }
+      WGB_CHECK_LAUNCH();
+    }
+    mh_mark(sp, "emit", st);
+    mh_collect_marks(sp);
+    return;
+  }
   void* out_minors   = output_alloc(c.env, c.minors, n_edges, idx_dt);
   void* out_majors   = (!csr && c.majors) ? output_alloc(c.env, c.majors, n_edges, idx_dt) : nullptr;
   long long* out_eid = static_cast<long long*>(output_alloc(c.env, c.edge_id, n_edges, WHOLEMEMORY_DT_INT64));
@@ -1107,10 +1440,11 @@ wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop
   cudaDeviceSynchronize();
   drop(s->table); drop(s->seed_slot); drop(s->slabel); drop(s->scan_state); drop(s->small_i32); drop(s->small_i64); drop(s->counts); drop(s->base);
   for (int i = 0; i <= wgb::kMaxHops; i++) {
-    drop(s->frontier[i]); drop(s->flabel[i]); drop(s->fr_off[i]);
+    drop(s->frontier[i]); drop(s->flabel[i]); drop(s->fr_off[i]); drop(s->tcnt[i]); drop(s->typed[i]);
   }
+  drop(s->vscan_state); drop(s->tbase); drop(s->desc_dev);
   for (int i = 0; i < wgb::kMaxHops; i++) {
-    drop(s->off[i]); drop(s->dest[i]); drop(s->erow[i]); drop(s->gid[i]); drop(s->slot[i]); drop(s->rank_of[i]);
+    drop(s->off[i]); drop(s->dest[i]); drop(s->erow[i]); drop(s->gid[i]); drop(s->slot[i]); drop(s->rank_of[i]); drop(s->pos[i]);
   }
   if (s->h_totals) cudaFreeHost(s->h_totals);
   if (s->ready) cudaEventDestroy(s->ready);
@@ -1122,81 +1456,163 @@ wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop
   return WHOLEMEMORY_SUCCESS;
 }
 
-wholememory_error_code_t wholegraph_multihop_neighbor_sample_begin(
-  wholegraph_multihop_sampler_t sampler, wholememory_tensor_t csr_row_ptr, wholememory_tensor_t csr_col,
-  wholememory_tensor_t csr_weight, wholememory_tensor_t csr_edge_id, wholememory_tensor_t seeds,
-  wholememory_tensor_t label_offsets, const int* fanout, int num_hops, unsigned long long random_state, int flags,
-  void* stream)
+namespace wgb {
+
+// shared by the homogeneous and the heterogeneous entry points: validate, fill the call, dispatch on (col dtype, chunked)
+static wholememory_error_code_t multihop_begin_entry(const char* what, wholegraph_multihop_sampler_t sampler, int T,
+                                                     const wholememory_tensor_t* csr_row_ptr, const wholememory_tensor_t* csr_col,
+                                                     const wholememory_tensor_t* csr_weight, const wholememory_tensor_t* csr_edge_id,
+                                                     const long long* vertex_type_offsets, int Vt, bool hetero,
+                                                     wholememory_tensor_t seeds, wholememory_tensor_t label_offsets,
+                                                     const int* fanout, int num_hops, unsigned long long random_state, int flags,
+                                                     void* stream)
 {
-  using namespace wgb;
   if (!sampler || !csr_row_ptr || !csr_col || !seeds || !label_offsets || !fanout) return WHOLEMEMORY_INVALID_INPUT;
+  if (T < 1 || T > kMaxEdgeTypes || Vt < 1 || Vt > kMaxVertexTypes) return WHOLEMEMORY_INVALID_INPUT;
   if (num_hops < 1 || num_hops >= kMaxHops - 1) return WHOLEMEMORY_INVALID_INPUT;
-  auto* rd = wholememory_tensor_get_tensor_description(csr_row_ptr);
-  auto* cd = wholememory_tensor_get_tensor_description(csr_col);
   auto* sd = wholememory_tensor_get_tensor_description(seeds);
   auto* ld = wholememory_tensor_get_tensor_description(label_offsets);
-  if (rd->dim != 1 || cd->dim != 1 || sd->dim != 1 || ld->dim != 1) return WHOLEMEMORY_INVALID_INPUT;
-  if (rd->dtype != WHOLEMEMORY_DT_INT64 || ld->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
-  if (cd->dtype != WHOLEMEMORY_DT_INT && cd->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
+  if (sd->dim != 1 || ld->dim != 1 || ld->dtype != WHOLEMEMORY_DT_INT64 || ld->sizes[0] < 1) return WHOLEMEMORY_INVALID_INPUT;
   if (sd->dtype != WHOLEMEMORY_DT_INT && sd->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
-  if (ld->sizes[0] < 1 || rd->sizes[0] < 1) return WHOLEMEMORY_INVALID_INPUT;
-  for (int h = 0; h < num_hops; h++)
-    if (fanout[h] > 1024) return WHOLEMEMORY_NOT_IMPLEMENTED;
-  if (csr_weight) {
-    auto* wd = wholememory_tensor_get_tensor_description(csr_weight);
-    if (wd->dim != 1 || wd->sizes[0] != cd->sizes[0] || (wd->dtype != WHOLEMEMORY_DT_FLOAT && wd->dtype != WHOLEMEMORY_DT_DOUBLE)) return WHOLEMEMORY_INVALID_INPUT;
+  bool weighted = csr_weight != nullptr && csr_weight[0] != nullptr;
+  for (int t = 0; t < T; t++) {
+    if (!csr_row_ptr[t] || !csr_col[t]) return WHOLEMEMORY_INVALID_INPUT;
+    auto* rd = wholememory_tensor_get_tensor_description(csr_row_ptr[t]);
+    auto* cd = wholememory_tensor_get_tensor_description(csr_col[t]);
+    auto* r0 = wholememory_tensor_get_tensor_description(csr_row_ptr[0]);
+    auto* c0 = wholememory_tensor_get_tensor_description(csr_col[0]);
+    if (rd->dim != 1 || cd->dim != 1 || rd->dtype != WHOLEMEMORY_DT_INT64 || rd->sizes[0] < 1) return WHOLEMEMORY_INVALID_INPUT;
+    if (cd->dtype != WHOLEMEMORY_DT_INT && cd->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
+    if (rd->sizes[0] != r0->sizes[0] || cd->dtype != c0->dtype) return WHOLEMEMORY_INVALID_INPUT;  // one id space, one id type
+    if (weighted != (csr_weight != nullptr && csr_weight[t] != nullptr)) return WHOLEMEMORY_INVALID_INPUT;
+    if (weighted) {
+      auto* wd = wholememory_tensor_get_tensor_description(csr_weight[t]);
+      auto* w0 = wholememory_tensor_get_tensor_description(csr_weight[0]);
+      if (wd->dim != 1 || wd->sizes[0] != cd->sizes[0] || (wd->dtype != WHOLEMEMORY_DT_FLOAT && wd->dtype != WHOLEMEMORY_DT_DOUBLE) || wd->dtype != w0->dtype) return WHOLEMEMORY_INVALID_INPUT;
+    }
+    if (csr_edge_id && csr_edge_id[t]) {
+      auto* ed = wholememory_tensor_get_tensor_description(csr_edge_id[t]);
+      if (ed->dim != 1 || ed->sizes[0] != cd->sizes[0] || ed->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
+    }
   }
-  if (csr_edge_id) {
-    auto* ed = wholememory_tensor_get_tensor_description(csr_edge_id);
-    if (ed->dim != 1 || ed->sizes[0] != cd->sizes[0] || ed->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
+  for (int i = 0; i < num_hops * T; i++)
+    if (fanout[i] > 1024) return WHOLEMEMORY_NOT_IMPLEMENTED;
+  if (hetero) {
+    if (!vertex_type_offsets || vertex_type_offsets[0] != 0) return WHOLEMEMORY_INVALID_INPUT;
+    for (int v = 0; v < Vt; v++)
+      if (vertex_type_offsets[v + 1] < vertex_type_offsets[v]) return WHOLEMEMORY_INVALID_INPUT;
   }
-  return guarded("wholegraph_multihop_neighbor_sample_begin", [&] {
+  return guarded(what, [&] {
     WGB_EXPECTS(sd->sizes[0] < (1LL << 31) - kScanTile, "too many seeds for one call");
     WGB_EXPECTS(ld->sizes[0] - 1 < (1LL << 23), "too many labels for one call");
     MhCall c;
-    memset(&c.wgt, 0, sizeof(c.wgt));
-    memset(&c.eid, 0, sizeof(c.eid));
-    c.sp          = sampler;
-    c.row_ptr     = make_chunk_ref(csr_row_ptr);
-    c.row_ptr_off = (unsigned long long)rd->storage_offset;
-    c.col         = make_chunk_ref(csr_col);
-    c.col_off     = (unsigned long long)cd->storage_offset;
-    c.col_dtype   = cd->dtype;
-    c.weighted    = csr_weight != nullptr;
-    c.wgt_off     = 0;
-    c.wgt_dtype   = WHOLEMEMORY_DT_FLOAT;
-    if (csr_weight) {
-      c.wgt       = make_chunk_ref(csr_weight);
-      c.wgt_off   = (unsigned long long)wholememory_tensor_get_tensor_description(csr_weight)->storage_offset;
-      c.wgt_dtype = wholememory_tensor_get_tensor_description(csr_weight)->dtype;
+    c.sp        = sampler;
+    c.T         = T;
+    c.Vt        = Vt;
+    c.hetero    = hetero;
+    c.weighted  = weighted;
+    c.wgt_dtype = weighted ? wholememory_tensor_get_tensor_description(csr_weight[0])->dtype : WHOLEMEMORY_DT_FLOAT;
+    c.col_dtype = wholememory_tensor_get_tensor_description(csr_col[0])->dtype;
+    c.chunked   = false;
+    for (int t = 0; t < T; t++) {
+      MhTypeCsr& g = c.csr[t];
+      memset(&g.wgt, 0, sizeof(g.wgt));
+      memset(&g.eid, 0, sizeof(g.eid));
+      g.row_ptr     = make_chunk_ref(csr_row_ptr[t]);
+      g.row_ptr_off = (unsigned long long)wholememory_tensor_get_tensor_description(csr_row_ptr[t])->storage_offset;
+      g.col         = make_chunk_ref(csr_col[t]);
+      g.col_off     = (unsigned long long)wholememory_tensor_get_tensor_description(csr_col[t])->storage_offset;
+      c.chunked     = c.chunked || g.row_ptr.world > 1 || g.col.world > 1;
+      if (weighted) {
+        g.wgt     = make_chunk_ref(csr_weight[t]);
+        g.wgt_off = (unsigned long long)wholememory_tensor_get_tensor_description(csr_weight[t])->storage_offset;
+        c.chunked = c.chunked || g.wgt.world > 1;
+      }
+      g.has_eid = csr_edge_id && csr_edge_id[t];
+      if (g.has_eid) {
+        g.eid     = make_chunk_ref(csr_edge_id[t]);
+        g.eid_off = (unsigned long long)wholememory_tensor_get_tensor_description(csr_edge_id[t])->storage_offset;
+        c.chunked = c.chunked || g.eid.world > 1;
+      }
     }
-    c.has_eid = csr_edge_id != nullptr;
-    c.eid_off = 0;
-    if (csr_edge_id) {
-      c.eid     = make_chunk_ref(csr_edge_id);
-      c.eid_off = (unsigned long long)wholememory_tensor_get_tensor_description(csr_edge_id)->storage_offset;
-    }
-    c.chunked = c.row_ptr.world > 1 || c.col.world > 1 || (c.weighted && c.wgt.world > 1) || (c.has_eid && c.eid.world > 1);
     c.seeds         = wholememory_tensor_get_data_pointer(seeds);
     c.seed_dtype    = sd->dtype;
     c.label_offsets = static_cast<const long long*>(wholememory_tensor_get_data_pointer(label_offsets));
     c.S             = (int)sd->sizes[0];
     c.B             = (int)ld->sizes[0] - 1;
     c.L             = num_hops;
-    for (int h = 0; h < num_hops; h++)
-      c.fanout[h] = fanout[h];
-    c.V = (unsigned long long)(rd->sizes[0] - 1);
+    for (int i = 0; i < num_hops * T; i++)
+      c.fanout[i] = fanout[i];
+    c.V = (unsigned long long)(wholememory_tensor_get_tensor_description(csr_row_ptr[0])->sizes[0] - 1);
+    for (int v = 0; v <= Vt; v++)
+      c.vto[v] = hetero ? vertex_type_offsets[v] : (v == 0 ? 0 : (long long)c.V);
+    if (hetero) WGB_EXPECTS((unsigned long long)c.vto[Vt] <= c.V, "vertex_type_offsets exceed the vertex id space of the CSRs");
     WGB_EXPECTS((long double)c.V * (long double)std::max(c.B, 1) < 72057594037927936.0L, "labels x vertices must stay below 2^56");
-    c.random_state      = random_state;
-    c.flags             = flags;
-    c.stream            = as_stream(stream);
-    if (cd->dtype == WHOLEMEMORY_DT_INT) {
+    c.random_state = random_state;
+    c.flags        = flags;
+    c.stream       = as_stream(stream);
+    if (c.col_dtype == WHOLEMEMORY_DT_INT) {
       if (c.chunked) multihop_begin<int, true>(c);
       else multihop_begin<int, false>(c);
     } else {
       if (c.chunked) multihop_begin<long long, true>(c);
       else multihop_begin<long long, false>(c);
     }
+  });
+}
+
+}  // namespace wgb
+
+wholememory_error_code_t wholegraph_multihop_neighbor_sample_begin(
+  wholegraph_multihop_sampler_t sampler, wholememory_tensor_t csr_row_ptr, wholememory_tensor_t csr_col,
+  wholememory_tensor_t csr_weight, wholememory_tensor_t csr_edge_id, wholememory_tensor_t seeds,
+  wholememory_tensor_t label_offsets, const int* fanout, int num_hops, unsigned long long random_state, int flags,
+  void* stream)
+{
+  return wgb::multihop_begin_entry("wholegraph_multihop_neighbor_sample_begin", sampler, 1, &csr_row_ptr, &csr_col, &csr_weight,
+                                   &csr_edge_id, nullptr, 1, false, seeds, label_offsets, fanout, num_hops, random_state, flags, stream);
+}
+
+wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_begin(
+  wholegraph_multihop_sampler_t sampler, int num_edge_types, const wholememory_tensor_t* csr_row_ptr,
+  const wholememory_tensor_t* csr_col, const wholememory_tensor_t* csr_weight, const wholememory_tensor_t* csr_edge_id,
+  const long long* vertex_type_offsets, int num_vertex_types, wholememory_tensor_t seeds, wholememory_tensor_t label_offsets,
+  const int* fanout, int num_hops, unsigned long long random_state, int flags, void* stream)
+{
+  if (flags & WHOLEGRAPH_MULTIHOP_CSR) return WHOLEMEMORY_INVALID_INPUT;
+  return wgb::multihop_begin_entry("wholegraph_hetero_multihop_neighbor_sample_begin", sampler, num_edge_types, csr_row_ptr, csr_col,
+                                   csr_weight, csr_edge_id, vertex_type_offsets, num_vertex_types, true, seeds, label_offsets, fanout,
+                                   num_hops, random_state, flags, stream);
+}
+
+wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_finish(
+  wholegraph_multihop_sampler_t sampler, void* out_majors_ctx, void* out_minors_ctx, void* out_edge_id_ctx,
+  void* out_edge_type_ctx, void* out_label_type_hop_offsets_ctx, void* out_renumber_map_ctx,
+  void* out_renumber_map_offsets_ctx, void* out_edge_renumber_map_ctx, void* out_edge_renumber_map_offsets_ctx,
+  void* out_label_type_step_base_ctx, wholememory_env_func_t* p_env_fns, void* stream)
+{
+  using namespace wgb;
+  if (!sampler || !p_env_fns) return WHOLEMEMORY_INVALID_INPUT;
+  if (!out_majors_ctx || !out_minors_ctx || !out_edge_id_ctx || !out_edge_type_ctx || !out_label_type_hop_offsets_ctx ||
+      !out_renumber_map_ctx || !out_renumber_map_offsets_ctx || !out_edge_renumber_map_ctx || !out_edge_renumber_map_offsets_ctx)
+    return WHOLEMEMORY_INVALID_INPUT;
+  return guarded("wholegraph_hetero_multihop_neighbor_sample_finish", [&] {
+    WGB_EXPECTS(sampler->pending.active && sampler->pending.hetero, "no heterogeneous call in flight on this sampler object");
+    MhOutCtx o;
+    o.majors                    = out_majors_ctx;
+    o.minors                    = out_minors_ctx;
+    o.edge_id                   = out_edge_id_ctx;
+    o.edge_type                 = out_edge_type_ctx;
+    o.lho                       = out_label_type_hop_offsets_ctx;
+    o.map                       = out_renumber_map_ctx;
+    o.rmo                       = out_renumber_map_offsets_ctx;
+    o.edge_renumber_map         = out_edge_renumber_map_ctx;
+    o.edge_renumber_map_offsets = out_edge_renumber_map_offsets_ctx;
+    o.major_offsets             = nullptr;
+    o.step_counts               = out_label_type_step_base_ctx;
+    o.env                       = p_env_fns;
+    o.stream                    = as_stream(stream);
+    multihop_finish(sampler, o);
   });
 }
 
@@ -1209,6 +1625,7 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample_finish(
   if (!sampler || !p_env_fns) return WHOLEMEMORY_INVALID_INPUT;
   if (!out_minors_ctx || !out_edge_id_ctx || !out_label_hop_offsets_ctx || !out_renumber_map_ctx || !out_renumber_map_offsets_ctx) return WHOLEMEMORY_INVALID_INPUT;
   return guarded("wholegraph_multihop_neighbor_sample_finish", [&] {
+    WGB_EXPECTS(!(sampler->pending.active && sampler->pending.hetero), "a heterogeneous call must be finished with wholegraph_hetero_multihop_neighbor_sample_finish");
     MhOutCtx o;
     o.majors        = out_majors_ctx;
     o.minors        = out_minors_ctx;

@@ -31,6 +31,18 @@ _finish = wmb.native_symbol("wholegraph_multihop_neighbor_sample_finish")
 _finish.restype = ctypes.c_int
 _finish.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
 
+_hbegin = wmb.native_symbol("wholegraph_hetero_multihop_neighbor_sample_begin")
+_hbegin.restype = ctypes.c_int
+_hbegin.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                    ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, _vp, _vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                    ctypes.c_ulonglong, ctypes.c_int, _vp]
+_hfinish = wmb.native_symbol("wholegraph_hetero_multihop_neighbor_sample_finish")
+_hfinish.restype = ctypes.c_int
+_hfinish.argtypes = [_vp] * 13
+
+_HETERO_OUT_NAMES = ("majors", "minors", "edge_id", "edge_type", "label_type_hop_offsets", "renumber_map", "renumber_map_offsets",
+                     "edge_renumber_map", "edge_renumber_map_offsets", "label_type_step_base")
+
 _OUT_NAMES = ("majors", "minors", "edge_id", "label_hop_offsets", "renumber_map", "renumber_map_offsets", "major_offsets",
               "label_step_base")
 
@@ -83,6 +95,46 @@ class MultiHopSampler(object):
         wmb.check_wholememory_error_code(err)
         return PendingSample(self, keep, csr, len(fanout))
 
+    def sample_hetero_async(self, csr_row_ptrs, csr_cols, vertex_type_offsets, seeds: "torch.Tensor",
+                            label_offsets: "torch.Tensor", fanout: List[int], random_state: int, *, csr_weights=None,
+                            csr_edge_ids=None, int64_ids: bool = False) -> "PendingHeteroSample":
+        """Heterogeneous call group: one CSR per edge type over one global id space (``csr_row_ptrs[t]``,
+        ``csr_cols[t]``), ``vertex_type_offsets`` [Vt+1] (host ints), ``fanout`` laid out [hop * T + edge type]."""
+        assert seeds.is_cuda and seeds.dim() == 1 and seeds.dtype in (torch.int32, torch.int64)
+        label_offsets = label_offsets.to(device=seeds.device, dtype=torch.int64)
+        T = len(csr_row_ptrs)
+        assert T >= 1 and len(csr_cols) == T and len(fanout) % T == 0
+        keep = []
+
+        def handle_array(ts):
+            if ts is None:
+                return None
+            arr = (_vp * T)()
+            for i, t in enumerate(ts):
+                h, k = _handle(t)
+                arr[i] = h
+                keep.append(k)
+            return arr
+
+        rp, col = handle_array(csr_row_ptrs), handle_array(csr_cols)
+        wgt, eid = handle_array(csr_weights), handle_array(csr_edge_ids)
+        hs, ks = _handle(seeds)
+        hl, kl = _handle(label_offsets)
+        keep += [ks, kl]
+        vto = [int(v) for v in vertex_type_offsets]
+        vto_c = (ctypes.c_longlong * len(vto))(*vto)
+        fan = (ctypes.c_int * len(fanout))(*[int(f) for f in fanout])
+        hops = len(fanout) // T
+        err = _hbegin(self._h, T, rp, col, wgt, eid, vto_c, len(vto) - 1, hs, hl, fan, hops,
+                      ctypes.c_ulonglong(random_state & 0xFFFFFFFFFFFFFFFF), FLAG_INT64_IDS if int64_ids else 0, get_stream())
+        wmb.check_wholememory_error_code(err)
+        return PendingHeteroSample(self, keep, hops, len(vto) - 1)
+
+    def sample_hetero(self, *args, **kwargs):
+        """Returns a dict with majors, minors, edge_id, edge_type, label_type_hop_offsets, renumber_map,
+        renumber_map_offsets, edge_renumber_map, edge_renumber_map_offsets, label_type_step_base [L+1, Vt, B]."""
+        return self.sample_hetero_async(*args, **kwargs).result()
+
     def sample(self, csr_row_ptr, csr_col, seeds: "torch.Tensor", label_offsets: "torch.Tensor", fanout: List[int],
                random_state: int, *, csr_weight=None, csr_edge_id=None, compression: str = "COO",
                int64_ids: bool = False):
@@ -119,6 +171,30 @@ class PendingSample(object):
         out = {n: ctx[n].get_tensor() for n in _OUT_NAMES if ctx[n].get_tensor() is not None}
         # [L+1, B]: first local id of the vertices each label discovered at step t (0 = seeds)
         out["label_step_base"] = out["label_step_base"].view(self._hops + 1, -1)
+        self._out = out
+        self._keep = None
+        return out
+
+
+class PendingHeteroSample(object):
+    """A heterogeneous call group whose hops are running on the device (MultiHopSampler.sample_hetero_async)."""
+
+    def __init__(self, sampler: MultiHopSampler, keep, hops: int, num_vertex_types: int):
+        self._sampler = sampler
+        self._keep = keep
+        self._hops = hops
+        self._vt = num_vertex_types
+        self._out = None
+
+    def result(self):
+        if self._out is not None:
+            return self._out
+        ctx = {n: TorchMemoryContext() for n in _HETERO_OUT_NAMES}
+        err = _hfinish(self._sampler._h, *[ctx[n].get_c_context() for n in _HETERO_OUT_NAMES], get_wholegraph_env_fns(),
+                       get_stream())
+        wmb.check_wholememory_error_code(err)
+        out = {n: ctx[n].get_tensor() for n in _HETERO_OUT_NAMES}
+        out["label_type_step_base"] = out["label_type_step_base"].view(self._hops + 1, self._vt, -1)
         self._out = out
         self._keep = None
         return out

@@ -115,6 +115,57 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample_finish(wholegraph_m
                                                                     wholememory_env_func_t* p_env_fns,
                                                                     void* stream);
 
+/* Heterogeneous form: what cugraph-pyg asks of pylibcugraph.heterogeneous_{uniform,biased}_neighbor_sample
+ * (/root/reference/python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:53-94, 784-819) and decodes in
+ * HeterogeneousSampleReader (/root/reference/python/cugraph-pyg/cugraph_pyg/sampler/sampler.py:280-490).
+ *
+ *   num_edge_types T (<= 16): one CSR per edge type over ONE global vertex id space (csr_row_ptr[t] int64 [V+1], csr_col[t],
+ *     optional csr_weight[t] -- all types or none --, optional csr_edge_id[t]); all cols share one dtype
+ *   vertex_type_offsets  host int64 [Vt+1] (Vt <= 16): vertex type vt owns the global ids [off[vt], off[vt+1])
+ *   fanout  [num_hops * T], laid out [hop * T + edge type]  (neighbor_loader.py:192-201)
+ *   hop h samples the whole frontier once per edge type with seed  random_state + h*0x9E3779B97F4A7C15 + t*0xD1B54A32D192ED03;
+ *   edge order inside a hop is (frontier row, edge type, slot), vertices are deduplicated per label in that order.
+ *
+ * Outputs (COO only, like the reference):
+ *   majors / minors           [E_s] ids local to (label, vertex type of the endpoint), hop-monotone, seeds first
+ *   edge_id                   int64 [E_s] position inside the (label, edge type) group
+ *   edge_type                 int32 [E_s]
+ *   label_type_hop_offsets    int64 [B*T*L+1], groups ordered [label][edge type][hop]
+ *   renumber_map              int64 [N_s] global ids; renumber_map_offsets int64 [B*Vt+1], segments [label][vertex type]
+ *   edge_renumber_map         int64 [E_s] original edge id of every output edge (csr_edge_id value, else the CSR position);
+ *   edge_renumber_map_offsets int64 [B*T+1]      => original id = edge_renumber_map[offsets[l*T+t] + edge_id]
+ *   label_type_step_base      int32 [(L+1)*Vt*B] optional: first local id of the type-vt vertices label l discovered at step s
+ */
+wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_begin(wholegraph_multihop_sampler_t sampler,
+                                                                          int num_edge_types,
+                                                                          const wholememory_tensor_t* csr_row_ptr,
+                                                                          const wholememory_tensor_t* csr_col,
+                                                                          const wholememory_tensor_t* csr_weight,
+                                                                          const wholememory_tensor_t* csr_edge_id,
+                                                                          const long long* vertex_type_offsets,
+                                                                          int num_vertex_types,
+                                                                          wholememory_tensor_t seeds,
+                                                                          wholememory_tensor_t label_offsets,
+                                                                          const int* fanout,
+                                                                          int num_hops,
+                                                                          unsigned long long random_state,
+                                                                          int flags,
+                                                                          void* stream);
+
+wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_finish(wholegraph_multihop_sampler_t sampler,
+                                                                           void* out_majors_ctx,
+                                                                           void* out_minors_ctx,
+                                                                           void* out_edge_id_ctx,
+                                                                           void* out_edge_type_ctx,
+                                                                           void* out_label_type_hop_offsets_ctx,
+                                                                           void* out_renumber_map_ctx,
+                                                                           void* out_renumber_map_offsets_ctx,
+                                                                           void* out_edge_renumber_map_ctx,
+                                                                           void* out_edge_renumber_map_offsets_ctx,
+                                                                           void* out_label_type_step_base_ctx,
+                                                                           wholememory_env_func_t* p_env_fns,
+                                                                           void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * A1: CSR neighbourhood aggregation of the sampled block (the SpMM that consumes the sampler output).
  *

@@ -798,4 +798,201 @@ void wgo_multihop_copy(void* h, int32_t* majors, int32_t* minors, int64_t* edge_
 }
 void wgo_multihop_free(void* h) { delete (wgo_multihop_result*)h; }
 
+
+// ---- heterogeneous multi-hop sampling ---------------------------------------------------------------
+// What cugraph-pyg asks of pylibcugraph.heterogeneous_{uniform,biased}_neighbor_sample
+// (python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:53-94, 784-819; fan-out vector laid out
+// [hop * T + etype], loader/neighbor_loader.py:192-201) and what HeterogeneousSampleReader decodes
+// (sampler/sampler.py:280-490); the only value-level pin in the reference is
+// tests/sampler/test_distributed_sampler.py:19-150 (fan-out -1), which tests/test_oracle_cpu.py replays.
+//
+// Definition used by this project (libcugraph itself is not in the tree):
+//   * vertices carry GLOBAL ids, vertex type vt owns [vtype_offsets[vt], vtype_offsets[vt+1]);
+//     edge type t has its own CSR over the global id space (rows of other types are empty);
+//   * hop h: the frontier is the label-major list of vertices new in the previous step (step 0: the
+//     label's distinct seeds).  For every edge type t with fanout[h*T+t] != 0 the WHOLE frontier is sampled on
+//     CSR_t with the one-hop algorithm (S1/S2), seed = type_seed(hop_seed(random_state, h), t);
+//   * edge order inside a hop: frontier row, then edge type, then sample slot; vertices are deduplicated per
+//     label in that order (first occurrence), over all types at once;
+//   * local ids restart per (label, vertex type): the i-th vertex of type vt that label l discovered;
+//   * outputs are grouped [label][edge type][hop]; edge_id is the position inside its (label, edge type)
+//     group and edge_renumber_map holds the original edge ids in that order (edge[etype] = emap[edge_id],
+//     sampler.py:334-341).
+struct wgo_hetero_result {
+  std::vector<int32_t> majors, minors, edge_type;
+  std::vector<int64_t> edge_id;
+  std::vector<int64_t> label_type_hop_offsets;     // B*T*L+1
+  std::vector<int64_t> renumber_map;               // [label][vtype] segments, global ids
+  std::vector<int64_t> renumber_map_offsets;       // B*Vt+1
+  std::vector<int64_t> edge_renumber_map;          // original edge ids, output order
+  std::vector<int64_t> edge_renumber_map_offsets;  // B*T+1
+  std::vector<int32_t> step_base;                  // [(L+1)][Vt][B] first typed local id discovered at step s
+};
+
+uint64_t wgo_type_seed(uint64_t hop_seed, int etype) { return hop_seed + (uint64_t)etype * 0xD1B54A32D192ED03ULL; }
+
+void* wgo_hetero_multihop_sample(int num_edge_types, const int64_t* const* row_ptr, const void* const* col, int col_dtype,
+                                 const void* const* wgt, int wgt_dtype, const int64_t* const* edge_ids,
+                                 const int64_t* vtype_offsets, int num_vertex_types, const int64_t* seeds,
+                                 const int64_t* label_offsets, int64_t num_labels, const int32_t* fanout, int num_hops,
+                                 uint64_t random_state)
+{
+  auto* res       = new wgo_hetero_result();
+  const int64_t B = num_labels;
+  const int L = num_hops, T = num_edge_types, Vt = num_vertex_types;
+  auto vtype_of = [&](int64_t v) {
+    int vt = 0;
+    while (vt + 1 < Vt && v >= vtype_offsets[vt + 1])
+      vt++;
+    return vt;
+  };
+  std::vector<std::vector<int64_t>> maps(B);  // discovery order, global ids
+  std::vector<std::unordered_map<int64_t, int32_t>> tables(B);
+  std::vector<std::vector<int64_t>> step_end(B, std::vector<int64_t>(L + 2, 0));  // discovery index at the end of step s
+  std::vector<int64_t> front_begin(B), front_end(B);
+  for (int64_t l = 0; l < B; l++) {
+    for (int64_t s = label_offsets[l]; s < label_offsets[l + 1]; s++) {
+      int64_t v = seeds[s];
+      if (tables[l].find(v) == tables[l].end()) {
+        tables[l].insert(std::make_pair(v, (int32_t)maps[l].size()));
+        maps[l].push_back(v);
+      }
+    }
+    front_begin[l] = 0;
+    front_end[l]   = (int64_t)maps[l].size();
+    step_end[l][1] = front_end[l];
+  }
+  struct Edge {
+    int32_t major, minor;  // discovery indices
+    int64_t id;
+  };
+  std::vector<std::vector<Edge>> edges((size_t)B * T * L);
+  for (int h = 0; h < L; h++) {
+    std::vector<int64_t> frontier;
+    std::vector<int64_t> fr_off(B + 1, 0);
+    for (int64_t l = 0; l < B; l++) {
+      fr_off[l] = (int64_t)frontier.size();
+      for (int64_t i = front_begin[l]; i < front_end[l]; i++)
+        frontier.push_back(maps[l][i]);
+    }
+    fr_off[B]  = (int64_t)frontier.size();
+    int64_t nf = (int64_t)frontier.size();
+    std::vector<std::vector<int32_t>> off(T, std::vector<int32_t>(nf + 1, 0));
+    std::vector<std::vector<int64_t>> dest(T), gid(T);
+    for (int t = 0; t < T; t++) {
+      int M = fanout[h * T + t];
+      if (M == 0 || nf == 0) continue;
+      wgo_sample_offsets(row_ptr[t], frontier.data(), DT_INT64, nf, M, off[t].data());
+      int64_t tot = off[t][nf];
+      dest[t].resize(tot);
+      gid[t].resize(tot);
+      std::vector<int32_t> lid(tot);
+      uint64_t hs     = wgo_type_seed(wgo_hop_seed(random_state, h), t);
+      const void* w_t = wgt ? wgt[t] : nullptr;
+      if (col_dtype == DT_INT64) {
+        if (w_t)
+          wgo_weighted_sample(row_ptr[t], col[t], col_dtype, w_t, wgt_dtype, frontier.data(), DT_INT64, nf, M, hs, off[t].data(), dest[t].data(), lid.data(), gid[t].data(), nullptr);
+        else
+          wgo_unweighted_sample(row_ptr[t], col[t], col_dtype, frontier.data(), DT_INT64, nf, M, hs, off[t].data(), dest[t].data(), lid.data(), gid[t].data());
+      } else {
+        std::vector<int32_t> d32(tot);
+        if (w_t)
+          wgo_weighted_sample(row_ptr[t], col[t], col_dtype, w_t, wgt_dtype, frontier.data(), DT_INT64, nf, M, hs, off[t].data(), d32.data(), lid.data(), gid[t].data(), nullptr);
+        else
+          wgo_unweighted_sample(row_ptr[t], col[t], col_dtype, frontier.data(), DT_INT64, nf, M, hs, off[t].data(), d32.data(), lid.data(), gid[t].data());
+        for (int64_t i = 0; i < tot; i++)
+          dest[t][i] = d32[i];
+      }
+    }
+    for (int64_t l = 0; l < B; l++) {
+      int64_t new_begin = (int64_t)maps[l].size();
+      for (int64_t f = fr_off[l]; f < fr_off[l + 1]; f++) {
+        int32_t major = (int32_t)(front_begin[l] + (f - fr_off[l]));
+        for (int t = 0; t < T; t++) {
+          for (int32_t e = off[t][f]; e < off[t][f + 1]; e++) {
+            int64_t v = dest[t][e];
+            auto it   = tables[l].find(v);
+            int32_t id;
+            if (it == tables[l].end()) {
+              id = (int32_t)maps[l].size();
+              tables[l].insert(std::make_pair(v, id));
+              maps[l].push_back(v);
+            } else {
+              id = it->second;
+            }
+            int64_t g = gid[t][e];
+            edges[((size_t)l * T + t) * L + h].push_back(Edge{major, id, (edge_ids && edge_ids[t]) ? edge_ids[t][g] : g});
+          }
+        }
+      }
+      front_begin[l]     = new_begin;
+      front_end[l]       = (int64_t)maps[l].size();
+      step_end[l][h + 2] = front_end[l];
+    }
+  }
+  // typed local ids
+  std::vector<std::vector<int32_t>> typed(B);
+  res->step_base.assign((size_t)(L + 1) * Vt * B, 0);
+  res->renumber_map_offsets.push_back(0);
+  for (int64_t l = 0; l < B; l++) {
+    std::vector<int32_t> counter(Vt, 0);
+    std::vector<std::vector<int64_t>> per_type(Vt);
+    typed[l].resize(maps[l].size());
+    int step = 0;  // step_end[l][s] = number of vertices discovered before step s started
+    for (size_t i = 0; i <= maps[l].size(); i++) {
+      while (step <= L && (int64_t)i == step_end[l][step]) {
+        for (int vt = 0; vt < Vt; vt++)
+          res->step_base[((size_t)step * Vt + vt) * B + l] = counter[vt];
+        step++;
+      }
+      if (i == maps[l].size()) break;
+      int vt      = vtype_of(maps[l][i]);
+      typed[l][i] = counter[vt]++;
+      per_type[vt].push_back(maps[l][i]);
+    }
+    for (int vt = 0; vt < Vt; vt++) {
+      res->renumber_map.insert(res->renumber_map.end(), per_type[vt].begin(), per_type[vt].end());
+      res->renumber_map_offsets.push_back((int64_t)res->renumber_map.size());
+    }
+  }
+  res->label_type_hop_offsets.push_back(0);
+  res->edge_renumber_map_offsets.push_back(0);
+  for (int64_t l = 0; l < B; l++) {
+    for (int t = 0; t < T; t++) {
+      int64_t in_group = 0;
+      for (int h = 0; h < L; h++) {
+        for (auto& e : edges[((size_t)l * T + t) * L + h]) {
+          res->majors.push_back(typed[l][e.major]);
+          res->minors.push_back(typed[l][e.minor]);
+          res->edge_type.push_back(t);
+          res->edge_id.push_back(in_group++);
+          res->edge_renumber_map.push_back(e.id);
+        }
+        res->label_type_hop_offsets.push_back((int64_t)res->majors.size());
+      }
+      res->edge_renumber_map_offsets.push_back((int64_t)res->edge_renumber_map.size());
+    }
+  }
+  return res;
+}
+
+int64_t wgo_hetero_num_edges(void* h) { return (int64_t)((wgo_hetero_result*)h)->majors.size(); }
+int64_t wgo_hetero_num_nodes(void* h) { return (int64_t)((wgo_hetero_result*)h)->renumber_map.size(); }
+void wgo_hetero_copy(void* h, int32_t* majors, int32_t* minors, int32_t* edge_type, int64_t* edge_id, int64_t* lto,
+                     int64_t* renumber_map, int64_t* rmo, int64_t* edge_renumber_map, int64_t* ermo, int32_t* step_base)
+{
+  auto* r = (wgo_hetero_result*)h;
+  memcpy(majors, r->majors.data(), r->majors.size() * 4);
+  memcpy(minors, r->minors.data(), r->minors.size() * 4);
+  memcpy(edge_type, r->edge_type.data(), r->edge_type.size() * 4);
+  memcpy(edge_id, r->edge_id.data(), r->edge_id.size() * 8);
+  memcpy(lto, r->label_type_hop_offsets.data(), r->label_type_hop_offsets.size() * 8);
+  memcpy(renumber_map, r->renumber_map.data(), r->renumber_map.size() * 8);
+  memcpy(rmo, r->renumber_map_offsets.data(), r->renumber_map_offsets.size() * 8);
+  memcpy(edge_renumber_map, r->edge_renumber_map.data(), r->edge_renumber_map.size() * 8);
+  memcpy(ermo, r->edge_renumber_map_offsets.data(), r->edge_renumber_map_offsets.size() * 8);
+  memcpy(step_base, r->step_base.data(), r->step_base.size() * 4);
+}
+void wgo_hetero_free(void* h) { delete (wgo_hetero_result*)h; }
+
 }  // extern "C"

@@ -246,3 +246,63 @@ def multihop_sample(row_ptr, col, seeds, label_offsets, fanout, random_state, we
                             _p(out["renumber_map"]), _p(out["renumber_map_offsets"]))
     lib().wgo_multihop_free(h)
     return out
+
+
+def hetero_multihop_sample(row_ptrs, cols, vertex_type_offsets, seeds, label_offsets, fanout, random_state, weights=None,
+                           edge_ids=None):
+    """Heterogeneous multi-hop sample: one CSR (global vertex ids) per edge type, fanout laid out [hop * T + etype].
+    Returns the pylibcugraph-shaped dict (COO) as numpy arrays."""
+    T = len(row_ptrs)
+    row_ptrs = [np.ascontiguousarray(r, dtype=np.int64) for r in row_ptrs]
+    cols = [np.ascontiguousarray(c) for c in cols]
+    assert all(c.dtype == cols[0].dtype for c in cols)
+    vto = np.ascontiguousarray(vertex_type_offsets, dtype=np.int64)
+    Vt = vto.shape[0] - 1
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    label_offsets = np.ascontiguousarray(label_offsets, dtype=np.int64)
+    fanout = np.ascontiguousarray(fanout, dtype=np.int32).reshape(-1)
+    assert fanout.shape[0] % T == 0
+    L = fanout.shape[0] // T
+    B = label_offsets.shape[0] - 1
+    vp = ctypes.c_void_p
+
+    def ptr_array(arrs):
+        return (vp * T)(*[(a.ctypes.data if a is not None else None) for a in arrs])
+
+    wdt = 0
+    w_arr = None
+    if weights is not None:
+        weights = [np.ascontiguousarray(w) for w in weights]
+        wdt = _dt(weights[0])
+        w_arr = ptr_array(weights)
+    e_arr = None
+    if edge_ids is not None:
+        edge_ids = [None if e is None else np.ascontiguousarray(e, dtype=np.int64) for e in edge_ids]
+        e_arr = ptr_array(edge_ids)
+    fn = lib().wgo_hetero_multihop_sample
+    fn.restype = ctypes.c_void_p
+    h = fn(ctypes.c_int(T), ptr_array(row_ptrs), ptr_array(cols), _dt(cols[0]), w_arr, ctypes.c_int(wdt), e_arr, _p(vto),
+           ctypes.c_int(Vt), _p(seeds), _p(label_offsets), ctypes.c_int64(B), _p(fanout), ctypes.c_int(L),
+           ctypes.c_uint64(random_state))
+    h = vp(h)
+    lib().wgo_hetero_num_edges.restype = ctypes.c_int64
+    lib().wgo_hetero_num_nodes.restype = ctypes.c_int64
+    ne = int(lib().wgo_hetero_num_edges(h))
+    nn = int(lib().wgo_hetero_num_nodes(h))
+    out = {
+        "majors": np.empty(ne, dtype=np.int32),
+        "minors": np.empty(ne, dtype=np.int32),
+        "edge_type": np.empty(ne, dtype=np.int32),
+        "edge_id": np.empty(ne, dtype=np.int64),
+        "label_type_hop_offsets": np.empty(B * T * L + 1, dtype=np.int64),
+        "renumber_map": np.empty(nn, dtype=np.int64),
+        "renumber_map_offsets": np.empty(B * Vt + 1, dtype=np.int64),
+        "edge_renumber_map": np.empty(ne, dtype=np.int64),
+        "edge_renumber_map_offsets": np.empty(B * T + 1, dtype=np.int64),
+        "label_type_step_base": np.empty((L + 1, Vt, B), dtype=np.int32),
+    }
+    lib().wgo_hetero_copy(h, _p(out["majors"]), _p(out["minors"]), _p(out["edge_type"]), _p(out["edge_id"]),
+                          _p(out["label_type_hop_offsets"]), _p(out["renumber_map"]), _p(out["renumber_map_offsets"]),
+                          _p(out["edge_renumber_map"]), _p(out["edge_renumber_map_offsets"]), _p(out["label_type_step_base"]))
+    lib().wgo_hetero_free(h)
+    return out

@@ -317,3 +317,108 @@ def test_multihop_reference_hetero_pin_homogeneous_projection(oracle):
             assert sorted(eids[pos][sel].tolist()) == exp["eids"]
             assert sorted(m[res["majors"][a:b]][sel].tolist()) == exp["srcs"]
             assert sorted(m[res["minors"][a:b]][sel].tolist()) == exp["dsts"]
+
+
+# ---- heterogeneous multi-hop ---------------------------------------------------------------------------
+def test_hetero_reference_pin_fanout_all(oracle):
+    """python/cugraph-pyg/cugraph_pyg/tests/sampler/test_distributed_sampler.py:19-150, assertion by assertion."""
+    from graphs import typed_csrs
+
+    pin = PINS["hetero_fanout_all"]
+    srcs, dsts, eids, etps = (np.array(pin[k]) for k in ("srcs", "dsts", "eids", "etps"))
+    row_ptrs, cols, pos = typed_csrs(srcs, dsts, etps, 2, 10)
+    out = oracle.hetero_multihop_sample(row_ptrs, cols, [0, 4, 10], np.array([4, 5]), np.array([0, 2]), [-1, -1, -1, -1], 62,
+                                        edge_ids=[eids[p] for p in pos])
+    lho, rmo, ermo = out["label_type_hop_offsets"], out["renumber_map_offsets"], out["edge_renumber_map_offsets"]
+    dmap0 = out["renumber_map"][rmo[0]:rmo[1]]
+    smap = out["renumber_map"][rmo[1]:rmo[2]]
+    expect = {  # (etype, hop): (count, edge ids, sources, destinations), all compared sorted as the reference does
+        (0, 0): (2, [0, 1], [4, 5], [0, 1]),
+        (0, 1): (2, [4, 5], [8, 9], [0, 3]),
+        (1, 0): (3, [5, 6, 7], [4, 5, 5], [8, 9, 9]),
+        (1, 1): (3, [0, 1, 2], [8, 8, 9], [4, 5, 6]),
+    }
+    for (t, h), (cnt, e_exp, s_exp, d_exp) in expect.items():
+        a, b = lho[t * 2 + h], lho[t * 2 + h + 1]
+        assert b - a == cnt
+        emap = out["edge_renumber_map"][ermo[t]:ermo[t + 1]]
+        assert sorted(emap[out["edge_id"][a:b]].tolist()) == e_exp
+        assert sorted(smap[out["majors"][a:b]].tolist()) == s_exp
+        dmap = dmap0 if t == 0 else smap
+        assert sorted(dmap[out["minors"][a:b]].tolist()) == d_exp
+        assert (out["edge_type"][a:b] == t).all()
+
+
+def test_hetero_with_one_type_equals_homogeneous(oracle):
+    row_ptr, col = random_csr(3000, 30000, seed=4)
+    rng = np.random.default_rng(3)
+    seeds = np.concatenate([rng.permutation(3000)[:50], rng.permutation(3000)[:20]]).astype(np.int64)
+    lo = np.array([0, 50, 70], dtype=np.int64)
+    for fanout in ([5, 3], [-1, 2], [4, 0, 3]):
+        homo = oracle.multihop_sample(row_ptr, col, seeds, lo, fanout, 11)
+        het = oracle.hetero_multihop_sample([row_ptr], [col], [0, 3000], seeds, lo, fanout, 11)
+        assert np.array_equal(het["majors"], homo["majors"])
+        assert np.array_equal(het["minors"], homo["minors"])
+        assert np.array_equal(het["renumber_map"], homo["renumber_map"])
+        assert np.array_equal(het["renumber_map_offsets"], homo["renumber_map_offsets"])
+        assert np.array_equal(het["label_type_hop_offsets"], homo["label_hop_offsets"])
+        assert np.array_equal(het["edge_renumber_map"], homo["edge_id"])
+
+
+def check_hetero_structure(res, vto, row_ptrs, cols, edge_types, seeds, lo, fanout):
+    """Invariants of the heterogeneous output contract (sampler.py:280-490)."""
+    T, Vt = len(row_ptrs), len(vto) - 1
+    B = len(lo) - 1
+    L = len(fanout) // T
+    lho, rmo, ermo = res["label_type_hop_offsets"], res["renumber_map_offsets"], res["edge_renumber_map_offsets"]
+    assert lho[0] == 0 and lho[-1] == len(res["majors"]) and (np.diff(lho) >= 0).all()
+    assert np.array_equal(ermo, lho[::L])
+    base = res["label_type_step_base"]
+    for l in range(B):
+        maps = [res["renumber_map"][rmo[l * Vt + vt]:rmo[l * Vt + vt + 1]] for vt in range(Vt)]
+        for vt in range(Vt):
+            assert ((maps[vt] >= vto[vt]) & (maps[vt] < vto[vt + 1])).all()
+            assert len(np.unique(maps[vt])) == len(maps[vt])
+            b = [base[s, vt, l] for s in range(L + 1)] + [len(maps[vt])]
+            assert all(b[s] <= b[s + 1] for s in range(L + 1)) and b[0] == 0
+        # seeds come first, in first-occurrence order, split by type
+        label_seeds = seeds[lo[l]:lo[l + 1]]
+        _, first = np.unique(label_seeds, return_index=True)
+        uniq = label_seeds[np.sort(first)]
+        for vt in range(Vt):
+            mine = uniq[(uniq >= vto[vt]) & (uniq < vto[vt + 1])]
+            assert np.array_equal(maps[vt][:len(mine)], mine)
+            assert base[1, vt, l] == len(mine)
+        for t, (sv, dv) in enumerate(edge_types):
+            emap = res["edge_renumber_map"][ermo[l * T + t]:ermo[l * T + t + 1]]
+            a0 = lho[(l * T + t) * L]
+            for h in range(L):
+                a, b = lho[(l * T + t) * L + h], lho[(l * T + t) * L + h + 1]
+                if fanout[h * T + t] == 0:
+                    assert a == b
+                mj, mn = res["majors"][a:b], res["minors"][a:b]
+                assert np.array_equal(res["edge_id"][a:b], np.arange(a - a0, b - a0))
+                assert (res["edge_type"][a:b] == t).all()
+                # majors are vertices discovered at step h, minors no later than step h + 1
+                assert ((mj >= base[h, sv, l]) & (mj < (base[h + 1, sv, l] if h + 1 <= L else len(maps[sv])))).all()
+                hi = base[h + 2, dv, l] if h + 2 <= L else len(maps[dv])
+                assert (mn < hi).all()
+                src_g, dst_g = maps[sv][mj], maps[dv][mn]
+                pos = emap[res["edge_id"][a:b]]  # CSR positions (no edge_ids given)
+                assert np.array_equal(cols[t][pos].astype(np.int64), dst_g)
+                assert ((row_ptrs[t][src_g] <= pos) & (pos < row_ptrs[t][src_g + 1])).all()
+                if fanout[h * T + t] > 0 and len(mj):
+                    assert np.bincount(mj).max() <= fanout[h * T + t]
+
+
+def test_hetero_structure_random_typed_graph(oracle):
+    from graphs import random_typed_graph
+
+    edge_types = [(0, 1), (1, 0), (1, 1)]
+    vto, row_ptrs, cols = random_typed_graph([400, 900], edge_types, [5000, 7000, 9000], seed=8)
+    rng = np.random.default_rng(2)
+    seeds = np.concatenate([rng.integers(0, 1300, 40), rng.integers(400, 1300, 25), rng.integers(0, 400, 1)]).astype(np.int64)
+    lo = np.array([0, 40, 40, 65, 66], dtype=np.int64)
+    for fanout in ([3, 2, 4, 2, 2, 2], [-1, 3, 0, 2, -1, 1], [5, 5, 5]):
+        res = oracle.hetero_multihop_sample(row_ptrs, cols, vto, seeds, lo, fanout, 99)
+        check_hetero_structure(res, vto, row_ptrs, cols, edge_types, seeds, lo, fanout)
