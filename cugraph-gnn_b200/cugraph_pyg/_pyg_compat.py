@@ -18,7 +18,7 @@ except Exception:  # ModuleNotFoundError or a broken install
     HAS_PYG = False
 
 if HAS_PYG:  # pragma: no cover
-    from torch_geometric.data import Data, FeatureStore as FeatureStoreBase, GraphStore as GraphStoreBase
+    from torch_geometric.data import Data, HeteroData, FeatureStore as FeatureStoreBase, GraphStore as GraphStoreBase
     from torch_geometric.data.feature_store import TensorAttr
     from torch_geometric.data.graph_store import EdgeAttr, EdgeLayout
     from torch_geometric.sampler import NodeSamplerInput, SamplerOutput, HeteroSamplerOutput
@@ -183,6 +183,41 @@ else:
             for k, v in self._store.items():
                 parts.append(f"{k}={list(v.shape)}" if torch.is_tensor(v) else f"{k}={v}")
             return "Data(" + ", ".join(parts) + ")"
+
+    class HeteroData:
+        """Per-type attribute bags with torch_geometric.data.HeteroData's basic protocol: ``data[node_type]`` /
+        ``data[(src, rel, dst)]`` return (creating on first use) the storage of that type; ``set_value_dict`` spreads a
+        {type: value} dict over the storages."""
+
+        def __init__(self):
+            object.__setattr__(self, "_stores", {})
+
+        def __getitem__(self, key):
+            if isinstance(key, list):
+                key = tuple(key)
+            stores = object.__getattribute__(self, "_stores")
+            if key not in stores:
+                stores[key] = Data()
+            return stores[key]
+
+        def __contains__(self, key):
+            return key in self._stores
+
+        @property
+        def node_types(self):
+            return [k for k in self._stores if isinstance(k, str)]
+
+        @property
+        def edge_types(self):
+            return [k for k in self._stores if isinstance(k, tuple)]
+
+        def set_value_dict(self, key, value_dict):
+            for k, v in (value_dict or {}).items():
+                self[k][key] = v
+            return self
+
+        def __repr__(self):
+            return "HeteroData(" + ", ".join(f"{k}={v!r}" for k, v in self._stores.items()) + ")"
 
     @dataclass
     class NodeSamplerInput:

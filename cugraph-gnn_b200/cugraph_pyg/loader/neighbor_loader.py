@@ -1,5 +1,7 @@
 """NeighborLoader (role of the reference's cugraph_pyg/loader/neighbor_loader.py:15-236)."""
 import warnings
+
+import numpy as np
 from typing import Callable, Dict, List, Optional, Union
 
 import cugraph_pyg
@@ -36,8 +38,24 @@ class NeighborLoader(NodeLoader):
             compression = "CSR" if graph_store.is_homogeneous else "COO"
         elif compression not in ("CSR", "COO"):
             raise ValueError("Invalid value for compression (expected 'CSR' or 'COO')")
-        if isinstance(num_neighbors, dict) or not graph_store.is_homogeneous:
-            raise NotImplementedError("heterogeneous sampling is not built yet (SURVEY.md §8e C5)")
+        if not graph_store.is_homogeneous and compression != "COO":
+            raise ValueError("Only COO format is supported for heterogeneous graphs!")
+        heterogeneous = not graph_store.is_homogeneous
+        num_edge_types = len(graph_store.get_all_edge_attrs())
+        if isinstance(num_neighbors, dict):
+            # fan-out vector laid out [hop * T + edge type], edge types in sorted order (reference :192-201)
+            sorted_keys, _, _ = graph_store._numeric_edge_types
+            hops = len(next(iter(num_neighbors.values())))
+            na = np.zeros(hops * len(sorted_keys), dtype="int32")
+            for i, key in enumerate(sorted_keys):
+                if key in num_neighbors:
+                    for hop in range(hops):
+                        na[hop * len(sorted_keys) + i] = num_neighbors[key][hop]
+            num_neighbors = na
+        elif heterogeneous or num_edge_types > 1:
+            # a plain list on a typed graph means "the same fan-out for every edge type" (PyG's convention)
+            num_neighbors = np.repeat(np.asarray(num_neighbors, dtype="int32"), num_edge_types)
+        heterogeneous = heterogeneous or num_edge_types > 1
         if weight_attr is not None:
             graph_store._set_weight_attr((feature_store, weight_attr))
         sampler = BaseSampler(
@@ -45,7 +63,8 @@ class NeighborLoader(NodeLoader):
                 graph_store._graph, retain_original_seeds=True, fanout=num_neighbors, prior_sources_behavior="exclude",
                 deduplicate_sources=True, compression=compression, compress_per_hop=False, with_replacement=replace,
                 disjoint=disjoint, local_seeds_per_call=local_seeds_per_call, biased=(weight_attr is not None),
-                heterogeneous=False, temporal=False, num_edge_types=1),
+                heterogeneous=heterogeneous, temporal=False, vertex_type_offsets=graph_store._vertex_offset_array,
+                num_edge_types=num_edge_types),
             (feature_store, graph_store), batch_size=batch_size)
         super().__init__((feature_store, graph_store), sampler, input_nodes=input_nodes, input_time=input_time,
                          transform=transform, transform_sampler_output=transform_sampler_output,

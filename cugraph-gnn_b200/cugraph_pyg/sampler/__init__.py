@@ -1,5 +1,5 @@
-from .sampler import BaseSampler, SampleIterator, SampleReader, HomogeneousSampleReader
+from .sampler import BaseSampler, SampleIterator, SampleReader, HomogeneousSampleReader, HeterogeneousSampleReader
 from .distributed_sampler import BaseDistributedSampler, DistributedNeighborSampler
 
-__all__ = ["BaseSampler", "SampleIterator", "SampleReader", "HomogeneousSampleReader", "BaseDistributedSampler",
+__all__ = ["BaseSampler", "SampleIterator", "SampleReader", "HomogeneousSampleReader", "HeterogeneousSampleReader", "BaseDistributedSampler",
            "DistributedNeighborSampler"]

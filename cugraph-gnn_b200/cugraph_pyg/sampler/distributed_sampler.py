@@ -125,12 +125,20 @@ class DistributedNeighborSampler(BaseDistributedSampler):
                  compression: str = "COO", compress_per_hop: bool = False, with_replacement: bool = False,
                  disjoint: bool = False, biased: bool = False, heterogeneous: bool = False, temporal: bool = False,
                  temporal_comparison: Optional[str] = None, vertex_type_offsets=None, num_edge_types: int = 1):
-        if heterogeneous or num_edge_types > 1:
-            raise NotImplementedError("heterogeneous sampling is not built yet (SURVEY.md §8e C5)")
         if temporal:
             raise NotImplementedError("temporal sampling is outside the B200 hot path")
+        if num_edge_types > 1 and not heterogeneous:
+            raise ValueError("Heterogeneous sampling must be selected if there is > 1 edge type.")
         self.__fanout = [int(f) for f in np.asarray(fanout).reshape(-1)]
-        self.__func = pylibcugraph.homogeneous_biased_neighbor_sample if biased else pylibcugraph.homogeneous_uniform_neighbor_sample
+        self.__heterogeneous = bool(heterogeneous)
+        self.__num_edge_types = int(num_edge_types)
+        table = {
+            (False, False): pylibcugraph.homogeneous_uniform_neighbor_sample,
+            (False, True): pylibcugraph.homogeneous_biased_neighbor_sample,
+            (True, False): pylibcugraph.heterogeneous_uniform_neighbor_sample,
+            (True, True): pylibcugraph.heterogeneous_biased_neighbor_sample,
+        }
+        self.__func = table[(self.__heterogeneous, bool(biased))]
         self.__func_kwargs = {
             "h_fan_out": np.asarray(self.__fanout, dtype="int32"),
             "prior_sources_behavior": prior_sources_behavior,
@@ -141,15 +149,28 @@ class DistributedNeighborSampler(BaseDistributedSampler):
             "with_replacement": with_replacement,
             "disjoint_sampling": disjoint,
         }
+        if heterogeneous:
+            if vertex_type_offsets is None:
+                raise ValueError("Heterogeneous sampling requires vertex type offsets.")
+            if len(self.__fanout) % self.__num_edge_types != 0:
+                raise ValueError(f"Illegal fanout for {num_edge_types} edge types.")
+            self.__func_kwargs["num_edge_types"] = self.__num_edge_types
+            self.__func_kwargs["vertex_type_offsets"] = torch.as_tensor(vertex_type_offsets).cpu()
         super().__init__(graph, self.__calc_local_seeds_per_call(local_seeds_per_call), retain_original_seeds)
 
     def __calc_local_seeds_per_call(self, local_seeds_per_call: Optional[int]) -> int:
         if local_seeds_per_call is not None:
             return int(local_seeds_per_call)
-        if any(f <= 0 for f in self.__fanout):
+        fanout = self.__fanout
+        if self.__heterogeneous:
+            # loaders lay the vector out [hop * T + etype] (neighbor_loader.py:192-201); the bound is the per-hop sum
+            T = self.__num_edge_types
+            fanout = [sum(fanout[h * T + t] for t in range(T)) if all(fanout[h * T + t] >= 0 for t in range(T)) else -1
+                      for h in range(len(fanout) // T)]
+        if any(f <= 0 for f in fanout):
             return DistributedNeighborSampler.UNKNOWN_VERTICES_DEFAULT
         total_memory = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
-        prod = reduce(lambda x, y: x * y, self.__fanout)
+        prod = reduce(lambda x, y: x * y, fanout)
         by_memory = int(DistributedNeighborSampler.BASE_VERTICES_PER_BYTE * total_memory / prod)
         return max(1, min(by_memory, DistributedNeighborSampler.MAX_EDGES_PER_HOP // prod))
 

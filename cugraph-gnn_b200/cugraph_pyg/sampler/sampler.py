@@ -10,8 +10,10 @@ from typing import Dict, Iterator, Tuple, Union
 
 import torch
 
-from cugraph_pyg._pyg_compat import SamplerOutput, NodeSamplerInput, ptr2index
-from .sampler_utils import filter_cugraph_pyg_store
+from typing import List
+
+from cugraph_pyg._pyg_compat import SamplerOutput, HeteroSamplerOutput, NodeSamplerInput, ptr2index
+from .sampler_utils import filter_cugraph_pyg_store, filter_cugraph_pyg_hetero_store
 
 
 class SampleIterator:
@@ -23,6 +25,8 @@ class SampleIterator:
 
     def __next__(self):
         s = next(self.__output_iter)
+        if isinstance(s, HeteroSamplerOutput):
+            return self.__hetero(s)
         if not isinstance(s, SamplerOutput):
             raise ValueError("Invalid output type")
         n_edges = int(s.edge.numel())
@@ -44,6 +48,24 @@ class SampleIterator:
         if s.csr is not None:
             # extension: the sampler's CSR block, for aggregation kernels that consume it directly
             data.csr_indptr, data.csr_indices = s.csr
+        return data
+
+    def __hetero(self, s: HeteroSamplerOutput):
+        """sampler.py:118-163 of the reference: HeteroData with per-type n_id / e_id / counts."""
+        data = filter_cugraph_pyg_hetero_store(self.__feature_store, self.__graph_store, s.node, s.row, s.col, s.edge, None)
+        for key, node in s.node.items():
+            if "n_id" not in data[key]:
+                data[key].n_id = node
+        for key, edge in (s.edge or {}).items():
+            if edge is not None and "e_id" not in data[key]:
+                data[key].e_id = edge.to(torch.long)
+        data.set_value_dict("batch", s.batch)
+        data.set_value_dict("num_sampled_nodes", s.num_sampled_nodes)
+        data.set_value_dict("num_sampled_edges", s.num_sampled_edges)
+        input_type, input_id = s.metadata[0]
+        data[input_type].input_id = input_id
+        data[input_type].batch_size = int(input_id.size(0))
+        data[input_type].seed_time = s.metadata[1]
         return data
 
     def __iter__(self):
@@ -134,6 +156,65 @@ class HomogeneousSampleReader(SampleReader):
         return out
 
 
+class HeterogeneousSampleReader(SampleReader):
+    """Heterogeneous call groups (role of the reference's sampler.py:231-502).  Same vectorised decode as the
+    homogeneous reader: the (label, edge type, hop) offsets, the map offsets and the per-step bases are copied to the
+    host once per call group; a mini-batch is then slices, one subtraction per vertex type and no host sync (the
+    reference reduces `majors[:lho].max()` on the device and calls `.cpu()` per type and hop, :349-362, 404-410)."""
+
+    def __init__(self, base_reader, src_types: torch.Tensor, dst_types: torch.Tensor, vertex_offsets: torch.Tensor,
+                 edge_types: List[Tuple[str, str, str]], vertex_types: List[str]):
+        self.__src_types = [int(x) for x in src_types.tolist()]
+        self.__dst_types = [int(x) for x in dst_types.tolist()]
+        self.__edge_types = list(edge_types)
+        self.__vertex_types = list(vertex_types)
+        self.__vertex_offsets = [int(x) for x in vertex_offsets.tolist()]
+        super().__init__(base_reader)
+
+    def _prepare(self, raw: Dict[str, torch.Tensor]):
+        if "major_offsets" in raw:
+            raise ValueError("CSR format not currently supported for heterogeneous graphs")
+        if raw.get("input_type") is None:
+            raise ValueError("No input type found!")
+        T, Vt = len(self.__edge_types), len(self.__vertex_types)
+        lto, rmo = raw["label_type_hop_offsets"], raw["renumber_map_offsets"]
+        B = (rmo.numel() - 1) // Vt
+        L = (lto.numel() - 1) // max(B * T, 1)
+        host = torch.cat([lto, rmo, raw["label_type_step_base"].reshape(-1).to(torch.int64)]).cpu()  # the only sync
+        raw["_T"], raw["_Vt"], raw["_L"], raw["_B"] = T, Vt, L, B
+        raw["_lto"] = host[:lto.numel()].tolist()
+        raw["_rmo"] = host[lto.numel():lto.numel() + rmo.numel()].tolist()
+        raw["_base"] = host[lto.numel() + rmo.numel():].view(L + 1, Vt, B).tolist()
+        raw["_input_offsets"] = raw["input_offsets"].tolist()
+
+    def _decode(self, raw: Dict[str, torch.Tensor], index: int):
+        T, Vt, L = raw["_T"], raw["_Vt"], raw["_L"]
+        lto, rmo, base = raw["_lto"], raw["_rmo"], raw["_base"]
+        node, num_sampled_nodes = {}, {}
+        for vt, name in enumerate(self.__vertex_types):
+            n0, n1 = rmo[index * Vt + vt], rmo[index * Vt + vt + 1]
+            node[name] = raw["map"][n0:n1] - self.__vertex_offsets[vt]
+            b = [base[s][vt][index] for s in range(L + 1)] + [n1 - n0]
+            num_sampled_nodes[name] = torch.tensor([b[s + 1] - b[s] for s in range(L + 1)])
+        row, col, edge, num_sampled_edges = {}, {}, {}, {}
+        for t, et in enumerate(self.__edge_types):
+            g = (index * T + t) * L
+            e0, e1 = lto[g], lto[g + L]
+            row[et] = raw["minors"][e0:e1]
+            col[et] = raw["majors"][e0:e1]
+            # edge_id is the position inside the (label, edge type) group and the group's slice of
+            # edge_renumber_map starts at its first edge, so emap[edge_id] (sampler.py:334-341) is this slice
+            edge[et] = raw["edge_renumber_map"][e0:e1]
+            num_sampled_edges[et] = torch.tensor([lto[g + h + 1] - lto[g + h] for h in range(L)])
+        input_type = raw["input_type"]
+        if not (isinstance(input_type, str) and input_type in self.__vertex_types):
+            raise ValueError("Input type did not match any vertex type!")
+        i0, i1 = raw["_input_offsets"][index], raw["_input_offsets"][index + 1]
+        input_index = raw["input_index"][i0:i1]
+        return HeteroSamplerOutput(node=node, row=row, col=col, edge=edge, batch=None, num_sampled_nodes=num_sampled_nodes,
+                                   num_sampled_edges=num_sampled_edges, metadata=((input_type, input_index), None))
+
+
 class BaseSampler:
     def __init__(self, sampler, data, batch_size: int = 16):
         self.__sampler = sampler
@@ -147,7 +228,10 @@ class BaseSampler:
         attrs = self.__graph_store.get_all_edge_attrs()
         if len(attrs) == 1 and attrs[0].edge_type[0] == attrs[0].edge_type[2]:
             return HomogeneousSampleReader(reader)
-        raise NotImplementedError("heterogeneous readers are not built yet (SURVEY.md §8e C5)")
+        edge_types, src_types, dst_types = self.__graph_store._numeric_edge_types
+        return HeterogeneousSampleReader(reader, src_types=src_types, dst_types=dst_types,
+                                         vertex_offsets=self.__graph_store._vertex_offset_array, edge_types=edge_types,
+                                         vertex_types=sorted(self.__graph_store._vertex_offsets.keys()))
 
     def sample_from_edges(self, *args, **kwargs):
         raise NotImplementedError("link-prediction sampling is outside the B200 hot path (SURVEY.md §8f row 2)")

@@ -11,7 +11,9 @@ result dictionary so that code written against pylibcugraph runs unchanged, and 
 Differences that callers can observe:
   * arrays are torch CUDA tensors (the reference converts cupy -> torch right after the call anyway);
   * the random stream is this project's (S1/S2 geometry per hop), not libcugraph's -- unverifiable either way;
-  * with_replacement=True, disjoint_sampling=True, temporal and heterogeneous sampling raise NotImplementedError.
+  * heterogeneous sampling keeps one CSR per edge type (built lazily from edge_type_array) and follows the definition in
+    include/wholememory/b200_ops.h: edge_id indexes edge_renumber_map per (label, edge type);
+  * with_replacement=True, disjoint_sampling=True and temporal sampling raise NotImplementedError.
 """
 from typing import Optional
 
@@ -94,6 +96,30 @@ class SGGraph:
         if self.weight is not None and self.weight.dtype not in (torch.float32, torch.float64):
             self.weight = self.weight.float()
         self._sampler = None
+        self._typed = {}
+
+    def _typed_csrs(self, num_edge_types: int):
+        """Per edge type: (row_ptr [V+1], col, weight|None, edge_id|None) over the global vertex id space, in the order
+        of the combined CSR (stable), built once per num_edge_types."""
+        if num_edge_types not in self._typed:
+            if self.edge_type is None:
+                if num_edge_types != 1:
+                    raise ValueError("the graph was built without edge_type_array")
+                self._typed[num_edge_types] = [(self.row_ptr, self.col, self.weight, self.edge_id)]
+            else:
+                deg = self.row_ptr[1:] - self.row_ptr[:-1]
+                rows = torch.repeat_interleave(torch.arange(self.num_vertices, device=self.col.device), deg)
+                out = []
+                for t in range(num_edge_types):
+                    sel = torch.nonzero(self.edge_type == t).reshape(-1)
+                    rp = torch.zeros(self.num_vertices + 1, dtype=torch.int64, device=self.col.device)
+                    if sel.numel():
+                        rp[1:] = torch.bincount(rows[sel], minlength=self.num_vertices).cumsum(0)
+                    out.append((rp, self.col[sel].contiguous(),
+                                None if self.weight is None else self.weight[sel].contiguous(),
+                                None if self.edge_id is None else self.edge_id[sel].contiguous()))
+                self._typed[num_edge_types] = out
+        return self._typed[num_edge_types]
 
     def _get_sampler(self):
         if self._sampler is None:
@@ -201,6 +227,73 @@ def homogeneous_biased_neighbor_sample(resource_handle, input_graph, start_verte
     return _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, True, **kwargs)
 
 
+def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, num_edge_types,
+                            vertex_type_offsets, biased, *, with_replacement=False, do_expensive_check=False,
+                            prior_sources_behavior=None, deduplicate_sources=False, return_hops=False, renumber=False,
+                            retain_seeds=False, compression="COO", compress_per_hop=False, random_state=None,
+                            disjoint_sampling=False, return_dict=True, **unused):
+    if with_replacement:
+        raise NotImplementedError("sampling with replacement is not on the B200 hot path")
+    if disjoint_sampling:
+        raise NotImplementedError("disjoint sampling is not on the B200 hot path")
+    if compress_per_hop or compression != "COO":
+        raise NotImplementedError("heterogeneous sampling returns COO (as the reference's reader requires)")
+    if not renumber:
+        raise NotImplementedError("the fused sampler always renumbers (cugraph-pyg calls with renumber=True)")
+    if prior_sources_behavior not in (None, "exclude") or (prior_sources_behavior is None and deduplicate_sources is False):
+        raise NotImplementedError("only deduplicate_sources=True with prior_sources_behavior='exclude' is supported")
+    if biased and input_graph.weight is None:
+        raise ValueError("biased sampling needs a graph with edge weights")
+    seeds = _as_cuda(start_vertex_list)
+    if seeds.dtype not in (torch.int32, torch.int64):
+        seeds = seeds.long()
+    if starting_vertex_label_offsets is None:
+        offsets = torch.tensor([0, seeds.numel()], dtype=torch.int64, device=seeds.device)
+    else:
+        offsets = _as_cuda(starting_vertex_label_offsets, torch.int64)
+    fanout = [int(f) for f in np.asarray(h_fan_out).reshape(-1)]
+    T = int(num_edge_types)
+    if T < 1 or len(fanout) % T != 0:
+        raise ValueError(f"Illegal fanout for {T} edge types.")
+    vto = [int(v) for v in torch.as_tensor(vertex_type_offsets).reshape(-1).tolist()]
+    if random_state is None:
+        random_state = int(np.random.randint(0, 2**62))
+    typed = input_graph._typed_csrs(T)
+    res = input_graph._get_sampler().sample_hetero(
+        [g[0] for g in typed], [g[1] for g in typed], vto, seeds, offsets, fanout, int(random_state),
+        csr_weights=[g[2] for g in typed] if biased else None,
+        csr_edge_ids=[g[3] for g in typed] if input_graph.edge_id is not None else None, int64_ids=True,
+    )
+    return {
+        "majors": res["majors"],
+        "minors": res["minors"],
+        "major_offsets": None,
+        "edge_id": res["edge_id"],
+        "edge_type": res["edge_type"],
+        "weight": None,
+        "hop_id": None,
+        "renumber_map": res["renumber_map"],
+        "renumber_map_offsets": res["renumber_map_offsets"],
+        "label_type_hop_offsets": res["label_type_hop_offsets"],
+        "edge_renumber_map": res["edge_renumber_map"],
+        "edge_renumber_map_offsets": res["edge_renumber_map_offsets"],
+        # extension: [L+1, Vt, B] first local id of the type-vt vertices each label discovered at step s
+        "label_type_step_base": res["label_type_step_base"],
+    }
+
+
+def heterogeneous_uniform_neighbor_sample(resource_handle, input_graph, start_vertex_list, starting_vertex_label_offsets,
+                                          vertex_type_offsets=None, h_fan_out=None, num_edge_types=1, **kwargs):
+    return _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, num_edge_types,
+                                   vertex_type_offsets, False, **kwargs)
+
+
+def heterogeneous_biased_neighbor_sample(resource_handle, input_graph, start_vertex_list, starting_vertex_label_offsets,
+                                         vertex_type_offsets=None, h_fan_out=None, num_edge_types=1, **kwargs):
+    return _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, num_edge_types,
+                                   vertex_type_offsets, True, **kwargs)
+
+
 def _not_on_path(name):
     def fn(*args, **kwargs):
         raise NotImplementedError(f"pylibcugraph.{name} is outside the B200 hot path (SURVEY.md §8: homogeneous node sampling)")
@@ -209,8 +302,6 @@ def _not_on_path(name):
     return fn
 
 
-heterogeneous_uniform_neighbor_sample = _not_on_path("heterogeneous_uniform_neighbor_sample")
-heterogeneous_biased_neighbor_sample = _not_on_path("heterogeneous_biased_neighbor_sample")
 homogeneous_uniform_temporal_neighbor_sample = _not_on_path("homogeneous_uniform_temporal_neighbor_sample")
 homogeneous_biased_temporal_neighbor_sample = _not_on_path("homogeneous_biased_temporal_neighbor_sample")
 heterogeneous_uniform_temporal_neighbor_sample = _not_on_path("heterogeneous_uniform_temporal_neighbor_sample")
