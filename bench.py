@@ -219,6 +219,9 @@ def run_ours(args):
         return samplers[k & 1].sample_async(wm_rp, wm_col, sd, label_offsets, FANOUT, SAMPLER_SEED + 7 * k)
 
     side = torch.cuda.Stream(device=dev) if args.gather_stream else None
+    n_metric = (labels * len(FANOUT) + 1) + (labels + 1) + labels * FEAT_DIM
+    host_ring = [torch.empty(n_metric, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    ring_pos = [0]
 
     def e2e_end(pending):
         res = pending.result()
@@ -228,11 +231,14 @@ def run_ours(args):
             x = emb.gather(res["renumber_map"])
             first = x.index_select(0, res["renumber_map_offsets"][:-1])  # [labels, F]
             metric = torch.cat([res["label_hop_offsets"].double(), res["renumber_map_offsets"].double(), first.double().reshape(-1)])
-            host = torch.empty(metric.shape, dtype=metric.dtype, pin_memory=True)
+            host = host_ring[ring_pos[0] % len(host_ring)]  # pinned, allocated once (cudaHostAlloc inside the loop stalls)
+            ring_pos[0] += 1
             host.copy_(metric, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
         return int(res["minors"].numel()), (host, res, x), ev
+
+    dbg = os.environ.get("BENCH_E2E_DEBUG")
 
     def e2e_loop(first_k, n):
         """n call groups, one sampler call in flight ahead of the gather; returns (edges, d2h bytes per step)."""
@@ -240,8 +246,12 @@ def run_ours(args):
         pend = e2e_begin(first_k)
         done = []
         for i in range(n):
+            t0 = time.perf_counter()
             nxt = e2e_begin(first_k + i + 1) if i + 1 < n else None
+            t1 = time.perf_counter()
             e, host, ev = e2e_end(pend)
+            if dbg:
+                log("[rank %d] step %d begin %.3f ms  end %.3f ms" % (rank, i, 1e3 * (t1 - t0), 1e3 * (time.perf_counter() - t1)))
             edges += e
             done.append((host, ev))
             if len(done) > 1:  # read the previous step's result on the host while this one runs
@@ -295,6 +305,8 @@ def run_ours(args):
     e_end.record()
     torch.cuda.synchronize()
     e2e_ms = e_begin.elapsed_time(e_end)
+    if dbg:
+        log("[rank %d] e2e %.3f ms for %d steps; value loop %.3f ms" % (rank, e2e_ms, args.steps, ms_total))
     clock_info = clocks.stop() if rank == 0 else None
 
     stats = torch.tensor([ms_total, e2e_ms, sample_ms, gather_ms], dtype=torch.float64, device=dev)
