@@ -121,6 +121,36 @@ class SGGraph:
                 self._typed[num_edge_types] = out
         return self._typed[num_edge_types]
 
+    @staticmethod
+    def _drop_zero_weight(row_ptr, col, weight, edge_id):
+        """pylibcugraph never samples an edge whose bias is zero, even when the row has fewer candidates than the fan-out
+        (pinned by the reference's test_neighbor_loader.py:97-133); the WholeGraph A-Res sampler takes every neighbour of
+        a row with deg <= fan-out.  Sampling on the CSR without its zero-weight edges gives pylibcugraph's behaviour
+        exactly; edge ids keep pointing at the caller's edges."""
+        keep = weight > 0
+        if bool(keep.all()):
+            return row_ptr, col, weight, edge_id
+        n = row_ptr.numel() - 1
+        rows = torch.repeat_interleave(torch.arange(n, device=col.device), row_ptr[1:] - row_ptr[:-1])
+        sel = torch.nonzero(keep).reshape(-1)
+        rp = torch.zeros(n + 1, dtype=torch.int64, device=col.device)
+        if sel.numel():
+            rp[1:] = torch.bincount(rows[sel], minlength=n).cumsum(0)
+        if edge_id is None:
+            edge_id = torch.arange(col.numel(), dtype=torch.int64, device=col.device)
+        return rp, col[sel].contiguous(), weight[sel].contiguous(), edge_id[sel].contiguous()
+
+    def _drop_zero_weight_cached(self):
+        if "biased_all" not in self._typed:
+            self._typed["biased_all"] = self._drop_zero_weight(self.row_ptr, self.col, self.weight, self.edge_id)
+        return self._typed["biased_all"]
+
+    def _biased_csrs(self, num_edge_types: int):
+        key = ("biased", num_edge_types)
+        if key not in self._typed:
+            self._typed[key] = [self._drop_zero_weight(*g) for g in self._typed_csrs(num_edge_types)]
+        return self._typed[key]
+
     def _get_sampler(self):
         if self._sampler is None:
             from pylibwholegraph.torch.multihop import MultiHopSampler
@@ -195,11 +225,12 @@ def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offse
     fanout = [int(f) for f in np.asarray(h_fan_out).reshape(-1)]
     if random_state is None:
         random_state = int(np.random.randint(0, 2**62))
-    res = input_graph._get_sampler().sample(
-        input_graph.row_ptr, input_graph.col, seeds, offsets, fanout, int(random_state),
-        csr_weight=input_graph.weight if biased else None, csr_edge_id=input_graph.edge_id,
-        compression=compression, int64_ids=True,
-    )
+    row_ptr, col, weight, edge_id = input_graph.row_ptr, input_graph.col, None, input_graph.edge_id
+    if biased:
+        # one CSR (edge types, if any, are ignored by the homogeneous entry point), zero-bias edges removed
+        row_ptr, col, weight, edge_id = input_graph._drop_zero_weight_cached()
+    res = input_graph._get_sampler().sample(row_ptr, col, seeds, offsets, fanout, int(random_state), csr_weight=weight,
+                                            csr_edge_id=edge_id, compression=compression, int64_ids=True)
     out = {
         "majors": res.get("majors"),
         "minors": res["minors"],
@@ -258,11 +289,11 @@ def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_labe
     vto = [int(v) for v in torch.as_tensor(vertex_type_offsets).reshape(-1).tolist()]
     if random_state is None:
         random_state = int(np.random.randint(0, 2**62))
-    typed = input_graph._typed_csrs(T)
+    typed = input_graph._biased_csrs(T) if biased else input_graph._typed_csrs(T)
     res = input_graph._get_sampler().sample_hetero(
         [g[0] for g in typed], [g[1] for g in typed], vto, seeds, offsets, fanout, int(random_state),
         csr_weights=[g[2] for g in typed] if biased else None,
-        csr_edge_ids=[g[3] for g in typed] if input_graph.edge_id is not None else None, int64_ids=True,
+        csr_edge_ids=[g[3] for g in typed] if any(g[3] is not None for g in typed) else None, int64_ids=True,
     )
     return {
         "majors": res["majors"],

@@ -246,3 +246,23 @@ def test_neighbor_loader_hetero_random_graph_matches_oracle(pyg, oracle):
             eid = batch[k].e_id.cpu().numpy()
             assert np.array_equal(s[eid], batch[k[0]].n_id.cpu().numpy()[ei[0].numpy()])
             assert np.array_equal(d[eid], batch[k[2]].n_id.cpu().numpy()[ei[1].numpy()])
+
+
+def test_neighbor_loader_biased_reference_pin(pyg):
+    """reference: test_neighbor_loader_biased (test_neighbor_loader.py:97-133) verbatim: a zero-bias edge is never
+    sampled, even though its row has fewer candidates than the fan-out."""
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    eix = torch.tensor([[3, 4, 5], [0, 1, 2]])
+    graph_store = GraphStore()
+    graph_store.put_edge_index(eix, ("person", "knows", "person"), "coo", False, (6, 6))
+    feature_store = FeatureStore()
+    feature_store["person", "feat", None] = torch.randint(128, (6, 12))
+    feature_store[("person", "knows", "person"), "bias", None] = torch.tensor([0, 12, 14], dtype=torch.float32)
+    loader = NeighborLoader((feature_store, graph_store), [1], input_nodes=torch.tensor([0, 1, 2], dtype=torch.int64),
+                            batch_size=3, weight_attr="bias")
+    out = list(iter(loader))
+    assert len(out) == 1
+    out = out[0]
+    assert out.edge_index.shape[1] == 2
+    assert (out.edge_index.cpu() == torch.tensor([[3, 4], [1, 2]])).all()
+    assert out.e_id.cpu().tolist() == [1, 2]
