@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(const MhSlot* __
       flags |= (f ? 1u : 0u) << k;
       if (lane == 0) s_cnt[k * kWarps + wid] = __popc(b);
     }
-    if (!SEEDS) {
+    if (!SEEDS || rank_of) {
       // references do not depend on the scan: written while the tile prefix is being looked up
       // tag(t, e'): bit 0 set, e' in bits 1..32;  fin(t', rank): bit 0 clear
 #pragma unroll
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kScanBlock) mh_compact_kernel(const MhSlot* __
         unsigned int rank   = (unsigned int)prefix + s_cnt[k * kWarps + wid] + within[k];
         next_frontier[rank] = (long long)vertices[e];
         next_flabel[rank]   = SEEDS ? flabel[e] : flabel[erow[e]];
-        if (!SEEDS) rank_of[e] = rank;
+        if (!SEEDS || rank_of) rank_of[e] = rank;
       }
     }
     if (n >= (long long)tile * kCompactTile && n < (long long)(tile + 1) * kCompactTile && threadIdx.x == 0)
@@ -481,6 +481,21 @@ __global__ void __launch_bounds__(1024) mh_scan3_kernel(MhScan3 a)
   if (threadIdx.x == 0) {
     out[n]               = s_carry;
     a.totals[blockIdx.x] = s_carry;
+  }
+}
+
+// local id of every INPUT seed (duplicates included): the link-prediction loaders index the label's nodes with it
+// (edge_label_index; the reference sorts + unique_consecutive's every batch in python for this,
+// sampler/distributed_sampler.py:487-533).  typed_local != null: heterogeneous ids (per label and vertex type).
+__global__ void __launch_bounds__(256) mh_seed_local_kernel(const unsigned int* __restrict__ seed_ref,
+                                                            const unsigned int* __restrict__ seed_rank,
+                                                            const int* __restrict__ slabel, const int* __restrict__ fr_off0,
+                                                            const int* __restrict__ typed_local0, int S, int* __restrict__ out)
+{
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x) {
+    const unsigned int first = seed_ref[s] & 0x0FFFFFFFu;  // position of the first occurrence of this seed's vertex
+    const unsigned int rank  = seed_rank[first];           // its row in frontier 0
+    out[s] = typed_local0 ? typed_local0[rank] : (int)rank - fr_off0[slabel[s]];
   }
 }
 
@@ -756,7 +771,7 @@ struct wholegraph_multihop_sampler_ {
   Buf table;
   unsigned int table_slots = 0;  // allocated capacity
   int epoch                = 0;  // last epoch handed out (0: table must be initialised)
-  Buf slabel, scan_state, small_i32, small_i64, counts, seed_slot;
+  Buf slabel, scan_state, small_i32, small_i64, counts, seed_slot, seed_rank;
   Buf frontier[wgb::kMaxHops + 1], flabel[wgb::kMaxHops + 1], fr_off[wgb::kMaxHops + 1];
   Buf off[wgb::kMaxHops], dest[wgb::kMaxHops], erow[wgb::kMaxHops], gid[wgb::kMaxHops], slot[wgb::kMaxHops], rank_of[wgb::kMaxHops];
   Buf base;
@@ -779,6 +794,10 @@ struct wholegraph_multihop_sampler_ {
     wgb::MhHopBufs hb;
     long long *lho = nullptr, *rmo = nullptr, *rbase = nullptr;
     int *base = nullptr, *n_rows_dev = nullptr, *n_edges_dev = nullptr;
+    int S = 0;
+    const unsigned int *seed_ref = nullptr, *seed_rank = nullptr;  // per input seed: reference to its first occurrence
+    const int* slabel = nullptr;
+    bool finished = false;  // outputs of the last call exist; seed ids may be asked for until the next _begin
     bool hetero = false;  // typed outputs ([label][edge type][hop], ids per (label, vertex type))
     int T = 1, Vt = 1;
     int* tbase = nullptr;
@@ -948,7 +967,8 @@ template <typename ColT, bool CHUNKED>
 static void multihop_begin(MhCall& c)
 {
   auto* sp        = c.sp;
-  sp->pending.active = false;  // a call that was begun but never finished is abandoned: its scratch is reused below
+  sp->pending.active   = false;  // a call that was begun but never finished is abandoned: its scratch is reused below
+  sp->pending.finished = false;
   sp->marks_used = 0;
   const int sms   = num_sms();
   const int B     = c.B, L = c.L, S = c.S;
@@ -1056,17 +1076,18 @@ static void multihop_begin(MhCall& c)
     WGB_CUDA_TRY(cudaMemcpyAsync(nslots_dev, &nslots0, sizeof(unsigned int), cudaMemcpyHostToDevice, st));
     unsigned long long epoch = next_epoch();
     unsigned int* slot0  = static_cast<unsigned int*>(ensure(sp->seed_slot, sizeof(unsigned int) * (size_t)std::max(S, 1)));
+    unsigned int* rank0  = static_cast<unsigned int*>(ensure(sp->seed_rank, sizeof(unsigned int) * (size_t)std::max(S, 1)));
     long long* frontier0 = static_cast<long long*>(ensure(sp->frontier[0], sizeof(long long) * (size_t)std::max(S, 1)));
     int* flabel0         = static_cast<int*>(ensure(sp->flabel[0], sizeof(int) * (size_t)std::max(S, 1)));
     auto ss              = scan_slice(S, kCompactTile);
     if (c.seed_dtype == WHOLEMEMORY_DT_INT) {
       mh_seed_insert_kernel<int><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const int*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
       WGB_CHECK_LAUNCH();
-      mh_compact_kernel<int, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const int*>(c.seeds), nullptr, S, nullptr, slabel, slot0, nullptr, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
+      mh_compact_kernel<int, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const int*>(c.seeds), nullptr, S, nullptr, slabel, slot0, rank0, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
     } else {
       mh_seed_insert_kernel<long long><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const long long*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
       WGB_CHECK_LAUNCH();
-      mh_compact_kernel<long long, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, nullptr, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
+      mh_compact_kernel<long long, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, rank0, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
     }
     WGB_CHECK_LAUNCH();
     mh_mark(sp, "seeds", st);
@@ -1266,6 +1287,8 @@ static void multihop_begin(MhCall& c)
   pd.B = B; pd.L = L; pd.flags = c.flags; pd.has_eid = c.csr[0].has_eid; pd.chunked = CHUNKED;
   pd.eid = c.csr[0].eid; pd.eid_off = c.csr[0].eid_off;
   pd.hetero = c.hetero; pd.T = T; pd.Vt = Vt; pd.tbase = tbase;
+  pd.S = S; pd.seed_ref = static_cast<const unsigned int*>(sp->seed_slot.p); pd.seed_rank = static_cast<const unsigned int*>(sp->seed_rank.p);
+  pd.slabel = slabel;
   for (int t = 0; t <= L; t++) pd.ub_rows[t] = ub_rows[t];
   for (int h = 0; h < L; h++) pd.ub_edges[h] = ub_edges[h];
   pd.fr = fr; pd.meta = meta; pd.hb = hb;
@@ -1287,6 +1310,7 @@ static void multihop_finish(wholegraph_multihop_sampler_* sp, const MhOutCtx& c)
   WGB_EXPECTS(sp->pending.active, "no call in flight on this sampler object");
   auto& pd        = sp->pending;
   pd.active       = false;
+  pd.finished     = true;
   const int sms   = num_sms();
   const int B = pd.B, L = pd.L;
   cudaStream_t st = c.stream;
@@ -1438,7 +1462,7 @@ wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop
     b.p = nullptr;
   };
   cudaDeviceSynchronize();
-  drop(s->table); drop(s->seed_slot); drop(s->slabel); drop(s->scan_state); drop(s->small_i32); drop(s->small_i64); drop(s->counts); drop(s->base);
+  drop(s->table); drop(s->seed_slot); drop(s->seed_rank); drop(s->slabel); drop(s->scan_state); drop(s->small_i32); drop(s->small_i64); drop(s->counts); drop(s->base);
   for (int i = 0; i <= wgb::kMaxHops; i++) {
     drop(s->frontier[i]); drop(s->flabel[i]); drop(s->fr_off[i]); drop(s->tcnt[i]); drop(s->typed[i]);
   }
@@ -1638,6 +1662,24 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample_finish(
     o.env           = p_env_fns;
     o.stream        = as_stream(stream);
     multihop_finish(sampler, o);
+  });
+}
+
+wholememory_error_code_t wholegraph_multihop_seed_local_ids(wholegraph_multihop_sampler_t sampler, void* out_seed_local_id_ctx,
+                                                            wholememory_env_func_t* p_env_fns, void* stream)
+{
+  using namespace wgb;
+  if (!sampler || !out_seed_local_id_ctx || !p_env_fns) return WHOLEMEMORY_INVALID_INPUT;
+  return guarded("wholegraph_multihop_seed_local_ids", [&] {
+    auto& pd = sampler->pending;
+    WGB_EXPECTS(pd.finished && !pd.active, "seed ids are available between _finish of a call and the next _begin on the same sampler object");
+    cudaStream_t st = as_stream(stream);
+    int* out        = static_cast<int*>(output_alloc(p_env_fns, out_seed_local_id_ctx, pd.S, WHOLEMEMORY_DT_INT));
+    if (pd.S > 0) {
+      mh_seed_local_kernel<<<grid_over(pd.S, num_sms()), 256, 0, st>>>(pd.seed_ref, pd.seed_rank, pd.slabel, pd.meta.fr_off[0],
+                                                                       pd.hetero ? sampler->desc_host.typed_local[0] : nullptr, pd.S, out);
+      WGB_CHECK_LAUNCH();
+    }
   });
 }
 

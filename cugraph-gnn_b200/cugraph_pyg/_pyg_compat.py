@@ -21,7 +21,7 @@ if HAS_PYG:  # pragma: no cover
     from torch_geometric.data import Data, HeteroData, FeatureStore as FeatureStoreBase, GraphStore as GraphStoreBase
     from torch_geometric.data.feature_store import TensorAttr
     from torch_geometric.data.graph_store import EdgeAttr, EdgeLayout
-    from torch_geometric.sampler import NodeSamplerInput, SamplerOutput, HeteroSamplerOutput
+    from torch_geometric.sampler import NodeSamplerInput, EdgeSamplerInput, NegativeSampling, SamplerOutput, HeteroSamplerOutput
     from torch_geometric.edge_index import ptr2index
 else:
 
@@ -227,6 +227,46 @@ else:
         input_type: Any = None
 
     @dataclass
+    class EdgeSamplerInput:
+        input_id: Any
+        row: Any
+        col: Any
+        label: Any = None
+        time: Any = None
+        input_type: Any = None
+
+    class NegativeSampling:
+        """torch_geometric.sampler.NegativeSampling: mode 'binary' | 'triplet', amount = negatives per positive."""
+
+        def __init__(self, mode, amount=1, src_weight=None, dst_weight=None):
+            mode = getattr(mode, "value", mode)
+            if mode not in ("binary", "triplet"):
+                raise ValueError(f"unknown negative sampling mode '{mode}'")
+            if amount <= 0:
+                raise ValueError(f"The attribute 'amount' needs to be positive (got {amount})")
+            if mode == "triplet" and amount != int(amount):
+                raise ValueError("'amount' needs to be an integer for triplet negative sampling")
+            self.mode, self.amount, self.src_weight, self.dst_weight = mode, amount, src_weight, dst_weight
+
+        def is_binary(self) -> bool:
+            return self.mode == "binary"
+
+        def is_triplet(self) -> bool:
+            return self.mode == "triplet"
+
+        @classmethod
+        def cast(cls, value):
+            if value is None or isinstance(value, cls):
+                return value
+            if isinstance(value, str):
+                return cls(value)
+            if isinstance(value, (tuple, list)):
+                return cls(*value)
+            if isinstance(value, dict):
+                return cls(**value)
+            raise ValueError(f"cannot cast {value!r} to NegativeSampling")
+
+    @dataclass
     class SamplerOutput:
         node: Any
         row: Any
@@ -274,3 +314,29 @@ def get_input_nodes(data, input_nodes, input_id=None):
         if input_id is not None:
             input_id = input_id[input_nodes.cpu()] if input_id.numel() != input_nodes.numel() else input_id
     return node_type, input_nodes, input_id
+
+
+def get_edge_label_index(data, edge_label_index):
+    """(edge_type | None, [2, n] tensor) -- torch_geometric.loader.utils.get_edge_label_index for store tuples."""
+    feature_store, graph_store = data
+    edge_type = None
+    if isinstance(edge_label_index, (tuple, list)) and len(edge_label_index) == 3 and all(isinstance(x, str) for x in edge_label_index):
+        edge_type, edge_label_index = tuple(edge_label_index), None
+    elif isinstance(edge_label_index, (tuple, list)) and len(edge_label_index) == 2 and not torch.is_tensor(edge_label_index[0]):
+        edge_type, edge_label_index = edge_label_index
+        edge_type = None if edge_type is None else tuple(edge_type)
+    if edge_label_index is None:
+        attrs = graph_store.get_all_edge_attrs()
+        if edge_type is None:
+            if len(attrs) != 1:
+                raise ValueError("edge_label_index needs an edge type on a graph with several edge types")
+            edge_type = attrs[0].edge_type
+        row, col = graph_store.get_edge_index(edge_type, "coo")
+        edge_label_index = torch.stack([row, col])
+    elif not torch.is_tensor(edge_label_index):
+        edge_label_index = torch.stack([torch.as_tensor(edge_label_index[0]), torch.as_tensor(edge_label_index[1])])
+    if edge_type is None and not graph_store.is_homogeneous:
+        raise ValueError("edge_label_index needs an edge type on a heterogeneous graph")
+    if graph_store.is_homogeneous and len(graph_store.get_all_edge_attrs()) == 1:
+        edge_type = None  # homogeneous loaders carry no input type (the reference's readers branch on it)
+    return edge_type, edge_label_index

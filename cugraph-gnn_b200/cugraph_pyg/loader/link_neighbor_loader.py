@@ -1,23 +1,24 @@
-"""NeighborLoader (role of the reference's cugraph_pyg/loader/neighbor_loader.py:15-236)."""
+"""LinkNeighborLoader (role of the reference's cugraph_pyg/loader/link_neighbor_loader.py:16-239)."""
 import warnings
+from typing import Callable, Dict, List, Optional, Union
 
 import numpy as np
-from typing import Callable, Dict, List, Optional, Union
 
 import cugraph_pyg
 from cugraph_pyg.sampler import BaseSampler, DistributedNeighborSampler
-from .node_loader import NodeLoader
+from .link_loader import LinkLoader
 
 
-class NeighborLoader(NodeLoader):
-    """Duck-typed torch_geometric.loader.NeighborLoader: GraphSAGE-style neighbour sampling of input nodes."""
+class LinkNeighborLoader(LinkLoader):
+    """Duck-typed torch_geometric.loader.LinkNeighborLoader: neighbour sampling around the endpoints of seed edges."""
 
-    def __init__(self, data, num_neighbors: Union[List[int], Dict], input_nodes=None, input_time=None, replace: bool = False,
-                 subgraph_type: str = "directional", disjoint: bool = False, temporal_strategy: str = "uniform",
-                 time_attr: Optional[str] = None, weight_attr: Optional[str] = None, transform: Optional[Callable] = None,
+    def __init__(self, data, num_neighbors: Union[List[int], Dict], edge_label_index=None, edge_label=None,
+                 edge_label_time=None, replace: bool = False, subgraph_type: str = "directional", disjoint: bool = False,
+                 temporal_strategy: str = "uniform", neg_sampling=None, neg_sampling_ratio=None, time_attr: Optional[str] = None,
+                 weight_attr: Optional[str] = None, transform: Optional[Callable] = None,
                  transform_sampler_output: Optional[Callable] = None, is_sorted: bool = False,
-                 filter_per_worker: Optional[bool] = None, neighbor_sampler=None, directed: bool = True,
-                 batch_size: int = 16, compression: Optional[str] = None, local_seeds_per_call: Optional[int] = None,
+                 filter_per_worker: Optional[bool] = None, neighbor_sampler=None, directed: bool = True, batch_size: int = 16,
+                 compression: Optional[str] = None, local_seeds_per_call: Optional[int] = None,
                  temporal_comparison: Optional[str] = None, **kwargs):
         if str(getattr(subgraph_type, "value", subgraph_type)) != "directional" or not directed:
             raise ValueError("Only directional subgraphs are currently supported")
@@ -25,7 +26,7 @@ class NeighborLoader(NodeLoader):
             raise ValueError("Passing a neighbor sampler is currently unsupported")
         if is_sorted:
             warnings.warn("The 'is_sorted' argument is ignored by cuGraph.")
-        if time_attr is not None or input_time is not None:
+        if time_attr is not None or edge_label_time is not None:
             raise NotImplementedError("temporal sampling is outside the B200 hot path")
         if replace:
             raise NotImplementedError("sampling with replacement is outside the B200 hot path")
@@ -43,7 +44,6 @@ class NeighborLoader(NodeLoader):
         heterogeneous = not graph_store.is_homogeneous
         num_edge_types = len(graph_store.get_all_edge_attrs())
         if isinstance(num_neighbors, dict):
-            # fan-out vector laid out [hop * T + edge type], edge types in sorted order (reference :192-201)
             sorted_keys, _, _ = graph_store._numeric_edge_types
             hops = len(next(iter(num_neighbors.values())))
             na = np.zeros(hops * len(sorted_keys), dtype="int32")
@@ -53,7 +53,6 @@ class NeighborLoader(NodeLoader):
                         na[hop * len(sorted_keys) + i] = num_neighbors[key][hop]
             num_neighbors = na
         elif heterogeneous or num_edge_types > 1:
-            # a plain list on a typed graph means "the same fan-out for every edge type" (PyG's convention)
             num_neighbors = np.repeat(np.asarray(num_neighbors, dtype="int32"), num_edge_types)
         heterogeneous = heterogeneous or num_edge_types > 1
         if heterogeneous:
@@ -68,6 +67,7 @@ class NeighborLoader(NodeLoader):
                 heterogeneous=heterogeneous, temporal=False, vertex_type_offsets=graph_store._vertex_offset_array,
                 num_edge_types=num_edge_types),
             (feature_store, graph_store), batch_size=batch_size)
-        super().__init__((feature_store, graph_store), sampler, input_nodes=input_nodes, input_time=input_time,
+        super().__init__((feature_store, graph_store), sampler, edge_label_index=edge_label_index, edge_label=edge_label,
+                         edge_label_time=None, neg_sampling=neg_sampling, neg_sampling_ratio=neg_sampling_ratio,
                          transform=transform, transform_sampler_output=transform_sampler_output,
                          filter_per_worker=filter_per_worker, batch_size=batch_size, **kwargs)

@@ -111,8 +111,79 @@ class BaseDistributedSampler:
 
         return gen()
 
-    def sample_from_edges(self, *args, **kwargs):
-        raise NotImplementedError("link-prediction sampling is outside the B200 hot path (SURVEY.md §8f row 2)")
+    def _edge_call_group(self, edges: torch.Tensor, index: torch.Tensor, label, batch_id_start: int, batch_size: int,
+                         random_state: int, metadata) -> Tuple[Dict[str, torch.Tensor], int, int]:
+        """One call group of seed EDGES.  A batch's seeds are the endpoints [sources | destinations] of its edges;
+        they are handed to the native sampler sorted inside each batch (ONE device sort per call group), which
+        deduplicates them in first-occurrence (= ascending) order -- the order the reference produces with a python
+        loop of sort + unique_consecutive per batch (distributed_sampler.py:487-533) -- and reports the local id of
+        every input seed, i.e. `edge_inverse`."""
+        n = int(edges.shape[1])
+        num_full, last = divmod(n, batch_size)
+        sizes = [batch_size] * num_full + ([last] if last else [])
+        input_offsets = torch.tensor([0] + sizes, dtype=torch.int64).cumsum(0)
+        dev = edges.device
+        # per batch [src ... | dst ...]: position of endpoint (side, e) = 2 * first(batch) + side * size(batch) + (e - first(batch))
+        e = torch.arange(n, device=dev)
+        batch_of = e // batch_size
+        first = batch_of * batch_size
+        size_of = torch.full((n,), batch_size, device=dev, dtype=torch.int64)
+        if last:
+            size_of[num_full * batch_size:] = last
+        pos_src = 2 * first + (e - first)
+        seeds = torch.empty(2 * n, dtype=torch.int64, device=dev)
+        seeds[pos_src] = edges[0]
+        seeds[pos_src + size_of] = edges[1]
+        seed_batch = torch.empty(2 * n, dtype=torch.int64, device=dev)
+        seed_batch[pos_src] = batch_of
+        seed_batch[pos_src + size_of] = batch_of
+        span = int(seeds.max()) + 1 if n else 1
+        order = torch.argsort(seed_batch * span + seeds, stable=True)  # batch-major, ascending id inside a batch
+        out = self.sample_batches(seeds=seeds[order], seed_times=None, batch_id_offsets=(2 * input_offsets).to(dev),
+                                  random_state=random_state, metadata=metadata, return_seed_local_ids=True)
+        inverse = torch.empty(2 * n, dtype=torch.int64, device=dev)
+        inverse[order] = out.pop("seed_local_ids").to(torch.int64)
+        out["edge_inverse"] = inverse  # 2 * batch entries per batch: local ids of the sources, then of the destinations
+        out["input_index"] = index.to(dev)
+        if label is not None:
+            out["input_label"] = label.to(dev)
+        out["input_offsets"] = input_offsets
+        out["map"] = out.pop("renumber_map")
+        out = {k: v for k, v in out.items() if v is not None}
+        return out, batch_id_start, batch_id_start + len(sizes) - 1
+
+    def sample_from_edges(self, edges: TensorType, *, batch_size: int = 16, random_state: int = 62,
+                          assume_equal_input_size: bool = False, input_id: Optional[TensorType] = None,
+                          input_time: Optional[TensorType] = None, input_label: Optional[TensorType] = None, metadata=None
+                          ) -> Iterator[Tuple[Dict[str, torch.Tensor], int, int]]:
+        """Sampling that starts from seed edges ([2, n], sources first): lazily yields (raw call-group dict, first batch
+        id, last batch id).  Role of the reference's distributed_sampler.py:428-726."""
+        verify_metadata(metadata)
+        if input_time is not None:
+            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+        edges = torch.as_tensor(edges).cuda()
+        n = int(edges.shape[-1])
+        input_id = torch.arange(n, dtype=torch.int64) if input_id is None else torch.as_tensor(input_id).cpu()
+        label = None if input_label is None else torch.as_tensor(input_label)
+        batches_per_call = max(1, self._local_seeds_per_call // batch_size)
+        per_call = batches_per_call * batch_size
+        local_num_batches = int(ceil(n / batch_size))
+        batch_id_start, equal = self.get_start_batch_offset(local_num_batches, assume_equal_input_size)
+        groups = [(edges[:, lo:lo + per_call], input_id[lo:lo + per_call], None if label is None else label[lo:lo + per_call])
+                  for lo in range(0, n, per_call)]
+        if self.is_multi_gpu and torch.distributed.is_initialized() and not equal:
+            t = torch.tensor([len(groups)], dtype=torch.int32, device="cuda")
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            groups += [(edges[:, :0], input_id[:0], None if label is None else label[:0])] * (int(t) - len(groups))
+
+        def gen():
+            start = batch_id_start
+            for call_id, (e, ix, lb) in enumerate(groups):
+                raw, first, last = self._edge_call_group(e, ix, lb, start, batch_size, random_state + call_id, metadata)
+                start = last + 1
+                yield raw, first, last
+
+        return gen()
 
 
 class DistributedNeighborSampler(BaseDistributedSampler):
@@ -174,7 +245,8 @@ class DistributedNeighborSampler(BaseDistributedSampler):
         by_memory = int(DistributedNeighborSampler.BASE_VERTICES_PER_BYTE * total_memory / prod)
         return max(1, min(by_memory, DistributedNeighborSampler.MAX_EDGES_PER_HOP // prod))
 
-    def sample_batches(self, seeds, seed_times, batch_id_offsets, random_state: int = 0, metadata=None) -> Dict[str, torch.Tensor]:
+    def sample_batches(self, seeds, seed_times, batch_id_offsets, random_state: int = 0, metadata=None,
+                       return_seed_local_ids: bool = False) -> Dict[str, torch.Tensor]:
         rank = torch.distributed.get_rank() if (self.is_multi_gpu and torch.distributed.is_initialized()) else 0
         kwargs = {
             "resource_handle": self._resource_handle,
@@ -187,6 +259,8 @@ class DistributedNeighborSampler(BaseDistributedSampler):
             "random_state": random_state + rank,
         }
         kwargs.update(self.__func_kwargs)
+        if return_seed_local_ids:
+            kwargs["return_seed_local_ids"] = True
         out = self.__func(**kwargs)
         out["fanout"] = torch.tensor(self.__fanout, dtype=torch.int32)
         out["rank"] = rank

@@ -12,8 +12,8 @@ import torch
 
 from typing import List
 
-from cugraph_pyg._pyg_compat import SamplerOutput, HeteroSamplerOutput, NodeSamplerInput, ptr2index
-from .sampler_utils import filter_cugraph_pyg_store, filter_cugraph_pyg_hetero_store
+from cugraph_pyg._pyg_compat import SamplerOutput, HeteroSamplerOutput, NodeSamplerInput, EdgeSamplerInput, ptr2index
+from .sampler_utils import filter_cugraph_pyg_store, filter_cugraph_pyg_hetero_store, neg_sample, neg_cat
 
 
 class SampleIterator:
@@ -44,7 +44,12 @@ class SampleIterator:
         data.num_sampled_edges = s.num_sampled_edges
         data.input_id = s.metadata[0]
         data.batch_size = int(data.input_id.size(0))
-        data.seed_time = s.metadata[1]
+        if len(s.metadata) == 2:
+            data.seed_time = s.metadata[1]
+        elif len(s.metadata) == 4:
+            data.edge_label_index, data.edge_label, data.seed_time = s.metadata[1:]
+        else:
+            raise ValueError("Invalid metadata")
         if s.csr is not None:
             # extension: the sampler's CSR block, for aggregation kernels that consume it directly
             data.csr_indptr, data.csr_indices = s.csr
@@ -65,7 +70,12 @@ class SampleIterator:
         input_type, input_id = s.metadata[0]
         data[input_type].input_id = input_id
         data[input_type].batch_size = int(input_id.size(0))
-        data[input_type].seed_time = s.metadata[1]
+        if len(s.metadata) == 2:
+            data[input_type].seed_time = s.metadata[1]
+        elif len(s.metadata) == 4:
+            data[input_type].edge_label_index, data[input_type].edge_label, data[input_type].seed_time = s.metadata[1:]
+        else:
+            raise ValueError("Invalid metadata")
         return data
 
     def __iter__(self):
@@ -108,6 +118,27 @@ class SampleReader:
     def _decode(self, raw, index: int):
         raise NotImplementedError("Must be implemented by subclass")
 
+    @staticmethod
+    def _seed_metadata(raw, index: int):
+        """(input_index, ...) of mini-batch `index`: node seeds -> (input_index, None); edge seeds ->
+        (input_index, edge_label_index, edge_label, None) with negatives (input id -1) dropped from input_index and
+        labelled 0 (reference: sampler.py:576-628)."""
+        i0, i1 = raw["_input_offsets"][index], raw["_input_offsets"][index + 1]
+        input_index = raw["input_index"][i0:i1]
+        if "edge_inverse" not in raw:
+            return (input_index, None)
+        num_seeds = i1 - i0
+        input_index = input_index[input_index >= 0]
+        num_pos = int(input_index.numel())
+        if num_seeds - num_pos > 0:
+            edge_label = torch.cat([torch.full((num_pos,), 1.0), torch.full((num_seeds - num_pos,), 0.0)])
+        elif "input_label" in raw:
+            edge_label = raw["input_label"][i0:i1]
+        else:
+            edge_label = None
+        edge_inverse = raw["edge_inverse"][2 * i0:2 * i1].view(2, -1)
+        return (input_index, edge_inverse, edge_label, None)
+
 
 class HomogeneousSampleReader(SampleReader):
     def _prepare(self, raw: Dict[str, torch.Tensor]):
@@ -139,12 +170,10 @@ class HomogeneousSampleReader(SampleReader):
         num_sampled_edges = torch.tensor([elho[index * L + h + 1] - elho[index * L + h] for h in range(L)])
         base = [raw["_base"][t][index] for t in range(L + 1)] + [n1 - n0]
         num_sampled_nodes = torch.tensor([base[t + 1] - base[t] for t in range(L + 1)])
-        i0, i1 = raw["_input_offsets"][index], raw["_input_offsets"][index + 1]
-        input_index = raw["input_index"][i0:i1]
         num_seeds = base[1]
         out = _Output(node=node, row=minors, col=None, edge=edge, batch=node[:num_seeds],
                       num_sampled_nodes=num_sampled_nodes, num_sampled_edges=num_sampled_edges,
-                      metadata=(input_index, None))
+                      metadata=self._seed_metadata(raw, index))
         if "major_offsets" in raw:
             r0, r1 = lho[index * L], lho[(index + 1) * L]
             out.col = raw["major_offsets"][r0:r1 + 1] - e0
@@ -207,12 +236,17 @@ class HeterogeneousSampleReader(SampleReader):
             edge[et] = raw["edge_renumber_map"][e0:e1]
             num_sampled_edges[et] = torch.tensor([lto[g + h + 1] - lto[g + h] for h in range(L)])
         input_type = raw["input_type"]
-        if not (isinstance(input_type, str) and input_type in self.__vertex_types):
+        if isinstance(input_type, (list, tuple)):
+            input_type = tuple(input_type)
+            if input_type not in self.__edge_types:
+                raise ValueError("Input type did not match any edge type!")
+        elif not (isinstance(input_type, str) and input_type in self.__vertex_types):
             raise ValueError("Input type did not match any vertex type!")
-        i0, i1 = raw["_input_offsets"][index], raw["_input_offsets"][index + 1]
-        input_index = raw["input_index"][i0:i1]
+        meta = self._seed_metadata(raw, index)
+        # edge_inverse already holds ids local to (label, vertex type): no de-offsetting by the other type's count
+        # (the reference subtracts `max + 1` of the lower type, sampler.py:452-461)
         return HeteroSamplerOutput(node=node, row=row, col=col, edge=edge, batch=None, num_sampled_nodes=num_sampled_nodes,
-                                   num_sampled_edges=num_sampled_edges, metadata=((input_type, input_index), None))
+                                   num_sampled_edges=num_sampled_edges, metadata=((input_type, meta[0]),) + tuple(meta[1:]))
 
 
 class BaseSampler:
@@ -225,6 +259,9 @@ class BaseSampler:
         metadata = {"input_type": index.input_type} if index.input_type is not None else None
         reader = self.__sampler.sample_from_nodes(index.node, batch_size=self.__batch_size, input_id=index.input_id,
                                                   input_time=index.time, metadata=metadata, **kwargs)
+        return self.__reader(reader)
+
+    def __reader(self, reader):
         attrs = self.__graph_store.get_all_edge_attrs()
         if len(attrs) == 1 and attrs[0].edge_type[0] == attrs[0].edge_type[2]:
             return HomogeneousSampleReader(reader)
@@ -233,5 +270,27 @@ class BaseSampler:
                                          vertex_offsets=self.__graph_store._vertex_offset_array, edge_types=edge_types,
                                          vertex_types=sorted(self.__graph_store._vertex_offsets.keys()))
 
-    def sample_from_edges(self, *args, **kwargs):
-        raise NotImplementedError("link-prediction sampling is outside the B200 hot path (SURVEY.md §8f row 2)")
+    def sample_from_edges(self, index: EdgeSamplerInput, neg_sampling=None, **kwargs) -> Iterator[SamplerOutput]:
+        """Link-prediction sampling (role of the reference's sampler.py:798-896): optional negative edges are drawn for
+        the whole epoch at once and interleaved batch by batch; negatives carry input id -1."""
+        src, dst, input_id = index.row, index.col, index.input_id
+        if index.time is not None:
+            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+        neg_batch_size = 0
+        if neg_sampling:
+            src_neg, dst_neg = neg_sample(self.__graph_store, index.row, index.col, index.input_type, self.__batch_size, neg_sampling)
+            if neg_sampling.is_binary():
+                src, _ = neg_cat(src.cuda(), src_neg, self.__batch_size)
+            else:
+                # triplet: repeat a random subset of the sources so that the lengths line up (same unique vertices)
+                scu = src.cuda()
+                per = torch.randint(0, scu.numel(), (dst_neg.numel(),), device=scu.device)
+                src, _ = neg_cat(scu, scu[per], self.__batch_size)
+            dst, neg_batch_size = neg_cat(dst.cuda(), dst_neg, self.__batch_size)
+            input_id, _ = neg_cat(input_id, torch.full((dst_neg.numel(),), -1, dtype=torch.int64, device=input_id.device),
+                                  self.__batch_size)
+        metadata = {"input_type": index.input_type} if index.input_type is not None else None
+        reader = self.__sampler.sample_from_edges(torch.stack([src.cuda(), dst.cuda()]), input_id=input_id, input_time=None,
+                                                  input_label=index.label, batch_size=self.__batch_size + neg_batch_size,
+                                                  metadata=metadata, **kwargs)
+        return self.__reader(reader)

@@ -1,5 +1,5 @@
-"""Helpers of the sampler layer (role of the reference's cugraph_pyg/sampler/sampler_utils.py:19-63; negative
-sampling lives on the link-prediction path, SURVEY.md §8f row 2, and is not built)."""
+"""Helpers of the sampler layer (role of the reference's cugraph_pyg/sampler/sampler_utils.py:19-336)."""
+from math import ceil
 from typing import Dict, Optional, Tuple, Union
 
 import torch
@@ -57,3 +57,47 @@ def filter_cugraph_pyg_hetero_store(feature_store, graph_store, node_dict, row_d
     for attr, tensor in zip(attrs, feature_store.multi_get_tensor(attrs)):
         data[attr.group_name][attr.attr_name] = tensor
     return data
+
+
+def neg_sample(graph_store, seed_src, seed_dst, input_type, batch_size: int, neg_sampling, seed_time=None,
+               node_time_func=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Negative (source, destination) pairs for a whole epoch of seed edges (reference: sampler_utils.py:95-315).
+    At least one negative per batch; ids come back type-offset, ready for the sampler."""
+    import pylibcugraph
+
+    if node_time_func is not None:
+        raise NotImplementedError("temporal negative sampling is outside the B200 hot path")
+    src_weight = getattr(neg_sampling, "src_weight", getattr(neg_sampling, "weight", None))
+    dst_weight = getattr(neg_sampling, "dst_weight", getattr(neg_sampling, "weight", None))
+    num_neg = max(int(ceil(neg_sampling.amount * seed_src.numel())), int(ceil(seed_src.numel() / batch_size)))
+    nv = graph_store._num_vertices()
+    if graph_store.is_homogeneous:
+        num_src = num_dst = list(nv.values())[0]
+        off_src = off_dst = 0
+    else:
+        num_src, num_dst = nv[input_type[0]], nv[input_type[2]]
+        off_src, off_dst = graph_store._vertex_offsets[input_type[0]], graph_store._vertex_offsets[input_type[2]]
+    for name, w, n in (("src_weight", src_weight, num_src), ("dst_weight", dst_weight, num_dst)):
+        if w is not None and w.numel() != n:
+            raise ValueError(f"The '{name}' attribute needs to match the number of nodes {n} (got {w.numel()})")
+    if src_weight is not None and dst_weight is not None and src_weight.dtype != dst_weight.dtype:
+        raise ValueError(f"The 'src_weight' and 'dst_weight' attributes need to have the same dtype "
+                         f"(got {src_weight.dtype} and {dst_weight.dtype})")
+    # sources and destinations are drawn from their own vertex-type ranges
+    res_s = pylibcugraph.negative_sampling(graph_store._resource_handle, graph_store._graph, num_neg,
+                                           vertices=torch.arange(num_src, device="cuda") + off_src, src_bias=src_weight,
+                                           dst_bias=None)
+    res_d = pylibcugraph.negative_sampling(graph_store._resource_handle, graph_store._graph, num_neg,
+                                           vertices=torch.arange(num_dst, device="cuda") + off_dst, src_bias=dst_weight,
+                                           dst_bias=None)
+    return res_s["sources"], res_d["sources"]
+
+
+def neg_cat(seed_pos: torch.Tensor, seed_neg: torch.Tensor, pos_batch_size: int) -> Tuple[torch.Tensor, int]:
+    """Interleaves positives and negatives batch by batch: [pos batch 0 | neg batch 0 | pos batch 1 | ...]
+    (reference: sampler_utils.py:318-336); returns the joined tensor and the negatives per batch."""
+    num_batches = int(ceil(seed_pos.numel() / pos_batch_size))
+    neg_batch_size = int(ceil(seed_neg.numel() / num_batches))
+    pos = torch.tensor_split(seed_pos, list(range(pos_batch_size, pos_batch_size * num_batches, pos_batch_size)))
+    neg = torch.tensor_split(seed_neg, list(range(neg_batch_size, neg_batch_size * num_batches, neg_batch_size)))
+    return torch.cat([torch.cat(pair) for pair in zip(pos, neg)]), neg_batch_size

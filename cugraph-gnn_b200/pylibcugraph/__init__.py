@@ -201,7 +201,7 @@ def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offse
                      with_replacement=False, do_expensive_check=False, prior_sources_behavior=None,
                      deduplicate_sources=False, return_hops=False, renumber=False, retain_seeds=False,
                      compression="COO", compress_per_hop=False, random_state=None, disjoint_sampling=False,
-                     return_dict=True, **unused):
+                     return_dict=True, return_seed_local_ids=False, **unused):
     if with_replacement:
         raise NotImplementedError("sampling with replacement is not on the B200 hot path")
     if disjoint_sampling:
@@ -229,8 +229,10 @@ def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offse
     if biased:
         # one CSR (edge types, if any, are ignored by the homogeneous entry point), zero-bias edges removed
         row_ptr, col, weight, edge_id = input_graph._drop_zero_weight_cached()
-    res = input_graph._get_sampler().sample(row_ptr, col, seeds, offsets, fanout, int(random_state), csr_weight=weight,
-                                            csr_edge_id=edge_id, compression=compression, int64_ids=True)
+    pend = input_graph._get_sampler().sample_async(row_ptr, col, seeds, offsets, fanout, int(random_state), csr_weight=weight,
+                                                   csr_edge_id=edge_id, compression=compression, int64_ids=True)
+    pend.want_seed_local_ids = bool(return_seed_local_ids)
+    res = pend.result()
     out = {
         "majors": res.get("majors"),
         "minors": res["minors"],
@@ -245,6 +247,8 @@ def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offse
         # extension: [L+1, B] first local id of the vertices each label discovered at step t (0 = seeds)
         "label_step_base": res["label_step_base"],
     }
+    if return_seed_local_ids:
+        out["seed_local_ids"] = res["seed_local_ids"]  # extension: local id of every input seed (link-prediction loaders)
     return out
 
 
@@ -262,7 +266,7 @@ def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_labe
                             vertex_type_offsets, biased, *, with_replacement=False, do_expensive_check=False,
                             prior_sources_behavior=None, deduplicate_sources=False, return_hops=False, renumber=False,
                             retain_seeds=False, compression="COO", compress_per_hop=False, random_state=None,
-                            disjoint_sampling=False, return_dict=True, **unused):
+                            disjoint_sampling=False, return_dict=True, return_seed_local_ids=False, **unused):
     if with_replacement:
         raise NotImplementedError("sampling with replacement is not on the B200 hot path")
     if disjoint_sampling:
@@ -290,12 +294,15 @@ def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_labe
     if random_state is None:
         random_state = int(np.random.randint(0, 2**62))
     typed = input_graph._biased_csrs(T) if biased else input_graph._typed_csrs(T)
-    res = input_graph._get_sampler().sample_hetero(
+    pend = input_graph._get_sampler().sample_hetero_async(
         [g[0] for g in typed], [g[1] for g in typed], vto, seeds, offsets, fanout, int(random_state),
         csr_weights=[g[2] for g in typed] if biased else None,
         csr_edge_ids=[g[3] for g in typed] if any(g[3] is not None for g in typed) else None, int64_ids=True,
     )
+    pend.want_seed_local_ids = bool(return_seed_local_ids)
+    res = pend.result()
     return {
+        **({"seed_local_ids": res["seed_local_ids"]} if return_seed_local_ids else {}),
         "majors": res["majors"],
         "minors": res["minors"],
         "major_offsets": None,
@@ -337,4 +344,56 @@ homogeneous_uniform_temporal_neighbor_sample = _not_on_path("homogeneous_uniform
 homogeneous_biased_temporal_neighbor_sample = _not_on_path("homogeneous_biased_temporal_neighbor_sample")
 heterogeneous_uniform_temporal_neighbor_sample = _not_on_path("heterogeneous_uniform_temporal_neighbor_sample")
 heterogeneous_biased_temporal_neighbor_sample = _not_on_path("heterogeneous_biased_temporal_neighbor_sample")
-negative_sampling = _not_on_path("negative_sampling")
+
+
+def negative_sampling(resource_handle, graph, num_samples, random_state=None, vertices=None, src_bias=None, dst_bias=None,
+                      remove_duplicates=False, remove_false_negatives=False, exact_number_of_samples=False,
+                      do_expensive_check=False):
+    """pylibcugraph.negative_sampling: `num_samples` random (source, destination) pairs, endpoints drawn independently
+    from `vertices` (default: every vertex) in proportion to src_bias / dst_bias (default: uniform).
+    remove_false_negatives drops pairs that are edges of `graph`, remove_duplicates repeated pairs; with
+    exact_number_of_samples the draw is repeated (a bounded number of times) until num_samples pairs remain.
+    Reference call site: python/cugraph-pyg/cugraph_pyg/sampler/sampler_utils.py:66-92."""
+    dev = graph.col.device
+    n = int(num_samples)
+    gen = None
+    if random_state is not None:
+        gen = torch.Generator(device=dev).manual_seed(int(random_state) & 0x7FFFFFFFFFFFFFFF)
+    verts = None if vertices is None else _as_cuda(vertices, torch.int64)
+    count = graph.num_vertices if verts is None else int(verts.numel())
+
+    def draw(bias, k):
+        if bias is None:
+            ix = torch.randint(0, count, (k,), device=dev, generator=gen)
+        else:
+            b = _as_cuda(bias).double()
+            if b.numel() != count:
+                raise ValueError("bias arrays must have one entry per candidate vertex")
+            cdf = torch.cumsum(b, 0)
+            u = torch.rand(k, device=dev, dtype=torch.float64, generator=gen) * cdf[-1]
+            ix = torch.searchsorted(cdf, u, right=True).clamp_(max=count - 1)
+        return ix if verts is None else verts[ix]
+
+    edge_keys = None
+    src = torch.empty(0, dtype=torch.int64, device=dev)
+    dst = torch.empty(0, dtype=torch.int64, device=dev)
+    for attempt in range(8):
+        need = n - int(src.numel())
+        if need <= 0:
+            break
+        s, d = draw(src_bias, need), draw(dst_bias, need)
+        if remove_false_negatives:
+            if edge_keys is None:
+                rows = torch.repeat_interleave(torch.arange(graph.num_vertices, device=dev), graph.row_ptr[1:] - graph.row_ptr[:-1])
+                edge_keys = torch.sort(rows * graph.num_vertices + graph.col.long()).values
+            key = s * graph.num_vertices + d
+            pos = torch.searchsorted(edge_keys, key).clamp_(max=max(int(edge_keys.numel()) - 1, 0))
+            ok = edge_keys[pos] != key if edge_keys.numel() else torch.ones_like(key, dtype=torch.bool)
+            s, d = s[ok], d[ok]
+        src, dst = torch.cat([src, s]), torch.cat([dst, d])
+        if remove_duplicates:
+            key = torch.unique(src * graph.num_vertices + dst)
+            src, dst = key // graph.num_vertices, key % graph.num_vertices
+        if not exact_number_of_samples:
+            break
+    return {"sources": src[:n], "destinations": dst[:n]}

@@ -40,6 +40,10 @@ _hfinish = wmb.native_symbol("wholegraph_hetero_multihop_neighbor_sample_finish"
 _hfinish.restype = ctypes.c_int
 _hfinish.argtypes = [_vp] * 13
 
+_seed_ids = wmb.native_symbol("wholegraph_multihop_seed_local_ids")
+_seed_ids.restype = ctypes.c_int
+_seed_ids.argtypes = [_vp, _vp, _vp, _vp]
+
 _HETERO_OUT_NAMES = ("majors", "minors", "edge_id", "edge_type", "label_type_hop_offsets", "renumber_map", "renumber_map_offsets",
                      "edge_renumber_map", "edge_renumber_map_offsets", "label_type_step_base")
 
@@ -94,6 +98,13 @@ class MultiHopSampler(object):
                      get_stream())
         wmb.check_wholememory_error_code(err)
         return PendingSample(self, keep, csr, len(fanout))
+
+    def seed_local_ids(self) -> "torch.Tensor":
+        """int32 [S]: local id of every input seed (duplicates included) of the call that was last finished on this
+        object; for heterogeneous calls local to the seed's (label, vertex type).  Call before the next sample*()."""
+        ctx = TorchMemoryContext()
+        wmb.check_wholememory_error_code(_seed_ids(self._h, ctx.get_c_context(), get_wholegraph_env_fns(), get_stream()))
+        return ctx.get_tensor()
 
     def sample_hetero_async(self, csr_row_ptrs, csr_cols, vertex_type_offsets, seeds: "torch.Tensor",
                             label_offsets: "torch.Tensor", fanout: List[int], random_state: int, *, csr_weights=None,
@@ -153,6 +164,7 @@ class PendingSample(object):
         self._csr = csr
         self._hops = hops
         self._out = None
+        self.want_seed_local_ids = False  # set before result(): adds out["seed_local_ids"]
 
     def result(self):
         if self._out is not None:
@@ -171,6 +183,8 @@ class PendingSample(object):
         out = {n: ctx[n].get_tensor() for n in _OUT_NAMES if ctx[n].get_tensor() is not None}
         # [L+1, B]: first local id of the vertices each label discovered at step t (0 = seeds)
         out["label_step_base"] = out["label_step_base"].view(self._hops + 1, -1)
+        if self.want_seed_local_ids:
+            out["seed_local_ids"] = self._sampler.seed_local_ids()
         self._out = out
         self._keep = None
         return out
@@ -185,6 +199,7 @@ class PendingHeteroSample(object):
         self._hops = hops
         self._vt = num_vertex_types
         self._out = None
+        self.want_seed_local_ids = False
 
     def result(self):
         if self._out is not None:
@@ -195,6 +210,8 @@ class PendingHeteroSample(object):
         wmb.check_wholememory_error_code(err)
         out = {n: ctx[n].get_tensor() for n in _HETERO_OUT_NAMES}
         out["label_type_step_base"] = out["label_type_step_base"].view(self._hops + 1, self._vt, -1)
+        if self.want_seed_local_ids:
+            out["seed_local_ids"] = self._sampler.seed_local_ids()
         self._out = out
         self._keep = None
         return out

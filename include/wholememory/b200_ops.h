@@ -115,6 +115,16 @@ wholememory_error_code_t wholegraph_multihop_neighbor_sample_finish(wholegraph_m
                                                                     wholememory_env_func_t* p_env_fns,
                                                                     void* stream);
 
+/* Local id of every INPUT seed of the call that was last finished on `sampler` (duplicates included, int32 [S]; for a
+ * heterogeneous call the id is local to the seed's (label, vertex type)).  The link-prediction loaders use it as
+ * edge_label_index: the reference sorts and unique_consecutive's the endpoints of every batch in python to get the same
+ * mapping (/root/reference/python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:487-533, "a good target for a
+ * C++ function").  Valid between _finish and the next _begin on the same sampler object. */
+wholememory_error_code_t wholegraph_multihop_seed_local_ids(wholegraph_multihop_sampler_t sampler,
+                                                            void* out_seed_local_id_ctx,
+                                                            wholememory_env_func_t* p_env_fns,
+                                                            void* stream);
+
 /* Heterogeneous form: what cugraph-pyg asks of pylibcugraph.heterogeneous_{uniform,biased}_neighbor_sample
  * (/root/reference/python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:53-94, 784-819) and decodes in
  * HeterogeneousSampleReader (/root/reference/python/cugraph-pyg/cugraph_pyg/sampler/sampler.py:280-490).

@@ -266,3 +266,107 @@ def test_neighbor_loader_biased_reference_pin(pyg):
     assert out.edge_index.shape[1] == 2
     assert (out.edge_index.cpu() == torch.tensor([[3, 4], [1, 2]])).all()
     assert out.e_id.cpu().tolist() == [1, 2]
+
+
+# ---- link prediction loaders (reference: test_neighbor_loader.py:196-352, 455-527) -----------------------------
+@pytest.mark.parametrize("num_nodes,num_edges,select_edges,batch_size", [(7, 29, 17, 1), (19, 62, 17, 3), (120, 1500, 700, 32)])
+@pytest.mark.parametrize("depth,num_neighbors", [(1, 1), (3, 4)])
+def test_link_neighbor_loader_basic(pyg, num_nodes, num_edges, select_edges, batch_size, depth, num_neighbors):
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    from cugraph_pyg.loader import LinkNeighborLoader
+
+    g = torch.Generator().manual_seed(num_edges)
+    graph_store = GraphStore()
+    ei = torch.stack([torch.randint(0, num_nodes, (num_edges,), generator=g), torch.randint(0, num_nodes, (num_edges,), generator=g)])
+    graph_store[("n", "e", "n"), "coo", False, (num_nodes, num_nodes)] = ei
+    eix = torch.randperm(num_edges, generator=g)[:select_edges]
+    elx = ei[:, eix]
+    loader = LinkNeighborLoader((FeatureStore(), graph_store), num_neighbors=[num_neighbors] * depth, edge_label_index=elx,
+                                batch_size=batch_size, shuffle=False)
+    assert len(loader) == (select_edges + batch_size - 1) // batch_size
+    have = set(zip(ei[0].tolist(), ei[1].tolist()))
+    seen = 0
+    for i, batch in enumerate(loader):
+        lo, hi = i * batch_size, min((i + 1) * batch_size, select_edges)
+        assert (batch.input_id.cpu() == torch.arange(lo, hi)).all()
+        assert (elx[:, lo:hi] == batch.n_id.cpu()[batch.edge_label_index.cpu()]).all()
+        # seeds (the batch's distinct endpoints) come first and sorted, as in the reference
+        uniq = torch.unique(elx[:, lo:hi])
+        assert batch.n_id[: uniq.numel()].cpu().tolist() == uniq.tolist()
+        src, dst = batch.n_id.cpu()[batch.edge_index[0].cpu()], batch.n_id.cpu()[batch.edge_index[1].cpu()]
+        assert all((int(s), int(d)) in have for s, d in zip(src, dst))
+        seen += 1
+    assert seen == len(loader)
+
+
+def test_link_neighbor_loader_len(pyg):
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    from cugraph_pyg.loader import LinkNeighborLoader
+
+    eli = torch.tensor([[0, 1, 2, 3, 4], [1, 2, 3, 4, 0]])
+    graph_store = GraphStore()
+    graph_store[("n", "e", "n"), "coo", False, (5, 5)] = eli
+    data = (FeatureStore(), graph_store)
+    assert len(LinkNeighborLoader(data, num_neighbors=[1], edge_label_index=eli, batch_size=2)) == 3
+    assert len(LinkNeighborLoader(data, num_neighbors=[1], edge_label_index=eli, batch_size=2, drop_last=True)) == 2
+    loader = LinkNeighborLoader(data, num_neighbors=[1], edge_label_index=("n", "e", "n"), batch_size=2)
+    with pytest.raises(ValueError, match="edge_label_index"):
+        len(loader)
+    assert sum(1 for _ in loader) == 3  # all edges of the type are the seeds
+
+
+@pytest.mark.parametrize("batch_size", [1, 2])
+@pytest.mark.parametrize("mode,amount", [("binary", 1), ("binary", 0.1), ("triplet", 2)])
+def test_link_neighbor_loader_negative_sampling(pyg, batch_size, mode, amount):
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    from cugraph_pyg.loader import LinkNeighborLoader
+    from cugraph_pyg._pyg_compat import NegativeSampling
+
+    num_edges, num_nodes, select_edges = 62, 19, 17
+    g = torch.Generator().manual_seed(5)
+    ei = torch.stack([torch.randint(0, num_nodes, (num_edges,), generator=g), torch.randint(0, num_nodes, (num_edges,), generator=g)])
+    graph_store = GraphStore()
+    graph_store[("n", "e", "n"), "coo", False, (num_nodes, num_nodes)] = ei
+    elx = ei[:, torch.randperm(num_edges, generator=g)[:select_edges]]
+    loader = LinkNeighborLoader((FeatureStore(), graph_store), num_neighbors=[3, 3, 3], edge_label_index=elx,
+                                batch_size=batch_size, neg_sampling=NegativeSampling(mode, amount), shuffle=False)
+    n_pos = 0
+    for i, batch in enumerate(loader):
+        assert batch.edge_label[0] == 1.0
+        pos = int((batch.edge_label == 1.0).sum())
+        assert pos == batch.input_id.numel() and batch.edge_label.numel() > pos  # at least one negative per batch
+        assert (batch.edge_label[pos:] == 0.0).all()
+        lo = i * batch_size
+        got = batch.n_id.cpu()[batch.edge_label_index.cpu()]
+        assert got.shape[1] == batch.edge_label.numel()
+        if mode == "binary":
+            assert (got[:, :pos] == elx[:, lo:lo + pos]).all()
+        else:
+            assert (got[1, :pos] == elx[1, lo:lo + pos]).all()
+        assert int(got.max()) < num_nodes
+        n_pos += pos
+    assert n_pos == select_edges
+
+
+def test_neighbor_loader_hetero_linkpred(pyg):
+    """reference: test_neighbor_loader_hetero_linkpred (:455-527) with its value-level expectations."""
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    from cugraph_pyg.loader import LinkNeighborLoader
+
+    graph_store, src, dst, asrc, adst = _paper_author(torch, GraphStore)
+    loader = LinkNeighborLoader((FeatureStore(), graph_store),
+                                num_neighbors={("paper", "cites", "paper"): [2, 2], ("author", "writes", "paper"): [2, 2]},
+                                edge_label_index=(("author", "writes", "paper"), torch.stack([asrc, adst])), batch_size=5)
+    out = next(iter(loader))
+    assert out["paper"].n_id.tolist() == [0, 1, 2, 3, 4, 5]
+    assert out["author"].n_id.tolist() == [0, 1, 2, 3]
+    assert out["paper"].num_sampled_nodes.tolist() == [5, 1, 0]
+    assert out["author"].num_sampled_nodes.tolist() == [4, 0, 0]
+    assert out["paper", "cites", "paper"].edge_index.shape == torch.Size([2, 8])
+    assert out["paper", "cites", "paper"].num_sampled_edges.tolist() == [7, 1]
+    assert "edge_label_index" not in out["paper", "cites", "paper"]
+    assert out["author", "writes", "paper"].edge_index.shape == torch.Size([2, 6])
+    assert out["author", "writes", "paper"].num_sampled_edges.tolist() == [5, 1]
+    assert list(out["author", "writes", "paper"].edge_label_index.shape) == [2, 5]
+    assert out["author", "writes", "paper"].edge_label_index.tolist()[0] == [0, 1, 2, 3, 3]
+    assert out["author", "writes", "paper"].edge_label_index.tolist()[1] == [0, 1, 2, 3, 4]
