@@ -274,36 +274,50 @@ __global__ void __launch_bounds__(256) uniform_small_kernel(ChunkRef row_ptr, un
       off_own       = offsets[b_own];
       if (N_own > M) skip_own = affine_skip_tab(tab, 32ULL * (unsigned long long)b_own);
     }
-    // phase 2: GPW rows per step
+    // phase 2: GPW rows per step.  The random `col` read of a step is its only long-latency operation; steps run in
+    // chunks of kChunk whose loads are all issued before the first dependent store, so a lane keeps kChunk DRAM
+    // reads in flight instead of one (the chain resolution in between is register/shuffle work only).
+    constexpr int kChunk = G < 8 ? G : 8;
 #pragma unroll 1
-    for (int step = 0; step < G; step++) {
-      const int src   = step * GPW + sub;
-      const int N     = __shfl_sync(0xffffffffu, N_own, src);
-      const long long start = __shfl_sync(0xffffffffu, start_own, src);
-      const int off   = __shfl_sync(0xffffffffu, off_own, src);
-      Affine row_skip;
-      row_skip.g = __shfl_sync(0xffffffffu, skip_own.g, src);
-      row_skip.s = __shfl_sync(0xffffffffu, skip_own.s, src);
-      const long long b = batch * 32 + src;
-      if (N > 0) {
-        int a      = g;
-        bool write = g < N;
-        if (N > M) {
-          const bool valid = g < M;
-          Pcg rng;
-          rng.init_with_skip(seed, 32ULL * (unsigned long long)b + (unsigned long long)g, affine_then(row_skip, lane_skip));
-          int xr = rng.next_i32();
-          int x  = valid ? xr % (N - g) : -1;
-          a      = resolve_chain_group<G>(x, valid, g, lane, sub, gmask, N, M, Wg);
-          write  = valid;
+    for (int step0 = 0; step0 < G; step0 += kChunk) {
+      ColT val[kChunk];
+      int pos[kChunk];
+      unsigned int wmask = 0;
+#pragma unroll
+      for (int k = 0; k < kChunk; k++) {
+        const int src   = (step0 + k) * GPW + sub;
+        const int N     = __shfl_sync(0xffffffffu, N_own, src);
+        const long long start = __shfl_sync(0xffffffffu, start_own, src);
+        const int off   = __shfl_sync(0xffffffffu, off_own, src);
+        Affine row_skip;
+        row_skip.g = __shfl_sync(0xffffffffu, skip_own.g, src);
+        row_skip.s = __shfl_sync(0xffffffffu, skip_own.s, src);
+        const long long b = batch * 32 + src;
+        pos[k] = off + g;
+        if (N > 0) {
+          int a      = g;
+          bool write = g < N;
+          if (N > M) {
+            const bool valid = g < M;
+            Pcg rng;
+            rng.init_with_skip(seed, 32ULL * (unsigned long long)b + (unsigned long long)g, affine_then(row_skip, lane_skip));
+            int xr = rng.next_i32();
+            int x  = valid ? xr % (N - g) : -1;
+            a      = resolve_chain_group<G>(x, valid, g, lane, sub, gmask, N, M, Wg);
+            write  = valid;
+          }
+          if (write) {
+            val[k] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + a));
+            if (lid) lid[off + g] = (int)b;
+            if (gid) gid[off + g] = start + a;
+            wmask |= 1u << k;
+          }
         }
-        if (write) {
-          out[off + g] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + a));
-          if (lid) lid[off + g] = (int)b;
-          if (gid) gid[off + g] = start + a;
-        }
+        __syncwarp();
       }
-      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < kChunk; k++)
+        if ((wmask >> k) & 1u) out[pos[k]] = val[k];
     }
   }
 }
