@@ -14,6 +14,7 @@ import torch
 import pylibcugraph
 from cugraph_pyg._pyg_compat import EdgeAttr, EdgeLayout, GraphStoreBase
 from cugraph_pyg.tensor import DistMatrix
+from cugraph_pyg.utils import dist as dist_utils
 
 
 class GraphStore(GraphStoreBase):
@@ -124,9 +125,7 @@ class GraphStore(GraphStoreBase):
                     bump(et[0], m.local_coo.max() + 1)
         if self.is_multi_gpu:
             for k in sorted(nv):
-                t = torch.tensor(nv[k], device="cuda")
-                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-                nv[k] = int(t)
+                nv[k] = dist_utils.all_reduce_max(nv[k])
         self.__num_vertices_cache = dict(nv)
         return nv
 
@@ -172,14 +171,7 @@ class GraphStore(GraphStoreBase):
 
     def __edge_list(self, finalize: bool):
         keys = sorted(self.__edge_indices.keys())
-        counts = torch.tensor([self.__edge_indices[k].local_row.numel() for k in keys], dtype=torch.int64, device="cuda")
-        if self.is_multi_gpu:
-            world, rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
-            all_counts = torch.empty((world, counts.numel()), dtype=torch.int64, device="cuda")
-            torch.distributed.all_gather_into_tensor(all_counts, counts)
-            starts = all_counts[:rank].sum(0)
-        else:
-            starts = torch.zeros_like(counts)
+        starts = dist_utils.edge_id_starts([self.__edge_indices[k].local_row.numel() for k in keys])
         offs = self._vertex_offsets
         dst, src, eid, etp, wgt = [], [], [], [], []
         for i, k in enumerate(keys):

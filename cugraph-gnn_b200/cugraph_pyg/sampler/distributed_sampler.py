@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 import pylibcugraph
+from cugraph_pyg.utils import dist as dist_utils
 from .sampler_utils import verify_metadata
 
 TensorType = Union[torch.Tensor, np.ndarray, list]
@@ -53,15 +54,9 @@ class BaseDistributedSampler:
 
     def get_start_batch_offset(self, local_num_batches: int, assume_equal_input_size: bool = False) -> Tuple[int, bool]:
         """First global batch id of this rank, and whether every rank has the same number of batches."""
-        if not (self.is_multi_gpu and torch.distributed.is_initialized()):
+        if not self.is_multi_gpu:
             return 0, True
-        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        if assume_equal_input_size:
-            return rank * local_num_batches, True
-        t = torch.empty((world,), dtype=torch.int64, device="cuda")
-        torch.distributed.all_gather_into_tensor(t, torch.tensor([local_num_batches], dtype=torch.int64, device="cuda"))
-        counts = t.tolist()
-        return int(sum(counts[:rank])), len(set(counts)) == 1
+        return dist_utils.batch_id_start(local_num_batches, assume_equal_input_size)
 
     def _call_group(self, seeds: torch.Tensor, index: torch.Tensor, batch_id_start: int, batch_size: int,
                     random_state: int, metadata) -> Tuple[Dict[str, torch.Tensor], int, int]:
@@ -94,11 +89,9 @@ class BaseDistributedSampler:
         batch_id_start, equal = self.get_start_batch_offset(local_num_batches, assume_equal_input_size)
         seed_groups = list(torch.split(nodes, seeds_per_call))
         index_groups = list(torch.split(input_id, seeds_per_call))
-        if self.is_multi_gpu and torch.distributed.is_initialized() and not equal:
+        if self.is_multi_gpu and not equal:
             # every rank makes the same number of calls (uneven ranks sample empty groups)
-            t = torch.tensor([len(seed_groups)], dtype=torch.int32, device="cuda")
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            pad = int(t) - len(seed_groups)
+            pad = dist_utils.equalized_call_count(len(seed_groups), equal) - len(seed_groups)
             seed_groups += [nodes[:0]] * pad
             index_groups += [input_id[:0]] * pad
 
@@ -171,10 +164,9 @@ class BaseDistributedSampler:
         batch_id_start, equal = self.get_start_batch_offset(local_num_batches, assume_equal_input_size)
         groups = [(edges[:, lo:lo + per_call], input_id[lo:lo + per_call], None if label is None else label[lo:lo + per_call])
                   for lo in range(0, n, per_call)]
-        if self.is_multi_gpu and torch.distributed.is_initialized() and not equal:
-            t = torch.tensor([len(groups)], dtype=torch.int32, device="cuda")
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            groups += [(edges[:, :0], input_id[:0], None if label is None else label[:0])] * (int(t) - len(groups))
+        if self.is_multi_gpu and not equal:
+            pad = dist_utils.equalized_call_count(len(groups), equal) - len(groups)
+            groups += [(edges[:, :0], input_id[:0], None if label is None else label[:0])] * pad
 
         def gen():
             start = batch_id_start
