@@ -188,8 +188,8 @@ class MGGraph(SGGraph):
             dist.all_gather(out, pad)
             return torch.cat([o[: int(s)] for o, s in zip(out, sizes)])
 
-        nv = None
-        if vertices_array is not None:
+        nv = kwargs.pop("num_vertices", None)
+        if nv is None and vertices_array is not None:
             v = gather(vertices_array, torch.int64)
             nv = int(v.max()) + 1 if v.numel() else 0
         super().__init__(resource_handle, graph_properties, gather(src_array, torch.int64), gather(dst_array, torch.int64),

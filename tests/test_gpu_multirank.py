@@ -133,3 +133,67 @@ def test_chunked_gather_scatter_two_ranks(partition):
 
 def test_chunked_csr_sampling_two_ranks():
     _run(_sampler_worker)
+
+
+# ---- cugraph_pyg loaders on two ranks (reference: tests/loader/test_neighbor_loader_mg.py:52-190) ---------------
+def _pyg_worker(rank, world, port, case):
+    torch = _setup(rank, world)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.distributed.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from cugraph_pyg.data import GraphStore, FeatureStore
+    from cugraph_pyg.loader import NeighborLoader
+    from graphs import karate_csr
+
+    if case == "karate":
+        row_ptr, col = karate_csr(np.int64)
+        dst = np.repeat(np.arange(34), np.diff(row_ptr))
+        ei_all = torch.from_numpy(np.stack([col, dst]))  # PyG (source, destination)
+        ei = torch.tensor_split(ei_all.clone(), world, dim=1)[rank].cuda()
+        graph_store = GraphStore()
+        graph_store.put_edge_index(ei, ("person", "knows", "person"), "coo", False, (34, 34))
+        feat = (torch.arange(34)[:, None] * 3 + torch.arange(16)[None, :]).float()
+        feature_store = FeatureStore()
+        feature_store["person", "feat", None] = torch.tensor_split(feat, world)[rank]  # every rank puts its slice
+        ix_train = torch.tensor_split(torch.arange(34), world)[rank]
+        loader = NeighborLoader((feature_store, graph_store), [5, 5], input_nodes=ix_train, batch_size=8)
+        have = set(zip(ei_all[0].tolist(), ei_all[1].tolist()))
+        seen = []
+        for batch in loader:
+            assert torch.equal(batch.feat.cpu(), feat[batch.n_id.cpu()])  # rows of both ranks, read by P2P
+            src, dst_ = batch.n_id.cpu()[batch.edge_index[0].cpu()], batch.n_id.cpu()[batch.edge_index[1].cpu()]
+            assert all((int(s), int(d)) in have for s, d in zip(src, dst_))  # edges contributed by either rank
+            assert int(batch.num_sampled_nodes.sum()) == batch.n_id.numel()
+            seen += batch.n_id[: batch.batch_size].cpu().tolist()
+        assert seen == ix_train.tolist()
+        # global edge ids: this rank's partition starts after the lower ranks' edges
+        assert len(loader) == (len(ix_train) + 7) // 8
+    else:
+        # reference: run_test_neighbor_loader_biased_mg -- the zero-bias edge of every rank is never sampled
+        eix = torch.stack([torch.arange(3 * (world + rank), 3 * (world + rank + 1)), torch.arange(3 * rank, 3 * (rank + 1))]).cuda()
+        graph_store = GraphStore()
+        graph_store.put_edge_index(eix, ("person", "knows", "person"), "coo")
+        feature_store = FeatureStore()
+        feature_store["person", "feat", None] = torch.randint(128, (6 * world, 12))
+        feature_store[("person", "knows", "person"), "bias", None] = torch.cat([torch.tensor([0, 1, 1], dtype=torch.float32) for _ in range(world)])
+        loader = NeighborLoader((feature_store, graph_store), [1], input_nodes=torch.arange(3 * rank, 3 * (rank + 1)).cuda(),
+                                batch_size=3, weight_attr="bias")
+        out = list(iter(loader))
+        assert len(out) == 1
+        assert (out[0].edge_index.cpu() == torch.tensor([[3, 4], [1, 2]])).all()
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize("case", ["karate", "biased"])
+def test_neighbor_loader_two_ranks(case):
+    import socket
+    import torch
+    from pylibwholegraph.utils.multiprocess import multiprocess_run
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("NCCL needs one GPU per rank")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    multiprocess_run(2, functools.partial(_pyg_worker, port=port, case=case))
