@@ -101,7 +101,7 @@ static double now_sec()
   return ts.tv_sec + ts.tv_nsec * 1e-9;
 }
 
-static void comm_barrier(wholememory_comm_t c)
+void comm_barrier(wholememory_comm_t c)
 {
   if (c->size <= 1) return;
   auto* reg = static_cast<ShmRegion*>(c->shm);
@@ -120,7 +120,7 @@ static void comm_barrier(wholememory_comm_t c)
 }
 
 // every rank contributes `bytes` (<= kSlotBytes); out receives size*bytes
-static void comm_allgather(wholememory_comm_t c, const void* in, void* out, size_t bytes)
+void comm_allgather(wholememory_comm_t c, const void* in, void* out, size_t bytes)
 {
   if (bytes > (size_t)kSlotBytes) throw logic_error("allgather payload too large");
   if (c->size <= 1) {
@@ -1303,6 +1303,7 @@ wholememory_error_code_t wholememory_create_embedding(wholememory_embedding_t* e
 wholememory_error_code_t wholememory_destroy_embedding(wholememory_embedding_t e)
 {
   if (!e) return WHOLEMEMORY_INVALID_INPUT;
+  wgb::embedding_release_training_state(e);  // optimizer states, inbox, scratch (collective, like the table itself)
   auto err = wholememory_destroy_tensor(e->tensor);
   delete e;
   return err;

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include <wholememory/embedding.h>
@@ -163,14 +164,26 @@ struct wholememory_tensor_ {
   bool is_wholememory         = false;
 };
 
+struct wholememory_embedding_optimizer_;
 struct wholememory_embedding_ {
   wholememory_tensor_t tensor = nullptr;
   int user_sms                = -1;
+  // trainable embeddings (embedding_optimizer.cu)
+  wholememory_embedding_optimizer_* optimizer = nullptr;
+  std::vector<std::pair<std::string, wholememory_tensor_t>> states;  // per-row optimizer states, partitioned like the table
+  std::vector<const char*> state_names;                              // nullptr-terminated view of `states`
+  wholememory_tensor_t inbox_idx = nullptr, inbox_grad = nullptr;    // peer-mapped (index, gradient) mailboxes
+  size_t inbox_cap                = 0;                               // entries per rank
+  void* scratch[6]                = {};
+  size_t scratch_bytes[6]         = {};
 };
 
 namespace wgb {
 
 ChunkRef make_chunk_ref(wholememory_tensor_t t);
+void comm_barrier(wholememory_comm_t c);
+void comm_allgather(wholememory_comm_t c, const void* in, void* out, size_t bytes);  // bytes <= 256 per rank
+void embedding_release_training_state(wholememory_embedding_t e);
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 int num_sms();
 

@@ -250,6 +250,13 @@ _c_create_emb = _sig("wholememory_create_embedding", _i, ctypes.POINTER(_vp), ct
 _c_destroy_emb = _sig("wholememory_destroy_embedding", _i, _vp)
 _c_emb_tensor = _sig("wholememory_embedding_get_embedding_tensor", _vp, _vp)
 _c_emb_gather = _sig("wholememory_embedding_gather", _i, _vp, _vp, _vp, ctypes.c_bool, _vp, ctypes.c_int64)
+_c_opt_create = _sig("wholememory_create_embedding_optimizer", _i, ctypes.POINTER(_vp), _i)
+_c_opt_set = _sig("wholememory_optimizer_set_parameter", _i, _vp, ctypes.c_char_p, _vp)
+_c_opt_destroy = _sig("wholememory_destroy_embedding_optimizer", None, _vp)
+_c_emb_set_opt = _sig("wholememory_embedding_set_optimizer", _i, _vp, _vp)
+_c_emb_apply = _sig("wholememory_embedding_gather_gradient_apply", _i, _vp, _vp, _vp, ctypes.c_bool, ctypes.c_float, _vp, ctypes.c_int64)
+_c_emb_state_names = _sig("wholememory_embedding_get_optimizer_state_names", ctypes.POINTER(ctypes.c_char_p), _vp)
+_c_emb_state = _sig("wholememory_embedding_get_optimizer_state", _vp, _vp, ctypes.c_char_p)
 
 
 def native_symbol(name):
@@ -761,6 +768,71 @@ class PyWholeMemoryEmbedding:
             check_wholememory_error_code(_c_destroy_emb(self._h))
             self._h = None
 
+    def get_optimizer_state_names(self):
+        names, arr, i = [], _c_emb_state_names(self._h), 0
+        while arr[i] is not None:
+            names.append(arr[i].decode())
+            i += 1
+        return names
+
+    def get_optimizer_state(self, state_name: str) -> PyWholeMemoryTensor:
+        h = _c_emb_state(self._h, state_name.encode())
+        if not h:
+            raise ValueError(f"no optimizer state named {state_name!r}")
+        return PyWholeMemoryTensor(h, owner=False)
+
+    def writeback_all_cache(self, stream_int=0):
+        pass
+
+    def drop_all_cache(self, stream_int=0):
+        pass
+
+
+class WholeMemoryOptimizerType(enum.IntEnum):
+    OptNone = 0
+    OptSgd = 1
+    OptLazyAdam = 2
+    OptRmsProp = 3
+    OptAdaGrad = 4
+
+
+class WholeMemoryOptimizer:
+    """wholememory_embedding_optimizer_t (reference: binding/wholememory_binding.pyx:672-708)."""
+
+    def __init__(self):
+        self._h = None
+        self.optimizer_type = WholeMemoryOptimizerType.OptNone
+        self.param_dict = {}
+
+    def create_optimizer(self, optimizer_type, param_dict: dict):
+        h = _vp()
+        check_wholememory_error_code(_c_opt_create(ctypes.byref(h), int(optimizer_type)))
+        self._h = h.value
+        self.optimizer_type = WholeMemoryOptimizerType(int(optimizer_type))
+        self.param_dict = dict(param_dict)
+        for key, value in param_dict.items():
+            v = ctypes.c_float(float(value))
+            check_wholememory_error_code(_c_opt_set(self._h, key.encode(), ctypes.cast(ctypes.byref(v), _vp)))
+
+    def add_embedding(self, embedding: PyWholeMemoryEmbedding):
+        check_wholememory_error_code(_c_emb_set_opt(embedding.get_c_handle(), self._h))
+
+    def destroy_optimizer(self):
+        if self._h:
+            _c_opt_destroy(self._h)
+            self._h = None
+        self.optimizer_type = WholeMemoryOptimizerType.OptNone
+
+
+def create_optimizer(optimizer_type, param_dict: dict):
+    o = WholeMemoryOptimizer()
+    o.create_optimizer(optimizer_type, param_dict)
+    return o
+
+
+def create_non_optimizer():
+    return WholeMemoryOptimizer()
+
 
 def create_embedding(tensor_desc, comm, memory_type, memory_location, cache_policy=None,
                      embedding_entry_partition=None, user_defined_sms=-1, round_robin_size=0):
@@ -773,6 +845,12 @@ def create_embedding(tensor_desc, comm, memory_type, memory_location, cache_poli
                       int(memory_location), None, part, user_defined_sms, round_robin_size)
     )
     return PyWholeMemoryEmbedding(h.value)
+
+
+def EmbeddingGatherGradientApply(wm_embedding, indice, grads, adjust_cache, lr, p_env_fns_int, stream_int):
+    check_wholememory_error_code(
+        _c_emb_apply(wm_embedding.get_c_handle(), _h(indice), _h(grads), bool(adjust_cache), float(lr), _vp(p_env_fns_int), stream_int or 0)
+    )
 
 
 def EmbeddingGatherForward(wm_embedding, indice, output, adjust_cache, p_env_fns_int, stream_int):

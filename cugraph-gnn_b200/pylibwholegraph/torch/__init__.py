@@ -18,6 +18,10 @@ from .embedding import (
     create_embedding_from_filelist,
     destroy_embedding,
     create_builtin_cache_policy,
+    WholeMemoryOptimizer,
+    EmbeddingLookupFn,
+    create_wholememory_optimizer,
+    destroy_wholememory_optimizer,
 )
 from .graph_structure import GraphStructure
 from .initialize import init, init_torch_env, init_torch_env_and_create_wm_comm, finalize

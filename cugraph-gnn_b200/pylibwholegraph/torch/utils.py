@@ -158,3 +158,16 @@ def view_as_torch(view):
     if 0 in shape or cai["data"][0] == 0:
         return torch.empty(shape, device="cuda", dtype=wholememory_dtype_to_torch_dtype(view.wm_dtype))
     return device_memory_as_torch(cai["data"][0], shape, view.strides_elts, view.wm_dtype, owner=view.owner)
+
+
+def str_to_wmb_wholememory_optimizer_type(str_wmb_optimizer_type: str):
+    """reference: pylibwholegraph/torch/utils.py (sgd, adam = lazy adam, adagrad, rmsprop)."""
+    table = {
+        "sgd": wmb.WholeMemoryOptimizerType.OptSgd,
+        "adam": wmb.WholeMemoryOptimizerType.OptLazyAdam,
+        "adagrad": wmb.WholeMemoryOptimizerType.OptAdaGrad,
+        "rmsprop": wmb.WholeMemoryOptimizerType.OptRmsProp,
+    }
+    if str_wmb_optimizer_type not in table:
+        raise ValueError("WholeMemory optimizer type %s not supported, should be (sgd, adam, adagrad, rmsprop)" % (str_wmb_optimizer_type,))
+    return table[str_wmb_optimizer_type]

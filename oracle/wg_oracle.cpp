@@ -995,4 +995,79 @@ void wgo_hetero_copy(void* h, int32_t* majors, int32_t* minors, int32_t* edge_ty
 }
 void wgo_hetero_free(void* h) { delete (wgo_hetero_result*)h; }
 
+
+// ---- sparse optimizers of trainable embeddings ------------------------------------------------------
+// wholememory_embedding_gather_gradient_apply (cpp/src/wholememory/embedding.cpp:136-315): gradients of repeated
+// indices are summed (dedup_indice_and_gradients), then ONE optimizer step per distinct row with the element rules of
+// cpp/src/wholememory_ops/functions/embedding_optimizer_func.cu:
+//   SGD      :205-213   g += wd*w; w -= lr*g
+//   LazyAdam :389-420   b1t*=beta1; b2t*=beta2 (per row, start 1); adam_w ? w -= lr*wd*w : g += wd*w;
+//                        m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g*g; w -= lr*(m/(1-b1t))/(sqrt(v/(1-b2t))+eps)
+//   AdaGrad  :655-668   g += wd*w; s += g*g; w -= lr*g/(sqrt(s)+eps)
+//   RMSProp  :865-880   g += wd*w; v = alpha*v+(1-alpha)*g*g; w -= lr*g/(sqrt(v)+eps)
+// optimizer_type: 1 SGD, 2 LazyAdam, 3 RMSProp, 4 AdaGrad (wholememory_optimizer_type_t, embedding.h:45-58).
+// Duplicates are summed in input order, in fp32, like the device path sums them in publish order.
+int wgo_embedding_gradient_apply(int optimizer_type, float weight_decay, float epsilon, float beta1, float beta2,
+                                 int adam_w, float alpha, float lr, float* emb, int64_t dim, const int64_t* indices,
+                                 int64_t n, const float* grads, float* state_a, float* state_b, float* per_row)
+{
+  std::unordered_map<int64_t, std::vector<float>> sum;
+  std::vector<int64_t> order;
+  for (int64_t i = 0; i < n; i++) {
+    auto it = sum.find(indices[i]);
+    if (it == sum.end()) {
+      it = sum.insert(std::make_pair(indices[i], std::vector<float>(dim, 0.f))).first;
+      order.push_back(indices[i]);
+    }
+    for (int64_t d = 0; d < dim; d++)
+      it->second[d] += grads[i * dim + d];
+  }
+  for (int64_t row : order) {
+    const std::vector<float>& gs = sum[row];
+    float b1t = 1.f, b2t = 1.f;
+    if (optimizer_type == 2) {
+      b1t = per_row[row * 2] * beta1;
+      b2t = per_row[row * 2 + 1] * beta2;
+    }
+    for (int64_t d = 0; d < dim; d++) {
+      float g = gs[d];
+      float x = emb[row * dim + d];
+      int64_t e = row * dim + d;
+      if (optimizer_type == 1) {
+        g += weight_decay * x;
+        x -= lr * g;
+      } else if (optimizer_type == 2) {
+        if (adam_w) x -= lr * weight_decay * x;
+        else g = g + weight_decay * x;
+        float m = state_a[e], v = state_b[e];
+        m = beta1 * m + (1 - beta1) * g;
+        v = beta2 * v + (1 - beta2) * g * g;
+        float mhat = m / (1 - b1t);
+        float vhat = v / (1 - b2t);
+        x = x - lr * mhat / (sqrtf(vhat) + epsilon);
+        state_a[e] = m;
+        state_b[e] = v;
+      } else if (optimizer_type == 4) {
+        g = g + weight_decay * x;
+        float s2 = state_a[e] + g * g;
+        x = x - lr * g / (sqrtf(s2) + epsilon);
+        state_a[e] = s2;
+      } else if (optimizer_type == 3) {
+        g = g + weight_decay * x;
+        float v = alpha * state_a[e] + (1 - alpha) * g * g;
+        x = x - lr * g / (sqrtf(v) + epsilon);
+        state_a[e] = v;
+      } else {
+        return 1;
+      }
+      emb[e] = x;
+    }
+    if (optimizer_type == 2) {
+      per_row[row * 2]     = b1t;
+      per_row[row * 2 + 1] = b2t;
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

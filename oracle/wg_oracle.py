@@ -306,3 +306,25 @@ def hetero_multihop_sample(row_ptrs, cols, vertex_type_offsets, seeds, label_off
                           _p(out["edge_renumber_map"]), _p(out["edge_renumber_map_offsets"]), _p(out["label_type_step_base"]))
     lib().wgo_hetero_free(h)
     return out
+
+
+OPT_TYPES = {"sgd": 1, "adam": 2, "lazy_adam": 2, "rmsprop": 3, "adagrad": 4}
+
+
+def embedding_gradient_apply(optimizer, params, emb, indices, grads, lr, states):
+    """In place on `emb` (fp32 [N, dim]) and `states` (dict of fp32 arrays: adam m/v/beta12t, adagrad state_sum,
+    rmsprop v): one optimizer step per distinct index with its summed gradient."""
+    t = OPT_TYPES[optimizer]
+    assert emb.dtype == np.float32 and emb.flags.c_contiguous
+    indices = np.ascontiguousarray(indices, dtype=np.int64)
+    grads = np.ascontiguousarray(grads, dtype=np.float32)
+    a = states.get("m") if t == 2 else states.get("state_sum") if t == 4 else states.get("v") if t == 3 else None
+    b = states.get("v") if t == 2 else None
+    pr = states.get("beta12t") if t == 2 else None
+    f = ctypes.c_float
+    rc = lib().wgo_embedding_gradient_apply(
+        ctypes.c_int(t), f(params.get("weight_decay", 0.0)), f(params.get("epsilon", 1e-8)), f(params.get("beta1", 0.9)),
+        f(params.get("beta2", 0.999)), ctypes.c_int(1 if params.get("adam_w", 0.0) > 0.5 else 0), f(params.get("alpha", 0.99)),
+        f(lr), _p(emb), ctypes.c_int64(emb.shape[1]), _p(indices), ctypes.c_int64(indices.shape[0]), _p(grads), _p(a), _p(b), _p(pr))
+    assert rc == 0
+    return emb

@@ -118,6 +118,53 @@ def _sampler_worker(rank, world, uid):
     comm.barrier()
 
 
+def _optimizer_worker(rank, world, uid):
+    """Trainable embedding on two ranks: every rank contributes gradients for rows of BOTH ranks (with repeats inside
+    and across ranks); owners pull them from the peers' mailboxes.  Result = the oracle applied to the concatenation
+    of the ranks' contributions in rank order."""
+    torch = _setup(rank, world)
+    wgth, comm = _comm(uid, rank, world)
+    import wg_oracle as oracle
+
+    rows, dim = 3001, 48
+    table = np.random.default_rng(0).standard_normal((rows, dim)).astype(np.float32)
+    for opt, params in (("sgd", {"weight_decay": 0.01}), ("adam", {"weight_decay": 0.01}), ("adagrad", {}), ("rmsprop", {"alpha": 0.9})):
+        emb = wgth.create_embedding(comm, "chunked", "cuda", torch.float32, [rows, dim])
+        local, start = emb.get_embedding_tensor().get_local_tensor()
+        local.copy_(torch.from_numpy(table[start:start + local.shape[0]]).cuda())
+        torch.cuda.synchronize()
+        comm.barrier()
+        optimizer = wgth.create_wholememory_optimizer(emb, opt, params)
+        ref = table.copy()
+        states = {"adam": {"m": np.zeros_like(ref), "v": np.zeros_like(ref), "beta12t": np.ones((rows, 2), np.float32)},
+                  "adagrad": {"state_sum": np.zeros_like(ref)}, "rmsprop": {"v": np.zeros_like(ref)}, "sgd": {}}[opt]
+        for step in range(3):
+            per_rank = []
+            for r in range(world):
+                g = np.random.default_rng(100 * step + r)
+                n = 700 + 300 * r  # uneven contributions; step 2: rank 0 contributes nothing
+                if step == 2 and r == 0:
+                    n = 0
+                idx = g.integers(0, rows, n)
+                idx[: n // 3] = g.integers(0, 25, n // 3)
+                per_rank.append((idx, g.standard_normal((n, dim)).astype(np.float32)))
+            idx, grads = per_rank[rank]
+            emb.add_gradients(torch.from_numpy(idx).cuda(), torch.from_numpy(grads).cuda())
+            emb.need_apply = True
+            optimizer.step(0.03)
+            oracle.embedding_gradient_apply(opt, params, ref, np.concatenate([p[0] for p in per_rank]),
+                                            np.concatenate([p[1] for p in per_rank]), 0.03, states)
+            got = local.cpu().numpy()
+            np.testing.assert_allclose(got, ref[start:start + local.shape[0]], rtol=3e-5, atol=3e-6)
+        comm.barrier()
+        wgth.destroy_wholememory_optimizer(optimizer)
+        wgth.destroy_embedding(emb)
+
+
+def test_trainable_embedding_two_ranks():
+    _run(_optimizer_worker)
+
+
 def _run(fn, **kw):
     import pylibwholegraph.binding.wholememory_binding as wmb
     from pylibwholegraph.utils.multiprocess import multiprocess_run

@@ -422,3 +422,43 @@ def test_hetero_structure_random_typed_graph(oracle):
     for fanout in ([3, 2, 4, 2, 2, 2], [-1, 3, 0, 2, -1, 1], [5, 5, 5]):
         res = oracle.hetero_multihop_sample(row_ptrs, cols, vto, seeds, lo, fanout, 99)
         check_hetero_structure(res, vto, row_ptrs, cols, edge_types, seeds, lo, fanout)
+
+
+# ---- sparse optimizers ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("opt", ["sgd", "adam", "adagrad", "rmsprop"])
+def test_embedding_optimizers_against_numpy_restatement(oracle, opt):
+    """Independent numpy (fp32) restatement of embedding_optimizer_func.cu's element rules, with duplicate indices."""
+    f = np.float32
+    rng = np.random.default_rng(3)
+    rows, dim = 50, 8
+    w0 = rng.standard_normal((rows, dim)).astype(f)
+    idx = np.array([3, 7, 3, 3, 49, 0, 7], dtype=np.int64)
+    grads = rng.standard_normal((len(idx), dim)).astype(f)
+    p = {"weight_decay": 0.1, "epsilon": 1e-6, "beta1": 0.9, "beta2": 0.99, "alpha": 0.95}
+    lr = f(0.05)
+    states = {"adam": {"m": np.zeros((rows, dim), f), "v": np.zeros((rows, dim), f), "beta12t": np.ones((rows, 2), f)},
+              "adagrad": {"state_sum": np.zeros((rows, dim), f)}, "rmsprop": {"v": np.zeros((rows, dim), f)}, "sgd": {}}[opt]
+    got = oracle.embedding_gradient_apply(opt, p, w0.copy(), idx, grads, float(lr), states)
+    exp = w0.copy()
+    wd, eps, b1, b2, al = (f(p[k]) for k in ("weight_decay", "epsilon", "beta1", "beta2", "alpha"))
+    for row in (3, 7, 49, 0):
+        g = np.zeros(dim, f)
+        for k in np.nonzero(idx == row)[0]:
+            g = (g + grads[k]).astype(f)
+        x = exp[row]
+        g = (g + wd * x).astype(f)
+        if opt == "sgd":
+            x = x - lr * g
+        elif opt == "adam":
+            m, v = (f(1) - b1) * g, (f(1) - b2) * g * g
+            x = x - lr * (m / (f(1) - b1)) / (np.sqrt(v / (f(1) - b2)) + eps)
+            assert np.allclose(states["m"][row], m, rtol=1e-6) and np.allclose(states["beta12t"][row], [b1, b2])
+        elif opt == "adagrad":
+            x = x - lr * g / (np.sqrt(g * g) + eps)
+        else:
+            v = (f(1) - al) * g * g
+            x = x - lr * g / (np.sqrt(v) + eps)
+        exp[row] = x.astype(f)
+    np.testing.assert_allclose(got, exp, rtol=2e-6, atol=1e-7)
+    untouched = np.setdiff1d(np.arange(rows), idx)
+    assert np.array_equal(got[untouched], w0[untouched])
