@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_under_ncu.log 2>&1
 # full sections for the kernels of one step (second step of the driver script)
 ncu --set full --clock-control none --import-source on \
-    -k regex:"rows_copy|mh_insert|uniform_small|mh_compact|mh_emit|count_scan|mh_reinsert|mh_seed" -s 12 -c 13 \
+    -k regex:"rows_copy|mh_insert|uniform_small|mh_compact|mh_emit|count_scan|mh_reinsert|mh_seed" -s 12 -c 18 \
     -o $out/${tag}_full python profiles/prof_step.py 2 > $out/${tag}_full.log 2>&1
 WGB_MH_TIMING=1 python profiles/prof_step.py 15 > $out/${tag}_stage_times.txt 2>&1
 python profiles/agg_bench.py 1024 6 > $out/${tag}_agg_c3.jsonl 2> $out/${tag}_agg.err
