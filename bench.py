@@ -18,6 +18,10 @@ every mini-batch (sampler/sampler.py:51-165 -> FeatureStore -> WholeMemoryEmbedd
 Every step uses a different seed set; the feature table (5.1 GB) and the bytes gathered per step exceed L2.
 
 metric = sampled edges / s for the whole step (sampling + renumbering + feature gather), whole job over all GPUs.
+`value`: K call groups with device-resident seeds, software-pipelined the way the loader runs them (call group k+1 is
+begun on a second sampler object before k is finished; for N > 1 the NVLink-bound gather runs on its own stream so the
+next call group's sampling kernels execute underneath it).  `e2e`: the same loop with pinned-host seeds in and the
+step's result read back to the host every step.
 Extra keys: gather_gbs (reference definition: gathered output bytes / gather time,
 cpp/bench/wholememory_ops/gather_scatter_bench.cu:352-355), stages (per-stage device times), roofline
 (dominant kernel = the gather), cpu_baseline (the oracle on the host cores, bounded sample).
@@ -222,7 +226,11 @@ def run_ours(args):
         sd = host_seeds[k].to(dev, non_blocking=True)  # H2D of the step's input, from pinned memory
         return samplers[k & 1].sample_async(wm_rp, wm_col, sd, label_offsets, FANOUT, SAMPLER_SEED + 7 * k)
 
-    side = torch.cuda.Stream(device=dev) if args.gather_stream else None
+    # Feature fetch on its own stream?  On one GPU both stages are bound by the same memory system and overlapping them is
+    # slower (measured 1.19 vs 1.03 ms/step); with the table striped over several GPUs the gather waits on NVLink while
+    # HBM and the SMs idle, so the next call group's sampling kernels run underneath it (default: on for N > 1).
+    use_side = (world > 1) if args.gather_stream < 0 else bool(args.gather_stream)
+    side = torch.cuda.Stream(device=dev) if use_side else None
     n_metric = (labels * len(FANOUT) + 1) + (labels + 1) + labels * FEAT_DIM
     host_ring = [torch.empty(n_metric, dtype=torch.float64, pin_memory=True) for _ in range(4)]
     ring_pos = [0]
@@ -312,21 +320,49 @@ def run_ours(args):
     if rank == 0:
         clocks.start()
     launches0 = int(launch_count())
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    # (a) the timed region of `value`: K call groups, device-resident seeds, software-pipelined like the loader (call group
+    #     k+1 is begun before k is finished); gather events are recorded on the stream the gather is launched on
+    gev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def begin_dev(k):
+        return samplers[k & 1].sample_async(wm_rp, wm_col, dev_seeds[k], label_offsets, FANOUT, SAMPLER_SEED + 7 * k)
+
     torch.cuda.synchronize()
     t_begin.record()
     tot_edges = tot_nodes = 0
-    for k in range(args.steps):
-        e, n, x, _ = step(dev_seeds[args.warmup + k], SAMPLER_SEED + 7 * (args.warmup + k), evs[k])
-        tot_edges += e
-        tot_nodes += n
+    alive = []
+    pend = begin_dev(args.warmup)
+    for i in range(args.steps):
+        nxt = begin_dev(args.warmup + i + 1) if i + 1 < args.steps else None
+        res = pend.result()
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            gev[i][0].record()
+            x = emb.gather(res["renumber_map"])
+            gev[i][1].record()
+        alive.append((res, x))  # outputs live until the stream that reads them has passed (3 call groups in flight at most)
+        if len(alive) > 3:
+            alive.pop(0)
+        tot_edges += int(res["minors"].numel())
+        tot_nodes += int(res["renumber_map"].numel())
+        pend = nxt
+    if side is not None:
+        torch.cuda.current_stream().wait_stream(side)
     t_end.record()
     torch.cuda.synchronize()
+    del alive
     launches = int(launch_count()) - launches0
     ms_total = t_begin.elapsed_time(t_end)
+    gather_ms = sum(ev[0].elapsed_time(ev[1]) for ev in gev)
+    # (b) per-stage times, one synchronous pass over the same call groups (not part of `value`)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    for k in range(args.steps):
+        step(dev_seeds[args.warmup + k], SAMPLER_SEED + 7 * (args.warmup + k), evs[k])
+    torch.cuda.synchronize()
     sample_ms = sum(ev[0].elapsed_time(ev[1]) for ev in evs)
-    gather_ms = sum(ev[1].elapsed_time(ev[2]) for ev in evs)
+    gather_alone_ms = sum(ev[1].elapsed_time(ev[2]) for ev in evs)
 
     # ---- end-to-end: pinned host seeds in, per-batch sizes + feature checksum out, every step -----------
     if world > 1:
@@ -347,12 +383,12 @@ def run_ours(args):
             rank, e2e_ms, args.steps, ms_total, sample_ms, gather_ms, " ".join("%.2f" % ev[1].elapsed_time(ev[2]) for ev in evs)))
     clock_info = clocks.stop() if rank == 0 else None
 
-    stats = torch.tensor([ms_total, e2e_ms, sample_ms, gather_ms], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_total, e2e_ms, sample_ms, gather_ms, gather_alone_ms], dtype=torch.float64, device=dev)
     counts = torch.tensor([tot_edges, tot_nodes, e2e_edges], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, sample_ms, gather_ms = stats.tolist()
+    ms_total, e2e_ms, sample_ms, gather_ms, gather_alone_ms = stats.tolist()
     tot_edges, tot_nodes, e2e_edges = counts.tolist()
 
     if rank == 0:
@@ -393,11 +429,14 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "labels_per_step_per_gpu": labels, "seeds_per_label": BATCH,
                        "l2": "inputs larger than L2 (5.1 GB table, >1 GB gathered per step); new seed set every step",
-                       "graph": "replicated per GPU", "features": "chunked over %d GPU(s), in-kernel P2P gather" % world},
+                       "graph": "replicated per GPU", "features": "chunked over %d GPU(s), in-kernel P2P gather" % world,
+                       "pipeline": "call group k+1 begun before k is finished; gather on %s" % ("its own stream" if use_side else "the same stream")},
             "gather_gbs": row_bytes * tot_nodes / (gather_ms * 1e-3) / 1e9,
             "stages": {
                 "sample_renumber_ms_per_step": sample_ms / args.steps,
                 "gather_ms_per_step": gather_ms / args.steps,
+                "gather_alone_ms_per_step": gather_alone_ms / args.steps,
+                "note": "gather_ms: inside the timed (pipelined) region; sample_renumber_ms and gather_alone_ms: separate synchronous pass",
                 "edges_per_step_per_gpu": tot_edges / args.steps / world,
                 "nodes_gathered_per_step_per_gpu": tot_nodes / args.steps / world,
                 "sample_stage_edges_per_sec_per_gpu": tot_edges / world / (sample_ms * 1e-3),
@@ -499,7 +538,7 @@ def main():
     ap.add_argument("--labels", type=int, default=LABELS_PER_STEP)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather-stream", type=int, default=0, help="e2e: run the feature gather on a second stream (1) or in line (0)")
+    ap.add_argument("--gather-stream", type=int, default=-1, help="run the feature gather on a second stream (1), in line (0), or 1 iff N > 1 (-1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
