@@ -195,6 +195,15 @@ def run_ours(args):
         hi = min(local.shape[0], lo + (1 << 20))
         local[lo:hi] = ((torch.arange(start + lo, start + hi, device=dev)[:, None] + ar) & 0xFFFF).float()
     comm.barrier()
+    hot_rows = 0
+    if world > 1 and args.hot_ratio > 0:
+        # replicate the hottest rows on every GPU (role of the reference's device cache for remote tables, static here):
+        # hotness of a vertex = how often it appears as a CSR column = how often the sampler can reach it
+        hot_rows = int(args.hot_ratio * NUM_NODES)
+        hotness = torch.bincount(wm_col.get_local_tensor()[0].long(), minlength=NUM_NODES)
+        emb.set_hot_rows(torch.topk(hotness, hot_rows).indices)
+        del hotness
+        comm.barrier()
     sampler = wgth.MultiHopSampler()
     labels = args.labels
     label_offsets = (torch.arange(labels + 1, dtype=torch.int64) * BATCH).to(dev)
@@ -306,7 +315,9 @@ def run_ours(args):
     # loop -- one being built, two whose results the host has not read yet).
     prime = []
     for _ in range(4):
-        prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
+        # the feature block is allocated on the stream that runs the gather: torch keeps one pool per stream
+        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+            prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
         prime.append(torch.empty(int(n_max * 1.25), dtype=torch.int64, device=dev))
         prime += [torch.empty(int(e_max * 1.25), dtype=torch.int32, device=dev) for _ in range(2)]
         prime.append(torch.empty(int(e_max * 1.25), dtype=torch.int64, device=dev))
@@ -380,7 +391,7 @@ def run_ours(args):
             rank, " ".join("%.2f|%.2f|%.2f" % (ev4[4 * i].elapsed_time(ev4[4 * i + 1]), ev4[4 * i + 1].elapsed_time(ev4[4 * i + 2]),
                                                ev4[4 * i + 2].elapsed_time(ev4[4 * i + 3])) for i in range(args.steps))))
         log("[rank %d] e2e %.3f ms for %d steps; value loop %.3f ms (sample %.3f, gather %.3f); per step gather: %s" % (
-            rank, e2e_ms, args.steps, ms_total, sample_ms, gather_ms, " ".join("%.2f" % ev[1].elapsed_time(ev[2]) for ev in evs)))
+            rank, e2e_ms, args.steps, ms_total, sample_ms, gather_ms, " ".join("%.2f" % ev[0].elapsed_time(ev[1]) for ev in gev)))
     clock_info = clocks.stop() if rank == 0 else None
 
     stats = torch.tensor([ms_total, e2e_ms, sample_ms, gather_ms, gather_alone_ms], dtype=torch.float64, device=dev)
@@ -430,6 +441,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "labels_per_step_per_gpu": labels, "seeds_per_label": BATCH,
                        "l2": "inputs larger than L2 (5.1 GB table, >1 GB gathered per step); new seed set every step",
                        "graph": "replicated per GPU", "features": "chunked over %d GPU(s), in-kernel P2P gather" % world,
+                       "hot_rows_replicated_per_gpu": hot_rows, "hot_rows_bytes_per_gpu": hot_rows * FEAT_DIM * 4 + (4 * NUM_NODES if hot_rows else 0),
                        "pipeline": "call group k+1 begun before k is finished; gather on %s" % ("its own stream" if use_side else "the same stream")},
             "gather_gbs": row_bytes * tot_nodes / (gather_ms * 1e-3) / 1e9,
             "stages": {
@@ -538,6 +550,8 @@ def main():
     ap.add_argument("--labels", type=int, default=LABELS_PER_STEP)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hot-ratio", type=float, default=0.1,
+                    help="N > 1: fraction of the feature rows (the highest-degree vertices) replicated on every GPU; 0 = none")
     ap.add_argument("--gather-stream", type=int, default=-1, help="run the feature gather on a second stream (1), in line (0), or 1 iff N > 1 (-1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

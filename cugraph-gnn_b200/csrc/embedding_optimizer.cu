@@ -320,6 +320,7 @@ static void launch_apply(bool chunked, int grid, cudaStream_t st, const long lon
 static void gradient_apply(wholememory_embedding_t e, wholememory_tensor_t indices, wholememory_tensor_t grads, float lr, cudaStream_t st)
 {
   WGB_EXPECTS(e->optimizer != nullptr && e->optimizer->type != WHOLEMEMORY_OPT_NONE, "the embedding has no optimizer");
+  embedding_drop_hot_rows(e);  // a replica of rows that are about to change would go stale
   auto* ed = wholememory_tensor_get_tensor_description(e->tensor);
   auto* id = wholememory_tensor_get_tensor_description(indices);
   auto* gd = wholememory_tensor_get_tensor_description(grads);

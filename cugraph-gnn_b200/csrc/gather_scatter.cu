@@ -81,7 +81,10 @@ constexpr int kUnroll = 4;
 
 // ---- same-dtype path: pure byte movement ---------------------------------------------------------
 // SCATTER=false: dense[i, :] = table[idx[i], :]      SCATTER=true: table[idx[i], :] = dense[i, :]
-template <typename IdxT, int VEC, bool CHUNKED, bool SCATTER>
+// HOT: rows replicated on this GPU (wgb_hot_rows) are read from the replica instead of the owning rank -- on a power-law
+// graph the hottest 10 % of the rows are 84 % of what a call group gathers (profiles/hot_rows_probe.py), which takes
+// that share of the traffic off NVLink.
+template <typename IdxT, int VEC, bool CHUNKED, bool SCATTER, bool HOT = false>
 __global__ void __launch_bounds__(kBlock) rows_copy_kernel(ChunkRef table,
                                                            unsigned long long table_off_bytes,
                                                            unsigned long long row_stride_bytes,
@@ -89,7 +92,8 @@ __global__ void __launch_bounds__(kBlock) rows_copy_kernel(ChunkRef table,
                                                            unsigned int total_vecs,
                                                            RowDiv vpr,
                                                            char* __restrict__ dense,
-                                                           unsigned long long dense_stride_bytes)
+                                                           unsigned long long dense_stride_bytes,
+                                                           wgb_hot_rows hot = wgb_hot_rows())
 {
   using V                   = typename vec_of<VEC>::type;
   const unsigned int window = kBlock * kUnroll;
@@ -107,7 +111,10 @@ __global__ void __launch_bounds__(kBlock) rows_copy_kernel(ChunkRef table,
       long long r      = ok[u] ? (long long)idx[row] : -1;
       ok[u]            = ok[u] && r >= 0;
       unsigned long long off = table_off_bytes + (unsigned long long)(r < 0 ? 0 : r) * row_stride_bytes;
-      tptr[u] = table.at<CHUNKED>(off) + (unsigned long long)c * VEC;
+      int hs                 = -1;
+      if (HOT && ok[u]) hs = __ldg(hot.slot + r);
+      tptr[u] = (HOT && hs >= 0) ? const_cast<char*>(hot.rows) + (unsigned long long)hs * hot.stride_bytes + (unsigned long long)c * VEC
+                                 : table.at<CHUNKED>(off) + (unsigned long long)c * VEC;
       dptr[u] = dense + (unsigned long long)row * dense_stride_bytes + (unsigned long long)c * VEC;
     }
 #pragma unroll
@@ -191,6 +198,7 @@ struct RowsOpArgs {
   int64_t n;
   void* dense;  // already offset-free base pointer
   wholememory_matrix_description_t dense_desc;
+  wgb_hot_rows hot;  // slot == nullptr: none
   bool scatter;
   int sms;
   cudaStream_t stream;
@@ -230,7 +238,10 @@ static void launch_copy(const RowsOpArgs& a, int64_t row0, int64_t rows, unsigne
   unsigned long long toff       = (unsigned long long)a.table_desc.storage_offset * elt;
   unsigned long long tstride    = (unsigned long long)a.table_desc.stride * elt;
   int grid                      = grid_for(total, kBlock * kUnroll, a.sms);
-  if (a.table.world > 1)
+  if (!SCATTER && a.hot.slot != nullptr && a.table.world > 1 && a.hot.stride_bytes % VEC == 0 &&
+      reinterpret_cast<unsigned long long>(a.hot.rows) % VEC == 0)
+    rows_copy_kernel<IdxT, VEC, true, false, true><<<grid, kBlock, 0, a.stream>>>(a.table, toff, tstride, idx, (unsigned int)total, rd, dense, dstride, a.hot);
+  else if (a.table.world > 1)
     rows_copy_kernel<IdxT, VEC, true, SCATTER><<<grid, kBlock, 0, a.stream>>>(a.table, toff, tstride, idx, (unsigned int)total, rd, dense, dstride);
   else
     rows_copy_kernel<IdxT, VEC, false, SCATTER><<<grid, kBlock, 0, a.stream>>>(a.table, toff, tstride, idx, (unsigned int)total, rd, dense, dstride);
@@ -350,8 +361,8 @@ static void run_rows_op_typed(const RowsOpArgs& a)
 
 // Validation shared by gather and scatter; mirrors cpp/src/wholememory_ops/gather_op.cpp:12-70 and
 // functions/gather_func.cu:53-66 (same error codes for the same mistakes).
-static wholememory_error_code_t rows_op(wholememory_tensor_t wm_tensor, wholememory_tensor_t indices_tensor,
-                                        wholememory_tensor_t dense_tensor, void* stream, int sms, bool scatter)
+wholememory_error_code_t rows_op(wholememory_tensor_t wm_tensor, wholememory_tensor_t indices_tensor,
+                                 wholememory_tensor_t dense_tensor, void* stream, int sms, bool scatter, const wgb_hot_rows* hot)
 {
   if (!wm_tensor || !indices_tensor || !dense_tensor) return WHOLEMEMORY_INVALID_INPUT;
   wholememory_tensor_description_t td = *wholememory_tensor_get_tensor_description(wm_tensor);
@@ -403,6 +414,7 @@ static wholememory_error_code_t rows_op(wholememory_tensor_t wm_tensor, wholemem
     a.dense      = dense_root->storage_ptr;
     a.dense_desc = dense_desc;
     a.scatter    = scatter;
+    if (hot && !scatter) a.hot = *hot;
     a.sms        = sms;
     a.stream     = as_stream(stream);
     if (idx_desc.dtype == WHOLEMEMORY_DT_INT) {
@@ -424,14 +436,14 @@ wholememory_error_code_t wholememory_gather(wholememory_tensor_t wholememory_ten
                                             wholememory_tensor_t output_tensor,
                                             wholememory_env_func_t* /*p_env_fns*/, void* stream, int gather_sms)
 {
-  return wgb::rows_op(wholememory_tensor, indices_tensor, output_tensor, stream, gather_sms, false);
+  return wgb::rows_op(wholememory_tensor, indices_tensor, output_tensor, stream, gather_sms, false, nullptr);
 }
 
 wholememory_error_code_t wholememory_scatter(wholememory_tensor_t input_tensor, wholememory_tensor_t indices_tensor,
                                              wholememory_tensor_t wholememory_tensor,
                                              wholememory_env_func_t* /*p_env_fns*/, void* stream, int scatter_sms)
 {
-  return wgb::rows_op(wholememory_tensor, indices_tensor, input_tensor, stream, scatter_sms, true);
+  return wgb::rows_op(wholememory_tensor, indices_tensor, input_tensor, stream, scatter_sms, true, nullptr);
 }
 
 }  // extern "C"

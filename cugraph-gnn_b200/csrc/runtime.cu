@@ -14,6 +14,8 @@
 
 #include "wm_common.cuh"
 
+#include <wholememory/b200_ops.h>
+
 #include <cuda.h>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -1304,6 +1306,7 @@ wholememory_error_code_t wholememory_destroy_embedding(wholememory_embedding_t e
 {
   if (!e) return WHOLEMEMORY_INVALID_INPUT;
   wgb::embedding_release_training_state(e);  // optimizer states, inbox, scratch (collective, like the table itself)
+  wgb::embedding_drop_hot_rows(e);
   auto err = wholememory_destroy_tensor(e->tensor);
   delete e;
   return err;
@@ -1316,7 +1319,78 @@ wholememory_error_code_t wholememory_embedding_gather(wholememory_embedding_t e,
                                                       wholememory_env_func_t* p_env_fns, int64_t stream_int)
 {
   if (!e) return WHOLEMEMORY_INVALID_INPUT;
-  return wholememory_gather(e->tensor, indices, output, p_env_fns, reinterpret_cast<void*>(stream_int), e->user_sms);
+  return wgb::rows_op(e->tensor, indices, output, reinterpret_cast<void*>(stream_int), e->user_sms, false,
+                      e->hot.slot ? &e->hot : nullptr);
 }
+
+}  // extern "C"
+
+// ---- replicated hot rows (b200_ops.h) --------------------------------------------------------------------------------
+namespace wgb {
+__global__ void hot_slot_kernel(const long long* __restrict__ idx, long long n, long long rows, int* __restrict__ slot)
+{
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    long long r = idx[i];
+    if (r >= 0 && r < rows) slot[r] = (int)i;  // duplicates: any of the copies is as good as another
+  }
+}
+
+void embedding_drop_hot_rows(wholememory_embedding_t e)
+{
+  if (e->hot_slot_mem) cudaFree(e->hot_slot_mem);
+  if (e->hot_rows_mem) cudaFree(e->hot_rows_mem);
+  e->hot_slot_mem = e->hot_rows_mem = nullptr;
+  e->hot                            = wgb_hot_rows();
+  e->hot_count                      = 0;
+  cudaGetLastError();
+}
+}  // namespace wgb
+
+extern "C" {
+
+wholememory_error_code_t wholememory_embedding_set_hot_rows(wholememory_embedding_t e, wholememory_tensor_t hot_indices, void* stream)
+{
+  using namespace wgb;
+  if (!e) return WHOLEMEMORY_INVALID_INPUT;
+  return guarded("wholememory_embedding_set_hot_rows", [&] {
+    cudaStream_t st = as_stream(stream);
+    WGB_CUDA_TRY(cudaStreamSynchronize(st));
+    embedding_drop_hot_rows(e);
+    if (!hot_indices) return;
+    auto* id = wholememory_tensor_get_tensor_description(hot_indices);
+    WGB_CHECK_INPUT(id->dim == 1 && id->dtype == WHOLEMEMORY_DT_INT64, "hot_indices must be a 1-D int64 device tensor");
+    const long long n = id->sizes[0];
+    if (n == 0) return;
+    WGB_CHECK_INPUT(n < (1LL << 31), "too many hot rows");
+    auto* td = wholememory_tensor_get_tensor_description(e->tensor);
+    const long long rows = td->sizes[0];
+    const size_t row_bytes = (size_t)td->sizes[1] * wholememory_dtype_get_element_size(td->dtype);
+    const size_t stride    = (row_bytes + 15) / 16 * 16;
+    WGB_CUDA_TRY(cudaMalloc(&e->hot_slot_mem, sizeof(int) * (size_t)rows));
+    WGB_CUDA_TRY(cudaMalloc(&e->hot_rows_mem, stride * (size_t)n));
+    WGB_CUDA_TRY(cudaMemsetAsync(e->hot_slot_mem, 0xFF, sizeof(int) * (size_t)rows, st));
+    const long long* idx = static_cast<const long long*>(wholememory_tensor_get_data_pointer(hot_indices)) + id->storage_offset;
+    hot_slot_kernel<<<(int)std::min<long long>((n + 255) / 256, 1184), 256, 0, st>>>(idx, n, rows, static_cast<int*>(e->hot_slot_mem));
+    WGB_CHECK_LAUNCH();
+    // fill the replica with a plain gather (peer rows arrive over NVLink once)
+    wholememory_tensor_description_t od = *td;
+    od.sizes[0]       = n;
+    od.strides[0]     = (int64_t)(stride / wholememory_dtype_get_element_size(td->dtype));
+    od.strides[1]     = 1;
+    od.storage_offset = 0;
+    wholememory_tensor_t out = nullptr;
+    WGB_EXPECTS(wholememory_make_tensor_from_pointer(&out, e->hot_rows_mem, &od) == WHOLEMEMORY_SUCCESS, "wrap replica");
+    auto err = rows_op(e->tensor, hot_indices, out, st, e->user_sms, false, nullptr);
+    wholememory_destroy_tensor(out);
+    WGB_EXPECTS(err == WHOLEMEMORY_SUCCESS, "could not fill the hot-row replica");
+    WGB_CUDA_TRY(cudaStreamSynchronize(st));
+    e->hot.slot         = static_cast<const int*>(e->hot_slot_mem);
+    e->hot.rows         = static_cast<const char*>(e->hot_rows_mem);
+    e->hot.stride_bytes = stride;
+    e->hot_count        = n;
+  });
+}
+
+long long wholememory_embedding_hot_row_count(wholememory_embedding_t e) { return e ? e->hot_count : 0; }
 
 }  // extern "C"

@@ -164,10 +164,22 @@ struct wholememory_tensor_ {
   bool is_wholememory         = false;
 };
 
+// Replica of the hottest rows of a read-only table on THIS GPU (wholememory_embedding_set_hot_rows, b200_ops.h):
+// slot[row] = index into `rows`, or -1.  Gathers consult it before going to the owning rank.
+struct wgb_hot_rows {
+  const int* slot                = nullptr;
+  const char* rows               = nullptr;
+  unsigned long long stride_bytes = 0;
+};
+
 struct wholememory_embedding_optimizer_;
 struct wholememory_embedding_ {
   wholememory_tensor_t tensor = nullptr;
   int user_sms                = -1;
+  wgb_hot_rows hot;            // valid iff hot.slot != nullptr
+  void* hot_slot_mem = nullptr;
+  void* hot_rows_mem = nullptr;
+  long long hot_count = 0;
   // trainable embeddings (embedding_optimizer.cu)
   wholememory_embedding_optimizer_* optimizer = nullptr;
   std::vector<std::pair<std::string, wholememory_tensor_t>> states;  // per-row optimizer states, partitioned like the table
@@ -184,6 +196,10 @@ ChunkRef make_chunk_ref(wholememory_tensor_t t);
 void comm_barrier(wholememory_comm_t c);
 void comm_allgather(wholememory_comm_t c, const void* in, void* out, size_t bytes);  // bytes <= 256 per rank
 void embedding_release_training_state(wholememory_embedding_t e);
+void embedding_drop_hot_rows(wholememory_embedding_t e);
+// gather / scatter of rows; `hot` (may be null) is consulted by same-dtype gathers only
+wholememory_error_code_t rows_op(wholememory_tensor_t wm_tensor, wholememory_tensor_t indices_tensor, wholememory_tensor_t dense_tensor,
+                                 void* stream, int sms, bool scatter, const wgb_hot_rows* hot);
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 int num_sms();
 

@@ -250,6 +250,8 @@ _c_create_emb = _sig("wholememory_create_embedding", _i, ctypes.POINTER(_vp), ct
 _c_destroy_emb = _sig("wholememory_destroy_embedding", _i, _vp)
 _c_emb_tensor = _sig("wholememory_embedding_get_embedding_tensor", _vp, _vp)
 _c_emb_gather = _sig("wholememory_embedding_gather", _i, _vp, _vp, _vp, ctypes.c_bool, _vp, ctypes.c_int64)
+_c_emb_set_hot = _sig("wholememory_embedding_set_hot_rows", _i, _vp, _vp, _vp)
+_c_emb_hot_count = _sig("wholememory_embedding_hot_row_count", ctypes.c_longlong, _vp)
 _c_opt_create = _sig("wholememory_create_embedding_optimizer", _i, ctypes.POINTER(_vp), _i)
 _c_opt_set = _sig("wholememory_optimizer_set_parameter", _i, _vp, ctypes.c_char_p, _vp)
 _c_opt_destroy = _sig("wholememory_destroy_embedding_optimizer", None, _vp)
@@ -767,6 +769,13 @@ class PyWholeMemoryEmbedding:
         if self._h:
             check_wholememory_error_code(_c_destroy_emb(self._h))
             self._h = None
+
+    def set_hot_rows(self, hot_indices, stream_int=0):
+        """hot_indices: wrapped int64 device tensor (or None to drop the replica); see include/wholememory/b200_ops.h."""
+        check_wholememory_error_code(_c_emb_set_hot(self._h, None if hot_indices is None else _h(hot_indices), _vp(stream_int or 0)))
+
+    def hot_row_count(self) -> int:
+        return int(_c_emb_hot_count(self._h))
 
     def get_optimizer_state_names(self):
         names, arr, i = [], _c_emb_state_names(self._h), 0

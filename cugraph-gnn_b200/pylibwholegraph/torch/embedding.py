@@ -131,6 +131,20 @@ class WholeMemoryEmbedding(object):
         )
         return out
 
+    def set_hot_rows(self, hot_indices: Union["torch.Tensor", None]):
+        """Replicate the given rows (int64 CUDA tensor; None drops the replica) on THIS GPU: later gathers serve them
+        locally instead of over NVLink, with identical results.  Typical choice: the vertices of highest degree
+        (`torch.bincount(col).topk(k).indices`).  Costs len(hot_indices) * row bytes + 4 bytes per table row of HBM;
+        rank-local; a snapshot of the rows (call again after changing the table)."""
+        if hot_indices is None:
+            self.wmb_embedding.set_hot_rows(None, get_stream())
+            return
+        hot_indices = hot_indices.to(device="cuda:%d" % torch.cuda.current_device(), dtype=torch.int64).contiguous()
+        self.wmb_embedding.set_hot_rows(wrap_torch_tensor(hot_indices), get_stream())
+
+    def hot_row_count(self) -> int:
+        return self.wmb_embedding.hot_row_count()
+
     def add_gradients(self, indice: "torch.Tensor", grad_outputs: "torch.Tensor"):
         self.sparse_indices.append(indice)
         self.sparse_grads.append(grad_outputs)

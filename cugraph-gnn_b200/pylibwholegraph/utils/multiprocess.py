@@ -26,6 +26,17 @@ def multiprocess_run(world_size: int, func, inline_single_process=False):
     for p in procs:
         p.start()
     errors = []
+    # a rank that dies leaves its peers waiting in a barrier: stop them as soon as one has failed
+    import time
+
+    while any(p.is_alive() for p in procs):
+        if any((not p.is_alive()) and p.exitcode not in (0, None) for p in procs):
+            time.sleep(1.0)
+            for p in procs:
+                if p.is_alive():
+                    p.terminate()
+            break
+        time.sleep(0.05)
     for p in procs:
         p.join()
     while not q.empty():

@@ -6,6 +6,7 @@
  */
 #pragma once
 
+#include <wholememory/embedding.h>
 #include <wholememory/env_func_ptrs.h>
 #include <wholememory/wholememory.h>
 #include <wholememory/wholememory_tensor.h>
@@ -175,6 +176,22 @@ wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_finish(whole
                                                                            void* out_label_type_step_base_ctx,
                                                                            wholememory_env_func_t* p_env_fns,
                                                                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Replicated hot rows: a read-only copy of the given rows of a WholeMemory embedding on THIS GPU.
+ * wholememory_embedding_gather then serves those rows locally instead of from the owning rank (same bytes out, bit
+ * for bit).  Role of the reference's device cache for remote tables (wholememory_create_embedding_cache_policy,
+ * /root/reference/cpp/include/wholememory/embedding.h:82-111), made static: the caller names the rows (e.g. the
+ * vertices of highest degree; on RMAT the hottest 10 % of the rows are 84 % of what a call group gathers) and pays
+ * hot_rows * row_bytes + 4 bytes per table row of HBM on every GPU that calls it.
+ *   hot_indices  int64 [H] local device tensor, or NULL to drop the replica.  Rank-local (not collective), synchronises
+ *   `stream`.  The replica is a snapshot: call again after the table has been modified (scatter / file load);
+ *   gradient apply drops it.
+ */
+wholememory_error_code_t wholememory_embedding_set_hot_rows(wholememory_embedding_t wholememory_embedding,
+                                                            wholememory_tensor_t hot_indices,
+                                                            void* stream);
+long long wholememory_embedding_hot_row_count(wholememory_embedding_t wholememory_embedding);
 
 /* ---------------------------------------------------------------------------------------------
  * A1: CSR neighbourhood aggregation of the sampled block (the SpMM that consumes the sampler output).

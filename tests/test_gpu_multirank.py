@@ -118,6 +118,53 @@ def _sampler_worker(rank, world, uid):
     comm.barrier()
 
 
+def _hot_rows_worker(rank, world, uid):
+    """Replicated hot rows: gathers return exactly the table's rows whether a row is served by the replica, the local
+    chunk or a peer; the replica is a snapshot until it is rebuilt."""
+    torch = _setup(rank, world)
+    wgth, comm = _comm(uid, rank, world)
+    rows, dim = 20011, 96
+    emb = wgth.create_embedding(comm, "chunked", "cuda", torch.float32, [rows, dim])
+    local, start = emb.get_embedding_tensor().get_local_tensor()
+    ids = torch.arange(start, start + local.shape[0], device="cuda")
+    local.copy_(((ids[:, None] * 5 + torch.arange(dim, device="cuda")[None, :]) % 8191).float())
+    torch.cuda.synchronize()
+    comm.barrier()
+    g = torch.Generator().manual_seed(3 + rank)
+    idx = torch.randint(0, rows, (30000,), generator=g)
+    idx[::13] = -1
+    exp = ((idx[:, None] * 5 + torch.arange(dim)[None, :]) % 8191).float()
+    keep = idx >= 0
+    plain = emb.gather(idx.cuda()).cpu()
+    hot = torch.randperm(rows, generator=torch.Generator().manual_seed(99))[:4000]  # rows of both ranks, same set on both
+    emb.set_hot_rows(hot.cuda())
+    assert emb.hot_row_count() == 4000
+    got = emb.gather(idx.cuda()).cpu()
+    assert torch.equal(got[keep], exp[keep]) and torch.equal(got[keep], plain[keep])
+    got32 = emb.gather(idx.int().cuda()).cpu()  # int32 indices
+    assert torch.equal(got32[keep], exp[keep])
+    got16 = emb.gather(idx.cuda(), force_dtype=torch.float16).cpu()  # converting path ignores the replica, same values
+    assert torch.equal(got16[keep], exp[keep].half())
+    comm.barrier()
+    # snapshot semantics: a row changed after set_hot_rows is still served from the replica until it is rebuilt
+    if rank == 0:
+        emb.get_embedding_tensor().scatter(torch.full((1, dim), -7.0).cuda(), hot[:1].cuda())
+        torch.cuda.synchronize()
+    comm.barrier()
+    one = emb.gather(hot[:1].cuda()).cpu()
+    assert torch.equal(one, ((hot[:1, None] * 5 + torch.arange(dim)[None, :]) % 8191).float())
+    emb.set_hot_rows(hot.cuda())
+    assert float(emb.gather(hot[:1].cuda())[0, 0]) == -7.0
+    emb.set_hot_rows(None)
+    assert emb.hot_row_count() == 0 and float(emb.gather(hot[:1].cuda())[0, 0]) == -7.0
+    comm.barrier()
+    wgth.destroy_embedding(emb)
+
+
+def test_hot_row_replica_two_ranks():
+    _run(_hot_rows_worker)
+
+
 def _optimizer_worker(rank, world, uid):
     """Trainable embedding on two ranks: every rank contributes gradients for rows of BOTH ranks (with repeats inside
     and across ranks); owners pull them from the peers' mailboxes.  Result = the oracle applied to the concatenation
