@@ -84,6 +84,35 @@ class FeatureStore(FeatureStoreBase):
             tx.get_comm().barrier()
         return tx
 
+    def replicate_hot_rows(self, graph_store, ratio: float = 0.1) -> Dict[Tuple, int]:
+        """B200 extension: on every GPU, keep a local copy of the `ratio` most frequently reachable rows of each 2-D node
+        feature (those of the vertices that are the PyG *source* of the most edges, i.e. the ones neighbour sampling
+        returns most often), so that most feature reads stop crossing NVLink (role of the reference's device cache of a
+        remote table; here the set is static).  Collective when the stores are multi-GPU (degree counts are summed over
+        the ranks).  Call after the features and edges have been put; returns {(group, attr): rows replicated}."""
+        world, _ = _world()
+        counts: Dict[str, torch.Tensor] = {}
+        nv = graph_store._num_vertices()
+        for attr in graph_store.get_all_edge_attrs():
+            src_type = attr.edge_type[0]
+            row, _ = graph_store.get_edge_index(attr.edge_type, "coo")
+            c = torch.bincount(row.cuda().long(), minlength=nv[src_type])
+            counts[src_type] = counts[src_type] + c if src_type in counts else c
+        done = {}
+        for (group, name), tx in self.__features.items():
+            if isinstance(group, tuple) or not isinstance(tx, DistEmbedding) or group not in counts:
+                continue
+            c = counts[group]
+            if world > 1:
+                c = c.clone()
+                torch.distributed.all_reduce(c)
+            k = min(int(ratio * tx.shape[0]), int((c > 0).sum()))
+            if k <= 0:
+                continue
+            tx.set_hot_rows(torch.topk(c, k).indices)
+            done[(group, name)] = k
+        return done
+
     def _put_tensor(self, tensor, attr: TensorAttr) -> bool:
         key = (attr.group_name, attr.attr_name)
         if attr.is_set("index") and attr.index is not None:

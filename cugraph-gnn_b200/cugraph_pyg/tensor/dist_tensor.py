@@ -133,6 +133,12 @@ class DistEmbedding(DistTensor):
         # (sampler.py:632 -> dist_tensor.py:513)
         return self._embedding.gather(idx if idx.is_cuda else idx.cuda())
 
+    def set_hot_rows(self, hot_indices: Optional[torch.Tensor]):
+        """Replicate the given rows on this GPU (WholeMemoryEmbedding.set_hot_rows): reads of those rows stop crossing
+        NVLink.  Rank-local; a snapshot of the rows -- call again after writing to the table.  None drops the replica."""
+        assert self._tensor is not None, "Please create WholeGraph embedding first."
+        self._embedding.set_hot_rows(hot_indices)
+
     @property
     def name(self):
         return self._name

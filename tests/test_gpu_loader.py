@@ -370,3 +370,19 @@ def test_neighbor_loader_hetero_linkpred(pyg):
     assert list(out["author", "writes", "paper"].edge_label_index.shape) == [2, 5]
     assert out["author", "writes", "paper"].edge_label_index.tolist()[0] == [0, 1, 2, 3, 3]
     assert out["author", "writes", "paper"].edge_label_index.tolist()[1] == [0, 1, 2, 3, 4]
+
+
+def test_feature_store_replicate_hot_rows_keeps_results(pyg):
+    """The hot-row replica (B200 extension) never changes what a loader returns."""
+    torch, GraphStore, FeatureStore, NeighborLoader = pyg
+    ei = _karate_edge_index(torch)
+    graph_store = GraphStore()
+    graph_store.put_edge_index(ei, ("person", "knows", "person"), "coo", False, (34, 34))
+    feature_store = FeatureStore()
+    feat = torch.arange(34 * 8).reshape(34, 8).float()
+    feature_store["person", "feat", None] = feat
+    done = feature_store.replicate_hot_rows(graph_store, ratio=0.25)
+    assert done == {("person", "feat"): 8}
+    assert torch.equal(feature_store["person", "feat", None][torch.arange(34).cuda()].cpu(), feat)
+    for batch in NeighborLoader((feature_store, graph_store), [5, 5], input_nodes=torch.arange(34)):
+        assert torch.equal(batch.feat.cpu(), feat[batch.n_id.cpu()])
