@@ -34,3 +34,29 @@ from .tensor import (
 from . import wholememory_ops, wholegraph_ops, graph_ops
 from .multihop import MultiHopSampler, multihop_neighbor_sample
 from .aggregate import csr_aggregate, csr_aggregate_forward, SAGEConv
+
+from .common_options import (
+    add_training_options,
+    add_common_graph_options,
+    add_common_model_options,
+    add_common_sampler_options,
+    add_node_classfication_options,
+    add_dataloader_options,
+    parse_max_neighbors,
+)
+from .data_loader import (
+    NodeClassificationDataset,
+    create_node_classification_datasets,
+    get_train_dataloader,
+    get_valid_test_dataloader,
+)
+from .distributed_launch import (
+    add_distributed_launch_options,
+    distributed_launch,
+    get_rank,
+    get_world_size,
+    get_local_rank,
+    get_local_size,
+)
+from .gnn_model import set_framework, create_gnn_layers, create_sub_graph, HomoGNNModel
+from .utils import get_part_file_name, get_part_file_list

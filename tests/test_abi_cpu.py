@@ -144,3 +144,23 @@ def _comm_worker(rank, world, uid):
     for _ in range(50):
         comm.barrier()
     wmb.destroy_communicator(comm)
+
+
+def test_example_support_modules_options_and_launch(monkeypatch):
+    """common_options / distributed_launch keep the reference's flags and environment contract (no GPU needed)."""
+    import argparse
+
+    import pylibwholegraph.torch as wgth
+
+    p = argparse.ArgumentParser()
+    for f in (wgth.add_training_options, wgth.add_common_graph_options, wgth.add_common_model_options, wgth.add_common_sampler_options,
+              wgth.add_node_classfication_options, wgth.add_dataloader_options, wgth.add_distributed_launch_options):
+        f(p)
+    a = p.parse_args(["--launch-agent", "pytorch", "-n", "10,5", "-l", "2", "--train-embedding"])
+    assert (a.epochs, a.batchsize, a.hiddensize, a.model, a.framework, a.classnum, a.cache_type) == (24, 1024, 256, "sage", "wg", 172, "none")
+    assert wgth.parse_max_neighbors(2, a.neighbors) == [10, 5] and wgth.parse_max_neighbors(3, "30") == [30, 30, 30]
+    for k, v in (("RANK", "3"), ("WORLD_SIZE", "8"), ("LOCAL_RANK", "3"), ("LOCAL_WORLD_SIZE", "8"), ("MASTER_ADDR", "127.0.0.1"), ("MASTER_PORT", "29999")):
+        monkeypatch.setenv(k, v)
+    seen = {}
+    wgth.distributed_launch(a, lambda: seen.update(rank=wgth.get_rank(), world=wgth.get_world_size(), local=wgth.get_local_rank(), lsize=wgth.get_local_size()))
+    assert seen == {"rank": 3, "world": 8, "local": 3, "lsize": 8}
