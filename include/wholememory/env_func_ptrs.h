@@ -22,14 +22,17 @@ enum wholememory_memory_allocation_type_t {
   WHOLEMEMORY_MA_PINNED,
 };
 
+/* A "memory context" is the caller's handle for ONE allocation (in Python: an object that ends up holding the torch
+ * tensor); `global_context` is passed back verbatim to every callback. */
 typedef void (*wholememory_create_memory_context_func_t)(void** memory_context, void* global_context);
 typedef void (*wholememory_destroy_memory_context_func_t)(void* memory_context, void* global_context);
+/* returns the data pointer of a fresh allocation described by `desc` (sizes, dtype) in the requested kind of memory */
 typedef void* (*wholememory_malloc_func_t)(wholememory_tensor_description_t* desc,
-                                           wholememory_memory_allocation_type_t memory_allocation_type,
-                                           void* memory_context,
+                                           wholememory_memory_allocation_type_t memory_allocation_type, void* memory_context,
                                            void* global_context);
 typedef void (*wholememory_free_func_t)(void* memory_context, void* global_context);
 
+/* scratch that lives for one op: context created and destroyed by the op itself */
 struct wholememory_temp_memory_func_t {
   wholememory_create_memory_context_func_t create_memory_context_fn;
   wholememory_destroy_memory_context_func_t destroy_memory_context_fn;
@@ -37,6 +40,7 @@ struct wholememory_temp_memory_func_t {
   wholememory_free_func_t free_fn;
   void* global_context;
 };
+/* results handed back to the caller: the caller creates the context, the op fills it through malloc_fn */
 struct wholememory_output_memory_func_t {
   wholememory_malloc_func_t malloc_fn;
   wholememory_free_func_t free_fn;

@@ -19,13 +19,13 @@
 extern "C" {
 #endif
 
-wholememory_error_code_t graph_append_unique(
-  wholememory_tensor_t target_nodes_tensor,
-  wholememory_tensor_t neighbor_nodes_tensor,
-  void* output_unique_node_memory_context,
-  wholememory_tensor_t output_neighbor_raw_to_unique_mapping_tensor,
-  wholememory_env_func_t* p_env_fns,
-  void* stream);
+/* target_nodes / neighbor_nodes: int32 | int64 local device tensors of one dtype; the unique list (same dtype) is allocated
+ * through p_env_fns->output_fns into output_unique_node_memory_context; the mapping tensor (int32 [len(neighbors)]) is
+ * caller-allocated and may be NULL.  One host synchronisation (to size the unique list). */
+wholememory_error_code_t graph_append_unique(wholememory_tensor_t target_nodes_tensor, wholememory_tensor_t neighbor_nodes_tensor,
+                                             void* output_unique_node_memory_context,
+                                             wholememory_tensor_t output_neighbor_raw_to_unique_mapping_tensor,
+                                             wholememory_env_func_t* p_env_fns, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,19 +20,15 @@
 extern "C" {
 #endif
 
-wholememory_error_code_t wholememory_gather(wholememory_tensor_t wholememory_tensor,
-                                            wholememory_tensor_t indices_tensor,
-                                            wholememory_tensor_t output_tensor,
-                                            wholememory_env_func_t* p_env_fns,
-                                            void* stream,
+/* gather_sms / scatter_sms: upper bound on the SMs the copy kernel may occupy (-1: all 148; the grid is 8 CTAs per SM).
+ * p_env_fns is accepted for signature compatibility: neither op allocates. */
+wholememory_error_code_t wholememory_gather(wholememory_tensor_t wholememory_tensor, wholememory_tensor_t indices_tensor,
+                                            wholememory_tensor_t output_tensor, wholememory_env_func_t* p_env_fns, void* stream,
                                             int gather_sms = -1);
 
-wholememory_error_code_t wholememory_scatter(wholememory_tensor_t input_tensor,
-                                             wholememory_tensor_t indices_tensor,
-                                             wholememory_tensor_t wholememory_tensor,
-                                             wholememory_env_func_t* p_env_fns,
-                                             void* stream,
-                                             int scatter_sms = -1);
+wholememory_error_code_t wholememory_scatter(wholememory_tensor_t input_tensor, wholememory_tensor_t indices_tensor,
+                                             wholememory_tensor_t wholememory_tensor, wholememory_env_func_t* p_env_fns,
+                                             void* stream, int scatter_sms = -1);
 
 #ifdef __cplusplus
 }
