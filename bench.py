@@ -235,10 +235,11 @@ def run_ours(args):
         sd = host_seeds[k].to(dev, non_blocking=True)  # H2D of the step's input, from pinned memory
         return samplers[k & 1].sample_async(wm_rp, wm_col, sd, label_offsets, FANOUT, SAMPLER_SEED + 7 * k)
 
-    # Feature fetch on its own stream?  On one GPU both stages are bound by the same memory system and overlapping them is
-    # slower (measured 1.19 vs 1.03 ms/step); with the table striped over several GPUs the gather waits on NVLink while
-    # HBM and the SMs idle, so the next call group's sampling kernels run underneath it (default: on for N > 1).
-    use_side = (world > 1) if args.gather_stream < 0 else bool(args.gather_stream)
+    # Feature fetch on its own stream: the next call group's sampling kernels (latency / random-access bound, little
+    # bandwidth) run underneath the bandwidth-bound gather.  Measured at N=1 with 20 steps: 0.845 ms/step against 0.881 on
+    # one stream; for N > 1 the gather additionally waits on NVLink while HBM and the SMs idle.  (An earlier measurement that
+    # found the overlap slower was taken before the per-stream allocator priming below and had cudaMalloc stalls in it.)
+    use_side = True if args.gather_stream < 0 else bool(args.gather_stream)
     side = torch.cuda.Stream(device=dev) if use_side else None
     n_metric = (labels * len(FANOUT) + 1) + (labels + 1) + labels * FEAT_DIM
     host_ring = [torch.empty(n_metric, dtype=torch.float64, pin_memory=True) for _ in range(4)]
@@ -552,7 +553,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hot-ratio", type=float, default=0.1,
                     help="N > 1: fraction of the feature rows (the highest-degree vertices) replicated on every GPU; 0 = none")
-    ap.add_argument("--gather-stream", type=int, default=-1, help="run the feature gather on a second stream (1), in line (0), or 1 iff N > 1 (-1)")
+    ap.add_argument("--gather-stream", type=int, default=-1, help="run the feature gather on a second stream (1, default) or in line (0)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
