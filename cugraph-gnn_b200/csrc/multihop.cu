@@ -8,20 +8,26 @@
 // host syncs, ~10 launches and several Python round trips PER HOP.
 //
 // B200-first design:
-//  * no host synchronisation until every hop is done: frontier sizes and edge counts stay on the device,
-//    kernels are launched over host-known upper bounds (|frontier| * fanout) and read the true sizes from
-//    device memory; a single 24-byte D2H copy at the end sizes the outputs.
-//  * per hop: count+scan (single pass) -> sample (sub-warp per row) -> hash insert with atomicMin of the
-//    first edge position -> single-pass flag+scan+compact that emits the next frontier in first-occurrence
-//    order and assigns local ids.  The next frontier of a label is exactly the vertices new in this hop.
-//  * one open-addressing table keyed (label, vertex) for the whole call group.  Its allocation covers the
-//    worst case, but every hop only uses the first `nslots` slots, chosen ON THE DEVICE from the true
-//    counts (2 x (known vertices + this hop's edges)), so the working set stays L2-resident (126 MB) even
-//    though the worst-case bound is ~10x larger.  Each hop runs in a new 8-bit epoch (no memset): the
+//  * a call is two halves, _begin (enqueue every hop, no host wait) and _finish (wait for ONE event that marks the
+//    output sizes, allocate through the callbacks, scatter scratch -> outputs), so loaders keep call group k+1 running
+//    while they finish call group k.  Frontier sizes and edge counts stay on the device; kernels are launched over
+//    host-known upper bounds (|frontier| * fanout) and read the true sizes from device memory.
+//  * per hop: count+scan (single pass, persistent ticketed tiles) -> sample (sub-warp per row) -> hash insert that
+//    records the first edge position of every (label, vertex) -> single-pass flag+scan+compact that emits the next
+//    frontier in first-occurrence order.  The next frontier of a label is exactly the vertices new in this hop.
+//  * one open-addressing table keyed (label, vertex), buckets of two 16-byte slots = one 32-byte sector, read with one
+//    256-bit load and claimed with one 128-bit CAS (what bounds dedup is the rate of random requests, not bytes).
+//    Its allocation covers the worst case, but every hop only uses the first `nslots` slots, chosen ON THE DEVICE from
+//    the true counts (2 x (known vertices + this hop's edges)).  Each hop runs in a new 8-bit epoch (no memset): the
 //    vertices numbered so far are re-inserted (cheap: earlier hops are an order of magnitude smaller).
-//  * the final pass scatters (major, minor, edge id) from hop-major scratch to the label-major / hop-minor
-//    layout the decoders expect (sampler/sampler.py:525-740) and turns hash slots into local ids, so
-//    renumbering costs no extra pass over the edges.
+//  * compact only READS the table: an edge's slot becomes a reference step(4) | index(28) that is either final (endpoint
+//    numbered in an earlier step) or "pending, first seen at edge e'"; the final pass resolves pending references
+//    through the dense rank_of array while it scatters (major, minor, edge id) from hop-major scratch to the
+//    label-major / hop-minor layout the decoders expect (sampler/sampler.py:525-740).
+//  * heterogeneous graphs (T edge types = T CSRs over one id space, Vt vertex types = id ranges): count+scan and sample
+//    run once per edge type, a small kernel interleaves the per-type offsets so that the hop's edge list stays
+//    label-major, insert / compact are unchanged; typed local ids and the [label][edge type][hop] grouping are
+//    bookkeeping after the hops.
 //
 // Random numbers: hop h draws with seed hop_seed(random_state, h) = random_state + h * 0x9E3779B97F4A7C15
 // and the S1/S2 stream geometry over the label-major concatenated frontier, which is what oracle/
