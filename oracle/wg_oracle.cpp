@@ -831,11 +831,29 @@ struct wgo_hetero_result {
 
 uint64_t wgo_type_seed(uint64_t hop_seed, int etype) { return hop_seed + (uint64_t)etype * 0xD1B54A32D192ED03ULL; }
 
-void* wgo_hetero_multihop_sample(int num_edge_types, const int64_t* const* row_ptr, const void* const* col, int col_dtype,
-                                 const void* const* wgt, int wgt_dtype, const int64_t* const* edge_ids,
-                                 const int64_t* vtype_offsets, int num_vertex_types, const int64_t* seeds,
-                                 const int64_t* label_offsets, int64_t num_labels, const int32_t* fanout, int num_hops,
-                                 uint64_t random_state)
+// comparison of an edge time with the time of the vertex it is sampled from (pylibcugraph temporal_sampling_comparison)
+enum { WGO_T_STRICTLY_INCREASING = 0, WGO_T_MONOTONICALLY_INCREASING = 1, WGO_T_STRICTLY_DECREASING = 2, WGO_T_MONOTONICALLY_DECREASING = 3 };
+static inline bool wgo_time_ok(int cmp, int64_t edge_time, int64_t vertex_time)
+{
+  switch (cmp) {
+    case WGO_T_STRICTLY_INCREASING: return edge_time > vertex_time;
+    case WGO_T_MONOTONICALLY_INCREASING: return edge_time >= vertex_time;
+    case WGO_T_STRICTLY_DECREASING: return edge_time < vertex_time;
+    default: return edge_time <= vertex_time;
+  }
+}
+
+// Shared implementation.  edge_times == nullptr: plain heterogeneous sampling (above).  Otherwise TEMPORAL sampling
+// (pylibcugraph.*_temporal_neighbor_sample; reference call site distributed_sampler.py:808-819, pins
+// tests/loader/test_neighbor_loader.py:943-1058): a frontier vertex carries a time (seed: its starting time; otherwise
+// the time of the edge that first reached it); only the edges of its row whose time compares as requested are eligible;
+// the one-hop uniform algorithm (S1) runs over the ELIGIBLE positions of the row, in CSR order, with the same stream
+// geometry.  Temporal + biased is not restated yet.
+static void* wgo_hetero_impl(int num_edge_types, const int64_t* const* row_ptr, const void* const* col, int col_dtype,
+                             const void* const* wgt, int wgt_dtype, const int64_t* const* edge_ids,
+                             const int64_t* vtype_offsets, int num_vertex_types, const int64_t* seeds,
+                             const int64_t* label_offsets, int64_t num_labels, const int32_t* fanout, int num_hops,
+                             uint64_t random_state, const int64_t* const* edge_times, const int64_t* seed_times, int time_cmp)
 {
   auto* res       = new wgo_hetero_result();
   const int64_t B = num_labels;
@@ -850,12 +868,14 @@ void* wgo_hetero_multihop_sample(int num_edge_types, const int64_t* const* row_p
   std::vector<std::unordered_map<int64_t, int32_t>> tables(B);
   std::vector<std::vector<int64_t>> step_end(B, std::vector<int64_t>(L + 2, 0));  // discovery index at the end of step s
   std::vector<int64_t> front_begin(B), front_end(B);
+  std::vector<std::vector<int64_t>> vtime(B);  // temporal: time of every discovered vertex (first arrival)
   for (int64_t l = 0; l < B; l++) {
     for (int64_t s = label_offsets[l]; s < label_offsets[l + 1]; s++) {
       int64_t v = seeds[s];
       if (tables[l].find(v) == tables[l].end()) {
         tables[l].insert(std::make_pair(v, (int32_t)maps[l].size()));
         maps[l].push_back(v);
+        vtime[l].push_back(seed_times ? seed_times[s] : 0);
       }
     }
     front_begin[l] = 0;
@@ -868,12 +888,14 @@ void* wgo_hetero_multihop_sample(int num_edge_types, const int64_t* const* row_p
   };
   std::vector<std::vector<Edge>> edges((size_t)B * T * L);
   for (int h = 0; h < L; h++) {
-    std::vector<int64_t> frontier;
+    std::vector<int64_t> frontier, ftime;
     std::vector<int64_t> fr_off(B + 1, 0);
     for (int64_t l = 0; l < B; l++) {
       fr_off[l] = (int64_t)frontier.size();
-      for (int64_t i = front_begin[l]; i < front_end[l]; i++)
+      for (int64_t i = front_begin[l]; i < front_end[l]; i++) {
         frontier.push_back(maps[l][i]);
+        ftime.push_back(vtime[l][i]);
+      }
     }
     fr_off[B]  = (int64_t)frontier.size();
     int64_t nf = (int64_t)frontier.size();
@@ -882,6 +904,48 @@ void* wgo_hetero_multihop_sample(int num_edge_types, const int64_t* const* row_p
     for (int t = 0; t < T; t++) {
       int M = fanout[h * T + t];
       if (M == 0 || nf == 0) continue;
+      if (edge_times) {
+        // temporal: S1 over the eligible positions of every row
+        uint64_t hs = wgo_type_seed(wgo_hop_seed(random_state, h), t);
+        std::vector<int> Q;
+        std::vector<int32_t> r;
+        for (int64_t f = 0; f < nf; f++) {
+          off[t][f] = (int32_t)dest[t].size();
+          int64_t v = frontier[f];
+          std::vector<int64_t> elig;
+          for (int64_t p = row_ptr[t][v]; p < row_ptr[t][v + 1]; p++)
+            if (wgo_time_ok(time_cmp, edge_times[t][p], ftime[f])) elig.push_back(p);
+          int N = (int)elig.size();
+          auto take = [&](int64_t p) {
+            dest[t].push_back(read_index(col[t], col_dtype, p));
+            gid[t].push_back(p);
+          };
+          if (M < 0 || N <= M) {
+            for (int64_t p : elig)
+              take(p);
+            continue;
+          }
+          int func_idx = (M - 1) / 32;
+          int TT       = kWarpCount[func_idx] * 32;
+          int ipt      = kItems[func_idx];
+          if ((int)r.size() < TT * ipt) r.resize(TT * ipt);
+          for (int j = 0; j < TT; j++) {
+            Pcg rng;
+            rng.init_raft(hs, 0, (uint64_t)(f * TT + j));
+            for (int k = 0; k < ipt; k++) {
+              int id    = k * TT + j;
+              int32_t x = rng.next_i32();
+              r[id]     = id < M ? x % (N - id) : N;
+            }
+          }
+          int a[1024];
+          resolve_chain(r.data(), M, N, Q, a);
+          for (int i = 0; i < M; i++)
+            take(elig[a[i]]);
+        }
+        off[t][nf] = (int32_t)dest[t].size();
+        continue;
+      }
       wgo_sample_offsets(row_ptr[t], frontier.data(), DT_INT64, nf, M, off[t].data());
       int64_t tot = off[t][nf];
       dest[t].resize(tot);
@@ -917,6 +981,7 @@ void* wgo_hetero_multihop_sample(int num_edge_types, const int64_t* const* row_p
               id = (int32_t)maps[l].size();
               tables[l].insert(std::make_pair(v, id));
               maps[l].push_back(v);
+              vtime[l].push_back(edge_times ? edge_times[t][gid[t][e]] : 0);
             } else {
               id = it->second;
             }
@@ -974,6 +1039,26 @@ void* wgo_hetero_multihop_sample(int num_edge_types, const int64_t* const* row_p
     }
   }
   return res;
+}
+
+void* wgo_hetero_multihop_sample(int num_edge_types, const int64_t* const* row_ptr, const void* const* col, int col_dtype,
+                                 const void* const* wgt, int wgt_dtype, const int64_t* const* edge_ids,
+                                 const int64_t* vtype_offsets, int num_vertex_types, const int64_t* seeds,
+                                 const int64_t* label_offsets, int64_t num_labels, const int32_t* fanout, int num_hops,
+                                 uint64_t random_state)
+{
+  return wgo_hetero_impl(num_edge_types, row_ptr, col, col_dtype, wgt, wgt_dtype, edge_ids, vtype_offsets, num_vertex_types, seeds,
+                         label_offsets, num_labels, fanout, num_hops, random_state, nullptr, nullptr, 0);
+}
+
+void* wgo_temporal_multihop_sample(int num_edge_types, const int64_t* const* row_ptr, const void* const* col, int col_dtype,
+                                   const int64_t* const* edge_ids, const int64_t* const* edge_times,
+                                   const int64_t* vtype_offsets, int num_vertex_types, const int64_t* seeds,
+                                   const int64_t* seed_times, const int64_t* label_offsets, int64_t num_labels,
+                                   const int32_t* fanout, int num_hops, uint64_t random_state, int time_cmp)
+{
+  return wgo_hetero_impl(num_edge_types, row_ptr, col, col_dtype, nullptr, 0, edge_ids, vtype_offsets, num_vertex_types, seeds,
+                         label_offsets, num_labels, fanout, num_hops, random_state, edge_times, seed_times, time_cmp);
 }
 
 int64_t wgo_hetero_num_edges(void* h) { return (int64_t)((wgo_hetero_result*)h)->majors.size(); }

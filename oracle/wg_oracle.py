@@ -328,3 +328,55 @@ def embedding_gradient_apply(optimizer, params, emb, indices, grads, lr, states)
         f(lr), _p(emb), ctypes.c_int64(emb.shape[1]), _p(indices), ctypes.c_int64(indices.shape[0]), _p(grads), _p(a), _p(b), _p(pr))
     assert rc == 0
     return emb
+
+
+TIME_CMP = {"strictly_increasing": 0, "monotonically_increasing": 1, "strictly_decreasing": 2, "monotonically_decreasing": 3}
+
+
+def temporal_multihop_sample(row_ptrs, cols, edge_times, vertex_type_offsets, seeds, seed_times, label_offsets, fanout,
+                             random_state, comparison="strictly_increasing", edge_ids=None):
+    """Temporal (uniform) multi-hop sample over typed CSRs: edge_times[t] int64 [E_t], seed_times int64 [S]; a vertex is
+    sampled only through edges whose time compares as requested with the time it was reached at.  ORACLE ONLY this
+    round: the product has no temporal path yet."""
+    T = len(row_ptrs)
+    row_ptrs = [np.ascontiguousarray(r, dtype=np.int64) for r in row_ptrs]
+    cols = [np.ascontiguousarray(c) for c in cols]
+    edge_times = [np.ascontiguousarray(t, dtype=np.int64) for t in edge_times]
+    vto = np.ascontiguousarray(vertex_type_offsets, dtype=np.int64)
+    Vt = vto.shape[0] - 1
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    seed_times = np.ascontiguousarray(seed_times, dtype=np.int64)
+    label_offsets = np.ascontiguousarray(label_offsets, dtype=np.int64)
+    fanout = np.ascontiguousarray(fanout, dtype=np.int32).reshape(-1)
+    L = fanout.shape[0] // T
+    B = label_offsets.shape[0] - 1
+    vp = ctypes.c_void_p
+
+    def ptr_array(arrs):
+        return (vp * T)(*[(a.ctypes.data if a is not None else None) for a in arrs])
+
+    e_arr = None
+    if edge_ids is not None:
+        edge_ids = [None if e is None else np.ascontiguousarray(e, dtype=np.int64) for e in edge_ids]
+        e_arr = ptr_array(edge_ids)
+    fn = lib().wgo_temporal_multihop_sample
+    fn.restype = ctypes.c_void_p
+    h = fn(ctypes.c_int(T), ptr_array(row_ptrs), ptr_array(cols), _dt(cols[0]), e_arr, ptr_array(edge_times), _p(vto), ctypes.c_int(Vt),
+           _p(seeds), _p(seed_times), _p(label_offsets), ctypes.c_int64(B), _p(fanout), ctypes.c_int(L), ctypes.c_uint64(random_state),
+           ctypes.c_int(TIME_CMP[comparison]))
+    h = vp(h)
+    lib().wgo_hetero_num_edges.restype = ctypes.c_int64
+    lib().wgo_hetero_num_nodes.restype = ctypes.c_int64
+    ne, nn = int(lib().wgo_hetero_num_edges(h)), int(lib().wgo_hetero_num_nodes(h))
+    out = {
+        "majors": np.empty(ne, dtype=np.int32), "minors": np.empty(ne, dtype=np.int32), "edge_type": np.empty(ne, dtype=np.int32),
+        "edge_id": np.empty(ne, dtype=np.int64), "label_type_hop_offsets": np.empty(B * T * L + 1, dtype=np.int64),
+        "renumber_map": np.empty(nn, dtype=np.int64), "renumber_map_offsets": np.empty(B * Vt + 1, dtype=np.int64),
+        "edge_renumber_map": np.empty(ne, dtype=np.int64), "edge_renumber_map_offsets": np.empty(B * T + 1, dtype=np.int64),
+        "label_type_step_base": np.empty((L + 1, Vt, B), dtype=np.int32),
+    }
+    lib().wgo_hetero_copy(h, _p(out["majors"]), _p(out["minors"]), _p(out["edge_type"]), _p(out["edge_id"]),
+                          _p(out["label_type_hop_offsets"]), _p(out["renumber_map"]), _p(out["renumber_map_offsets"]),
+                          _p(out["edge_renumber_map"]), _p(out["edge_renumber_map_offsets"]), _p(out["label_type_step_base"]))
+    lib().wgo_hetero_free(h)
+    return out

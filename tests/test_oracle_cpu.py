@@ -462,3 +462,72 @@ def test_embedding_optimizers_against_numpy_restatement(oracle, opt):
     np.testing.assert_allclose(got, exp, rtol=2e-6, atol=1e-7)
     untouched = np.setdiff1d(np.arange(rows), idx)
     assert np.array_equal(got[untouched], w0[untouched])
+
+
+# ---- temporal sampling (oracle only this round) --------------------------------------------------------------------
+def _pyg_to_typed(edges_by_type, vertex_counts):
+    """edges_by_type: [(pyg_src_ids, pyg_dst_ids, src_vtype, dst_vtype, times)]; the sampler walks PyG in-edges, so CSR rows
+    are PyG destinations (cuGraph sources).  Returns typed CSRs + per-type (edge ids in input order, times) in CSR order."""
+    from graphs import typed_csrs
+
+    vto = np.concatenate([[0], np.cumsum(vertex_counts)]).astype(np.int64)
+    srcs, dsts, etps = [], [], []
+    for t, (ps, pd, sv, dv, _) in enumerate(edges_by_type):
+        srcs.append(np.asarray(pd) + vto[dv])
+        dsts.append(np.asarray(ps) + vto[sv])
+        etps.append(np.full(len(ps), t))
+    row_ptrs, cols, pos = typed_csrs(np.concatenate(srcs), np.concatenate(dsts), np.concatenate(etps), len(edges_by_type), int(vto[-1]))
+    first = np.cumsum([0] + [len(e[0]) for e in edges_by_type])
+    eids = [p - first[t] for t, p in enumerate(pos)]  # running index per type, as GraphStore assigns them
+    times = [np.asarray(edges_by_type[t][4], dtype=np.int64)[eids[t]] for t in range(len(edges_by_type))]
+    return vto, row_ptrs, cols, eids, times
+
+
+def test_temporal_reference_pin_homogeneous(oracle):
+    """tests/loader/test_neighbor_loader.py:943-990 (test_neighbor_loader_temporal_simple): strictly increasing times
+    along the path; n_id [3,2,1,0], e_id [0,1,2], one node and one edge per hop."""
+    # graph_store[...] = [dst_cite, src_cite]: PyG edge_index row 0 (sources) is dst_cite, row 1 (destinations) src_cite
+    src_cite, dst_cite, tme = [3, 2, 1, 2], [2, 1, 0, 0], [0, 1, 2, 0]
+    vto, row_ptrs, cols, eids, times = _pyg_to_typed([(dst_cite, src_cite, 0, 0, tme)], [4])
+    out = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, [3], [-1], [0, 1], [2, 2, 2], 62, "strictly_increasing", edge_ids=eids)
+    assert out["renumber_map"].tolist() == [3, 2, 1, 0]
+    assert out["edge_renumber_map"][out["edge_id"]].tolist() == [0, 1, 2]
+    assert np.diff(out["label_type_hop_offsets"]).tolist() == [1, 1, 1]
+    assert np.diff(np.append(out["label_type_step_base"][:, 0, 0], 4)).tolist() == [1, 1, 1, 1]
+    # monotonically_increasing additionally admits the 0 -> 2 edge (time 0 == time of vertex 2)
+    out = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, [3], [-1], [0, 1], [2, 2, 2], 62, "monotonically_increasing", edge_ids=eids)
+    assert sorted(out["edge_renumber_map"].tolist()) == [0, 1, 2, 3]
+
+
+def test_temporal_reference_pin_heterogeneous(oracle):
+    """tests/loader/test_neighbor_loader.py:993-1058 (test_neighbor_loader_temporal_hetero)."""
+    src_cite, dst_cite, tme_cite = [3, 2, 1, 2], [2, 1, 0, 0], [0, 1, 2, 0]
+    src_author, dst_author, tme_author = [3, 2, 2, 1, 3, 2, 0], [0, 0, 1, 1, 2, 2, 2], [0, 0, 1, 0, 2, 1, 1]
+    # vertex types sorted: author (0), paper (1); edge types sorted: (author, writes, paper) = 0, (paper, cites, paper) = 1
+    edges = [(dst_author, src_author, 0, 1, tme_author), (dst_cite, src_cite, 1, 1, tme_cite)]
+    vto, row_ptrs, cols, eids, times = _pyg_to_typed(edges, [3, 4])
+    fanout = [2, 2, 2, 2, 0, 2]  # [hop * T + etype]: writes [2, 2, 0], cites [2, 2, 2]
+    out = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, [3 + 3], [-1], [0, 1], fanout, 62, "strictly_increasing", edge_ids=eids)
+    rmo, lto, ermo = out["renumber_map_offsets"], out["label_type_hop_offsets"], out["edge_renumber_map_offsets"]
+    authors = out["renumber_map"][rmo[0]:rmo[1]] - vto[0]
+    papers = out["renumber_map"][rmo[1]:rmo[2]] - vto[1]
+    assert sorted(authors.tolist()) == [0, 1, 2] and papers.tolist() == [3, 2, 1, 0]
+    writes = out["edge_renumber_map"][ermo[0]:ermo[1]]
+    assert sorted(writes.tolist()) == [0, 2, 4, 5]
+    assert np.diff(lto[0:4]).tolist() == [2, 2, 0]  # (author, writes, paper) edges per hop
+
+
+def test_temporal_with_open_window_equals_plain_sampling(oracle):
+    """With every edge eligible the temporal path reduces to the plain heterogeneous sampler (same streams)."""
+    from graphs import random_typed_graph
+
+    edge_types = [(0, 1), (1, 0)]
+    vto, row_ptrs, cols = random_typed_graph([200, 300], edge_types, [3000, 3000], seed=6)
+    times = [np.ones(c.shape[0], dtype=np.int64) for c in cols]
+    rng = np.random.default_rng(0)
+    seeds = rng.integers(0, 500, 30).astype(np.int64)
+    lo = np.array([0, 30], dtype=np.int64)
+    plain = oracle.hetero_multihop_sample(row_ptrs, cols, vto, seeds, lo, [4, 3, 2, 2], 5)
+    temp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, np.ones(30, np.int64), lo, [4, 3, 2, 2], 5, "monotonically_increasing")
+    for k in plain:
+        assert np.array_equal(plain[k], temp[k]), k
