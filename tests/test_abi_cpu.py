@@ -164,3 +164,27 @@ def test_example_support_modules_options_and_launch(monkeypatch):
     seen = {}
     wgth.distributed_launch(a, lambda: seen.update(rank=wgth.get_rank(), world=wgth.get_world_size(), local=wgth.get_local_rank(), lsize=wgth.get_local_size()))
     assert seen == {"rank": 3, "world": 8, "local": 3, "lsize": 8}
+
+
+def test_missing_library_fails_loudly_and_product_never_imports_the_oracle():
+    """No CPU fallback: if the shared library cannot be loaded, importing the binding raises; and no product module
+    (package, bench's own arm, entry points) reaches into oracle/."""
+    import subprocess
+    import sys
+
+    pkg = os.path.join(ROOT, "cugraph-gnn_b200")
+    code = ("import ctypes, sys\n"
+            "def boom(*a, **k):\n    raise OSError('libwholegraph_b200.so: cannot open shared object file')\n"
+            "ctypes.CDLL = boom\n"
+            "sys.path.insert(0, %r)\n"
+            "import pylibwholegraph.binding.wholememory_binding\n" % pkg)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0 and "ImportError" in r.stderr and "could not be loaded" in r.stderr
+    offenders = []
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(d, f)).read()
+                if re.search(r"^\s*(import|from)\s+wg_oracle|oracle[/\\.]wg_oracle|sys\.path.*oracle", text, re.M):
+                    offenders.append(os.path.join(d, f))
+    assert not offenders, offenders
