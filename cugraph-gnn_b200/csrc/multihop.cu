@@ -36,6 +36,7 @@
 #include "wm_common.cuh"
 #include "pcg.cuh"
 #include "sample_device.cuh"
+#include "temporal_device.cuh"
 
 #include <wholememory/b200_ops.h>
 
@@ -505,6 +506,50 @@ __global__ void __launch_bounds__(256) mh_seed_local_kernel(const unsigned int* 
   }
 }
 
+// ---- temporal calls: the time every frontier row carries (temporal_device.cuh) ------------------------------------
+// step 0: the time of the FIRST occurrence of a (label, seed) pair is the one its frontier row gets
+__global__ void __launch_bounds__(256) mh_seed_time_kernel(const unsigned int* __restrict__ seed_ref,
+                                                           const unsigned int* __restrict__ seed_rank,
+                                                           const long long* __restrict__ seed_times, int S,
+                                                           long long* __restrict__ ftime0)
+{
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < S; s += gridDim.x * blockDim.x)
+    if ((seed_ref[s] & 0x0FFFFFFFu) == (unsigned int)s) ftime0[seed_rank[s]] = seed_times[s];
+}
+
+// after the compaction of a hop: a vertex that is new in this hop takes the time of the edge that reached it first
+// (the edge whose reference is "pending, first seen at myself").  Edge times per edge type live in device memory.
+struct MhTemporalDesc {
+  int T;
+  ChunkRef etime[16];
+  unsigned long long etime_off[16];
+};
+struct MhTypePos {
+  const int* pos[16];  // [t][f]: first edge of (row f, type t) in the hop's edge list; only read when T > 1
+};
+template <bool CHUNKED>
+__global__ void __launch_bounds__(256) mh_next_time_kernel(const MhTemporalDesc* __restrict__ d, MhTypePos tp,
+                                                           const int* __restrict__ n_edges,
+                                                           const unsigned int* __restrict__ slot_to_ref,
+                                                           const unsigned int* __restrict__ rank_of,
+                                                           const int* __restrict__ erow, const long long* __restrict__ gid,
+                                                           long long* __restrict__ next_ftime)
+{
+  const int n = *n_edges;
+  const int T = d->T;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const unsigned int ref = slot_to_ref[e];
+    if ((ref >> 28) != kRefPending || (ref & 0x0FFFFFFFu) != (unsigned int)e) continue;
+    int t = 0;
+    if (T > 1) {
+      const int f = erow[e];
+      for (int i = 1; i < T; i++)
+        t += tp.pos[i][f] <= e ? 1 : 0;  // pos is non-decreasing in the type for a fixed row
+    }
+    next_ftime[rank_of[e]] = load_i64<CHUNKED>(d->etime[t], d->etime_off[t] + (unsigned long long)gid[e]);
+  }
+}
+
 // ---- final pass -------------------------------------------------------------------------------------------
 struct MhHopBufs {
   const int* off[kMaxHops];
@@ -599,6 +644,7 @@ __global__ void __launch_bounds__(256) mh_csr_label_hop_kernel(int L, int B, con
 // that restart per (label, vertex type).  The descriptor lives in device memory (too large for a parameter block).
 constexpr int kMaxEdgeTypes   = 16;
 constexpr int kMaxVertexTypes = 16;
+static_assert(kMaxEdgeTypes == 16, "MhTemporalDesc / MhTypePos are sized for 16 edge types");
 
 struct MhHeteroDesc {
   int T, Vt, L, B;
@@ -783,6 +829,9 @@ struct wholegraph_multihop_sampler_ {
   Buf base;
   // heterogeneous calls only
   Buf pos[wgb::kMaxHops], tcnt[wgb::kMaxHops + 1], typed[wgb::kMaxHops + 1], vscan_state, tbase, desc_dev;
+  // temporal calls only
+  Buf ftime[wgb::kMaxHops + 1], eligible[wgb::kMaxHops], clipped, tdesc_dev;
+  wgb::MhTemporalDesc tdesc_host;
   wgb::MhHeteroDesc desc_host;
   long long* h_totals = nullptr;  // pinned
   int device          = -1;
@@ -906,8 +955,8 @@ static void mh_print_marks(wholegraph_multihop_sampler_* sp)
 static int grid_over(long long n, int sms) { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, (long long)sms * 8)); }
 
 struct MhTypeCsr {
-  ChunkRef row_ptr, col, wgt, eid;
-  unsigned long long row_ptr_off = 0, col_off = 0, wgt_off = 0, eid_off = 0;
+  ChunkRef row_ptr, col, wgt, eid, etime;
+  unsigned long long row_ptr_off = 0, col_off = 0, wgt_off = 0, eid_off = 0, etime_off = 0;
   bool has_eid = false;
 };
 
@@ -928,6 +977,10 @@ struct MhCall {
   unsigned long long random_state;
   int flags;
   cudaStream_t stream;
+  // temporal calls (edge times per type in csr[t].etime)
+  bool temporal                = false;
+  int time_cmp                 = 0;
+  const long long* seed_times  = nullptr;  // device, [S]
 };
 
 template <typename ColT, bool CHUNKED>
@@ -1056,6 +1109,20 @@ static void multihop_begin(MhCall& c)
     }
   }
 
+  const MhTemporalDesc* tdesc_dev = nullptr;
+  if (c.temporal) {
+    MhTemporalDesc& td = sp->tdesc_host;
+    memset(&td, 0, sizeof(td));
+    td.T = T;
+    for (int t = 0; t < T; t++) {
+      td.etime[t]     = c.csr[t].etime;
+      td.etime_off[t] = c.csr[t].etime_off;
+    }
+    void* p = ensure(sp->tdesc_dev, sizeof(MhTemporalDesc));
+    WGB_CUDA_TRY(cudaMemcpyAsync(p, &td, sizeof(MhTemporalDesc), cudaMemcpyHostToDevice, st));
+    tdesc_dev = static_cast<const MhTemporalDesc*>(p);
+  }
+
   auto scan_slice = [&](long long n_items, int tile_items = kScanTile) {
     int tiles    = (int)((n_items + tile_items) / tile_items);
     size_t bytes = scan_state_bytes(tiles);
@@ -1096,6 +1163,11 @@ static void multihop_begin(MhCall& c)
       mh_compact_kernel<long long, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, rank0, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
     }
     WGB_CHECK_LAUNCH();
+    if (c.temporal) {
+      long long* ftime0 = static_cast<long long*>(ensure(sp->ftime[0], sizeof(long long) * (size_t)std::max(S, 1)));
+      mh_seed_time_kernel<<<grid_over(S, sms), 256, 0, st>>>(slot0, rank0, c.seed_times, S, ftime0);
+      WGB_CHECK_LAUNCH();
+    }
     mh_mark(sp, "seeds", st);
     fr.frontier[0]  = frontier0;
     fr.flabel[0]    = flabel0;
@@ -1117,6 +1189,10 @@ static void multihop_begin(MhCall& c)
     const int* pos_t[kMaxEdgeTypes];
     for (int t = 0; t < T; t++)
       off_t[t] = pos_t[t] = nullptr;
+    if (c.temporal) {
+      ensure(sp->eligible[h], sizeof(int) * off_stride * (size_t)T);
+      ensure(sp->clipped, sizeof(int) * off_stride);
+    }
     if (fs != 0 && rows_ub > 0) {
       // K1: counts + scan over the frontier, once per edge type
       for (int t = 0; t < T; t++) {
@@ -1124,7 +1200,19 @@ static void multihop_begin(MhCall& c)
         if (M == 0) continue;
         int* off = off_all + (size_t)t * off_stride;
         auto ss  = scan_slice(rows_ub);
-        count_scan_kernel<long long, CHUNKED><<<scan_grid(ss.second), kScanBlock, 0, st>>>(c.csr[t].row_ptr, c.csr[t].row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, ticket_of(ss), n_rows_dev + h, T > 1 ? n_edges_t_dev + h * T + t : n_edges_dev + h);
+        int* total_out = T > 1 ? n_edges_t_dev + h * T + t : n_edges_dev + h;
+        if (c.temporal) {
+          // eligible edges per row (the whole row is read), clipped to the fan-out, then the same single-pass scan
+          int* eligible = static_cast<int*>(sp->eligible[h].p) + (size_t)t * off_stride;
+          int* clipped  = static_cast<int*>(sp->clipped.p);
+          temporal_count_kernel<CHUNKED><<<std::max(1, (int)std::min<long long>((rows_ub + 7) / 8, (long long)sms * 8)), 256, 0, st>>>(
+            c.csr[t].row_ptr, c.csr[t].row_ptr_off, c.csr[t].etime, c.csr[t].etime_off, frontier, static_cast<const long long*>(sp->ftime[h].p), M,
+            c.time_cmp, eligible, clipped, n_rows_dev + h);
+          WGB_CHECK_LAUNCH();
+          scan_counts_kernel<<<scan_grid(ss.second), kScanBlock, 0, st>>>(clipped, off, ss.first, ticket_of(ss), n_rows_dev + h, total_out);
+        } else {
+          count_scan_kernel<long long, CHUNKED><<<scan_grid(ss.second), kScanBlock, 0, st>>>(c.csr[t].row_ptr, c.csr[t].row_ptr_off, frontier, (int)rows_ub, M, off, ss.first, ticket_of(ss), n_rows_dev + h, total_out);
+        }
         WGB_CHECK_LAUNCH();
         off_t[t] = off;
       }
@@ -1202,8 +1290,17 @@ static void multihop_begin(MhCall& c)
       const unsigned long long hop_seed = c.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL;
       for (int t = 0; t < T; t++) {
         if (!off_t[t]) continue;
-        launch_hop_sample<ColT, CHUNKED>(c, c.csr[t], frontier, n_rows_dev + h, rows_ub, c.fanout[h * T + t],
-                                         hop_seed + (unsigned long long)t * 0xD1B54A32D192ED03ULL, pos_t[t], dest, erow, gid);
+        const unsigned long long type_seed = hop_seed + (unsigned long long)t * 0xD1B54A32D192ED03ULL;
+        if (c.temporal) {
+          const int* eligible = static_cast<const int*>(sp->eligible[h].p) + (size_t)t * off_stride;
+          temporal_uniform_kernel<ColT, CHUNKED><<<std::max(1, (int)std::min<long long>(rows_ub, (long long)sms * 16)), kGeneralBlock, 0, st>>>(
+            c.csr[t].row_ptr, c.csr[t].row_ptr_off, c.csr[t].col, c.csr[t].col_off, c.csr[t].etime, c.csr[t].etime_off, frontier,
+            static_cast<const long long*>(sp->ftime[h].p), eligible, c.fanout[h * T + t], c.time_cmp, type_seed, pos_t[t], dest, erow, gid,
+            skip_table_device(), n_rows_dev + h);
+          WGB_CHECK_LAUNCH();
+        } else {
+          launch_hop_sample<ColT, CHUNKED>(c, c.csr[t], frontier, n_rows_dev + h, rows_ub, c.fanout[h * T + t], type_seed, pos_t[t], dest, erow, gid);
+        }
       }
       mh_mark(sp, hop_stage(sp, h, "sample"), st);
       // K3: insert (label, neighbour)
@@ -1214,6 +1311,14 @@ static void multihop_begin(MhCall& c)
       auto ss = scan_slice(edges_ub, kCompactTile);
       mh_compact_kernel<ColT, false><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, (unsigned int)(h + 1), dest, n_edges_dev + h, 0, erow, flabel, slot, rank_of, next_frontier, next_flabel, n_rows_dev + h + 1, ss.first, ticket_of(ss));
       WGB_CHECK_LAUNCH();
+      if (c.temporal) {
+        long long* next_ftime = static_cast<long long*>(ensure(sp->ftime[h + 1], sizeof(long long) * ecap));
+        MhTypePos tp;
+        for (int t = 0; t < kMaxEdgeTypes; t++)
+          tp.pos[t] = t < T ? pos_t[t] : nullptr;
+        mh_next_time_kernel<CHUNKED><<<grid_over(edges_ub, sms), 256, 0, st>>>(tdesc_dev, tp, n_edges_dev + h, slot, rank_of, erow, gid, next_ftime);
+        WGB_CHECK_LAUNCH();
+      }
       mh_mark(sp, hop_stage(sp, h, "compact"), st);
     } else {
       WGB_CUDA_TRY(cudaMemsetAsync(n_rows_dev + h + 1, 0, sizeof(int), st));
@@ -1472,7 +1577,11 @@ wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop
   for (int i = 0; i <= wgb::kMaxHops; i++) {
     drop(s->frontier[i]); drop(s->flabel[i]); drop(s->fr_off[i]); drop(s->tcnt[i]); drop(s->typed[i]);
   }
-  drop(s->vscan_state); drop(s->tbase); drop(s->desc_dev);
+  drop(s->vscan_state); drop(s->tbase); drop(s->desc_dev); drop(s->clipped); drop(s->tdesc_dev);
+  for (int i = 0; i <= wgb::kMaxHops; i++)
+    drop(s->ftime[i]);
+  for (int i = 0; i < wgb::kMaxHops; i++)
+    drop(s->eligible[i]);
   for (int i = 0; i < wgb::kMaxHops; i++) {
     drop(s->off[i]); drop(s->dest[i]); drop(s->erow[i]); drop(s->gid[i]); drop(s->slot[i]); drop(s->rank_of[i]); drop(s->pos[i]);
   }
@@ -1495,9 +1604,18 @@ static wholememory_error_code_t multihop_begin_entry(const char* what, wholegrap
                                                      const long long* vertex_type_offsets, int Vt, bool hetero,
                                                      wholememory_tensor_t seeds, wholememory_tensor_t label_offsets,
                                                      const int* fanout, int num_hops, unsigned long long random_state, int flags,
-                                                     void* stream)
+                                                     void* stream, const wholememory_tensor_t* csr_edge_time = nullptr,
+                                                     wholememory_tensor_t seed_times = nullptr, int time_cmp = 0)
 {
   if (!sampler || !csr_row_ptr || !csr_col || !seeds || !label_offsets || !fanout) return WHOLEMEMORY_INVALID_INPUT;
+  const bool temporal = csr_edge_time != nullptr;
+  if (temporal) {
+    if (!seed_times || time_cmp < kTimeStrictlyIncreasing || time_cmp > kTimeMonotonicallyDecreasing) return WHOLEMEMORY_INVALID_INPUT;
+    if (csr_weight != nullptr && csr_weight[0] != nullptr) return WHOLEMEMORY_NOT_IMPLEMENTED;  // biased temporal sampling
+    auto* td = wholememory_tensor_get_tensor_description(seed_times);
+    auto* s0 = wholememory_tensor_get_tensor_description(seeds);
+    if (td->dim != 1 || td->dtype != WHOLEMEMORY_DT_INT64 || td->sizes[0] != s0->sizes[0]) return WHOLEMEMORY_INVALID_INPUT;
+  }
   if (T < 1 || T > kMaxEdgeTypes || Vt < 1 || Vt > kMaxVertexTypes) return WHOLEMEMORY_INVALID_INPUT;
   if (num_hops < 1 || num_hops >= kMaxHops - 1) return WHOLEMEMORY_INVALID_INPUT;
   auto* sd = wholememory_tensor_get_tensor_description(seeds);
@@ -1523,6 +1641,11 @@ static wholememory_error_code_t multihop_begin_entry(const char* what, wholegrap
     if (csr_edge_id && csr_edge_id[t]) {
       auto* ed = wholememory_tensor_get_tensor_description(csr_edge_id[t]);
       if (ed->dim != 1 || ed->sizes[0] != cd->sizes[0] || ed->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
+    }
+    if (temporal) {
+      if (!csr_edge_time[t]) return WHOLEMEMORY_INVALID_INPUT;
+      auto* et = wholememory_tensor_get_tensor_description(csr_edge_time[t]);
+      if (et->dim != 1 || et->sizes[0] != cd->sizes[0] || et->dtype != WHOLEMEMORY_DT_INT64) return WHOLEMEMORY_INVALID_INPUT;
     }
   }
   for (int i = 0; i < num_hops * T; i++)
@@ -1558,6 +1681,12 @@ static wholememory_error_code_t multihop_begin_entry(const char* what, wholegrap
         g.wgt_off = (unsigned long long)wholememory_tensor_get_tensor_description(csr_weight[t])->storage_offset;
         c.chunked = c.chunked || g.wgt.world > 1;
       }
+      memset(&g.etime, 0, sizeof(g.etime));
+      if (temporal) {
+        g.etime     = make_chunk_ref(csr_edge_time[t]);
+        g.etime_off = (unsigned long long)wholememory_tensor_get_tensor_description(csr_edge_time[t])->storage_offset;
+        c.chunked   = c.chunked || g.etime.world > 1;
+      }
       g.has_eid = csr_edge_id && csr_edge_id[t];
       if (g.has_eid) {
         g.eid     = make_chunk_ref(csr_edge_id[t]);
@@ -1581,6 +1710,9 @@ static wholememory_error_code_t multihop_begin_entry(const char* what, wholegrap
     c.random_state = random_state;
     c.flags        = flags;
     c.stream       = as_stream(stream);
+    c.temporal     = temporal;
+    c.time_cmp     = time_cmp;
+    c.seed_times   = temporal ? static_cast<const long long*>(wholememory_tensor_get_data_pointer(seed_times)) : nullptr;
     if (c.col_dtype == WHOLEMEMORY_DT_INT) {
       if (c.chunked) multihop_begin<int, true>(c);
       else multihop_begin<int, false>(c);
@@ -1613,6 +1745,25 @@ wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_begin(
   return wgb::multihop_begin_entry("wholegraph_hetero_multihop_neighbor_sample_begin", sampler, num_edge_types, csr_row_ptr, csr_col,
                                    csr_weight, csr_edge_id, vertex_type_offsets, num_vertex_types, true, seeds, label_offsets, fanout,
                                    num_hops, random_state, flags, stream);
+}
+
+wholememory_error_code_t wholegraph_temporal_multihop_neighbor_sample_begin(
+  wholegraph_multihop_sampler_t sampler, int num_edge_types, const wholememory_tensor_t* csr_row_ptr,
+  const wholememory_tensor_t* csr_col, const wholememory_tensor_t* csr_edge_time, const wholememory_tensor_t* csr_edge_id,
+  const long long* vertex_type_offsets, int num_vertex_types, int heterogeneous, wholememory_tensor_t seeds,
+  wholememory_tensor_t seed_times, wholememory_tensor_t label_offsets, const int* fanout, int num_hops,
+  unsigned long long random_state, int time_comparison, int flags, void* stream)
+{
+  if (!csr_edge_time || !seed_times) return WHOLEMEMORY_INVALID_INPUT;
+  if (heterogeneous) {
+    if (flags & WHOLEGRAPH_MULTIHOP_CSR) return WHOLEMEMORY_INVALID_INPUT;
+  } else if (num_edge_types != 1) {
+    return WHOLEMEMORY_INVALID_INPUT;
+  }
+  return wgb::multihop_begin_entry("wholegraph_temporal_multihop_neighbor_sample_begin", sampler, num_edge_types, csr_row_ptr, csr_col,
+                                   nullptr, csr_edge_id, heterogeneous ? vertex_type_offsets : nullptr, heterogeneous ? num_vertex_types : 1,
+                                   heterogeneous != 0, seeds, label_offsets, fanout, num_hops, random_state, flags, stream, csr_edge_time,
+                                   seed_times, time_comparison);
 }
 
 wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_finish(

@@ -34,6 +34,7 @@ class GraphStore(GraphStoreBase):
         self.__graph = None
         self.__vertex_offsets = None
         self.__weight_attr = None
+        self.__time_attr = None
         self.__numeric_edge_types = None
         self.__num_vertices_cache = None
 
@@ -41,10 +42,10 @@ class GraphStore(GraphStoreBase):
         """Build the sampler graph now and drop the COO copies; the store becomes read-only."""
         if self.__finalized:
             raise RuntimeError("This GraphStore object has already been finalized.")
-        if time_attr is not None:
-            raise NotImplementedError("temporal sampling is outside the B200 hot path")
         if weight_attr is not None:
             self._set_weight_attr(weight_attr)
+        if time_attr is not None:
+            self._set_time_attr(time_attr)
         self.__construct_graph(finalize=True)
         self.__finalized = True
         return self
@@ -151,11 +152,25 @@ class GraphStore(GraphStoreBase):
 
     def _set_weight_attr(self, attr):
         if attr != self.__weight_attr:
+            time_attr = self.__time_attr
             self.__clear_graph()
             self.__weight_attr = attr
+            self.__time_attr = time_attr
 
     def _set_time_attr(self, attr):
-        raise NotImplementedError("temporal sampling is outside the B200 hot path")
+        """(feature_store, attribute name) of the EDGE times used by temporal sampling (reference :410-416, 621-629:
+        edge-based temporal sampling only)."""
+        if attr != self.__time_attr:
+            weight_attr = self.__weight_attr
+            self.__clear_graph()
+            self.__time_attr = attr
+            self.__weight_attr = weight_attr
+
+    def _get_ntime_func(self):
+        if self.__time_attr is None:
+            return None
+        fs, name = self.__time_attr
+        return lambda node_type, node_id: fs[node_type, name][node_id]
 
     @property
     def _numeric_edge_types(self):
@@ -173,7 +188,7 @@ class GraphStore(GraphStoreBase):
         keys = sorted(self.__edge_indices.keys())
         starts = dist_utils.edge_id_starts([self.__edge_indices[k].local_row.numel() for k in keys])
         offs = self._vertex_offsets
-        dst, src, eid, etp, wgt = [], [], [], [], []
+        dst, src, eid, etp, wgt, tme = [], [], [], [], [], []
         for i, k in enumerate(keys):
             m = self.__edge_indices[k]
             n = m.local_row.numel()
@@ -186,12 +201,21 @@ class GraphStore(GraphStoreBase):
                 w = fs[k, name, None]
                 ids = torch.arange(int(starts[i]), int(starts[i]) + n, device="cuda")
                 wgt.append(w[ids].reshape(-1).float() if n else torch.empty(0, device="cuda"))
+            if self.__time_attr is not None:
+                fs, name = self.__time_attr
+                tm = fs[k, name, None]
+                if tm is None:
+                    raise ValueError("Time property must be present for all edge types.")
+                ids = torch.arange(int(starts[i]), int(starts[i]) + n, device="cuda")
+                tme.append(tm[ids].reshape(-1).to(device="cuda", dtype=torch.int64) if n else torch.empty(0, dtype=torch.int64, device="cuda"))
         d = {"dst": torch.cat(dst) if dst else torch.empty(0, dtype=torch.int64, device="cuda"),
              "src": torch.cat(src) if src else torch.empty(0, dtype=torch.int64, device="cuda"),
              "eid": torch.cat(eid) if eid else torch.empty(0, dtype=torch.int64, device="cuda"),
              "etp": torch.cat(etp) if etp else torch.empty(0, dtype=torch.int32, device="cuda")}
         if wgt:
             d["wgt"] = torch.cat(wgt)
+        if tme:
+            d["etime"] = torch.cat(tme)
         return d
 
     def __construct_graph(self, finalize: bool = False):
@@ -206,7 +230,8 @@ class GraphStore(GraphStoreBase):
             props = pylibcugraph.GraphProperties(is_multigraph=True, is_symmetric=False)
             cls = pylibcugraph.MGGraph if self.is_multi_gpu else pylibcugraph.SGGraph
             self.__graph = cls(self._resource_handle, props, d["src"], d["dst"], weight_array=d.get("wgt"),
-                               edge_id_array=d["eid"], edge_type_array=d["etp"], num_vertices=num_vertices)
+                               edge_id_array=d["eid"], edge_type_array=d["etp"], num_vertices=num_vertices,
+                               edge_start_time_array=d.get("etime"))
         if finalize:
             for k in list(self.__edge_indices.keys()):
                 self.__edge_indices[k] = DistMatrix(None, shape=self.__sizes[k])

@@ -28,7 +28,7 @@ class LinkLoader:
         if neg_sampling_ratio is not None:
             warnings.warn("The 'neg_sampling_ratio' argument is deprecated in PyG and is not supported in cuGraph-PyG.")
         if edge_label_time is not None:
-            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+            raise NotImplementedError("temporal sampling from seed edges is not implemented (DESIGN.md §10)")
         neg_sampling = NegativeSampling.cast(neg_sampling)
         explicit = edge_label_index is not None
         if isinstance(edge_label_index, (list, tuple)):

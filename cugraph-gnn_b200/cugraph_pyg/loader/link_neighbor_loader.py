@@ -27,7 +27,7 @@ class LinkNeighborLoader(LinkLoader):
         if is_sorted:
             warnings.warn("The 'is_sorted' argument is ignored by cuGraph.")
         if time_attr is not None or edge_label_time is not None:
-            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+            raise NotImplementedError("temporal sampling from seed edges is not implemented (DESIGN.md §10)")
         if replace:
             raise NotImplementedError("sampling with replacement is outside the B200 hot path")
         if disjoint:

@@ -25,8 +25,15 @@ class NeighborLoader(NodeLoader):
             raise ValueError("Passing a neighbor sampler is currently unsupported")
         if is_sorted:
             warnings.warn("The 'is_sorted' argument is ignored by cuGraph.")
-        if time_attr is not None or input_time is not None:
-            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+        if temporal_strategy != "uniform":
+            warnings.warn("Only the uniform temporal strategy is currently supported")
+        if temporal_comparison is None:
+            temporal_comparison = "monotonically_decreasing"
+        is_temporal = time_attr is not None
+        if input_time is not None and not is_temporal:
+            raise ValueError("input_time needs time_attr (the name of the edge time attribute)")
+        if is_temporal and weight_attr is not None:
+            raise NotImplementedError("biased temporal sampling is not implemented (DESIGN.md §10)")
         if replace:
             raise NotImplementedError("sampling with replacement is outside the B200 hot path")
         if disjoint:
@@ -34,6 +41,16 @@ class NeighborLoader(NodeLoader):
         if not isinstance(data, (list, tuple)) or not isinstance(data[1], cugraph_pyg.data.GraphStore):
             raise NotImplementedError("Currently can't accept non-cugraph graphs")
         feature_store, graph_store = data
+        if is_temporal:
+            graph_store._set_time_attr((feature_store, time_attr))
+            if input_time is None:
+                # the time attribute is assumed to exist for the input nodes as well (reference :178-187)
+                from cugraph_pyg._pyg_compat import get_input_nodes
+
+                in_type, in_nodes, _ = get_input_nodes(data, input_nodes, None)
+                if in_type is None:
+                    in_type = list(graph_store._vertex_offsets.keys())[0]
+                input_time = feature_store[in_type, time_attr, None][in_nodes]
         if compression is None:
             compression = "CSR" if graph_store.is_homogeneous else "COO"
         elif compression not in ("CSR", "COO"):
@@ -65,7 +82,8 @@ class NeighborLoader(NodeLoader):
                 graph_store._graph, retain_original_seeds=True, fanout=num_neighbors, prior_sources_behavior="exclude",
                 deduplicate_sources=True, compression=compression, compress_per_hop=False, with_replacement=replace,
                 disjoint=disjoint, local_seeds_per_call=local_seeds_per_call, biased=(weight_attr is not None),
-                heterogeneous=heterogeneous, temporal=False, vertex_type_offsets=graph_store._vertex_offset_array,
+                heterogeneous=heterogeneous, temporal=is_temporal, temporal_comparison=temporal_comparison,
+                vertex_type_offsets=graph_store._vertex_offset_array,
                 num_edge_types=num_edge_types),
             (feature_store, graph_store), batch_size=batch_size)
         super().__init__((feature_store, graph_store), sampler, input_nodes=input_nodes, input_time=input_time,

@@ -38,7 +38,10 @@ class NodeLoader:
             input_nodes += data[1]._vertex_offsets[input_type]
         self.__input_data = NodeSamplerInput(
             input_id=torch.arange(len(input_nodes), dtype=torch.int64) if input_id is None else input_id,
-            node=input_nodes, time=input_time, input_type=input_type)
+            node=input_nodes, time=None if input_time is None else torch.as_tensor(input_time).reshape(-1),
+            input_type=input_type)
+        if self.__input_data.time is not None and self.__input_data.time.numel() != input_nodes.numel():
+            raise ValueError("input_time must have one entry per input node")
         self.__data = data
         self.__node_sampler = node_sampler
         self.__batch_size = batch_size
@@ -53,7 +56,9 @@ class NodeLoader:
         node = self.__input_data.node
         perm_dev = perm.to(node.device)
         input_data = NodeSamplerInput(input_id=self.__input_data.input_id[perm.to(self.__input_data.input_id.device)],
-                                      node=node[perm_dev], time=None, input_type=self.__input_data.input_type)
+                                      node=node[perm_dev],
+                                      time=None if self.__input_data.time is None else self.__input_data.time[perm.to(self.__input_data.time.device)],
+                                      input_type=self.__input_data.input_type)
         return cugraph_pyg.sampler.SampleIterator(
             self.__data, self.__node_sampler.sample_from_nodes(input_data, random_state=generate_seed()))
 

@@ -59,12 +59,12 @@ class BaseDistributedSampler:
         return dist_utils.batch_id_start(local_num_batches, assume_equal_input_size)
 
     def _call_group(self, seeds: torch.Tensor, index: torch.Tensor, batch_id_start: int, batch_size: int,
-                    random_state: int, metadata) -> Tuple[Dict[str, torch.Tensor], int, int]:
+                    random_state: int, metadata, times: Optional[torch.Tensor] = None) -> Tuple[Dict[str, torch.Tensor], int, int]:
         n = int(seeds.numel())
         num_full, last = divmod(n, batch_size)
         sizes = [batch_size] * num_full + ([last] if last else [])
         input_offsets = torch.tensor([0] + sizes, dtype=torch.int64).cumsum(0)
-        out = self.sample_batches(seeds=seeds, seed_times=None, batch_id_offsets=input_offsets.cuda(non_blocking=True),
+        out = self.sample_batches(seeds=seeds, seed_times=times, batch_id_offsets=input_offsets.cuda(non_blocking=True),
                                   random_state=random_state, metadata=metadata)
         out["input_index"] = index.cuda(non_blocking=True)
         out["input_offsets"] = input_offsets  # host: readers slice with python ints
@@ -78,10 +78,12 @@ class BaseDistributedSampler:
                           ) -> Iterator[Tuple[Dict[str, torch.Tensor], int, int]]:
         """Lazily yields (raw call-group dict, first batch id, last batch id)."""
         verify_metadata(metadata)
-        if input_time is not None:
-            raise NotImplementedError("temporal sampling is outside the B200 hot path")
         nodes = torch.as_tensor(nodes).cuda()
         num_seeds = int(nodes.numel())
+        if input_time is not None:
+            input_time = torch.as_tensor(input_time).reshape(-1).to(device=nodes.device, dtype=torch.int64)
+            if input_time.numel() != num_seeds:
+                raise ValueError("input_time must have one entry per input node")
         input_id = torch.arange(num_seeds, dtype=torch.int64) if input_id is None else torch.as_tensor(input_id).cpu()
         batches_per_call = max(1, self._local_seeds_per_call // batch_size)
         seeds_per_call = batches_per_call * batch_size
@@ -89,16 +91,18 @@ class BaseDistributedSampler:
         batch_id_start, equal = self.get_start_batch_offset(local_num_batches, assume_equal_input_size)
         seed_groups = list(torch.split(nodes, seeds_per_call))
         index_groups = list(torch.split(input_id, seeds_per_call))
+        time_groups = list(torch.split(input_time, seeds_per_call)) if input_time is not None else [None] * len(seed_groups)
         if self.is_multi_gpu and not equal:
             # every rank makes the same number of calls (uneven ranks sample empty groups)
             pad = dist_utils.equalized_call_count(len(seed_groups), equal) - len(seed_groups)
             seed_groups += [nodes[:0]] * pad
             index_groups += [input_id[:0]] * pad
+            time_groups += [None if input_time is None else input_time[:0]] * pad
 
         def gen():
             start = batch_id_start
-            for call_id, (s, ix) in enumerate(zip(seed_groups, index_groups)):
-                raw, first, last = self._call_group(s, ix, start, batch_size, random_state + call_id, metadata)
+            for call_id, (s, ix, tm) in enumerate(zip(seed_groups, index_groups, time_groups)):
+                raw, first, last = self._call_group(s, ix, start, batch_size, random_state + call_id, metadata, times=tm)
                 start = last + 1
                 yield raw, first, last
 
@@ -153,7 +157,7 @@ class BaseDistributedSampler:
         id, last batch id).  Role of the reference's distributed_sampler.py:428-726."""
         verify_metadata(metadata)
         if input_time is not None:
-            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+            raise NotImplementedError("temporal sampling from seed edges is not implemented (DESIGN.md §10)")
         edges = torch.as_tensor(edges).cuda()
         n = int(edges.shape[-1])
         input_id = torch.arange(n, dtype=torch.int64) if input_id is None else torch.as_tensor(input_id).cpu()
@@ -188,20 +192,23 @@ class DistributedNeighborSampler(BaseDistributedSampler):
                  compression: str = "COO", compress_per_hop: bool = False, with_replacement: bool = False,
                  disjoint: bool = False, biased: bool = False, heterogeneous: bool = False, temporal: bool = False,
                  temporal_comparison: Optional[str] = None, vertex_type_offsets=None, num_edge_types: int = 1):
-        if temporal:
-            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+        if temporal and biased:
+            raise NotImplementedError("biased temporal sampling is not implemented (DESIGN.md §10)")
         if num_edge_types > 1 and not heterogeneous:
             raise ValueError("Heterogeneous sampling must be selected if there is > 1 edge type.")
         self.__fanout = [int(f) for f in np.asarray(fanout).reshape(-1)]
         self.__heterogeneous = bool(heterogeneous)
         self.__num_edge_types = int(num_edge_types)
+        self.__temporal = bool(temporal)
         table = {
-            (False, False): pylibcugraph.homogeneous_uniform_neighbor_sample,
-            (False, True): pylibcugraph.homogeneous_biased_neighbor_sample,
-            (True, False): pylibcugraph.heterogeneous_uniform_neighbor_sample,
-            (True, True): pylibcugraph.heterogeneous_biased_neighbor_sample,
+            (False, False, False): pylibcugraph.homogeneous_uniform_neighbor_sample,
+            (False, True, False): pylibcugraph.homogeneous_biased_neighbor_sample,
+            (True, False, False): pylibcugraph.heterogeneous_uniform_neighbor_sample,
+            (True, True, False): pylibcugraph.heterogeneous_biased_neighbor_sample,
+            (False, False, True): pylibcugraph.homogeneous_uniform_temporal_neighbor_sample,
+            (True, False, True): pylibcugraph.heterogeneous_uniform_temporal_neighbor_sample,
         }
-        self.__func = table[(self.__heterogeneous, bool(biased))]
+        self.__func = table[(self.__heterogeneous, bool(biased), self.__temporal)]
         self.__func_kwargs = {
             "h_fan_out": np.asarray(self.__fanout, dtype="int32"),
             "prior_sources_behavior": prior_sources_behavior,
@@ -212,6 +219,9 @@ class DistributedNeighborSampler(BaseDistributedSampler):
             "with_replacement": with_replacement,
             "disjoint_sampling": disjoint,
         }
+        if temporal:
+            self.__func_kwargs["temporal_property_name"] = "time"
+            self.__func_kwargs["temporal_sampling_comparison"] = temporal_comparison or "monotonically_decreasing"
         if heterogeneous:
             if vertex_type_offsets is None:
                 raise ValueError("Heterogeneous sampling requires vertex type offsets.")
@@ -253,6 +263,10 @@ class DistributedNeighborSampler(BaseDistributedSampler):
         kwargs.update(self.__func_kwargs)
         if return_seed_local_ids:
             kwargs["return_seed_local_ids"] = True
+        if seed_times is not None:
+            if not self.__temporal:
+                raise ValueError("seed times were given to a sampler that was built with temporal=False")
+            kwargs["starting_vertex_times"] = seed_times
         out = self.__func(**kwargs)
         out["fanout"] = torch.tensor(self.__fanout, dtype=torch.int32)
         out["rank"] = rank

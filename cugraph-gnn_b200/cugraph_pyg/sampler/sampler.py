@@ -275,7 +275,7 @@ class BaseSampler:
         the whole epoch at once and interleaved batch by batch; negatives carry input id -1."""
         src, dst, input_id = index.row, index.col, index.input_id
         if index.time is not None:
-            raise NotImplementedError("temporal sampling is outside the B200 hot path")
+            raise NotImplementedError("temporal sampling from seed edges is not implemented (DESIGN.md §10)")
         neg_batch_size = 0
         if neg_sampling:
             src_neg, dst_neg = neg_sample(self.__graph_store, index.row, index.col, index.input_type, self.__batch_size, neg_sampling)

@@ -66,7 +66,7 @@ def neg_sample(graph_store, seed_src, seed_dst, input_type, batch_size: int, neg
     import pylibcugraph
 
     if node_time_func is not None:
-        raise NotImplementedError("temporal negative sampling is outside the B200 hot path")
+        raise NotImplementedError("temporal negative sampling is not implemented (DESIGN.md §10)")
     src_weight = getattr(neg_sampling, "src_weight", getattr(neg_sampling, "weight", None))
     dst_weight = getattr(neg_sampling, "dst_weight", getattr(neg_sampling, "weight", None))
     num_neg = max(int(ceil(neg_sampling.amount * seed_src.numel())), int(ceil(seed_src.numel() / batch_size)))

@@ -13,7 +13,9 @@ Differences that callers can observe:
   * the random stream is this project's (S1/S2 geometry per hop), not libcugraph's -- unverifiable either way;
   * heterogeneous sampling keeps one CSR per edge type (built lazily from edge_type_array) and follows the definition in
     include/wholememory/b200_ops.h: edge_id indexes edge_renumber_map per (label, edge type);
-  * with_replacement=True, disjoint_sampling=True and temporal sampling raise NotImplementedError.
+  * temporal sampling (edge_start_time_array + the *_uniform_temporal_* entry points) follows the definition in
+    include/wholememory/b200_ops.h; the biased temporal entry points raise NotImplementedError;
+  * with_replacement=True and disjoint_sampling=True raise NotImplementedError.
 """
 from typing import Optional
 
@@ -59,8 +61,8 @@ class SGGraph:
                  edge_type_array=None, input_array_format="COO", vertices_array=None, drop_self_loops=False,
                  drop_multi_edges=False, symmetrize=False, edge_start_time_array=None, edge_end_time_array=None,
                  num_vertices: Optional[int] = None):
-        if edge_start_time_array is not None or edge_end_time_array is not None:
-            raise NotImplementedError("temporal graphs are outside the B200 hot path")
+        if edge_end_time_array is not None:
+            raise NotImplementedError("edge end times are not supported (cugraph-pyg passes start times only)")
         if drop_self_loops or drop_multi_edges or symmetrize or renumber or store_transposed:
             raise NotImplementedError("graph transformations are not supported; pass the final COO")
         self.properties = graph_properties
@@ -93,6 +95,7 @@ class SGGraph:
             self.edge_id = order  # position in the caller's COO
         self.edge_type = pick(edge_type_array, torch.int32)
         self.weight = pick(weight_array)
+        self.edge_time = pick(edge_start_time_array, torch.int64)
         if self.weight is not None and self.weight.dtype not in (torch.float32, torch.float64):
             self.weight = self.weight.float()
         self._sampler = None
@@ -105,7 +108,7 @@ class SGGraph:
             if self.edge_type is None:
                 if num_edge_types != 1:
                     raise ValueError("the graph was built without edge_type_array")
-                self._typed[num_edge_types] = [(self.row_ptr, self.col, self.weight, self.edge_id)]
+                self._typed[num_edge_types] = [(self.row_ptr, self.col, self.weight, self.edge_id, self.edge_time)]
             else:
                 deg = self.row_ptr[1:] - self.row_ptr[:-1]
                 rows = torch.repeat_interleave(torch.arange(self.num_vertices, device=self.col.device), deg)
@@ -117,7 +120,8 @@ class SGGraph:
                         rp[1:] = torch.bincount(rows[sel], minlength=self.num_vertices).cumsum(0)
                     out.append((rp, self.col[sel].contiguous(),
                                 None if self.weight is None else self.weight[sel].contiguous(),
-                                None if self.edge_id is None else self.edge_id[sel].contiguous()))
+                                None if self.edge_id is None else self.edge_id[sel].contiguous(),
+                                None if self.edge_time is None else self.edge_time[sel].contiguous()))
                 self._typed[num_edge_types] = out
         return self._typed[num_edge_types]
 
@@ -148,7 +152,7 @@ class SGGraph:
     def _biased_csrs(self, num_edge_types: int):
         key = ("biased", num_edge_types)
         if key not in self._typed:
-            self._typed[key] = [self._drop_zero_weight(*g) for g in self._typed_csrs(num_edge_types)]
+            self._typed[key] = [self._drop_zero_weight(*g[:4]) for g in self._typed_csrs(num_edge_types)]
         return self._typed[key]
 
     def _get_sampler(self):
@@ -167,7 +171,7 @@ class MGGraph(SGGraph):
 
     def __init__(self, resource_handle, graph_properties, src_array, dst_array, weight_array=None, store_transposed=False,
                  do_expensive_check=False, edge_id_array=None, edge_type_array=None, vertices_array=None, num_arrays=1,
-                 size=None, **kwargs):
+                 size=None, edge_start_time_array=None, **kwargs):
         import torch.distributed as dist
 
         def gather(a, dtype=None):
@@ -194,7 +198,8 @@ class MGGraph(SGGraph):
             nv = int(v.max()) + 1 if v.numel() else 0
         super().__init__(resource_handle, graph_properties, gather(src_array, torch.int64), gather(dst_array, torch.int64),
                          weight_array=gather(weight_array), edge_id_array=gather(edge_id_array, torch.int64),
-                         edge_type_array=gather(edge_type_array, torch.int32), num_vertices=nv, **kwargs)
+                         edge_type_array=gather(edge_type_array, torch.int32), num_vertices=nv,
+                         edge_start_time_array=gather(edge_start_time_array, torch.int64), **kwargs)
 
 
 def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, biased, *,
@@ -332,17 +337,107 @@ def heterogeneous_biased_neighbor_sample(resource_handle, input_graph, start_ver
                                    vertex_type_offsets, True, **kwargs)
 
 
+def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, *, heterogeneous,
+                              num_edge_types=1, vertex_type_offsets=None, starting_vertex_times=None,
+                              temporal_property_name=None, temporal_sampling_comparison="strictly_increasing",
+                              with_replacement=False, do_expensive_check=False, prior_sources_behavior=None,
+                              deduplicate_sources=False, return_hops=False, renumber=False, retain_seeds=False,
+                              compression="COO", compress_per_hop=False, random_state=None, disjoint_sampling=False,
+                              return_dict=True, return_seed_local_ids=False, **unused):
+    """pylibcugraph.{homogeneous,heterogeneous}_uniform_temporal_neighbor_sample (reference call site:
+    python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:56-80, 808-810, 897-900).  Edge times are the graph's
+    edge_start_time_array; without starting_vertex_times the first hop is unconstrained."""
+    if with_replacement:
+        raise NotImplementedError("sampling with replacement is not on the B200 hot path")
+    if disjoint_sampling:
+        raise NotImplementedError("disjoint sampling is not on the B200 hot path")
+    if compress_per_hop or (heterogeneous and compression != "COO"):
+        raise NotImplementedError("compress_per_hop / heterogeneous CSR output are not supported")
+    if not renumber:
+        raise NotImplementedError("the fused sampler always renumbers (cugraph-pyg calls with renumber=True)")
+    if prior_sources_behavior not in (None, "exclude") or (prior_sources_behavior is None and deduplicate_sources is False):
+        raise NotImplementedError("only deduplicate_sources=True with prior_sources_behavior='exclude' is supported")
+    if input_graph.edge_time is None:
+        raise ValueError("temporal sampling needs a graph built with edge_start_time_array")
+    from pylibwholegraph.torch.multihop import TIME_COMPARISONS
+
+    if temporal_sampling_comparison not in TIME_COMPARISONS:
+        raise ValueError("temporal_sampling_comparison must be one of %s" % sorted(TIME_COMPARISONS))
+    seeds = _as_cuda(start_vertex_list)
+    if seeds.dtype not in (torch.int32, torch.int64):
+        seeds = seeds.long()
+    if starting_vertex_label_offsets is None:
+        offsets = torch.tensor([0, seeds.numel()], dtype=torch.int64, device=seeds.device)
+    else:
+        offsets = _as_cuda(starting_vertex_label_offsets, torch.int64)
+    if starting_vertex_times is None:
+        info = torch.iinfo(torch.int64)
+        open_end = info.min if "increasing" in temporal_sampling_comparison else info.max
+        times = torch.full((seeds.numel(),), open_end, dtype=torch.int64, device=seeds.device)
+    else:
+        times = _as_cuda(starting_vertex_times, torch.int64)
+        if times.numel() != seeds.numel():
+            raise ValueError("starting_vertex_times must have one entry per start vertex")
+    fanout = [int(f) for f in np.asarray(h_fan_out).reshape(-1)]
+    T = int(num_edge_types) if heterogeneous else 1
+    if T < 1 or len(fanout) % T != 0:
+        raise ValueError(f"Illegal fanout for {T} edge types.")
+    if random_state is None:
+        random_state = int(np.random.randint(0, 2**62))
+    typed = input_graph._typed_csrs(T) if heterogeneous else [(input_graph.row_ptr, input_graph.col, None, input_graph.edge_id,
+                                                               input_graph.edge_time)]
+    vto = None
+    if heterogeneous:
+        vto = [int(v) for v in torch.as_tensor(vertex_type_offsets).reshape(-1).tolist()]
+    pend = input_graph._get_sampler().sample_temporal_async(
+        [g[0] for g in typed], [g[1] for g in typed], [g[4] for g in typed], seeds, times, offsets, fanout, int(random_state),
+        temporal_sampling_comparison, vertex_type_offsets=vto,
+        csr_edge_ids=[g[3] for g in typed] if all(g[3] is not None for g in typed) else None,
+        compression=compression, int64_ids=True)
+    pend.want_seed_local_ids = bool(return_seed_local_ids)
+    res = pend.result()
+    extra = {"seed_local_ids": res["seed_local_ids"]} if return_seed_local_ids else {}
+    if heterogeneous:
+        return {
+            **extra,
+            "majors": res["majors"], "minors": res["minors"], "major_offsets": None, "edge_id": res["edge_id"],
+            "edge_type": res["edge_type"], "weight": None, "hop_id": None, "renumber_map": res["renumber_map"],
+            "renumber_map_offsets": res["renumber_map_offsets"], "label_type_hop_offsets": res["label_type_hop_offsets"],
+            "edge_renumber_map": res["edge_renumber_map"], "edge_renumber_map_offsets": res["edge_renumber_map_offsets"],
+            "label_type_step_base": res["label_type_step_base"],
+        }
+    return {
+        **extra,
+        "majors": res.get("majors"), "minors": res["minors"], "major_offsets": res.get("major_offsets"),
+        "edge_id": res["edge_id"], "edge_type": None, "weight": None, "hop_id": None, "renumber_map": res["renumber_map"],
+        "renumber_map_offsets": res["renumber_map_offsets"], "label_hop_offsets": res["label_hop_offsets"],
+        "label_step_base": res["label_step_base"],
+    }
+
+
+def homogeneous_uniform_temporal_neighbor_sample(resource_handle, input_graph, start_vertex_list,
+                                                 starting_vertex_label_offsets, h_fan_out, **kwargs):
+    return _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out,
+                                     heterogeneous=False, **kwargs)
+
+
+def heterogeneous_uniform_temporal_neighbor_sample(resource_handle, input_graph, start_vertex_list,
+                                                   starting_vertex_label_offsets, vertex_type_offsets=None, h_fan_out=None,
+                                                   num_edge_types=1, **kwargs):
+    return _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out,
+                                     heterogeneous=True, num_edge_types=num_edge_types, vertex_type_offsets=vertex_type_offsets,
+                                     **kwargs)
+
+
 def _not_on_path(name):
     def fn(*args, **kwargs):
-        raise NotImplementedError(f"pylibcugraph.{name} is outside the B200 hot path (SURVEY.md §8: homogeneous node sampling)")
+        raise NotImplementedError(f"pylibcugraph.{name}: biased temporal sampling is not implemented (DESIGN.md §10)")
 
     fn.__name__ = name
     return fn
 
 
-homogeneous_uniform_temporal_neighbor_sample = _not_on_path("homogeneous_uniform_temporal_neighbor_sample")
 homogeneous_biased_temporal_neighbor_sample = _not_on_path("homogeneous_biased_temporal_neighbor_sample")
-heterogeneous_uniform_temporal_neighbor_sample = _not_on_path("heterogeneous_uniform_temporal_neighbor_sample")
 heterogeneous_biased_temporal_neighbor_sample = _not_on_path("heterogeneous_biased_temporal_neighbor_sample")
 
 

@@ -40,6 +40,16 @@ _hfinish = wmb.native_symbol("wholegraph_hetero_multihop_neighbor_sample_finish"
 _hfinish.restype = ctypes.c_int
 _hfinish.argtypes = [_vp] * 13
 
+_tbegin = wmb.native_symbol("wholegraph_temporal_multihop_neighbor_sample_begin")
+_tbegin.restype = ctypes.c_int
+_tbegin.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                    ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int),
+                    ctypes.c_int, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int, _vp]
+
+# pylibcugraph's temporal_sampling_comparison strings -> time_comparison of the C call (include/wholememory/b200_ops.h)
+TIME_COMPARISONS = {"strictly_increasing": 0, "monotonically_increasing": 1, "strictly_decreasing": 2,
+                    "monotonically_decreasing": 3}
+
 _seed_ids = wmb.native_symbol("wholegraph_multihop_seed_local_ids")
 _seed_ids.restype = ctypes.c_int
 _seed_ids.argtypes = [_vp, _vp, _vp, _vp]
@@ -140,6 +150,58 @@ class MultiHopSampler(object):
                       ctypes.c_ulonglong(random_state & 0xFFFFFFFFFFFFFFFF), FLAG_INT64_IDS if int64_ids else 0, get_stream())
         wmb.check_wholememory_error_code(err)
         return PendingHeteroSample(self, keep, hops, len(vto) - 1)
+
+    def sample_temporal_async(self, csr_row_ptrs, csr_cols, csr_edge_times, seeds: "torch.Tensor", seed_times: "torch.Tensor",
+                              label_offsets: "torch.Tensor", fanout: List[int], random_state: int, comparison: str, *,
+                              vertex_type_offsets=None, csr_edge_ids=None, compression: str = "COO", int64_ids: bool = False):
+        """Temporal call group (include/wholememory/b200_ops.h: wholegraph_temporal_multihop_neighbor_sample_begin).
+        ``csr_edge_times[t]`` int64 per edge type in CSR order, ``seed_times`` int64 [S], ``comparison`` one of
+        TIME_COMPARISONS.  ``vertex_type_offsets`` given: heterogeneous arguments and result (PendingHeteroSample);
+        None: one edge type, homogeneous result (PendingSample)."""
+        assert seeds.is_cuda and seeds.dim() == 1 and seeds.dtype in (torch.int32, torch.int64)
+        if comparison not in TIME_COMPARISONS:
+            raise ValueError("temporal comparison must be one of %s, got %r" % (sorted(TIME_COMPARISONS), comparison))
+        label_offsets = label_offsets.to(device=seeds.device, dtype=torch.int64)
+        seed_times = seed_times.to(device=seeds.device, dtype=torch.int64).contiguous()
+        assert seed_times.shape == seeds.shape
+        hetero = vertex_type_offsets is not None
+        T = len(csr_row_ptrs)
+        assert T >= 1 and len(csr_cols) == T and len(csr_edge_times) == T and len(fanout) % T == 0
+        assert hetero or T == 1, "more than one edge type needs vertex_type_offsets"
+        assert compression in ("COO", "CSR") and not (hetero and compression == "CSR")
+        csr = compression == "CSR"
+        keep = []
+
+        def handle_array(ts):
+            if ts is None:
+                return None
+            arr = (_vp * T)()
+            for i, t in enumerate(ts):
+                h, k = _handle(t)
+                arr[i] = h
+                keep.append(k)
+            return arr
+
+        rp, col, tim = handle_array(csr_row_ptrs), handle_array(csr_cols), handle_array(csr_edge_times)
+        eid = handle_array(csr_edge_ids)
+        hs, ks = _handle(seeds)
+        ht, kt = _handle(seed_times)
+        hl, kl = _handle(label_offsets)
+        keep += [ks, kt, kl]
+        vto = [int(v) for v in vertex_type_offsets] if hetero else [0, 0]
+        vto_c = (ctypes.c_longlong * len(vto))(*vto)
+        fan = (ctypes.c_int * len(fanout))(*[int(f) for f in fanout])
+        hops = len(fanout) // T
+        flags = (FLAG_CSR if csr else 0) | (FLAG_INT64_IDS if int64_ids else 0)
+        err = _tbegin(self._h, T, rp, col, tim, eid, vto_c, len(vto) - 1, 1 if hetero else 0, hs, ht, hl, fan, hops,
+                      ctypes.c_ulonglong(random_state & 0xFFFFFFFFFFFFFFFF), TIME_COMPARISONS[comparison], flags, get_stream())
+        wmb.check_wholememory_error_code(err)
+        if hetero:
+            return PendingHeteroSample(self, keep, hops, len(vto) - 1)
+        return PendingSample(self, keep, csr, hops)
+
+    def sample_temporal(self, *args, **kwargs):
+        return self.sample_temporal_async(*args, **kwargs).result()
 
     def sample_hetero(self, *args, **kwargs):
         """Returns a dict with majors, minors, edge_id, edge_type, label_type_hop_offsets, renumber_map,

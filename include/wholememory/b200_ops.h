@@ -177,6 +177,42 @@ wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_finish(whole
                                                                            wholememory_env_func_t* p_env_fns,
                                                                            void* stream);
 
+/* Temporal form: what cugraph-pyg asks of pylibcugraph.{homogeneous,heterogeneous}_uniform_temporal_neighbor_sample
+ * (/root/reference/python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:56-80, 808-810, 897-900; behaviour
+ * pinned by /root/reference/python/cugraph-pyg/cugraph_pyg/tests/loader/test_neighbor_loader.py:943-1058).
+ *
+ *   csr_edge_time[t]   int64 [E_t], the time of every edge of type t, in CSR order (required, one per edge type)
+ *   seed_times         int64 [S] local device tensor, starting time of every seed (first occurrence wins for a repeated seed)
+ *   time_comparison    0 strictly increasing, 1 monotonically increasing, 2 strictly decreasing, 3 monotonically
+ *                      decreasing: an edge of a frontier vertex is eligible iff its time compares so with the vertex's
+ *                      time; a sampled vertex takes the time of the edge that reached it first
+ *   heterogeneous      != 0: arguments and outputs of the heterogeneous form, finish with
+ *                      wholegraph_hetero_multihop_neighbor_sample_finish; 0: num_edge_types must be 1,
+ *                      vertex_type_offsets is ignored, finish with wholegraph_multihop_neighbor_sample_finish
+ *   The uniform one-hop algorithm runs over the eligible edges of a row in CSR order with the plain sampler's random
+ *   streams: with every edge eligible the call returns exactly what the non-temporal call returns.
+ *   Biased temporal sampling is not implemented.
+ *   STATUS: compiled for sm_100a, not yet run on a GPU.
+ */
+wholememory_error_code_t wholegraph_temporal_multihop_neighbor_sample_begin(wholegraph_multihop_sampler_t sampler,
+                                                                            int num_edge_types,
+                                                                            const wholememory_tensor_t* csr_row_ptr,
+                                                                            const wholememory_tensor_t* csr_col,
+                                                                            const wholememory_tensor_t* csr_edge_time,
+                                                                            const wholememory_tensor_t* csr_edge_id,
+                                                                            const long long* vertex_type_offsets,
+                                                                            int num_vertex_types,
+                                                                            int heterogeneous,
+                                                                            wholememory_tensor_t seeds,
+                                                                            wholememory_tensor_t seed_times,
+                                                                            wholememory_tensor_t label_offsets,
+                                                                            const int* fanout,
+                                                                            int num_hops,
+                                                                            unsigned long long random_state,
+                                                                            int time_comparison,
+                                                                            int flags,
+                                                                            void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Replicated hot rows: a read-only copy of the given rows of a WholeMemory embedding on THIS GPU.
  * wholememory_embedding_gather then serves those rows locally instead of from the owning rank (same bytes out, bit

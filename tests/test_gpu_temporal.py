@@ -1,0 +1,188 @@
+"""S0 temporal: wholegraph_temporal_multihop_neighbor_sample_begin against the oracle (bit-exact), the reference's
+deterministic pins (tests/loader/test_neighbor_loader.py:943-1058) and the "open window = plain sampling" identity.
+
+The temporal path was written after this round's GPU budget was spent: it is compiled and exported,
+but has not run on a GPU yet, so these tests only run when WGB_RUN_UNVERIFIED=1.  First thing next round:
+    WGB_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_temporal.py -m gpu -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+from graphs import random_typed_graph
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("WGB_RUN_UNVERIFIED") != "1",
+                                 reason="temporal path not yet verified on a GPU; set WGB_RUN_UNVERIFIED=1 to run")]
+
+HETERO_KEYS = ("label_type_hop_offsets", "renumber_map_offsets", "renumber_map", "majors", "minors", "edge_id", "edge_type",
+               "edge_renumber_map", "edge_renumber_map_offsets", "label_type_step_base")
+COMPARISONS = ("strictly_increasing", "monotonically_increasing", "strictly_decreasing", "monotonically_decreasing")
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    import pylibwholegraph.torch as wgth
+
+    torch.cuda.set_device(0)
+    wgth.init(0, 1, 0, 1)
+    return wgth, wgth.get_global_communicator(), wgth.MultiHopSampler()
+
+
+def _dev(arrs):
+    import torch
+
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
+
+
+def _assert_equal(got, exp, keys=HETERO_KEYS):
+    for k in keys:
+        g = got[k].cpu().numpy()
+        assert g.shape == exp[k].shape, (k, g.shape, exp[k].shape)
+        assert np.array_equal(g, exp[k]), k
+
+
+@pytest.mark.parametrize("comparison", COMPARISONS)
+@pytest.mark.parametrize("fanout", [[3, 2, 4, 2, 2, 2], [-1, 3, 0, 2, -1, 1], [5, 5, 5], [0, 0, 0, 4, 4, 4], [2, 40, 1], [33, 70, 8, 3, 3, 3]])
+@pytest.mark.parametrize("col_dtype", [np.int32, np.int64])
+def test_temporal_hetero_bit_exact_vs_oracle(env, oracle, comparison, fanout, col_dtype):
+    import torch
+
+    wgth, comm, sampler = env
+    edge_types = [(0, 1), (1, 0), (1, 1)]
+    vto, row_ptrs, cols = random_typed_graph([700, 1500], edge_types, [9000, 14000, 60000], seed=len(fanout), col_dtype=col_dtype)
+    rng = np.random.default_rng(4)
+    times = [rng.integers(0, 50, c.shape[0]).astype(np.int64) for c in cols]
+    eids = [rng.permutation(c.shape[0]).astype(np.int64) + 1000000 * t for t, c in enumerate(cols)]
+    seeds = np.concatenate([rng.integers(0, 2200, 60), rng.integers(700, 2200, 33), rng.integers(0, 700, 1)]).astype(np.int64)
+    seeds[7] = seeds[3]  # a repeated seed inside a label: the first occurrence's time counts
+    lo = np.array([0, 60, 60, 93, 94], dtype=np.int64)
+    mid = 10 if "increasing" in comparison else 40
+    seed_times = (mid + rng.integers(-5, 6, seeds.shape[0])).astype(np.int64)
+    d_rp, d_col, d_tm, d_eid = _dev(row_ptrs), _dev(cols), _dev(times), _dev(eids)
+    for rep in range(2):
+        got = sampler.sample_temporal(d_rp, d_col, d_tm, torch.from_numpy(seeds).cuda(), torch.from_numpy(seed_times).cuda(),
+                                      torch.from_numpy(lo).cuda(), fanout, 31 + rep, comparison, vertex_type_offsets=vto.tolist(),
+                                      csr_edge_ids=d_eid)
+        exp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, seed_times, lo, fanout, 31 + rep, comparison, edge_ids=eids)
+        assert exp["majors"].shape[0] > 0
+        _assert_equal(got, exp)
+
+
+@pytest.mark.parametrize("fanout", [[4, 3], [40, 5], [-1, 2]])
+def test_temporal_homogeneous_matches_oracle(env, oracle, fanout):
+    """One edge type through the homogeneous finish: COO output against the oracle's T = 1, Vt = 1 result."""
+    import torch
+
+    wgth, comm, sampler = env
+    vto, row_ptrs, cols = random_typed_graph([3000], [(0, 0)], [90000], seed=11)
+    rng = np.random.default_rng(1)
+    times = [rng.integers(0, 1000, cols[0].shape[0]).astype(np.int64)]
+    seeds = rng.integers(0, 3000, 200).astype(np.int64)
+    seed_times = rng.integers(300, 700, 200).astype(np.int64)
+    lo = np.array([0, 64, 128, 200], dtype=np.int64)
+    got = sampler.sample_temporal(_dev(row_ptrs), _dev(cols), _dev(times), torch.from_numpy(seeds).cuda(),
+                                  torch.from_numpy(seed_times).cuda(), torch.from_numpy(lo).cuda(), fanout, 62, "monotonically_decreasing")
+    exp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, seed_times, lo, fanout, 62, "monotonically_decreasing")
+    L, B = len(fanout), 3
+    assert np.array_equal(got["majors"].cpu().numpy(), exp["majors"])
+    assert np.array_equal(got["minors"].cpu().numpy(), exp["minors"])
+    assert np.array_equal(got["edge_id"].cpu().numpy(), exp["edge_renumber_map"])  # homogeneous edge_id = original edge id
+    assert np.array_equal(got["renumber_map"].cpu().numpy(), exp["renumber_map"])
+    assert np.array_equal(got["renumber_map_offsets"].cpu().numpy(), exp["renumber_map_offsets"])
+    assert np.array_equal(got["label_hop_offsets"].cpu().numpy(), exp["label_type_hop_offsets"])
+    assert np.array_equal(got["label_step_base"].cpu().numpy(), exp["label_type_step_base"].reshape(L + 1, B))
+    # hop-0 edges respect the comparison with their seed's time (majors of hop 0 are seed-local ids in first-occurrence order)
+    lho = exp["label_type_hop_offsets"]
+    for l in range(B):
+        uniq = list(dict.fromkeys(seeds[lo[l]:lo[l + 1]].tolist()))
+        first_time = {v: seed_times[lo[l] + seeds[lo[l]:lo[l + 1]].tolist().index(v)] for v in uniq}
+        a, b = lho[l * L], lho[l * L + 1]
+        maj = got["majors"].cpu().numpy()[a:b]
+        eid = got["edge_id"].cpu().numpy()[a:b]
+        assert all(times[0][e] <= first_time[uniq[m]] for m, e in zip(maj, eid))
+
+
+def test_temporal_open_window_equals_plain_sampling(env):
+    """With every edge eligible the temporal kernels must return exactly what the plain kernels return (same streams,
+    same order) -- at a size the oracle would not finish quickly."""
+    import torch
+
+    wgth, comm, sampler = env
+    edge_types = [(0, 1), (1, 0)]
+    vto, row_ptrs, cols = random_typed_graph([20000, 30000], edge_types, [600000, 900000], seed=6)
+    times = [np.ones(c.shape[0], dtype=np.int64) for c in cols]
+    rng = np.random.default_rng(0)
+    seeds = rng.integers(0, 50000, 4096).astype(np.int64)
+    lo = np.arange(0, 4097, 256, dtype=np.int64)
+    d_rp, d_col, d_tm = _dev(row_ptrs), _dev(cols), _dev(times)
+    d_seeds, d_lo = torch.from_numpy(seeds).cuda(), torch.from_numpy(lo).cuda()
+    for fanout in ([10, 10, 5, 5], [40, 3, 2, 2], [-1, 2, 1, 1]):
+        plain = sampler.sample_hetero(d_rp, d_col, vto.tolist(), d_seeds, d_lo, fanout, 5)
+        temp = sampler.sample_temporal(d_rp, d_col, d_tm, d_seeds, torch.ones(4096, dtype=torch.int64).cuda(), d_lo, fanout, 5,
+                                       "monotonically_increasing", vertex_type_offsets=vto.tolist())
+        for k in HETERO_KEYS:
+            assert torch.equal(plain[k], temp[k]), (fanout, k)
+
+
+def test_temporal_rejects_bad_arguments(env):
+    import torch
+
+    wgth, comm, sampler = env
+    vto, row_ptrs, cols = random_typed_graph([50], [(0, 0)], [300], seed=2)
+    d_rp, d_col = _dev(row_ptrs), _dev(cols)
+    tm = [torch.zeros(300, dtype=torch.int64).cuda()]
+    seeds, lo = torch.arange(10).cuda(), torch.tensor([0, 10]).cuda()
+    with pytest.raises(ValueError):
+        sampler.sample_temporal(d_rp, d_col, tm, seeds, torch.zeros(10, dtype=torch.int64).cuda(), lo, [2], 1, "sometimes")
+    with pytest.raises(Exception):  # edge times shorter than the edge list
+        sampler.sample_temporal(d_rp, d_col, [tm[0][:100]], seeds, torch.zeros(10, dtype=torch.int64).cuda(), lo, [2], 1, "strictly_increasing")
+
+
+def test_temporal_loader_reference_pin_homogeneous():
+    """tests/loader/test_neighbor_loader.py:943-990 (uniform variant) through GraphStore / NeighborLoader."""
+    import torch
+    import cugraph_pyg
+    from cugraph_pyg.data import GraphStore, FeatureStore
+
+    src_cite, dst_cite, tme_cite = torch.tensor([3, 2, 1, 2]), torch.tensor([2, 1, 0, 0]), torch.tensor([0, 1, 2, 0])
+    graph_store, feature_store = GraphStore(), FeatureStore()
+    graph_store[("paper", "cites", "paper"), "coo", False, (4, 4)] = [dst_cite, src_cite]
+    feature_store[("paper", "cites", "paper"), "time", None] = tme_cite
+    loader = cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors=[2, 2, 2], batch_size=1,
+                                               input_nodes=torch.tensor([3]), input_time=torch.tensor([-1]), time_attr="time",
+                                               shuffle=False, temporal_comparison="strictly_increasing")
+    out = next(iter(loader))
+    assert out.n_id.tolist() == [3, 2, 1, 0]
+    assert out.e_id.tolist() == [0, 1, 2]
+    assert out.num_sampled_nodes.tolist() == [1, 1, 1, 1]
+    assert out.num_sampled_edges.tolist() == [1, 1, 1]
+
+
+def test_temporal_loader_reference_pin_heterogeneous():
+    """tests/loader/test_neighbor_loader.py:993-1058 (uniform variant)."""
+    import torch
+    import cugraph_pyg
+    from cugraph_pyg.data import GraphStore, FeatureStore
+
+    src_cite, dst_cite, tme_cite = torch.tensor([3, 2, 1, 2]), torch.tensor([2, 1, 0, 0]), torch.tensor([0, 1, 2, 0])
+    src_author = torch.tensor([3, 2, 2, 1, 3, 2, 0])
+    dst_author = torch.tensor([0, 0, 1, 1, 2, 2, 2])
+    tme_author = torch.tensor([0, 0, 1, 0, 2, 1, 1])
+    graph_store, feature_store = GraphStore(), FeatureStore()
+    graph_store[("paper", "cites", "paper"), "coo", False, (4, 4)] = [dst_cite, src_cite]
+    graph_store[("author", "writes", "paper"), "coo", False, (3, 4)] = [dst_author, src_author]
+    feature_store[("paper", "cites", "paper"), "time", None] = tme_cite
+    feature_store[("author", "writes", "paper"), "time", None] = tme_author
+    loader = cugraph_pyg.loader.NeighborLoader(
+        (feature_store, graph_store),
+        num_neighbors={("paper", "cites", "paper"): [2, 2, 2], ("author", "writes", "paper"): [2, 2, 0]},
+        batch_size=1, input_nodes=("paper", torch.tensor([3])), input_time=torch.tensor([-1]), time_attr="time", shuffle=False,
+        temporal_comparison="strictly_increasing")
+    out = next(iter(loader))
+    assert sorted(out["author"].n_id.tolist()) == [0, 1, 2]
+    assert out["paper"].n_id.tolist() == [3, 2, 1, 0]
+    assert sorted(out["author", "writes", "paper"].e_id.tolist()) == [0, 2, 4, 5]
+    assert out["author", "writes", "paper"].num_sampled_edges.tolist() == [2, 2, 0]
