@@ -50,6 +50,15 @@ RMAT = (0.57, 0.19, 0.19, 0.05)
 SCRAMBLE_MUL, SCRAMBLE_ADD = 7_919_717, 1_234_567  # multiplier coprime with every |V| used here (odd, not a multiple of 3 or 5)
 WORKLOAD = "C2 synthetic RMAT |V|=10M |E|=160M fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"
 METRIC = "sampled_edges_per_sec (multi-hop sample + renumber + feature gather, fanout [25,10])"
+# --workload: the other shapes BASELINE.json names for this metric (same step, same kernels; not the default bench line).
+# c2 is the default and is what the constants above say; the others overwrite them in main().
+WORKLOADS = {
+    "c2": None,
+    "c4": {"NUM_NODES": 111_000_000, "NUM_EDGES": 1_600_000_000, "FEAT_DIM": 128,
+           "WORKLOAD": "C4 ogbn-papers100M-shape synthetic RMAT |V|=111M |E|=1.6B fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"},
+    "headline": {"NUM_NODES": 100_000_000, "NUM_EDGES": 1_000_000_000, "FEAT_DIM": 256,
+                 "WORKLOAD": "north-star synthetic RMAT |V|=100M |E|=1B fanout=[25,10] feat_dim=256 fp32, sampler+renumber+gather"},
+}
 
 
 def log(*a):
@@ -93,6 +102,10 @@ def seed_sets(torch, num_sets, labels, rank=0):
     """num_sets call groups of `labels` mini-batches of BATCH distinct seeds (int64, like NodeLoader's randperm)."""
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     out = []
+    if NUM_NODES > 20_000_000 and num_sets * labels * BATCH <= NUM_NODES:
+        # the large shapes: ONE permutation cut into call groups (a permutation of 10^8 ids per call group takes seconds)
+        perm = torch.randperm(NUM_NODES, generator=g)
+        return [perm[i * labels * BATCH:(i + 1) * labels * BATCH].clone() for i in range(num_sets)]
     for _ in range(num_sets):
         out.append(torch.randperm(NUM_NODES, generator=g)[: labels * BATCH].contiguous())
     return out
@@ -440,7 +453,7 @@ def run_ours(args):
             "dtype": "int64/int32 ids, fp32 features",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "labels_per_step_per_gpu": labels, "seeds_per_label": BATCH,
-                       "l2": "inputs larger than L2 (5.1 GB table, >1 GB gathered per step); new seed set every step",
+                       "l2": "inputs larger than L2 (%.1f GB table, >1 GB gathered per step); new seed set every step" % (NUM_NODES * FEAT_DIM * 4 / 1e9),
                        "graph": "replicated per GPU", "features": "chunked over %d GPU(s), in-kernel P2P gather" % world,
                        "hot_rows_replicated_per_gpu": hot_rows, "hot_rows_bytes_per_gpu": hot_rows * FEAT_DIM * 4 + (4 * NUM_NODES if hot_rows else 0),
                        "pipeline": "call group k+1 begun before k is finished; gather on %s" % ("its own stream" if use_side else "the same stream")},
@@ -483,6 +496,8 @@ def cpu_baseline(row_ptr, col, budget_s=15.0, labels=4, steps=None):
 
     table = None
     try:
+        if NUM_NODES * FEAT_DIM * 4 > (8 << 30):
+            raise MemoryError  # the large shapes: closed-form rows instead of a host copy of the table
         table = np.empty((NUM_NODES, FEAT_DIM), dtype=np.float32)
         for lo in range(0, NUM_NODES, 1 << 20):
             hi = min(NUM_NODES, lo + (1 << 20))
@@ -554,7 +569,11 @@ def main():
     ap.add_argument("--hot-ratio", type=float, default=0.1,
                     help="N > 1: fraction of the feature rows (the highest-degree vertices) replicated on every GPU; 0 = none")
     ap.add_argument("--gather-stream", type=int, default=-1, help="run the feature gather on a second stream (1, default) or in line (0)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
+                    help="c2 (default, the bench line) | c4 (papers100M shape) | headline (|V|=100M, |E|=1B, F=256)")
     args = ap.parse_args()
+    if WORKLOADS[args.workload] is not None:
+        globals().update(WORKLOADS[args.workload])
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
