@@ -18,6 +18,11 @@ __device__ __forceinline__ T load_elt(const ChunkRef& ref, unsigned long long el
   return __ldg(reinterpret_cast<const T*>(ref.at<CHUNKED>(elt * sizeof(T))));
 }
 
+#ifdef WGB_HOST_EMULATION
+// tests/emu compiles this header with g++ to check kernel LOGIC on the CPU (test infrastructure, never the product)
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+#else
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
 {
   unsigned long long v;
@@ -28,6 +33,7 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+#endif
 
 // ---- single-pass exclusive scan (decoupled look-back) ----------------------------------------------
 // A tile publishes one 64-bit word: flag(2 bits) | value(62 bits); flag 1 = tile aggregate,
