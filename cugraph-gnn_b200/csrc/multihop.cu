@@ -98,6 +98,33 @@ __device__ __forceinline__ unsigned int mh_home(unsigned long long item, unsigne
 struct MhBucket {
   unsigned long long k[kBucket], a[kBucket];
 };
+#ifdef WGB_HOST_EMULATION
+// tests/emu compiles this file with g++ to check its LOGIC on the CPU (test infrastructure, never the product): the two
+// PTX accesses become an unordered read of the four words and a 128-bit CAS serialised by a lock shared with nothing else
+// (aux words are only ever lowered by atomicMin on slots whose key is already installed, so the lock is enough).
+__device__ __forceinline__ MhBucket mh_load_bucket(const MhSlot* table, unsigned int g)
+{
+  MhBucket r;
+  for (unsigned int j = 0; j < kBucket; j++) {
+    r.k[j] = __atomic_load_n(&table[g + j].key, __ATOMIC_RELAXED);
+    r.a[j] = __atomic_load_n(&table[g + j].aux, __ATOMIC_RELAXED);
+  }
+  return r;
+}
+__device__ __forceinline__ void mh_cas_slot(MhSlot* p, unsigned long long ek, unsigned long long ea, unsigned long long nk,
+                                            unsigned long long na, unsigned long long& ok, unsigned long long& oa)
+{
+  static int lock = 0;
+  while (__atomic_exchange_n(&lock, 1, __ATOMIC_ACQUIRE)) {}
+  ok = __atomic_load_n(&p->key, __ATOMIC_RELAXED);
+  oa = __atomic_load_n(&p->aux, __ATOMIC_RELAXED);
+  if (ok == ek && oa == ea) {
+    __atomic_store_n(&p->aux, na, __ATOMIC_RELAXED);
+    __atomic_store_n(&p->key, nk, __ATOMIC_RELEASE);
+  }
+  __atomic_store_n(&lock, 0, __ATOMIC_RELEASE);
+}
+#else
 __device__ __forceinline__ MhBucket mh_load_bucket(const MhSlot* table, unsigned int g)
 {
   MhBucket r;
@@ -119,6 +146,7 @@ __device__ __forceinline__ void mh_cas_slot(MhSlot* p, unsigned long long ek, un
     : "l"(ek), "l"(ea), "l"(nk), "l"(na), "l"(p)
     : "memory");
 }
+#endif
 
 // Claim-or-find the slot of `item` (= label * V + vertex) in the current epoch, starting at bucket `g` whose
 // contents have already been loaded into `cur` (lets callers batch the first, random, access of several items).

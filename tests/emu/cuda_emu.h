@@ -1,7 +1,8 @@
 // TEST INFRASTRUCTURE ONLY (never part of the product, never linked into libwholegraph_b200.so).
 //
 // A tiny SIMT emulator that lets g++ compile the product's device kernels (csrc/*.cuh) and run their LOGIC on the CPU:
-// one thread block at a time, every CUDA thread an OS thread, __syncthreads() / warp intrinsics as pthread barriers.
+// one thread block at a time, every CUDA thread a cooperative fiber (ucontext) on ONE OS thread, __syncthreads() and the
+// warp intrinsics as fiber barriers (deterministic; a barrier that cannot complete is reported as a deadlock).
 // It exists because a round can run out of GPU minutes before a newly written kernel has been on hardware: the kernel's
 // control flow, indexing and barrier placement can still be checked against the oracle here.  It says nothing about
 // memory ordering, occupancy or speed; the GPU parity tests stay the gate.
@@ -9,20 +10,26 @@
 // Supported: threadIdx/blockIdx/blockDim/gridDim (.x/.y), __shared__ (function-scope static: one block runs at a time),
 // __syncthreads, __syncwarp, __ballot_sync, __any_sync, __shfl_sync/_up/_xor (int, unsigned, long long, unsigned long
 // long), __match_any_sync, atomicAdd/atomicMax/atomicMin, __ldg, __popc, __clz, __ffs, __clzll, __float_as_uint.
-// Every warp intrinsic is a rendezvous of ALL 32 lanes of the warp: kernels whose sub-warp groups diverge around
-// intrinsics with partial masks (uniform_small_kernel) cannot be emulated; masks only select which lanes are evaluated.
+// A warp intrinsic is a rendezvous of exactly the lanes named in its mask (one barrier per distinct mask and warp), so
+// sub-warp groups that diverge from each other around partial-mask intrinsics (uniform_small_kernel) work; the lanes of
+// one mask must all arrive, as on the hardware.
+// Host side: the CUDA runtime calls the product's host code makes are defined in emu_runtime.cpp (malloc / memcpy /
+// no-op streams and events), kernel launches are rewritten by emu_preprocess.py into launch_dim() below.
 #pragma once
 
 #include <cuda_runtime.h>  // types (dim3, uint3) and the host-side definitions of __host__/__device__ (empty under g++)
 
-#include <pthread.h>
+#include <ucontext.h>
 
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
-#include <thread>
+#include <map>
+#include <memory>
 #include <vector>
 
 #undef __shared__
@@ -40,120 +47,199 @@ struct Idx {
   unsigned int x = 0, y = 0, z = 0;
 };
 
+// A barrier for cooperative fibers: the last arrival opens the next generation, the others yield until it has.
+struct Bar {
+  unsigned int count   = 0;
+  unsigned int arrived = 0;
+  unsigned long gen    = 0;
+};
+
 struct Warp {
-  pthread_barrier_t bar;
+  unsigned int lanes = 32;  // threads of the block that live in this warp
   unsigned long long v64[32];
+  std::map<unsigned int, Bar> bars;  // one per mask in use
+};
+
+struct Fiber {
+  ucontext_t ctx;
+  Idx idx;
+  bool done = false;
 };
 
 struct Block {
-  pthread_barrier_t bar;
-  std::vector<Warp> warps;
+  Bar bar;
+  std::unique_ptr<Warp[]> warps;
+  std::vector<Fiber> fibers;
+  ucontext_t sched;
+  unsigned int cur       = 0;
+  unsigned long progress = 0;  // barrier releases + fiber exits: no change over a whole sweep = deadlock
 };
 
-inline thread_local Idx t_threadIdx;
 inline Idx g_blockIdx, g_blockDim, g_gridDim;
-inline Block* g_block = nullptr;
+inline Block* g_block                     = nullptr;
+inline const std::function<void()>* g_body = nullptr;
+inline std::vector<char*> g_stacks;  // reused across launches
+constexpr size_t kStackBytes = 256 << 10;
 
-inline Warp& my_warp() { return g_block->warps[t_threadIdx.x >> 5]; }
-inline int my_lane() { return (int)(t_threadIdx.x & 31u); }
+inline Idx& cur_idx() { return g_block->fibers[g_block->cur].idx; }
+inline Warp& my_warp() { return g_block->warps[cur_idx().x >> 5]; }
+inline int my_lane() { return (int)(cur_idx().x & 31u); }
 
-// every lane publishes `v`, then reads what it needs through `read(all 32 values)`
+inline void yield()
+{
+  Block* b = g_block;
+  swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+}
+
+inline void wait(Bar& bar)
+{
+  const unsigned long gen = bar.gen;
+  if (++bar.arrived == bar.count) {
+    bar.arrived = 0;
+    bar.gen++;
+    g_block->progress++;
+  } else {
+    while (bar.gen == gen)
+      yield();
+  }
+}
+
+inline void warp_rendezvous(unsigned int mask)
+{
+  Warp& w = my_warp();
+  if (w.lanes < 32) mask &= (1u << w.lanes) - 1u;
+  Bar& bar = w.bars[mask];
+  if (bar.count == 0) bar.count = (unsigned int)__builtin_popcount(mask);
+  wait(bar);
+}
+
+// every lane of `mask` publishes `v`, then reads what it needs through `read(all 32 values)` (only the slots of the
+// lanes in `mask` are meaningful)
 template <typename F>
-inline auto exchange(unsigned long long v, F&& read)
+inline auto exchange(unsigned int mask, unsigned long long v, F&& read)
 {
   Warp& w = my_warp();
   w.v64[my_lane()] = v;
-  pthread_barrier_wait(&w.bar);
+  warp_rendezvous(mask);
   auto r = read(w.v64);
-  pthread_barrier_wait(&w.bar);
+  warp_rendezvous(mask);
   return r;
 }
 
-// run `body` for every thread of every block of a grid (blocks sequentially)
+inline void fiber_entry()
+{
+  (*g_body)();
+  Block* b                = g_block;
+  b->fibers[b->cur].done  = true;
+  b->progress++;
+  // returning switches to uc_link = the scheduler
+}
+
+// run `body` for every thread of every block of a grid: blocks one after the other, the threads of a block as fibers
+// scheduled round-robin on this OS thread (a fiber runs until it waits at a barrier or returns)
 inline void launch(unsigned int grid_x, unsigned int grid_y, unsigned int block_x, const std::function<void()>& body)
 {
   g_gridDim.x = grid_x; g_gridDim.y = grid_y; g_gridDim.z = 1;
   g_blockDim.x = block_x; g_blockDim.y = 1; g_blockDim.z = 1;
   const unsigned int nwarps = (block_x + 31) / 32;
+  while (g_stacks.size() < block_x)
+    g_stacks.push_back(static_cast<char*>(std::malloc(kStackBytes)));
+  g_body = &body;
   for (unsigned int by = 0; by < grid_y; by++)
     for (unsigned int bx = 0; bx < grid_x; bx++) {
       Block blk;
-      blk.warps.resize(nwarps);
-      pthread_barrier_init(&blk.bar, nullptr, block_x);
+      blk.warps.reset(new Warp[nwarps]);
+      blk.bar.count = block_x;
       for (unsigned int w = 0; w < nwarps; w++)
-        pthread_barrier_init(&blk.warps[w].bar, nullptr, std::min(32u, block_x - 32u * w));
+        blk.warps[w].lanes = std::min(32u, block_x - 32u * w);
+      blk.fibers.resize(block_x);
       g_block      = &blk;
       g_blockIdx.x = bx; g_blockIdx.y = by; g_blockIdx.z = 0;
-      std::vector<std::thread> ts;
-      ts.reserve(block_x);
-      for (unsigned int t = 0; t < block_x; t++)
-        ts.emplace_back([t, &body] {
-          t_threadIdx.x = t; t_threadIdx.y = 0; t_threadIdx.z = 0;
-          body();
-        });
-      for (auto& th : ts)
-        th.join();
-      for (unsigned int w = 0; w < nwarps; w++)
-        pthread_barrier_destroy(&blk.warps[w].bar);
-      pthread_barrier_destroy(&blk.bar);
+      for (unsigned int t = 0; t < block_x; t++) {
+        Fiber& f = blk.fibers[t];
+        f.idx.x  = t;
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp   = g_stacks[t];
+        f.ctx.uc_stack.ss_size = kStackBytes;
+        f.ctx.uc_link          = &blk.sched;
+        makecontext(&f.ctx, fiber_entry, 0);
+      }
+      unsigned int remaining = block_x;
+      while (remaining) {
+        const unsigned long before = blk.progress;
+        for (unsigned int t = 0; t < block_x; t++) {
+          Fiber& f = blk.fibers[t];
+          if (f.done) continue;
+          blk.cur = t;
+          swapcontext(&blk.sched, &f.ctx);
+          if (f.done) remaining--;
+        }
+        if (remaining && blk.progress == before) {
+          std::fprintf(stderr, "cuda_emu: deadlock in block (%u, %u): %u thread(s) wait at barriers that cannot complete\n", bx, by, remaining);
+          std::abort();
+        }
+      }
       g_block = nullptr;
     }
+  g_body = nullptr;
 }
+
+inline void launch_dim(dim3 grid, dim3 block, const std::function<void()>& body) { launch(grid.x, grid.y, block.x, body); }
 
 }  // namespace cuda_emu
 
-#define threadIdx (::cuda_emu::t_threadIdx)
+#define threadIdx (::cuda_emu::cur_idx())
 #define blockIdx (::cuda_emu::g_blockIdx)
 #define blockDim (::cuda_emu::g_blockDim)
 #define gridDim (::cuda_emu::g_gridDim)
 
-inline void __syncthreads() { pthread_barrier_wait(&::cuda_emu::g_block->bar); }
-inline void __syncwarp(unsigned int = 0xffffffffu) { pthread_barrier_wait(&::cuda_emu::my_warp().bar); }
+inline void __syncthreads() { ::cuda_emu::wait(::cuda_emu::g_block->bar); }
+inline void __syncwarp(unsigned int mask = 0xffffffffu) { ::cuda_emu::warp_rendezvous(mask); }
 
 inline unsigned int __ballot_sync(unsigned int mask, bool pred)
 {
-  return ::cuda_emu::exchange(pred ? 1ULL : 0ULL, [mask](const unsigned long long* v) {
+  return ::cuda_emu::exchange(mask, pred ? 1ULL : 0ULL, [mask](const unsigned long long* v) {
     unsigned int r = 0;
     for (int i = 0; i < 32; i++)
       if (((mask >> i) & 1u) && v[i]) r |= 1u << i;
     return r;
   });
 }
-inline bool __any_sync(unsigned int mask, bool pred) { return (__ballot_sync(0xffffffffu, pred) & mask) != 0u; }
+inline bool __any_sync(unsigned int mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
 
 template <typename T>
-inline T __shfl_sync(unsigned int, T val, int src, int width = 32)
+inline T __shfl_sync(unsigned int mask, T val, int src, int width = 32)
 {
   static_assert(sizeof(T) <= 8, "emulated shuffles move up to 64 bits");
   unsigned long long raw = 0;
   std::memcpy(&raw, &val, sizeof(T));
   const int lane = ::cuda_emu::my_lane();
   const int base = lane & ~(width - 1);
-  unsigned long long got = ::cuda_emu::exchange(raw, [=](const unsigned long long* v) { return v[base + (src & (width - 1))]; });
+  unsigned long long got = ::cuda_emu::exchange(mask, raw, [=](const unsigned long long* v) { return v[base + (src & (width - 1))]; });
   T out;
   std::memcpy(&out, &got, sizeof(T));
   return out;
 }
 template <typename T>
-inline T __shfl_up_sync(unsigned int, T val, unsigned int delta, int width = 32)
+inline T __shfl_up_sync(unsigned int mask, T val, unsigned int delta, int width = 32)
 {
   unsigned long long raw = 0;
   std::memcpy(&raw, &val, sizeof(T));
   const int lane = ::cuda_emu::my_lane();
   const int base = lane & ~(width - 1);
-  unsigned long long got = ::cuda_emu::exchange(raw, [=](const unsigned long long* v) { return lane - (int)delta >= base ? v[lane - (int)delta] : v[lane]; });
+  unsigned long long got = ::cuda_emu::exchange(mask, raw, [=](const unsigned long long* v) { return lane - (int)delta >= base ? v[lane - (int)delta] : v[lane]; });
   T out;
   std::memcpy(&out, &got, sizeof(T));
   return out;
 }
 template <typename T>
-inline T __shfl_xor_sync(unsigned int, T val, int lane_mask, int width = 32)
+inline T __shfl_xor_sync(unsigned int mask, T val, int lane_mask, int width = 32)
 {
   unsigned long long raw = 0;
   std::memcpy(&raw, &val, sizeof(T));
   const int lane = ::cuda_emu::my_lane();
   (void)width;
-  unsigned long long got = ::cuda_emu::exchange(raw, [=](const unsigned long long* v) { return v[(lane ^ lane_mask) & 31]; });
+  unsigned long long got = ::cuda_emu::exchange(mask, raw, [=](const unsigned long long* v) { return v[(lane ^ lane_mask) & 31]; });
   T out;
   std::memcpy(&out, &got, sizeof(T));
   return out;
@@ -162,7 +248,7 @@ inline unsigned int __match_any_sync(unsigned int mask, int value)
 {
   const int lane = ::cuda_emu::my_lane();
   (void)lane;
-  return ::cuda_emu::exchange((unsigned long long)(unsigned int)value, [=](const unsigned long long* v) {
+  return ::cuda_emu::exchange(mask, (unsigned long long)(unsigned int)value, [=](const unsigned long long* v) {
     unsigned int r = 0;
     for (int i = 0; i < 32; i++)
       if (((mask >> i) & 1u) && v[i] == (unsigned long long)(unsigned int)value) r |= 1u << i;

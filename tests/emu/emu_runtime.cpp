@@ -1,0 +1,143 @@
+// TEST INFRASTRUCTURE ONLY: the pieces of the CUDA runtime and of libwholegraph_b200's own runtime (runtime.cu,
+// sample.cu) that csrc/multihop.cu's HOST code calls, restated for the CPU emulation in tests/emu: device memory is
+// malloc, copies are memcpy (launches are synchronous in the emulator, so stream order is program order), streams and
+// events are no-ops.  Tensors are plain pointer tensors.
+#include "cuda_emu.h"
+
+#include "wm_common.cuh"
+#include "pcg.cuh"
+
+#include <cstdarg>
+#include <cstdlib>
+
+extern "C" {
+
+cudaError_t cudaMalloc(void** p, size_t n)
+{
+  *p = std::malloc(n ? n : 1);
+  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFree(void* p)
+{
+  std::free(p);
+  return cudaSuccess;
+}
+cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
+cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
+cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t)
+{
+  if (n) std::memmove(dst, src, n);
+  return cudaSuccess;
+}
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)
+{
+  for (size_t r = 0; r < height; r++)
+    std::memmove(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+  return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t)
+{
+  if (n) std::memset(p, v, n);
+  return cudaSuccess;
+}
+cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
+cudaError_t cudaEventCreate(cudaEvent_t* e)
+{
+  *e = nullptr;
+  return cudaSuccess;
+}
+cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned int)
+{
+  *e = nullptr;
+  return cudaSuccess;
+}
+cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t)
+{
+  *ms = 0.f;
+  return cudaSuccess;
+}
+cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned int) { return cudaSuccess; }
+cudaError_t cudaGetDevice(int* d)
+{
+  *d = 0;
+  return cudaSuccess;
+}
+cudaError_t cudaGetLastError(void) { return cudaSuccess; }
+const char* cudaGetErrorString(cudaError_t) { return "emulated CUDA runtime"; }
+
+// ---- tensor descriptions / pointer tensors (product: csrc/runtime.cu) ----
+size_t wholememory_dtype_get_element_size(wholememory_dtype_t dt)
+{
+  switch (dt) {
+    case WHOLEMEMORY_DT_INT8: return 1;
+    case WHOLEMEMORY_DT_INT16:
+    case WHOLEMEMORY_DT_HALF:
+    case WHOLEMEMORY_DT_BF16: return 2;
+    case WHOLEMEMORY_DT_INT:
+    case WHOLEMEMORY_DT_FLOAT: return 4;
+    case WHOLEMEMORY_DT_INT64:
+    case WHOLEMEMORY_DT_DOUBLE: return 8;
+    default: return (size_t)-1;
+  }
+}
+void wholememory_initialize_tensor_desc(wholememory_tensor_description_t* d)
+{
+  std::memset(d, 0, sizeof(*d));
+  d->dtype = WHOLEMEMORY_DT_UNKNOWN;
+}
+wholememory_tensor_description_t* wholememory_tensor_get_tensor_description(wholememory_tensor_t t) { return &t->desc; }
+void* wholememory_tensor_get_data_pointer(wholememory_tensor_t t)
+{
+  return static_cast<char*>(t->storage_ptr) + t->desc.storage_offset * wholememory_dtype_get_element_size(t->desc.dtype);
+}
+
+}  // extern "C"
+
+namespace wgb {
+
+int g_log_level                     = 0;
+unsigned long long g_kernel_launches = 0;
+
+void log_msg(int, const char* fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  std::vfprintf(stderr, fmt, ap);
+  std::fprintf(stderr, "\n");
+  va_end(ap);
+}
+
+int num_sms() { return 2; }  // small grids: every grid-stride loop and persistent ticket loop iterates
+
+ChunkRef make_chunk_ref(wholememory_tensor_t t)
+{
+  ChunkRef r;
+  std::memset(&r, 0, sizeof(r));
+  r.base[0]  = static_cast<char*>(t->storage_ptr);
+  r.start[1] = (unsigned long long)(t->desc.storage_offset + t->desc.sizes[0]) * wholememory_dtype_get_element_size(t->desc.dtype);
+  r.world    = 1;
+  return r;
+}
+
+const Affine* skip_table_device()
+{
+  static std::vector<Affine> host;
+  if (host.empty()) {
+    host.resize(kSkipTabSize);
+    for (int p = 0; p < kSkipTabBytes; p++) {
+      Affine unit = affine_skip_loop(1ULL << (8 * p));
+      Affine acc{1ULL, 0ULL};
+      for (int v = 0; v < 256; v++) {
+        host[p * 256 + v] = acc;
+        acc               = affine_then(acc, unit);
+      }
+    }
+  }
+  return host.data();
+}
+
+}  // namespace wgb

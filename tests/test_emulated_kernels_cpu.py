@@ -9,31 +9,24 @@ uniform_general_kernel) is run through the same shim first, which validates the 
 """
 import ctypes
 import os
-import subprocess
 
 import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(HERE)
-CUDA_INC = "/usr/local/cuda/include"
 COMPARISONS = ("strictly_increasing", "monotonically_increasing", "strictly_decreasing", "monotonically_decreasing")
 
 
 @pytest.fixture(scope="module")
 def emu():
-    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime.h")):
+    import sys
+
+    sys.path.insert(0, os.path.join(HERE, "emu"))
+    import build_emu
+
+    if not build_emu.available():
         pytest.skip("CUDA headers not installed")
-    out_dir = os.path.join(HERE, "emu", "_build")
-    os.makedirs(out_dir, exist_ok=True)
-    lib = os.path.join(out_dir, "libtemporal_emu.so")
-    src = os.path.join(HERE, "emu", "temporal_emu.cpp")
-    deps = [src, os.path.join(HERE, "emu", "cuda_emu.h")] + [os.path.join(ROOT, "cugraph-gnn_b200", "csrc", f)
-                                                             for f in ("temporal_device.cuh", "sample_device.cuh", "pcg.cuh", "wm_common.cuh")]
-    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-DWGB_HOST_EMULATION", "-fPIC", "-shared", "-pthread", "-I", os.path.join(HERE, "emu"),
-                               "-I", os.path.join(ROOT, "cugraph-gnn_b200", "csrc"), "-I", os.path.join(ROOT, "include"), "-I", CUDA_INC, src, "-o", lib])
-    return ctypes.CDLL(lib)
+    return ctypes.CDLL(build_emu.build_kernels())
 
 
 def _p(a):

@@ -1,0 +1,192 @@
+"""The product's fused multi-hop sampler (csrc/multihop.cu: host code AND kernels) compiled for the CPU through the SIMT
+shim in tests/emu and compared with the oracle, bit for bit.
+
+What this is: a LOGIC check of the exact source the GPU runs (launch order, scratch sizing, indexing, barriers, hash
+table protocol, random-stream geometry), available without a GPU.  It was written when the temporal path had to be
+finished after the round's GPU minutes were spent; the emulated plain / heterogeneous calls below are the calibration --
+that path is GPU-verified (tests/test_gpu_multihop.py, test_gpu_hetero.py), and the emulator reproduces it.
+What this is not: evidence about memory ordering, races that need real parallelism, or speed.  The GPU parity tests stay
+the gate (tests/test_gpu_temporal.py), and nothing here is linked into the product.
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from graphs import random_typed_graph
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+VP = ctypes.c_void_p
+FLAG_CSR, FLAG_INT64 = 1, 2
+COMPARISONS = ("strictly_increasing", "monotonically_increasing", "strictly_decreasing", "monotonically_decreasing")
+HETERO = ("majors", "minors", "edge_id", "edge_type", "label_type_hop_offsets", "renumber_map", "renumber_map_offsets",
+          "edge_renumber_map", "edge_renumber_map_offsets", "label_type_step_base")
+HOMO = ("majors", "minors", "edge_id", "label_hop_offsets", "renumber_map", "renumber_map_offsets", "major_offsets", "label_step_base")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    sys.path.insert(0, os.path.join(HERE, "emu"))
+    import build_emu
+
+    if not build_emu.available():
+        pytest.skip("CUDA headers not installed")
+    return ctypes.CDLL(build_emu.build_multihop())
+
+
+def _run(lib, row_ptrs, cols, vto, seeds, lo, fanout, random_state, *, hetero=True, times=None, seed_times=None, cmp=0, eids=None,
+         flags=FLAG_INT64, expect_rc=0, reps=1):
+    T = len(row_ptrs)
+    rp = [np.ascontiguousarray(r, dtype=np.int64) for r in row_ptrs]
+    cl = [np.ascontiguousarray(c) for c in cols]
+    is64 = cl[0].dtype == np.int64
+    ne = np.array([c.shape[0] for c in cl], dtype=np.int64)
+    tm = None if times is None else [np.ascontiguousarray(t, dtype=np.int64) for t in times]
+    ei = None if eids is None else [None if e is None else np.ascontiguousarray(e, dtype=np.int64) for e in eids]
+    vto = np.ascontiguousarray(vto, dtype=np.int64)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    st = np.zeros_like(seeds) if seed_times is None else np.ascontiguousarray(seed_times, dtype=np.int64)
+    lo = np.ascontiguousarray(lo, dtype=np.int64)
+    fo = np.ascontiguousarray(fanout, dtype=np.int32)
+
+    def arr(xs):
+        return (VP * T)(*[None if x is None else x.ctypes.data for x in xs])
+
+    out_ptr, out_cnt, out_elt = (VP * 10)(), (ctypes.c_longlong * 10)(), (ctypes.c_int * 10)()
+    lib.emu_multihop.restype = ctypes.c_int
+    rc = lib.emu_multihop(T, arr(rp), ctypes.c_longlong(rp[0].shape[0] - 1), arr(cl), ne.ctypes.data_as(VP), int(is64),
+                          None if tm is None else arr(tm), None if ei is None else arr(ei), vto.ctypes.data_as(VP), vto.shape[0] - 1,
+                          int(hetero), seeds.ctypes.data_as(VP), st.ctypes.data_as(VP), ctypes.c_longlong(seeds.shape[0]), lo.ctypes.data_as(VP),
+                          ctypes.c_longlong(lo.shape[0] - 1), fo.ctypes.data_as(VP), fo.shape[0] // T, ctypes.c_ulonglong(random_state), cmp,
+                          flags, reps, out_ptr, out_cnt, out_elt)
+    assert rc == expect_rc, rc
+    outs = {}
+    for k, name in enumerate(HETERO if hetero else HOMO):
+        if not out_ptr[k]:
+            continue
+        dt = {4: np.int32, 8: np.int64}[out_elt[k]]
+        n = int(out_cnt[k])
+        outs[name] = np.frombuffer(ctypes.string_at(out_ptr[k], n * out_elt[k]), dtype=dt).copy() if n else np.empty(0, dt)
+        lib.emu_free(VP(out_ptr[k]))
+    return outs
+
+
+def _same(got, exp, names):
+    for name in names:
+        e = np.asarray(exp[name]).reshape(-1)
+        assert got[name].shape == e.shape, (name, got[name].shape, e.shape)
+        assert np.array_equal(got[name].astype(np.int64), e.astype(np.int64)), name
+
+
+def _majors_of_csr(out, L, B):
+    """major_offsets -> majors, label by label (local ids restart per label; the CSR rows of a label are its sources)."""
+    lho, moff = out["label_hop_offsets"], out["major_offsets"]
+    majors = []
+    for l in range(B):
+        r0, r1 = lho[l * L], lho[(l + 1) * L]
+        majors.append(np.repeat(np.arange(r1 - r0), np.diff(moff[r0:r1 + 1])))
+    return np.concatenate(majors)
+
+
+def _typed_case(col_dtype=np.int32, seed=6):
+    edge_types = [(0, 1), (1, 0), (1, 1)]
+    vto, row_ptrs, cols = random_typed_graph([700, 1500], edge_types, [9000, 14000, 60000], seed=seed, col_dtype=col_dtype)
+    rng = np.random.default_rng(4)
+    seeds = np.concatenate([rng.integers(0, 2200, 60), rng.integers(700, 2200, 33), rng.integers(0, 700, 1)]).astype(np.int64)
+    seeds[7] = seeds[3]
+    lo = np.array([0, 60, 60, 93, 94], dtype=np.int64)
+    return vto, row_ptrs, cols, seeds, lo, rng
+
+
+# ---- calibration: the GPU-verified paths through the emulator ----------------------------------------------------------------
+@pytest.mark.parametrize("fanout,flags", [([25, 10], FLAG_INT64), ([4, 3, 2], FLAG_CSR | FLAG_INT64), ([40, 5], 0), ([-1, 2], FLAG_INT64)])
+def test_emulated_plain_homogeneous_matches_oracle(emu, oracle, fanout, flags):
+    vto, row_ptrs, cols = random_typed_graph([3000], [(0, 0)], [90000], seed=11)
+    rng = np.random.default_rng(1)
+    seeds = rng.integers(0, 3000, 200).astype(np.int64)
+    lo = np.array([0, 64, 128, 200], dtype=np.int64)
+    got = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 62, hetero=False, flags=flags)
+    exp = oracle.multihop_sample(row_ptrs[0], cols[0], seeds, lo, fanout, 62)
+    _same(got, exp, ["minors", "edge_id", "renumber_map", "renumber_map_offsets"])
+    if flags & FLAG_CSR:
+        assert np.array_equal(_majors_of_csr(got, len(fanout), 3), exp["majors"])
+    else:
+        _same(got, exp, ["majors", "label_hop_offsets"])
+
+
+@pytest.mark.parametrize("fanout", [[3, 2, 4, 2, 2, 2], [40, 33, 35, -1, 2, 50], [0, 0, 0, 4, 4, 4]])
+def test_emulated_plain_heterogeneous_matches_oracle(emu, oracle, fanout):
+    vto, row_ptrs, cols, seeds, lo, _ = _typed_case()
+    got = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 31, reps=2)
+    _same(got, oracle.hetero_multihop_sample(row_ptrs, cols, vto, seeds, lo, fanout, 31), HETERO)
+
+
+# ---- the temporal path (not yet run on a GPU) -----------------------------------------------------------------------------
+@pytest.mark.parametrize("comparison", range(4))
+@pytest.mark.parametrize("fanout", [[3, 2, 4, 2, 2, 2], [-1, 3, 0, 2, -1, 1], [5, 5, 5], [0, 0, 0, 4, 4, 4], [2, 40, 1], [33, 70, 8, 3, 3, 3]])
+@pytest.mark.parametrize("col_dtype", [np.int32, np.int64])
+def test_emulated_temporal_heterogeneous_matches_oracle(emu, oracle, comparison, fanout, col_dtype):
+    """The configurations of tests/test_gpu_temporal.py::test_temporal_hetero_bit_exact_vs_oracle."""
+    vto, row_ptrs, cols, seeds, lo, rng = _typed_case(col_dtype, seed=len(fanout))
+    times = [rng.integers(0, 50, c.shape[0]).astype(np.int64) for c in cols]
+    eids = [rng.permutation(c.shape[0]).astype(np.int64) + 1000000 * t for t, c in enumerate(cols)]
+    mid = 10 if comparison < 2 else 40
+    seed_times = (mid + rng.integers(-5, 6, seeds.shape[0])).astype(np.int64)
+    if col_dtype is np.int64 and comparison != 0 and os.environ.get("WGB_EMU_FULL") != "1":
+        pytest.skip("64-bit columns are swept with one comparison by default; WGB_EMU_FULL=1 runs all")
+    got = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 31, times=times, seed_times=seed_times, cmp=comparison, eids=eids,
+               reps=2 if comparison == 0 else 1)
+    exp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, seed_times, lo, fanout, 31, COMPARISONS[comparison], edge_ids=eids)
+    assert exp["majors"].shape[0] > 0 or not any(fanout[:3])  # hop 0 with fan-out 0 for every type: nothing is sampled
+    _same(got, exp, HETERO)
+
+
+@pytest.mark.parametrize("fanout,flags", [([4, 3], FLAG_INT64), ([40, 5], 0), ([-1, 2], FLAG_INT64)])
+def test_emulated_temporal_homogeneous_matches_oracle(emu, oracle, fanout, flags):
+    vto, row_ptrs, cols = random_typed_graph([3000], [(0, 0)], [90000], seed=11)
+    rng = np.random.default_rng(1)
+    times = [rng.integers(0, 1000, cols[0].shape[0]).astype(np.int64)]
+    seeds = rng.integers(0, 3000, 200).astype(np.int64)
+    seed_times = rng.integers(300, 700, 200).astype(np.int64)
+    lo = np.array([0, 64, 128, 200], dtype=np.int64)
+    got = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 62, hetero=False, times=times, seed_times=seed_times, cmp=3, flags=flags)
+    exp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, seed_times, lo, fanout, 62, "monotonically_decreasing")
+    assert np.array_equal(got["majors"], exp["majors"]) and np.array_equal(got["minors"], exp["minors"])
+    assert np.array_equal(got["edge_id"], exp["edge_renumber_map"])
+    assert np.array_equal(got["renumber_map"], exp["renumber_map"]) and np.array_equal(got["renumber_map_offsets"], exp["renumber_map_offsets"])
+    assert np.array_equal(got["label_hop_offsets"], exp["label_type_hop_offsets"])
+    assert np.array_equal(got["label_step_base"], exp["label_type_step_base"].reshape(-1))
+
+
+def test_emulated_temporal_csr_output(emu, oracle):
+    """Temporal + CSR compression (what NeighborLoader asks for on a homogeneous graph): major_offsets against the COO result."""
+    vto, row_ptrs, cols = random_typed_graph([800], [(0, 0)], [20000], seed=3)
+    rng = np.random.default_rng(5)
+    times = [rng.integers(0, 100, cols[0].shape[0]).astype(np.int64)]
+    seeds = rng.permutation(800)[:96].astype(np.int64)
+    seed_times = rng.integers(30, 70, 96).astype(np.int64)
+    lo = np.array([0, 32, 64, 96], dtype=np.int64)
+    coo = _run(emu, row_ptrs, cols, vto, seeds, lo, [5, 3], 9, hetero=False, times=times, seed_times=seed_times, cmp=1)
+    csr = _run(emu, row_ptrs, cols, vto, seeds, lo, [5, 3], 9, hetero=False, times=times, seed_times=seed_times, cmp=1, flags=FLAG_CSR | FLAG_INT64)
+    assert np.array_equal(coo["minors"], csr["minors"]) and np.array_equal(coo["edge_id"], csr["edge_id"])
+    assert np.array_equal(_majors_of_csr(csr, 2, 3), coo["majors"])
+    assert csr["major_offsets"][-1] == coo["label_hop_offsets"][-1] == coo["majors"].shape[0] > 0
+
+
+def test_emulated_temporal_open_window_equals_plain(emu):
+    vto, row_ptrs, cols, seeds, lo, _ = _typed_case()
+    times = [np.ones(c.shape[0], dtype=np.int64) for c in cols]
+    for fanout in ([10, 10, 5, 5, 5, 5], [40, 3, 2, 2, 2, 2], [-1, 2, 1, 1, 1, 1]):
+        plain = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 5)
+        temp = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 5, times=times, seed_times=np.ones_like(seeds), cmp=1)
+        _same(temp, plain, HETERO)
+
+
+def test_emulated_temporal_argument_checks(emu):
+    vto, row_ptrs, cols = random_typed_graph([50], [(0, 0)], [300], seed=2)
+    seeds, lo = np.arange(10, dtype=np.int64), np.array([0, 10], dtype=np.int64)
+    tm = [np.zeros(300, dtype=np.int64)]
+    _run(emu, row_ptrs, cols, vto, seeds, lo, [2], 1, hetero=False, times=tm, seed_times=np.zeros(10, np.int64), cmp=7, expect_rc=6)  # INVALID_INPUT
+    _run(emu, row_ptrs, cols, vto, seeds, lo, [2000], 1, hetero=False, times=tm, seed_times=np.zeros(10, np.int64), cmp=0, expect_rc=2)  # NOT_IMPLEMENTED

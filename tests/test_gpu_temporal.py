@@ -67,7 +67,7 @@ def test_temporal_hetero_bit_exact_vs_oracle(env, oracle, comparison, fanout, co
                                       torch.from_numpy(lo).cuda(), fanout, 31 + rep, comparison, vertex_type_offsets=vto.tolist(),
                                       csr_edge_ids=d_eid)
         exp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, seed_times, lo, fanout, 31 + rep, comparison, edge_ids=eids)
-        assert exp["majors"].shape[0] > 0
+        assert exp["majors"].shape[0] > 0 or not any(fanout[:3])  # hop 0 with fan-out 0 for every type: nothing is sampled
         _assert_equal(got, exp)
 
 
