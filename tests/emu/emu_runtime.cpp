@@ -9,19 +9,63 @@
 
 #include <cstdarg>
 #include <cstdlib>
+#include <map>
 
 extern "C" {
 
+// "Device" allocations are adversarial on purpose: filled with garbage (cudaMalloc does not zero memory either) and fenced by
+// guard words that are checked when the block is freed -- a kernel or a host-side sizing bug that writes past a scratch
+// buffer shows up as a non-zero emu_guard_violations() instead of passing silently.
+namespace {
+constexpr size_t kGuard = 64;
+std::map<void*, size_t>& live()
+{
+  static std::map<void*, size_t> m;
+  return m;
+}
+long long g_violations = 0;
+bool guards_ok(char* raw, size_t n)
+{
+  for (size_t i = 0; i < kGuard; i++)
+    if ((unsigned char)raw[i] != 0xC3 || (unsigned char)raw[kGuard + n + i] != 0xC3) return false;
+  return true;
+}
+}  // namespace
+
 cudaError_t cudaMalloc(void** p, size_t n)
 {
-  *p = std::malloc(n ? n : 1);
-  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+  char* raw = static_cast<char*>(std::malloc(n + 2 * kGuard));
+  if (!raw) return cudaErrorMemoryAllocation;
+  std::memset(raw, 0xC3, kGuard);
+  std::memset(raw + kGuard, 0xA5, n);
+  std::memset(raw + kGuard + n, 0xC3, kGuard);
+  *p = raw + kGuard;
+  live()[*p] = n;
+  return cudaSuccess;
 }
 cudaError_t cudaFree(void* p)
 {
-  std::free(p);
+  if (!p) return cudaSuccess;
+  auto it = live().find(p);
+  if (it == live().end()) {
+    g_violations++;  // not a live allocation (double free / foreign pointer)
+    return cudaErrorInvalidValue;
+  }
+  char* raw = static_cast<char*>(p) - kGuard;
+  if (!guards_ok(raw, it->second)) g_violations++;
+  live().erase(it);
+  std::free(raw);
   return cudaSuccess;
 }
+// guard check over everything still allocated + the violations seen at frees so far
+long long emu_guard_violations()
+{
+  long long v = g_violations;
+  for (auto& kv : live())
+    if (!guards_ok(static_cast<char*>(kv.first) - kGuard, kv.second)) v++;
+  return v;
+}
+long long emu_live_allocations() { return (long long)live().size(); }
 cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t)

@@ -10,6 +10,9 @@
 #include <cstdlib>
 #include <vector>
 
+extern "C" long long emu_guard_violations();
+extern "C" long long emu_live_allocations();
+
 namespace {
 
 struct Out {
@@ -112,7 +115,10 @@ int emu_multihop(int T, const long long* const* row_ptr, long long V, const void
     }
     if (rc != WHOLEMEMORY_SUCCESS) break;
   }
+  const long long dirty = emu_guard_violations();  // before the scratch is released: every buffer of the call is still live
   wholegraph_destroy_multihop_sampler(sp);
+  if (rc == WHOLEMEMORY_SUCCESS && (dirty != 0 || emu_guard_violations() != 0)) rc = -102;  // a write outside a device allocation
+  if (rc == WHOLEMEMORY_SUCCESS && emu_live_allocations() != 0) rc = -103;                  // the sampler object leaked device memory
   for (int k = 0; k < 10; k++) {
     out_ptr[k]   = outs[k].ptr;
     out_count[k] = outs[k].count;
