@@ -12,11 +12,14 @@ from emu_preprocess import rewrite_launches
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "cugraph-gnn_b200", "csrc")
-OUT = os.path.join(HERE, "_build")
+ASAN = os.environ.get("WGB_EMU_ASAN") == "1"  # tests/emu/run_asan.sh: same tests, libraries built with -fsanitize=address
+OUT = os.path.join(HERE, "_build_asan" if ASAN else "_build")
 CUDA_INC = os.environ.get("CUDA_INC", "/usr/local/cuda/include")
 # -Bsymbolic: the stand-ins for the CUDA runtime must win over a real libcudart that torch may have loaded into the process
 FLAGS = ["g++", "-O2", "-std=c++17", "-w", "-DWGB_HOST_EMULATION", "-DWGB_BUILDING_LIB", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-I", HERE, "-I", CSRC,
          "-I", os.path.join(ROOT, "include"), "-I", CUDA_INC]
+if ASAN:
+    FLAGS = [f for f in FLAGS if f != "-O2"] + ["-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer"]
 
 
 def available() -> bool:

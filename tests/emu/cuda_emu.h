@@ -20,6 +20,9 @@
 #include <cuda_runtime.h>  // types (dim3, uint3) and the host-side definitions of __host__/__device__ (empty under g++)
 
 #include <ucontext.h>
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/common_interface_defs.h>  // fiber switch annotations: the emulator can run under AddressSanitizer
+#endif
 
 #include <algorithm>
 #include <cmath>
@@ -85,10 +88,33 @@ inline Idx& cur_idx() { return g_block->fibers[g_block->cur].idx; }
 inline Warp& my_warp() { return g_block->warps[cur_idx().x >> 5]; }
 inline int my_lane() { return (int)(cur_idx().x & 31u); }
 
+// AddressSanitizer has to be told about every stack switch (no-ops otherwise)
+inline const void* g_sched_stack_bottom = nullptr;
+inline size_t g_sched_stack_size        = 0;
+inline void switch_begin(void** fake, const void* bottom, size_t size)
+{
+#if defined(__SANITIZE_ADDRESS__)
+  __sanitizer_start_switch_fiber(fake, bottom, size);
+#else
+  (void)fake; (void)bottom; (void)size;
+#endif
+}
+inline void switch_end(void* fake, const void** old_bottom, size_t* old_size)
+{
+#if defined(__SANITIZE_ADDRESS__)
+  __sanitizer_finish_switch_fiber(fake, old_bottom, old_size);
+#else
+  (void)fake; (void)old_bottom; (void)old_size;
+#endif
+}
+
 inline void yield()
 {
-  Block* b = g_block;
+  Block* b   = g_block;
+  void* fake = nullptr;
+  switch_begin(&fake, g_sched_stack_bottom, g_sched_stack_size);
   swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+  switch_end(fake, nullptr, nullptr);
 }
 
 inline void wait(Bar& bar)
@@ -128,10 +154,12 @@ inline auto exchange(unsigned int mask, unsigned long long v, F&& read)
 
 inline void fiber_entry()
 {
+  switch_end(nullptr, &g_sched_stack_bottom, &g_sched_stack_size);  // first entry: learn the scheduler's stack
   (*g_body)();
   Block* b                = g_block;
   b->fibers[b->cur].done  = true;
   b->progress++;
+  switch_begin(nullptr, g_sched_stack_bottom, g_sched_stack_size);  // nullptr: this fiber's stack is not coming back
   // returning switches to uc_link = the scheduler
 }
 
@@ -170,8 +198,11 @@ inline void launch(unsigned int grid_x, unsigned int grid_y, unsigned int block_
         for (unsigned int t = 0; t < block_x; t++) {
           Fiber& f = blk.fibers[t];
           if (f.done) continue;
-          blk.cur = t;
+          blk.cur    = t;
+          void* fake = nullptr;
+          switch_begin(&fake, g_stacks[t], kStackBytes);
           swapcontext(&blk.sched, &f.ctx);
+          switch_end(fake, nullptr, nullptr);
           if (f.done) remaining--;
         }
         if (remaining && blk.progress == before) {

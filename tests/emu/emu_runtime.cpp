@@ -17,7 +17,11 @@ extern "C" {
 // guard words that are checked when the block is freed -- a kernel or a host-side sizing bug that writes past a scratch
 // buffer shows up as a non-zero emu_guard_violations() instead of passing silently.
 namespace {
+#if defined(__SANITIZE_ADDRESS__)
+constexpr size_t kGuard = 0;  // under AddressSanitizer its own red zones fence the block (and catch out-of-bounds READS too)
+#else
 constexpr size_t kGuard = 64;
+#endif
 std::map<void*, size_t>& live()
 {
   static std::map<void*, size_t> m;
