@@ -1320,11 +1320,33 @@ static void multihop_begin(MhCall& c)
         if (!off_t[t]) continue;
         const unsigned long long type_seed = hop_seed + (unsigned long long)t * 0xD1B54A32D192ED03ULL;
         if (c.temporal) {
-          const int* eligible = static_cast<const int*>(sp->eligible[h].p) + (size_t)t * off_stride;
-          temporal_uniform_kernel<ColT, CHUNKED><<<std::max(1, (int)std::min<long long>(rows_ub, (long long)sms * 16)), kGeneralBlock, 0, st>>>(
-            c.csr[t].row_ptr, c.csr[t].row_ptr_off, c.csr[t].col, c.csr[t].col_off, c.csr[t].etime, c.csr[t].etime_off, frontier,
-            static_cast<const long long*>(sp->ftime[h].p), eligible, c.fanout[h * T + t], c.time_cmp, type_seed, pos_t[t], dest, erow, gid,
-            skip_table_device(), n_rows_dev + h);
+          const int* eligible    = static_cast<const int*>(sp->eligible[h].p) + (size_t)t * off_stride;
+          const long long* ftime = static_cast<const long long*>(sp->ftime[h].p);
+          const MhTypeCsr& g     = c.csr[t];
+          const int M            = c.fanout[h * T + t];
+          const Affine* tab      = skip_table_device();
+          if (c.weighted) {
+            const int grid = std::max(1, (int)std::min<long long>(rows_ub, (long long)sms * 8));
+            auto launch = [&](auto wt_tag, auto block_tag) {
+              using WT             = decltype(wt_tag);
+              constexpr int kBlock = decltype(block_tag)::value;
+              temporal_weighted_kernel<ColT, WT, kBlock, CHUNKED><<<grid, kBlock, 0, st>>>(
+                g.row_ptr, g.row_ptr_off, g.col, g.col_off, g.wgt, g.wgt_off, g.etime, g.etime_off, frontier, ftime, eligible, M, c.time_cmp,
+                type_seed, pos_t[t], dest, erow, gid, tab, n_rows_dev + h);
+            };
+            // BLOCK is part of the random-stream geometry (thread j of BLOCK owns positions j, j + BLOCK, ...), as in launch_hop_sample
+            if (c.wgt_dtype == WHOLEMEMORY_DT_FLOAT) {
+              if (M <= 256) launch(0.f, std::integral_constant<int, 128>{});
+              else launch(0.f, std::integral_constant<int, 256>{});
+            } else {
+              if (M <= 256) launch(0.0, std::integral_constant<int, 128>{});
+              else launch(0.0, std::integral_constant<int, 256>{});
+            }
+          } else {
+            temporal_uniform_kernel<ColT, CHUNKED><<<std::max(1, (int)std::min<long long>(rows_ub, (long long)sms * 16)), kGeneralBlock, 0, st>>>(
+              g.row_ptr, g.row_ptr_off, g.col, g.col_off, g.etime, g.etime_off, frontier, ftime, eligible, M, c.time_cmp, type_seed, pos_t[t],
+              dest, erow, gid, tab, n_rows_dev + h);
+          }
           WGB_CHECK_LAUNCH();
         } else {
           launch_hop_sample<ColT, CHUNKED>(c, c.csr[t], frontier, n_rows_dev + h, rows_ub, c.fanout[h * T + t], type_seed, pos_t[t], dest, erow, gid);
@@ -1639,7 +1661,6 @@ static wholememory_error_code_t multihop_begin_entry(const char* what, wholegrap
   const bool temporal = csr_edge_time != nullptr;
   if (temporal) {
     if (!seed_times || time_cmp < kTimeStrictlyIncreasing || time_cmp > kTimeMonotonicallyDecreasing) return WHOLEMEMORY_INVALID_INPUT;
-    if (csr_weight != nullptr && csr_weight[0] != nullptr) return WHOLEMEMORY_NOT_IMPLEMENTED;  // biased temporal sampling
     auto* td = wholememory_tensor_get_tensor_description(seed_times);
     auto* s0 = wholememory_tensor_get_tensor_description(seeds);
     if (td->dim != 1 || td->dtype != WHOLEMEMORY_DT_INT64 || td->sizes[0] != s0->sizes[0]) return WHOLEMEMORY_INVALID_INPUT;
@@ -1777,9 +1798,9 @@ wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_begin(
 
 wholememory_error_code_t wholegraph_temporal_multihop_neighbor_sample_begin(
   wholegraph_multihop_sampler_t sampler, int num_edge_types, const wholememory_tensor_t* csr_row_ptr,
-  const wholememory_tensor_t* csr_col, const wholememory_tensor_t* csr_edge_time, const wholememory_tensor_t* csr_edge_id,
-  const long long* vertex_type_offsets, int num_vertex_types, int heterogeneous, wholememory_tensor_t seeds,
-  wholememory_tensor_t seed_times, wholememory_tensor_t label_offsets, const int* fanout, int num_hops,
+  const wholememory_tensor_t* csr_col, const wholememory_tensor_t* csr_weight, const wholememory_tensor_t* csr_edge_time,
+  const wholememory_tensor_t* csr_edge_id, const long long* vertex_type_offsets, int num_vertex_types, int heterogeneous,
+  wholememory_tensor_t seeds, wholememory_tensor_t seed_times, wholememory_tensor_t label_offsets, const int* fanout, int num_hops,
   unsigned long long random_state, int time_comparison, int flags, void* stream)
 {
   if (!csr_edge_time || !seed_times) return WHOLEMEMORY_INVALID_INPUT;
@@ -1789,7 +1810,7 @@ wholememory_error_code_t wholegraph_temporal_multihop_neighbor_sample_begin(
     return WHOLEMEMORY_INVALID_INPUT;
   }
   return wgb::multihop_begin_entry("wholegraph_temporal_multihop_neighbor_sample_begin", sampler, num_edge_types, csr_row_ptr, csr_col,
-                                   nullptr, csr_edge_id, heterogeneous ? vertex_type_offsets : nullptr, heterogeneous ? num_vertex_types : 1,
+                                   csr_weight, csr_edge_id, heterogeneous ? vertex_type_offsets : nullptr, heterogeneous ? num_vertex_types : 1,
                                    heterogeneous != 0, seeds, label_offsets, fanout, num_hops, random_state, flags, stream, csr_edge_time,
                                    seed_times, time_comparison);
 }

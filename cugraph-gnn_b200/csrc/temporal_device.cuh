@@ -11,7 +11,8 @@
 //     CSR order, with the stream geometry of the plain sampler, so that an open time window reproduces plain sampling
 //     bit for bit.
 //
-// Three kernels per (hop, edge type): count eligible edges per row, scan the clipped counts, sample.  All of them read
+// Three kernels per (hop, edge type): count eligible edges per row, scan the clipped counts, sample (uniform: the S1 chain
+// over the eligible list; biased: A-Res where only eligible edges compete).  All of them read
 // the whole row (the eligibility of an edge is data), so a temporal hop costs deg(v) * 8 B of edge-time reads per
 // frontier row where the plain sampler touches 16 B of row_ptr: it is bound by the edge-time stream, which is read
 // coalesced (a warp / a CTA walks one row).
@@ -98,6 +99,52 @@ __global__ void __launch_bounds__(kScanBlock) scan_counts_kernel(const int* __re
   }
 }
 
+// Block-wide exclusive prefix over one eligibility flag per thread (BLOCK threads, ballots + BLOCK/32 warp counts in
+// shared memory): returns this thread's index in the chunk's eligible list, `total` = eligible edges of the chunk.
+// Every thread of the block must call it; contains one __syncthreads (callers add one before s_wcnt is reused).
+template <int BLOCK>
+__device__ __forceinline__ int chunk_eligible_index(bool f, int* s_wcnt, int& total)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned int bal = __ballot_sync(0xffffffffu, f);
+  const int within       = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) s_wcnt[wid] = __popc(bal);
+  __syncthreads();
+  int wbase = 0;
+  total     = 0;
+#pragma unroll
+  for (int w = 0; w < BLOCK / 32; w++) {
+    int s = s_wcnt[w];
+    if (w < wid) wbase += s;
+    total += s;
+  }
+  return wbase + within;
+}
+
+// every eligible edge of one row, in CSR order, to out[off ..): the row is walked in chunks of BLOCK positions
+template <typename ColT, bool CHUNKED, int BLOCK>
+__device__ __forceinline__ void copy_eligible_row(const ChunkRef& col, unsigned long long col_off, const ChunkRef& etime,
+                                                  unsigned long long etime_off, long long start, long long end, long long tv, int cmp,
+                                                  int off, int b, ColT* __restrict__ out, int* __restrict__ lid,
+                                                  long long* __restrict__ gid, int* s_wcnt)
+{
+  int running = 0;
+  for (long long chunk = start; chunk < end; chunk += BLOCK) {
+    const long long p = chunk + threadIdx.x;
+    const bool f      = p < end && time_ok(cmp, load_i64<CHUNKED>(etime, etime_off + (unsigned long long)p), tv);
+    int total;
+    const int idx = chunk_eligible_index<BLOCK>(f, s_wcnt, total);
+    if (f) {
+      const int o = off + running + idx;
+      out[o]      = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)p);
+      if (lid) lid[o] = b;
+      if (gid) gid[o] = p;
+    }
+    running += total;
+    __syncthreads();  // s_wcnt is rewritten by the next chunk
+  }
+}
+
 // One CTA per frontier row.  N = eligible[b].  N <= M (or M <= 0): every eligible edge, in CSR order.  Otherwise the
 // chain of uniform_general_kernel picks M indices into the row's eligible list (same draws: thread j of row b uses
 // stream b * T + j, T and the draws per thread from the fan-out tables -- for M <= 32 that is stream 32 b + j, one draw,
@@ -118,7 +165,7 @@ __global__ void __launch_bounds__(kGeneralBlock) temporal_uniform_kernel(
   __shared__ int sel[1024];                   // sel[i]: index of the i-th pick in the row's eligible list
   __shared__ long long s_pos[kGeneralBlock];  // edge positions of the eligible edges of the chunk being walked
   __shared__ int s_wcnt[kGeneralBlock / 32];
-  const int tid = threadIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int tid = threadIdx.x;
   int T = 32, ipt = 1, P = 32, P2 = 64;
   if (M > 0) {
     const int func_idx = (M - 1) / 32;
@@ -190,46 +237,112 @@ __global__ void __launch_bounds__(kGeneralBlock) temporal_uniform_kernel(
       }
       __syncthreads();
     }
-    // walk the row: chunk-wide exclusive prefix of the eligibility flags = index in the eligible list
+    if (take_all) {
+      copy_eligible_row<ColT, CHUNKED, kGeneralBlock>(col, col_off, etime, etime_off, start, end, tv, cmp, off, b, out, lid, gid, s_wcnt);
+      continue;
+    }
+    // walk the row once more: the chunk-wide prefix of the eligibility flags is the index in the eligible list
     int running = 0;
     for (long long chunk = start; chunk < end; chunk += blockDim.x) {
       const long long p = chunk + tid;
       const bool f      = p < end && time_ok(cmp, load_i64<CHUNKED>(etime, etime_off + (unsigned long long)p), tv);
-      const unsigned int bal = __ballot_sync(0xffffffffu, f);
-      const int within       = __popc(bal & ((1u << lane) - 1u));
-      if (lane == 0) s_wcnt[wid] = __popc(bal);
+      int total;
+      const int idx = chunk_eligible_index<kGeneralBlock>(f, s_wcnt, total);
+      if (f) s_pos[idx] = p;
       __syncthreads();
-      int wbase = 0, total = 0;
-#pragma unroll
-      for (int w = 0; w < kGeneralBlock / 32; w++) {
-        int s = s_wcnt[w];
-        if (w < wid) wbase += s;
-        total += s;
-      }
-      const int idx = wbase + within;
-      if (take_all) {
-        if (f) {
-          const int o = off + running + idx;
-          out[o]      = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)p);
-          if (lid) lid[o] = b;
-          if (gid) gid[o] = p;
-        }
-      } else {
-        if (f) s_pos[idx] = p;
-        __syncthreads();
-        for (int i = tid; i < M; i += blockDim.x) {
-          const int a = sel[i] - running;
-          if (a >= 0 && a < total) {
-            const long long q = s_pos[a];
-            out[off + i]      = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)q);
-            if (lid) lid[off + i] = b;
-            if (gid) gid[off + i] = q;
-          }
+      for (int i = tid; i < M; i += blockDim.x) {
+        const int a = sel[i] - running;
+        if (a >= 0 && a < total) {
+          const long long q = s_pos[a];
+          out[off + i]      = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)q);
+          if (lid) lid[off + i] = b;
+          if (gid) gid[off + i] = q;
         }
       }
       running += total;
       __syncthreads();  // s_wcnt / s_pos are rewritten by the next chunk (and sel, keys, ... by the next row)
     }
+  }
+}
+
+// Biased form: the A-Res selection of weighted_kernel (sample_device.cuh: thread j of BLOCK owns positions j, j + BLOCK, ...
+// of the row, stream b * BLOCK + j, key = log2(u) / w, the M largest keys win) where only ELIGIBLE positions draw a key and
+// compete.  Rows with at most M eligible edges return all of them in CSR order.  With every edge eligible this is
+// weighted_kernel (same draws, same candidates).
+template <typename ColT, typename WT, int BLOCK, bool CHUNKED>
+__global__ void __launch_bounds__(BLOCK) temporal_weighted_kernel(
+  ChunkRef row_ptr, unsigned long long row_ptr_off, ChunkRef col, unsigned long long col_off, ChunkRef wgt, unsigned long long wgt_off,
+  ChunkRef etime, unsigned long long etime_off, const long long* __restrict__ centers, const long long* __restrict__ ftime,
+  const int* __restrict__ eligible, int M, int cmp, unsigned long long seed, const int* __restrict__ offsets, ColT* __restrict__ out,
+  int* __restrict__ lid, long long* __restrict__ gid, const Affine* __restrict__ tab, const int* __restrict__ n_dev)
+{
+  const int n = *n_dev;
+  constexpr int C = 2048;
+  __shared__ unsigned long long cand[C];
+  __shared__ int s_cnt;
+  __shared__ unsigned int s_thr;
+  __shared__ int s_wcnt[BLOCK / 32];
+  const int tid = threadIdx.x;
+  for (int b = blockIdx.x; b < n; b += gridDim.x) {
+    const int Ne = eligible[b];
+    if (Ne <= 0) continue;  // block-uniform
+    const unsigned long long node = (unsigned long long)centers[b];
+    const long long start = load_i64<CHUNKED>(row_ptr, row_ptr_off + node);
+    const long long end   = load_i64<CHUNKED>(row_ptr, row_ptr_off + node + 1);
+    const long long tv    = ftime[b];
+    const int N           = (int)(end - start);
+    const int off         = offsets[b];
+    if (M <= 0 || Ne <= M) {
+      copy_eligible_row<ColT, CHUNKED, BLOCK>(col, col_off, etime, etime_off, start, end, tv, cmp, off, b, out, lid, gid, s_wcnt);
+      continue;
+    }
+    if (tid == 0) {
+      s_cnt = 0;
+      s_thr = 0u;
+    }
+    __syncthreads();
+    Pcg rng;
+    rng.init_tab(seed, (unsigned long long)b * BLOCK + (unsigned long long)tid, tab);
+    int ub           = 0;  // block-uniform upper bound of s_cnt
+    const int rounds = (N + BLOCK - 1) / BLOCK;
+    for (int r = 0; r <= rounds; r++) {
+      const bool last = r == rounds;
+      if (last || ub + BLOCK > C) {
+        // compact: keep the M largest
+        int cnt = s_cnt;
+        __syncthreads();
+        for (int i = cnt + tid; i < C; i += BLOCK)
+          cand[i] = 0ULL;
+        __syncthreads();
+        bitonic_sort_smem(cand, C, true);
+        if (tid == 0) {
+          s_cnt = min(cnt, M);
+          s_thr = cnt >= M ? (unsigned int)(cand[M - 1] >> 32) : 0u;
+        }
+        ub = M;
+        __syncthreads();
+        if (last) break;
+      }
+      const int id = r * BLOCK + tid;
+      if (id < N && time_ok(cmp, load_i64<CHUNKED>(etime, etime_off + (unsigned long long)(start + id)), tv)) {
+        WT w             = load_elt<WT, CHUNKED>(wgt, wgt_off + (unsigned long long)(start + id));
+        float key        = gen_key_from_weight_dev<WT>(w, rng);
+        unsigned int enc = float_order_bits(key);
+        if (enc >= s_thr) {
+          int pos   = atomicAdd(&s_cnt, 1);
+          cand[pos] = ((unsigned long long)enc << 32) | (unsigned long long)(0xffffffffu - (unsigned int)id);
+        }
+      }
+      ub += BLOCK;
+      __syncthreads();
+    }
+    for (int i = tid; i < M; i += BLOCK) {
+      const int id = (int)(0xffffffffu - (unsigned int)(cand[i] & 0xffffffffULL));
+      out[off + i] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + id));
+      if (lid) lid[off + i] = b;
+      if (gid) gid[off + i] = start + id;
+    }
+    __syncthreads();
   }
 }
 

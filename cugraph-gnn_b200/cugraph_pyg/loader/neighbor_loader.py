@@ -32,8 +32,6 @@ class NeighborLoader(NodeLoader):
         is_temporal = time_attr is not None
         if input_time is not None and not is_temporal:
             raise ValueError("input_time needs time_attr (the name of the edge time attribute)")
-        if is_temporal and weight_attr is not None:
-            raise NotImplementedError("biased temporal sampling is not implemented (DESIGN.md §10)")
         if replace:
             raise NotImplementedError("sampling with replacement is outside the B200 hot path")
         if disjoint:

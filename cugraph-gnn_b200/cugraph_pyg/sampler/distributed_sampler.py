@@ -192,8 +192,6 @@ class DistributedNeighborSampler(BaseDistributedSampler):
                  compression: str = "COO", compress_per_hop: bool = False, with_replacement: bool = False,
                  disjoint: bool = False, biased: bool = False, heterogeneous: bool = False, temporal: bool = False,
                  temporal_comparison: Optional[str] = None, vertex_type_offsets=None, num_edge_types: int = 1):
-        if temporal and biased:
-            raise NotImplementedError("biased temporal sampling is not implemented (DESIGN.md §10)")
         if num_edge_types > 1 and not heterogeneous:
             raise ValueError("Heterogeneous sampling must be selected if there is > 1 edge type.")
         self.__fanout = [int(f) for f in np.asarray(fanout).reshape(-1)]
@@ -207,6 +205,8 @@ class DistributedNeighborSampler(BaseDistributedSampler):
             (True, True, False): pylibcugraph.heterogeneous_biased_neighbor_sample,
             (False, False, True): pylibcugraph.homogeneous_uniform_temporal_neighbor_sample,
             (True, False, True): pylibcugraph.heterogeneous_uniform_temporal_neighbor_sample,
+            (False, True, True): pylibcugraph.homogeneous_biased_temporal_neighbor_sample,
+            (True, True, True): pylibcugraph.heterogeneous_biased_temporal_neighbor_sample,
         }
         self.__func = table[(self.__heterogeneous, bool(biased), self.__temporal)]
         self.__func_kwargs = {

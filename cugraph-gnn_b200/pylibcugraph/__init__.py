@@ -13,8 +13,8 @@ Differences that callers can observe:
   * the random stream is this project's (S1/S2 geometry per hop), not libcugraph's -- unverifiable either way;
   * heterogeneous sampling keeps one CSR per edge type (built lazily from edge_type_array) and follows the definition in
     include/wholememory/b200_ops.h: edge_id indexes edge_renumber_map per (label, edge type);
-  * temporal sampling (edge_start_time_array + the *_uniform_temporal_* entry points) follows the definition in
-    include/wholememory/b200_ops.h; the biased temporal entry points raise NotImplementedError;
+  * temporal sampling (edge_start_time_array + the *_temporal_* entry points, uniform and biased) follows the definition in
+    include/wholememory/b200_ops.h;
   * with_replacement=True and disjoint_sampling=True raise NotImplementedError.
 """
 from typing import Optional
@@ -126,14 +126,14 @@ class SGGraph:
         return self._typed[num_edge_types]
 
     @staticmethod
-    def _drop_zero_weight(row_ptr, col, weight, edge_id):
+    def _drop_zero_weight(row_ptr, col, weight, edge_id, edge_time=None):
         """pylibcugraph never samples an edge whose bias is zero, even when the row has fewer candidates than the fan-out
         (pinned by the reference's test_neighbor_loader.py:97-133); the WholeGraph A-Res sampler takes every neighbour of
         a row with deg <= fan-out.  Sampling on the CSR without its zero-weight edges gives pylibcugraph's behaviour
         exactly; edge ids keep pointing at the caller's edges."""
         keep = weight > 0
         if bool(keep.all()):
-            return row_ptr, col, weight, edge_id
+            return row_ptr, col, weight, edge_id, edge_time
         n = row_ptr.numel() - 1
         rows = torch.repeat_interleave(torch.arange(n, device=col.device), row_ptr[1:] - row_ptr[:-1])
         sel = torch.nonzero(keep).reshape(-1)
@@ -142,17 +142,18 @@ class SGGraph:
             rp[1:] = torch.bincount(rows[sel], minlength=n).cumsum(0)
         if edge_id is None:
             edge_id = torch.arange(col.numel(), dtype=torch.int64, device=col.device)
-        return rp, col[sel].contiguous(), weight[sel].contiguous(), edge_id[sel].contiguous()
+        return (rp, col[sel].contiguous(), weight[sel].contiguous(), edge_id[sel].contiguous(),
+                None if edge_time is None else edge_time[sel].contiguous())
 
     def _drop_zero_weight_cached(self):
         if "biased_all" not in self._typed:
-            self._typed["biased_all"] = self._drop_zero_weight(self.row_ptr, self.col, self.weight, self.edge_id)
+            self._typed["biased_all"] = self._drop_zero_weight(self.row_ptr, self.col, self.weight, self.edge_id, self.edge_time)
         return self._typed["biased_all"]
 
     def _biased_csrs(self, num_edge_types: int):
         key = ("biased", num_edge_types)
         if key not in self._typed:
-            self._typed[key] = [self._drop_zero_weight(*g[:4]) for g in self._typed_csrs(num_edge_types)]
+            self._typed[key] = [self._drop_zero_weight(*g) for g in self._typed_csrs(num_edge_types)]
         return self._typed[key]
 
     def _get_sampler(self):
@@ -233,7 +234,7 @@ def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offse
     row_ptr, col, weight, edge_id = input_graph.row_ptr, input_graph.col, None, input_graph.edge_id
     if biased:
         # one CSR (edge types, if any, are ignored by the homogeneous entry point), zero-bias edges removed
-        row_ptr, col, weight, edge_id = input_graph._drop_zero_weight_cached()
+        row_ptr, col, weight, edge_id, _ = input_graph._drop_zero_weight_cached()
     pend = input_graph._get_sampler().sample_async(row_ptr, col, seeds, offsets, fanout, int(random_state), csr_weight=weight,
                                                    csr_edge_id=edge_id, compression=compression, int64_ids=True)
     pend.want_seed_local_ids = bool(return_seed_local_ids)
@@ -337,14 +338,14 @@ def heterogeneous_biased_neighbor_sample(resource_handle, input_graph, start_ver
                                    vertex_type_offsets, True, **kwargs)
 
 
-def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, *, heterogeneous,
+def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, *, heterogeneous, biased=False,
                               num_edge_types=1, vertex_type_offsets=None, starting_vertex_times=None,
                               temporal_property_name=None, temporal_sampling_comparison="strictly_increasing",
                               with_replacement=False, do_expensive_check=False, prior_sources_behavior=None,
                               deduplicate_sources=False, return_hops=False, renumber=False, retain_seeds=False,
                               compression="COO", compress_per_hop=False, random_state=None, disjoint_sampling=False,
                               return_dict=True, return_seed_local_ids=False, **unused):
-    """pylibcugraph.{homogeneous,heterogeneous}_uniform_temporal_neighbor_sample (reference call site:
+    """pylibcugraph.{homogeneous,heterogeneous}_{uniform,biased}_temporal_neighbor_sample (reference call site:
     python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:56-80, 808-810, 897-900).  Edge times are the graph's
     edge_start_time_array; without starting_vertex_times the first hop is unconstrained."""
     if with_replacement:
@@ -359,6 +360,8 @@ def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_la
         raise NotImplementedError("only deduplicate_sources=True with prior_sources_behavior='exclude' is supported")
     if input_graph.edge_time is None:
         raise ValueError("temporal sampling needs a graph built with edge_start_time_array")
+    if biased and input_graph.weight is None:
+        raise ValueError("biased sampling needs a graph with edge weights")
     from pylibwholegraph.torch.multihop import TIME_COMPARISONS
 
     if temporal_sampling_comparison not in TIME_COMPARISONS:
@@ -384,8 +387,12 @@ def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_la
         raise ValueError(f"Illegal fanout for {T} edge types.")
     if random_state is None:
         random_state = int(np.random.randint(0, 2**62))
-    typed = input_graph._typed_csrs(T) if heterogeneous else [(input_graph.row_ptr, input_graph.col, None, input_graph.edge_id,
-                                                               input_graph.edge_time)]
+    if heterogeneous:
+        typed = input_graph._biased_csrs(T) if biased else input_graph._typed_csrs(T)
+    elif biased:
+        typed = [input_graph._drop_zero_weight_cached()]  # zero-bias edges are never sampled (see _drop_zero_weight)
+    else:
+        typed = [(input_graph.row_ptr, input_graph.col, None, input_graph.edge_id, input_graph.edge_time)]
     vto = None
     if heterogeneous:
         vto = [int(v) for v in torch.as_tensor(vertex_type_offsets).reshape(-1).tolist()]
@@ -393,7 +400,7 @@ def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_la
         [g[0] for g in typed], [g[1] for g in typed], [g[4] for g in typed], seeds, times, offsets, fanout, int(random_state),
         temporal_sampling_comparison, vertex_type_offsets=vto,
         csr_edge_ids=[g[3] for g in typed] if all(g[3] is not None for g in typed) else None,
-        compression=compression, int64_ids=True)
+        csr_weights=[g[2] for g in typed] if biased else None, compression=compression, int64_ids=True)
     pend.want_seed_local_ids = bool(return_seed_local_ids)
     res = pend.result()
     extra = {"seed_local_ids": res["seed_local_ids"]} if return_seed_local_ids else {}
@@ -429,16 +436,18 @@ def heterogeneous_uniform_temporal_neighbor_sample(resource_handle, input_graph,
                                      **kwargs)
 
 
-def _not_on_path(name):
-    def fn(*args, **kwargs):
-        raise NotImplementedError(f"pylibcugraph.{name}: biased temporal sampling is not implemented (DESIGN.md §10)")
-
-    fn.__name__ = name
-    return fn
+def homogeneous_biased_temporal_neighbor_sample(resource_handle, input_graph, start_vertex_list,
+                                                starting_vertex_label_offsets, h_fan_out, **kwargs):
+    return _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out,
+                                     heterogeneous=False, biased=True, **kwargs)
 
 
-homogeneous_biased_temporal_neighbor_sample = _not_on_path("homogeneous_biased_temporal_neighbor_sample")
-heterogeneous_biased_temporal_neighbor_sample = _not_on_path("heterogeneous_biased_temporal_neighbor_sample")
+def heterogeneous_biased_temporal_neighbor_sample(resource_handle, input_graph, start_vertex_list,
+                                                  starting_vertex_label_offsets, vertex_type_offsets=None, h_fan_out=None,
+                                                  num_edge_types=1, **kwargs):
+    return _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out,
+                                     heterogeneous=True, biased=True, num_edge_types=num_edge_types,
+                                     vertex_type_offsets=vertex_type_offsets, **kwargs)
 
 
 def negative_sampling(resource_handle, graph, num_samples, random_state=None, vertices=None, src_bias=None, dst_bias=None,

@@ -42,7 +42,7 @@ _hfinish.argtypes = [_vp] * 13
 
 _tbegin = wmb.native_symbol("wholegraph_temporal_multihop_neighbor_sample_begin")
 _tbegin.restype = ctypes.c_int
-_tbegin.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+_tbegin.argtypes = [_vp, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
                     ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, ctypes.POINTER(ctypes.c_int),
                     ctypes.c_int, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int, _vp]
 
@@ -153,11 +153,13 @@ class MultiHopSampler(object):
 
     def sample_temporal_async(self, csr_row_ptrs, csr_cols, csr_edge_times, seeds: "torch.Tensor", seed_times: "torch.Tensor",
                               label_offsets: "torch.Tensor", fanout: List[int], random_state: int, comparison: str, *,
-                              vertex_type_offsets=None, csr_edge_ids=None, compression: str = "COO", int64_ids: bool = False):
+                              vertex_type_offsets=None, csr_edge_ids=None, csr_weights=None, compression: str = "COO",
+                              int64_ids: bool = False):
         """Temporal call group (include/wholememory/b200_ops.h: wholegraph_temporal_multihop_neighbor_sample_begin).
         ``csr_edge_times[t]`` int64 per edge type in CSR order, ``seed_times`` int64 [S], ``comparison`` one of
         TIME_COMPARISONS.  ``vertex_type_offsets`` given: heterogeneous arguments and result (PendingHeteroSample);
-        None: one edge type, homogeneous result (PendingSample)."""
+        None: one edge type, homogeneous result (PendingSample).  ``csr_weights[t]`` (fp32 / fp64): biased instead of
+        uniform selection among the eligible edges."""
         assert seeds.is_cuda and seeds.dim() == 1 and seeds.dtype in (torch.int32, torch.int64)
         if comparison not in TIME_COMPARISONS:
             raise ValueError("temporal comparison must be one of %s, got %r" % (sorted(TIME_COMPARISONS), comparison))
@@ -183,7 +185,7 @@ class MultiHopSampler(object):
             return arr
 
         rp, col, tim = handle_array(csr_row_ptrs), handle_array(csr_cols), handle_array(csr_edge_times)
-        eid = handle_array(csr_edge_ids)
+        eid, wgt = handle_array(csr_edge_ids), handle_array(csr_weights)
         hs, ks = _handle(seeds)
         ht, kt = _handle(seed_times)
         hl, kl = _handle(label_offsets)
@@ -193,7 +195,7 @@ class MultiHopSampler(object):
         fan = (ctypes.c_int * len(fanout))(*[int(f) for f in fanout])
         hops = len(fanout) // T
         flags = (FLAG_CSR if csr else 0) | (FLAG_INT64_IDS if int64_ids else 0)
-        err = _tbegin(self._h, T, rp, col, tim, eid, vto_c, len(vto) - 1, 1 if hetero else 0, hs, ht, hl, fan, hops,
+        err = _tbegin(self._h, T, rp, col, wgt, tim, eid, vto_c, len(vto) - 1, 1 if hetero else 0, hs, ht, hl, fan, hops,
                       ctypes.c_ulonglong(random_state & 0xFFFFFFFFFFFFFFFF), TIME_COMPARISONS[comparison], flags, get_stream())
         wmb.check_wholememory_error_code(err)
         if hetero:

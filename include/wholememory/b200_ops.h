@@ -177,7 +177,7 @@ wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_finish(whole
                                                                            wholememory_env_func_t* p_env_fns,
                                                                            void* stream);
 
-/* Temporal form: what cugraph-pyg asks of pylibcugraph.{homogeneous,heterogeneous}_uniform_temporal_neighbor_sample
+/* Temporal form: what cugraph-pyg asks of pylibcugraph.{homogeneous,heterogeneous}_{uniform,biased}_temporal_neighbor_sample
  * (/root/reference/python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:56-80, 808-810, 897-900; behaviour
  * pinned by /root/reference/python/cugraph-pyg/cugraph_pyg/tests/loader/test_neighbor_loader.py:943-1058).
  *
@@ -191,13 +191,16 @@ wholememory_error_code_t wholegraph_hetero_multihop_neighbor_sample_finish(whole
  *                      vertex_type_offsets is ignored, finish with wholegraph_multihop_neighbor_sample_finish
  *   The uniform one-hop algorithm runs over the eligible edges of a row in CSR order with the plain sampler's random
  *   streams: with every edge eligible the call returns exactly what the non-temporal call returns.
- *   Biased temporal sampling is not implemented.
+ *   csr_weight         NULL: uniform.  Otherwise fp32 | fp64 [E_t] per edge type (all types): the A-Res selection of the
+ *                      biased sampler in which only eligible edges draw a key and compete; a row with at most `fanout`
+ *                      eligible edges returns all of them in CSR order.  Same open-window identity.
  *   STATUS: compiled for sm_100a, not yet run on a GPU.
  */
 wholememory_error_code_t wholegraph_temporal_multihop_neighbor_sample_begin(wholegraph_multihop_sampler_t sampler,
                                                                             int num_edge_types,
                                                                             const wholememory_tensor_t* csr_row_ptr,
                                                                             const wholememory_tensor_t* csr_col,
+                                                                            const wholememory_tensor_t* csr_weight,
                                                                             const wholememory_tensor_t* csr_edge_time,
                                                                             const wholememory_tensor_t* csr_edge_id,
                                                                             const long long* vertex_type_offsets,

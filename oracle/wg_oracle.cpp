@@ -848,7 +848,9 @@ static inline bool wgo_time_ok(int cmp, int64_t edge_time, int64_t vertex_time)
 // tests/loader/test_neighbor_loader.py:943-1058): a frontier vertex carries a time (seed: its starting time; otherwise
 // the time of the edge that first reached it); only the edges of its row whose time compares as requested are eligible;
 // the one-hop uniform algorithm (S1) runs over the ELIGIBLE positions of the row, in CSR order, with the same stream
-// geometry.  Temporal + biased is not restated yet.
+// geometry.  Temporal + biased: the A-Res algorithm (S2) with its own geometry (thread j of `block` owns positions j,
+// j + block, ... of the row) where only eligible positions draw a key and compete; rows with at most `fanout` eligible
+// edges return all of them in CSR order.  Both reduce to the plain samplers when every edge is eligible.
 static void* wgo_hetero_impl(int num_edge_types, const int64_t* const* row_ptr, const void* const* col, int col_dtype,
                              const void* const* wgt, int wgt_dtype, const int64_t* const* edge_ids,
                              const int64_t* vtype_offsets, int num_vertex_types, const int64_t* seeds,
@@ -923,6 +925,36 @@ static void* wgo_hetero_impl(int num_edge_types, const int64_t* const* row_ptr, 
           if (M < 0 || N <= M) {
             for (int64_t p : elig)
               take(p);
+            continue;
+          }
+          if (wgt) {
+            // S2 over the eligible positions (weighted_row above, masked); output in ascending key order like weighted_row
+            const int block     = M > 256 ? 256 : 128;
+            const int64_t start = row_ptr[t][v], deg = row_ptr[t][v + 1] - row_ptr[t][v];
+            typedef std::pair<float, int64_t> KI;
+            auto cmp = [](const KI& l, const KI& r) { return l.first > r.first; };
+            std::priority_queue<KI, std::vector<KI>, decltype(cmp)> heap(cmp);
+            int processed = 0;
+            for (int j = 0; j < block; j++) {
+              Pcg rng;
+              rng.init_raft(hs, 0, (uint64_t)(f * block + j));
+              for (int64_t id = j; id < deg; id += block) {
+                if (!wgo_time_ok(time_cmp, edge_times[t][start + id], ftime[f])) continue;
+                float key = wgt_dtype == DT_FLOAT ? gen_key_from_weight<float>(((const float*)wgt[t])[start + id], rng)
+                                                  : gen_key_from_weight<double>(((const double*)wgt[t])[start + id], rng);
+                processed++;
+                if (processed <= M) {
+                  heap.push(KI(key, start + id));
+                } else if (heap.top().first < key) {
+                  heap.pop();
+                  heap.push(KI(key, start + id));
+                }
+              }
+            }
+            for (int i = 0; i < M; i++) {
+              take(heap.top().second);
+              heap.pop();
+            }
             continue;
           }
           int func_idx = (M - 1) / 32;
@@ -1058,6 +1090,16 @@ void* wgo_temporal_multihop_sample(int num_edge_types, const int64_t* const* row
                                    const int32_t* fanout, int num_hops, uint64_t random_state, int time_cmp)
 {
   return wgo_hetero_impl(num_edge_types, row_ptr, col, col_dtype, nullptr, 0, edge_ids, vtype_offsets, num_vertex_types, seeds,
+                         label_offsets, num_labels, fanout, num_hops, random_state, edge_times, seed_times, time_cmp);
+}
+
+void* wgo_temporal_biased_multihop_sample(int num_edge_types, const int64_t* const* row_ptr, const void* const* col, int col_dtype,
+                                          const void* const* wgt, int wgt_dtype, const int64_t* const* edge_ids,
+                                          const int64_t* const* edge_times, const int64_t* vtype_offsets, int num_vertex_types,
+                                          const int64_t* seeds, const int64_t* seed_times, const int64_t* label_offsets,
+                                          int64_t num_labels, const int32_t* fanout, int num_hops, uint64_t random_state, int time_cmp)
+{
+  return wgo_hetero_impl(num_edge_types, row_ptr, col, col_dtype, wgt, wgt_dtype, edge_ids, vtype_offsets, num_vertex_types, seeds,
                          label_offsets, num_labels, fanout, num_hops, random_state, edge_times, seed_times, time_cmp);
 }
 

@@ -334,10 +334,10 @@ TIME_CMP = {"strictly_increasing": 0, "monotonically_increasing": 1, "strictly_d
 
 
 def temporal_multihop_sample(row_ptrs, cols, edge_times, vertex_type_offsets, seeds, seed_times, label_offsets, fanout,
-                             random_state, comparison="strictly_increasing", edge_ids=None):
-    """Temporal (uniform) multi-hop sample over typed CSRs: edge_times[t] int64 [E_t], seed_times int64 [S]; a vertex is
-    sampled only through edges whose time compares as requested with the time it was reached at.  ORACLE ONLY this
-    round: the product has no temporal path yet."""
+                             random_state, comparison="strictly_increasing", edge_ids=None, weights=None):
+    """Temporal multi-hop sample over typed CSRs: edge_times[t] int64 [E_t], seed_times int64 [S]; a vertex is sampled only
+    through edges whose time compares as requested with the time it was reached at.  weights[t] (fp32 / fp64, all types):
+    biased (A-Res over the eligible edges) instead of uniform."""
     T = len(row_ptrs)
     row_ptrs = [np.ascontiguousarray(r, dtype=np.int64) for r in row_ptrs]
     cols = [np.ascontiguousarray(c) for c in cols]
@@ -359,11 +359,20 @@ def temporal_multihop_sample(row_ptrs, cols, edge_times, vertex_type_offsets, se
     if edge_ids is not None:
         edge_ids = [None if e is None else np.ascontiguousarray(e, dtype=np.int64) for e in edge_ids]
         e_arr = ptr_array(edge_ids)
-    fn = lib().wgo_temporal_multihop_sample
-    fn.restype = ctypes.c_void_p
-    h = fn(ctypes.c_int(T), ptr_array(row_ptrs), ptr_array(cols), _dt(cols[0]), e_arr, ptr_array(edge_times), _p(vto), ctypes.c_int(Vt),
-           _p(seeds), _p(seed_times), _p(label_offsets), ctypes.c_int64(B), _p(fanout), ctypes.c_int(L), ctypes.c_uint64(random_state),
-           ctypes.c_int(TIME_CMP[comparison]))
+    if weights is None:
+        fn = lib().wgo_temporal_multihop_sample
+        fn.restype = ctypes.c_void_p
+        h = fn(ctypes.c_int(T), ptr_array(row_ptrs), ptr_array(cols), _dt(cols[0]), e_arr, ptr_array(edge_times), _p(vto), ctypes.c_int(Vt),
+               _p(seeds), _p(seed_times), _p(label_offsets), ctypes.c_int64(B), _p(fanout), ctypes.c_int(L), ctypes.c_uint64(random_state),
+               ctypes.c_int(TIME_CMP[comparison]))
+    else:
+        weights = [np.ascontiguousarray(w) for w in weights]
+        assert all(w.dtype == weights[0].dtype and w.dtype in (np.float32, np.float64) for w in weights)
+        fn = lib().wgo_temporal_biased_multihop_sample
+        fn.restype = ctypes.c_void_p
+        h = fn(ctypes.c_int(T), ptr_array(row_ptrs), ptr_array(cols), _dt(cols[0]), ptr_array(weights), _dt(weights[0]), e_arr,
+               ptr_array(edge_times), _p(vto), ctypes.c_int(Vt), _p(seeds), _p(seed_times), _p(label_offsets), ctypes.c_int64(B), _p(fanout),
+               ctypes.c_int(L), ctypes.c_uint64(random_state), ctypes.c_int(TIME_CMP[comparison]))
     h = vp(h)
     lib().wgo_hetero_num_edges.restype = ctypes.c_int64
     lib().wgo_hetero_num_nodes.restype = ctypes.c_int64

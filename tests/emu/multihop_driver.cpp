@@ -55,14 +55,14 @@ extern "C" {
 // outs[k] receive malloc'ed arrays (freed by emu_free): heterogeneous order = majors, minors, edge_id, edge_type,
 // label_type_hop_offsets, renumber_map, renumber_map_offsets, edge_renumber_map, edge_renumber_map_offsets, step base;
 // homogeneous order = majors, minors, edge_id, label_hop_offsets, renumber_map, renumber_map_offsets, major_offsets, step base.
-// col_is_int64: dtype of the cols; edge_time == NULL: the plain (non-temporal) call; weights are not supported here.
+// col_is_int64: dtype of the cols; edge_time == NULL: the plain (non-temporal) call; weight == NULL: uniform.
 int emu_multihop(int T, const long long* const* row_ptr, long long V, const void* const* col, const long long* num_edges, int col_is_int64,
-                 const long long* const* edge_time, const long long* const* edge_id, const long long* vto, int Vt, int hetero,
+                 const long long* const* edge_time, const void* const* weight, int weight_is_double, const long long* const* edge_id, const long long* vto, int Vt, int hetero,
                  const long long* seeds, const long long* seed_times, long long S, const long long* label_offsets, long long B, const int* fanout,
                  int hops, unsigned long long random_state, int cmp, int flags, int reps, void** out_ptr, long long* out_count, int* out_elt)
 {
-  std::vector<wholememory_tensor_> rp(T), cl(T), tm(T), ei(T);
-  std::vector<wholememory_tensor_t> rp_h(T), cl_h(T), tm_h(T), ei_h(T);
+  std::vector<wholememory_tensor_> rp(T), cl(T), tm(T), ei(T), wt(T);
+  std::vector<wholememory_tensor_t> rp_h(T), cl_h(T), tm_h(T), ei_h(T), wt_h(T);
   bool any_eid = false;
   for (int t = 0; t < T; t++) {
     rp[t]   = make_tensor(row_ptr[t], V + 1, WHOLEMEMORY_DT_INT64);
@@ -72,6 +72,10 @@ int emu_multihop(int T, const long long* const* row_ptr, long long V, const void
     if (edge_time) {
       tm[t]   = make_tensor(edge_time[t], num_edges[t], WHOLEMEMORY_DT_INT64);
       tm_h[t] = &tm[t];
+    }
+    if (weight) {
+      wt[t]   = make_tensor(weight[t], num_edges[t], weight_is_double ? WHOLEMEMORY_DT_DOUBLE : WHOLEMEMORY_DT_FLOAT);
+      wt_h[t] = &wt[t];
     }
     ei_h[t] = nullptr;
     if (edge_id && edge_id[t]) {
@@ -96,13 +100,14 @@ int emu_multihop(int T, const long long* const* row_ptr, long long V, const void
       o = Out();
     }
     if (edge_time) {
-      rc = wholegraph_temporal_multihop_neighbor_sample_begin(sp, T, rp_h.data(), cl_h.data(), tm_h.data(), any_eid ? ei_h.data() : nullptr, vto, Vt,
-                                                              hetero, &sd, &st, &lo, fanout, hops, random_state, cmp, flags, nullptr);
+      rc = wholegraph_temporal_multihop_neighbor_sample_begin(sp, T, rp_h.data(), cl_h.data(), weight ? wt_h.data() : nullptr, tm_h.data(),
+                                                              any_eid ? ei_h.data() : nullptr, vto, Vt, hetero, &sd, &st, &lo, fanout, hops,
+                                                              random_state, cmp, flags, nullptr);
     } else if (hetero) {
-      rc = wholegraph_hetero_multihop_neighbor_sample_begin(sp, T, rp_h.data(), cl_h.data(), nullptr, any_eid ? ei_h.data() : nullptr, vto, Vt, &sd,
+      rc = wholegraph_hetero_multihop_neighbor_sample_begin(sp, T, rp_h.data(), cl_h.data(), weight ? wt_h.data() : nullptr, any_eid ? ei_h.data() : nullptr, vto, Vt, &sd,
                                                             &lo, fanout, hops, random_state, flags, nullptr);
     } else {
-      rc = wholegraph_multihop_neighbor_sample_begin(sp, rp_h[0], cl_h[0], nullptr, ei_h[0], &sd, &lo, fanout, hops, random_state, flags, nullptr);
+      rc = wholegraph_multihop_neighbor_sample_begin(sp, rp_h[0], cl_h[0], weight ? wt_h[0] : nullptr, ei_h[0], &sd, &lo, fanout, hops, random_state, flags, nullptr);
     }
     if (rc != WHOLEMEMORY_SUCCESS) break;
     if (hetero) {

@@ -37,7 +37,7 @@ def emu():
 
 
 def _run(lib, row_ptrs, cols, vto, seeds, lo, fanout, random_state, *, hetero=True, times=None, seed_times=None, cmp=0, eids=None,
-         flags=FLAG_INT64, expect_rc=0, reps=1):
+         flags=FLAG_INT64, expect_rc=0, reps=1, weights=None):
     T = len(row_ptrs)
     rp = [np.ascontiguousarray(r, dtype=np.int64) for r in row_ptrs]
     cl = [np.ascontiguousarray(c) for c in cols]
@@ -45,6 +45,7 @@ def _run(lib, row_ptrs, cols, vto, seeds, lo, fanout, random_state, *, hetero=Tr
     ne = np.array([c.shape[0] for c in cl], dtype=np.int64)
     tm = None if times is None else [np.ascontiguousarray(t, dtype=np.int64) for t in times]
     ei = None if eids is None else [None if e is None else np.ascontiguousarray(e, dtype=np.int64) for e in eids]
+    wt = None if weights is None else [np.ascontiguousarray(w) for w in weights]
     vto = np.ascontiguousarray(vto, dtype=np.int64)
     seeds = np.ascontiguousarray(seeds, dtype=np.int64)
     st = np.zeros_like(seeds) if seed_times is None else np.ascontiguousarray(seed_times, dtype=np.int64)
@@ -57,7 +58,8 @@ def _run(lib, row_ptrs, cols, vto, seeds, lo, fanout, random_state, *, hetero=Tr
     out_ptr, out_cnt, out_elt = (VP * 10)(), (ctypes.c_longlong * 10)(), (ctypes.c_int * 10)()
     lib.emu_multihop.restype = ctypes.c_int
     rc = lib.emu_multihop(T, arr(rp), ctypes.c_longlong(rp[0].shape[0] - 1), arr(cl), ne.ctypes.data_as(VP), int(is64),
-                          None if tm is None else arr(tm), None if ei is None else arr(ei), vto.ctypes.data_as(VP), vto.shape[0] - 1,
+                          None if tm is None else arr(tm), None if wt is None else arr(wt), int(wt is not None and wt[0].dtype == np.float64),
+                          None if ei is None else arr(ei), vto.ctypes.data_as(VP), vto.shape[0] - 1,
                           int(hetero), seeds.ctypes.data_as(VP), st.ctypes.data_as(VP), ctypes.c_longlong(seeds.shape[0]), lo.ctypes.data_as(VP),
                           ctypes.c_longlong(lo.shape[0] - 1), fo.ctypes.data_as(VP), fo.shape[0] // T, ctypes.c_ulonglong(random_state), cmp,
                           flags, reps, out_ptr, out_cnt, out_elt)
@@ -190,3 +192,89 @@ def test_emulated_temporal_argument_checks(emu):
     tm = [np.zeros(300, dtype=np.int64)]
     _run(emu, row_ptrs, cols, vto, seeds, lo, [2], 1, hetero=False, times=tm, seed_times=np.zeros(10, np.int64), cmp=7, expect_rc=6)  # INVALID_INPUT
     _run(emu, row_ptrs, cols, vto, seeds, lo, [2000], 1, hetero=False, times=tm, seed_times=np.zeros(10, np.int64), cmp=0, expect_rc=2)  # NOT_IMPLEMENTED
+
+
+# ---- biased temporal --------------------------------------------------------------------------------------------------------
+def _rows_as_sets(out, T, L, B):
+    """{(label, type, hop, major): sorted original edge ids} of a heterogeneous result."""
+    lto, groups = out["label_type_hop_offsets"], {}
+    for l in range(B):
+        for t in range(T):
+            for h in range(L):
+                a, b = lto[(l * T + t) * L + h], lto[(l * T + t) * L + h + 1]
+                for m, e in zip(out["majors"][a:b].tolist(), out["edge_renumber_map"][a:b].tolist()):
+                    groups.setdefault((l, t, h, m), []).append(e)
+    return {k: sorted(v) for k, v in groups.items()}
+
+
+@pytest.mark.parametrize("wdtype", [np.float32, np.float64])
+def test_emulated_biased_temporal_open_window_equals_plain_biased(emu, wdtype):
+    """Every edge eligible: the masked A-Res kernel must be weighted_kernel (same draws, same candidates, same order), over
+    two hops and three edge types."""
+    vto, row_ptrs, cols, seeds, lo, rng = _typed_case()
+    wts = [(rng.random(c.shape[0]) + 0.01).astype(wdtype) for c in cols]
+    times = [np.full(c.shape[0], 3, dtype=np.int64) for c in cols]
+    for fanout in ([4, 3, 2, 2, 2, 2],) if wdtype is np.float64 else ([4, 3, 2, 2, 2, 2], [40, 3, 20, 2, 2, 2]):
+        plain = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 5, weights=wts)
+        temp = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 5, weights=wts, times=times, seed_times=np.full_like(seeds, 3), cmp=3)
+        assert plain["majors"].shape[0] > 0
+        _same(temp, plain, HETERO)
+
+
+@pytest.mark.parametrize("comparison", [0, 3])
+def test_emulated_biased_temporal_one_hop_sets_match_oracle(emu, oracle, comparison):
+    """One hop: per frontier row the SET of sampled edges equals the oracle's (the reference compares weighted samples as
+    sets; the oracle lists a row in ascending key order, the kernel in descending order)."""
+    vto, row_ptrs, cols, seeds, lo, rng = _typed_case()
+    wts = [(rng.random(c.shape[0]) + 0.01).astype(np.float32) for c in cols]
+    times = [rng.integers(0, 50, c.shape[0]).astype(np.int64) for c in cols]
+    seed_times = ((10 if comparison < 2 else 40) + rng.integers(-5, 6, seeds.shape[0])).astype(np.int64)
+    fanout = [4, 40, 3]
+    got = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 77, weights=wts, times=times, seed_times=seed_times, cmp=comparison)
+    exp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, seed_times, lo, fanout, 77, COMPARISONS[comparison], weights=wts)
+    _same(got, exp, ["label_type_hop_offsets", "majors", "edge_type", "edge_id", "edge_renumber_map_offsets"])  # counts are data only
+    a, b = _rows_as_sets(got, 3, 1, 4), _rows_as_sets(exp, 3, 1, 4)
+    assert a == b and len(a) > 100
+    assert sorted(got["renumber_map"].tolist()) == sorted(exp["renumber_map"].tolist())
+
+
+def test_emulated_biased_temporal_two_hops_are_valid(emu):
+    """Two hops, two edge types over ONE vertex type (local ids are then frontier rows, so the hop's edge order -- source row,
+    edge type, slot -- can be rebuilt from the output): every sampled edge is eligible with respect to the time its source
+    carries (seed time / time of the edge that reached it first), rows hold min(eligible, fan-out) distinct edges."""
+    vto, row_ptrs, cols = random_typed_graph([1500], [(0, 0), (0, 0)], [20000, 45000], seed=21)
+    rng = np.random.default_rng(8)
+    T, L, B = 2, 2, 3
+    seeds = rng.integers(0, 1500, 90).astype(np.int64)
+    lo = np.array([0, 30, 60, 90], dtype=np.int64)
+    wts = [(rng.random(c.shape[0]) + 0.01).astype(np.float32) for c in cols]
+    times = [rng.integers(0, 50, c.shape[0]).astype(np.int64) for c in cols]
+    seed_times = (10 + rng.integers(-5, 6, seeds.shape[0])).astype(np.int64)
+    fanout = [3, 5, 4, 2]
+    out = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 9, weights=wts, times=times, seed_times=seed_times, cmp=1)
+    lto, rmo = out["label_type_hop_offsets"], out["renumber_map_offsets"]
+    checked = 0
+    for l in range(B):
+        gmap = out["renumber_map"][rmo[l]:rmo[l + 1]]
+        vtime = {}
+        for s in range(lo[l], lo[l + 1]):
+            vtime.setdefault(int(seeds[s]), int(seed_times[s]))  # first occurrence of a repeated seed
+        for h in range(L):
+            arrivals = []
+            for t in range(T):
+                a, b = lto[(l * T + t) * L + h], lto[(l * T + t) * L + h + 1]
+                src, dst = gmap[out["majors"][a:b]], gmap[out["minors"][a:b]]
+                pos = out["edge_renumber_map"][a:b]  # no edge ids given: CSR positions of type t
+                assert np.array_equal(cols[t][pos].astype(np.int64), dst)
+                assert ((row_ptrs[t][src] <= pos) & (pos < row_ptrs[t][src + 1])).all()
+                for u in np.unique(src):
+                    sel = pos[src == u]
+                    assert len(np.unique(sel)) == len(sel)
+                    row_t = times[t][row_ptrs[t][u]:row_ptrs[t][u + 1]]
+                    eligible = int((row_t >= vtime[int(u)]).sum())
+                    assert len(sel) == min(eligible, fanout[h * T + t]) and (times[t][sel] >= vtime[int(u)]).all()
+                    checked += 1
+                arrivals += [(int(m), t, i, int(d), int(times[t][p])) for i, (m, d, p) in enumerate(zip(out["majors"][a:b], dst, pos))]
+            for _, _, _, d, tm in sorted(arrivals):  # the hop's edge order: a new vertex keeps the time of its first arrival
+                vtime.setdefault(d, tm)
+    assert checked > 150

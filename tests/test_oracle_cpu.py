@@ -531,3 +531,39 @@ def test_temporal_with_open_window_equals_plain_sampling(oracle):
     temp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, np.ones(30, np.int64), lo, [4, 3, 2, 2], 5, "monotonically_increasing")
     for k in plain:
         assert np.array_equal(plain[k], temp[k]), k
+
+
+def test_biased_temporal_with_open_window_equals_biased_sampling(oracle):
+    """Every edge eligible: the masked A-Res restatement is the plain biased sampler (same streams, same heap order)."""
+    from graphs import random_typed_graph
+
+    edge_types = [(0, 1), (1, 0)]
+    vto, row_ptrs, cols = random_typed_graph([200, 300], edge_types, [3000, 3000], seed=6)
+    rng = np.random.default_rng(0)
+    wts = [(rng.random(c.shape[0]) + 0.01).astype(np.float32) for c in cols]
+    times = [np.ones(c.shape[0], dtype=np.int64) for c in cols]
+    seeds = rng.integers(0, 500, 30).astype(np.int64)
+    lo = np.array([0, 30], dtype=np.int64)
+    plain = oracle.hetero_multihop_sample(row_ptrs, cols, vto, seeds, lo, [4, 3, 2, 2], 5, weights=wts)
+    temp = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, np.ones(30, np.int64), lo, [4, 3, 2, 2], 5, "monotonically_decreasing", weights=wts)
+    for k in plain:
+        assert np.array_equal(plain[k], temp[k]), k
+
+
+def test_biased_temporal_reference_pins(oracle):
+    """The reference runs its two deterministic temporal tests with biased=True and unit weights as well
+    (test_neighbor_loader.py:944, 991): every row there has at most `fanout` eligible edges, so the result is the uniform one."""
+    src_cite, dst_cite, tme = [3, 2, 1, 2], [2, 1, 0, 0], [0, 1, 2, 0]
+    vto, row_ptrs, cols, eids, times = _pyg_to_typed([(dst_cite, src_cite, 0, 0, tme)], [4])
+    w = [np.ones(c.shape[0], dtype=np.float32) for c in cols]
+    out = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, [3], [-1], [0, 1], [2, 2, 2], 62, "strictly_increasing", edge_ids=eids, weights=w)
+    assert out["renumber_map"].tolist() == [3, 2, 1, 0]
+    assert out["edge_renumber_map"][out["edge_id"]].tolist() == [0, 1, 2]
+    src_author, dst_author, tme_author = [3, 2, 2, 1, 3, 2, 0], [0, 0, 1, 1, 2, 2, 2], [0, 0, 1, 0, 2, 1, 1]
+    edges = [(dst_author, src_author, 0, 1, tme_author), (dst_cite, src_cite, 1, 1, tme)]
+    vto, row_ptrs, cols, eids, times = _pyg_to_typed(edges, [3, 4])
+    w = [np.ones(c.shape[0], dtype=np.float32) for c in cols]
+    out = oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, [3 + 3], [-1], [0, 1], [2, 2, 2, 2, 0, 2], 62, "strictly_increasing", edge_ids=eids, weights=w)
+    rmo, ermo = out["renumber_map_offsets"], out["edge_renumber_map_offsets"]
+    assert sorted((out["renumber_map"][rmo[0]:rmo[1]]).tolist()) == [0, 1, 2] and (out["renumber_map"][rmo[1]:rmo[2]] - 3).tolist() == [3, 2, 1, 0]
+    assert sorted(out["edge_renumber_map"][ermo[0]:ermo[1]].tolist()) == [0, 2, 4, 5]
