@@ -201,7 +201,7 @@ def run_ours(args):
     wm_col = wgth.create_wholememory_tensor(one, "chunked", "cuda", [col.numel()], torch.int32, [1])
     wm_col.get_local_tensor()[0].copy_(col)
     del col
-    emb = wgth.create_embedding(comm, "chunked", "cuda", torch.float32, [NUM_NODES, FEAT_DIM])
+    emb = wgth.create_embedding(comm, "chunked", "cuda", torch.float32, [NUM_NODES, FEAT_DIM], gather_sms=args.gather_sms)
     local, start = emb.get_embedding_tensor().get_local_tensor()
     ar = torch.arange(FEAT_DIM, device=dev)[None, :]
     for lo in range(0, local.shape[0], 1 << 20):
@@ -456,7 +456,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (%.1f GB table, >1 GB gathered per step); new seed set every step" % (NUM_NODES * FEAT_DIM * 4 / 1e9),
                        "graph": "replicated per GPU", "features": "chunked over %d GPU(s), in-kernel P2P gather" % world,
                        "hot_rows_replicated_per_gpu": hot_rows, "hot_rows_bytes_per_gpu": hot_rows * FEAT_DIM * 4 + (4 * NUM_NODES if hot_rows else 0),
-                       "pipeline": "call group k+1 begun before k is finished; gather on %s" % ("its own stream" if use_side else "the same stream")},
+                       "pipeline": "call group k+1 begun before k is finished; gather on %s" % ("its own stream" if use_side else "the same stream"),
+                       **({"gather_sms": args.gather_sms} if args.gather_sms > 0 else {})},
             "gather_gbs": row_bytes * tot_nodes / (gather_ms * 1e-3) / 1e9,
             "stages": {
                 "sample_renumber_ms_per_step": sample_ms / args.steps,
@@ -569,6 +570,9 @@ def main():
     ap.add_argument("--hot-ratio", type=float, default=0.1,
                     help="N > 1: fraction of the feature rows (the highest-degree vertices) replicated on every GPU; 0 = none")
     ap.add_argument("--gather-stream", type=int, default=-1, help="run the feature gather on a second stream (1, default) or in line (0)")
+    ap.add_argument("--gather-sms", type=int, default=-1,
+                    help="SM budget of the feature gather (reference knob `gather_sms`; grid = 8 CTAs x this many SMs, spread over all SMs); "
+                         "-1 = every SM (default).  Experiment: 74 leaves half of every SM to the sampling kernels of the next call group")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
                     help="c2 (default, the bench line) | c4 (papers100M shape) | headline (|V|=100M, |E|=1B, F=256)")
     args = ap.parse_args()
