@@ -1,0 +1,193 @@
+"""The cugraph_pyg mirror's loader stack (GraphStore -> pylibcugraph graph -> DistributedNeighborSampler -> readers ->
+SampleIterator -> NeighborLoader) on the CPU: every line of Python is the product's; underneath, "cuda" tensors are CPU
+tensors (torch factory functions / Tensor.cuda / Tensor.to are patched for the duration of a test), the feature store is a
+dictionary, and the native sampler is the CPU emulation of csrc/multihop.cu (tests/emu).
+
+Purpose: the temporal path (time_attr / input_time / temporal_comparison) reached the loaders after the round's GPU minutes
+were spent; this replays the reference's loader-level temporal tests (tests/loader/test_neighbor_loader.py:943-1058,
+uniform and biased) and guards the non-temporal loader paths the change touched.  Test infrastructure only.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from test_emulated_multihop_cpu import emu  # noqa: E402,F401  (fixture)
+from test_pylibcugraph_emulated_cpu import EmulatedSampler  # noqa: E402
+
+
+def _cpu_device(d):
+    if d is None:
+        return None
+    return "cpu" if str(d).startswith("cuda") else d
+
+
+@pytest.fixture()
+def stack(monkeypatch, emu):  # noqa: F811
+    """Patches torch so that device='cuda' means the CPU, and pylibcugraph so that graphs sample through the emulator."""
+    for name in ("arange", "full", "empty", "zeros", "ones", "tensor", "as_tensor", "randint", "rand", "randperm", "full_like", "empty_like"):
+        real = getattr(torch, name)
+
+        def wrapped(*a, __real=real, **k):
+            if "device" in k:
+                k["device"] = _cpu_device(k["device"])
+            return __real(*a, **k)
+
+        monkeypatch.setattr(torch, name, wrapped)
+    real_to = torch.Tensor.to
+
+    def to(self, *a, **k):
+        a = tuple(_cpu_device(x) if isinstance(x, (str, torch.device)) else x for x in a)
+        if "device" in k:
+            k["device"] = _cpu_device(k["device"])
+        return real_to(self, *a, **k)
+
+    monkeypatch.setattr(torch.Tensor, "to", to)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    import pylibcugraph
+
+    sampler = EmulatedSampler(emu)
+    monkeypatch.setattr(pylibcugraph.SGGraph, "_get_sampler", lambda self: sampler)
+    import cugraph_pyg
+    from cugraph_pyg._pyg_compat import FeatureStoreBase, TensorAttr
+
+    class DictFeatureStore(FeatureStoreBase):
+        """FeatureStore interface over a dictionary of CPU tensors (the product's FeatureStore lives on WholeMemory)."""
+
+        def __init__(self):
+            super().__init__()
+            self._t = {}
+
+        def _put_tensor(self, tensor, attr):
+            self._t[(attr.group_name, attr.attr_name)] = torch.as_tensor(tensor)
+            return True
+
+        def _get_tensor(self, attr):
+            t = self._t.get((attr.group_name, attr.attr_name))
+            if t is None:
+                return None
+            if attr.is_set("index") and attr.index is not None:
+                return t[attr.index]
+            return t
+
+        def _remove_tensor(self, attr):
+            return self._t.pop((attr.group_name, attr.attr_name), None) is not None
+
+        def _get_tensor_size(self, attr):
+            return tuple(self._t[(attr.group_name, attr.attr_name)].shape)
+
+        def get_all_tensor_attrs(self):
+            return [TensorAttr(group_name=g, attr_name=a) for g, a in self._t]
+
+    return cugraph_pyg, DictFeatureStore, sampler
+
+
+def _cite_graph(cugraph_pyg, FS, biased):
+    src_cite, dst_cite, tme_cite = torch.tensor([3, 2, 1, 2]), torch.tensor([2, 1, 0, 0]), torch.tensor([0, 1, 2, 0])
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    graph_store[("paper", "cites", "paper"), "coo", False, (4, 4)] = [dst_cite, src_cite]
+    feature_store[("paper", "cites", "paper"), "time", None] = tme_cite
+    if biased:
+        feature_store[("paper", "cites", "paper"), "bias", None] = torch.tensor([1.0] * 4)
+    return graph_store, feature_store
+
+
+@pytest.mark.parametrize("biased", [False, True])
+def test_neighbor_loader_temporal_simple(stack, biased):
+    """tests/loader/test_neighbor_loader.py:943-988 of the reference, verbatim expectations."""
+    cugraph_pyg, FS, sampler = stack
+    graph_store, feature_store = _cite_graph(cugraph_pyg, FS, biased)
+    loader = cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors=[2, 2, 2], batch_size=1,
+                                               input_nodes=torch.tensor([3]), input_time=torch.tensor([-1]), time_attr="time", shuffle=False,
+                                               weight_attr="bias" if biased else None, temporal_comparison="strictly_increasing",
+                                               local_seeds_per_call=64)
+    out = next(iter(loader))
+    assert sampler.calls == ["temporal"]
+    assert out.n_id.tolist() == [3, 2, 1, 0]
+    assert out.e_id.tolist() == [0, 1, 2]
+    assert out.num_sampled_nodes.tolist() == [1, 1, 1, 1]
+    assert out.num_sampled_edges.tolist() == [1, 1, 1]
+
+
+@pytest.mark.parametrize("biased", [False, True])
+def test_neighbor_loader_temporal_hetero(stack, biased):
+    """tests/loader/test_neighbor_loader.py:991-1056 of the reference, verbatim expectations."""
+    cugraph_pyg, FS, sampler = stack
+    graph_store, feature_store = _cite_graph(cugraph_pyg, FS, biased)
+    src_author = torch.tensor([3, 2, 2, 1, 3, 2, 0])
+    dst_author = torch.tensor([0, 0, 1, 1, 2, 2, 2])
+    graph_store[("author", "writes", "paper"), "coo", False, (3, 4)] = [dst_author, src_author]
+    feature_store[("author", "writes", "paper"), "time", None] = torch.tensor([0, 0, 1, 0, 2, 1, 1])
+    if biased:
+        feature_store[("author", "writes", "paper"), "bias", None] = torch.tensor([1.0] * 7)
+    loader = cugraph_pyg.loader.NeighborLoader(
+        (feature_store, graph_store),
+        num_neighbors={("paper", "cites", "paper"): [2, 2, 2], ("author", "writes", "paper"): [2, 2, 0]},
+        batch_size=1, input_nodes=("paper", torch.tensor([3])), input_time=torch.tensor([-1]), time_attr="time",
+        weight_attr="bias" if biased else None, shuffle=False, temporal_comparison="strictly_increasing", local_seeds_per_call=64)
+    out = next(iter(loader))
+    assert sampler.calls == ["temporal"]
+    assert sorted(out["author"].n_id.tolist()) == [0, 1, 2]
+    assert out["paper"].n_id.tolist() == [3, 2, 1, 0]
+    assert sorted(out["author", "writes", "paper"].e_id.tolist()) == [0, 2, 4, 5]
+    assert out["author", "writes", "paper"].num_sampled_edges.tolist() == [2, 2, 0]
+
+
+def test_neighbor_loader_temporal_batches_carry_their_own_times(stack):
+    """Several batches and call groups: every batch is sampled with ITS seeds' times (times follow the shuffle / the
+    call-group split), checked through the hop-0 edges: they respect the comparison with the seed's time."""
+    cugraph_pyg, FS, sampler = stack
+    rng = np.random.default_rng(0)
+    n, e = 60, 1500
+    src, dst = torch.from_numpy(rng.integers(0, n, e)), torch.from_numpy(rng.integers(0, n, e))
+    tme = torch.from_numpy(rng.integers(0, 100, e))
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    graph_store[("n", "to", "n"), "coo", False, (n, n)] = [src, dst]
+    feature_store[("n", "to", "n"), "time", None] = tme
+    feature_store["n", "x", None] = torch.arange(n * 4, dtype=torch.float32).reshape(n, 4)
+    seeds = torch.from_numpy(rng.permutation(n)[:40])
+    seed_time = torch.from_numpy(rng.integers(20, 80, 40))
+    loader = cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors=[4, 2], batch_size=8, input_nodes=seeds,
+                                               input_time=seed_time, time_attr="time", shuffle=True, temporal_comparison="monotonically_decreasing",
+                                               local_seeds_per_call=16)  # 2 batches per call group, 3 call groups
+    time_of = dict(zip(seeds.tolist(), seed_time.tolist()))
+    batches = 0
+    for out in loader:
+        batches += 1
+        assert out.x.shape == (out.n_id.numel(), 4) and torch.equal(out.x[:, 0], out.n_id.float() * 4)
+        k = int(out.num_sampled_edges[0])
+        assert k > 0
+        hop0_dst_local = out.edge_index[1][:k]  # PyG: messages flow source -> destination; hop-0 destinations are the seeds
+        assert int(hop0_dst_local.max()) < int(out.num_sampled_nodes[0])
+        seed_ids = out.n_id[hop0_dst_local].tolist()
+        edge_times = tme[out.e_id[:k]].tolist()
+        assert all(t <= time_of[s] for s, t in zip(seed_ids, edge_times))
+        # the sampled edges are edges of the graph: e_id indexes the put order
+        assert torch.equal(src[out.e_id], out.n_id[out.edge_index[0]]) and torch.equal(dst[out.e_id], out.n_id[out.edge_index[1]])
+    assert batches == 5 and sampler.calls == ["temporal"] * 3
+
+
+def test_plain_loaders_unchanged(stack, oracle):
+    """Non-temporal homogeneous (CSR decode) and heterogeneous loaders through the same stack: the paths the temporal work
+    touched (NodeLoader's input data, call-group splitting, GraphStore's edge list) still produce valid mini-batches."""
+    cugraph_pyg, FS, sampler = stack
+    rng = np.random.default_rng(1)
+    n, e = 80, 2500
+    src, dst = torch.from_numpy(rng.integers(0, n, e)), torch.from_numpy(rng.integers(0, n, e))
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    graph_store[("n", "to", "n"), "coo", False, (n, n)] = [src, dst]
+    feature_store["n", "x", None] = torch.arange(n * 2, dtype=torch.float32).reshape(n, 2)
+    loader = cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors=[5, 3], batch_size=16, input_nodes=torch.arange(40),
+                                               shuffle=False, local_seeds_per_call=32)
+    seen = 0
+    for i, out in enumerate(loader):
+        assert out.input_id.tolist() == list(range(16 * i, min(16 * i + 16, 40)))
+        assert out.n_id[:out.batch_size].tolist() == out.input_id.tolist()  # seeds first
+        assert torch.equal(src[out.e_id], out.n_id[out.edge_index[0]]) and torch.equal(dst[out.e_id], out.n_id[out.edge_index[1]])
+        assert int(out.num_sampled_nodes.sum()) == out.n_id.numel() and int(out.num_sampled_edges.sum()) == out.e_id.numel()
+        assert torch.equal(out.x[:, 0], out.n_id.float() * 2)
+        seen += out.batch_size
+    assert seen == 40 and sampler.calls == ["plain", "plain"]
+    with pytest.raises(ValueError):
+        cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors=[5], input_nodes=torch.arange(4), input_time=torch.arange(4))
