@@ -27,9 +27,11 @@ class LinkLoader:
                 warnings.warn(f"{name} is currently ignored")
         if neg_sampling_ratio is not None:
             warnings.warn("The 'neg_sampling_ratio' argument is deprecated in PyG and is not supported in cuGraph-PyG.")
-        if edge_label_time is not None:
-            raise NotImplementedError("temporal sampling from seed edges is not implemented (DESIGN.md §10)")
         neg_sampling = NegativeSampling.cast(neg_sampling)
+        if edge_label_time is not None:
+            if neg_sampling is not None:
+                raise NotImplementedError("temporal negative sampling is not implemented (DESIGN.md §10)")
+            edge_label_time = torch.as_tensor(edge_label_time).reshape(-1)
         explicit = edge_label_index is not None
         if isinstance(edge_label_index, (list, tuple)):
             if len(edge_label_index) == 3 and all(isinstance(v, str) for v in edge_label_index):
@@ -54,7 +56,9 @@ class LinkLoader:
                              "positive and negative samples.")
         self.__input_data = EdgeSamplerInput(
             input_id=torch.arange(edge_label_index[0].numel(), dtype=torch.int64) if input_id is None else input_id,
-            row=edge_label_index[0], col=edge_label_index[1], label=edge_label, time=None, input_type=input_type)
+            row=edge_label_index[0], col=edge_label_index[1], label=edge_label, time=edge_label_time, input_type=input_type)
+        if edge_label_time is not None and edge_label_time.numel() != edge_label_index.shape[1]:
+            raise ValueError("edge_label_time must have one entry per seed edge")
         self.__data = data
         self.__link_sampler = link_sampler
         self.__neg_sampling = neg_sampling
@@ -70,8 +74,8 @@ class LinkLoader:
         d = self.__input_data
         input_data = EdgeSamplerInput(input_id=d.input_id[perm.to(d.input_id.device)], row=d.row[perm.to(d.row.device)],
                                       col=d.col[perm.to(d.col.device)],
-                                      label=None if d.label is None else d.label[perm.to(d.label.device)], time=None,
-                                      input_type=d.input_type)
+                                      label=None if d.label is None else d.label[perm.to(d.label.device)],
+                                      time=None if d.time is None else d.time[perm.to(d.time.device)], input_type=d.input_type)
         return cugraph_pyg.sampler.SampleIterator(
             self.__data, self.__link_sampler.sample_from_edges(input_data, neg_sampling=self.__neg_sampling,
                                                                random_state=generate_seed()))

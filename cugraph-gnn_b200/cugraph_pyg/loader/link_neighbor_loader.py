@@ -26,8 +26,17 @@ class LinkNeighborLoader(LinkLoader):
             raise ValueError("Passing a neighbor sampler is currently unsupported")
         if is_sorted:
             warnings.warn("The 'is_sorted' argument is ignored by cuGraph.")
-        if time_attr is not None or edge_label_time is not None:
-            raise NotImplementedError("temporal sampling from seed edges is not implemented (DESIGN.md §10)")
+        if temporal_strategy != "uniform":
+            warnings.warn("Only the uniform temporal strategy is currently supported")
+        if temporal_comparison is None:
+            temporal_comparison = "monotonically_decreasing"
+        is_temporal = (edge_label_time is not None) and (time_attr is not None)
+        if not is_temporal and (edge_label_time is not None or time_attr is not None):
+            warnings.warn("Edge-based temporal sampling requires that both edge_label_time and time_attr are provided. "
+                          "Defaulting to non-temporal sampling.")
+            edge_label_time = None
+        if is_temporal and neg_sampling is not None:
+            raise NotImplementedError("temporal negative sampling is not implemented (DESIGN.md §10)")
         if replace:
             raise NotImplementedError("sampling with replacement is outside the B200 hot path")
         if disjoint:
@@ -35,6 +44,8 @@ class LinkNeighborLoader(LinkLoader):
         if not isinstance(data, (list, tuple)) or not isinstance(data[1], cugraph_pyg.data.GraphStore):
             raise NotImplementedError("Currently can't accept non-cugraph graphs")
         feature_store, graph_store = data
+        if is_temporal:
+            graph_store._set_time_attr((feature_store, time_attr))
         if compression is None:
             compression = "CSR" if graph_store.is_homogeneous else "COO"
         elif compression not in ("CSR", "COO"):
@@ -64,10 +75,11 @@ class LinkNeighborLoader(LinkLoader):
                 graph_store._graph, retain_original_seeds=True, fanout=num_neighbors, prior_sources_behavior="exclude",
                 deduplicate_sources=True, compression=compression, compress_per_hop=False, with_replacement=replace,
                 disjoint=disjoint, local_seeds_per_call=local_seeds_per_call, biased=(weight_attr is not None),
-                heterogeneous=heterogeneous, temporal=False, vertex_type_offsets=graph_store._vertex_offset_array,
+                heterogeneous=heterogeneous, temporal=is_temporal, temporal_comparison=temporal_comparison,
+                vertex_type_offsets=graph_store._vertex_offset_array,
                 num_edge_types=num_edge_types),
             (feature_store, graph_store), batch_size=batch_size)
         super().__init__((feature_store, graph_store), sampler, edge_label_index=edge_label_index, edge_label=edge_label,
-                         edge_label_time=None, neg_sampling=neg_sampling, neg_sampling_ratio=neg_sampling_ratio,
+                         edge_label_time=edge_label_time, neg_sampling=neg_sampling, neg_sampling_ratio=neg_sampling_ratio,
                          transform=transform, transform_sampler_output=transform_sampler_output,
                          filter_per_worker=filter_per_worker, batch_size=batch_size, **kwargs)

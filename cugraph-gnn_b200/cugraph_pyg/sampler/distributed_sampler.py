@@ -109,7 +109,7 @@ class BaseDistributedSampler:
         return gen()
 
     def _edge_call_group(self, edges: torch.Tensor, index: torch.Tensor, label, batch_id_start: int, batch_size: int,
-                         random_state: int, metadata) -> Tuple[Dict[str, torch.Tensor], int, int]:
+                         random_state: int, metadata, times: Optional[torch.Tensor] = None) -> Tuple[Dict[str, torch.Tensor], int, int]:
         """One call group of seed EDGES.  A batch's seeds are the endpoints [sources | destinations] of its edges;
         they are handed to the native sampler sorted inside each batch (ONE device sort per call group), which
         deduplicates them in first-occurrence (= ascending) order -- the order the reference produces with a python
@@ -136,7 +136,15 @@ class BaseDistributedSampler:
         seed_batch[pos_src + size_of] = batch_of
         span = int(seeds.max()) + 1 if n else 1
         order = torch.argsort(seed_batch * span + seeds, stable=True)  # batch-major, ascending id inside a batch
-        out = self.sample_batches(seeds=seeds[order], seed_times=None, batch_id_offsets=(2 * input_offsets).to(dev),
+        seed_times = None
+        if times is not None:
+            # both endpoints of a seed edge start at the edge's time (reference :490-493); a vertex that is an endpoint of
+            # several edges of the batch keeps the time of its first occurrence in the sorted seed list
+            seed_times = torch.empty(2 * n, dtype=torch.int64, device=dev)
+            seed_times[pos_src] = times
+            seed_times[pos_src + size_of] = times
+            seed_times = seed_times[order]
+        out = self.sample_batches(seeds=seeds[order], seed_times=seed_times, batch_id_offsets=(2 * input_offsets).to(dev),
                                   random_state=random_state, metadata=metadata, return_seed_local_ids=True)
         inverse = torch.empty(2 * n, dtype=torch.int64, device=dev)
         inverse[order] = out.pop("seed_local_ids").to(torch.int64)
@@ -156,26 +164,28 @@ class BaseDistributedSampler:
         """Sampling that starts from seed edges ([2, n], sources first): lazily yields (raw call-group dict, first batch
         id, last batch id).  Role of the reference's distributed_sampler.py:428-726."""
         verify_metadata(metadata)
-        if input_time is not None:
-            raise NotImplementedError("temporal sampling from seed edges is not implemented (DESIGN.md §10)")
         edges = torch.as_tensor(edges).cuda()
         n = int(edges.shape[-1])
+        if input_time is not None:
+            input_time = torch.as_tensor(input_time).reshape(-1).to(device=edges.device, dtype=torch.int64)
+            if input_time.numel() != n:
+                raise ValueError("input_time must have one entry per seed edge")
         input_id = torch.arange(n, dtype=torch.int64) if input_id is None else torch.as_tensor(input_id).cpu()
         label = None if input_label is None else torch.as_tensor(input_label)
         batches_per_call = max(1, self._local_seeds_per_call // batch_size)
         per_call = batches_per_call * batch_size
         local_num_batches = int(ceil(n / batch_size))
         batch_id_start, equal = self.get_start_batch_offset(local_num_batches, assume_equal_input_size)
-        groups = [(edges[:, lo:lo + per_call], input_id[lo:lo + per_call], None if label is None else label[lo:lo + per_call])
-                  for lo in range(0, n, per_call)]
+        groups = [(edges[:, lo:lo + per_call], input_id[lo:lo + per_call], None if label is None else label[lo:lo + per_call],
+                   None if input_time is None else input_time[lo:lo + per_call]) for lo in range(0, n, per_call)]
         if self.is_multi_gpu and not equal:
             pad = dist_utils.equalized_call_count(len(groups), equal) - len(groups)
-            groups += [(edges[:, :0], input_id[:0], None if label is None else label[:0])] * pad
+            groups += [(edges[:, :0], input_id[:0], None if label is None else label[:0], None if input_time is None else input_time[:0])] * pad
 
         def gen():
             start = batch_id_start
-            for call_id, (e, ix, lb) in enumerate(groups):
-                raw, first, last = self._edge_call_group(e, ix, lb, start, batch_size, random_state + call_id, metadata)
+            for call_id, (e, ix, lb, tm) in enumerate(groups):
+                raw, first, last = self._edge_call_group(e, ix, lb, start, batch_size, random_state + call_id, metadata, times=tm)
                 start = last + 1
                 yield raw, first, last
 

@@ -274,8 +274,8 @@ class BaseSampler:
         """Link-prediction sampling (role of the reference's sampler.py:798-896): optional negative edges are drawn for
         the whole epoch at once and interleaved batch by batch; negatives carry input id -1."""
         src, dst, input_id = index.row, index.col, index.input_id
-        if index.time is not None:
-            raise NotImplementedError("temporal sampling from seed edges is not implemented (DESIGN.md §10)")
+        if index.time is not None and neg_sampling:
+            raise NotImplementedError("temporal negative sampling is not implemented (DESIGN.md §10)")
         neg_batch_size = 0
         if neg_sampling:
             src_neg, dst_neg = neg_sample(self.__graph_store, index.row, index.col, index.input_type, self.__batch_size, neg_sampling)
@@ -290,7 +290,7 @@ class BaseSampler:
             input_id, _ = neg_cat(input_id, torch.full((dst_neg.numel(),), -1, dtype=torch.int64, device=input_id.device),
                                   self.__batch_size)
         metadata = {"input_type": index.input_type} if index.input_type is not None else None
-        reader = self.__sampler.sample_from_edges(torch.stack([src.cuda(), dst.cuda()]), input_id=input_id, input_time=None,
+        reader = self.__sampler.sample_from_edges(torch.stack([src.cuda(), dst.cuda()]), input_id=input_id, input_time=index.time,
                                                   input_label=index.label, batch_size=self.__batch_size + neg_batch_size,
                                                   metadata=metadata, **kwargs)
         return self.__reader(reader)

@@ -54,12 +54,14 @@ extern "C" {
 
 // outs[k] receive malloc'ed arrays (freed by emu_free): heterogeneous order = majors, minors, edge_id, edge_type,
 // label_type_hop_offsets, renumber_map, renumber_map_offsets, edge_renumber_map, edge_renumber_map_offsets, step base;
-// homogeneous order = majors, minors, edge_id, label_hop_offsets, renumber_map, renumber_map_offsets, major_offsets, step base.
+// homogeneous order = majors, minors, edge_id, label_hop_offsets, renumber_map, renumber_map_offsets, major_offsets, step base;
+// outs[10] = seed local ids (want_seed_ids).  out_ptr / out_count / out_elt hold 11 entries.
 // col_is_int64: dtype of the cols; edge_time == NULL: the plain (non-temporal) call; weight == NULL: uniform.
 int emu_multihop(int T, const long long* const* row_ptr, long long V, const void* const* col, const long long* num_edges, int col_is_int64,
                  const long long* const* edge_time, const void* const* weight, int weight_is_double, const long long* const* edge_id, const long long* vto, int Vt, int hetero,
                  const long long* seeds, const long long* seed_times, long long S, const long long* label_offsets, long long B, const int* fanout,
-                 int hops, unsigned long long random_state, int cmp, int flags, int reps, void** out_ptr, long long* out_count, int* out_elt)
+                 int hops, unsigned long long random_state, int cmp, int flags, int reps, int want_seed_ids, void** out_ptr, long long* out_count,
+                 int* out_elt)
 {
   std::vector<wholememory_tensor_> rp(T), cl(T), tm(T), ei(T), wt(T);
   std::vector<wholememory_tensor_t> rp_h(T), cl_h(T), tm_h(T), ei_h(T), wt_h(T);
@@ -92,7 +94,7 @@ int emu_multihop(int T, const long long* const* row_ptr, long long V, const void
   env.output_fns.free_fn   = out_free;
   wholegraph_multihop_sampler_t sp = nullptr;
   if (wholegraph_create_multihop_sampler(&sp) != WHOLEMEMORY_SUCCESS) return -100;
-  Out outs[10];
+  Out outs[11];  // [10]: local id of every input seed (wholegraph_multihop_seed_local_ids), when asked for
   int rc = -101;
   for (int rep = 0; rep < reps; rep++) {  // reps > 1: the same call again on one sampler object (scratch reuse, epochs, tickets)
     for (auto& o : outs) {
@@ -119,12 +121,16 @@ int emu_multihop(int T, const long long* const* row_ptr, long long V, const void
                                                       csr ? &outs[6] : nullptr, &outs[7], &env, nullptr);
     }
     if (rc != WHOLEMEMORY_SUCCESS) break;
+    if (want_seed_ids) {
+      rc = wholegraph_multihop_seed_local_ids(sp, &outs[10], &env, nullptr);
+      if (rc != WHOLEMEMORY_SUCCESS) break;
+    }
   }
   const long long dirty = emu_guard_violations();  // before the scratch is released: every buffer of the call is still live
   wholegraph_destroy_multihop_sampler(sp);
   if (rc == WHOLEMEMORY_SUCCESS && (dirty != 0 || emu_guard_violations() != 0)) rc = -102;  // a write outside a device allocation
   if (rc == WHOLEMEMORY_SUCCESS && emu_live_allocations() != 0) rc = -103;                  // the sampler object leaked device memory
-  for (int k = 0; k < 10; k++) {
+  for (int k = 0; k < 11; k++) {
     out_ptr[k]   = outs[k].ptr;
     out_count[k] = outs[k].count;
     out_elt[k]   = outs[k].elt;

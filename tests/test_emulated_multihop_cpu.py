@@ -37,7 +37,7 @@ def emu():
 
 
 def _run(lib, row_ptrs, cols, vto, seeds, lo, fanout, random_state, *, hetero=True, times=None, seed_times=None, cmp=0, eids=None,
-         flags=FLAG_INT64, expect_rc=0, reps=1, weights=None):
+         flags=FLAG_INT64, expect_rc=0, reps=1, weights=None, seed_local_ids=False):
     T = len(row_ptrs)
     rp = [np.ascontiguousarray(r, dtype=np.int64) for r in row_ptrs]
     cl = [np.ascontiguousarray(c) for c in cols]
@@ -55,17 +55,17 @@ def _run(lib, row_ptrs, cols, vto, seeds, lo, fanout, random_state, *, hetero=Tr
     def arr(xs):
         return (VP * T)(*[None if x is None else x.ctypes.data for x in xs])
 
-    out_ptr, out_cnt, out_elt = (VP * 10)(), (ctypes.c_longlong * 10)(), (ctypes.c_int * 10)()
+    out_ptr, out_cnt, out_elt = (VP * 11)(), (ctypes.c_longlong * 11)(), (ctypes.c_int * 11)()
     lib.emu_multihop.restype = ctypes.c_int
     rc = lib.emu_multihop(T, arr(rp), ctypes.c_longlong(rp[0].shape[0] - 1), arr(cl), ne.ctypes.data_as(VP), int(is64),
                           None if tm is None else arr(tm), None if wt is None else arr(wt), int(wt is not None and wt[0].dtype == np.float64),
                           None if ei is None else arr(ei), vto.ctypes.data_as(VP), vto.shape[0] - 1,
                           int(hetero), seeds.ctypes.data_as(VP), st.ctypes.data_as(VP), ctypes.c_longlong(seeds.shape[0]), lo.ctypes.data_as(VP),
                           ctypes.c_longlong(lo.shape[0] - 1), fo.ctypes.data_as(VP), fo.shape[0] // T, ctypes.c_ulonglong(random_state), cmp,
-                          flags, reps, out_ptr, out_cnt, out_elt)
+                          flags, reps, int(seed_local_ids), out_ptr, out_cnt, out_elt)
     assert rc == expect_rc, rc
     outs = {}
-    for k, name in enumerate(HETERO if hetero else HOMO):
+    for k, name in enumerate((HETERO if hetero else HOMO + ("unused", "unused2")) + ("seed_local_ids",)):
         if not out_ptr[k]:
             continue
         dt = {4: np.int32, 8: np.int64}[out_elt[k]]

@@ -245,3 +245,36 @@ def test_temporal_loader_reference_pin_heterogeneous():
     assert out["paper"].n_id.tolist() == [3, 2, 1, 0]
     assert sorted(out["author", "writes", "paper"].e_id.tolist()) == [0, 2, 4, 5]
     assert out["author", "writes", "paper"].num_sampled_edges.tolist() == [2, 2, 0]
+
+
+def test_temporal_link_loader_reference_pins():
+    """tests/loader/test_neighbor_loader.py:1059-1170 (uniform variants): seed edges with edge_label_time."""
+    import torch
+    import cugraph_pyg
+    from cugraph_pyg.data import GraphStore, FeatureStore
+
+    src_cite, dst_cite, tme_cite = torch.tensor([3, 2, 1, 2]), torch.tensor([2, 1, 0, 0]), torch.tensor([0, 1, 2, 0])
+    graph_store, feature_store = GraphStore(), FeatureStore()
+    graph_store[("paper", "cites", "paper"), "coo", False, (4, 4)] = [dst_cite, src_cite]
+    feature_store[("paper", "cites", "paper"), "time", None] = tme_cite
+    loader = cugraph_pyg.loader.LinkNeighborLoader((feature_store, graph_store), num_neighbors=[2, 2, 2], batch_size=1,
+                                                   edge_label_index=torch.tensor([[3], [3]]), edge_label_time=torch.tensor([-1]), time_attr="time",
+                                                   shuffle=False, temporal_comparison="strictly_increasing")
+    out = next(iter(loader))
+    assert out.n_id.tolist() == [3, 2, 1, 0]
+
+    graph_store, feature_store = GraphStore(), FeatureStore()
+    graph_store[("paper", "cites", "paper"), "coo", False, (4, 4)] = [dst_cite, src_cite]
+    graph_store[("author", "writes", "paper"), "coo", False, (3, 4)] = [torch.tensor([0, 0, 1, 1, 2, 2, 2]), torch.tensor([3, 2, 2, 1, 3, 2, 0])]
+    feature_store[("paper", "cites", "paper"), "time", None] = tme_cite
+    feature_store[("author", "writes", "paper"), "time", None] = torch.tensor([0, 0, 1, 0, 2, 1, 1])
+    loader = cugraph_pyg.loader.LinkNeighborLoader(
+        (feature_store, graph_store),
+        num_neighbors={("paper", "cites", "paper"): [2, 2, 2], ("author", "writes", "paper"): [2, 2, 0]},
+        batch_size=1, edge_label_index=(("author", "writes", "paper"), torch.tensor([[0], [3]])), edge_label_time=torch.tensor([-1]),
+        time_attr="time", shuffle=False, temporal_comparison="strictly_increasing")
+    out = next(iter(loader))
+    assert sorted(out["author"].n_id.tolist()) == [0, 1, 2]
+    assert out["paper"].n_id.tolist() == [3, 2, 1, 0]
+    assert sorted(out["author", "writes", "paper"].e_id.tolist()) == [0, 2, 4, 5]
+    assert out["author", "writes", "paper"].num_sampled_edges.tolist() == [2, 2, 0]

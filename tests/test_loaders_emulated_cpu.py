@@ -191,3 +191,59 @@ def test_plain_loaders_unchanged(stack, oracle):
     assert seen == 40 and sampler.calls == ["plain", "plain"]
     with pytest.raises(ValueError):
         cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors=[5], input_nodes=torch.arange(4), input_time=torch.arange(4))
+
+
+@pytest.mark.parametrize("biased", [False, True])
+def test_link_neighbor_loader_temporal_homogeneous(stack, biased):
+    """tests/loader/test_neighbor_loader.py:1059-1101 of the reference (seed edge 3 -> 3 at time -1)."""
+    cugraph_pyg, FS, sampler = stack
+    graph_store, feature_store = _cite_graph(cugraph_pyg, FS, biased)
+    loader = cugraph_pyg.loader.LinkNeighborLoader((feature_store, graph_store), num_neighbors=[2, 2, 2], batch_size=1,
+                                                   edge_label_index=torch.tensor([[3], [3]]), edge_label_time=torch.tensor([-1]), time_attr="time",
+                                                   weight_attr="bias" if biased else None, shuffle=False, temporal_comparison="strictly_increasing",
+                                                   local_seeds_per_call=64)
+    out = next(iter(loader))
+    assert sampler.calls == ["temporal"]
+    assert out.n_id.tolist() == [3, 2, 1, 0]
+    assert out.edge_label_index.tolist() == [[0], [0]]
+
+
+@pytest.mark.parametrize("biased", [False, True])
+def test_link_neighbor_loader_temporal_heterogeneous(stack, biased):
+    """tests/loader/test_neighbor_loader.py:1106-1170 of the reference (seed edge author 0 -> paper 3 at time -1)."""
+    cugraph_pyg, FS, sampler = stack
+    graph_store, feature_store = _cite_graph(cugraph_pyg, FS, biased)
+    graph_store[("author", "writes", "paper"), "coo", False, (3, 4)] = [torch.tensor([0, 0, 1, 1, 2, 2, 2]), torch.tensor([3, 2, 2, 1, 3, 2, 0])]
+    feature_store[("author", "writes", "paper"), "time", None] = torch.tensor([0, 0, 1, 0, 2, 1, 1])
+    if biased:
+        feature_store[("author", "writes", "paper"), "bias", None] = torch.tensor([1.0] * 7)
+    loader = cugraph_pyg.loader.LinkNeighborLoader(
+        (feature_store, graph_store),
+        num_neighbors={("paper", "cites", "paper"): [2, 2, 2], ("author", "writes", "paper"): [2, 2, 0]},
+        batch_size=1, edge_label_index=(("author", "writes", "paper"), torch.tensor([[0], [3]])), edge_label_time=torch.tensor([-1]),
+        time_attr="time", weight_attr="bias" if biased else None, shuffle=False, temporal_comparison="strictly_increasing",
+        local_seeds_per_call=64)
+    out = next(iter(loader))
+    assert sorted(out["author"].n_id.tolist()) == [0, 1, 2]
+    assert out["paper"].n_id.tolist() == [3, 2, 1, 0]
+    assert sorted(out["author", "writes", "paper"].e_id.tolist()) == [0, 2, 4, 5]
+    assert out["author", "writes", "paper"].num_sampled_edges.tolist() == [2, 2, 0]
+
+
+def test_plain_link_loader_unchanged(stack):
+    """Non-temporal link prediction (GPU-verified) through the same stack: edge_label_index maps the seed edges' endpoints."""
+    cugraph_pyg, FS, sampler = stack
+    rng = np.random.default_rng(2)
+    n, e = 70, 1800
+    src, dst = torch.from_numpy(rng.integers(0, n, e)), torch.from_numpy(rng.integers(0, n, e))
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    graph_store[("n", "to", "n"), "coo", False, (n, n)] = [src, dst]
+    feature_store["n", "x", None] = torch.arange(n, dtype=torch.float32).reshape(n, 1)
+    eli = torch.stack([src[:24], dst[:24]])
+    loader = cugraph_pyg.loader.LinkNeighborLoader((feature_store, graph_store), num_neighbors=[3, 2], batch_size=8, edge_label_index=eli,
+                                                   shuffle=False, local_seeds_per_call=16)
+    for i, out in enumerate(loader):
+        lo = 8 * i
+        assert torch.equal(out.n_id[out.edge_label_index[0]], eli[0, lo:lo + 8]) and torch.equal(out.n_id[out.edge_label_index[1]], eli[1, lo:lo + 8])
+        assert torch.equal(out.x[:, 0], out.n_id.float())
+    assert i == 2 and sampler.calls == ["plain", "plain"]

@@ -16,13 +16,14 @@ CMP = {"strictly_increasing": 0, "monotonically_increasing": 1, "strictly_decrea
 
 
 class _Pending:
-    def __init__(self, out):
-        self._out = out
+    """The emulated call runs when result() is asked for (the callers set want_seed_local_ids in between)."""
+
+    def __init__(self, run):
+        self._run = run
         self.want_seed_local_ids = False
 
     def result(self):
-        assert not self.want_seed_local_ids, "seed_local_ids are not emulated"
-        return self._out
+        return self._run(self.want_seed_local_ids)
 
 
 class EmulatedSampler:
@@ -36,32 +37,37 @@ class EmulatedSampler:
     def _np(t):
         return None if t is None else t.detach().cpu().numpy()
 
-    def _wrap(self, out, hops, hetero, vt=1):
-        res = {k: torch.from_numpy(v) for k, v in out.items()}
-        if hetero:
-            res["label_type_step_base"] = res["label_type_step_base"].view(hops + 1, vt, -1)
-        else:
-            res["label_step_base"] = res["label_step_base"].view(hops + 1, -1)
-        return _Pending(res)
+    def _pending(self, call, hops, hetero, vt=1):
+        def run(want_seed_ids):
+            out = call(want_seed_ids)
+            res = {k: torch.from_numpy(v) for k, v in out.items()}
+            if hetero:
+                res["label_type_step_base"] = res["label_type_step_base"].view(hops + 1, vt, -1)
+            else:
+                res["label_step_base"] = res["label_step_base"].view(hops + 1, -1)
+            return res
+
+        return _Pending(run)
 
     def sample_async(self, csr_row_ptr, csr_col, seeds, label_offsets, fanout, random_state, *, csr_weight=None, csr_edge_id=None,
                      compression="COO", int64_ids=False):
         self.calls.append("plain")
         V = csr_row_ptr.numel() - 1
         flags = (FLAG_CSR if compression == "CSR" else 0) | (FLAG_INT64 if int64_ids else 0)
-        out = _run(self.lib, [self._np(csr_row_ptr)], [self._np(csr_col)], [0, V], self._np(seeds), self._np(label_offsets), fanout, random_state,
-                   hetero=False, eids=None if csr_edge_id is None else [self._np(csr_edge_id)],
-                   weights=None if csr_weight is None else [self._np(csr_weight)], flags=flags)
-        return self._wrap(out, len(fanout), False)
+        return self._pending(lambda want: _run(
+            self.lib, [self._np(csr_row_ptr)], [self._np(csr_col)], [0, V], self._np(seeds), self._np(label_offsets), fanout, random_state,
+            hetero=False, eids=None if csr_edge_id is None else [self._np(csr_edge_id)],
+            weights=None if csr_weight is None else [self._np(csr_weight)], flags=flags, seed_local_ids=want), len(fanout), False)
 
     def sample_hetero_async(self, csr_row_ptrs, csr_cols, vertex_type_offsets, seeds, label_offsets, fanout, random_state, *, csr_weights=None,
                             csr_edge_ids=None, int64_ids=False):
         self.calls.append("hetero")
         T = len(csr_row_ptrs)
-        out = _run(self.lib, [self._np(r) for r in csr_row_ptrs], [self._np(c) for c in csr_cols], vertex_type_offsets, self._np(seeds),
-                   self._np(label_offsets), fanout, random_state, eids=None if csr_edge_ids is None else [self._np(e) for e in csr_edge_ids],
-                   weights=None if csr_weights is None else [self._np(w) for w in csr_weights], flags=FLAG_INT64 if int64_ids else 0)
-        return self._wrap(out, len(fanout) // T, True, len(vertex_type_offsets) - 1)
+        return self._pending(lambda want: _run(
+            self.lib, [self._np(r) for r in csr_row_ptrs], [self._np(c) for c in csr_cols], vertex_type_offsets, self._np(seeds),
+            self._np(label_offsets), fanout, random_state, eids=None if csr_edge_ids is None else [self._np(e) for e in csr_edge_ids],
+            weights=None if csr_weights is None else [self._np(w) for w in csr_weights], flags=FLAG_INT64 if int64_ids else 0,
+            seed_local_ids=want), len(fanout) // T, True, len(vertex_type_offsets) - 1)
 
     def sample_temporal_async(self, csr_row_ptrs, csr_cols, csr_edge_times, seeds, seed_times, label_offsets, fanout, random_state, comparison, *,
                               vertex_type_offsets=None, csr_edge_ids=None, csr_weights=None, compression="COO", int64_ids=False):
@@ -70,11 +76,12 @@ class EmulatedSampler:
         hetero = vertex_type_offsets is not None
         V = csr_row_ptrs[0].numel() - 1
         flags = (FLAG_CSR if compression == "CSR" else 0) | (FLAG_INT64 if int64_ids else 0)
-        out = _run(self.lib, [self._np(r) for r in csr_row_ptrs], [self._np(c) for c in csr_cols], vertex_type_offsets if hetero else [0, V],
-                   self._np(seeds), self._np(label_offsets), fanout, random_state, hetero=hetero, times=[self._np(t) for t in csr_edge_times],
-                   seed_times=self._np(seed_times), cmp=CMP[comparison], eids=None if csr_edge_ids is None else [self._np(e) for e in csr_edge_ids],
-                   weights=None if csr_weights is None else [self._np(w) for w in csr_weights], flags=flags)
-        return self._wrap(out, len(fanout) // T, hetero, (len(vertex_type_offsets) - 1) if hetero else 1)
+        return self._pending(lambda want: _run(
+            self.lib, [self._np(r) for r in csr_row_ptrs], [self._np(c) for c in csr_cols], vertex_type_offsets if hetero else [0, V],
+            self._np(seeds), self._np(label_offsets), fanout, random_state, hetero=hetero, times=[self._np(t) for t in csr_edge_times],
+            seed_times=self._np(seed_times), cmp=CMP[comparison], eids=None if csr_edge_ids is None else [self._np(e) for e in csr_edge_ids],
+            weights=None if csr_weights is None else [self._np(w) for w in csr_weights], flags=flags, seed_local_ids=want),
+            len(fanout) // T, hetero, (len(vertex_type_offsets) - 1) if hetero else 1)
 
 
 @pytest.fixture()
