@@ -278,3 +278,31 @@ def test_emulated_biased_temporal_two_hops_are_valid(emu):
             for _, _, _, d, tm in sorted(arrivals):  # the hop's edge order: a new vertex keeps the time of its first arrival
                 vtime.setdefault(d, tm)
     assert checked > 150
+
+
+def test_emulated_temporal_edge_cases(emu, oracle):
+    """Empty call, empty labels, nothing eligible anywhere, and the largest fan-out (1024) on rows heavier than it."""
+    rng = np.random.default_rng(12)
+    deg = np.concatenate([rng.integers(0, 6, 60), [1500, 2600, 0, 1100]])
+    row_ptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    V = deg.shape[0]
+    col = rng.integers(0, V, int(row_ptr[-1])).astype(np.int32)
+    times = [rng.integers(0, 10, col.shape[0]).astype(np.int64)]
+    vto = np.array([0, V], dtype=np.int64)
+    # no seeds at all / labels without seeds
+    out = _run(emu, [row_ptr], [col], vto, np.empty(0, np.int64), [0, 0, 0], [3, 2], 1, times=times, seed_times=np.empty(0, np.int64), cmp=1)
+    assert out["majors"].shape[0] == 0 and out["renumber_map"].shape[0] == 0 and out["label_type_hop_offsets"].tolist() == [0] * 5
+    seeds = np.array([60, 61, 62, 63, 5, 61], dtype=np.int64)
+    lo = np.array([0, 0, 4, 4, 6], dtype=np.int64)
+    # nothing eligible: every edge time is < 100
+    out = _run(emu, [row_ptr], [col], vto, seeds, lo, [5, 5], 3, times=times, seed_times=np.full(6, 100, np.int64), cmp=0)
+    exp = oracle.temporal_multihop_sample([row_ptr], [col], times, vto, seeds, np.full(6, 100, np.int64), lo, [5, 5], 3, "strictly_increasing")
+    assert out["majors"].shape[0] == 0
+    _same(out, exp, HETERO)
+    # fan-out 1024 (the largest the samplers accept) on rows with 1500 / 2600 / 1100 edges, about half of them eligible
+    st = np.array([4, 5, 5, 4, 5, 3], dtype=np.int64)
+    for fanout in ([1024, 2], [700, 1]):
+        out = _run(emu, [row_ptr], [col], vto, seeds, lo, fanout, 7, times=times, seed_times=st, cmp=1)
+        exp = oracle.temporal_multihop_sample([row_ptr], [col], times, vto, seeds, st, lo, fanout, 7, "monotonically_increasing")
+        assert exp["majors"].shape[0] > 1500
+        _same(out, exp, HETERO)
