@@ -39,8 +39,6 @@ class LinkNeighborLoader(LinkLoader):
             raise NotImplementedError("temporal negative sampling is not implemented (DESIGN.md §10)")
         if replace:
             raise NotImplementedError("sampling with replacement is outside the B200 hot path")
-        if disjoint:
-            raise NotImplementedError("disjoint sampling is outside the B200 hot path")
         if not isinstance(data, (list, tuple)) or not isinstance(data[1], cugraph_pyg.data.GraphStore):
             raise NotImplementedError("Currently can't accept non-cugraph graphs")
         feature_store, graph_store = data
@@ -68,6 +66,10 @@ class LinkNeighborLoader(LinkLoader):
         heterogeneous = heterogeneous or num_edge_types > 1
         if heterogeneous:
             compression = "COO"
+        if disjoint:
+            if heterogeneous:
+                raise NotImplementedError("disjoint sampling is implemented for homogeneous graphs only (DESIGN.md §10)")
+            compression = "COO"  # cross-tree edges are removed from the COO result (pylibcugraph._disjoint_filter)
         if weight_attr is not None:
             graph_store._set_weight_attr((feature_store, weight_attr))
         sampler = BaseSampler(

@@ -15,7 +15,8 @@ Differences that callers can observe:
     include/wholememory/b200_ops.h: edge_id indexes edge_renumber_map per (label, edge type);
   * temporal sampling (edge_start_time_array + the *_temporal_* entry points, uniform and biased) follows the definition in
     include/wholememory/b200_ops.h;
-  * with_replacement=True and disjoint_sampling=True raise NotImplementedError.
+  * disjoint_sampling=True (homogeneous graphs, COO) is the plain sample with cross-tree edges removed (_disjoint_filter);
+  * with_replacement=True raises NotImplementedError.
 """
 from typing import Optional
 
@@ -203,6 +204,49 @@ class MGGraph(SGGraph):
                          edge_start_time_array=gather(edge_start_time_array, torch.int64), **kwargs)
 
 
+def _disjoint_filter(out, num_hops: int):
+    """disjoint_sampling=True on a homogeneous COO result (reference: `disjoint` of the loaders, pinned by
+    tests/loader/test_neighbor_loader.py:138-187, 838-935): every seed of a label roots its own tree, a vertex belongs to the
+    tree that reached it first (first edge in the hop's edge order -- the order the renumbering already uses), and an edge
+    whose endpoints lie in different trees is dropped, so the trees of a mini-batch share no vertex.  The vertex set is
+    unchanged (a vertex keeps the edge that discovered it); edges, label_hop_offsets and the per-node tree ids are rebuilt
+    with a handful of vectorised torch ops per hop (host glue, not a hot path).  libcugraph's own choice among competing
+    trees is not observable; the reference's tests check exactly the invariants above."""
+    majors, minors = out["majors"], out["minors"]
+    lho, rmo, base = out["label_hop_offsets"], out["renumber_map_offsets"], out["label_step_base"]
+    dev = minors.device
+    E, N, L = int(minors.numel()), int(out["renumber_map"].numel()), int(num_hops)
+    B = int(rmo.numel()) - 1
+    edge_pos = torch.arange(E, device=dev)
+    group = torch.bucketize(edge_pos, lho[1:], right=True)  # (label, hop) group of every edge
+    label, hop = group // L, group % L
+    gmaj, gmin = majors.long() + rmo[label], minors.long() + rmo[label]  # positions in renumber_map
+    node_pos = torch.arange(N, device=dev)
+    node_label = torch.bucketize(node_pos, rmo[1:], right=True)
+    local = node_pos - rmo[node_label]
+    tree = torch.full((N,), -1, dtype=torch.int64, device=dev)
+    is_seed = local < base[1].long()[node_label] if B else torch.zeros(0, dtype=torch.bool, device=dev)
+    tree[is_seed] = local[is_seed]
+    keep = torch.ones(E, dtype=torch.bool, device=dev)
+    for h in range(L):
+        sel = torch.nonzero(hop == h).reshape(-1)
+        if sel.numel() == 0:
+            continue
+        mj, mn = gmaj[sel], gmin[sel]
+        new = tree[mn] < 0
+        first = torch.full((N,), E, dtype=torch.int64, device=dev)
+        first.scatter_reduce_(0, mn[new], sel[new], reduce="amin")  # the edge that discovered each new vertex
+        has = first < E
+        tree[has] = tree[gmaj[first[has]]]
+        keep[sel] = tree[mj] == tree[mn]
+    counts = torch.bincount(group[keep], minlength=B * L) if E else torch.zeros(B * L, dtype=torch.int64, device=dev)
+    out = dict(out)
+    out["majors"], out["minors"], out["edge_id"] = majors[keep], minors[keep], out["edge_id"][keep]
+    out["label_hop_offsets"] = torch.cat([torch.zeros(1, dtype=lho.dtype, device=dev), counts.cumsum(0).to(lho.dtype)])
+    out["tree"] = tree  # extension: per renumber_map entry, the local id of the seed whose tree the vertex belongs to
+    return out
+
+
 def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, biased, *,
                      with_replacement=False, do_expensive_check=False, prior_sources_behavior=None,
                      deduplicate_sources=False, return_hops=False, renumber=False, retain_seeds=False,
@@ -210,8 +254,8 @@ def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offse
                      return_dict=True, return_seed_local_ids=False, **unused):
     if with_replacement:
         raise NotImplementedError("sampling with replacement is not on the B200 hot path")
-    if disjoint_sampling:
-        raise NotImplementedError("disjoint sampling is not on the B200 hot path")
+    if disjoint_sampling and compression != "COO":
+        raise NotImplementedError("disjoint sampling returns COO")
     if compress_per_hop:
         raise NotImplementedError("compress_per_hop=True is not supported")
     if not renumber:
@@ -255,6 +299,8 @@ def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offse
     }
     if return_seed_local_ids:
         out["seed_local_ids"] = res["seed_local_ids"]  # extension: local id of every input seed (link-prediction loaders)
+    if disjoint_sampling:
+        out = _disjoint_filter(out, len(fanout))
     return out
 
 
@@ -276,7 +322,7 @@ def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_labe
     if with_replacement:
         raise NotImplementedError("sampling with replacement is not on the B200 hot path")
     if disjoint_sampling:
-        raise NotImplementedError("disjoint sampling is not on the B200 hot path")
+        raise NotImplementedError("disjoint sampling is implemented for homogeneous graphs only (DESIGN.md §10)")
     if compress_per_hop or compression != "COO":
         raise NotImplementedError("heterogeneous sampling returns COO (as the reference's reader requires)")
     if not renumber:
@@ -350,8 +396,8 @@ def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_la
     edge_start_time_array; without starting_vertex_times the first hop is unconstrained."""
     if with_replacement:
         raise NotImplementedError("sampling with replacement is not on the B200 hot path")
-    if disjoint_sampling:
-        raise NotImplementedError("disjoint sampling is not on the B200 hot path")
+    if disjoint_sampling and (heterogeneous or compression != "COO"):
+        raise NotImplementedError("disjoint sampling is implemented for homogeneous graphs and returns COO (DESIGN.md §10)")
     if compress_per_hop or (heterogeneous and compression != "COO"):
         raise NotImplementedError("compress_per_hop / heterogeneous CSR output are not supported")
     if not renumber:
@@ -413,13 +459,14 @@ def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_la
             "edge_renumber_map": res["edge_renumber_map"], "edge_renumber_map_offsets": res["edge_renumber_map_offsets"],
             "label_type_step_base": res["label_type_step_base"],
         }
-    return {
+    out = {
         **extra,
         "majors": res.get("majors"), "minors": res["minors"], "major_offsets": res.get("major_offsets"),
         "edge_id": res["edge_id"], "edge_type": None, "weight": None, "hop_id": None, "renumber_map": res["renumber_map"],
         "renumber_map_offsets": res["renumber_map_offsets"], "label_hop_offsets": res["label_hop_offsets"],
         "label_step_base": res["label_step_base"],
     }
+    return _disjoint_filter(out, len(fanout)) if disjoint_sampling else out
 
 
 def homogeneous_uniform_temporal_neighbor_sample(resource_handle, input_graph, start_vertex_list,

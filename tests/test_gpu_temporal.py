@@ -278,3 +278,28 @@ def test_temporal_link_loader_reference_pins():
     assert out["paper"].n_id.tolist() == [3, 2, 1, 0]
     assert sorted(out["author", "writes", "paper"].e_id.tolist()) == [0, 2, 4, 5]
     assert out["author", "writes", "paper"].num_sampled_edges.tolist() == [2, 2, 0]
+
+
+def test_disjoint_loader_reference_pins():
+    """Disjoint sampling (pylibcugraph._disjoint_filter: torch ops on top of the plain call; checked on the CPU in
+    tests/test_loaders_emulated_cpu.py, gated here with the rest of what has not run on a GPU):
+    tests/loader/test_neighbor_loader.py:838-885 and :138-187 of the reference."""
+    import torch
+    import cugraph_pyg
+    from cugraph_pyg.data import GraphStore, FeatureStore
+
+    graph_store, feature_store = GraphStore(), FeatureStore()
+    graph_store.put_edge_index(torch.stack([torch.tensor([2, 2]), torch.tensor([0, 1])]), ("node", "connects", "node"), "coo", False, (3, 3))
+    feature_store["node", "feat", None] = torch.randint(128, (3, 8)).float()
+    batch_d = next(iter(cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), [1], input_nodes=torch.tensor([0, 1]), batch_size=2,
+                                                          disjoint=True)))
+    assert batch_d.e_id.numel() == 1 and sorted(batch_d.input_id.tolist()) == [0, 1] and sorted(batch_d.n_id.tolist()) == [0, 1, 2]
+
+    graph_store, feature_store = GraphStore(), FeatureStore()
+    graph_store[("node", "connects", "node"), "coo", False, (5, 5)] = torch.stack([torch.tensor([4, 4, 4, 4]), torch.tensor([0, 1, 2, 3])])
+    feature_store["node", "feat", None] = torch.zeros(5, 2)
+    eli = torch.tensor([[0, 2], [1, 3]])
+    batch_d = next(iter(cugraph_pyg.loader.LinkNeighborLoader((feature_store, graph_store), num_neighbors=[1], edge_label_index=eli, batch_size=2,
+                                                              shuffle=False, disjoint=True)))
+    assert batch_d.e_id.numel() == 1
+    assert batch_d.n_id[batch_d.edge_label_index[0]].tolist() == [0, 2] and batch_d.n_id[batch_d.edge_label_index[1]].tolist() == [1, 3]

@@ -247,3 +247,81 @@ def test_plain_link_loader_unchanged(stack):
         assert torch.equal(out.n_id[out.edge_label_index[0]], eli[0, lo:lo + 8]) and torch.equal(out.n_id[out.edge_label_index[1]], eli[1, lo:lo + 8])
         assert torch.equal(out.x[:, 0], out.n_id.float())
     assert i == 2 and sampler.calls == ["plain", "plain"]
+
+
+# ---- disjoint sampling (homogeneous): the reference's three loader tests -----------------------------------------------------
+def test_neighbor_loader_disjoint(stack):
+    """tests/loader/test_neighbor_loader.py:838-885 of the reference, verbatim expectations."""
+    cugraph_pyg, FS, sampler = stack
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    graph_store.put_edge_index(torch.stack([torch.tensor([2, 2]), torch.tensor([0, 1])]), ("node", "connects", "node"), "coo", False, (3, 3))
+    feature_store["node", "feat", None] = torch.randint(128, (3, 8))
+    NeighborLoader = cugraph_pyg.loader.NeighborLoader
+    batch_nd = next(iter(NeighborLoader((feature_store, graph_store), [1], input_nodes=torch.tensor([0, 1]), batch_size=2, disjoint=False,
+                                        local_seeds_per_call=64)))
+    assert batch_nd.e_id.numel() == 2
+    batch_d = next(iter(NeighborLoader((feature_store, graph_store), [1], input_nodes=torch.tensor([0, 1]), batch_size=2, disjoint=True,
+                                       local_seeds_per_call=64)))
+    assert batch_d.e_id.numel() == 1
+    assert batch_d.input_id.min() >= 0
+    assert batch_d.input_id.max() == batch_d.batch_size - 1
+    assert sorted(batch_d.input_id.tolist()) == [0, 1]
+    assert sorted(batch_d.n_id.tolist()) == [0, 1, 2]
+
+
+@pytest.mark.parametrize("batch_size", [1, 2, 4, 8, 16])
+def test_neighbor_loader_disjoint_batch_structure(stack, batch_size):
+    """tests/loader/test_neighbor_loader.py:888-935 of the reference on the karate graph: the vertex sets of the trees grown
+    from the seeds of a mini-batch are pairwise disjoint."""
+    import os
+
+    cugraph_pyg, FS, sampler = stack
+    el = np.loadtxt(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "karate.csv"), delimiter=" ", usecols=(0, 1)).astype(np.int64)
+    src, dst = torch.from_numpy(el[:, 0].copy()), torch.from_numpy(el[:, 1].copy())
+    num_nodes = int(el.max()) + 1
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    graph_store.put_edge_index(torch.stack([dst, src]), ("person", "knows", "person"), "coo", False, (num_nodes, num_nodes))
+    feature_store["person", "feat", None] = torch.randint(128, (num_nodes, 16))
+    loader = cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), [5, 5], input_nodes=torch.arange(num_nodes), batch_size=batch_size,
+                                               disjoint=True, local_seeds_per_call=64)
+    batches = edges = 0
+    for batch in loader:
+        batches += 1
+        edges += int(batch.e_id.numel())
+        assert int(batch.num_sampled_edges.sum()) == batch.edge_index.shape[1] == batch.e_id.numel()
+        tree_vertices = {}
+        for n_id in range(int(batch.num_sampled_nodes[0])):
+            tree_vertices[n_id] = {n_id}
+            edge_offset = 0
+            for hop in range(len(batch.num_sampled_edges)):
+                edges_hop = int(batch.num_sampled_edges[hop])
+                e_h = batch.edge_index[:, edge_offset:edge_offset + edges_hop]
+                e_in = torch.isin(e_h[1], torch.tensor(list(tree_vertices[n_id])))
+                tree_vertices[n_id].update(e_h[0][e_in].tolist())
+                edge_offset += edges_hop
+        tv = list(tree_vertices.values())
+        for i in range(len(tv)):
+            for j in range(i + 1, len(tv)):
+                assert (tv[i] & tv[j]) == set()
+        # every vertex of the mini-batch belongs to exactly one tree, and the sampled edges are edges of the graph
+        assert sorted(set().union(*tv)) == list(range(batch.n_id.numel()))
+        assert torch.equal(dst[batch.e_id], batch.n_id[batch.edge_index[0]]) and torch.equal(src[batch.e_id], batch.n_id[batch.edge_index[1]])
+    assert batches == (num_nodes + batch_size - 1) // batch_size and edges > 0
+
+
+def test_link_neighbor_loader_disjoint(stack):
+    """tests/loader/test_neighbor_loader.py:138-187 of the reference, verbatim expectations."""
+    cugraph_pyg, FS, sampler = stack
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    graph_store[("node", "connects", "node"), "coo", False, (5, 5)] = torch.stack([torch.tensor([4, 4, 4, 4]), torch.tensor([0, 1, 2, 3])])
+    eli = torch.tensor([[0, 2], [1, 3]])
+    L = cugraph_pyg.loader.LinkNeighborLoader
+    batch_nd = next(iter(L((feature_store, graph_store), num_neighbors=[1], edge_label_index=eli, batch_size=2, shuffle=False, disjoint=False,
+                           local_seeds_per_call=64)))
+    assert batch_nd.e_id.numel() == 4
+    batch_d = next(iter(L((feature_store, graph_store), num_neighbors=[1], edge_label_index=eli, batch_size=2, shuffle=False, disjoint=True,
+                          local_seeds_per_call=64)))
+    assert batch_d.e_id.numel() == 1
+    assert batch_d.edge_label_index.shape == (2, 2)
+    assert batch_d.edge_label_index.min() >= 0 and batch_d.edge_label_index.max() < batch_d.n_id.numel()
+    assert batch_d.n_id[batch_d.edge_label_index[0]].tolist() == [0, 2] and batch_d.n_id[batch_d.edge_label_index[1]].tolist() == [1, 3]
