@@ -37,6 +37,7 @@ __device__ __forceinline__ V ld_stream(const V* p)
 {
   return *p;
 }
+#ifndef WGB_HOST_EMULATION  // tests/emu compiles this file with g++ (logic check on the CPU): plain loads there
 template <>
 __device__ __forceinline__ uint4 ld_stream<uint4>(const uint4* p)
 {
@@ -53,6 +54,7 @@ __device__ __forceinline__ uint2 ld_stream<uint2>(const uint2* p)
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
   return v;
 }
+#endif
 
 struct RowDiv {  // q = n / d for n < 2^31 via multiply-shift
   unsigned int mul;

@@ -56,3 +56,22 @@ def build_multihop() -> str:
             f.write(text)
         subprocess.check_call(FLAGS + ["-include", "cuda_emu.h", gen] + srcs + ["-o", lib])
     return lib
+
+
+def build_rows() -> str:
+    """gather / scatter (gather_scatter.cu) and CSR aggregation (aggregate.cu) behind rows_driver.cpp"""
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "librows_emu.so")
+    cus = [os.path.join(CSRC, "gather_scatter.cu"), os.path.join(CSRC, "aggregate.cu")]
+    srcs = [os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "rows_driver.cpp")]
+    if _stale(lib, cus + [os.path.join(HERE, "emu_preprocess.py")] + srcs + _headers()):
+        gens = []
+        for cu in cus:
+            text, n = rewrite_launches(open(cu).read())
+            assert n > 0
+            gen = os.path.join(OUT, os.path.basename(cu)[:-3] + "_emu.cpp")
+            with open(gen, "w") as f:
+                f.write(text)
+            gens.append(gen)
+        subprocess.check_call(FLAGS + ["-include", "cuda_emu.h"] + gens + srcs + ["-o", lib])
+    return lib

@@ -305,6 +305,43 @@ inline T atomicMin(T* p, T v)
   return old;
 }
 
+inline float atomicAdd(float* p, float v)
+{
+  float old = *p;  // fibers run on one OS thread and only switch at barriers: read-modify-write is atomic by construction
+  *p        = old + v;
+  return old;
+}
+inline double atomicAdd(double* p, double v)
+{
+  double old = *p;
+  *p         = old + v;
+  return old;
+}
+template <typename T>
+inline T atomicCAS(T* p, T expected, T desired)
+{
+  __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return expected;  // the value found (== the old `expected` iff the swap happened)
+}
+inline float __uint_as_float(unsigned int u)
+{
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline float __int_as_float(int u)
+{
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+inline int __float_as_int(float f)
+{
+  int u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 inline int __popc(unsigned int x) { return __builtin_popcount(x); }

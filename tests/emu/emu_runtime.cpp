@@ -137,6 +137,47 @@ void wholememory_initialize_tensor_desc(wholememory_tensor_description_t* d)
   std::memset(d, 0, sizeof(*d));
   d->dtype = WHOLEMEMORY_DT_UNKNOWN;
 }
+bool wholememory_dtype_is_floating_number(wholememory_dtype_t dt)
+{
+  return dt == WHOLEMEMORY_DT_FLOAT || dt == WHOLEMEMORY_DT_HALF || dt == WHOLEMEMORY_DT_DOUBLE || dt == WHOLEMEMORY_DT_BF16;
+}
+bool wholememory_dtype_is_integer_number(wholememory_dtype_t dt)
+{
+  return dt == WHOLEMEMORY_DT_INT || dt == WHOLEMEMORY_DT_INT64 || dt == WHOLEMEMORY_DT_INT16 || dt == WHOLEMEMORY_DT_INT8;
+}
+bool wholememory_convert_tensor_desc_to_array(wholememory_array_description_t* a, wholememory_tensor_description_t* t)
+{
+  if (t->dim != 1 && t->dim != 0) return false;
+  if (t->dim == 1 && t->strides[0] != 1) return false;
+  a->size           = t->dim == 0 ? 1 : t->sizes[0];
+  a->storage_offset = t->storage_offset;
+  a->dtype          = t->dtype;
+  return true;
+}
+bool wholememory_convert_tensor_desc_to_matrix(wholememory_matrix_description_t* m, wholememory_tensor_description_t* t)
+{
+  if (t->dim != 2 || t->strides[1] != 1) return false;
+  m->sizes[0]       = t->sizes[0];
+  m->sizes[1]       = t->sizes[1];
+  m->stride         = t->strides[0];
+  m->storage_offset = t->storage_offset;
+  m->dtype          = t->dtype;
+  return true;
+}
+bool wholememory_unsqueeze_tensor(wholememory_tensor_description_t* t, int dim)
+{
+  if (dim < 0 || dim > t->dim || t->dim >= WHOLEMEMORY_MAX_TENSOR_DIM) return false;
+  int64_t new_stride = dim == t->dim ? 1 : t->sizes[dim] * t->strides[dim];
+  for (int i = t->dim; i > dim; i--) {
+    t->sizes[i]   = t->sizes[i - 1];
+    t->strides[i] = t->strides[i - 1];
+  }
+  t->sizes[dim]   = 1;
+  t->strides[dim] = new_stride;
+  t->dim++;
+  return true;
+}
+wholememory_tensor_t wholememory_tensor_get_root(wholememory_tensor_t t) { return t ? (t->root ? t->root : t) : nullptr; }
 wholememory_tensor_description_t* wholememory_tensor_get_tensor_description(wholememory_tensor_t t) { return &t->desc; }
 void* wholememory_tensor_get_data_pointer(wholememory_tensor_t t)
 {
@@ -161,13 +202,25 @@ void log_msg(int, const char* fmt, ...)
 
 int num_sms() { return 2; }  // small grids: every grid-stride loop and persistent ticket loop iterates
 
+// emu_set_split_world(W > 1): every tensor is presented to the kernels as if it were CHUNKED over W ranks (row-aligned
+// boundaries, chunk r based at ptr + start[r], i.e. the same memory): the CHUNKED template variants and their owner lookup run.
+int g_split_world = 1;
+
 ChunkRef make_chunk_ref(wholememory_tensor_t t)
 {
   ChunkRef r;
   std::memset(&r, 0, sizeof(r));
-  r.base[0]  = static_cast<char*>(t->storage_ptr);
-  r.start[1] = (unsigned long long)(t->desc.storage_offset + t->desc.sizes[0]) * wholememory_dtype_get_element_size(t->desc.dtype);
-  r.world    = 1;
+  const unsigned long long elt = wholememory_dtype_get_element_size(t->desc.dtype);
+  const long long rows   = t->desc.sizes[0];
+  const long long stride = t->desc.dim == 2 ? t->desc.strides[0] : 1;
+  const int W            = std::max(1, std::min(g_split_world, kMaxWorld));
+  r.world                = W;
+  r.base[0]              = static_cast<char*>(t->storage_ptr);
+  for (int k = 1; k < W; k++) {
+    r.start[k] = (unsigned long long)(t->desc.storage_offset + (rows * k / W) * stride) * elt;
+    r.base[k]  = static_cast<char*>(t->storage_ptr) + r.start[k];
+  }
+  r.start[W] = (unsigned long long)(t->desc.storage_offset + rows * stride) * elt;
   return r;
 }
 
@@ -189,3 +242,5 @@ const Affine* skip_table_device()
 }
 
 }  // namespace wgb
+
+extern "C" void emu_set_split_world(int w) { wgb::g_split_world = w; }

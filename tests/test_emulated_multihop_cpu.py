@@ -306,3 +306,21 @@ def test_emulated_temporal_edge_cases(emu, oracle):
         exp = oracle.temporal_multihop_sample([row_ptr], [col], times, vto, seeds, st, lo, fanout, 7, "monotonically_increasing")
         assert exp["majors"].shape[0] > 1500
         _same(out, exp, HETERO)
+
+
+def test_emulated_chunked_graph(emu, oracle):
+    """CSR arrays presented as CHUNKED over 3 ranks (tests/emu/emu_runtime.cpp: emu_set_split_world): the CHUNKED template
+    variants of every sampler kernel -- plain and temporal -- with their per-access owner lookup."""
+    vto, row_ptrs, cols, seeds, lo, rng = _typed_case()
+    times = [rng.integers(0, 50, c.shape[0]).astype(np.int64) for c in cols]
+    eids = [rng.permutation(c.shape[0]).astype(np.int64) for c in cols]
+    seed_times = (10 + rng.integers(-5, 6, seeds.shape[0])).astype(np.int64)
+    emu.emu_set_split_world(3)
+    try:
+        got = _run(emu, row_ptrs, cols, vto, seeds, lo, [3, 40, -1, 2, 2, 2], 31, eids=eids)
+        tgot = _run(emu, row_ptrs, cols, vto, seeds, lo, [3, 40, -1, 2, 2, 2], 31, times=times, seed_times=seed_times, cmp=1, eids=eids)
+    finally:
+        emu.emu_set_split_world(1)
+    _same(got, oracle.hetero_multihop_sample(row_ptrs, cols, vto, seeds, lo, [3, 40, -1, 2, 2, 2], 31, edge_ids=eids), HETERO)
+    _same(tgot, oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, seed_times, lo, [3, 40, -1, 2, 2, 2], 31,
+                                                "monotonically_increasing", edge_ids=eids), HETERO)
