@@ -59,10 +59,10 @@ def build_multihop() -> str:
 
 
 def build_rows() -> str:
-    """gather / scatter (gather_scatter.cu) and CSR aggregation (aggregate.cu) behind rows_driver.cpp"""
+    """gather / scatter (gather_scatter.cu), CSR aggregation (aggregate.cu) and append-unique (append_unique.cu) behind rows_driver.cpp"""
     os.makedirs(OUT, exist_ok=True)
     lib = os.path.join(OUT, "librows_emu.so")
-    cus = [os.path.join(CSRC, "gather_scatter.cu"), os.path.join(CSRC, "aggregate.cu")]
+    cus = [os.path.join(CSRC, "gather_scatter.cu"), os.path.join(CSRC, "aggregate.cu"), os.path.join(CSRC, "append_unique.cu")]
     srcs = [os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "rows_driver.cpp")]
     if _stale(lib, cus + [os.path.join(HERE, "emu_preprocess.py")] + srcs + _headers()):
         gens = []

@@ -7,6 +7,7 @@
 #include "wm_common.cuh"
 
 #include <wholememory/b200_ops.h>
+#include <wholememory/graph_op.h>
 
 #include <vector>
 
@@ -100,6 +101,72 @@ int emu_csr_aggregate(const void* indptr, int indptr_is_int64, long long n_dst, 
   }
   if (rc == WHOLEMEMORY_SUCCESS && (emu_guard_violations() != 0 || emu_live_allocations() != 0)) rc = -102;
   return rc;
+}
+
+// S3: graph_append_unique (csrc/append_unique.cu).  unique_out holds T + N entries of the id type; returns the unique count, or a
+// negative error (-(1000 + code) for a product error code, -102 for a write outside an allocation).
+namespace {
+struct TempCtx {
+  void* p = nullptr;
+};
+void temp_create(void** ctx, void*) { *ctx = new TempCtx(); }
+void temp_destroy(void* ctx, void*) { delete static_cast<TempCtx*>(ctx); }
+void* temp_malloc(wholememory_tensor_description_t* d, wholememory_memory_allocation_type_t, void* ctx, void*)
+{
+  size_t bytes = (size_t)std::max<long long>(d->sizes[0], 1) * wholememory_dtype_get_element_size(d->dtype);
+  cudaMalloc(&static_cast<TempCtx*>(ctx)->p, bytes);
+  return static_cast<TempCtx*>(ctx)->p;
+}
+void temp_free(void* ctx, void*)
+{
+  cudaFree(static_cast<TempCtx*>(ctx)->p);
+  static_cast<TempCtx*>(ctx)->p = nullptr;
+}
+struct OutCtx {
+  void* p         = nullptr;
+  long long count = 0;
+};
+void* out_malloc2(wholememory_tensor_description_t* d, wholememory_memory_allocation_type_t, void* ctx, void*)
+{
+  OutCtx* o = static_cast<OutCtx*>(ctx);
+  o->count  = d->sizes[0];
+  cudaMalloc(&o->p, (size_t)std::max<long long>(o->count, 1) * wholememory_dtype_get_element_size(d->dtype));
+  return o->p;
+}
+void out_free2(void* ctx, void*) { cudaFree(static_cast<OutCtx*>(ctx)->p); }
+}  // namespace
+
+long long emu_append_unique(const void* targets, long long T, const void* neighbors, long long N, int is_int64, void* unique_out, int* raw_to_unique)
+{
+  const size_t e = is_int64 ? 8 : 4;
+  long long result;
+  {
+    DevBuf d_t(targets, (size_t)T * e), d_n(neighbors, (size_t)N * e), d_r(nullptr, (size_t)N * 4);
+    const wholememory_dtype_t dt = is_int64 ? WHOLEMEMORY_DT_INT64 : WHOLEMEMORY_DT_INT;
+    wholememory_tensor_ tt = tensor1d(d_t.p, T, dt), tn = tensor1d(d_n.p, N, dt), tr = tensor1d(d_r.p, N, WHOLEMEMORY_DT_INT);
+    wholememory_env_func_t env;
+    std::memset(&env, 0, sizeof(env));
+    env.temporary_fns.create_memory_context_fn  = temp_create;
+    env.temporary_fns.destroy_memory_context_fn = temp_destroy;
+    env.temporary_fns.malloc_fn                 = temp_malloc;
+    env.temporary_fns.free_fn                   = temp_free;
+    env.output_fns.malloc_fn                    = out_malloc2;
+    env.output_fns.free_fn                      = out_free2;
+    OutCtx out;
+    int rc = graph_append_unique(&tt, &tn, &out, raw_to_unique ? &tr : nullptr, &env, nullptr);
+    if (rc != WHOLEMEMORY_SUCCESS) {
+      result = -(1000 + rc);
+    } else {
+      result = emu_guard_violations() != 0 ? -102 : out.count;
+      if (result >= 0) {
+        std::memcpy(unique_out, out.p, (size_t)out.count * e);
+        if (raw_to_unique) std::memcpy(raw_to_unique, d_r.p, (size_t)N * 4);
+      }
+    }
+    cudaFree(out.p);
+  }
+  if (result >= 0 && (emu_guard_violations() != 0 || emu_live_allocations() != 0)) result = -102;
+  return result;
 }
 
 }  // extern "C"

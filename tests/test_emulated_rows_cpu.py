@@ -159,3 +159,20 @@ def test_csr_aggregate(emu, F, xdtype, reduce, use_map, idx64):
         if seg.shape[0]:
             exp[i] = seg.sum(0) / (seg.shape[0] if reduce == 1 else 1)
     assert np.allclose(out, exp, rtol=1e-3, atol=1e-4)  # north_star: within 1e-3 relative for fp32 aggregation
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64])
+@pytest.mark.parametrize("T,N,span", [(0, 0, 10), (5, 0, 10), (0, 7, 4), (300, 5000, 900), (1, 3000, 50), (700, 700, 100000)])
+def test_append_unique(emu, oracle, dtype, T, N, span):
+    """S3 (graph_append_unique): targets keep ids 0..T-1, every new neighbour gets the next id in first-occurrence order."""
+    rng = np.random.default_rng(T + N)
+    targets = rng.permutation(span)[:T].astype(dtype) if T <= span else rng.integers(0, span, T).astype(dtype)
+    neighbors = rng.integers(0, span, N).astype(dtype)
+    uniq = np.full(T + N + 1, -5, dtype=dtype)
+    r2u = np.full(max(N, 1), -5, dtype=np.int32)
+    emu.emu_append_unique.restype = ctypes.c_longlong
+    cnt = emu.emu_append_unique(_p(targets), ctypes.c_longlong(T), _p(neighbors), ctypes.c_longlong(N), int(dtype is np.int64), _p(uniq), _p(r2u))
+    e_uniq, e_r2u = oracle.append_unique(targets, neighbors)
+    assert cnt == e_uniq.shape[0]
+    assert np.array_equal(uniq[:cnt], e_uniq) and uniq[cnt] == -5
+    assert np.array_equal(r2u[:N], e_r2u)
