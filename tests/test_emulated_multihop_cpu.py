@@ -324,3 +324,21 @@ def test_emulated_chunked_graph(emu, oracle):
     _same(got, oracle.hetero_multihop_sample(row_ptrs, cols, vto, seeds, lo, [3, 40, -1, 2, 2, 2], 31, edge_ids=eids), HETERO)
     _same(tgot, oracle.temporal_multihop_sample(row_ptrs, cols, times, vto, seeds, seed_times, lo, [3, 40, -1, 2, 2, 2], 31,
                                                 "monotonically_increasing", edge_ids=eids), HETERO)
+
+
+def test_emulated_c1_karate(emu, oracle):
+    """BASELINE.json configs[0] ("karate.csv 1-hop fanout=[5] on CPU, bit-exact COO check, no GPU") with the PRODUCT's sampler
+    source run on the CPU: every vertex a seed, one label, sampler seed 62 -- COO, renumber map and edge ids against the oracle;
+    the same call is checked on the GPU in tests/test_gpu_multihop.py::test_multihop_c1_karate_and_large_properties."""
+    from graphs import karate_csr
+
+    row_ptr, col = karate_csr(np.int64)
+    seeds = np.arange(34, dtype=np.int64)
+    lo = np.array([0, 34], dtype=np.int64)
+    got = _run(emu, [row_ptr], [col], [0, 34], seeds, lo, [5], 62, hetero=False)
+    exp = oracle.multihop_sample(row_ptr, col, seeds, lo, [5], 62)
+    _same(got, exp, ["majors", "minors", "edge_id", "label_hop_offsets", "renumber_map", "renumber_map_offsets"])
+    deg = np.diff(row_ptr)
+    assert got["majors"].shape[0] == int(np.minimum(deg, 5).sum())
+    src = got["renumber_map"][got["majors"]]
+    assert np.array_equal(col[got["edge_id"]], got["renumber_map"][got["minors"]]) and np.array_equal(np.searchsorted(row_ptr, got["edge_id"], "right") - 1, src)
