@@ -75,3 +75,19 @@ def build_rows() -> str:
             gens.append(gen)
         subprocess.check_call(FLAGS + ["-include", "cuda_emu.h"] + gens + srcs + ["-o", lib])
     return lib
+
+
+def build_onehop() -> str:
+    """the one-hop samplers S1 / S2 (sample.cu, host code and kernels) behind onehop_driver.cpp"""
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "libonehop_emu.so")
+    cu = os.path.join(CSRC, "sample.cu")
+    srcs = [os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "onehop_driver.cpp")]
+    if _stale(lib, [cu, os.path.join(HERE, "emu_preprocess.py")] + srcs + _headers()):
+        text, n = rewrite_launches(open(cu).read())
+        assert n > 0
+        gen = os.path.join(OUT, "sample_emu.cpp")
+        with open(gen, "w") as f:
+            f.write(text)
+        subprocess.check_call(FLAGS + ["-DEMU_PRODUCT_SKIP_TABLE", "-include", "cuda_emu.h", gen] + srcs + ["-o", lib])
+    return lib

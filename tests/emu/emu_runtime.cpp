@@ -77,6 +77,11 @@ cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind
   if (n) std::memmove(dst, src, n);
   return cudaSuccess;
 }
+cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind)
+{
+  if (n) std::memmove(dst, src, n);
+  return cudaSuccess;
+}
 cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t)
 {
   for (size_t r = 0; r < height; r++)
@@ -224,6 +229,7 @@ ChunkRef make_chunk_ref(wholememory_tensor_t t)
   return r;
 }
 
+#ifndef EMU_PRODUCT_SKIP_TABLE  // the library that contains csrc/sample.cu has the product's own skip_table_device()
 const Affine* skip_table_device()
 {
   static std::vector<Affine> host;
@@ -240,6 +246,7 @@ const Affine* skip_table_device()
   }
   return host.data();
 }
+#endif
 
 }  // namespace wgb
 
