@@ -67,9 +67,7 @@ class LinkNeighborLoader(LinkLoader):
         if heterogeneous:
             compression = "COO"
         if disjoint:
-            if heterogeneous:
-                raise NotImplementedError("disjoint sampling is implemented for homogeneous graphs only (DESIGN.md §10)")
-            compression = "COO"  # cross-tree edges are removed from the COO result (pylibcugraph._disjoint_filter)
+            compression = "COO"  # cross-tree edges are removed from the COO result (pylibcugraph._disjoint_filter[_hetero])
         if weight_attr is not None:
             graph_store._set_weight_attr((feature_store, weight_attr))
         sampler = BaseSampler(

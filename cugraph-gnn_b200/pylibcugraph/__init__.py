@@ -15,7 +15,7 @@ Differences that callers can observe:
     include/wholememory/b200_ops.h: edge_id indexes edge_renumber_map per (label, edge type);
   * temporal sampling (edge_start_time_array + the *_temporal_* entry points, uniform and biased) follows the definition in
     include/wholememory/b200_ops.h;
-  * disjoint_sampling=True (homogeneous graphs, COO) is the plain sample with cross-tree edges removed (_disjoint_filter);
+  * disjoint_sampling=True (COO) is the plain sample with cross-tree edges removed (_disjoint_filter, _disjoint_filter_hetero);
   * with_replacement=True raises NotImplementedError.
 """
 from typing import Optional
@@ -247,6 +247,58 @@ def _disjoint_filter(out, num_hops: int):
     return out
 
 
+def _disjoint_filter_hetero(out, num_edge_types: int, num_hops: int, src_vtype, dst_vtype):
+    """_disjoint_filter for a heterogeneous result: vertices are addressed by their position in renumber_map (segments
+    [label][vertex type]), an edge of type t joins a src_vtype[t] vertex (major) to a dst_vtype[t] vertex (minor).  Among the
+    edges of one hop that reach the same new vertex, the first in OUTPUT order (label, edge type, position) defines its tree
+    (the interleaving of edge types inside a hop is not recoverable from the typed result; any one choice gives vertex-disjoint
+    trees).  edge_id is renumbered inside every (label, edge type) group, as the native call defines it."""
+    majors, minors = out["majors"], out["minors"]
+    lto, rmo, base = out["label_type_hop_offsets"], out["renumber_map_offsets"], out["label_type_step_base"]
+    dev = minors.device
+    T, L = int(num_edge_types), int(num_hops)
+    Vt = int(base.shape[1])
+    B = (int(rmo.numel()) - 1) // Vt
+    E, N = int(minors.numel()), int(out["renumber_map"].numel())
+    svt = torch.as_tensor(src_vtype, dtype=torch.int64, device=dev)
+    dvt = torch.as_tensor(dst_vtype, dtype=torch.int64, device=dev)
+    edge_pos = torch.arange(E, device=dev)
+    group = torch.bucketize(edge_pos, lto[1:], right=True)  # (label * T + type) * L + hop
+    label, etype, hop = group // (T * L), (group // L) % T, group % L
+    gmaj = majors.long() + rmo[label * Vt + svt[etype]]
+    gmin = minors.long() + rmo[label * Vt + dvt[etype]]
+    node_pos = torch.arange(N, device=dev)
+    seg = torch.bucketize(node_pos, rmo[1:], right=True)  # label * Vt + vertex type
+    local = node_pos - rmo[seg]
+    tree = torch.full((N,), -1, dtype=torch.int64, device=dev)
+    is_seed = local < base[1].long()[seg % Vt, seg // Vt] if N else torch.zeros(0, dtype=torch.bool, device=dev)
+    tree[is_seed] = node_pos[is_seed]
+    keep = torch.ones(E, dtype=torch.bool, device=dev)
+    for h in range(L):
+        sel = torch.nonzero(hop == h).reshape(-1)
+        if sel.numel() == 0:
+            continue
+        mj, mn = gmaj[sel], gmin[sel]
+        new = tree[mn] < 0
+        first = torch.full((N,), E, dtype=torch.int64, device=dev)
+        first.scatter_reduce_(0, mn[new], sel[new], reduce="amin")
+        has = first < E
+        tree[has] = tree[gmaj[first[has]]]
+        keep[sel] = tree[mj] == tree[mn]
+    counts = torch.bincount(group[keep], minlength=B * T * L) if E else torch.zeros(B * T * L, dtype=torch.int64, device=dev)
+    new_lto = torch.cat([torch.zeros(1, dtype=lto.dtype, device=dev), counts.cumsum(0).to(lto.dtype)])
+    out = dict(out)
+    for k in ("majors", "minors", "edge_type", "edge_renumber_map"):
+        out[k] = out[k][keep]
+    kept_group = group[keep]
+    type_start = new_lto[(kept_group // L) * L]  # first edge of the (label, edge type) group of every kept edge
+    out["edge_id"] = (torch.arange(int(keep.sum()), device=dev) - type_start).to(out["edge_id"].dtype)
+    out["label_type_hop_offsets"] = new_lto
+    out["edge_renumber_map_offsets"] = new_lto[::L].contiguous()
+    out["tree"] = tree
+    return out
+
+
 def _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, biased, *,
                      with_replacement=False, do_expensive_check=False, prior_sources_behavior=None,
                      deduplicate_sources=False, return_hops=False, renumber=False, retain_seeds=False,
@@ -314,6 +366,22 @@ def homogeneous_biased_neighbor_sample(resource_handle, input_graph, start_verte
     return _neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, True, **kwargs)
 
 
+def _edge_type_endpoints(typed, vto):
+    """(vertex type of the rows, vertex type of the columns) of every per-type CSR, read off its first edge."""
+    bounds = torch.as_tensor(vto[1:-1], dtype=torch.int64)
+    src, dst = [], []
+    for g in typed:
+        row_ptr, col = g[0], g[1]
+        if col.numel() == 0:
+            src.append(0)
+            dst.append(0)
+            continue
+        first_row = int(torch.nonzero(row_ptr[1:] > row_ptr[:-1])[0])
+        src.append(int(torch.bucketize(torch.tensor([first_row]), bounds, right=True)))
+        dst.append(int(torch.bucketize(col[:1].long().cpu(), bounds, right=True)))
+    return src, dst
+
+
 def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_label_offsets, h_fan_out, num_edge_types,
                             vertex_type_offsets, biased, *, with_replacement=False, do_expensive_check=False,
                             prior_sources_behavior=None, deduplicate_sources=False, return_hops=False, renumber=False,
@@ -321,8 +389,6 @@ def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_labe
                             disjoint_sampling=False, return_dict=True, return_seed_local_ids=False, **unused):
     if with_replacement:
         raise NotImplementedError("sampling with replacement is not on the B200 hot path")
-    if disjoint_sampling:
-        raise NotImplementedError("disjoint sampling is implemented for homogeneous graphs only (DESIGN.md §10)")
     if compress_per_hop or compression != "COO":
         raise NotImplementedError("heterogeneous sampling returns COO (as the reference's reader requires)")
     if not renumber:
@@ -353,6 +419,8 @@ def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_labe
     )
     pend.want_seed_local_ids = bool(return_seed_local_ids)
     res = pend.result()
+    if disjoint_sampling:
+        res = _disjoint_filter_hetero(res, T, len(fanout) // T, *_edge_type_endpoints(typed, vto))
     return {
         **({"seed_local_ids": res["seed_local_ids"]} if return_seed_local_ids else {}),
         "majors": res["majors"],

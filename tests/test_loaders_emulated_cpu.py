@@ -325,3 +325,60 @@ def test_link_neighbor_loader_disjoint(stack):
     assert batch_d.edge_label_index.shape == (2, 2)
     assert batch_d.edge_label_index.min() >= 0 and batch_d.edge_label_index.max() < batch_d.n_id.numel()
     assert batch_d.n_id[batch_d.edge_label_index[0]].tolist() == [0, 2] and batch_d.n_id[batch_d.edge_label_index[1]].tolist() == [1, 3]
+
+
+def test_neighbor_loader_disjoint_heterogeneous(stack):
+    """Disjoint sampling on a typed graph (no reference test exists; same invariants as the homogeneous ones): the trees grown
+    from the seeds of a mini-batch share no vertex, every sampled vertex lies in exactly one tree, every kept edge is an edge of
+    the graph, and cross-tree edges are gone (fewer edges than the plain loader returns for the same seeds)."""
+    cugraph_pyg, FS, sampler = stack
+    rng = np.random.default_rng(4)
+    na, nb = 30, 40
+    ets = {("a", "x", "b"): (na, nb, 300), ("b", "y", "a"): (nb, na, 300), ("b", "z", "b"): (nb, nb, 400)}
+    edges = {et: (torch.from_numpy(rng.integers(0, ns, m)), torch.from_numpy(rng.integers(0, nd, m))) for et, (ns, nd, m) in ets.items()}
+
+    def stores():
+        graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+        for et, (s, d) in edges.items():
+            graph_store[et, "coo", False, (ets[et][0], ets[et][1])] = [s, d]
+        feature_store["a", "x", None] = torch.arange(na, dtype=torch.float32).reshape(na, 1)
+        feature_store["b", "x", None] = torch.arange(nb, dtype=torch.float32).reshape(nb, 1)
+        return feature_store, graph_store
+
+    fan = {et: [3, 2] for et in ets}
+    seeds = torch.from_numpy(rng.permutation(nb)[:24])
+    totals = {}
+    for disjoint in (False, True):
+        loader = cugraph_pyg.loader.NeighborLoader(stores(), num_neighbors=fan, input_nodes=("b", seeds), batch_size=8, shuffle=False,
+                                                   disjoint=disjoint, local_seeds_per_call=16)
+        total = 0
+        for i, batch in enumerate(loader):
+            assert batch["b"].n_id[:8].tolist() == seeds[8 * i:8 * i + 8].tolist()
+            for et, (s, d) in edges.items():
+                ei, eid = batch[et].edge_index, batch[et].e_id
+                total += int(eid.numel())
+                assert torch.equal(s[eid], batch[et[0]].n_id[ei[0]]) and torch.equal(d[eid], batch[et[2]].n_id[ei[1]])
+                assert int(batch[et].num_sampled_edges.sum()) == eid.numel()
+            if not disjoint:
+                continue
+            trees = [{("b", k)} for k in range(8)]
+            offset = {et: 0 for et in ets}
+            for hop in range(2):
+                grown = [set() for _ in trees]
+                for et in ets:
+                    k = int(batch[et].num_sampled_edges[hop])
+                    e = batch[et].edge_index[:, offset[et]:offset[et] + k]
+                    offset[et] += k
+                    for s_l, d_l in zip(e[0].tolist(), e[1].tolist()):
+                        for j, tr in enumerate(trees):
+                            if (et[2], d_l) in tr:
+                                grown[j].add((et[0], s_l))
+                for tr, g in zip(trees, grown):
+                    tr |= g
+            for a in range(8):
+                for b in range(a + 1, 8):
+                    assert not (trees[a] & trees[b])
+            every = set().union(*trees)
+            assert every == {("a", k) for k in range(batch["a"].n_id.numel())} | {("b", k) for k in range(batch["b"].n_id.numel())}
+        totals[disjoint] = total
+    assert 0 < totals[True] < totals[False]
