@@ -420,7 +420,10 @@ def _hetero_neighbor_sample(input_graph, start_vertex_list, starting_vertex_labe
     pend.want_seed_local_ids = bool(return_seed_local_ids)
     res = pend.result()
     if disjoint_sampling:
-        res = _disjoint_filter_hetero(res, T, len(fanout) // T, *_edge_type_endpoints(typed, vto))
+        key = ("endpoints", T, bool(biased))
+        if key not in input_graph._typed:  # host syncs: once per graph, not per call group
+            input_graph._typed[key] = _edge_type_endpoints(typed, vto)
+        res = _disjoint_filter_hetero(res, T, len(fanout) // T, *input_graph._typed[key])
     return {
         **({"seed_local_ids": res["seed_local_ids"]} if return_seed_local_ids else {}),
         "majors": res["majors"],
