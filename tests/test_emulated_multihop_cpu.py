@@ -214,7 +214,9 @@ def test_emulated_biased_temporal_open_window_equals_plain_biased(emu, wdtype):
     vto, row_ptrs, cols, seeds, lo, rng = _typed_case()
     wts = [(rng.random(c.shape[0]) + 0.01).astype(wdtype) for c in cols]
     times = [np.full(c.shape[0], 3, dtype=np.int64) for c in cols]
-    for fanout in ([4, 3, 2, 2, 2, 2],) if wdtype is np.float64 else ([4, 3, 2, 2, 2, 2], [40, 3, 20, 2, 2, 2]):
+    for fanout in ([4, 3, 2, 2, 2, 2],) if wdtype is np.float64 else ([4, 3, 2, 2, 2, 2], [40, 3, 20, 1, 1, 1]):
+        if fanout[0] == 40:  # the A-Res kernel sorts 2048 candidates per heavy row: keep the emulated call group small
+            seeds, lo = seeds[:24], np.array([0, 12, 24], dtype=np.int64)
         plain = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 5, weights=wts)
         temp = _run(emu, row_ptrs, cols, vto, seeds, lo, fanout, 5, weights=wts, times=times, seed_times=np.full_like(seeds, 3), cmp=3)
         assert plain["majors"].shape[0] > 0
