@@ -467,8 +467,8 @@ def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_la
     edge_start_time_array; without starting_vertex_times the first hop is unconstrained."""
     if with_replacement:
         raise NotImplementedError("sampling with replacement is not on the B200 hot path")
-    if disjoint_sampling and (heterogeneous or compression != "COO"):
-        raise NotImplementedError("disjoint sampling is implemented for homogeneous graphs and returns COO (DESIGN.md §10)")
+    if disjoint_sampling and compression != "COO":
+        raise NotImplementedError("disjoint sampling returns COO")
     if compress_per_hop or (heterogeneous and compression != "COO"):
         raise NotImplementedError("compress_per_hop / heterogeneous CSR output are not supported")
     if not renumber:
@@ -522,6 +522,11 @@ def _temporal_neighbor_sample(input_graph, start_vertex_list, starting_vertex_la
     res = pend.result()
     extra = {"seed_local_ids": res["seed_local_ids"]} if return_seed_local_ids else {}
     if heterogeneous:
+        if disjoint_sampling:
+            key = ("endpoints", T, bool(biased))
+            if key not in input_graph._typed:
+                input_graph._typed[key] = _edge_type_endpoints(typed, vto)
+            res = _disjoint_filter_hetero(res, T, len(fanout) // T, *input_graph._typed[key])
         return {
             **extra,
             "majors": res["majors"], "minors": res["minors"], "major_offsets": None, "edge_id": res["edge_id"],

@@ -382,3 +382,25 @@ def test_neighbor_loader_disjoint_heterogeneous(stack):
             assert every == {("a", k) for k in range(batch["a"].n_id.numel())} | {("b", k) for k in range(batch["b"].n_id.numel())}
         totals[disjoint] = total
     assert 0 < totals[True] < totals[False]
+
+
+def test_temporal_and_disjoint_combine(stack):
+    """time_attr + disjoint on a typed graph: the temporal call's result goes through the same cross-tree filter."""
+    cugraph_pyg, FS, sampler = stack
+    graph_store, feature_store = _cite_graph(cugraph_pyg, FS, False)
+    graph_store[("author", "writes", "paper"), "coo", False, (3, 4)] = [torch.tensor([0, 0, 1, 1, 2, 2, 2]), torch.tensor([3, 2, 2, 1, 3, 2, 0])]
+    feature_store[("author", "writes", "paper"), "time", None] = torch.tensor([0, 0, 1, 0, 2, 1, 1])
+    kw = dict(num_neighbors={("paper", "cites", "paper"): [2, 2], ("author", "writes", "paper"): [2, 2]}, batch_size=2,
+              input_nodes=("paper", torch.tensor([3, 2])), input_time=torch.tensor([-1, -1]), time_attr="time", shuffle=False,
+              temporal_comparison="strictly_increasing", local_seeds_per_call=64)
+    plain = next(iter(cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), disjoint=False, **kw)))
+    graph_store, feature_store = _cite_graph(cugraph_pyg, FS, False)
+    graph_store[("author", "writes", "paper"), "coo", False, (3, 4)] = [torch.tensor([0, 0, 1, 1, 2, 2, 2]), torch.tensor([3, 2, 2, 1, 3, 2, 0])]
+    feature_store[("author", "writes", "paper"), "time", None] = torch.tensor([0, 0, 1, 0, 2, 1, 1])
+    dis = next(iter(cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), disjoint=True, **kw)))
+    assert sampler.calls == ["temporal", "temporal"]
+    for t in ("author", "paper"):
+        assert dis[t].n_id.tolist() == plain[t].n_id.tolist()  # the vertex set does not change
+    n_plain = sum(int(plain[et].e_id.numel()) for et in (("paper", "cites", "paper"), ("author", "writes", "paper")))
+    n_dis = sum(int(dis[et].e_id.numel()) for et in (("paper", "cites", "paper"), ("author", "writes", "paper")))
+    assert 0 < n_dis < n_plain  # seed 3 reaches paper 2 (the other seed) and shared authors: those edges cross trees
