@@ -390,7 +390,8 @@ def test_temporal_and_disjoint_combine(stack):
     graph_store, feature_store = _cite_graph(cugraph_pyg, FS, False)
     graph_store[("author", "writes", "paper"), "coo", False, (3, 4)] = [torch.tensor([0, 0, 1, 1, 2, 2, 2]), torch.tensor([3, 2, 2, 1, 3, 2, 0])]
     feature_store[("author", "writes", "paper"), "time", None] = torch.tensor([0, 0, 1, 0, 2, 1, 1])
-    kw = dict(num_neighbors={("paper", "cites", "paper"): [2, 2], ("author", "writes", "paper"): [2, 2]}, batch_size=2,
+    # fan-outs above every eligible count: both loaders take all eligible edges, whatever seed they draw for the epoch
+    kw = dict(num_neighbors={("paper", "cites", "paper"): [8, 8], ("author", "writes", "paper"): [8, 8]}, batch_size=2,
               input_nodes=("paper", torch.tensor([3, 2])), input_time=torch.tensor([-1, -1]), time_attr="time", shuffle=False,
               temporal_comparison="strictly_increasing", local_seeds_per_call=64)
     plain = next(iter(cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), disjoint=False, **kw)))
