@@ -405,3 +405,41 @@ def test_temporal_and_disjoint_combine(stack):
     n_plain = sum(int(plain[et].e_id.numel()) for et in (("paper", "cites", "paper"), ("author", "writes", "paper")))
     n_dis = sum(int(dis[et].e_id.numel()) for et in (("paper", "cites", "paper"), ("author", "writes", "paper")))
     assert 0 < n_dis < n_plain  # seed 3 reaches paper 2 (the other seed) and shared authors: those edges cross trees
+
+
+@pytest.mark.parametrize("mode", ["binary", "triplet"])
+def test_link_loader_negative_sampling_unchanged(stack, mode):
+    """Negative sampling (GPU-verified) through the same stack: guards BaseSampler.sample_from_edges, which the temporal link
+    path touched."""
+    cugraph_pyg, FS, sampler = stack
+    from cugraph_pyg._pyg_compat import NegativeSampling
+
+    rng = np.random.default_rng(6)
+    n, e = 50, 900
+    src, dst = torch.from_numpy(rng.integers(0, n, e)), torch.from_numpy(rng.integers(0, n, e))
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    graph_store[("n", "to", "n"), "coo", False, (n, n)] = [src, dst]
+    feature_store["n", "x", None] = torch.arange(n, dtype=torch.float32).reshape(n, 1)
+    eli = torch.stack([src[:16], dst[:16]])
+    loader = cugraph_pyg.loader.LinkNeighborLoader((feature_store, graph_store), num_neighbors=[3], batch_size=8, edge_label_index=eli,
+                                                   neg_sampling=NegativeSampling(mode, amount=1.0), shuffle=False, local_seeds_per_call=64)
+    seen = 0
+    for out in loader:
+        seen += 1
+        assert torch.equal(out.x[:, 0], out.n_id.float())
+        if mode == "binary":
+            lab = out.edge_label
+            assert out.edge_label_index.shape[1] == lab.numel() and int((lab == 1).sum()) == 8 and int((lab == 0).sum()) >= 1
+            pos = lab == 1
+            assert torch.equal(out.n_id[out.edge_label_index[0][pos]], eli[0, 8 * (seen - 1):8 * seen])
+            assert torch.equal(out.n_id[out.edge_label_index[1][pos]], eli[1, 8 * (seen - 1):8 * seen])
+        else:  # as tests/test_gpu_loader.py::test_link_neighbor_loader_negative_sampling checks the triplet form
+            lab = out.edge_label
+            pos = int((lab == 1.0).sum())
+            assert pos == out.input_id.numel() == 8 and lab.numel() > pos and bool((lab[pos:] == 0.0).all())
+            got = out.n_id[out.edge_label_index]
+            assert got.shape[1] == lab.numel() and torch.equal(got[1, :pos], eli[1, 8 * (seen - 1):8 * seen])
+    assert seen == 2
+    with pytest.raises(NotImplementedError):
+        cugraph_pyg.loader.LinkNeighborLoader((feature_store, graph_store), num_neighbors=[3], edge_label_index=eli, edge_label_time=torch.zeros(16),
+                                              time_attr="x", neg_sampling=NegativeSampling("binary"))
