@@ -71,6 +71,8 @@ class EmulatedSampler:
 
     def sample_temporal_async(self, csr_row_ptrs, csr_cols, csr_edge_times, seeds, seed_times, label_offsets, fanout, random_state, comparison, *,
                               vertex_type_offsets=None, csr_edge_ids=None, csr_weights=None, compression="COO", int64_ids=False):
+        if comparison not in CMP:  # as MultiHopSampler.sample_temporal_async
+            raise ValueError("temporal comparison must be one of %s, got %r" % (sorted(CMP), comparison))
         self.calls.append("temporal")
         T = len(csr_row_ptrs)
         hetero = vertex_type_offsets is not None
