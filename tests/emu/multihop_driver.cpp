@@ -60,8 +60,8 @@ extern "C" {
 int emu_multihop(int T, const long long* const* row_ptr, long long V, const void* const* col, const long long* num_edges, int col_is_int64,
                  const long long* const* edge_time, const void* const* weight, int weight_is_double, const long long* const* edge_id, const long long* vto, int Vt, int hetero,
                  const long long* seeds, const long long* seed_times, long long S, const long long* label_offsets, long long B, const int* fanout,
-                 int hops, unsigned long long random_state, int cmp, int flags, int reps, int want_seed_ids, void** out_ptr, long long* out_count,
-                 int* out_elt)
+                 int hops, unsigned long long random_state, int cmp, int flags, int reps, int want_seed_ids, const long long* num_times,
+                 void** out_ptr, long long* out_count, int* out_elt)
 {
   std::vector<wholememory_tensor_> rp(T), cl(T), tm(T), ei(T), wt(T);
   std::vector<wholememory_tensor_t> rp_h(T), cl_h(T), tm_h(T), ei_h(T), wt_h(T);
@@ -72,7 +72,7 @@ int emu_multihop(int T, const long long* const* row_ptr, long long V, const void
     rp_h[t] = &rp[t];
     cl_h[t] = &cl[t];
     if (edge_time) {
-      tm[t]   = make_tensor(edge_time[t], num_edges[t], WHOLEMEMORY_DT_INT64);
+      tm[t]   = make_tensor(edge_time[t], num_times ? num_times[t] : num_edges[t], WHOLEMEMORY_DT_INT64);  // real length: the entry point checks it
       tm_h[t] = &tm[t];
     }
     if (weight) {

@@ -62,7 +62,8 @@ def _run(lib, row_ptrs, cols, vto, seeds, lo, fanout, random_state, *, hetero=Tr
                           None if ei is None else arr(ei), vto.ctypes.data_as(VP), vto.shape[0] - 1,
                           int(hetero), seeds.ctypes.data_as(VP), st.ctypes.data_as(VP), ctypes.c_longlong(seeds.shape[0]), lo.ctypes.data_as(VP),
                           ctypes.c_longlong(lo.shape[0] - 1), fo.ctypes.data_as(VP), fo.shape[0] // T, ctypes.c_ulonglong(random_state), cmp,
-                          flags, reps, int(seed_local_ids), out_ptr, out_cnt, out_elt)
+                          flags, reps, int(seed_local_ids), None if tm is None else np.array([t.shape[0] for t in tm], dtype=np.int64).ctypes.data_as(VP),
+                          out_ptr, out_cnt, out_elt)
     assert rc == expect_rc, rc
     outs = {}
     for k, name in enumerate((HETERO if hetero else HOMO + ("unused", "unused2")) + ("seed_local_ids",)):
