@@ -1,23 +1,16 @@
-"""Everything that was written after round 1's GPU minutes were spent and has therefore not run on a GPU yet:
+"""Temporal and disjoint sampling on the GPU (first run on hardware in round 2: 59 passed, gpurun_out/r2a_temporal_tests.log):
   * S0 temporal (wholegraph_temporal_multihop_neighbor_sample_begin, uniform and biased): bit-exact against the oracle, the
     reference's deterministic pins (tests/loader/test_neighbor_loader.py:943-1170), "open window = plain sampling";
   * the temporal node / link loaders;
-  * disjoint sampling (torch post-filter on the plain call).
-All of it is logic-checked on the CPU (tests/test_emulated_*_cpu.py, test_pylibcugraph_emulated_cpu.py,
-test_loaders_emulated_cpu.py: the product's source through the SIMT emulator in tests/emu).  These GPU tests only run when
-WGB_RUN_UNVERIFIED=1.  First thing next round (profiles/run_round2_first_pass.sh does it, under `timeout`):
-    WGB_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_temporal.py -m gpu -x -q
+  * disjoint sampling.
+The same configurations also run on the CPU through the SIMT emulator in tests/emu (tests/test_emulated_*_cpu.py).
 """
-import os
-
 import numpy as np
 import pytest
 
 from graphs import random_typed_graph
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("WGB_RUN_UNVERIFIED") != "1",
-                                 reason="not yet run on a GPU (CPU-emulated only); set WGB_RUN_UNVERIFIED=1 to run")]
+pytestmark = [pytest.mark.gpu]
 
 HETERO_KEYS = ("label_type_hop_offsets", "renumber_map_offsets", "renumber_map", "majors", "minors", "edge_id", "edge_type",
                "edge_renumber_map", "edge_renumber_map_offsets", "label_type_step_base")
