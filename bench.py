@@ -4,9 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                     (the CPU implementation of the same path)
 
-Workload (BASELINE.json configs[1], "C2"): synthetic RMAT |V| = 10 M, |E| = 160 M (a,b,c,d = .57,.19,.19,.05,
-seed 42, vertex ids scrambled by an affine bijection as Graph500 does), CSR by destination, int64 row_ptr / int32 col_idx; features fp32 [|V|, 128] with the closed form
-table[i][d] = (i + d) & 0xFFFF; fan-out [25, 10]; sampler seed 62.
+Workload = the configuration BASELINE.json's metric is quoted on ("C4", ogbn-papers100M shape): synthetic RMAT
+|V| = 111 M, |E| = 1.6 B (a,b,c,d = .57,.19,.19,.05, seed 42, vertex ids scrambled by an affine bijection as Graph500
+does), CSR by destination, int64 row_ptr / int32 col_idx (7.3 GB, replicated per GPU); features fp32 [|V|, 128] with the
+closed form table[i][d] = (i + d) & 0xFFFF (56.8 GB, striped over the GPUs of the box, WholeGraph "chunked"); fan-out
+[25, 10]; sampler seed 62; pylibcugraph output shape (int64 majors / minors / edge ids).  It fits one B200 (64 GB of 180),
+so N = 1 runs it too.  --workload c2 | headline | c5 select the other shapes BASELINE.json names (c5: heterogeneous,
+with a DDP-wrapped 2-layer SAGE step so that the NCCL all-reduce of the dense weights is on the timeline).
 
 One step = one call group of 64 mini-batches ("labels") x 1024 seeds per GPU, i.e. what
 cugraph_pyg.sampler.DistributedNeighborSampler hands to the native sampler in one call
@@ -15,7 +19,9 @@ every mini-batch (sampler/sampler.py:51-165 -> FeatureStore -> WholeMemoryEmbedd
     1. fused multi-hop sampler: per label, hop 1 samples 25 neighbours of the seeds, hop 2 samples 10 neighbours
        of the vertices new in hop 1; per-label renumbering (seeds first, first-occurrence order); COO output
     2. gather the feature row of every vertex of every sampled sub-graph (the concatenated renumber maps).
-Every step uses a different seed set; the feature table (5.1 GB) and the bytes gathered per step exceed L2.
+Every step uses a different seed set; the feature table and the bytes gathered per step exceed L2 many times over.
+Before timing, rank 0 runs one 4-label call group through the CPU oracle on the same graph and asserts that the GPU result
+is identical (COO, edge ids, renumber map, offsets, gathered rows): "parity_checked" in the line.
 
 metric = sampled edges / s for the whole step (sampling + renumbering + feature gather), whole job over all GPUs.
 `value`: K call groups with device-resident seeds, software-pipelined the way the loader runs them (call group k+1 is
@@ -24,7 +30,9 @@ next call group's sampling kernels execute underneath it).  `e2e`: the same loop
 step's result read back to the host every step.
 Extra keys: gather_gbs (reference definition: gathered output bytes / gather time,
 cpp/bench/wholememory_ops/gather_scatter_bench.cu:352-355), stages (per-stage device times), roofline
-(dominant kernel = the gather), cpu_baseline (the oracle on the host cores, bounded sample).
+(dominant kernel = the gather), roofline_sampler (the sampling + renumbering stage against the same HBM peak),
+cpu_baseline (the oracle on the host cores, bounded sample); for N > 1 also striped_only (the same timed loop without the
+replicated hot rows: every remote row crosses NVLink) with its NVLink roofline.
 """
 import argparse
 import contextlib
@@ -39,23 +47,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "cugraph-gnn_b200"))
 
-NUM_NODES = 10_000_000
-NUM_EDGES = 160_000_000
+NUM_NODES = 111_000_000
+NUM_EDGES = 1_600_000_000
 FEAT_DIM = 128
 FANOUT = [25, 10]
 BATCH = 1024
 LABELS_PER_STEP = 64
 SAMPLER_SEED = 62
 RMAT = (0.57, 0.19, 0.19, 0.05)
+GATHER_TRAFFIC_FILE = "r1_gather_traffic.json"     # ncu --set full captures (per-unit DRAM bytes), refreshed per round
+SAMPLER_TRAFFIC_FILE = "r2_sampler_traffic.json"
 SCRAMBLE_MUL, SCRAMBLE_ADD = 7_919_717, 1_234_567  # multiplier coprime with every |V| used here (odd, not a multiple of 3 or 5)
-WORKLOAD = "C2 synthetic RMAT |V|=10M |E|=160M fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"
+WORKLOAD = "C4 ogbn-papers100M-shape synthetic RMAT |V|=111M |E|=1.6B fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"
 METRIC = "sampled_edges_per_sec (multi-hop sample + renumber + feature gather, fanout [25,10])"
 # --workload: the other shapes BASELINE.json names for this metric (same step, same kernels; not the default bench line).
-# c2 is the default and is what the constants above say; the others overwrite them in main().
+# c4 (the shape the metric is quoted on) is the default and is what the constants above say; the others overwrite them in main().
 WORKLOADS = {
-    "c2": None,
-    "c4": {"NUM_NODES": 111_000_000, "NUM_EDGES": 1_600_000_000, "FEAT_DIM": 128,
-           "WORKLOAD": "C4 ogbn-papers100M-shape synthetic RMAT |V|=111M |E|=1.6B fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"},
+    "c4": None,
+    "c2": {"NUM_NODES": 10_000_000, "NUM_EDGES": 160_000_000, "FEAT_DIM": 128,
+           "WORKLOAD": "C2 synthetic RMAT |V|=10M |E|=160M fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"},
+    "tiny": {"NUM_NODES": 200_000, "NUM_EDGES": 3_200_000, "FEAT_DIM": 128,  # CPU-side self-test of the harness (tests/test_bench_cpu.py)
+             "WORKLOAD": "tiny synthetic RMAT |V|=200k |E|=3.2M fanout=[25,10] feat_dim=128 fp32 (harness self-test, not a bench line)"},
     "headline": {"NUM_NODES": 100_000_000, "NUM_EDGES": 1_000_000_000, "FEAT_DIM": 256,
                  "WORKLOAD": "north-star synthetic RMAT |V|=100M |E|=1B fanout=[25,10] feat_dim=256 fp32, sampler+renumber+gather"},
 }
@@ -194,7 +206,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     log("[rank %d] RMAT CSR built in %.1fs, |E|=%d, max degree %d" % (rank, time.time() - t0, col.numel(), int((row_ptr[1:] - row_ptr[:-1]).max())))
 
-    # graph: replicated per GPU (720 MB); features: striped over the GPUs of the box and read by P2P
+    # graph: replicated per GPU (C4: 7.3 GB); features: striped over the GPUs of the box and read by P2P
     one = wgth.create_group_communicator(1, 1) if world > 1 else comm
     wm_rp = wgth.create_wholememory_tensor(one, "chunked", "cuda", [NUM_NODES + 1], torch.int64, [1])
     wm_rp.get_local_tensor()[0].copy_(row_ptr)
@@ -213,13 +225,25 @@ def run_ours(args):
         # replicate the hottest rows on every GPU (role of the reference's device cache for remote tables, static here):
         # hotness of a vertex = how often it appears as a CSR column = how often the sampler can reach it
         hot_rows = int(args.hot_ratio * NUM_NODES)
-        hotness = torch.bincount(wm_col.get_local_tensor()[0].long(), minlength=NUM_NODES)
-        emb.set_hot_rows(torch.topk(hotness, hot_rows).indices)
-        del hotness
+        hotness = torch.zeros(NUM_NODES, dtype=torch.int64, device=dev)
+        col_local = wm_col.get_local_tensor()[0]
+        for lo in range(0, col_local.numel(), 1 << 28):  # chunked: a 1.6 B-element int64 copy of col_idx would take 12.8 GB
+            hotness += torch.bincount(col_local[lo:lo + (1 << 28)].long(), minlength=NUM_NODES)
+        emb.set_hot_rows(torch.argsort(hotness, descending=True)[:hot_rows].contiguous())
+        del hotness, col_local
         comm.barrier()
     sampler = wgth.MultiHopSampler()
     labels = args.labels
     label_offsets = (torch.arange(labels + 1, dtype=torch.int64) * BATCH).to(dev)
+
+    # ---- parity, outside every timed region: one 4-label call group on THIS graph through the CPU oracle (test
+    # infrastructure, used here as the checker only) must equal what the GPU path returns, bit for bit
+    host_graph = None
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        host_graph = (row_ptr.cpu().numpy(), wm_col.get_local_tensor()[0].cpu().numpy())
+        parity = parity_check(torch, wgth, sampler, emb, wm_rp, wm_col, host_graph, dev)
+        log("[rank 0] parity vs oracle on the bench graph: %s" % parity)
 
     n_sets = args.steps + args.warmup
     host_seeds = [s.pin_memory() for s in seed_sets(torch, n_sets, labels, rank)]
@@ -227,7 +251,7 @@ def run_ours(args):
     def step(seeds_dev, seed, ev=None):
         if ev:
             ev[0].record()
-        res = sampler.sample(wm_rp, wm_col, seeds_dev, label_offsets, FANOUT, seed)
+        res = sampler.sample(wm_rp, wm_col, seeds_dev, label_offsets, FANOUT, seed, int64_ids=True)
         if ev:
             ev[1].record()
         x = emb.gather(res["renumber_map"])
@@ -246,7 +270,7 @@ def run_ours(args):
 
     def e2e_begin(k):
         sd = host_seeds[k].to(dev, non_blocking=True)  # H2D of the step's input, from pinned memory
-        return samplers[k & 1].sample_async(wm_rp, wm_col, sd, label_offsets, FANOUT, SAMPLER_SEED + 7 * k)
+        return samplers[k & 1].sample_async(wm_rp, wm_col, sd, label_offsets, FANOUT, SAMPLER_SEED + 7 * k, int64_ids=True)
 
     # Feature fetch on its own stream: the next call group's sampling kernels (latency / random-access bound, little
     # bandwidth) run underneath the bandwidth-bound gather.  Measured at N=1 with 20 steps: 0.845 ms/step against 0.881 on
@@ -333,8 +357,7 @@ def run_ours(args):
         with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
             prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
         prime.append(torch.empty(int(n_max * 1.25), dtype=torch.int64, device=dev))
-        prime += [torch.empty(int(e_max * 1.25), dtype=torch.int32, device=dev) for _ in range(2)]
-        prime.append(torch.empty(int(e_max * 1.25), dtype=torch.int64, device=dev))
+        prime += [torch.empty(int(e_max * 1.25), dtype=torch.int64, device=dev) for _ in range(3)]
     del prime
     torch.cuda.synchronize()
     if world > 1:
@@ -344,43 +367,48 @@ def run_ours(args):
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    launches0 = int(launch_count())
-    # (a) the timed region of `value`: K call groups, device-resident seeds, software-pipelined like the loader (call group
-    #     k+1 is begun before k is finished); gather events are recorded on the stream the gather is launched on
-    gev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
-    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def begin_dev(k):
-        return samplers[k & 1].sample_async(wm_rp, wm_col, dev_seeds[k], label_offsets, FANOUT, SAMPLER_SEED + 7 * k)
+        return samplers[k & 1].sample_async(wm_rp, wm_col, dev_seeds[k], label_offsets, FANOUT, SAMPLER_SEED + 7 * k, int64_ids=True)
 
-    torch.cuda.synchronize()
-    t_begin.record()
-    tot_edges = tot_nodes = 0
-    alive = []
-    pend = begin_dev(args.warmup)
-    for i in range(args.steps):
-        nxt = begin_dev(args.warmup + i + 1) if i + 1 < args.steps else None
-        res = pend.result()
+    def value_loop():
+        """The timed region of `value`: K call groups, device-resident seeds, software-pipelined like the loader (call group
+        k+1 is begun before k is finished); gather events are recorded on the stream the gather is launched on."""
+        launches0 = int(launch_count())
+        gev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(args.steps)]
+        t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_begin.record()
+        tot_edges = tot_nodes = 0
+        alive = []
+        pend = begin_dev(args.warmup)
+        for i in range(args.steps):
+            nxt = begin_dev(args.warmup + i + 1) if i + 1 < args.steps else None
+            res = pend.result()
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                gev[i][0].record()
+                x = emb.gather(res["renumber_map"])
+                gev[i][1].record()
+            alive.append((res, x))  # outputs live until the stream that reads them has passed (3 call groups in flight at most)
+            if len(alive) > 3:
+                alive.pop(0)
+            tot_edges += int(res["minors"].numel())
+            tot_nodes += int(res["renumber_map"].numel())
+            pend = nxt
         if side is not None:
-            side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-            gev[i][0].record()
-            x = emb.gather(res["renumber_map"])
-            gev[i][1].record()
-        alive.append((res, x))  # outputs live until the stream that reads them has passed (3 call groups in flight at most)
-        if len(alive) > 3:
-            alive.pop(0)
-        tot_edges += int(res["minors"].numel())
-        tot_nodes += int(res["renumber_map"].numel())
-        pend = nxt
-    if side is not None:
-        torch.cuda.current_stream().wait_stream(side)
-    t_end.record()
-    torch.cuda.synchronize()
-    del alive
-    launches = int(launch_count()) - launches0
-    ms_total = t_begin.elapsed_time(t_end)
-    gather_ms = sum(ev[0].elapsed_time(ev[1]) for ev in gev)
+            torch.cuda.current_stream().wait_stream(side)
+        t_end.record()
+        torch.cuda.synchronize()
+        del alive
+        return {"ms": t_begin.elapsed_time(t_end), "gather_ms": sum(ev[0].elapsed_time(ev[1]) for ev in gev),
+                "edges": tot_edges, "nodes": tot_nodes, "launches": int(launch_count()) - launches0}
+
+    main_run = value_loop()
+    ms_total, gather_ms, tot_edges, tot_nodes, launches = (main_run[k] for k in ("ms", "gather_ms", "edges", "nodes", "launches"))
     # (b) per-stage times, one synchronous pass over the same call groups (not part of `value`)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     for k in range(args.steps):
@@ -404,17 +432,24 @@ def run_ours(args):
         log("[rank %d] e2e device phases per step (before-result | result->gather done | gather->metric done): %s" % (
             rank, " ".join("%.2f|%.2f|%.2f" % (ev4[4 * i].elapsed_time(ev4[4 * i + 1]), ev4[4 * i + 1].elapsed_time(ev4[4 * i + 2]),
                                                ev4[4 * i + 2].elapsed_time(ev4[4 * i + 3])) for i in range(args.steps))))
-        log("[rank %d] e2e %.3f ms for %d steps; value loop %.3f ms (sample %.3f, gather %.3f); per step gather: %s" % (
-            rank, e2e_ms, args.steps, ms_total, sample_ms, gather_ms, " ".join("%.2f" % ev[0].elapsed_time(ev[1]) for ev in gev)))
+        log("[rank %d] e2e %.3f ms for %d steps; value loop %.3f ms (sample %.3f, gather %.3f)" % (rank, e2e_ms, args.steps, ms_total, sample_ms, gather_ms))
     clock_info = clocks.stop() if rank == 0 else None
 
-    stats = torch.tensor([ms_total, e2e_ms, sample_ms, gather_ms, gather_alone_ms], dtype=torch.float64, device=dev)
-    counts = torch.tensor([tot_edges, tot_nodes, e2e_edges], dtype=torch.float64, device=dev)
+    # ---- N > 1: the same timed loop with the replica dropped (every remote row crosses NVLink), reported beside `value`
+    striped = None
+    if world > 1 and hot_rows > 0:
+        emb.set_hot_rows(None)
+        comm.barrier()
+        value_loop()  # one untimed pass: allocator / clocks settle on the new gather durations
+        striped = value_loop()
+    stats = torch.tensor([ms_total, e2e_ms, sample_ms, gather_ms, gather_alone_ms] + ([striped["ms"], striped["gather_ms"]] if striped else [0.0, 0.0]),
+                         dtype=torch.float64, device=dev)
+    counts = torch.tensor([tot_edges, tot_nodes, e2e_edges] + ([striped["edges"], striped["nodes"]] if striped else [0, 0]), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, sample_ms, gather_ms, gather_alone_ms = stats.tolist()
-    tot_edges, tot_nodes, e2e_edges = counts.tolist()
+    ms_total, e2e_ms, sample_ms, gather_ms, gather_alone_ms, striped_ms, striped_gather_ms = stats.tolist()
+    tot_edges, tot_nodes, e2e_edges, striped_edges, striped_nodes = counts.tolist()
 
     if rank == 0:
         peaks = {}
@@ -425,20 +460,27 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         row_bytes = FEAT_DIM * 4
-        traffic, traffic_src = None, None
-        try:  # DRAM bytes of the gather kernel from the committed ncu --set full capture, scaled to this run's rows per launch
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r1_gather_traffic.json")))
-            per_row = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["rows_in_launch"]
-            traffic = per_row * (tot_nodes / world / args.steps)
-            traffic_src = "ncu dram__bytes_read+write per row (%s) x rows per launch of this run" % cap["source"]
-        except Exception:
-            pass
+
+        def captured(name, per_key, units):
+            """DRAM bytes per unit of work from a committed `ncu --set full` capture (profiles/<name>), scaled to this run."""
+            try:
+                cap = json.load(open(os.path.join(ROOT, "profiles", name)))
+                per = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap[per_key]
+                return per * units, "ncu dram__bytes_read+write per %s (%s) x this run's count per step" % (per_key.split("_")[0], cap["source"])
+            except Exception:
+                return None, None
+
         rows_per_rank = tot_nodes / world
+        edges_per_rank = tot_edges / world
+        traffic, traffic_src = captured(GATHER_TRAFFIC_FILE, "rows_in_launch", rows_per_rank / args.steps)
         gather_alg_bytes = (2 * row_bytes + 8) * rows_per_rank  # per rank, all steps
         gather_achieved = gather_alg_bytes / (gather_ms * 1e-3) / 1e9
-        # sampler algorithmic bytes (BASELINE.md §3, int32 ids out / int64 edge ids): per edge col 4 + minor 4 + major 4 + edge id 8,
-        # per frontier vertex id 8 + row_ptr 16
-        sample_alg_bytes = (20.0 * tot_edges + 24.0 * tot_nodes) / world
+        # sampler algorithmic bytes (SURVEY.md 8d, pylibcugraph shape = what this run returns): per sampled edge col 8 (4 read here:
+        # int32 col_idx) + minor 8 + major 8 + edge id 8 = 32 B, per frontier vertex id 8 + row_ptr 16 = 24 B
+        sample_alg_bytes = 32.0 * edges_per_rank + 24.0 * rows_per_rank
+        s_traffic, s_traffic_src = captured(SAMPLER_TRAFFIC_FILE, "edges_in_step", edges_per_rank / args.steps)
+        sampler_achieved = sample_alg_bytes / (sample_ms * 1e-3) / 1e9
+        step_alg_bytes = gather_alg_bytes + sample_alg_bytes
         out = {
             "metric": METRIC,
             "value": tot_edges / (ms_total * 1e-3),
@@ -450,14 +492,18 @@ def run_ours(args):
             "higher_is_better": True,
             "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "int64/int32 ids, fp32 features",
+            "dtype": "int64 ids (int32 col_idx in the CSR), fp32 features",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "labels_per_step_per_gpu": labels, "seeds_per_label": BATCH,
-                       "l2": "inputs larger than L2 (%.1f GB table, >1 GB gathered per step); new seed set every step" % (NUM_NODES * FEAT_DIM * 4 / 1e9),
+                       "l2": "inputs larger than L2 (%.1f GB table, ~1 GB gathered per step); new seed set every step" % (NUM_NODES * FEAT_DIM * 4 / 1e9),
                        "graph": "replicated per GPU", "features": "chunked over %d GPU(s), in-kernel P2P gather" % world,
-                       "hot_rows_replicated_per_gpu": hot_rows, "hot_rows_bytes_per_gpu": hot_rows * FEAT_DIM * 4 + (4 * NUM_NODES if hot_rows else 0),
+                       "output_shape": "pylibcugraph (int64 majors, minors, edge ids, renumber map)",
+                       "hot_rows_replicated_per_gpu": hot_rows if world > 1 else "n/a at N=1 (every row is local)",
+                       "hot_rows_bytes_per_gpu": hot_rows * FEAT_DIM * 4 + (4 * NUM_NODES if hot_rows else 0),
                        "pipeline": "call group k+1 begun before k is finished; gather on %s" % ("its own stream" if use_side else "the same stream"),
-                       **({"gather_sms": args.gather_sms} if args.gather_sms > 0 else {})},
+                       "gather_sms": args.gather_sms},
+            "parity_checked": bool(parity and parity.get("ok")),
+            "parity": parity,
             "gather_gbs": row_bytes * tot_nodes / (gather_ms * 1e-3) / 1e9,
             "stages": {
                 "sample_renumber_ms_per_step": sample_ms / args.steps,
@@ -467,18 +513,39 @@ def run_ours(args):
                 "edges_per_step_per_gpu": tot_edges / args.steps / world,
                 "nodes_gathered_per_step_per_gpu": tot_nodes / args.steps / world,
                 "sample_stage_edges_per_sec_per_gpu": tot_edges / world / (sample_ms * 1e-3),
-                "sample_stage_alg_gbs": sample_alg_bytes / (sample_ms * 1e-3) / 1e9,
             },
             "roofline": {"kernel": "rows_copy_kernel (feature gather)", "bound": "hbm", "achieved": gather_achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": gather_achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": gather_alg_bytes / args.steps, "peak_source": peak_src},
+            "roofline_sampler": {"kernel": "sampling + renumbering stage (all kernels of one MultiHopSampler call, synchronous pass)", "bound": "hbm",
+                                 "achieved": sampler_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": sampler_achieved / hbm_peak,
+                                 "traffic": s_traffic, "traffic_source": s_traffic_src,
+                                 "wasted_traffic_ratio": (s_traffic / (sample_alg_bytes / args.steps)) if s_traffic else None,
+                                 "algorithmic_bytes_per_step": sample_alg_bytes / args.steps,
+                                 "algorithmic_bytes": "32 B per sampled edge + 24 B per frontier vertex"},
+            "roofline_step": {"bound": "hbm", "achieved": step_alg_bytes / (ms_total * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": step_alg_bytes / (ms_total * 1e-3) / 1e9 / hbm_peak,
+                              "note": "algorithmic bytes of sampler + gather over the pipelined step time"},
             "e2e": {"value": e2e_edges / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": labels * BATCH * 8, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches,
             "clocks": clock_info,
         }
+        if striped:
+            # per-GPU NVLink bound of a striped table: (W-1)/W of the gathered bytes arrive over NVLink at the measured 770 GB/s
+            out_bytes_rank = row_bytes * striped_nodes / world
+            nvl_ms = out_bytes_rank * (world - 1) / world / 770e9 * 1e3
+            out["striped_only"] = {"value": striped_edges / (striped_ms * 1e-3), "unit": "edges/s", "ms_per_step": striped_ms / args.steps,
+                                   "gather_ms_per_step": striped_gather_ms / args.steps,
+                                   "gather_gbs_per_gpu": out_bytes_rank / (striped_gather_ms * 1e-3) / 1e9,
+                                   "roofline": {"bound": "nvlink", "peak": 770.0 * world / (world - 1), "unit": "GB/s of gathered output per GPU",
+                                                "achieved": out_bytes_rank / (striped_gather_ms * 1e-3) / 1e9,
+                                                "frac": nvl_ms / striped_gather_ms, "peak_source": "measured peer copy 770 GB/s per direction (B200_PROFILING.md)"},
+                                   "note": "same timed loop, replica dropped: every remote row crosses NVLink"}
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(row_ptr.cpu().numpy(), wm_col.get_local_tensor()[0].cpu().numpy(), budget_s=15.0)
+            if host_graph is None:
+                host_graph = (row_ptr.cpu().numpy(), wm_col.get_local_tensor()[0].cpu().numpy())
+            out["cpu_baseline"] = cpu_baseline(host_graph[0], host_graph[1], budget_s=15.0, labels=labels)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -489,34 +556,63 @@ def run_ours(args):
 # CPU arm: the oracle (a C++/OpenMP restatement of the reference's own host reference algorithms; the
 # reference's implementation cannot be compiled or installed here -- SURVEY.md §8c) on the host cores.
 # ----------------------------------------------------------------------------------------------------
-def cpu_baseline(row_ptr, col, budget_s=15.0, labels=4, steps=None):
-    import numpy as np
-
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import wg_oracle as oracle
 
-    table = None
-    try:
-        if NUM_NODES * FEAT_DIM * 4 > (8 << 30):
-            raise MemoryError  # the large shapes: closed-form rows instead of a host copy of the table
-        table = np.empty((NUM_NODES, FEAT_DIM), dtype=np.float32)
-        for lo in range(0, NUM_NODES, 1 << 20):
-            hi = min(NUM_NODES, lo + (1 << 20))
-            table[lo:hi] = (np.arange(lo, hi, dtype=np.int64)[:, None] + np.arange(FEAT_DIM)[None, :]) & 0xFFFF
-    except MemoryError:
-        table = None
+    # the host arm always gets every core of the box: torchrun exports OMP_NUM_THREADS=1 into each rank's environment
+    oracle.set_num_threads(os.cpu_count() or 1)
+    return oracle
+
+
+def parity_check(torch, wgth, sampler, emb, wm_rp, wm_col, host_graph, dev, labels=4):
+    """One `labels`-label call group on the bench graph through the GPU path and through the CPU oracle (checker only, outside
+    every timed region): COO, edge ids, renumber map, offsets and the gathered feature rows must be identical."""
+    import numpy as np
+
+    oracle = _oracle()
+    row_ptr, col = host_graph
+    g = torch.Generator(device="cpu").manual_seed(99)
+    seeds = torch.randperm(NUM_NODES, generator=g)[: labels * BATCH].contiguous()
+    lo = (np.arange(labels + 1) * BATCH).astype(np.int64)
+    res = sampler.sample(wm_rp, wm_col, seeds.to(dev), torch.from_numpy(lo).to(dev), FANOUT, SAMPLER_SEED, int64_ids=True)
+    x = emb.gather(res["renumber_map"])
+    exp = oracle.multihop_sample(row_ptr, col, seeds.numpy(), lo, FANOUT, SAMPLER_SEED)
+    keys = ("majors", "minors", "edge_id", "renumber_map", "renumber_map_offsets", "label_hop_offsets")
+    bad = [k for k in keys if not np.array_equal(res[k].cpu().numpy(), exp[k])]
+    ids = exp["renumber_map"].astype(np.int64)
+    want = ((ids[:, None] + np.arange(FEAT_DIM)[None, :]) & 0xFFFF).astype(np.float32)  # closed form of the table
+    if not np.array_equal(x.cpu().numpy(), want):
+        bad.append("gathered_features")
+    assert not bad, "GPU result differs from the oracle on the bench graph: %s" % bad
+    return {"ok": True, "labels": labels, "edges": int(exp["minors"].shape[0]), "nodes": int(ids.shape[0]), "compared": list(keys) + ["gathered_features"]}
+
+
+PROXY_ROWS = 4_000_000  # CPU arm: rows of the host feature table the gather reads (ids mod PROXY_ROWS)
+
+
+def cpu_baseline(row_ptr, col, budget_s=15.0, labels=4, steps=None):
+    import numpy as np
+
+    oracle = _oracle()
+    # Feature fetch on the host: random rows of a real fp32 table with the bench's row size.  The large shapes' tables
+    # (56.8 / 102 GB) are not replicated in host memory; the gather reads a 4 M-row proxy (2-4 GB, far beyond any LLC) at
+    # ids mod 4 M -- the same number of random row copies per step.
+    rows = min(NUM_NODES, PROXY_ROWS)
+    table = np.empty((rows, FEAT_DIM), dtype=np.float32)
+    for lo_ in range(0, rows, 1 << 20):
+        hi_ = min(rows, lo_ + (1 << 20))
+        table[lo_:hi_] = (np.arange(lo_, hi_, dtype=np.int64)[:, None] + np.arange(FEAT_DIM)[None, :]) & 0xFFFF
 
     def feat(ids):
-        if table is not None:
-            return oracle.gather(table, ids)
-        return ((ids[:, None] + np.arange(FEAT_DIM)[None, :]) & 0xFFFF).astype(np.float32)
+        return oracle.gather(table, ids if rows == NUM_NODES else ids % rows)
 
     rng = np.random.default_rng(0)
     lo = (np.arange(labels + 1) * BATCH).astype(np.int64)
     edges, busy, n_steps = 0, 0.0, 0
     t0 = time.time()
     while True:
-        seeds = rng.permutation(NUM_NODES)[: labels * BATCH].astype(np.int64)
+        seeds = rng.choice(NUM_NODES, size=labels * BATCH, replace=False).astype(np.int64)
         t1 = time.time()
         res = oracle.multihop_sample(row_ptr, col, seeds, lo, FANOUT, SAMPLER_SEED + n_steps)
         feat(res["renumber_map"])
@@ -531,7 +627,9 @@ def cpu_baseline(row_ptr, col, budget_s=15.0, labels=4, steps=None):
         elif time.time() - t0 > budget_s and n_steps >= 3:
             break
     return {"value": edges / busy, "unit": "edges/s", "cores": oracle.num_threads(), "kind": "port",
-            "sample": "%d timed steps of %d labels x %d seeds (same graph, fan-out, seed rule; 1 untimed warm-up step)" % (n_steps - 1, labels, BATCH)}
+            "sample": "%d timed steps of %d labels x %d seeds (same graph, fan-out, seed rule as the GPU arm; 1 untimed warm-up step; "
+                      "feature rows from a %d-row host table)" % (n_steps - 1, labels, BATCH, rows),
+            "ms_per_step": 1e3 * busy / max(1, n_steps - 1)}
 
 
 def run_reference(args):
@@ -543,16 +641,18 @@ def run_reference(args):
     dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
     row_ptr, col = rmat_csr(torch, NUM_NODES, NUM_EDGES, 42, dev)  # input generation only; nothing timed runs on the GPU
     row_ptr, col = row_ptr.cpu().numpy(), col.cpu().numpy()
-    t0 = time.time()
-    base = cpu_baseline(row_ptr, col, steps=args.steps + args.warmup - 1, labels=4)
-    wall = time.time() - t0
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+    # same step as the GPU arm: one call group of args.labels labels x 1024 seeds; W untimed + K timed steps
+    base = cpu_baseline(row_ptr, col, steps=args.steps + args.warmup - 1, labels=args.labels)
     out = {
         "impl": "reference",
         "metric": METRIC,
         "value": base["value"], "unit": "edges/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * wall / max(1, args.steps + args.warmup), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int64/int32 ids, fp32 features", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "labels_per_step": 4, "seeds_per_label": BATCH},
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int64 ids (int32 col_idx in the CSR), fp32 features", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "labels_per_step": args.labels, "seeds_per_label": BATCH,
+                   "host_threads": base["cores"], "note": "CPU arm runs on rank 0's host cores only, whatever N is"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -567,14 +667,15 @@ def main():
     ap.add_argument("--labels", type=int, default=LABELS_PER_STEP)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison on the bench graph (profiling runs)")
     ap.add_argument("--hot-ratio", type=float, default=0.1,
                     help="N > 1: fraction of the feature rows (the highest-degree vertices) replicated on every GPU; 0 = none")
     ap.add_argument("--gather-stream", type=int, default=-1, help="run the feature gather on a second stream (1, default) or in line (0)")
     ap.add_argument("--gather-sms", type=int, default=-1,
                     help="SM budget of the feature gather (reference knob `gather_sms`; grid = 8 CTAs x this many SMs, spread over all SMs); "
                          "-1 = every SM (default).  Experiment: 74 leaves half of every SM to the sampling kernels of the next call group")
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS),
-                    help="c2 (default, the bench line) | c4 (papers100M shape) | headline (|V|=100M, |E|=1B, F=256)")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS),
+                    help="c4 (default, the shape the metric is quoted on: papers100M) | c2 (|V|=10M, |E|=160M) | headline (|V|=100M, |E|=1B, F=256) | tiny (harness self-test)")
     args = ap.parse_args()
     if WORKLOADS[args.workload] is not None:
         globals().update(WORKLOADS[args.workload])

@@ -445,6 +445,7 @@ wholememory_error_code_t wholememory_scatter(wholememory_tensor_t input_tensor, 
                                              wholememory_tensor_t wholememory_tensor,
                                              wholememory_env_func_t* /*p_env_fns*/, void* stream, int scatter_sms)
 {
+  wgb::hot_rows_invalidate_for_tensor(wholememory_tensor);  // a replica of rows that are about to change would go stale
   return wgb::rows_op(wholememory_tensor, indices_tensor, input_tensor, stream, scatter_sms, true, nullptr);
 }
 

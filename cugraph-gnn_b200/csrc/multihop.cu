@@ -196,7 +196,8 @@ __global__ void __launch_bounds__(256) mh_seed_insert_kernel(MhSlot* table, cons
                                                              unsigned long long epoch, unsigned long long V,
                                                              const SeedT* __restrict__ seeds, int S,
                                                              const long long* __restrict__ label_offsets, int B,
-                                                             int* __restrict__ slabel, unsigned int* __restrict__ slot_of)
+                                                             int* __restrict__ slabel, unsigned int* __restrict__ slot_of,
+                                                             long long* __restrict__ clean, long long* __restrict__ bad_seed)
 {
   const unsigned int nslots          = *nslots_dev;
   const unsigned long long inv_epoch = (255ULL - epoch) << 56;
@@ -208,7 +209,15 @@ __global__ void __launch_bounds__(256) mh_seed_insert_kernel(MhSlot* table, cons
       else hi = mid;
     }
     slabel[s]                     = lo;
-    const unsigned long long item = (unsigned long long)lo * V + (unsigned long long)seeds[s];
+    // a seed outside [0, V) would alias another label's key and index row_ptr out of bounds: flag it (the call fails
+    // at _finish with WHOLEMEMORY_INVALID_INPUT) and carry on with vertex 0 so that nothing is read out of bounds
+    long long sv = (long long)seeds[s];
+    if (sv < 0 || (unsigned long long)sv >= V) {
+      *bad_seed = 1;
+      sv        = 0;
+    }
+    clean[s]                      = sv;  // what every later kernel of the call reads as "the seeds"
+    const unsigned long long item = (unsigned long long)lo * V + (unsigned long long)sv;
     const unsigned long long mine = inv_epoch | mh_tag(0u, (unsigned int)s);
     const unsigned int home       = mh_home(item, nslots);
     unsigned long long seen;
@@ -840,6 +849,8 @@ __global__ void __launch_bounds__(256) mh_hetero_emit_edges_kernel(const MhHeter
 
 }  // namespace wgb
 
+#include "multihop_fused.cuh"  // device half of the fused per-label path (FzArgs, kernels)
+
 // ---------------------------------------------------------------------------------------------------
 // sampler object: persistent scratch + hash table
 // ---------------------------------------------------------------------------------------------------
@@ -851,7 +862,8 @@ struct wholegraph_multihop_sampler_ {
   Buf table;
   unsigned int table_slots = 0;  // allocated capacity
   int epoch                = 0;  // last epoch handed out (0: table must be initialised)
-  Buf slabel, scan_state, small_i32, small_i64, counts, seed_slot, seed_rank;
+  Buf slabel, scan_state, small_i32, small_i64, counts, seed_slot, seed_rank, seed_clean;
+  long long* bad_seed_dev = nullptr;  // device flag of the call in flight: a seed was outside [0, V)
   Buf frontier[wgb::kMaxHops + 1], flabel[wgb::kMaxHops + 1], fr_off[wgb::kMaxHops + 1];
   Buf off[wgb::kMaxHops], dest[wgb::kMaxHops], erow[wgb::kMaxHops], gid[wgb::kMaxHops], slot[wgb::kMaxHops], rank_of[wgb::kMaxHops];
   Buf base;
@@ -859,6 +871,8 @@ struct wholegraph_multihop_sampler_ {
   Buf pos[wgb::kMaxHops], tcnt[wgb::kMaxHops + 1], typed[wgb::kMaxHops + 1], vscan_state, tbase, desc_dev;
   // temporal calls only
   Buf ftime[wgb::kMaxHops + 1], eligible[wgb::kMaxHops], clipped, tdesc_dev;
+  // fused per-label path (multihop_fused.cuh): label-major scratch
+  Buf fz[12];
   wgb::MhTemporalDesc tdesc_host;
   wgb::MhHeteroDesc desc_host;
   long long* h_totals = nullptr;  // pinned
@@ -884,6 +898,10 @@ struct wholegraph_multihop_sampler_ {
     bool hetero = false;  // typed outputs ([label][edge type][hop], ids per (label, vertex type))
     int T = 1, Vt = 1;
     int* tbase = nullptr;
+#ifndef WGB_HOST_EMULATION
+    bool fused = false;  // begun by multihop_begin_fused: finish copies label segments
+    wgb::FzArgs fz;
+#endif
   } pending;
   cudaEvent_t ready = nullptr;  // recorded after the output sizes have been copied to h_totals
   // WGB_MH_TIMING=1: per-stage device times (cudaEvents between launches), averaged, printed at destroy
@@ -1050,9 +1068,18 @@ static void launch_hop_sample(const MhCall& c, const MhTypeCsr& g, const long lo
   WGB_CHECK_LAUNCH();
 }
 
+#ifndef WGB_HOST_EMULATION
+template <typename ColT>
+static bool multihop_begin_fused(MhCall& c);
+#endif
+
 template <typename ColT, bool CHUNKED>
 static void multihop_begin(MhCall& c)
 {
+#ifndef WGB_HOST_EMULATION
+  c.sp->pending.fused = false;
+  if (!CHUNKED && multihop_begin_fused<ColT>(c)) return;
+#endif
   auto* sp        = c.sp;
   sp->pending.active   = false;  // a call that was begun but never finished is abandoned: its scratch is reused below
   sp->pending.finished = false;
@@ -1181,15 +1208,17 @@ static void multihop_begin(MhCall& c)
     long long* frontier0 = static_cast<long long*>(ensure(sp->frontier[0], sizeof(long long) * (size_t)std::max(S, 1)));
     int* flabel0         = static_cast<int*>(ensure(sp->flabel[0], sizeof(int) * (size_t)std::max(S, 1)));
     auto ss              = scan_slice(S, kCompactTile);
-    if (c.seed_dtype == WHOLEMEMORY_DT_INT) {
-      mh_seed_insert_kernel<int><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const int*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
-      WGB_CHECK_LAUNCH();
-      mh_compact_kernel<int, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const int*>(c.seeds), nullptr, S, nullptr, slabel, slot0, rank0, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
-    } else {
-      mh_seed_insert_kernel<long long><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const long long*>(c.seeds), S, c.label_offsets, B, slabel, slot0);
-      WGB_CHECK_LAUNCH();
-      mh_compact_kernel<long long, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, static_cast<const long long*>(c.seeds), nullptr, S, nullptr, slabel, slot0, rank0, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
-    }
+    // seeds are range-checked on the device (no host copy of them exists): bad_seed travels to the host with the sizes
+    long long* clean    = static_cast<long long*>(ensure(sp->seed_clean, sizeof(long long) * (size_t)std::max(S, 1) + 16));
+    long long* bad_seed = clean + std::max(S, 1);
+    WGB_CUDA_TRY(cudaMemsetAsync(bad_seed, 0, sizeof(long long), st));
+    sp->bad_seed_dev = bad_seed;
+    if (c.seed_dtype == WHOLEMEMORY_DT_INT)
+      mh_seed_insert_kernel<int><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const int*>(c.seeds), S, c.label_offsets, B, slabel, slot0, clean, bad_seed);
+    else
+      mh_seed_insert_kernel<long long><<<grid_over(S, sms), 256, 0, st>>>(table, nslots_dev, epoch, c.V, static_cast<const long long*>(c.seeds), S, c.label_offsets, B, slabel, slot0, clean, bad_seed);
+    WGB_CHECK_LAUNCH();
+    mh_compact_kernel<long long, true><<<scan_grid(ss.second), kScanBlock, 0, st>>>(table, 0u, clean, nullptr, S, nullptr, slabel, slot0, rank0, frontier0, flabel0, n_rows_dev, ss.first, ticket_of(ss));
     WGB_CHECK_LAUNCH();
     if (c.temporal) {
       long long* ftime0 = static_cast<long long*>(ensure(sp->ftime[0], sizeof(long long) * (size_t)std::max(S, 1)));
@@ -1442,6 +1471,7 @@ static void multihop_begin(MhCall& c)
   WGB_CHECK_LAUNCH();
   // ---- output sizes travel to pinned memory; _finish waits for `ready`, not for the stream ----------------------
   WGB_CUDA_TRY(cudaMemcpyAsync(sp->h_totals, totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  WGB_CUDA_TRY(cudaMemcpyAsync(sp->h_totals + 3, sp->bad_seed_dev, sizeof(long long), cudaMemcpyDeviceToHost, st));
   WGB_CUDA_TRY(cudaEventRecord(sp->ready, st));
   mh_mark(sp, "meta+scan3", st);
   auto& pd = sp->pending;
@@ -1465,10 +1495,21 @@ struct MhOutCtx {
   cudaStream_t stream;
 };
 
+}  // namespace wgb
+#define WGB_FZ_HOST_HALF
+#include "multihop_fused.cuh"  // host half: multihop_begin_fused / multihop_finish_fused
+namespace wgb {
+
 // second half of a call: wait for the sizes, allocate the outputs, scatter scratch -> outputs
 static void multihop_finish(wholegraph_multihop_sampler_* sp, const MhOutCtx& c)
 {
   WGB_EXPECTS(sp->pending.active, "no call in flight on this sampler object");
+#ifndef WGB_HOST_EMULATION
+  if (sp->pending.fused) {
+    multihop_finish_fused(sp, c);
+    return;
+  }
+#endif
   auto& pd        = sp->pending;
   pd.active       = false;
   pd.finished     = true;
@@ -1486,6 +1527,7 @@ static void multihop_finish(wholegraph_multihop_sampler_* sp, const MhOutCtx& c)
   WGB_CUDA_TRY(cudaEventSynchronize(sp->ready));
   WGB_CUDA_TRY(cudaStreamWaitEvent(st, sp->ready, 0));  // no-op on the stream the call was begun on
   const long long n_edges = sp->h_totals[0], n_nodes = sp->h_totals[1], n_srcrows = sp->h_totals[2];
+  if (sp->h_totals[3] != 0) throw invalid_input("a seed vertex id is outside [0, number of vertices)");
 
   const bool csr    = (pd.flags & WHOLEGRAPH_MULTIHOP_CSR) != 0;
   const bool idx64  = (pd.flags & WHOLEGRAPH_MULTIHOP_INT64_IDS) != 0;
@@ -1623,11 +1665,13 @@ wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop
     b.p = nullptr;
   };
   cudaDeviceSynchronize();
-  drop(s->table); drop(s->seed_slot); drop(s->seed_rank); drop(s->slabel); drop(s->scan_state); drop(s->small_i32); drop(s->small_i64); drop(s->counts); drop(s->base);
+  drop(s->table); drop(s->seed_slot); drop(s->seed_rank); drop(s->seed_clean); drop(s->slabel); drop(s->scan_state); drop(s->small_i32); drop(s->small_i64); drop(s->counts); drop(s->base);
   for (int i = 0; i <= wgb::kMaxHops; i++) {
     drop(s->frontier[i]); drop(s->flabel[i]); drop(s->fr_off[i]); drop(s->tcnt[i]); drop(s->typed[i]);
   }
   drop(s->vscan_state); drop(s->tbase); drop(s->desc_dev); drop(s->clipped); drop(s->tdesc_dev);
+  for (auto& b : s->fz)
+    drop(b);
   for (int i = 0; i <= wgb::kMaxHops; i++)
     drop(s->ftime[i]);
   for (int i = 0; i < wgb::kMaxHops; i++)
@@ -1706,6 +1750,7 @@ static wholememory_error_code_t multihop_begin_entry(const char* what, wholegrap
   }
   return guarded(what, [&] {
     WGB_EXPECTS(sd->sizes[0] < (1LL << 31) - kScanTile, "too many seeds for one call");
+    WGB_CHECK_INPUT(sd->sizes[0] == 0 || wholememory_tensor_get_tensor_description(csr_row_ptr[0])->sizes[0] > 1, "seeds were given for a graph without vertices");
     WGB_EXPECTS(ld->sizes[0] - 1 < (1LL << 23), "too many labels for one call");
     MhCall c;
     c.sp        = sampler;
@@ -1881,6 +1926,12 @@ wholememory_error_code_t wholegraph_multihop_seed_local_ids(wholegraph_multihop_
     WGB_EXPECTS(pd.finished && !pd.active, "seed ids are available between _finish of a call and the next _begin on the same sampler object");
     cudaStream_t st = as_stream(stream);
     int* out        = static_cast<int*>(output_alloc(p_env_fns, out_seed_local_id_ctx, pd.S, WHOLEMEMORY_DT_INT));
+#ifndef WGB_HOST_EMULATION
+    if (pd.fused) {
+      if (pd.S > 0) WGB_CUDA_TRY(cudaMemcpyAsync(out, pd.fz.seed_local, sizeof(int) * (size_t)pd.S, cudaMemcpyDeviceToDevice, st));
+      return;
+    }
+#endif
     if (pd.S > 0) {
       mh_seed_local_kernel<<<grid_over(pd.S, num_sms()), 256, 0, st>>>(pd.seed_ref, pd.seed_rank, pd.slabel, pd.meta.fr_off[0],
                                                                        pd.hetero ? sampler->desc_host.typed_local[0] : nullptr, pd.S, out);

@@ -1,0 +1,701 @@
+// S0, fused form: every hop of a call group in ONE persistent kernel, one thread-block cluster per label (mini-batch).
+// Included by multihop.cu (needs its sampler object); same results, bit for bit, as the per-hop kernel chain there.
+//
+// Why: the kernel chain of multihop.cu (count+scan -> plan -> reinsert -> sample -> insert -> compact per hop, ~16
+// launches) streams every intermediate of the call group (2.5 M edges x ~40 B) through DRAM between kernels and keeps
+// one 16 B/slot hash table for all labels (94 MB at the bench shape: beyond L2) -- measured 7x the algorithmic DRAM
+// traffic.  A label (1024 seeds -> <= 282 k vertices at fan-out [25,10], ~40 k in practice) is an independent unit of
+// work; everything it produces between its hops fits in L2 next to the other labels in flight.  So:
+//   * a cluster of CL CTAs (CL = 1..8, chosen so that labels-in-flight x CL covers the 148 SMs) takes labels by ticket
+//     and runs seeds -> [count -> sample -> dedup -> compact] x hops for its label, phases separated by cluster barriers
+//     (barrier.cluster, ~0.2 us) instead of kernel boundaries; per-CTA partial sums travel through distributed shared
+//     memory;
+//   * the label's hash table is private (no label in the key): 8-byte slots {vertex:32 | aux:32}, buckets of four = one
+//     32-byte sector read by one 256-bit load, sized from the label's true counts every hop and memset by the cluster
+//     itself, so it lives and dies in L2;
+//   * all per-label scratch is laid out label-major (label l's vertices at lo[l] * fstride, edges at lo[l] * estride):
+//     the label's vertex array IS its renumber map (seeds first, then every hop's new vertices in first-occurrence
+//     order), its edge arrays ARE the output segments -- _finish is a segmented copy;
+//   * the only cross-label dependency is the random stream geometry (row b of the label-major concatenated frontier
+//     draws from subsequence 32 b + lane): the base row index of a label at a hop is a decoupled look-back over the
+//     labels before it (flag | count words, labels are taken in ticket order so every predecessor is resident or done).
+// Eligibility (multihop_begin decides): homogeneous, uniform, not temporal, graph on this GPU (world 1), every fan-out
+// in [1, 32], |V| < 2^32 - 1.  Everything else takes the kernel chain.
+// The file is included twice by multihop.cu: first for the device half (before the sampler object, whose pending-call state
+// holds an FzArgs), then with WGB_FZ_HOST_HALF defined for the host half (after MhCall / MhOutCtx exist).
+#ifndef WGB_HOST_EMULATION
+#ifndef WGB_FZ_HOST_HALF
+
+#include <cooperative_groups.h>
+
+namespace wgb {
+
+namespace cg = cooperative_groups;
+
+constexpr int kFzThreads            = 1024;
+constexpr unsigned int kFzPending   = 0x80000000u;
+constexpr unsigned long long kFzEmpty = ~0ULL;
+constexpr unsigned long long kFzFlagAgg = 1ULL << 62, kFzFlagPrefix = 2ULL << 62, kFzValMask = (1ULL << 62) - 1;
+
+struct FzArgs {
+  ChunkRef row_ptr, col;  // world 1
+  unsigned long long row_ptr_off, col_off;
+  const void* seeds;
+  int seed_is64;
+  const long long* label_offsets;
+  int B, L;
+  int fanout[kMaxHops];
+  long long fstride, estride;  // upper bounds per seed: vertices (1 + estride), edges
+  unsigned long long random_state;
+  // label-major scratch (label l: vertices at lo[l] * fstride, edges at lo[l] * estride, table at fz_table_base(l))
+  long long* F;           // vertices = renumber map segments
+  int* Orow;              // per source row: label-local offset of its first edge
+  int* maj;               // per edge: local id of its source row
+  int* mnr;               // per edge: local id of its endpoint
+  long long* gid;         // per edge: position in the CSR
+  void* dest;             // per edge: endpoint (global id, ColT)
+  unsigned int* aux;      // per edge: slot index, then the slot's aux word
+  unsigned int* rank_of;  // per edge that is a first occurrence: rank among the hop's new vertices
+  unsigned long long* table;
+  int* seed_local;          // [S] local id of every input seed
+  int* n_step;              // [B][L+1] vertices discovered at step t
+  int* e_hop;               // [B][L] edges of hop h
+  unsigned long long* pub;  // [L][B] look-back words: frontier rows of (hop, label)
+  unsigned int* ticket;
+  long long* bad_seed;   // set when a seed is outside [0, V): the call fails at _finish
+  unsigned long long V;
+  const Affine* tab;
+};
+
+__device__ __forceinline__ long long fz_table_base(long long lo_l, long long fstride, int l)
+{
+  return 4 * ((lo_l * fstride + 1) / 2 + 16LL * l);  // in slots; a multiple of 4 (bucket = 32-byte sector)
+}
+
+__device__ __forceinline__ unsigned int fz_home(unsigned int v, unsigned int nb)
+{
+  unsigned int h = v * 0x9E3779B1u;
+  h ^= h >> 15;
+  h *= 0x85EBCA77u;
+  h ^= h >> 13;
+  return (unsigned int)(((unsigned long long)h * nb) >> 32);
+}
+
+// claim-or-find `v` in a table of nb buckets; the slot's aux after this thread's visit is at most `mine`
+__device__ __forceinline__ unsigned int fz_upsert(unsigned long long* __restrict__ tbl, unsigned int nb, unsigned int v, unsigned int mine)
+{
+  unsigned int b = fz_home(v, nb);
+  const unsigned long long fresh = ((unsigned long long)v << 32) | mine;
+  while (true) {
+    unsigned long long w[4];
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+                 : "l"(tbl + 4ULL * b)
+                 : "memory");
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      unsigned long long cur = w[j];
+      if (cur == kFzEmpty) {
+        cur = atomicCAS(&tbl[4ULL * b + j], kFzEmpty, fresh);
+        if (cur == kFzEmpty) return 4u * b + j;
+      }
+      if ((unsigned int)(cur >> 32) == v) {
+        // little endian: the aux word is the low half of the slot
+        if ((unsigned int)cur > mine) atomicMin(reinterpret_cast<unsigned int*>(&tbl[4ULL * b + j]), mine);
+        return 4u * b + j;
+      }
+    }
+    b = b + 1 == nb ? 0u : b + 1;
+  }
+}
+
+struct FzShared {
+  unsigned int warp[34];
+  unsigned long long xchg[2][2];  // [parity][0] = this CTA's partial sum of the current exchange
+  long long rowbase;              // CTA 0: first row of this label in the label-major frontier of the next hop
+  int label;
+  int W[kFzThreads / 32][32];
+};
+
+// exclusive scan of one value per thread over the CTA; total in every thread
+__device__ __forceinline__ unsigned int fz_block_scan(unsigned int v, unsigned int* s_warp, unsigned int& total)
+{
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  if (lane == 31) s_warp[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    unsigned int w = lane < kFzThreads / 32 ? s_warp[lane] : 0u;
+    unsigned int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    s_warp[lane] = wi - w;
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  const unsigned int r = s_warp[wid] + inc - v;
+  total                = s_warp[32];
+  __syncthreads();
+  return r;
+}
+
+struct FzCluster {
+  FzShared* sh;
+  unsigned int rank, size;
+  unsigned int xround;
+
+  // every thread contributes `mine`; returns the sum over the CTAs before this one, `total` over all.  One cluster barrier.
+  __device__ __forceinline__ unsigned long long exchange(unsigned long long mine, unsigned long long& total)
+  {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    __shared__ unsigned long long s_part[kFzThreads / 32];
+    if (lane == 0) s_part[wid] = mine;
+    __syncthreads();
+    const unsigned int par = xround & 1u;
+    xround++;
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+      for (int w = 0; w < kFzThreads / 32; w++)
+        t += s_part[w];
+      sh->xchg[par][0] = t;
+    }
+    cg::this_cluster().sync();
+    unsigned long long before = 0;
+    total                     = 0;
+    for (unsigned int r = 0; r < size; r++) {
+      const unsigned long long t = size == 1 ? sh->xchg[par][0] : cg::this_cluster().map_shared_rank(&sh->xchg[par][0], r)[0];
+      if (r < rank) before += t;
+      total += t;
+    }
+    return before;
+  }
+  __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+};
+
+// Ordered exclusive scan over n items spread over the cluster: CTA c owns the contiguous chunk [c * chunk, (c+1) * chunk).
+//   first(i)           -> value of item i (may have side effects; called once per item)
+//   second(i)          -> the same value again (cheap form)
+//   out(i, prefix, v)  -> called once per item with its exclusive prefix
+// Returns the total.  Costs one cluster barrier.
+template <typename First, typename Second, typename Out>
+__device__ __forceinline__ unsigned int fz_ordered_scan(FzCluster& c, long long n, First first, Second second, Out out)
+{
+  const long long chunk = ((n + c.size - 1) / c.size + kFzThreads - 1) / kFzThreads * kFzThreads;
+  const long long beg   = (long long)c.rank * chunk < n ? (long long)c.rank * chunk : n;
+  const long long end   = beg + chunk < n ? beg + chunk : n;
+  unsigned long long mine = 0;
+  for (long long i = beg + threadIdx.x; i < end; i += kFzThreads)
+    mine += first(i);
+  unsigned long long total;
+  unsigned long long carry = c.exchange(mine, total);
+  for (long long t0 = beg; t0 < end; t0 += kFzThreads) {
+    const long long i    = t0 + threadIdx.x;
+    const unsigned int v = i < end ? second(i) : 0u;
+    unsigned int tile_total;
+    const unsigned int ex = fz_block_scan(v, c.sh->warp, tile_total);
+    if (i < end) out(i, (unsigned int)carry + ex, v);
+    carry += tile_total;
+  }
+  return (unsigned int)total;
+}
+
+// decoupled look-back over the labels before `l` (one warp): publishes this label's count, returns the sum of the counts
+// of labels 0..l-1
+__device__ __forceinline__ unsigned long long fz_lookback(unsigned long long* state, int l, unsigned long long agg)
+{
+  const int lane               = threadIdx.x & 31;
+  unsigned long long exclusive = 0;
+  if (l == 0) {
+    if (lane == 0) st_relaxed_u64(&state[0], kFzFlagPrefix | agg);
+  } else {
+    if (lane == 0) st_relaxed_u64(&state[l], kFzFlagAgg | agg);
+    int idx = l - 1;
+    while (true) {
+      const int t = idx - lane;
+      unsigned long long w;
+      do {
+        w = (t >= 0) ? ld_relaxed_u64(&state[t]) : kFzFlagPrefix;
+      } while (__any_sync(0xffffffffu, (w >> 62) == 0));
+      const unsigned int pm  = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+      unsigned long long val = w & kFzValMask;
+      if (pm) {
+        const int first = __ffs(pm) - 1;
+        if (lane > first) val = 0;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+        val += __shfl_xor_sync(0xffffffffu, val, o);
+      exclusive += val;
+      if (pm) break;
+      idx -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(&state[l], kFzFlagPrefix | ((exclusive + agg) & kFzValMask));
+  }
+  return exclusive;
+}
+
+template <typename ColT>
+struct FzSink {
+  ColT* __restrict__ dest;
+  int* __restrict__ maj;
+  long long* __restrict__ gid;
+  __device__ __forceinline__ void ids(int pos, int tag, long long edge_pos) const
+  {
+    maj[pos] = tag;
+    gid[pos] = edge_pos;
+  }
+  __device__ __forceinline__ void val(int pos, ColT v) const { dest[pos] = v; }
+};
+
+template <typename ColT, int G>
+__device__ __forceinline__ void fz_sample_rows(const FzArgs& a, FzCluster& c, const long long* __restrict__ Fl, const int* __restrict__ Ol,
+                                               int nbase, int n_rows, int ebase, long long rowbase, int M, unsigned long long seed,
+                                               FzSink<ColT>& sink)
+{
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = lane & (G - 1), sub = lane / G;
+  const Affine lane_skip = affine_skip_loop((unsigned long long)g);
+  int* Wg                = &c.sh->W[wib][sub * G];
+  const int warps        = (int)c.size * (kFzThreads / 32);
+  for (int batch = (int)c.rank * (kFzThreads / 32) + wib; (long long)batch * 32 < n_rows; batch += warps) {
+    const int r         = batch * 32 + lane;
+    long long start_own = 0;
+    int N_own = 0, off_own = 0;
+    if (r < n_rows) {
+      const unsigned long long node = (unsigned long long)Fl[nbase + r];
+      start_own     = load_i64<false>(a.row_ptr, a.row_ptr_off + node);
+      long long end = load_i64<false>(a.row_ptr, a.row_ptr_off + node + 1);
+      N_own         = (int)(end - start_own);
+      off_own       = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
+    }
+    uniform_small_rows32<ColT, G, false>(a.col, a.col_off, M, seed, a.tab, lane_skip, Wg, lane, rowbase + r, nbase + r, start_own, N_own,
+                                         off_own, sink);
+  }
+}
+
+template <typename ColT>
+__global__ void __launch_bounds__(kFzThreads, 1) fz_label_kernel(const __grid_constant__ FzArgs a)
+{
+  __shared__ FzShared sh;
+  FzCluster c;
+  c.sh     = &sh;
+  c.rank   = cg::this_cluster().block_rank();
+  c.size   = cg::this_cluster().num_blocks();
+  c.xround = 0;
+  const int tid          = threadIdx.x;
+  const unsigned int CT  = c.size * kFzThreads;        // threads of the cluster
+  const unsigned int cti = c.rank * kFzThreads + tid;  // this thread's index in the cluster
+  const int L            = a.L, B = a.B;
+
+  while (true) {
+    // ---- next label (tickets are handed out in label order) ------------------------------------------------
+    if (c.rank == 0 && tid == 0) sh.label = (int)atomicAdd(a.ticket, 1u);
+    c.sync();
+    const int l = c.size == 1 ? sh.label : *cg::this_cluster().map_shared_rank(&sh.label, 0);
+    c.sync();  // everybody has read it before CTA 0 takes the next ticket
+    if (l >= B) return;
+
+    const long long lo_l = a.label_offsets[l];
+    const int n_seeds    = (int)(a.label_offsets[l + 1] - lo_l);
+    long long* __restrict__ Fl          = a.F + lo_l * a.fstride;
+    int* __restrict__ Ol                = a.Orow + lo_l * a.fstride;
+    const long long ebeg                = lo_l * a.estride;
+    int* __restrict__ majl              = a.maj + ebeg;
+    int* __restrict__ mnrl              = a.mnr + ebeg;
+    long long* __restrict__ gidl        = a.gid + ebeg;
+    ColT* __restrict__ destl            = static_cast<ColT*>(a.dest) + ebeg;
+    unsigned int* __restrict__ auxl     = a.aux + ebeg;
+    unsigned int* __restrict__ rankl    = a.rank_of + ebeg;
+    unsigned long long* __restrict__ tb = a.table + fz_table_base(lo_l, a.fstride, l);
+    int* __restrict__ n_step            = a.n_step + (long long)l * (L + 1);
+    int* __restrict__ e_hop             = a.e_hop + (long long)l * L;
+
+    // ---- step 0: the label's distinct seeds, first occurrence first ----------------------------------------
+    unsigned int nb = ((unsigned int)n_seeds >> 1) + 8u;
+    for (unsigned int i = cti; i < nb * 4u; i += CT)
+      tb[i] = kFzEmpty;
+    c.sync();
+    for (int s = (int)cti; s < n_seeds; s += (int)CT) {
+      long long v = a.seed_is64 ? static_cast<const long long*>(a.seeds)[lo_l + s] : (long long)static_cast<const int*>(a.seeds)[lo_l + s];
+      if (v < 0 || (unsigned long long)v >= a.V) {  // flagged; carry on with vertex 0 so that nothing is read out of bounds
+        *a.bad_seed = 1;
+        v           = 0;
+      }
+      gidl[s] = v;  // the label's edge scratch is free until hop 0 writes it: sanitised seeds for the compaction below
+      auxl[s] = fz_upsert(tb, nb, (unsigned int)v, kFzPending | (unsigned int)s);
+    }
+    c.sync();
+    int known = (int)fz_ordered_scan(
+      c, n_seeds,
+      [&](long long s) -> unsigned int {
+        const unsigned int ax = (unsigned int)ld_relaxed_u64(&tb[auxl[s]]);
+        auxl[s]               = ax;
+        return ax == (kFzPending | (unsigned int)s) ? 1u : 0u;
+      },
+      [&](long long s) -> unsigned int { return auxl[s] == (kFzPending | (unsigned int)s) ? 1u : 0u; },
+      [&](long long s, unsigned int rank, unsigned int f) {
+        if (f) {
+          Fl[rank] = gidl[s];
+          rankl[s] = rank;
+        }
+      });
+    if (c.rank == 0 && tid < 32) {
+      const unsigned long long rb = fz_lookback(a.pub, l, (unsigned long long)known);
+      if (tid == 0) {
+        sh.rowbase = (long long)rb;
+        n_step[0]  = known;
+      }
+    }
+    c.sync();  // ranks of the first occurrences are visible
+    for (int s = (int)cti; s < n_seeds; s += (int)CT)
+      a.seed_local[lo_l + s] = (int)rankl[auxl[s] & ~kFzPending];
+
+    // ---- hops ----------------------------------------------------------------------------------------------------
+    int nbase = 0, n_rows = known, ebase = 0;  // frontier of hop h = Fl[nbase, nbase + n_rows)
+    for (int h = 0; h < L; h++) {
+      const int M = a.fanout[h];
+      // P1: min(deg, M) per frontier row, exclusive scan in row order -> the row's first edge
+      const int e_h = (int)fz_ordered_scan(
+        c, n_rows,
+        [&](long long r) -> unsigned int {
+          const unsigned long long node = (unsigned long long)Fl[nbase + r];
+          const long long s0 = load_i64<false>(a.row_ptr, a.row_ptr_off + node);
+          const long long s1 = load_i64<false>(a.row_ptr, a.row_ptr_off + node + 1);
+          long long d        = s1 - s0;
+          d                  = d < 0 ? 0 : (d > M ? M : d);
+          Ol[nbase + r]      = (int)d;
+          return (unsigned int)d;
+        },
+        [&](long long r) -> unsigned int { return (unsigned int)Ol[nbase + r]; },
+        [&](long long r, unsigned int prefix, unsigned int) { Ol[nbase + r] = ebase + (int)prefix; });
+      // (the scan's barrier also ordered CTA 0's rowbase before everybody's read below)
+      const long long rowbase = c.size == 1 ? sh.rowbase : *cg::this_cluster().map_shared_rank(&sh.rowbase, 0);
+      if (c.rank == 0 && tid == 0) e_hop[h] = e_h;
+      known = nbase + n_rows;
+      // P2: a fresh table for (everything numbered so far + this hop's edges)
+      nb = (((unsigned int)known + (unsigned int)e_h) >> 1) + 8u;
+      for (unsigned int i = cti; i < nb * 4u; i += CT)
+        tb[i] = kFzEmpty;
+      c.sync();  // table cleared, row offsets visible
+      // P3: numbered vertices enter with their local id; the hop's rows are sampled (independent of the table)
+      for (int j = (int)cti; j < known; j += (int)CT)
+        fz_upsert(tb, nb, (unsigned int)Fl[j], (unsigned int)j);
+      if (e_h > 0) {
+        FzSink<ColT> sink{destl + ebase, majl + ebase, gidl + ebase};
+        const unsigned long long hop_seed = a.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL;
+        if (M <= 8) fz_sample_rows<ColT, 8>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
+        else if (M <= 16) fz_sample_rows<ColT, 16>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
+        else fz_sample_rows<ColT, 32>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
+      }
+      c.sync();  // edges written, known vertices in the table
+      // P4: endpoints enter the table; the smallest edge index wins a new vertex
+      for (int i = (int)cti; i < e_h; i += (int)CT)
+        auxl[ebase + i] = fz_upsert(tb, nb, (unsigned int)destl[ebase + i], kFzPending | (unsigned int)i);
+      c.sync();
+      // P5: first occurrences in edge order -> the next frontier, appended to the label's vertex array
+      const int n_new = (int)fz_ordered_scan(
+        c, e_h,
+        [&](long long i) -> unsigned int {
+          const unsigned int ax = (unsigned int)ld_relaxed_u64(&tb[auxl[ebase + i]]);
+          auxl[ebase + i]       = ax;
+          return ax == (kFzPending | (unsigned int)i) ? 1u : 0u;
+        },
+        [&](long long i) -> unsigned int { return auxl[ebase + i] == (kFzPending | (unsigned int)i) ? 1u : 0u; },
+        [&](long long i, unsigned int rank, unsigned int f) {
+          if (f) {
+            Fl[known + rank]  = (long long)destl[ebase + i];
+            rankl[ebase + i] = rank;
+          }
+        });
+      if (c.rank == 0 && tid < 32) {
+        unsigned long long rb = 0;
+        if (h + 1 < L) rb = fz_lookback(a.pub + (long long)(h + 1) * B, l, (unsigned long long)n_new);
+        if (tid == 0) {
+          sh.rowbase    = (long long)rb;
+          n_step[h + 1] = n_new;
+        }
+      }
+      c.sync();  // ranks visible
+      // P6: endpoints -> local ids
+      for (int i = (int)cti; i < e_h; i += (int)CT) {
+        const unsigned int ax = auxl[ebase + i];
+        mnrl[ebase + i]       = (ax & kFzPending) ? known + (int)rankl[ebase + (ax & ~kFzPending)] : (int)ax;
+      }
+      nbase  = known;
+      n_rows = n_new;
+      ebase += e_h;
+    }
+    // the next label's first barrier orders this label's last reads before its scratch is touched again (it is not:
+    // scratch is per label), and sh.* before it is rewritten
+  }
+}
+
+// ---- after the labels: offsets in the layout of multihop_finish -----------------------------------------------------
+// counts[0 .. B*L) edges of (label, hop); counts[B*L .. +B) vertices of label; counts[B*L+B .. +B) source rows of label;
+// base[t*B + l] local id of the first vertex label l discovered at step t
+__global__ void __launch_bounds__(256) fz_meta_kernel(int B, int L, const int* __restrict__ n_step, const int* __restrict__ e_hop,
+                                                      long long* __restrict__ counts, int* __restrict__ base)
+{
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < B; l += gridDim.x * blockDim.x) {
+    int acc = 0, rows = 0;
+    for (int t = 0; t <= L; t++) {
+      base[t * B + l] = acc;
+      acc += n_step[(long long)l * (L + 1) + t];
+      if (t == L - 1) rows = acc;
+    }
+    for (int h = 0; h < L; h++)
+      counts[(long long)l * L + h] = e_hop[(long long)l * L + h];
+    counts[(long long)B * L + l]     = acc;
+    counts[(long long)B * L + B + l] = rows;
+  }
+}
+
+// label-major scratch -> outputs: blockIdx.y = label
+template <typename OutT, bool CHUNKED>
+__global__ void __launch_bounds__(256) fz_emit_edges_kernel(int L, const long long* __restrict__ label_offsets, long long estride,
+                                                            const long long* __restrict__ lho, const int* __restrict__ maj,
+                                                            const int* __restrict__ mnr, const long long* __restrict__ gid,
+                                                            ChunkRef edge_id_ref, unsigned long long edge_id_off, bool has_edge_id,
+                                                            OutT* __restrict__ majors, OutT* __restrict__ minors,
+                                                            long long* __restrict__ edge_id_out)
+{
+  const int l        = blockIdx.y;
+  const long long p0 = lho[(long long)l * L], n = lho[(long long)(l + 1) * L] - p0;
+  const long long s0 = label_offsets[l] * estride;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (majors) majors[p0 + i] = (OutT)maj[s0 + i];
+    minors[p0 + i] = (OutT)mnr[s0 + i];
+    long long g    = gid[s0 + i];
+    if (has_edge_id) g = load_i64<CHUNKED>(edge_id_ref, edge_id_off + (unsigned long long)g);
+    edge_id_out[p0 + i] = g;
+  }
+}
+
+__global__ void __launch_bounds__(256) fz_emit_rows_kernel(int L, const long long* __restrict__ label_offsets, long long fstride,
+                                                           const long long* __restrict__ rmo, const long long* __restrict__ rbase,
+                                                           const long long* __restrict__ lho, const long long* __restrict__ F,
+                                                           const int* __restrict__ Orow, long long* __restrict__ map_out,
+                                                           long long* __restrict__ major_offsets)
+{
+  const int l        = blockIdx.y;
+  const long long m0 = rmo[l], n = rmo[l + 1] - m0;
+  const long long s0 = label_offsets[l] * fstride;
+  const long long r0 = major_offsets ? rbase[l] : 0, nr = major_offsets ? rbase[l + 1] - r0 : 0;
+  const long long e0 = lho[(long long)l * L];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    map_out[m0 + i] = F[s0 + i];
+    if (i < nr) major_offsets[r0 + i] = e0 + (long long)Orow[s0 + i];
+  }
+}
+
+}  // namespace wgb
+
+#else  // WGB_FZ_HOST_HALF
+// ---- host side ---------------------------------------------------------------------------------------------------
+namespace wgb {
+
+// WGB_MH_FUSED=0 sends every call down the kernel chain (A/B measurements, tests of both paths); read per call
+static bool fz_enabled()
+{
+  const char* e = getenv("WGB_MH_FUSED");
+  return !(e && atoi(e) == 0);
+}
+
+// first half of a call on the fused path; false: not eligible, the caller runs the kernel chain
+template <typename ColT>
+static bool multihop_begin_fused(MhCall& c)
+{
+  if (!fz_enabled() || c.hetero || c.temporal || c.weighted || c.chunked || c.T != 1) return false;
+  if (c.S <= 0 || c.B <= 0 || c.V >= 0xFFFFFFFFULL) return false;
+  long long estride = 0, prod = 1;
+  for (int h = 0; h < c.L; h++) {
+    if (c.fanout[h] < 1 || c.fanout[h] > 32) return false;
+    prod *= c.fanout[h];
+    if ((long long)c.S * prod >= (1LL << 28)) return false;  // the kernel chain reports the limit
+    estride += prod;
+  }
+  if ((long long)c.S / c.B > 65536) return false;  // a label is one cluster's work: keep it mini-batch sized
+  auto* sp        = c.sp;
+  const int B = c.B, L = c.L, S = c.S;
+  cudaStream_t st = c.stream;
+  const long long fstride = estride + 1;
+  const size_t nv = (size_t)S * (size_t)fstride, ne = (size_t)S * (size_t)estride;
+  const size_t slots = (size_t)(4 * (((long long)S * fstride + 1) / 2 + 16LL * B)) + 64;
+
+  FzArgs a;
+  memset(&a, 0, sizeof(a));
+  a.row_ptr = c.csr[0].row_ptr; a.row_ptr_off = c.csr[0].row_ptr_off;
+  a.col = c.csr[0].col; a.col_off = c.csr[0].col_off;
+  a.seeds = c.seeds; a.seed_is64 = c.seed_dtype == WHOLEMEMORY_DT_INT64 ? 1 : 0;
+  a.label_offsets = c.label_offsets;
+  a.B = B; a.L = L;
+  for (int h = 0; h < L; h++) a.fanout[h] = c.fanout[h];
+  a.fstride = fstride; a.estride = estride;
+  a.random_state = c.random_state;
+  a.F       = static_cast<long long*>(ensure(sp->fz[0], nv * sizeof(long long)));
+  a.Orow    = static_cast<int*>(ensure(sp->fz[1], nv * sizeof(int)));
+  a.maj     = static_cast<int*>(ensure(sp->fz[2], ne * sizeof(int)));
+  a.mnr     = static_cast<int*>(ensure(sp->fz[3], ne * sizeof(int)));
+  a.gid     = static_cast<long long*>(ensure(sp->fz[4], ne * sizeof(long long)));
+  a.dest    = ensure(sp->fz[5], ne * sizeof(ColT));
+  a.aux     = static_cast<unsigned int*>(ensure(sp->fz[6], ne * sizeof(unsigned int)));
+  a.rank_of = static_cast<unsigned int*>(ensure(sp->fz[7], ne * sizeof(unsigned int)));
+  a.table   = static_cast<unsigned long long*>(ensure(sp->fz[8], slots * sizeof(unsigned long long)));
+  a.seed_local = static_cast<int*>(ensure(sp->fz[9], (size_t)S * sizeof(int)));
+  int* counters = static_cast<int*>(ensure(sp->fz[10], sizeof(int) * (size_t)B * (size_t)(2 * L + 1)));
+  a.n_step = counters;
+  a.e_hop  = counters + (size_t)B * (size_t)(L + 1);
+  const size_t pub_bytes = sizeof(unsigned long long) * ((size_t)L * (size_t)B + 2);
+  unsigned long long* pub = static_cast<unsigned long long*>(ensure(sp->fz[11], pub_bytes));
+  WGB_CUDA_TRY(cudaMemsetAsync(pub, 0, pub_bytes, st));
+  a.pub      = pub;
+  a.ticket   = reinterpret_cast<unsigned int*>(pub + (size_t)L * (size_t)B);
+  a.bad_seed = reinterpret_cast<long long*>(pub + (size_t)L * (size_t)B + 1);
+  a.V        = c.V;
+  a.tab    = skip_table_device();
+
+  sp->pending.active   = false;
+  sp->pending.finished = false;
+  sp->marks_used       = 0;
+  mh_mark(sp, "start", st);
+
+  // one cluster per label in flight; CL CTAs per cluster so that the labels in flight cover the SMs
+  const int sms = num_sms();
+  int CL = 1;
+  while (CL < 8 && (long long)B * (CL * 2) <= sms) CL *= 2;
+  static int max_clusters[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // [ColT is 64-bit][log2 CL]
+  int& mc = max_clusters[sizeof(ColT) == 8 ? 1 : 0][CL == 1 ? 0 : CL == 2 ? 1 : CL == 4 ? 2 : 3];
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  attr[0].id               = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned int)CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.blockDim         = dim3(kFzThreads, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream           = st;
+  cfg.attrs            = attr;
+  cfg.numAttrs         = 1;
+  if (mc == 0) {
+    cfg.gridDim = dim3((unsigned int)(CL * std::max(1, sms / CL)), 1, 1);
+    int n       = 0;
+    WGB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, fz_label_kernel<ColT>, &cfg));
+    WGB_EXPECTS(n > 0, "the fused sampler kernel does not fit on this device");
+    mc = n;
+  }
+  const int clusters = std::min(B, mc);
+  cfg.gridDim        = dim3((unsigned int)(clusters * CL), 1, 1);
+  WGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, fz_label_kernel<ColT>, a));
+  WGB_CHECK_LAUNCH();
+  mh_mark(sp, "fused labels", st);
+
+  // ---- offsets, in the arrays multihop_finish reads ----------------------------------------------------------------
+  const long long n_groups = (long long)B * L, n_counts = n_groups + 2LL * B;
+  long long* counts = static_cast<long long*>(ensure(sp->counts, sizeof(long long) * (size_t)(n_counts + 1)));
+  long long* scans  = static_cast<long long*>(ensure(sp->small_i64, sizeof(long long) * (size_t)(n_counts + 8)));
+  long long* lho    = scans;
+  long long* rmo    = scans + n_groups + 1;
+  long long* rbase  = rmo + B + 1;
+  long long* totals = rbase + B + 1;
+  int* base = static_cast<int*>(ensure(sp->base, sizeof(int) * (size_t)(L + 1) * (size_t)B));
+  fz_meta_kernel<<<grid_over(B, sms), 256, 0, st>>>(B, L, a.n_step, a.e_hop, counts, base);
+  WGB_CHECK_LAUNCH();
+  MhScan3 sc;
+  sc.in[0] = counts;                sc.out[0] = lho;   sc.n[0] = n_groups;
+  sc.in[1] = counts + n_groups;     sc.out[1] = rmo;   sc.n[1] = B;
+  sc.in[2] = counts + n_groups + B; sc.out[2] = rbase; sc.n[2] = B;
+  sc.totals = totals;
+  mh_scan3_kernel<<<3, 1024, 0, st>>>(sc);
+  WGB_CHECK_LAUNCH();
+  WGB_CUDA_TRY(cudaMemcpyAsync(sp->h_totals, totals, 3 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+  WGB_CUDA_TRY(cudaMemcpyAsync(sp->h_totals + 3, a.bad_seed, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  WGB_CUDA_TRY(cudaEventRecord(sp->ready, st));
+  mh_mark(sp, "meta+scan3", st);
+
+  auto& pd = sp->pending;
+  pd.fused = true;
+  pd.fz    = a;
+  pd.B = B; pd.L = L; pd.flags = c.flags; pd.has_eid = c.csr[0].has_eid; pd.chunked = false;
+  pd.eid = c.csr[0].eid; pd.eid_off = c.csr[0].eid_off;
+  pd.hetero = false; pd.T = 1; pd.Vt = 1; pd.tbase = nullptr;
+  pd.S = S;
+  pd.lho = lho; pd.rmo = rmo; pd.rbase = rbase; pd.base = base;
+  pd.active = true;
+  return true;
+}
+
+// second half: wait for the sizes, allocate the outputs, copy the label segments
+static void multihop_finish_fused(wholegraph_multihop_sampler_* sp, const MhOutCtx& c)
+{
+  auto& pd        = sp->pending;
+  pd.active       = false;
+  pd.finished     = true;
+  const int sms   = num_sms();
+  const int B = pd.B, L = pd.L;
+  cudaStream_t st = c.stream;
+  const FzArgs& a = pd.fz;
+  WGB_CUDA_TRY(cudaEventSynchronize(sp->ready));
+  WGB_CUDA_TRY(cudaStreamWaitEvent(st, sp->ready, 0));
+  const long long n_edges = sp->h_totals[0], n_nodes = sp->h_totals[1], n_srcrows = sp->h_totals[2];
+  if (sp->h_totals[3] != 0) throw invalid_input("a seed vertex id is outside [0, number of vertices)");
+  const bool csr    = (pd.flags & WHOLEGRAPH_MULTIHOP_CSR) != 0;
+  const bool idx64  = (pd.flags & WHOLEGRAPH_MULTIHOP_INT64_IDS) != 0;
+  const wholememory_dtype_t idx_dt = idx64 ? WHOLEMEMORY_DT_INT64 : WHOLEMEMORY_DT_INT;
+  void* out_minors   = output_alloc(c.env, c.minors, n_edges, idx_dt);
+  void* out_majors   = (!csr && c.majors) ? output_alloc(c.env, c.majors, n_edges, idx_dt) : nullptr;
+  long long* out_eid = static_cast<long long*>(output_alloc(c.env, c.edge_id, n_edges, WHOLEMEMORY_DT_INT64));
+  long long* out_lho = static_cast<long long*>(output_alloc(c.env, c.lho, (long long)B * L + 1, WHOLEMEMORY_DT_INT64));
+  long long* out_map = static_cast<long long*>(output_alloc(c.env, c.map, n_nodes, WHOLEMEMORY_DT_INT64));
+  long long* out_rmo = static_cast<long long*>(output_alloc(c.env, c.rmo, B + 1, WHOLEMEMORY_DT_INT64));
+  long long* out_moff = nullptr;
+  if (csr) {
+    WGB_EXPECTS(c.major_offsets != nullptr, "CSR compression needs a major_offsets output context");
+    out_moff = static_cast<long long*>(output_alloc(c.env, c.major_offsets, n_srcrows + 1, WHOLEMEMORY_DT_INT64));
+  }
+  if (c.step_counts) {
+    int* out_sc = static_cast<int*>(output_alloc(c.env, c.step_counts, (long long)(L + 1) * B, WHOLEMEMORY_DT_INT));
+    WGB_CUDA_TRY(cudaMemcpyAsync(out_sc, pd.base, sizeof(int) * (size_t)(L + 1) * (size_t)B, cudaMemcpyDeviceToDevice, st));
+  }
+  WGB_CUDA_TRY(cudaMemcpyAsync(out_rmo, pd.rmo, sizeof(long long) * (size_t)(B + 1), cudaMemcpyDeviceToDevice, st));
+  if (!csr) {
+    WGB_CUDA_TRY(cudaMemcpyAsync(out_lho, pd.lho, sizeof(long long) * (size_t)((long long)B * L + 1), cudaMemcpyDeviceToDevice, st));
+  } else {
+    mh_csr_label_hop_kernel<<<grid_over((long long)B * L + 1, sms), 256, 0, st>>>(L, B, pd.base, pd.rbase, pd.lho, out_lho, out_moff);
+    WGB_CHECK_LAUNCH();
+  }
+  // grid: blockIdx.y = label, enough CTAs per label to cover its segment with ~4 items per thread
+  auto gx = [&](long long total) { return (unsigned int)std::max<long long>(1, std::min<long long>(64, (total / std::max(B, 1) + 1023) / 1024)); };
+  if (n_edges > 0) {
+    dim3 grid(gx(n_edges), (unsigned int)B);
+    if (idx64)
+      fz_emit_edges_kernel<long long, false><<<grid, 256, 0, st>>>(L, a.label_offsets, a.estride, pd.lho, a.maj, a.mnr, a.gid, pd.eid, pd.eid_off, pd.has_eid,
+                                                                   static_cast<long long*>(out_majors), static_cast<long long*>(out_minors), out_eid);
+    else
+      fz_emit_edges_kernel<int, false><<<grid, 256, 0, st>>>(L, a.label_offsets, a.estride, pd.lho, a.maj, a.mnr, a.gid, pd.eid, pd.eid_off, pd.has_eid,
+                                                             static_cast<int*>(out_majors), static_cast<int*>(out_minors), out_eid);
+    WGB_CHECK_LAUNCH();
+  }
+  if (n_nodes > 0) {
+    fz_emit_rows_kernel<<<dim3(gx(n_nodes), (unsigned int)B), 256, 0, st>>>(L, a.label_offsets, a.fstride, pd.rmo, pd.rbase, pd.lho, a.F, a.Orow, out_map, out_moff);
+    WGB_CHECK_LAUNCH();
+  }
+  mh_mark(sp, "emit", st);
+  mh_collect_marks(sp);
+}
+
+}  // namespace wgb
+
+#endif  // WGB_FZ_HOST_HALF
+#endif  // WGB_HOST_EMULATION

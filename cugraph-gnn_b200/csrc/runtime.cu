@@ -1335,8 +1335,42 @@ __global__ void hot_slot_kernel(const long long* __restrict__ idx, long long n, 
   }
 }
 
+// embeddings that currently hold a replica: scatters into their table drop it (a replica of rows that have changed would
+// serve stale rows silently)
+static std::mutex g_hot_mutex;
+static std::vector<wholememory_embedding_t> g_hot_embeddings;
+
+void hot_rows_invalidate_for_tensor(wholememory_tensor_t written)
+{
+  if (!written) return;
+  std::vector<wholememory_embedding_t> hit;
+  {
+    std::lock_guard<std::mutex> lock(g_hot_mutex);
+    if (g_hot_embeddings.empty()) return;
+    wholememory_tensor_t wroot = written->root ? written->root : written;
+    for (auto* e : g_hot_embeddings) {
+      wholememory_tensor_t eroot = e->tensor && e->tensor->root ? e->tensor->root : e->tensor;
+      if (eroot == wroot || (eroot && wroot && eroot->handle && eroot->handle == wroot->handle)) hit.push_back(e);
+    }
+  }
+  for (auto* e : hit) {
+    log_msg(LEVEL_WARN, "scatter into a table with %lld replicated hot rows: the replica on this GPU is dropped "
+            "(replicas on other GPUs are theirs to refresh: call set_hot_rows again on every rank)", e->hot_count);
+    cudaDeviceSynchronize();  // gathers that still read the replica finish first
+    embedding_drop_hot_rows(e);
+  }
+}
+
 void embedding_drop_hot_rows(wholememory_embedding_t e)
 {
+  {
+    std::lock_guard<std::mutex> lock(g_hot_mutex);
+    for (size_t i = 0; i < g_hot_embeddings.size(); i++)
+      if (g_hot_embeddings[i] == e) {
+        g_hot_embeddings.erase(g_hot_embeddings.begin() + i);
+        break;
+      }
+  }
   if (e->hot_slot_mem) cudaFree(e->hot_slot_mem);
   if (e->hot_rows_mem) cudaFree(e->hot_rows_mem);
   e->hot_slot_mem = e->hot_rows_mem = nullptr;
@@ -1388,6 +1422,10 @@ wholememory_error_code_t wholememory_embedding_set_hot_rows(wholememory_embeddin
     e->hot.rows         = static_cast<const char*>(e->hot_rows_mem);
     e->hot.stride_bytes = stride;
     e->hot_count        = n;
+    {
+      std::lock_guard<std::mutex> lock(g_hot_mutex);
+      g_hot_embeddings.push_back(e);
+    }
   });
 }
 

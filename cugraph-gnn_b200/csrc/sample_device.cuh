@@ -248,6 +248,83 @@ __device__ __forceinline__ int resolve_chain_group(int x, bool valid, int g, int
 // fan-out <= 32: G = 8/16/32 lanes per seed row.
 // RNG geometry of the reference for M <= 32: block = 32 threads, 1 draw per thread, thread j of seed
 // row b uses subsequence b*32 + j (func.cuh:412-447) -> lane g draws once from stream 32*b + g.
+//
+// One warp, 32 consecutive frontier rows (lane = row in phase 1, G lanes per row in phase 2).  Shared by the one-hop /
+// per-hop kernel below and by the fused per-label sampler (multihop_fused.cuh): `b_own` is the row's index in the
+// label-major concatenated frontier (it fixes the random stream, nothing else), `tag_own` what the sink records as the
+// edge's source row, `off_own` where the row's edges start in the sink's arrays.
+//   sink.ids(pos, tag, edge_position_in_csr)   and   sink.val(pos, neighbour)
+template <typename ColT, int G, bool CHUNKED, typename Sink>
+__device__ __forceinline__ void uniform_small_rows32(const ChunkRef& col, unsigned long long col_off, int M, unsigned long long seed,
+                                                     const Affine* __restrict__ tab, const Affine& lane_skip, int* Wg, int lane,
+                                                     long long b_own, int tag_own, long long start_own, int N_own, int off_own,
+                                                     Sink& sink)
+{
+  constexpr int GPW = 32 / G;
+  const int g = lane & (G - 1), sub = lane / G;
+  const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
+  Affine skip_own{1ULL, 0ULL};
+  if (N_own > M) skip_own = affine_skip_tab(tab, 32ULL * (unsigned long long)b_own);
+  // GPW rows per step.  The random `col` read of a step is its only long-latency operation; steps run in
+  // chunks of kChunk whose loads are all issued before the first dependent store, so a lane keeps kChunk DRAM
+  // reads in flight instead of one (the chain resolution in between is register/shuffle work only).
+  constexpr int kChunk = G < 8 ? G : 8;
+#pragma unroll 1
+  for (int step0 = 0; step0 < G; step0 += kChunk) {
+    ColT val[kChunk];
+    int pos[kChunk];
+    unsigned int wmask = 0;
+#pragma unroll
+    for (int k = 0; k < kChunk; k++) {
+      const int src   = (step0 + k) * GPW + sub;
+      const int N     = __shfl_sync(0xffffffffu, N_own, src);
+      const long long start = __shfl_sync(0xffffffffu, start_own, src);
+      const int off   = __shfl_sync(0xffffffffu, off_own, src);
+      const int tag   = __shfl_sync(0xffffffffu, tag_own, src);
+      Affine row_skip;
+      row_skip.g = __shfl_sync(0xffffffffu, skip_own.g, src);
+      row_skip.s = __shfl_sync(0xffffffffu, skip_own.s, src);
+      const long long b = __shfl_sync(0xffffffffu, b_own, src);
+      pos[k] = off + g;
+      if (N > 0) {
+        int a      = g;
+        bool write = g < N;
+        if (N > M) {
+          const bool valid = g < M;
+          Pcg rng;
+          rng.init_with_skip(seed, 32ULL * (unsigned long long)b + (unsigned long long)g, affine_then(row_skip, lane_skip));
+          int xr = rng.next_i32();
+          int x  = valid ? xr % (N - g) : -1;
+          a      = resolve_chain_group<G>(x, valid, g, lane, sub, gmask, N, M, Wg);
+          write  = valid;
+        }
+        if (write) {
+          val[k] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + a));
+          sink.ids(off + g, tag, start + a);
+          wmask |= 1u << k;
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int k = 0; k < kChunk; k++)
+      if ((wmask >> k) & 1u) sink.val(pos[k], val[k]);
+  }
+}
+
+template <typename ColT>
+struct OneHopSink {
+  ColT* __restrict__ out;
+  int* __restrict__ lid;
+  long long* __restrict__ gid;
+  __device__ __forceinline__ void ids(int pos, int tag, long long edge_pos) const
+  {
+    if (lid) lid[pos] = tag;
+    if (gid) gid[pos] = edge_pos;
+  }
+  __device__ __forceinline__ void val(int pos, ColT v) const { out[pos] = v; }
+};
+
 template <typename IdT, typename ColT, int G, bool CHUNKED>
 __global__ void __launch_bounds__(256) uniform_small_kernel(ChunkRef row_ptr, unsigned long long row_ptr_off,
                                                             ChunkRef col, unsigned long long col_off,
@@ -258,73 +335,27 @@ __global__ void __launch_bounds__(256) uniform_small_kernel(ChunkRef row_ptr, un
                                                             const int* __restrict__ n_dev = nullptr)
 {
   if (n_dev) n = *n_dev;
-  constexpr int GPW = 32 / G;
   __shared__ int W[8][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = lane & (G - 1), sub = lane / G;
-  const unsigned int gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
   const Affine lane_skip   = affine_skip_loop((unsigned long long)g);
   int* Wg                  = &W[wib][sub * G];
   const long long nwarps   = (long long)gridDim.x * 8;
+  OneHopSink<ColT> sink{out, lid, gid};
   for (long long batch = (long long)blockIdx.x * 8 + wib; batch * 32 < n; batch += nwarps) {
     // phase 1: one lane per seed row -- 32 independent row_ptr reads in flight per warp
     const long long b_own = batch * 32 + lane;
     long long start_own   = 0;
     int N_own = 0, off_own = 0;
-    Affine skip_own{1ULL, 0ULL};
     if (b_own < n) {
       unsigned long long node = (unsigned long long)centers[b_own];
       start_own     = load_i64<CHUNKED>(row_ptr, row_ptr_off + node);
       long long end = load_i64<CHUNKED>(row_ptr, row_ptr_off + node + 1);
       N_own         = (int)(end - start_own);
       off_own       = offsets[b_own];
-      if (N_own > M) skip_own = affine_skip_tab(tab, 32ULL * (unsigned long long)b_own);
     }
-    // phase 2: GPW rows per step.  The random `col` read of a step is its only long-latency operation; steps run in
-    // chunks of kChunk whose loads are all issued before the first dependent store, so a lane keeps kChunk DRAM
-    // reads in flight instead of one (the chain resolution in between is register/shuffle work only).
-    constexpr int kChunk = G < 8 ? G : 8;
-#pragma unroll 1
-    for (int step0 = 0; step0 < G; step0 += kChunk) {
-      ColT val[kChunk];
-      int pos[kChunk];
-      unsigned int wmask = 0;
-#pragma unroll
-      for (int k = 0; k < kChunk; k++) {
-        const int src   = (step0 + k) * GPW + sub;
-        const int N     = __shfl_sync(0xffffffffu, N_own, src);
-        const long long start = __shfl_sync(0xffffffffu, start_own, src);
-        const int off   = __shfl_sync(0xffffffffu, off_own, src);
-        Affine row_skip;
-        row_skip.g = __shfl_sync(0xffffffffu, skip_own.g, src);
-        row_skip.s = __shfl_sync(0xffffffffu, skip_own.s, src);
-        const long long b = batch * 32 + src;
-        pos[k] = off + g;
-        if (N > 0) {
-          int a      = g;
-          bool write = g < N;
-          if (N > M) {
-            const bool valid = g < M;
-            Pcg rng;
-            rng.init_with_skip(seed, 32ULL * (unsigned long long)b + (unsigned long long)g, affine_then(row_skip, lane_skip));
-            int xr = rng.next_i32();
-            int x  = valid ? xr % (N - g) : -1;
-            a      = resolve_chain_group<G>(x, valid, g, lane, sub, gmask, N, M, Wg);
-            write  = valid;
-          }
-          if (write) {
-            val[k] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + a));
-            if (lid) lid[off + g] = (int)b;
-            if (gid) gid[off + g] = start + a;
-            wmask |= 1u << k;
-          }
-        }
-        __syncwarp();
-      }
-#pragma unroll
-      for (int k = 0; k < kChunk; k++)
-        if ((wmask >> k) & 1u) out[pos[k]] = val[k];
-    }
+    // phase 2: G lanes per row
+    uniform_small_rows32<ColT, G, CHUNKED>(col, col_off, M, seed, tab, lane_skip, Wg, lane, b_own, (int)b_own, start_own, N_own, off_own, sink);
   }
 }
 

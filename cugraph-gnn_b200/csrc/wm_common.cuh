@@ -197,6 +197,7 @@ void comm_barrier(wholememory_comm_t c);
 void comm_allgather(wholememory_comm_t c, const void* in, void* out, size_t bytes);  // bytes <= 256 per rank
 void embedding_release_training_state(wholememory_embedding_t e);
 void embedding_drop_hot_rows(wholememory_embedding_t e);
+void hot_rows_invalidate_for_tensor(wholememory_tensor_t written);  // scatter / file load into a table that has a replica
 // gather / scatter of rows; `hot` (may be null) is consulted by same-dtype gathers only
 wholememory_error_code_t rows_op(wholememory_tensor_t wm_tensor, wholememory_tensor_t indices_tensor, wholememory_tensor_t dense_tensor,
                                  void* stream, int sms, bool scatter, const wgb_hot_rows* hot);

@@ -172,7 +172,10 @@ class BaseDistributedSampler:
                 raise ValueError("input_time must have one entry per seed edge")
         input_id = torch.arange(n, dtype=torch.int64) if input_id is None else torch.as_tensor(input_id).cpu()
         label = None if input_label is None else torch.as_tensor(input_label)
-        batches_per_call = max(1, self._local_seeds_per_call // batch_size)
+        # every seed edge contributes TWO seed vertices to the native call: a call group holds local_seeds_per_call // 2
+        # edges, so that its vertex count (and with it the per-hop edge bound of the native sampler) stays what the
+        # node path gets
+        batches_per_call = max(1, (self._local_seeds_per_call // 2) // batch_size)
         per_call = batches_per_call * batch_size
         local_num_batches = int(ceil(n / batch_size))
         batch_id_start, equal = self.get_start_batch_offset(local_num_batches, assume_equal_input_size)

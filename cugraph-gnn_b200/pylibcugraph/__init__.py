@@ -176,32 +176,74 @@ class MGGraph(SGGraph):
                  size=None, edge_start_time_array=None, **kwargs):
         import torch.distributed as dist
 
-        def gather(a, dtype=None):
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        world = dist.get_world_size() if multi else 1
+        counts = None  # edges per rank, agreed on once: every per-edge array is laid out with the same offsets
+
+        def local(a, dtype=None):
             if a is None:
                 return None
             if isinstance(a, (list, tuple)):
                 a = torch.cat([_as_cuda(x, dtype) for x in a]) if len(a) else torch.empty(0, dtype=dtype)
-            t = _as_cuda(a, dtype)
-            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return _as_cuda(a, dtype)
+
+        def gather(a, dtype=None, per_edge=True):
+            """all ranks' parts, concatenated in rank order, received straight into ONE buffer of the exact total size
+            (no padding to the largest partition, no list of W padded copies, no torch.cat)"""
+            nonlocal counts
+            t = local(a, dtype)
+            if t is None or not multi:
                 return t
-            n = torch.tensor([t.numel()], device=t.device, dtype=torch.int64)
-            sizes = [torch.zeros_like(n) for _ in range(dist.get_world_size())]
-            dist.all_gather(sizes, n)
-            mx = int(max(int(s) for s in sizes))
-            pad = torch.zeros(mx, dtype=t.dtype, device=t.device)
-            pad[: t.numel()] = t
-            out = [torch.empty_like(pad) for _ in range(dist.get_world_size())]
-            dist.all_gather(out, pad)
-            return torch.cat([o[: int(s)] for o, s in zip(out, sizes)])
+            if per_edge and counts is not None:
+                sizes = counts
+            else:
+                n = torch.tensor([t.numel()], device=t.device, dtype=torch.int64)
+                every = torch.empty(world, device=t.device, dtype=torch.int64)
+                dist.all_gather_into_tensor(every, n)
+                sizes = [int(x) for x in every.tolist()]
+            if per_edge and counts is None:
+                counts = sizes
+                self._check_replicated_fit(sum(sizes), t.device, [weight_array, edge_id_array, edge_type_array, edge_start_time_array])
+            if t.numel() != sizes[dist.get_rank()]:
+                raise ValueError("MGGraph: every per-edge array of a rank must have as many entries as its src_array")
+            out = torch.empty(sum(sizes), dtype=t.dtype, device=t.device)
+            off = 0
+            for r, n_r in enumerate(sizes):
+                part = out[off:off + n_r]
+                if r == dist.get_rank():
+                    part.copy_(t)
+                if n_r:
+                    dist.broadcast(part, src=r)
+                off += n_r
+            return out
 
         nv = kwargs.pop("num_vertices", None)
         if nv is None and vertices_array is not None:
-            v = gather(vertices_array, torch.int64)
+            v = gather(vertices_array, torch.int64, per_edge=False)
             nv = int(v.max()) + 1 if v.numel() else 0
         super().__init__(resource_handle, graph_properties, gather(src_array, torch.int64), gather(dst_array, torch.int64),
                          weight_array=gather(weight_array), edge_id_array=gather(edge_id_array, torch.int64),
                          edge_type_array=gather(edge_type_array, torch.int32), num_vertices=nv,
                          edge_start_time_array=gather(edge_start_time_array, torch.int64), **kwargs)
+
+
+def _mg_check_replicated_fit(self, total_edges: int, device, optional_arrays):
+    """The CSR of an MGGraph is REPLICATED on every GPU (limits): refuse up front, with the numbers, a
+    graph whose replica cannot fit, instead of failing with an opaque CUDA out-of-memory half way through the build."""
+    per_edge = 16 + sum(8 for a in optional_arrays if a is not None)  # src + dst (+ weight / id / type / time, <= 8 B each)
+    need = int(total_edges) * (per_edge + 24)  # + sort keys, permutation and the CSR column array while building
+    try:
+        free, _total = torch.cuda.mem_get_info(device)
+    except Exception:
+        return
+    if need > free:
+        raise MemoryError(
+            "MGGraph replicates the CSR on every GPU: %d edges need about %.1f GB per GPU to build, %.1f GB are free. "
+            "Stripe the graph with WholeMemory tensors instead (pylibwholegraph.torch.MultiHopSampler samples a CHUNKED "
+            "row_ptr / col_idx pair by in-kernel P2P), see INTEGRATION.md." % (total_edges, need / 1e9, free / 1e9))
+
+
+MGGraph._check_replicated_fit = _mg_check_replicated_fit
 
 
 def _disjoint_filter(out, num_hops: int):

@@ -421,6 +421,16 @@ int wgo_num_threads()
 #endif
 }
 
+// benchmarks size the OpenMP pool themselves: torchrun exports OMP_NUM_THREADS=1 into every rank's environment
+void wgo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 // ---- RNG twins -------------------------------------------------------------------------------
 // published pcg32 (initstate, initseq) stream, for the known-answer pin
 void wgo_pcg32_reference_stream(uint64_t initstate, uint64_t initseq, uint32_t* out, int n)

@@ -60,6 +60,12 @@ def num_threads():
     return int(lib().wgo_num_threads())
 
 
+def set_num_threads(n):
+    """Size the OpenMP pool explicitly (torchrun exports OMP_NUM_THREADS=1 into every rank)."""
+    lib().wgo_set_num_threads(ctypes.c_int(int(n)))
+    return num_threads()
+
+
 def pcg32_reference_stream(initstate, initseq, n):
     out = np.empty(n, dtype=np.uint32)
     lib().wgo_pcg32_reference_stream(ctypes.c_uint64(initstate), ctypes.c_uint64(initseq), _p(out), ctypes.c_int(n))

@@ -1,4 +1,5 @@
-"""Short driver for ncu: builds the C2 workload and runs a few sampler + gather steps (no timing)."""
+"""Short driver for ncu: builds the bench workload (argv[3]: c4 default | c2 | headline) and runs a few sampler + gather
+steps (no timing).  Same call shape as bench.py (int64 ids)."""
 import os
 import sys
 
@@ -11,6 +12,10 @@ import pylibwholegraph.torch as wgth
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 labels = int(sys.argv[2]) if len(sys.argv) > 2 else bench.LABELS_PER_STEP
+workload = sys.argv[3] if len(sys.argv) > 3 else "c4"
+if bench.WORKLOADS[workload] is not None:
+    for k, v in bench.WORKLOADS[workload].items():
+        setattr(bench, k, v)
 torch.cuda.set_device(0)
 dev = torch.device("cuda", 0)
 wgth.init(0, 1, 0, 1)
@@ -27,7 +32,7 @@ lo = (torch.arange(labels + 1, dtype=torch.int64) * bench.BATCH).to(dev)
 seeds = [s.to(dev) for s in bench.seed_sets(torch, steps, labels)]
 torch.cuda.synchronize()
 for k in range(steps):
-    res = sampler.sample(wm_rp, wm_col, seeds[k], lo, bench.FANOUT, 62 + k)
+    res = sampler.sample(wm_rp, wm_col, seeds[k], lo, bench.FANOUT, 62 + k, int64_ids=True)
     x = emb.gather(res["renumber_map"])
 torch.cuda.synchronize()
 print("edges", res["minors"].numel(), "nodes", res["renumber_map"].numel())

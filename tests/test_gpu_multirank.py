@@ -146,13 +146,19 @@ def _hot_rows_worker(rank, world, uid):
     got16 = emb.gather(idx.cuda(), force_dtype=torch.float16).cpu()  # converting path ignores the replica, same values
     assert torch.equal(got16[keep], exp[keep].half())
     comm.barrier()
-    # snapshot semantics: a row changed after set_hot_rows is still served from the replica until it is rebuilt
+    # a scatter into the table drops the replica of the rank that scatters (it would serve stale rows otherwise); replicas
+    # on other ranks are snapshots until their owners rebuild them
     if rank == 0:
         emb.get_embedding_tensor().scatter(torch.full((1, dim), -7.0).cuda(), hot[:1].cuda())
         torch.cuda.synchronize()
+        assert emb.hot_row_count() == 0
     comm.barrier()
     one = emb.gather(hot[:1].cuda()).cpu()
-    assert torch.equal(one, ((hot[:1, None] * 5 + torch.arange(dim)[None, :]) % 8191).float())
+    if rank == 0:
+        assert float(one[0, 0]) == -7.0
+    else:
+        assert emb.hot_row_count() == 4000
+        assert torch.equal(one, ((hot[:1, None] * 5 + torch.arange(dim)[None, :]) % 8191).float())
     emb.set_hot_rows(hot.cuda())
     assert float(emb.gather(hot[:1].cuda())[0, 0]) == -7.0
     emb.set_hot_rows(None)
