@@ -29,7 +29,7 @@ FLAGS = [
     "-I", os.path.join(ROOT, "include"),
     "-I", CSRC,
     "-DWGB_BUILDING_LIB",
-]
+] + os.environ.get("WGB_EXTRA_NVCC_FLAGS", "").split()  # tuning experiments: e.g. -DWGB_FZ_THREADS=1024 -DWGB_FZ_ILP=1
 
 
 def _stale(target, deps):

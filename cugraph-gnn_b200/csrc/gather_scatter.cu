@@ -130,6 +130,143 @@ __global__ void __launch_bounds__(kBlock) rows_copy_kernel(ChunkRef table,
   }
 }
 
+// ---- same-dtype gather as bulk-async copies (TMA) ---------------------------------------------------------
+// The register path above needs every thread slot and every register of an SM to keep ~64 KB of loads in flight
+// (256 threads x 8 CTAs x 4 x 16 B); while it runs, nothing else fits on the SM, so the sampler of the next call group
+// cannot execute underneath the gather although the two bind different resources (measured: step = sum, not max).
+// Here the bytes in flight live in SHARED memory, moved by the copy engine: a warp owns a ring of `stages` tiles of 32
+// rows; lane j issues ONE cp.async.bulk (global -> shared, completion counted on the tile's mbarrier) for row j of a
+// tile, and a whole tile leaves with ONE bulk store (shared -> global) because gathered rows are consecutive in the
+// output.  The data never passes through registers.  A CTA is 2-8 warps with a handful of registers each: it co-resides
+// with the fused sampler CTA (multihop_fused.cuh: 30 warps, no shared memory to speak of) on every SM.
+// Rows whose index is negative are skipped (output untouched): tiles that contain one, or the ragged last tile, leave
+// row by row.  CHUNKED: the source of a row is the owning GPU's memory (peer-mapped, the copy crosses NVLink).
+constexpr int kBulkRows     = 32;
+constexpr int kBulkMaxWarps = 4;  // 128 threads x <= 64 registers: fits beside a 28-warp sampler CTA in the register file
+
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+template <typename IdxT, bool CHUNKED, bool HOT>
+__global__ void __launch_bounds__(kBulkMaxWarps * 32) rows_bulk_gather_kernel(ChunkRef table, unsigned long long table_off_bytes,
+                                                               unsigned long long row_stride_bytes, const IdxT* __restrict__ idx,
+                                                               long long n_rows, unsigned int row_bytes, char* __restrict__ dense,
+                                                               unsigned long long dense_stride_bytes, int stages, wgb_hot_rows hot,
+                                                               unsigned int* __restrict__ ticket)
+{
+  extern __shared__ __align__(128) unsigned char bulk_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  const unsigned int tile_bytes = kBulkRows * row_bytes;
+  unsigned char* ring           = bulk_smem + (size_t)wib * stages * tile_bytes;
+  unsigned long long* bars      = reinterpret_cast<unsigned long long*>(bulk_smem + (size_t)warps * stages * tile_bytes) + wib * stages;
+  if (lane == 0) {
+    for (int s = 0; s < stages; s++)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[s])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  const long long n_tiles = (n_rows + kBulkRows - 1) / kBulkRows;
+  const long long gw = (long long)blockIdx.x * warps + wib, nw = (long long)gridDim.x * warps;
+  // gathered rows are touched once: evict-first in L2, so that the stream does not push out the sampler's tables
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+
+  auto source_of = [&](long long i, bool& ok) -> const char* {
+    long long r = i < n_rows ? (long long)idx[i] : -1;
+    ok          = r >= 0;
+    if (!ok) return nullptr;
+    if (HOT) {
+      const int hs = __ldg(hot.slot + r);
+      if (hs >= 0) return hot.rows + (unsigned long long)hs * hot.stride_bytes;
+    }
+    return table.at<CHUNKED>(table_off_bytes + (unsigned long long)r * row_stride_bytes);
+  };
+  auto issue_loads = [&](long long tile, int s) {
+    bool ok;
+    const char* src         = source_of(tile * kBulkRows + lane, ok);
+    const unsigned int mask = __ballot_sync(0xffffffffu, ok);
+    const unsigned int bar  = smem_u32(&bars[s]);
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(__popc(mask) * row_bytes) : "memory");
+    __syncwarp();
+    if (ok)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(ring + (size_t)s * tile_bytes + (size_t)lane * row_bytes)),
+                   "l"(src), "r"(row_bytes), "r"(bar), "l"(pol)
+                   : "memory");
+  };
+
+  // Tiles are handed out by ticket, one per request: the grid may hold more CTAs than are resident at once (two per SM
+  // when the gather has the SM to itself, one when a sampler CTA lives there) and a CTA that starts late simply finds
+  // fewer tiles left.
+  auto next_tile = [&]() -> long long {
+    unsigned int t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1u);
+    return (long long)__shfl_sync(0xffffffffu, t, 0);
+  };
+  // the ring remembers which tile sits in which stage (registers: stages <= 8, indexed by unrolled compare chains)
+  long long in_stage[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++)
+    in_stage[k] = n_tiles;
+  auto set_stage = [&](int s, long long t) {
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k == s) in_stage[k] = t;
+  };
+  auto get_stage = [&](int s) -> long long {
+    long long t = n_tiles;
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+      if (k == s) t = in_stage[k];
+    return t;
+  };
+  // prologue: stages - 1 tiles in flight
+  for (int k = 0; k < stages - 1; k++) {
+    const long long t = next_tile();
+    set_stage(k, t);
+    if (t < n_tiles) issue_loads(t, k);
+  }
+  int s = 0;
+  unsigned int parity = 0;
+  while (true) {
+    const long long tile = get_stage(s);
+    if (tile >= n_tiles) break;  // tickets are monotonic: every later stage holds nothing either
+    // the tile's rows have landed
+    const unsigned int bar = smem_u32(&bars[s]);
+    asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+    const long long i       = tile * kBulkRows + lane;
+    const bool ok           = i < n_rows && (long long)idx[i] >= 0;
+    const unsigned int mask = __ballot_sync(0xffffffffu, ok);
+    const unsigned char* st = ring + (size_t)s * tile_bytes;
+    if (mask == 0xffffffffu && dense_stride_bytes == row_bytes) {
+      if (lane == 0)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dense + (unsigned long long)tile * kBulkRows * dense_stride_bytes),
+                     "r"(smem_u32(st)), "r"(tile_bytes), "l"(pol)
+                     : "memory");
+    } else if (ok) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dense + (unsigned long long)i * dense_stride_bytes),
+                   "r"(smem_u32(st + (size_t)lane * row_bytes)), "r"(row_bytes), "l"(pol)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    // refill the stage the PREVIOUS tile left from: its store must have finished reading shared memory
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    const int sp          = s == 0 ? stages - 1 : s - 1;
+    const long long ahead = next_tile();
+    set_stage(sp, ahead);
+    if (ahead < n_tiles) issue_loads(ahead, sp);
+    if (++s == stages) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ---- converting path -----------------------------------------------------------------------------
 // element conversion as the reference does it (gather_scatter_func.cuh:150-197): half / bf16 go
 // through float, everything else is a static_cast.
@@ -250,9 +387,104 @@ static void launch_copy(const RowsOpArgs& a, int64_t row0, int64_t rows, unsigne
   WGB_CHECK_LAUNCH();
 }
 
+// Which same-dtype gathers go through the copy engine.  Measured on C4 (profiles/r2k_*.json, one GPU): alone the bulk kernel
+// is the faster one (0.335 ms against 0.382 for 2.1 M rows of 512 B: 1.0 against 0.88 of the HBM peak), but a loader runs the
+// gather of call group k beside the sampler of call group k+1, and there the register kernel is the better neighbour (step
+// 0.642 ms against 0.68-0.77): its CTAs only fit where the sampler leaves registers free, so it fills the gaps of the
+// sampler's stream instead of taking HBM bandwidth away from a latency-bound kernel.  Default: bulk copies for tables
+// striped over several GPUs (the copy engine keeps more NVLink reads in flight per SM than 4 x 16 B per thread), the
+// register kernel for local tables.  WGB_GATHER_BULK=1 / 0 forces one path for every call; read per call.
+static bool bulk_enabled(int world)
+{
+  const char* e = getenv("WGB_GATHER_BULK");
+  if (e && *e) return atoi(e) != 0;
+  return world > 1;
+}
+
+// Shared memory of the tile rings per CTA: 96 KB (2 warps x 3 tiles of 16 KB at 512-byte rows).  An SM that runs nothing
+// else takes two such CTAs (128 KB of row loads in flight); an SM that runs a sampler CTA takes one -- the L1 / shared
+// split of an SM cannot change while CTAs are resident, so the gather CTA only fits because the sampler kernel asks for a
+// 132 KB carve-out (WGB_MH_CARVEOUT in multihop_fused.cuh).  WGB_GATHER_BULK_KB overrides the ring size.
+static size_t bulk_smem_budget()
+{
+  if (const char* e = getenv("WGB_GATHER_BULK_KB"))
+    if (atoi(e) >= 16 && atoi(e) <= 200) return (size_t)atoi(e) * 1024;
+  return 96 * 1024;
+}
+constexpr long long kBulkMinRows = 4096;
+
+// tile tickets of the launches in flight: a small ring of device counters, one per launch, zeroed on the launch's stream
+static unsigned int* bulk_ticket_slot(cudaStream_t st)
+{
+  constexpr int kSlots = 256;
+  static thread_local unsigned int* slots[kMaxWorld * 2] = {};
+  static thread_local unsigned int next[kMaxWorld * 2]  = {};
+  int dev = 0;
+  WGB_CUDA_TRY(cudaGetDevice(&dev));
+  WGB_EXPECTS(dev < kMaxWorld * 2, "device ordinal out of range");
+  if (!slots[dev]) WGB_CUDA_TRY(cudaMalloc(&slots[dev], kSlots * sizeof(unsigned int)));
+  unsigned int* p = slots[dev] + (next[dev]++ % kSlots);
+  WGB_CUDA_TRY(cudaMemsetAsync(p, 0, sizeof(unsigned int), st));
+  return p;
+}
+
+// same-dtype gather through the copy engine when shapes allow it (everything 16-byte aligned, a tile ring fits)
+template <typename IdxT>
+static bool try_bulk_gather(const RowsOpArgs& a)
+{
+  if (!bulk_enabled(a.table.world) || a.n < kBulkMinRows) return false;
+  const size_t elt                   = dtype_size(a.table_desc.dtype);
+  const unsigned long long row_bytes = (unsigned long long)a.table_desc.sizes[1] * elt;
+  const unsigned long long tstride   = (unsigned long long)a.table_desc.stride * elt;
+  const unsigned long long toff      = (unsigned long long)a.table_desc.storage_offset * elt;
+  const unsigned long long dstride   = (unsigned long long)a.dense_desc.stride * elt;
+  char* dense                        = static_cast<char*>(a.dense) + (unsigned long long)a.dense_desc.storage_offset * elt;
+  unsigned long long align_or        = row_bytes | tstride | toff | dstride | reinterpret_cast<unsigned long long>(dense);
+  for (int r = 0; r < a.table.world; r++)
+    align_or |= reinterpret_cast<unsigned long long>(a.table.base[r]) | (r > 0 ? a.table.start[r] : 0ULL);
+  const bool hot = a.hot.slot != nullptr && a.table.world > 1;
+  if (hot) align_or |= a.hot.stride_bytes | reinterpret_cast<unsigned long long>(a.hot.rows);
+  if (align_or % 16 != 0 || row_bytes == 0) return false;
+  const size_t tile_bytes = (size_t)kBulkRows * row_bytes;
+  const size_t kBulkSmemBudget = bulk_smem_budget();
+  // bytes in flight per SM = warps x (stages - 1) x tile: deep rings on few warps (the copy engine does the work)
+  if (kBulkSmemBudget / tile_bytes < 2) return false;  // rows above 2 KB: the register path
+  const int warps  = (int)std::max<size_t>(1, std::min<size_t>(kBulkMaxWarps, kBulkSmemBudget / (3 * tile_bytes)));
+  const int stages = (int)std::min<size_t>(8, kBulkSmemBudget / ((size_t)warps * tile_bytes));  // >= 2
+  const size_t smem = (size_t)warps * stages * tile_bytes + (size_t)warps * stages * sizeof(unsigned long long);
+  const int sms     = num_sms();
+  const long long tiles = (a.n + kBulkRows - 1) / kBulkRows;
+  // as many CTAs as fit an SM that has nothing else on it (at most 2): tiles are taken by ticket, so CTAs that only start
+  // when the sampler kernel leaves cost nothing
+  const int per_sm  = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / (smem + 1024)));
+  int grid          = (int)std::min<long long>((tiles + warps - 1) / warps, (long long)(a.sms > 0 ? std::min(a.sms, sms) : sms) * per_sm);
+  unsigned int* ticket = bulk_ticket_slot(a.stream);
+  auto launch = [&](auto kernel) {
+    static thread_local const void* configured[8] = {};
+    bool known = false;
+    for (auto* k : configured) known = known || k == reinterpret_cast<const void*>(kernel);
+    if (!known) {
+      WGB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 201 * 1024));
+      for (auto& k : configured)
+        if (!k) {
+          k = reinterpret_cast<const void*>(kernel);
+          break;
+        }
+    }
+    kernel<<<grid, warps * 32, smem, a.stream>>>(a.table, toff, tstride, static_cast<const IdxT*>(a.idx), (long long)a.n, (unsigned int)row_bytes, dense,
+                                                 dstride, stages, a.hot, ticket);
+    WGB_CHECK_LAUNCH();
+  };
+  if (hot) launch(rows_bulk_gather_kernel<IdxT, true, true>);
+  else if (a.table.world > 1) launch(rows_bulk_gather_kernel<IdxT, true, false>);
+  else launch(rows_bulk_gather_kernel<IdxT, false, false>);
+  return true;
+}
+
 template <typename IdxT, bool SCATTER>
 static void run_copy(const RowsOpArgs& a)
 {
+  if (!SCATTER && try_bulk_gather<IdxT>(a)) return;
   size_t elt = dtype_size(a.table_desc.dtype);
   unsigned long long row_bytes = (unsigned long long)a.table_desc.sizes[1] * elt;
   unsigned long long dense_addr = reinterpret_cast<unsigned long long>(a.dense) + (unsigned long long)a.dense_desc.storage_offset * elt;

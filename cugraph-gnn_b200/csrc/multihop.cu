@@ -872,7 +872,10 @@ struct wholegraph_multihop_sampler_ {
   // temporal calls only
   Buf ftime[wgb::kMaxHops + 1], eligible[wgb::kMaxHops], clipped, tdesc_dev;
   // fused per-label path (multihop_fused.cuh): label-major scratch
-  Buf fz[12];
+  Buf fz[13];
+  double fz_phase_ns[32] = {};  // WGB_MH_TIMING: in-kernel phase clock of the fused path
+  double fz_span_ns = 0;
+  long long fz_phase_labels = 0, fz_calls = 0;
   wgb::MhTemporalDesc tdesc_host;
   wgb::MhHeteroDesc desc_host;
   long long* h_totals = nullptr;  // pinned
@@ -1682,6 +1685,9 @@ wholememory_error_code_t wholegraph_destroy_multihop_sampler(wholegraph_multihop
   if (s->h_totals) cudaFreeHost(s->h_totals);
   if (s->ready) cudaEventDestroy(s->ready);
   wgb::mh_print_marks(s);
+#ifndef WGB_HOST_EMULATION
+  wgb::fz_print_phases(s);
+#endif
   for (auto& m : s->marks)
     cudaEventDestroy(m.second);
   cudaGetLastError();

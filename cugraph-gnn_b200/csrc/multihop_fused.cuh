@@ -32,7 +32,14 @@ namespace wgb {
 
 namespace cg = cooperative_groups;
 
-constexpr int kFzThreads            = 1024;
+#ifndef WGB_FZ_THREADS
+#define WGB_FZ_THREADS 896
+#endif
+#ifndef WGB_FZ_ILP
+#define WGB_FZ_ILP 1
+#endif
+constexpr int kFzThreads            = WGB_FZ_THREADS;  // 28 warps x 64 registers: leaves 8 K registers of the SM, i.e. one 256-thread CTA
+                                                        // of the feature gather of the previous call group can sit beside it
 constexpr unsigned int kFzPending   = 0x80000000u;
 constexpr unsigned long long kFzEmpty = ~0ULL;
 constexpr unsigned long long kFzFlagAgg = 1ULL << 62, kFzFlagPrefix = 2ULL << 62, kFzValMask = (1ULL << 62) - 1;
@@ -64,6 +71,7 @@ struct FzArgs {
   unsigned int* ticket;
   long long* bad_seed;   // set when a seed is outside [0, V): the call fails at _finish
   unsigned long long V;
+  long long* dbg;        // WGB_MH_TIMING: [B][kFzDbgSlots] global-timer stamps of the label's phases (else null)
   const Affine* tab;
 };
 
@@ -81,20 +89,38 @@ __device__ __forceinline__ unsigned int fz_home(unsigned int v, unsigned int nb)
   return (unsigned int)(((unsigned long long)h * nb) >> 32);
 }
 
-// claim-or-find `v` in a table of nb buckets; the slot's aux after this thread's visit is at most `mine`
-__device__ __forceinline__ unsigned int fz_upsert(unsigned long long* __restrict__ tbl, unsigned int nb, unsigned int v, unsigned int mine)
+struct FzProbe {
+  unsigned long long w[4];  // the key's home bucket as it was when the probe was issued
+  unsigned int v;
+};
+
+__device__ __forceinline__ void fz_load_bucket(const unsigned long long* __restrict__ tbl, unsigned int b, unsigned long long (&w)[4])
 {
-  unsigned int b = fz_home(v, nb);
+  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+               : "l"(tbl + 4ULL * b)
+               : "memory");
+}
+
+__device__ __forceinline__ FzProbe fz_probe(const unsigned long long* __restrict__ tbl, unsigned int nb, unsigned int v)
+{
+  FzProbe p;
+  p.v = v;
+  fz_load_bucket(tbl, fz_home(v, nb), p.w);
+  return p;
+}
+
+// claim-or-find `p.v` in a table of nb buckets, starting from its already loaded home bucket; the slot's aux after this
+// thread's visit is at most `mine`.  Returns the slot.
+__device__ __forceinline__ unsigned int fz_upsert(unsigned long long* __restrict__ tbl, unsigned int nb, FzProbe p, unsigned int mine)
+{
+  const unsigned int v = p.v;
+  unsigned int b       = fz_home(v, nb);
   const unsigned long long fresh = ((unsigned long long)v << 32) | mine;
   while (true) {
-    unsigned long long w[4];
-    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];"
-                 : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
-                 : "l"(tbl + 4ULL * b)
-                 : "memory");
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      unsigned long long cur = w[j];
+      unsigned long long cur = p.w[j];
       if (cur == kFzEmpty) {
         cur = atomicCAS(&tbl[4ULL * b + j], kFzEmpty, fresh);
         if (cur == kFzEmpty) return 4u * b + j;
@@ -106,6 +132,7 @@ __device__ __forceinline__ unsigned int fz_upsert(unsigned long long* __restrict
       }
     }
     b = b + 1 == nb ? 0u : b + 1;
+    fz_load_bucket(tbl, b, p.w);
   }
 }
 
@@ -117,59 +144,21 @@ struct FzShared {
   int W[kFzThreads / 32][32];
 };
 
-// exclusive scan of one value per thread over the CTA; total in every thread
-__device__ __forceinline__ unsigned int fz_block_scan(unsigned int v, unsigned int* s_warp, unsigned int& total)
-{
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  unsigned int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned int y = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += y;
-  }
-  if (lane == 31) s_warp[wid] = inc;
-  __syncthreads();
-  if (wid == 0) {
-    unsigned int w = lane < kFzThreads / 32 ? s_warp[lane] : 0u;
-    unsigned int wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned int y = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += y;
-    }
-    s_warp[lane] = wi - w;
-    if (lane == 31) s_warp[32] = wi;
-  }
-  __syncthreads();
-  const unsigned int r = s_warp[wid] + inc - v;
-  total                = s_warp[32];
-  __syncthreads();
-  return r;
-}
+constexpr int kFzDbgSlots = 32;
+constexpr int kFzIlp = WGB_FZ_ILP;  // items a thread keeps in flight per stage of a latency-bound loop
 
 struct FzCluster {
   FzShared* sh;
   unsigned int rank, size;
   unsigned int xround;
 
-  // every thread contributes `mine`; returns the sum over the CTAs before this one, `total` over all.  One cluster barrier.
+  // `mine` = this CTA's partial sum (same value in every thread); returns the sum over the CTAs before this one, `total`
+  // over all.  One cluster barrier.
   __device__ __forceinline__ unsigned long long exchange(unsigned long long mine, unsigned long long& total)
   {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-      mine += __shfl_xor_sync(0xffffffffu, mine, o);
-    __shared__ unsigned long long s_part[kFzThreads / 32];
-    if (lane == 0) s_part[wid] = mine;
-    __syncthreads();
     const unsigned int par = xround & 1u;
     xround++;
-    if (threadIdx.x == 0) {
-      unsigned long long t = 0;
-      for (int w = 0; w < kFzThreads / 32; w++)
-        t += s_part[w];
-      sh->xchg[par][0] = t;
-    }
+    if (threadIdx.x == 0) sh->xchg[par][0] = mine;
     cg::this_cluster().sync();
     unsigned long long before = 0;
     total                     = 0;
@@ -183,31 +172,93 @@ struct FzCluster {
   __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
 };
 
-// Ordered exclusive scan over n items spread over the cluster: CTA c owns the contiguous chunk [c * chunk, (c+1) * chunk).
-//   first(i)           -> value of item i (may have side effects; called once per item)
-//   second(i)          -> the same value again (cheap form)
-//   out(i, prefix, v)  -> called once per item with its exclusive prefix
-// Returns the total.  Costs one cluster barrier.
-template <typename First, typename Second, typename Out>
-__device__ __forceinline__ unsigned int fz_ordered_scan(FzCluster& c, long long n, First first, Second second, Out out)
+// Ordered exclusive scan over n items spread over the cluster.  CTA c owns the contiguous chunk [c * chunk, (c+1) * chunk),
+// warp w of it a contiguous 1/32 of that; a warp walks its part 32 items at a time (coalesced), so the whole scan costs ONE
+// block-wide scan (of the 32 warp totals) and one cluster barrier, whatever n is.
+// Pass 1 runs in three stages, kFzIlp items per thread per stage, so that the long-latency loads of a stage are all in
+// flight before the first dependent instruction:
+//   a(i) -> A            first (address-generating) load
+//   b(i, A) -> Bv        the long-latency load(s), nothing but loads
+//   c(i, Bv) -> value    arithmetic + side effects (called once per item)
+// Pass 2:  again(i) -> the same value (cheap form);  out(i, exclusive_prefix, value).
+// Returns the total.
+template <typename StA, typename StB, typename StC, typename Again, typename Out>
+__device__ __forceinline__ unsigned int fz_ordered_scan(FzCluster& c, long long n, StA sa, StB sb, StC sc, Again again, Out out)
 {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long chunk = ((n + c.size - 1) / c.size + kFzThreads - 1) / kFzThreads * kFzThreads;
   const long long beg   = (long long)c.rank * chunk < n ? (long long)c.rank * chunk : n;
   const long long end   = beg + chunk < n ? beg + chunk : n;
-  unsigned long long mine = 0;
-  for (long long i = beg + threadIdx.x; i < end; i += kFzThreads)
-    mine += first(i);
+  const long long wlen  = chunk / (kFzThreads / 32);  // a multiple of 32
+  const long long wbeg  = beg + wid * wlen < end ? beg + wid * wlen : end;
+  const long long wend  = wbeg + wlen < end ? wbeg + wlen : end;
+  unsigned int mine = 0;
+  for (long long i0 = wbeg + lane; i0 < wend; i0 += 32 * kFzIlp) {
+    decltype(sa(0LL)) A[kFzIlp];
+    decltype(sb(0LL, A[0])) Bv[kFzIlp];
+#pragma unroll
+    for (int u = 0; u < kFzIlp; u++)
+      if (i0 + 32 * u < wend) A[u] = sa(i0 + 32 * u);
+#pragma unroll
+    for (int u = 0; u < kFzIlp; u++)
+      if (i0 + 32 * u < wend) Bv[u] = sb(i0 + 32 * u, A[u]);
+#pragma unroll
+    for (int u = 0; u < kFzIlp; u++)
+      if (i0 + 32 * u < wend) mine += sc(i0 + 32 * u, Bv[u]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0) c.sh->warp[wid] = mine;
+  __syncthreads();
+  if (wid == 0) {
+    const unsigned int w = lane < kFzThreads / 32 ? c.sh->warp[lane] : 0u;
+    unsigned int wi      = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    c.sh->warp[lane] = wi - w;
+    if (lane == 31) c.sh->warp[32] = wi;
+  }
+  __syncthreads();
+  const unsigned int wbase = c.sh->warp[wid];
   unsigned long long total;
-  unsigned long long carry = c.exchange(mine, total);
-  for (long long t0 = beg; t0 < end; t0 += kFzThreads) {
-    const long long i    = t0 + threadIdx.x;
-    const unsigned int v = i < end ? second(i) : 0u;
-    unsigned int tile_total;
-    const unsigned int ex = fz_block_scan(v, c.sh->warp, tile_total);
-    if (i < end) out(i, (unsigned int)carry + ex, v);
-    carry += tile_total;
+  unsigned int carry = (unsigned int)c.exchange((unsigned long long)c.sh->warp[32], total) + wbase;  // (barrier: warp[] is free again)
+  for (long long i0 = wbeg; i0 < wend; i0 += 32) {
+    const long long i    = i0 + lane;
+    const unsigned int v = i < wend ? again(i) : 0u;
+    unsigned int inc     = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int y = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += y;
+    }
+    if (i < wend) out(i, carry + inc - v, v);
+    carry += __shfl_sync(0xffffffffu, inc, 31);
   }
   return (unsigned int)total;
+}
+
+// a plain loop over n items of the cluster in the same staged form (no ordering between items)
+template <typename StA, typename StB, typename StC>
+__device__ __forceinline__ void fz_for_each(const FzCluster& c, int n, StA sa, StB sb, StC sc)
+{
+  const int CT = (int)c.size * kFzThreads, cti = (int)c.rank * kFzThreads + (int)threadIdx.x;
+  for (int i0 = cti; i0 < n; i0 += CT * kFzIlp) {
+    decltype(sa(0)) A[kFzIlp];
+    decltype(sb(0, A[0])) Bv[kFzIlp];
+#pragma unroll
+    for (int u = 0; u < kFzIlp; u++)
+      if (i0 + CT * u < n) A[u] = sa(i0 + CT * u);
+#pragma unroll
+    for (int u = 0; u < kFzIlp; u++)
+      if (i0 + CT * u < n) Bv[u] = sb(i0 + CT * u, A[u]);
+#pragma unroll
+    for (int u = 0; u < kFzIlp; u++)
+      if (i0 + CT * u < n) sc(i0 + CT * u, Bv[u]);
+  }
 }
 
 // decoupled look-back over the labels before `l` (one warp): publishes this label's count, returns the sum of the counts
@@ -284,8 +335,10 @@ __device__ __forceinline__ void fz_sample_rows(const FzArgs& a, FzCluster& c, co
   }
 }
 
+// launch bound 1024 (the CTA is kFzThreads = 896 wide): caps the kernel at 64 registers per thread, so that 28 warps take
+// 56 K of the SM's 64 K registers and the bulk-copy gather CTA (4 warps x 64) fits beside it
 template <typename ColT>
-__global__ void __launch_bounds__(kFzThreads, 1) fz_label_kernel(const __grid_constant__ FzArgs a)
+__global__ void __launch_bounds__(1024, 1) fz_label_kernel(const __grid_constant__ FzArgs a)
 {
   __shared__ FzShared sh;
   FzCluster c;
@@ -308,40 +361,59 @@ __global__ void __launch_bounds__(kFzThreads, 1) fz_label_kernel(const __grid_co
 
     const long long lo_l = a.label_offsets[l];
     const int n_seeds    = (int)(a.label_offsets[l + 1] - lo_l);
-    long long* __restrict__ Fl          = a.F + lo_l * a.fstride;
-    int* __restrict__ Ol                = a.Orow + lo_l * a.fstride;
-    const long long ebeg                = lo_l * a.estride;
-    int* __restrict__ majl              = a.maj + ebeg;
-    int* __restrict__ mnrl              = a.mnr + ebeg;
-    long long* __restrict__ gidl        = a.gid + ebeg;
-    ColT* __restrict__ destl            = static_cast<ColT*>(a.dest) + ebeg;
-    unsigned int* __restrict__ auxl     = a.aux + ebeg;
-    unsigned int* __restrict__ rankl    = a.rank_of + ebeg;
-    unsigned long long* __restrict__ tb = a.table + fz_table_base(lo_l, a.fstride, l);
-    int* __restrict__ n_step            = a.n_step + (long long)l * (L + 1);
-    int* __restrict__ e_hop             = a.e_hop + (long long)l * L;
+    // the label's slices of the scratch arrays: base pointers come from the parameter block every time they are used (two
+    // 64-bit offsets stay live across the label instead of eleven pointers -- the kernel is capped at 64 registers)
+    const long long vbeg = lo_l * a.fstride, ebeg = lo_l * a.estride;
+#define Fl (a.F + vbeg)
+#define Ol (a.Orow + vbeg)
+#define majl (a.maj + ebeg)
+#define mnrl (a.mnr + ebeg)
+#define gidl (a.gid + ebeg)
+#define destl (static_cast<ColT*>(a.dest) + ebeg)
+#define auxl (a.aux + ebeg)
+#define rankl (a.rank_of + ebeg)
+#define tb (a.table + tbeg)
+#define n_step (a.n_step + (long long)l * (L + 1))
+#define e_hop (a.e_hop + (long long)l * L)
+    const long long tbeg = fz_table_base(lo_l, a.fstride, l);
 
+    // optional phase clock (WGB_MH_TIMING): thread 0 of the cluster stamps the global timer after every phase
+#define FZ_T(p)                                                                            \
+  do {                                                                                     \
+    if (a.dbg && cti == 0 && (p) < kFzDbgSlots) {                                          \
+      unsigned long long t_;                                                               \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                               \
+      a.dbg[(long long)l * kFzDbgSlots + (p)] = (long long)t_;                             \
+    }                                                                                      \
+  } while (0)
+    FZ_T(0);
     // ---- step 0: the label's distinct seeds, first occurrence first ----------------------------------------
     unsigned int nb = ((unsigned int)n_seeds >> 1) + 8u;
     for (unsigned int i = cti; i < nb * 4u; i += CT)
       tb[i] = kFzEmpty;
     c.sync();
-    for (int s = (int)cti; s < n_seeds; s += (int)CT) {
-      long long v = a.seed_is64 ? static_cast<const long long*>(a.seeds)[lo_l + s] : (long long)static_cast<const int*>(a.seeds)[lo_l + s];
-      if (v < 0 || (unsigned long long)v >= a.V) {  // flagged; carry on with vertex 0 so that nothing is read out of bounds
-        *a.bad_seed = 1;
-        v           = 0;
-      }
-      gidl[s] = v;  // the label's edge scratch is free until hop 0 writes it: sanitised seeds for the compaction below
-      auxl[s] = fz_upsert(tb, nb, (unsigned int)v, kFzPending | (unsigned int)s);
-    }
-    c.sync();
-    int known = (int)fz_ordered_scan(
+    FZ_T(1);
+    fz_for_each(
       c, n_seeds,
-      [&](long long s) -> unsigned int {
-        const unsigned int ax = (unsigned int)ld_relaxed_u64(&tb[auxl[s]]);
-        auxl[s]               = ax;
-        return ax == (kFzPending | (unsigned int)s) ? 1u : 0u;
+      [&](int s) -> long long {
+        long long v = a.seed_is64 ? static_cast<const long long*>(a.seeds)[lo_l + s] : (long long)static_cast<const int*>(a.seeds)[lo_l + s];
+        if (v < 0 || (unsigned long long)v >= a.V) {  // flagged; carry on with vertex 0 so that nothing is read out of bounds
+          *a.bad_seed = 1;
+          v           = 0;
+        }
+        gidl[s] = v;  // the label's edge scratch is free until hop 0 writes it: sanitised seeds for the compaction below
+        return v;
+      },
+      [&](int, long long v) -> FzProbe { return fz_probe(tb, nb, (unsigned int)v); },
+      [&](int s, const FzProbe& pr) { auxl[s] = fz_upsert(tb, nb, pr, kFzPending | (unsigned int)s); });
+    c.sync();
+    FZ_T(2);
+    int known = (int)fz_ordered_scan(
+      c, n_seeds, [&](long long s) -> unsigned int { return auxl[s]; },
+      [&](long long, unsigned int slot) -> unsigned long long { return ld_relaxed_u64(&tb[slot]); },
+      [&](long long s, unsigned long long w) -> unsigned int {
+        auxl[s] = (unsigned int)w;
+        return (unsigned int)w == (kFzPending | (unsigned int)s) ? 1u : 0u;
       },
       [&](long long s) -> unsigned int { return auxl[s] == (kFzPending | (unsigned int)s) ? 1u : 0u; },
       [&](long long s, unsigned int rank, unsigned int f) {
@@ -358,23 +430,32 @@ __global__ void __launch_bounds__(kFzThreads, 1) fz_label_kernel(const __grid_co
       }
     }
     c.sync();  // ranks of the first occurrences are visible
+    FZ_T(3);
     for (int s = (int)cti; s < n_seeds; s += (int)CT)
       a.seed_local[lo_l + s] = (int)rankl[auxl[s] & ~kFzPending];
+    FZ_T(4);
 
     // ---- hops ----------------------------------------------------------------------------------------------------
     int nbase = 0, n_rows = known, ebase = 0;  // frontier of hop h = Fl[nbase, nbase + n_rows)
     for (int h = 0; h < L; h++) {
       const int M = a.fanout[h];
+      const int T0 = 5 + 6 * h;
       // P1: min(deg, M) per frontier row, exclusive scan in row order -> the row's first edge
+      struct Row2 {
+        long long s0, s1;
+      };
       const int e_h = (int)fz_ordered_scan(
-        c, n_rows,
-        [&](long long r) -> unsigned int {
-          const unsigned long long node = (unsigned long long)Fl[nbase + r];
-          const long long s0 = load_i64<false>(a.row_ptr, a.row_ptr_off + node);
-          const long long s1 = load_i64<false>(a.row_ptr, a.row_ptr_off + node + 1);
-          long long d        = s1 - s0;
-          d                  = d < 0 ? 0 : (d > M ? M : d);
-          Ol[nbase + r]      = (int)d;
+        c, n_rows, [&](long long r) -> long long { return Fl[nbase + r]; },
+        [&](long long, long long node) -> Row2 {
+          Row2 x;
+          x.s0 = load_i64<false>(a.row_ptr, a.row_ptr_off + (unsigned long long)node);
+          x.s1 = load_i64<false>(a.row_ptr, a.row_ptr_off + (unsigned long long)node + 1);
+          return x;
+        },
+        [&](long long r, const Row2& x) -> unsigned int {
+          long long d   = x.s1 - x.s0;
+          d             = d < 0 ? 0 : (d > M ? M : d);
+          Ol[nbase + r] = (int)d;
           return (unsigned int)d;
         },
         [&](long long r) -> unsigned int { return (unsigned int)Ol[nbase + r]; },
@@ -383,14 +464,14 @@ __global__ void __launch_bounds__(kFzThreads, 1) fz_label_kernel(const __grid_co
       const long long rowbase = c.size == 1 ? sh.rowbase : *cg::this_cluster().map_shared_rank(&sh.rowbase, 0);
       if (c.rank == 0 && tid == 0) e_hop[h] = e_h;
       known = nbase + n_rows;
+      FZ_T(T0);
       // P2: a fresh table for (everything numbered so far + this hop's edges)
       nb = (((unsigned int)known + (unsigned int)e_h) >> 1) + 8u;
       for (unsigned int i = cti; i < nb * 4u; i += CT)
         tb[i] = kFzEmpty;
       c.sync();  // table cleared, row offsets visible
-      // P3: numbered vertices enter with their local id; the hop's rows are sampled (independent of the table)
-      for (int j = (int)cti; j < known; j += (int)CT)
-        fz_upsert(tb, nb, (unsigned int)Fl[j], (unsigned int)j);
+      FZ_T(T0 + 1);
+      // P3: the hop's rows are sampled (independent of the table); numbered vertices enter the table with their local id
       if (e_h > 0) {
         FzSink<ColT> sink{destl + ebase, majl + ebase, gidl + ebase};
         const unsigned long long hop_seed = a.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL;
@@ -398,23 +479,31 @@ __global__ void __launch_bounds__(kFzThreads, 1) fz_label_kernel(const __grid_co
         else if (M <= 16) fz_sample_rows<ColT, 16>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
         else fz_sample_rows<ColT, 32>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
       }
+      fz_for_each(
+        c, known, [&](int j) -> unsigned int { return (unsigned int)Fl[j]; },
+        [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v); },
+        [&](int j, const FzProbe& pr) { fz_upsert(tb, nb, pr, (unsigned int)j); });
       c.sync();  // edges written, known vertices in the table
+      FZ_T(T0 + 2);
       // P4: endpoints enter the table; the smallest edge index wins a new vertex
-      for (int i = (int)cti; i < e_h; i += (int)CT)
-        auxl[ebase + i] = fz_upsert(tb, nb, (unsigned int)destl[ebase + i], kFzPending | (unsigned int)i);
+      fz_for_each(
+        c, e_h, [&](int i) -> unsigned int { return (unsigned int)destl[ebase + i]; },
+        [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v); },
+        [&](int i, const FzProbe& pr) { auxl[ebase + i] = fz_upsert(tb, nb, pr, kFzPending | (unsigned int)i); });
       c.sync();
+      FZ_T(T0 + 3);
       // P5: first occurrences in edge order -> the next frontier, appended to the label's vertex array
       const int n_new = (int)fz_ordered_scan(
-        c, e_h,
-        [&](long long i) -> unsigned int {
-          const unsigned int ax = (unsigned int)ld_relaxed_u64(&tb[auxl[ebase + i]]);
-          auxl[ebase + i]       = ax;
-          return ax == (kFzPending | (unsigned int)i) ? 1u : 0u;
+        c, e_h, [&](long long i) -> unsigned int { return auxl[ebase + i]; },
+        [&](long long, unsigned int slot) -> unsigned long long { return ld_relaxed_u64(&tb[slot]); },
+        [&](long long i, unsigned long long w) -> unsigned int {
+          auxl[ebase + i] = (unsigned int)w;
+          return (unsigned int)w == (kFzPending | (unsigned int)i) ? 1u : 0u;
         },
         [&](long long i) -> unsigned int { return auxl[ebase + i] == (kFzPending | (unsigned int)i) ? 1u : 0u; },
         [&](long long i, unsigned int rank, unsigned int f) {
           if (f) {
-            Fl[known + rank]  = (long long)destl[ebase + i];
+            Fl[known + rank] = (long long)destl[ebase + i];
             rankl[ebase + i] = rank;
           }
         });
@@ -427,15 +516,32 @@ __global__ void __launch_bounds__(kFzThreads, 1) fz_label_kernel(const __grid_co
         }
       }
       c.sync();  // ranks visible
+      FZ_T(T0 + 4);
       // P6: endpoints -> local ids
-      for (int i = (int)cti; i < e_h; i += (int)CT) {
-        const unsigned int ax = auxl[ebase + i];
-        mnrl[ebase + i]       = (ax & kFzPending) ? known + (int)rankl[ebase + (ax & ~kFzPending)] : (int)ax;
-      }
+      fz_for_each(
+        c, e_h, [&](int i) -> unsigned int { return auxl[ebase + i]; },
+        [&](int, unsigned int ax) -> unsigned int { return (ax & kFzPending) ? rankl[ebase + (ax & ~kFzPending)] : 0u; },
+        [&](int i, unsigned int rk) {
+          const unsigned int ax = auxl[ebase + i];
+          mnrl[ebase + i]       = (ax & kFzPending) ? known + (int)rk : (int)ax;
+        });
+      FZ_T(T0 + 5);
       nbase  = known;
       n_rows = n_new;
       ebase += e_h;
     }
+#undef FZ_T
+#undef Fl
+#undef Ol
+#undef majl
+#undef mnrl
+#undef gidl
+#undef destl
+#undef auxl
+#undef rankl
+#undef tb
+#undef n_step
+#undef e_hop
     // the next label's first barrier orders this label's last reads before its scratch is touched again (it is not:
     // scratch is per label), and sh.* before it is rewritten
   }
@@ -563,6 +669,11 @@ static bool multihop_begin_fused(MhCall& c)
   a.ticket   = reinterpret_cast<unsigned int*>(pub + (size_t)L * (size_t)B);
   a.bad_seed = reinterpret_cast<long long*>(pub + (size_t)L * (size_t)B + 1);
   a.V        = c.V;
+  a.dbg      = nullptr;
+  if (sp->timing) {
+    a.dbg = static_cast<long long*>(ensure(sp->fz[12], sizeof(long long) * (size_t)B * kFzDbgSlots));
+    WGB_CUDA_TRY(cudaMemsetAsync(a.dbg, 0, sizeof(long long) * (size_t)B * kFzDbgSlots, st));
+  }
   a.tab    = skip_table_device();
 
   sp->pending.active   = false;
@@ -589,6 +700,13 @@ static bool multihop_begin_fused(MhCall& c)
   cfg.attrs            = attr;
   cfg.numAttrs         = 1;
   if (mc == 0) {
+    // WGB_MH_CARVEOUT=<percent of 228 KB>: ask for a larger shared-memory carve-out than the kernel needs (< 4 KB), so that a
+    // bulk-copy gather CTA (gather_scatter.cu, 96 KB of tile rings) can join the SM -- the L1 / shared split is fixed while
+    // a CTA is resident.  Off by default: measured on C4 (profiles/r2k_*.json), a gather that co-resides takes HBM
+    // bandwidth from this latency-bound kernel and the pipelined step gets no shorter than running the two back to back
+    // (0.77 ms), while a gather that only fills the gaps this kernel leaves gives 0.64 ms.
+    if (const char* e = getenv("WGB_MH_CARVEOUT"))
+      if (atoi(e) > 0) WGB_CUDA_TRY(cudaFuncSetAttribute(fz_label_kernel<ColT>, cudaFuncAttributePreferredSharedMemoryCarveout, std::min(100, atoi(e))));
     cfg.gridDim = dim3((unsigned int)(CL * std::max(1, sms / CL)), 1, 1);
     int n       = 0;
     WGB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, fz_label_kernel<ColT>, &cfg));
@@ -693,6 +811,44 @@ static void multihop_finish_fused(wholegraph_multihop_sampler_* sp, const MhOutC
   }
   mh_mark(sp, "emit", st);
   mh_collect_marks(sp);
+  if (a.dbg) {  // WGB_MH_TIMING: per-phase time of a label, averaged over labels and calls
+    std::vector<long long> t((size_t)B * kFzDbgSlots);
+    WGB_CUDA_TRY(cudaMemcpy(t.data(), a.dbg, t.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    long long first = 0, last = 0;
+    for (int l = 0; l < B; l++) {
+      const long long* tl = t.data() + (size_t)l * kFzDbgSlots;
+      long long prev = tl[0];
+      if (l == 0 || tl[0] < first) first = tl[0];
+      for (int p = 1; p < kFzDbgSlots; p++) {
+        if (tl[p] == 0) continue;
+        sp->fz_phase_ns[p] += (double)(tl[p] - prev);
+        prev = tl[p];
+        if (tl[p] > last) last = tl[p];
+      }
+    }
+    sp->fz_phase_labels += B;
+    sp->fz_span_ns += (double)(last - first);
+    sp->fz_calls++;
+  }
+}
+
+static void fz_print_phases(wholegraph_multihop_sampler_* sp)
+{
+  if (!sp->timing || sp->fz_phase_labels == 0) return;
+  static const char* seed_names[5] = {"", "seeds: clear table", "seeds: insert", "seeds: first occurrences", "seeds: local ids"};
+  static const char* hop_names[6]  = {"count + scan", "clear table", "sample + re-insert known", "insert endpoints", "first occurrences", "local ids"};
+  fprintf(stderr, "[wgb multihop fused] mean time of a label per phase (%lld labels), kernel span %.1f us per call\n", sp->fz_phase_labels,
+          1e-3 * sp->fz_span_ns / (double)std::max<long long>(1, sp->fz_calls));
+  double tot = 0;
+  for (int p = 1; p < kFzDbgSlots; p++) {
+    if (sp->fz_phase_ns[p] == 0) continue;
+    char name[64];
+    if (p < 5) snprintf(name, sizeof(name), "%s", seed_names[p]);
+    else snprintf(name, sizeof(name), "hop%d: %s", (p - 5) / 6, hop_names[(p - 5) % 6]);
+    fprintf(stderr, "  %-36s %9.2f us\n", name, 1e-3 * sp->fz_phase_ns[p] / (double)sp->fz_phase_labels);
+    tot += sp->fz_phase_ns[p];
+  }
+  fprintf(stderr, "  %-36s %9.2f us\n", "label total", 1e-3 * tot / (double)sp->fz_phase_labels);
 }
 
 }  // namespace wgb

@@ -216,32 +216,38 @@ __global__ void __launch_bounds__(256) sample_all_kernel(ChunkRef row_ptr, unsig
 //           -> V_i = y_root(i) after pointer jumping over f.
 //   a_i  = V_j* where j* is the latest j < i with x_j == x_i, or x_i if there is none.
 // Lane g of a G-lane group owns step i = g.  `Wg` is G ints of shared memory private to the group.
+// Every lane of the warp calls this together (groups that have nothing to resolve pass valid = false): all collectives
+// run under the full mask -- a sub-warp mask costs a WARPSYNC + reconvergence sequence around every shuffle / vote / match
+// (19 % of the instructions of the sampling loop before this form) -- and groups are told apart by the sub-group id in
+// the match key and by the shuffle width.
 template <int G>
 __device__ __forceinline__ int resolve_chain_group(int x, bool valid, int g, int lane, int sub, unsigned int gmask,
                                                    int N, int M, int* Wg)
 {
-  int key          = valid ? x : (int)(0x80000000u | (unsigned int)lane);
-  unsigned int m   = __match_any_sync(gmask, key);
+  const unsigned long long key = valid ? (((unsigned long long)(unsigned int)sub << 32) | (unsigned int)x)
+                                       : (0x8000000000000000ULL | (unsigned long long)lane);
+  unsigned int m   = __match_any_sync(0xffffffffu, key) & gmask;
   unsigned int low = m & ((1u << lane) - 1u);
   bool has_prev    = valid && low != 0;
   // fast path (the common case when N >> M): no two steps read the same position and no step reads one of
   // the M tail positions that get copied -> Q is still the identity wherever it is read, a[i] = r[i].
-  if (!__any_sync(gmask, has_prev || (valid && x >= N - M))) return x;
+  const unsigned int slow = __ballot_sync(0xffffffffu, has_prev || (valid && x >= N - M));
+  if (slow == 0u) return x;  // warp-uniform
   int jstar        = has_prev ? (31 - __clz(low)) - sub * G : 0;
   Wg[g]            = -1;
-  __syncwarp(gmask);
+  __syncwarp();
   if (valid && x >= N - M) {
     int t = N - 1 - x;
     if (t != g) atomicMax(&Wg[t], g);
   }
-  __syncwarp(gmask);
+  __syncwarp();
   int f = Wg[g];
-  __syncwarp(gmask);
+  __syncwarp();
   int p = f >= 0 ? f : g;
-  for (int s = 1; s < M; s <<= 1)
-    p = __shfl_sync(gmask, p, p, G);
+  for (int s = 1; s < G; s <<= 1)  // log2(G) >= log2(M) rounds: extra rounds leave the roots where they are
+    p = __shfl_sync(0xffffffffu, p, p, G);
   int V  = N - 1 - p;
-  int Vj = __shfl_sync(gmask, V, jstar, G);
+  int Vj = __shfl_sync(0xffffffffu, V, jstar, G);
   return has_prev ? Vj : x;
 }
 
@@ -286,23 +292,24 @@ __device__ __forceinline__ void uniform_small_rows32(const ChunkRef& col, unsign
       row_skip.s = __shfl_sync(0xffffffffu, skip_own.s, src);
       const long long b = __shfl_sync(0xffffffffu, b_own, src);
       pos[k] = off + g;
-      if (N > 0) {
-        int a      = g;
-        bool write = g < N;
-        if (N > M) {
-          const bool valid = g < M;
-          Pcg rng;
-          rng.init_with_skip(seed, 32ULL * (unsigned long long)b + (unsigned long long)g, affine_then(row_skip, lane_skip));
-          int xr = rng.next_i32();
-          int x  = valid ? xr % (N - g) : -1;
-          a      = resolve_chain_group<G>(x, valid, g, lane, sub, gmask, N, M, Wg);
-          write  = valid;
-        }
-        if (write) {
-          val[k] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + a));
-          sink.ids(off + g, tag, start + a);
-          wmask |= 1u << k;
-        }
+      // every lane takes part in the chain resolution (full-mask collectives); rows that are copied whole, empty rows
+      // and lanes beyond the fan-out pass valid = false
+      const bool sampled = N > M;
+      const bool valid   = sampled && g < M;
+      int x              = -1;
+      if (sampled) {
+        Pcg rng;
+        rng.init_with_skip(seed, 32ULL * (unsigned long long)b + (unsigned long long)g, affine_then(row_skip, lane_skip));
+        const int xr = rng.next_i32();
+        if (valid) x = xr % (N - g);
+      }
+      const int ar     = resolve_chain_group<G>(x, valid, g, lane, sub, gmask, N, M, Wg);
+      const int a      = sampled ? ar : g;
+      const bool write = sampled ? valid : g < N;
+      if (write) {
+        val[k] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + a));
+        sink.ids(off + g, tag, start + a);
+        wmask |= 1u << k;
       }
       __syncwarp();
     }

@@ -287,6 +287,16 @@ inline unsigned int __match_any_sync(unsigned int mask, int value)
   });
 }
 
+inline unsigned int __match_any_sync(unsigned int mask, unsigned long long value)
+{
+  return ::cuda_emu::exchange(mask, value, [=](const unsigned long long* v) {
+    unsigned int r = 0;
+    for (int i = 0; i < 32; i++)
+      if (((mask >> i) & 1u) && v[i] == value) r |= 1u << i;
+    return r;
+  });
+}
+
 inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }

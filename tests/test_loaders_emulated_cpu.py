@@ -246,7 +246,8 @@ def test_plain_link_loader_unchanged(stack):
         lo = 8 * i
         assert torch.equal(out.n_id[out.edge_label_index[0]], eli[0, lo:lo + 8]) and torch.equal(out.n_id[out.edge_label_index[1]], eli[1, lo:lo + 8])
         assert torch.equal(out.x[:, 0], out.n_id.float())
-    assert i == 2 and sampler.calls == ["plain", "plain"]
+    # local_seeds_per_call counts seed VERTICES: 16 = one batch of 8 seed edges per native call -> three call groups
+    assert i == 2 and sampler.calls == ["plain", "plain", "plain"]
 
 
 # ---- disjoint sampling (homogeneous): the reference's three loader tests -----------------------------------------------------
