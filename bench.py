@@ -553,6 +553,85 @@ def run_ours(args):
 
 
 # ----------------------------------------------------------------------------------------------------
+# --loader: the same hot path driven through the reference-facing Python stack, one mini-batch at a time
+# ----------------------------------------------------------------------------------------------------
+def run_loader(args):
+    """cugraph_pyg.loader.NeighborLoader(batch_size=1024, num_neighbors=[25, 10]) over GraphStore / FeatureStore on the bench
+    graph (role of the reference's sampler/sampler.py:51-165 -> loader iteration): mini-batches / s and sampled edges / s as
+    a training loop sees them (every batch arrives with its features gathered), next to the device time the native calls of
+    the same call groups take (the share of the wall clock the hot-path kernels keep the GPU busy).  One GPU.
+    Not the driver's line: `python bench.py --loader [--workload c2]` prints its own JSON line."""
+    import torch
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    os.environ.setdefault("LOCAL_WORLD_SIZE", "1")
+    import pylibwholegraph.torch as wgth
+    from cugraph_pyg.data import FeatureStore, GraphStore
+    from cugraph_pyg.loader import NeighborLoader
+
+    t0 = time.time()
+    row_ptr, col = rmat_csr(torch, NUM_NODES, NUM_EDGES, 42, dev)
+    dst = torch.repeat_interleave(torch.arange(NUM_NODES, device=dev), row_ptr[1:] - row_ptr[:-1])
+    graph_store = GraphStore()
+    graph_store[("n", "e", "n"), "coo", False, (NUM_NODES, NUM_NODES)] = torch.stack([col.long(), dst])  # PyG: [source; destination]
+    del dst, col, row_ptr
+    feature_store = FeatureStore(location="cuda")
+    x = torch.empty((NUM_NODES, FEAT_DIM), dtype=torch.float32, device=dev)
+    ar = torch.arange(FEAT_DIM, device=dev)[None, :]
+    for lo in range(0, NUM_NODES, 1 << 20):
+        hi = min(NUM_NODES, lo + (1 << 20))
+        x[lo:hi] = ((torch.arange(lo, hi, device=dev)[:, None] + ar) & 0xFFFF).float()
+    feature_store["n", "x", None] = x
+    del x
+    torch.cuda.empty_cache()
+    log("[loader] stores built in %.1fs" % (time.time() - t0))
+    labels = args.labels
+    per_group = labels * BATCH
+    n_groups = args.steps + args.warmup
+    seeds = torch.randperm(NUM_NODES, generator=torch.Generator().manual_seed(1234))[: n_groups * per_group]
+
+    def one_pass(nodes):
+        loader = NeighborLoader((feature_store, graph_store), FANOUT, input_nodes=nodes, batch_size=BATCH, shuffle=False,
+                                local_seeds_per_call=per_group)
+        nb = ne = nn = 0
+        acc = torch.zeros((), device=dev)
+        for batch in loader:
+            nb += 1
+            ne += int(batch.edge_index.shape[1])
+            nn += int(batch.n_id.shape[0])
+            acc += batch.x[0, 0] + batch.x[-1, -1]  # the features are there (device-side use, no host sync per batch)
+        return nb, ne, nn, acc
+
+    one_pass(seeds[: args.warmup * per_group])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    nb, ne, nn, acc = one_pass(seeds[args.warmup * per_group:])
+    e1.record()
+    torch.cuda.synchronize()
+    wall_ms = 1e3 * (time.perf_counter() - w0)
+    dev_ms = e0.elapsed_time(e1)
+    float(acc)
+    out = {
+        "mode": "loader",
+        "metric": "loader_minibatches_per_sec (NeighborLoader over GraphStore / FeatureStore, batch 1024, fan-out [25,10], features gathered)",
+        "value": nb / (wall_ms * 1e-3), "unit": "mini-batches/s",
+        "edges_per_sec": ne / (wall_ms * 1e-3), "nodes_gathered_per_sec": nn / (wall_ms * 1e-3),
+        "gather_gbs": nn * FEAT_DIM * 4 / (wall_ms * 1e-3) / 1e9,
+        "minibatches": nb, "call_groups": args.steps, "ms_per_call_group": wall_ms / args.steps, "ms_per_minibatch": wall_ms / nb,
+        "device_span_ms": dev_ms, "wall_ms": wall_ms,
+        "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_size": BATCH, "minibatches_per_call_group": labels,
+                   "stack": "cugraph_pyg.loader.NeighborLoader -> DistributedNeighborSampler -> pylibcugraph shim -> libwholegraph_b200 (fused sampler) ; "
+                            "FeatureStore -> WholeMemoryEmbedding.gather"},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
 # CPU arm: the oracle (a C++/OpenMP restatement of the reference's own host reference algorithms; the
 # reference's implementation cannot be compiled or installed here -- SURVEY.md §8c) on the host cores.
 # ----------------------------------------------------------------------------------------------------
@@ -666,6 +745,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--labels", type=int, default=LABELS_PER_STEP)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--loader", action="store_true",
+                    help="time the same hot path through cugraph_pyg.loader.NeighborLoader + FeatureStore, per mini-batch (one GPU; c2 recommended)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle comparison on the bench graph (profiling runs)")
     ap.add_argument("--hot-ratio", type=float, default=0.1,
@@ -682,6 +763,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.loader:
+        run_loader(args)
     else:
         run_ours(args)
 

@@ -387,18 +387,18 @@ static void launch_copy(const RowsOpArgs& a, int64_t row0, int64_t rows, unsigne
   WGB_CHECK_LAUNCH();
 }
 
-// Which same-dtype gathers go through the copy engine.  Measured on C4 (profiles/r2k_*.json, one GPU): alone the bulk kernel
-// is the faster one (0.335 ms against 0.382 for 2.1 M rows of 512 B: 1.0 against 0.88 of the HBM peak), but a loader runs the
-// gather of call group k beside the sampler of call group k+1, and there the register kernel is the better neighbour (step
-// 0.642 ms against 0.68-0.77): its CTAs only fit where the sampler leaves registers free, so it fills the gaps of the
-// sampler's stream instead of taking HBM bandwidth away from a latency-bound kernel.  Default: bulk copies for tables
-// striped over several GPUs (the copy engine keeps more NVLink reads in flight per SM than 4 x 16 B per thread), the
-// register kernel for local tables.  WGB_GATHER_BULK=1 / 0 forces one path for every call; read per call.
-static bool bulk_enabled(int world)
+// Which same-dtype gathers go through the copy engine: those of callers that ask for it (WGB_GATHER_BULK=1; read per call).
+// Measured on C4 (profiles/r2k_*.json one GPU, profiles/r2l_*.json two GPUs): alone the bulk kernel is the faster one
+// (local table: 0.335 ms against 0.382 for 2.1 M rows of 512 B = 1.0 against 0.88 of the HBM peak; table striped over two
+// GPUs, no replica: 0.846 against 0.865 ms = 0.83 against 0.81 of the NVLink bound), but a loader runs the gather of call
+// group k beside the sampler of call group k+1, and there the register kernel is the better neighbour (step 0.642 against
+// 0.68-0.77 ms on one GPU, 0.811 against 0.900 on two): its CTAs only fit where the sampler leaves registers free, so it
+// fills the gaps of the sampler's stream, while the copy engine keeps HBM saturated and the latency-bound sampler pays.
+// So the register kernel stays the default; the bulk kernel is for gathers that have the GPU to themselves.
+static bool bulk_enabled(int /*world*/)
 {
   const char* e = getenv("WGB_GATHER_BULK");
-  if (e && *e) return atoi(e) != 0;
-  return world > 1;
+  return e && *e && atoi(e) != 0;
 }
 
 // Shared memory of the tile rings per CTA: 96 KB (2 warps x 3 tiles of 16 KB at 512-byte rows).  An SM that runs nothing

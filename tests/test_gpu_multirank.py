@@ -218,6 +218,44 @@ def test_trainable_embedding_two_ranks():
     _run(_optimizer_worker)
 
 
+def _file_io_worker(rank, world, uid, tmpdir):
+    """(f3) two ranks, uneven parts: every rank stores its own part file (to_file_prefix), a tensor with ANOTHER partition
+    is loaded from the two files (from_file_prefix: each rank reads exactly the byte range of its chunk out of the
+    concatenation), and gathers over both chunks return the closed form."""
+    torch = _setup(rank, world)
+    wgth, comm = _comm(uid, rank, world)
+    rows, dim, stride = 10_007, 48, 64
+    part = [rows // 3, rows - rows // 3]
+    t = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [rows, dim], torch.float32, [stride, 1], part)
+    local, start = t.get_local_tensor()
+    ids = torch.arange(start, start + local.shape[0], device="cuda")
+    local.copy_(((ids[:, None] * 11 + torch.arange(dim, device="cuda")[None, :]) % 2039).float())
+    torch.cuda.synchronize()
+    comm.barrier()
+    prefix = os.path.join(tmpdir, "emb")
+    t.to_file_prefix(prefix)
+    comm.barrier()
+    sizes = [os.path.getsize("%s_part_%d_of_2" % (prefix, r)) for r in range(2)]
+    assert sizes == [part[0] * dim * 4, part[1] * dim * 4], sizes  # rows without their stride padding
+    back = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [rows, dim], torch.float32, [dim, 1])  # equal partition, no padding
+    back.get_local_tensor()[0].fill_(-1.0)
+    back.from_file_prefix(prefix)
+    comm.barrier()
+    idx = torch.randint(0, rows, (4000,), generator=torch.Generator().manual_seed(9))
+    exp = ((idx[:, None] * 11 + torch.arange(dim)[None, :]) % 2039).float()
+    assert torch.equal(back.gather(idx.cuda()).cpu(), exp), "rank %d: rows loaded from the part files differ" % rank
+    lb, sb = back.get_local_tensor()
+    want = ((torch.arange(sb, sb + lb.shape[0])[:, None] * 11 + torch.arange(dim)[None, :]) % 2039).float()
+    assert torch.equal(lb.cpu(), want)
+    comm.barrier()
+    wgth.destroy_wholememory_tensor(t)
+    wgth.destroy_wholememory_tensor(back)
+
+
+def test_file_round_trip_two_ranks_uneven_parts(tmp_path):
+    _run(_file_io_worker, tmpdir=str(tmp_path))
+
+
 def _run(fn, **kw):
     import pylibwholegraph.binding.wholememory_binding as wmb
     from pylibwholegraph.utils.multiprocess import multiprocess_run
