@@ -77,9 +77,13 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def rmat_csr(torch, num_nodes, num_edges, seed, device):
-    """RMAT edge list generated on `device`, folded into [0, num_nodes), returned as CSR by destination."""
-    scale = max(1, (num_nodes - 1).bit_length())
+def rmat_csr(torch, num_nodes, num_edges, seed, device, rows=None, cols=None):
+    """RMAT edge list generated on `device`, folded into [0, num_nodes), returned as CSR by destination.
+    rows / cols = (first id, count): destinations / sources live in those id ranges of a num_nodes-wide id space
+    (heterogeneous graphs: one call per edge type); default: both span [0, num_nodes)."""
+    r0, rn = rows if rows is not None else (0, num_nodes)
+    c0, cn = cols if cols is not None else (0, num_nodes)
+    scale = max(1, (max(rn, cn) - 1).bit_length())
     a, b, c, d = RMAT
     g = torch.Generator(device=device).manual_seed(seed)
     chunk = 1 << 24
@@ -97,8 +101,8 @@ def rmat_csr(torch, num_nodes, num_edges, seed, device):
         # RMAT concentrates the edges on small ids; scramble the ids with an affine bijection of [0, V) (Graph500
         # scrambles too) so that hubs are spread over the contiguous row partitions of the feature table instead of all
         # living on rank 0 (measured at N=2 before this: rank 0 gathered 0.54 ms/step, rank 1 1.31 ms/step)
-        src = ((src % num_nodes) * SCRAMBLE_MUL + SCRAMBLE_ADD) % num_nodes
-        dst = ((dst % num_nodes) * SCRAMBLE_MUL + SCRAMBLE_ADD) % num_nodes
+        src = ((src % cn) * SCRAMBLE_MUL + SCRAMBLE_ADD) % cn + c0
+        dst = ((dst % rn) * SCRAMBLE_MUL + SCRAMBLE_ADD) % rn + r0
         keys[lo:lo + n] = (dst << 32) | src
         del src, dst
     keys, _ = torch.sort(keys)
@@ -338,6 +342,11 @@ def run_ours(args):
 
     dev_seeds = [s.to(dev) for s in host_seeds]
     torch.cuda.synchronize()
+    # clocks / throttle reasons are sampled from before the warm-up to after the last timed region: nvidia-smi takes a few
+    # hundred ms to come up and stalls CUDA calls while it does (measured in the C5 step: 300 ms on the first timed step)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     n_max = e_max = 0
     for w in range(args.warmup):
         e, n, x, _ = step(dev_seeds[w], SAMPLER_SEED + 7 * w)
@@ -364,9 +373,6 @@ def run_ours(args):
         dist.barrier()
 
     # ---- device-resident timing: `value` -------------------------------------------------------------
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
 
     def begin_dev(k):
         return samplers[k & 1].sample_async(wm_rp, wm_col, dev_seeds[k], label_offsets, FANOUT, SAMPLER_SEED + 7 * k, int64_ids=True)
@@ -546,6 +552,284 @@ def run_ours(args):
             if host_graph is None:
                 host_graph = (row_ptr.cpu().numpy(), wm_col.get_local_tensor()[0].cpu().numpy())
             out["cpu_baseline"] = cpu_baseline(host_graph[0], host_graph[1], budget_s=15.0, labels=labels)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------
+# --workload c5: heterogeneous call groups + a DDP-wrapped GNN step (BASELINE.json configs[4])
+# ----------------------------------------------------------------------------------------------------
+C5_NODES = (25_000_000, 25_000_000)                    # vertex types "a", "b": global ids [0, 25 M) and [25 M, 50 M)
+C5_EDGE_TYPES = (("a", "a"), ("b", "a"), ("a", "b"))     # (source type, destination type); CSR rows are destinations
+C5_EDGES = 800_000_000
+C5_FANOUT = [10, 10]                                     # per edge type and hop -> h_fan_out [hop * T + etype] (neighbor_loader.py:192-201)
+C5_HIDDEN, C5_CLASSES = 256, 47
+C5_WORKLOAD = ("C5 heterogeneous synthetic: 3 edge types over |V|=50M (2 vertex types), |E|=800M, per-type fan-out [10,10], feat_dim=128 fp32, "
+               "hetero sampler + striped P2P gather + 2-layer SAGE step (NCCL all-reduce of the dense weights)")
+
+
+def run_c5(args):
+    """One step per GPU = one heterogeneous call group (args.labels mini-batches x 1024 seeds of type "a") through the
+    fused hetero sampler, the feature rows of every sampled vertex from the table striped over the GPUs (in-kernel P2P,
+    no collective), then forward + backward of a 2-layer GraphSAGE (pylibwholegraph.torch.SAGEConv: CSR aggregation kernel +
+    dense layers) over the sampled block, wrapped in DistributedDataParallel so that the NCCL all-reduce of the dense
+    weights is on the timeline (reference loop: examples/gcn_dist_mnmg.py:233-251, 427).  Reports per-stage device times."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    import pylibwholegraph.binding.wholememory_binding as wmb
+    import pylibwholegraph.torch as wgth
+    from pylibwholegraph.torch.aggregate import SAGEConv, csr_transpose
+
+    wgth.init(rank, world, local_rank, world)
+    comm = wgth.get_global_communicator()
+    launch_count = wmb.native_symbol("wholememory_b200_kernel_launch_count")
+    launch_count.restype = ctypes.c_ulonglong
+    one = wgth.create_group_communicator(1, 1) if world > 1 else comm
+    V = sum(C5_NODES)
+    vto = [0, C5_NODES[0], V]
+    rng_of = {"a": (0, C5_NODES[0]), "b": (C5_NODES[0], C5_NODES[1])}
+    T = len(C5_EDGE_TYPES)
+    t0 = time.time()
+    wm_rps, wm_cols = [], []
+    for t, (st, dt) in enumerate(C5_EDGE_TYPES):
+        rp, col = rmat_csr(torch, V, C5_EDGES // T, 42 + t, dev, rows=rng_of[dt], cols=rng_of[st])
+        w_rp = wgth.create_wholememory_tensor(one, "chunked", "cuda", [V + 1], torch.int64, [1])
+        w_rp.get_local_tensor()[0].copy_(rp)
+        w_col = wgth.create_wholememory_tensor(one, "chunked", "cuda", [col.numel()], torch.int32, [1])
+        w_col.get_local_tensor()[0].copy_(col)
+        wm_rps.append(w_rp)
+        wm_cols.append(w_col)
+        del rp, col
+    torch.cuda.synchronize()
+    log("[rank %d] 3 typed RMAT CSRs built in %.1fs" % (rank, time.time() - t0))
+    emb = wgth.create_embedding(comm, "chunked", "cuda", torch.float32, [V, FEAT_DIM])
+    local, start = emb.get_embedding_tensor().get_local_tensor()
+    ar = torch.arange(FEAT_DIM, device=dev)[None, :]
+    for lo in range(0, local.shape[0], 1 << 20):
+        hi = min(local.shape[0], lo + (1 << 20))
+        local[lo:hi] = ((torch.arange(start + lo, start + hi, device=dev)[:, None] + ar) & 0xFF).float() / 256.0
+    comm.barrier()
+
+    labels = args.labels
+    fan = [f for f in C5_FANOUT for _ in range(T)]  # [hop * T + etype]
+    L, Vt = len(C5_FANOUT), 2
+    lo_dev = (torch.arange(labels + 1, dtype=torch.int64) * BATCH).to(dev)
+    g = torch.Generator(device="cpu").manual_seed(4321 + rank)
+    n_sets = args.steps + args.warmup
+    seed_sets_ = [torch.randint(0, C5_NODES[0], (labels * BATCH,), generator=g).to(dev) for _ in range(n_sets)]
+    sampler = wgth.MultiHopSampler()
+    row_t = torch.tensor([0 if dt == "a" else 1 for _, dt in C5_EDGE_TYPES], device=dev)  # vertex type of the majors (CSR rows)
+    col_t = torch.tensor([0 if st == "a" else 1 for st, _ in C5_EDGE_TYPES], device=dev)
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1 = SAGEConv(FEAT_DIM, C5_HIDDEN)
+            self.c2 = SAGEConv(C5_HIDDEN, C5_CLASSES)
+
+        def forward(self, x, indptr, indices, indptr_t, indices_t):
+            h = torch.relu(self.c1(x, indptr, indices, (indptr_t, indices_t)))
+            return self.c2(h, indptr, indices, (indptr_t, indices_t))
+
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = True  # the dense layers are the model's business (cuBLAS), not this repo's kernels
+    net = Net().to(dev)
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local_rank]) if world > 1 else net
+    opt = torch.optim.SGD(model.parameters(), lr=0.01)
+    n_params = sum(p.numel() for p in net.parameters())
+
+    def build_block(res):
+        """typed local ids -> row numbers of the gathered feature matrix (= positions in the concatenated renumber maps,
+        segment (label, vertex type) at renumber_map_offsets[label * Vt + vtype]), then a CSR by destination."""
+        ltho, rmo = res["label_type_hop_offsets"], res["renumber_map_offsets"]
+        E = int(res["minors"].numel())
+        group = torch.searchsorted(ltho[1:].contiguous(), torch.arange(E, device=dev), right=True)  # edge -> (label, type, hop)
+        lab, typ = group // (T * L), (group // L) % T
+        dst = rmo[lab * Vt + row_t[typ]] + res["majors"]
+        src = rmo[lab * Vt + col_t[typ]] + res["minors"]
+        n = int(res["renumber_map"].numel())
+        order = torch.argsort(dst)
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        indptr[1:] = torch.bincount(dst, minlength=n).cumsum(0)
+        indices = src[order].to(torch.int32).contiguous()
+        return (indptr, indices) + csr_transpose(indptr, indices, n) + (n,)  # + the reversed block for the backward pass
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(k, marks=None, sync_grads=True):
+        def mark():
+            if marks is not None:
+                e = ev()
+                e.record()
+                marks.append(e)
+
+        mark()
+        res = sampler.sample_hetero(wm_rps, wm_cols, vto, seed_sets_[k], lo_dev, fan, SAMPLER_SEED + 7 * k, int64_ids=True)
+        mark()
+        x = emb.gather(res["renumber_map"])
+        mark()
+        indptr, indices, indptr_t, indices_t, n = build_block(res)
+        mark()
+        out = model(x, indptr, indices, indptr_t, indices_t)
+        # "labels": a closed form of the global id, on the seed rows of every mini-batch (first rows of each (label, "a") segment)
+        seed_rows = (res["renumber_map_offsets"][0::Vt][:-1, None] if Vt > 1 else res["renumber_map_offsets"][:-1, None])
+        seed_rows = (seed_rows + torch.arange(BATCH, device=dev)[None, :]).reshape(-1)
+        seed_rows = seed_rows[seed_rows < n]
+        target = res["renumber_map"][seed_rows] % C5_CLASSES
+        loss = torch.nn.functional.cross_entropy(out[seed_rows], target)
+        mark()
+        opt.zero_grad(set_to_none=True)
+        if world == 1 or sync_grads == "ddp":
+            loss.backward()  # DDP: the reducer's bucketed NCCL all-reduce runs inside backward
+        else:
+            with model.no_sync():
+                loss.backward()
+            if sync_grads:  # one NCCL all-reduce of the flattened dense gradients (what DDP's single bucket holds)
+                flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+                dist.all_reduce(flat)
+                flat /= world
+                off = 0
+                for p in net.parameters():
+                    p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+        opt.step()
+        mark()
+        return int(res["minors"].numel()), n, loss
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()  # before the warm-up: nvidia-smi takes a few hundred ms to come up and must not do that inside the timed region
+    for w in range(args.warmup):
+        step(w)
+    # Block sizes differ from call group to call group; the first time a step needs a larger activation block than any
+    # before, torch's caching allocator goes to cudaMalloc, which takes tens of ms once NCCL has enabled peer access
+    # (measured: 40 ms backward on first sight of a shape against 10.5 ms afterwards).  A training run sees every shape
+    # within a few steps; a 10-step measurement would time the allocator, so the timed call groups pass once untimed.
+    for k in range(args.steps):
+        step(args.warmup + k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = int(launch_count())
+    marks = []
+    t_b, t_e = ev(), ev()
+    torch.cuda.synchronize()
+    t_b.record()
+    edges = nodes = 0
+    for k in range(args.steps):
+        e, n, loss = step(args.warmup + k, marks)
+        edges += e
+        nodes += n
+    t_e.record()
+    torch.cuda.synchronize()
+    ms_total = t_b.elapsed_time(t_e)
+    launches = int(launch_count()) - launches0
+    names = ["sample_renumber", "gather", "block_build_torch", "forward_aggregation_dense", "backward_allreduce_optimizer"]
+    stage = [0.0] * 5
+    for k in range(args.steps):
+        m = marks[6 * k: 6 * k + 6]
+        for j in range(5):
+            stage[j] += m[j].elapsed_time(m[j + 1])
+        log("[rank %d] step %d: %s" % (rank, k, " ".join("%.2f" % m[j].elapsed_time(m[j + 1]) for j in range(5))))
+    # the same steps (a) without any gradient all-reduce and (b) with DDP's own reducer doing it inside backward
+    nosync_bwd = ddp_bwd = 0.0
+    if world > 1:
+        for mode in (False, "ddp"):
+            dist.barrier()
+            m2 = []
+            for k in range(args.steps):
+                step(args.warmup + k, m2, sync_grads=mode)
+            torch.cuda.synchronize()
+            t = sum(m2[6 * k + 4].elapsed_time(m2[6 * k + 5]) for k in range(args.steps)) / args.steps
+            if mode == "ddp":
+                ddp_bwd = t
+            else:
+                nosync_bwd = t
+    # the aggregation kernel by itself on the last step's block (first layer: 128-wide rows)
+    from pylibwholegraph.torch.aggregate import csr_aggregate_forward
+    res = sampler.sample_hetero(wm_rps, wm_cols, vto, seed_sets_[-1], lo_dev, fan, SAMPLER_SEED, int64_ids=True)
+    xg = emb.gather(res["renumber_map"])
+    indptr, indices, indptr_t, indices_t, n_blk = build_block(res)
+    gh = torch.randn((n_blk, C5_HIDDEN), device=dev)
+    csr_aggregate_forward(indptr_t, indices_t, gh, "sum")
+    b0, b1 = ev(), ev()
+    b0.record()
+    for _ in range(3):
+        csr_aggregate_forward(indptr_t, indices_t, gh, "sum")
+    b1.record()
+    torch.cuda.synchronize()
+    agg_bwd_ms = b0.elapsed_time(b1) / 3
+    max_in, max_out = int((indptr[1:] - indptr[:-1]).max()), int((indptr_t[1:] - indptr_t[:-1]).max())
+    del gh, indptr_t, indices_t
+    csr_aggregate_forward(indptr, indices, xg, "mean")
+    g0, g1 = ev(), ev()
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(10):
+        csr_aggregate_forward(indptr, indices, xg, "mean")
+    g1.record()
+    torch.cuda.synchronize()
+    agg_ms = g0.elapsed_time(g1) / 10
+    agg_bytes = int(indices.numel()) * (FEAT_DIM * 4 + 4) + n_blk * FEAT_DIM * 4
+    del xg, indptr, indices
+    # the all-reduce by itself: a tensor of the model's size, K times
+    ar_ms = 0.0
+    if world > 1:
+        buf = torch.zeros(n_params, device=dev)
+        dist.all_reduce(buf)
+        a0, a1 = ev(), ev()
+        torch.cuda.synchronize()
+        a0.record()
+        for _ in range(args.steps):
+            dist.all_reduce(buf)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = a0.elapsed_time(a1) / args.steps
+    clock_info = clocks.stop() if rank == 0 else None
+    stats = torch.tensor([ms_total, ar_ms, nosync_bwd, ddp_bwd] + stage, dtype=torch.float64, device=dev)
+    counts = torch.tensor([edges, nodes], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    ms_total, ar_ms, nosync_bwd, ddp_bwd = stats[0].item(), stats[1].item(), stats[2].item(), stats[3].item()
+    stage = stats[4:].tolist()
+    edges, nodes = counts.tolist()
+    if rank == 0:
+        out = {
+            "metric": "sampled_edges_per_sec (heterogeneous multi-hop sample + renumber + feature gather + SAGE step, per-type fanout [10,10])",
+            "value": edges / (ms_total * 1e-3), "unit": "edges/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64 ids (int32 col_idx in the CSRs), fp32 features and model", "data": "synthetic",
+            "config": {"workload": C5_WORKLOAD, "labels_per_step_per_gpu": labels, "seeds_per_label": BATCH, "edge_types": ["%s->%s" % et for et in C5_EDGE_TYPES],
+                       "h_fan_out": fan, "graph": "3 CSRs over one id space, replicated per GPU", "features": "chunked over %d GPU(s), in-kernel P2P gather" % world,
+                       "model": "2-layer GraphSAGE %d-%d-%d (pylibwholegraph.torch.SAGEConv), %d dense parameters, %s" % (
+                           FEAT_DIM, C5_HIDDEN, C5_CLASSES, n_params, "DistributedDataParallel (NCCL)" if world > 1 else "single process"),
+                       "nccl_ranks": world},
+            "stages_ms_per_step": {nm: v / args.steps for nm, v in zip(names, stage)},
+            "aggregation_kernel_alone": {"ms": agg_ms, "algorithmic_gbs": agg_bytes / (agg_ms * 1e-3) / 1e9,
+                                         "note": "csr_aggregate (mean) over the whole sampled block, 128-wide fp32 rows, rank 0's last block",
+                                         "backward_as_gather_over_reversed_block_ms_256_wide": agg_bwd_ms,
+                                         "max_row_degree": max_in, "max_row_degree_reversed": max_out},
+            "allreduce_alone_ms": ar_ms, "allreduce_bytes": n_params * 4, "backward_ms_without_allreduce (no_sync)": nosync_bwd,
+            "backward_ms_with_ddp_reducer": ddp_bwd,
+            "gradient_sync": "timed steps: backward under DDP.no_sync() + ONE NCCL all-reduce of the flattened dense gradients; "
+                             "backward_ms_with_ddp_reducer = the same steps with DistributedDataParallel's own bucketed reducer" if world > 1 else "single process",
+            "edges_per_step_per_gpu": edges / args.steps / world, "nodes_gathered_per_step_per_gpu": nodes / args.steps / world,
+            "gather_gbs": FEAT_DIM * 4 * nodes / (stage[1] * 1e-3) / 1e9,
+            "final_loss": float(loss.detach()), "gpu_launches": launches, "clocks": clock_info,
+        }
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
@@ -755,9 +1039,14 @@ def main():
     ap.add_argument("--gather-sms", type=int, default=-1,
                     help="SM budget of the feature gather (reference knob `gather_sms`; grid = 8 CTAs x this many SMs, spread over all SMs); "
                          "-1 = every SM (default).  Experiment: 74 leaves half of every SM to the sampling kernels of the next call group")
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS),
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5"],
                     help="c4 (default, the shape the metric is quoted on: papers100M) | c2 (|V|=10M, |E|=160M) | headline (|V|=100M, |E|=1B, F=256) | tiny (harness self-test)")
     args = ap.parse_args()
+    if args.workload == "c5":
+        if args.labels == LABELS_PER_STEP:
+            args.labels = 32
+        args.warmup = max(args.warmup, 3)
+        return run_c5(args)
     if WORKLOADS[args.workload] is not None:
         globals().update(WORKLOADS[args.workload])
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

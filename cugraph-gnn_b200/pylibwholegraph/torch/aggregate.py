@@ -48,10 +48,25 @@ def csr_aggregate_forward(indptr, indices, x, reduce="mean", gather_map=None):
     return out
 
 
+def csr_transpose(indptr, indices, n_src):
+    """(indptr_T [n_src + 1], indices_T) of the block with the edges reversed (rows = sources, entries = destination rows),
+    int64 / int32: lets the backward pass of the aggregation run as a gather-reduce (the forward kernel, no atomics).
+    A few torch ops per block (host glue, built once per mini-batch block and shared by every layer)."""
+    n_dst = indptr.shape[0] - 1
+    deg = (indptr[1:] - indptr[:-1]).to(torch.int64)
+    dst = torch.repeat_interleave(torch.arange(n_dst, device=indptr.device), deg)
+    src = indices.to(torch.int64)
+    order = torch.argsort(src, stable=True)
+    indptr_t = torch.zeros(n_src + 1, dtype=torch.int64, device=indptr.device)
+    indptr_t[1:] = torch.bincount(src, minlength=n_src).cumsum(0)
+    return indptr_t, dst[order].to(torch.int32).contiguous()
+
+
 class _CsrAggregate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, indptr, indices, x, reduce):
-        ctx.save_for_backward(indptr, indices)
+    def forward(ctx, indptr, indices, x, reduce, transposed):
+        ctx.save_for_backward(indptr, indices, *(transposed if transposed is not None else ()))
+        ctx.has_t = transposed is not None
         ctx.reduce = reduce
         ctx.x_shape = x.shape
         ctx.x_dtype = x.dtype
@@ -59,18 +74,32 @@ class _CsrAggregate(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        indptr, indices = ctx.saved_tensors
+        if not ctx.needs_input_grad[2]:  # first layer: the gathered features carry no gradient
+            return None, None, None, None, None
+        saved = ctx.saved_tensors
+        indptr, indices = saved[0], saved[1]
         grad_out = grad_out.contiguous().float()
+        if ctx.has_t:
+            # gather-reduce over the reversed block: grad_x[s] = sum over edges (s -> d) of grad_out[d] (/ deg(d) for mean)
+            indptr_t, indices_t = saved[2], saved[3]
+            if _REDUCE[ctx.reduce] == 1:
+                deg = (indptr[1:] - indptr[:-1]).clamp(min=1).to(torch.float32)
+                grad_out = grad_out / deg[:, None]
+            if indptr_t.shape[0] - 1 != ctx.x_shape[0]:
+                raise ValueError("csr_transpose was built for %d source rows, x has %d" % (indptr_t.shape[0] - 1, ctx.x_shape[0]))
+            grad_x = csr_aggregate_forward(indptr_t, indices_t, grad_out, "sum")
+            return None, None, grad_x.to(ctx.x_dtype), None, None
         grad_x = torch.zeros(ctx.x_shape, device=grad_out.device, dtype=torch.float32)
         hs = [_h(indptr), _h(indices), _h(grad_out), _h(grad_x)]
         err = _bwd(hs[0][0], hs[1][0], hs[2][0], _REDUCE[ctx.reduce], hs[3][0], get_stream())
         wmb.check_wholememory_error_code(err)
-        return None, None, grad_x.to(ctx.x_dtype), None
+        return None, None, grad_x.to(ctx.x_dtype), None, None
 
 
-def csr_aggregate(indptr, indices, x, reduce="mean"):
-    """Differentiable (w.r.t. x) aggregation over a sampled CSR block."""
-    return _CsrAggregate.apply(indptr, indices, x, reduce)
+def csr_aggregate(indptr, indices, x, reduce="mean", transposed=None):
+    """Differentiable (w.r.t. x) aggregation over a sampled CSR block.  transposed = csr_transpose(indptr, indices,
+    x.shape[0]): the backward pass is then a second gather-reduce instead of an atomicAdd scatter."""
+    return _CsrAggregate.apply(indptr, indices, x, reduce, transposed)
 
 
 class SAGEConv(torch.nn.Module):
@@ -83,7 +112,7 @@ class SAGEConv(torch.nn.Module):
         self.lin_l = torch.nn.Linear(in_channels, out_channels, bias=bias)
         self.lin_r = torch.nn.Linear(in_channels, out_channels, bias=False)
 
-    def forward(self, x, indptr, indices):
+    def forward(self, x, indptr, indices, transposed=None):
         n_dst = indptr.shape[0] - 1
-        agg = csr_aggregate(indptr, indices, x, self.aggr)
+        agg = csr_aggregate(indptr, indices, x, self.aggr, transposed)
         return self.lin_l(agg.to(x.dtype)) + self.lin_r(x[:n_dst])
