@@ -691,19 +691,8 @@ def run_c5(args):
         loss = torch.nn.functional.cross_entropy(out[seed_rows], target)
         mark()
         opt.zero_grad(set_to_none=True)
-        if world == 1 or sync_grads == "ddp":
-            loss.backward()  # DDP: the reducer's bucketed NCCL all-reduce runs inside backward
-        else:
-            with model.no_sync():
-                loss.backward()
-            if sync_grads:  # one NCCL all-reduce of the flattened dense gradients (what DDP's single bucket holds)
-                flat = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
-                dist.all_reduce(flat)
-                flat /= world
-                off = 0
-                for p in net.parameters():
-                    p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                    off += p.numel()
+        with contextlib.nullcontext() if (sync_grads or world == 1) else model.no_sync():
+            loss.backward()  # DDP: the reducer's bucketed NCCL all-reduce of the dense weights runs inside backward
         opt.step()
         mark()
         return int(res["minors"].numel()), n, loss
@@ -743,20 +732,15 @@ def run_c5(args):
         for j in range(5):
             stage[j] += m[j].elapsed_time(m[j + 1])
         log("[rank %d] step %d: %s" % (rank, k, " ".join("%.2f" % m[j].elapsed_time(m[j + 1]) for j in range(5))))
-    # the same steps (a) without any gradient all-reduce and (b) with DDP's own reducer doing it inside backward
-    nosync_bwd = ddp_bwd = 0.0
+    # the same steps without the gradient all-reduce (DDP no_sync): the difference is what the collective costs on the timeline
+    nosync_bwd = 0.0
     if world > 1:
-        for mode in (False, "ddp"):
-            dist.barrier()
-            m2 = []
-            for k in range(args.steps):
-                step(args.warmup + k, m2, sync_grads=mode)
-            torch.cuda.synchronize()
-            t = sum(m2[6 * k + 4].elapsed_time(m2[6 * k + 5]) for k in range(args.steps)) / args.steps
-            if mode == "ddp":
-                ddp_bwd = t
-            else:
-                nosync_bwd = t
+        dist.barrier()
+        m2 = []
+        for k in range(args.steps):
+            step(args.warmup + k, m2, sync_grads=False)
+        torch.cuda.synchronize()
+        nosync_bwd = sum(m2[6 * k + 4].elapsed_time(m2[6 * k + 5]) for k in range(args.steps)) / args.steps
     # the aggregation kernel by itself on the last step's block (first layer: 128-wide rows)
     from pylibwholegraph.torch.aggregate import csr_aggregate_forward
     res = sampler.sample_hetero(wm_rps, wm_cols, vto, seed_sets_[-1], lo_dev, fan, SAMPLER_SEED, int64_ids=True)
@@ -798,13 +782,13 @@ def run_c5(args):
         torch.cuda.synchronize()
         ar_ms = a0.elapsed_time(a1) / args.steps
     clock_info = clocks.stop() if rank == 0 else None
-    stats = torch.tensor([ms_total, ar_ms, nosync_bwd, ddp_bwd] + stage, dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_total, ar_ms, nosync_bwd] + stage, dtype=torch.float64, device=dev)
     counts = torch.tensor([edges, nodes], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-    ms_total, ar_ms, nosync_bwd, ddp_bwd = stats[0].item(), stats[1].item(), stats[2].item(), stats[3].item()
-    stage = stats[4:].tolist()
+    ms_total, ar_ms, nosync_bwd = stats[0].item(), stats[1].item(), stats[2].item()
+    stage = stats[3:].tolist()
     edges, nodes = counts.tolist()
     if rank == 0:
         out = {
@@ -823,9 +807,6 @@ def run_c5(args):
                                          "backward_as_gather_over_reversed_block_ms_256_wide": agg_bwd_ms,
                                          "max_row_degree": max_in, "max_row_degree_reversed": max_out},
             "allreduce_alone_ms": ar_ms, "allreduce_bytes": n_params * 4, "backward_ms_without_allreduce (no_sync)": nosync_bwd,
-            "backward_ms_with_ddp_reducer": ddp_bwd,
-            "gradient_sync": "timed steps: backward under DDP.no_sync() + ONE NCCL all-reduce of the flattened dense gradients; "
-                             "backward_ms_with_ddp_reducer = the same steps with DistributedDataParallel's own bucketed reducer" if world > 1 else "single process",
             "edges_per_step_per_gpu": edges / args.steps / world, "nodes_gathered_per_step_per_gpu": nodes / args.steps / world,
             "gather_gbs": FEAT_DIM * 4 * nodes / (stage[1] * 1e-3) / 1e9,
             "final_loss": float(loss.detach()), "gpu_launches": launches, "clocks": clock_info,

@@ -33,7 +33,7 @@ from .tensor import (
 )
 from . import wholememory_ops, wholegraph_ops, graph_ops
 from .multihop import MultiHopSampler, multihop_neighbor_sample
-from .aggregate import csr_aggregate, csr_aggregate_forward, SAGEConv
+from .aggregate import csr_aggregate, csr_aggregate_forward, csr_transpose, sage_layer_forward, SAGEConv
 
 from .common_options import (
     add_training_options,

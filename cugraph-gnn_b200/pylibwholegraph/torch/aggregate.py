@@ -116,3 +116,39 @@ class SAGEConv(torch.nn.Module):
         n_dst = indptr.shape[0] - 1
         agg = csr_aggregate(indptr, indices, x, self.aggr, transposed)
         return self.lin_l(agg.to(x.dtype)) + self.lin_r(x[:n_dst])
+
+    def forward_fused(self, x, indptr, indices):
+        """Inference form of forward() for bf16 rows of width 128 with mean aggregation: ONE kernel (csrc/sage_tile.cu) --
+        warp-per-row gather-mean written straight into the shared-memory operand tile, [mean || self] . [W_l || W_r]^T on the
+        tensor cores (tcgen05.mma, accumulator in tensor memory), bias added in the epilogue.  fp32 result [n_dst, out]."""
+        if self.aggr != "mean":
+            raise ValueError("the fused layer implements mean aggregation")
+        w_cat = torch.cat([self.lin_l.weight, self.lin_r.weight], dim=1).detach().to(torch.bfloat16).contiguous()
+        bias = self.lin_l.bias.detach().float() if self.lin_l.bias is not None else None
+        return sage_layer_forward(indptr, indices, x, w_cat, bias)
+
+
+_sage = wmb.native_symbol("wholegraph_sage_layer_forward")
+_sage.restype = ctypes.c_int
+_sage.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp]
+
+
+def sage_layer_forward(indptr, indices, x, w_cat, bias=None):
+    """out[i] = [mean_{e in row i} x[indices[e]] || x[i]] . w_cat^T (+ bias), fp32 [n_dst, F_out]  (wholegraph_sage_layer_forward,
+    include/wholememory/b200_ops.h).  x: bf16 [n_src, 128], destination rows first; w_cat: bf16 [F_out, 256] = [W_l || W_r];
+    bias: fp32 [F_out] or None.  F_out is padded to a multiple of 16 here (the MMA's N granularity) and sliced back."""
+    if x.dtype != torch.bfloat16 or w_cat.dtype != torch.bfloat16:
+        raise TypeError("sage_layer_forward takes bf16 feature rows and bf16 weights (fp32 accumulation and output)")
+    f_out = w_cat.shape[0]
+    pad = (-f_out) % 16
+    if pad:
+        w_cat = torch.cat([w_cat, w_cat.new_zeros((pad, w_cat.shape[1]))], dim=0)
+        if bias is not None:
+            bias = torch.cat([bias, bias.new_zeros(pad)])
+    w_cat = w_cat.contiguous()
+    n_dst = indptr.shape[0] - 1
+    out = torch.empty((n_dst, f_out + pad), device=x.device, dtype=torch.float32)
+    hs = [_h(indptr), _h(indices), _h(x), _h(w_cat), _h(bias.contiguous() if bias is not None else None), _h(out)]
+    err = _sage(hs[0][0], hs[1][0], hs[2][0], hs[3][0], hs[4][0], hs[5][0], get_stream())
+    wmb.check_wholememory_error_code(err)
+    return out[:, :f_out] if pad else out

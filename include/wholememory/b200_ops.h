@@ -267,6 +267,25 @@ wholememory_error_code_t wholegraph_csr_aggregate_backward(wholememory_tensor_t 
                                                            wholememory_tensor_t grad_x,
                                                            void* stream);
 
+/**
+ * Fused GraphSAGE layer on a sampled CSR block, dense part on the tensor cores (csrc/sage_tile.cu: warp-per-row gather-mean
+ * into a shared-memory bf16 operand tile, W brought by TMA, tcgen05.mma with the accumulator in tensor memory):
+ *     out[i, :] = [ mean over e in [indptr[i], indptr[i+1]) of x[indices[e], :]  ||  x[i, :] ] . w_cat^T (+ bias)
+ * Replaces, for one layer, the aggregation kernel + two GEMMs of the reference's consumer
+ * (python/pylibwholegraph/pylibwholegraph/torch/gnn_model.py:119-125; PyG SAGEConv maths with aggr = "mean", root weight).
+ *   indptr int32 | int64 [n_dst + 1], indices int32 | int64 [nnz]: the sampler's CSR block; destination rows are the first
+ *   n_dst rows of x.   x bf16 [n_src, 128].   w_cat bf16 [F_out, 256] = [W_l || W_r], contiguous, F_out a multiple of 16 <= 256.
+ *   bias fp32 [F_out] or NULL.   out fp32 [n_dst, F_out].   All local device tensors.
+ * WHOLEMEMORY_NOT_IMPLEMENTED for other feature widths (use wholegraph_csr_aggregate + GEMMs).
+ */
+wholememory_error_code_t wholegraph_sage_layer_forward(wholememory_tensor_t indptr,
+                                                       wholememory_tensor_t indices,
+                                                       wholememory_tensor_t x,
+                                                       wholememory_tensor_t w_cat,
+                                                       wholememory_tensor_t bias,
+                                                       wholememory_tensor_t out,
+                                                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
