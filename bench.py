@@ -12,7 +12,7 @@ closed form table[i][d] = (i + d) & 0xFFFF (56.8 GB, striped over the GPUs of th
 so N = 1 runs it too.  --workload c2 | headline | c5 select the other shapes BASELINE.json names (c5: heterogeneous,
 with a DDP-wrapped 2-layer SAGE step so that the NCCL all-reduce of the dense weights is on the timeline).
 
-One step = one call group of 64 mini-batches ("labels") x 1024 seeds per GPU, i.e. what
+One step = one call group of 148 mini-batches ("labels": one per SM of a B200) x 1024 seeds per GPU, i.e. what
 cugraph_pyg.sampler.DistributedNeighborSampler hands to the native sampler in one call
 (python/cugraph-pyg/cugraph_pyg/sampler/distributed_sampler.py:877-908) followed by the feature fetch of
 every mini-batch (sampler/sampler.py:51-165 -> FeatureStore -> WholeMemoryEmbedding.gather):
@@ -52,7 +52,8 @@ NUM_EDGES = 1_600_000_000
 FEAT_DIM = 128
 FANOUT = [25, 10]
 BATCH = 1024
-LABELS_PER_STEP = 64
+LABELS_PER_STEP = 148  # mini-batches per call group (the reference's `local_seeds_per_call` / batch size): one label per SM -- the fused sampler
+                       # then runs one CTA per label (profiles/run_r2p.sh: 3.95 us per label against 5.3 at 64 labels per call)
 SAMPLER_SEED = 62
 RMAT = (0.57, 0.19, 0.19, 0.05)
 GATHER_TRAFFIC_FILE = "r1_gather_traffic.json"     # ncu --set full captures (per-unit DRAM bytes), refreshed per round
@@ -282,8 +283,10 @@ def run_ours(args):
     # found the overlap slower was taken before the per-stream allocator priming below and had cudaMalloc stalls in it.)
     use_side = True if args.gather_stream < 0 else bool(args.gather_stream)
     side = torch.cuda.Stream(device=dev) if use_side else None
-    n_metric = (labels * len(FANOUT) + 1) + (labels + 1) + labels * FEAT_DIM
-    host_ring = [torch.empty(n_metric, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    # what crosses back per step: label_hop_offsets and renumber_map_offsets (int64) + the first gathered row of every label (fp32);
+    # pinned, allocated once (cudaHostAlloc inside the loop stalls), three DMA copies per step and no conversion kernels
+    host_ring = [(torch.empty(labels * len(FANOUT) + 1, dtype=torch.int64, pin_memory=True), torch.empty(labels + 1, dtype=torch.int64, pin_memory=True),
+                  torch.empty((labels, FEAT_DIM), dtype=torch.float32, pin_memory=True)) for _ in range(4)]
     ring_pos = [0]
 
     dbg_events = []
@@ -304,10 +307,11 @@ def run_ours(args):
             x = emb.gather(res["renumber_map"])
             mark()
             first = x.index_select(0, res["renumber_map_offsets"][:-1])  # [labels, F]
-            metric = torch.cat([res["label_hop_offsets"].double(), res["renumber_map_offsets"].double(), first.double().reshape(-1)])
-            host = host_ring[ring_pos[0] % len(host_ring)]  # pinned, allocated once (cudaHostAlloc inside the loop stalls)
+            host = host_ring[ring_pos[0] % len(host_ring)]
             ring_pos[0] += 1
-            host.copy_(metric, non_blocking=True)
+            host[0].copy_(res["label_hop_offsets"], non_blocking=True)
+            host[1].copy_(res["renumber_map_offsets"], non_blocking=True)
+            host[2].copy_(first, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             mark()
@@ -332,12 +336,12 @@ def run_ours(args):
             if len(done) > 1:  # read the previous step's result on the host while this one runs
                 h0, ev0 = done.pop(0)
                 ev0.synchronize()
-                nbytes = h0[0].numel() * 8
-                assert h0[0][0] == 0.0
+                nbytes = sum(t.numel() * t.element_size() for t in h0[0])
+                assert int(h0[0][0][0]) == 0 and int(h0[0][1][0]) == 0
             pend = nxt
         for h0, ev0 in done:
             ev0.synchronize()
-            nbytes = h0[0].numel() * 8
+            nbytes = sum(t.numel() * t.element_size() for t in h0[0])
         return edges, nbytes
 
     dev_seeds = [s.to(dev) for s in host_seeds]

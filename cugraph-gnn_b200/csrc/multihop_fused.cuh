@@ -33,13 +33,17 @@ namespace wgb {
 namespace cg = cooperative_groups;
 
 #ifndef WGB_FZ_THREADS
-#define WGB_FZ_THREADS 896
+#define WGB_FZ_THREADS 1024
 #endif
 #ifndef WGB_FZ_ILP
 #define WGB_FZ_ILP 1
 #endif
-constexpr int kFzThreads            = WGB_FZ_THREADS;  // 28 warps x 64 registers: leaves 8 K registers of the SM, i.e. one 256-thread CTA
-                                                        // of the feature gather of the previous call group can sit beside it
+#ifndef WGB_FZ_BOUND
+#define WGB_FZ_BOUND 1024  // launch bound: the register cap of the kernel is 65536 / WGB_FZ_BOUND
+#endif
+constexpr int kFzThreads            = WGB_FZ_THREADS;  // 32 warps x 64 registers = the SM's register file.  Measured on C4 (profiles/
+                                                        // run_r2p.sh): 1024 threads 0.340 ms per 64-label call group, 896 0.357, 768 0.382, 640 0.385
+                                                        // (wider register budgets do not pay for the lost warps: the kernel is latency bound)
 constexpr unsigned int kFzPending   = 0x80000000u;
 constexpr unsigned long long kFzEmpty = ~0ULL;
 constexpr unsigned long long kFzFlagAgg = 1ULL << 62, kFzFlagPrefix = 2ULL << 62, kFzValMask = (1ULL << 62) - 1;
@@ -146,6 +150,10 @@ struct FzShared {
 
 constexpr int kFzDbgSlots = 32;
 constexpr int kFzIlp = WGB_FZ_ILP;  // items a thread keeps in flight per stage of a latency-bound loop
+#ifndef WGB_FZ_ILP_HASH
+#define WGB_FZ_ILP_HASH 1
+#endif
+constexpr int kFzIlpHash = WGB_FZ_ILP_HASH;  // the same, for the three per-hop loops over the hash table (re-insert, insert, local ids)
 
 struct FzCluster {
   FzShared* sh;
@@ -159,7 +167,7 @@ struct FzCluster {
     const unsigned int par = xround & 1u;
     xround++;
     if (threadIdx.x == 0) sh->xchg[par][0] = mine;
-    cg::this_cluster().sync();
+    sync();
     unsigned long long before = 0;
     total                     = 0;
     for (unsigned int r = 0; r < size; r++) {
@@ -169,7 +177,13 @@ struct FzCluster {
     }
     return before;
   }
-  __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+  // a one-CTA cluster (call groups of >= 74 labels: one label per SM) synchronises with the CTA barrier: no cluster-scope
+  // release (MEMBAR.ALL.GPU + barrier.cluster were 25 % of the kernel's stall samples at cluster size 2)
+  __device__ __forceinline__ void sync()
+  {
+    if (size == 1) __syncthreads();
+    else cg::this_cluster().sync();
+  }
 };
 
 // Ordered exclusive scan over n items spread over the cluster.  CTA c owns the contiguous chunk [c * chunk, (c+1) * chunk),
@@ -242,21 +256,22 @@ __device__ __forceinline__ unsigned int fz_ordered_scan(FzCluster& c, long long 
 }
 
 // a plain loop over n items of the cluster in the same staged form (no ordering between items)
-template <typename StA, typename StB, typename StC>
+template <int ILP = kFzIlp, typename StA, typename StB, typename StC>
 __device__ __forceinline__ void fz_for_each(const FzCluster& c, int n, StA sa, StB sb, StC sc)
 {
   const int CT = (int)c.size * kFzThreads, cti = (int)c.rank * kFzThreads + (int)threadIdx.x;
-  for (int i0 = cti; i0 < n; i0 += CT * kFzIlp) {
-    decltype(sa(0)) A[kFzIlp];
-    decltype(sb(0, A[0])) Bv[kFzIlp];
+#pragma unroll 1
+  for (int i0 = cti; i0 < n; i0 += CT * ILP) {
+    decltype(sa(0)) A[ILP];
+    decltype(sb(0, A[0])) Bv[ILP];
 #pragma unroll
-    for (int u = 0; u < kFzIlp; u++)
+    for (int u = 0; u < ILP; u++)
       if (i0 + CT * u < n) A[u] = sa(i0 + CT * u);
 #pragma unroll
-    for (int u = 0; u < kFzIlp; u++)
+    for (int u = 0; u < ILP; u++)
       if (i0 + CT * u < n) Bv[u] = sb(i0 + CT * u, A[u]);
 #pragma unroll
-    for (int u = 0; u < kFzIlp; u++)
+    for (int u = 0; u < ILP; u++)
       if (i0 + CT * u < n) sc(i0 + CT * u, Bv[u]);
   }
 }
@@ -338,7 +353,7 @@ __device__ __forceinline__ void fz_sample_rows(const FzArgs& a, FzCluster& c, co
 // launch bound 1024 (the CTA is kFzThreads = 896 wide): caps the kernel at 64 registers per thread, so that 28 warps take
 // 56 K of the SM's 64 K registers and the bulk-copy gather CTA (4 warps x 64) fits beside it
 template <typename ColT>
-__global__ void __launch_bounds__(1024, 1) fz_label_kernel(const __grid_constant__ FzArgs a)
+__global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_constant__ FzArgs a)
 {
   __shared__ FzShared sh;
   FzCluster c;
@@ -479,14 +494,14 @@ __global__ void __launch_bounds__(1024, 1) fz_label_kernel(const __grid_constant
         else if (M <= 16) fz_sample_rows<ColT, 16>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
         else fz_sample_rows<ColT, 32>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
       }
-      fz_for_each(
+      fz_for_each<kFzIlpHash>(
         c, known, [&](int j) -> unsigned int { return (unsigned int)Fl[j]; },
         [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v); },
         [&](int j, const FzProbe& pr) { fz_upsert(tb, nb, pr, (unsigned int)j); });
       c.sync();  // edges written, known vertices in the table
       FZ_T(T0 + 2);
       // P4: endpoints enter the table; the smallest edge index wins a new vertex
-      fz_for_each(
+      fz_for_each<kFzIlpHash>(
         c, e_h, [&](int i) -> unsigned int { return (unsigned int)destl[ebase + i]; },
         [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v); },
         [&](int i, const FzProbe& pr) { auxl[ebase + i] = fz_upsert(tb, nb, pr, kFzPending | (unsigned int)i); });
@@ -518,7 +533,7 @@ __global__ void __launch_bounds__(1024, 1) fz_label_kernel(const __grid_constant
       c.sync();  // ranks visible
       FZ_T(T0 + 4);
       // P6: endpoints -> local ids
-      fz_for_each(
+      fz_for_each<kFzIlpHash>(
         c, e_h, [&](int i) -> unsigned int { return auxl[ebase + i]; },
         [&](int, unsigned int ax) -> unsigned int { return (ax & kFzPending) ? rankl[ebase + (ax & ~kFzPending)] : 0u; },
         [&](int i, unsigned int rk) {

@@ -4,7 +4,7 @@
 //
 // Consumer replaced: pylibwholegraph/torch/gnn_model.py:119-125 of the reference (layer(sub_graph, x_feat, x_target_feat):
 // a scatter-add aggregation kernel, then two cuBLAS GEMMs, W_l on the aggregate and W_r on the target rows).  Here:
-//   * sparse side  = warp-per-row gather-mean (the same access pattern as aggregate.cu), fp32 accumulation in registers;
+//   * sparse side  = gather-mean, a quarter-warp per destination row (four rows per warp at once), fp32 accumulation in registers;
 //     the result never goes to HBM: it is written, as bf16, straight into the A operand tile in shared memory, in the
 //     K-major 128-byte-swizzled layout tcgen05.mma reads.  The mean is kept to ~16 bits of mantissa by splitting it into
 //     two bf16 terms (hi + lo), both multiplied by the same W_l tile, so the fp32 aggregation of the SIMT path survives the
@@ -14,7 +14,8 @@
 //     one elected thread issues 24 tcgen05.mma (M = 128, N = F_out, K = 16) per tile, accumulator in tensor memory
 //     (128 lanes x F_out fp32 columns), completion through tcgen05.commit -> mbarrier;
 //   * epilogue     = all 32 warps read the accumulator (tcgen05.ld 32x32b.x32: warp w owns lanes 32 (w % 4), columns
-//     32 (w / 4)), add the bias, and store fp32 rows.
+//     32 (w / 4)), add the bias, and store fp32 rows; tensor memory holds two accumulator stages, so the epilogue of tile
+//     t - 1 runs underneath the MMAs of tile t.
 // F_in = 128 (the feature width of every BASELINE config), F_out a multiple of 16 up to 256.
 // The kernel is bound by the gather (nnz x 256 B of bf16 rows from HBM/L2); the tensor-core work of a tile (25 MFLOP)
 // takes ~1 us.  What the fusion saves is the write + re-read of the aggregate and of the target rows and two launches.
@@ -34,7 +35,7 @@ constexpr int kKBlock    = 64;                                 // bf16 elements 
 constexpr int kABlocks   = 3 * kFin / kKBlock;                 // mean_hi | mean_lo | self
 constexpr int kBBlocks   = 2 * kFin / kKBlock;                 // W_l | W_r
 constexpr int kABlockBytes = kTileRows * 128;                  // 16 KB
-constexpr int kTmemCols  = 256;
+constexpr int kTmemCols  = 512;                                // two accumulator stages of 256 fp32 columns
 
 __device__ __forceinline__ unsigned int smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 
@@ -66,10 +67,6 @@ __device__ __forceinline__ unsigned int umma_idesc_bf16(int M, int N)
   return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned int)(N >> 3) << 17) | ((unsigned int)(M >> 4) << 24);
 }
 
-struct alignas(8) bf16x4 {
-  __nv_bfloat162 a, b;
-};
-
 // byte offset of (row r, bf16 element k) inside an A tile made of K-blocks of 64 elements, 128-byte swizzle:
 // the 16-byte chunk index of a row is XORed with the row's position in its 8-row group
 __device__ __forceinline__ unsigned int a_tile_offset(int r, int k)
@@ -79,6 +76,39 @@ __device__ __forceinline__ unsigned int a_tile_offset(int r, int k)
   return (unsigned int)(kb * kABlockBytes + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4) + (kk & 7) * 2);
 }
 
+// fp32 accumulation of eight bf16 values packed in a uint4 (a bf16 is the upper half of the fp32 with the same value)
+__device__ __forceinline__ void acc_bf16x8(float (&acc)[8], const uint4& v)
+{
+  acc[0] += __uint_as_float(v.x << 16); acc[1] += __uint_as_float(v.x & 0xFFFF0000u);
+  acc[2] += __uint_as_float(v.y << 16); acc[3] += __uint_as_float(v.y & 0xFFFF0000u);
+  acc[4] += __uint_as_float(v.z << 16); acc[5] += __uint_as_float(v.z & 0xFFFF0000u);
+  acc[6] += __uint_as_float(v.w << 16); acc[7] += __uint_as_float(v.w & 0xFFFF0000u);
+}
+
+// eight fp32 means -> hi (bf16 round-to-nearest) and lo (bf16 of the remainder): hi + lo carries ~16 bits of mantissa
+__device__ __forceinline__ void split_bf16x8(const float (&m)[8], uint4& hi, uint4& lo)
+{
+  unsigned int h[4], l[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const __nv_bfloat162 hh = __floats2bfloat162_rn(m[2 * c], m[2 * c + 1]);
+    const float2 hf         = __bfloat1622float2(hh);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(m[2 * c] - hf.x, m[2 * c + 1] - hf.y);
+    h[c] = *reinterpret_cast<const unsigned int*>(&hh);
+    l[c] = *reinterpret_cast<const unsigned int*>(&ll);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Persistent CTA, 32 warps, one 128-row tile per iteration:
+//   gather(t): a quarter-warp (8 lanes) per destination row, 4 rows per warp at once; lane q of the quarter owns feature
+//              columns [8q, 8q + 8) and [64 + 8q, 64 + 8q + 8) (two 16-byte chunks: one per 64-column K-block, so the 8 lanes of a
+//              row read 128 contiguous bytes per load instruction and write 128 contiguous swizzled bytes of the operand tile);
+//              the row's first 16 neighbour ids are prefetched one tile ahead (registers), so the critical path of a tile is one
+//              round of row reads, two neighbours (4 x 16 B per lane) in flight;
+//   mma(t)   : one thread, 24 tcgen05.mma into accumulator stage t & 1 (tensor memory holds two stages of 256 columns);
+//   epilogue(t - 1): runs while mma(t) executes -- the accumulator of the previous tile is read (tcgen05.ld), biased and stored.
 template <typename IdxT, typename PtrT>
 __global__ void __launch_bounds__(kThreads, 1) sage_tile_kernel(const __grid_constant__ CUtensorMap w_map, const PtrT* __restrict__ indptr,
                                                                 const IdxT* __restrict__ indices, const __nv_bfloat16* __restrict__ x,
@@ -91,13 +121,14 @@ __global__ void __launch_bounds__(kThreads, 1) sage_tile_kernel(const __grid_con
   unsigned char* sA = smem;                                     // kABlocks x 16 KB
   unsigned char* sB = smem + kABlocks * kABlockBytes;           // kBBlocks x (f_out x 128 B)
   const unsigned int b_block_bytes = (unsigned int)f_out * 128u;
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sB + kBBlocks * b_block_bytes);  // [0] W landed, [1] MMAs of a tile done
-  unsigned int* tmem_slot  = reinterpret_cast<unsigned int*>(bars + 2);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(sB + kBBlocks * b_block_bytes);  // [0] W landed, [1 + s] MMAs into stage s done
+  unsigned int* tmem_slot  = reinterpret_cast<unsigned int*>(bars + 3);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -122,61 +153,156 @@ __global__ void __launch_bounds__(kThreads, 1) sage_tile_kernel(const __grid_con
 
   const unsigned int idesc = umma_idesc_bf16(kTileRows, f_out);
   const long long n_tiles  = (n_dst + kTileRows - 1) / kTileRows;
-  unsigned int mma_parity  = 0;
-  bool w_ready             = false;
-  constexpr int kRowsPerWarp = kTileRows / (kThreads / 32);  // 4
-  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ---- sparse side: mean of the neighbour rows and the target row, as bf16, into the A tile -----------------------
-#pragma unroll 1
-    for (int j = 0; j < kRowsPerWarp; j++) {
-      const int r       = wid * kRowsPerWarp + j;
-      const long long i = tile * kTileRows + r;
-      float acc[4]      = {0.f, 0.f, 0.f, 0.f};
-      bf16x4 self;
-      self.a = self.b = __floats2bfloat162_rn(0.f, 0.f);
-      if (i < n_dst) {
-        const long long s = (long long)indptr[i], e = (long long)indptr[i + 1];
-        self = *reinterpret_cast<const bf16x4*>(x + i * x_stride + 4 * lane);
-        long long p = s;
-        for (; p + 4 <= e; p += 4) {  // four rows in flight per lane
-          bf16x4 v[4];
+  const int ql = lane & 7;                 // lane of the quarter-warp
+  const int r  = wid * 4 + (lane >> 3);    // the quarter's row of the tile
+  const __nv_bfloat16* xq = x + 8 * ql;    // this lane's two column chunks start here and 64 columns further
+
+  // row range and first 16 neighbour ids of this quarter's row of `tile` (lane ql holds ids ql and 8 + ql; -1: none)
+  auto row_range = [&](long long tile, long long& s, long long& e) {
+    const long long i = tile * kTileRows + r;
+    s = e = 0;
+    if (tile < n_tiles && i < n_dst) {
+      s = (long long)indptr[i];
+      e = (long long)indptr[i + 1];
+    }
+  };
+  auto first_ids = [&](long long s, long long e, int& i0, int& i1) {
+    i0 = s + ql < e ? (int)indices[s + ql] : -1;
+    i1 = s + 8 + ql < e ? (int)indices[s + 8 + ql] : -1;
+  };
+  auto epilogue = [&](long long tile, unsigned int stage) {
+    const int lane_grp = wid & 3, col0 = (wid >> 2) * 32;
+    if (col0 < f_out) {
+      unsigned int v[32];
+      const unsigned int taddr = tmem + ((unsigned int)(lane_grp * 32) << 16) + stage * 256u + (unsigned int)col0;
+      asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // v[c] = D[row = lane][col0 + c].  A row-per-lane store would touch 32 different 128-byte lines per instruction (half of
+      // the kernel's stall samples in the first version: LSU throttle).  Transpose the 32 x 32 block inside the warp (five
+      // butterfly rounds of 16 shuffles), after which v[r] = D[row r][col0 + lane] and every store instruction writes one
+      // 128-byte line; the bias of the lane's column rides along as a single register.
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-            v[u] = *reinterpret_cast<const bf16x4*>(x + (long long)indices[p + u] * x_stride + 4 * lane);
+      for (int sft = 16; sft >= 1; sft >>= 1) {
+        const bool upper = (lane & sft) != 0;
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const float2 a = __bfloat1622float2(v[u].a), b = __bfloat1622float2(v[u].b);
-            acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        for (int c = 0; c < 32; c++) {
+          if ((c & sft) == 0) {
+            const unsigned int send = upper ? v[c] : v[c + sft];
+            const unsigned int recv = __shfl_xor_sync(0xffffffffu, send, sft);
+            if (upper) v[c] = recv;
+            else v[c + sft] = recv;
           }
         }
-        for (; p < e; p++) {
-          const bf16x4 v = *reinterpret_cast<const bf16x4*>(x + (long long)indices[p] * x_stride + 4 * lane);
-          const float2 a = __bfloat1622float2(v.a), b = __bfloat1622float2(v.b);
-          acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-        }
-        const float inv = e > s ? 1.0f / (float)(e - s) : 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-          acc[c] *= inv;
       }
-      bf16x4 hi, lo;
-      hi.a = __floats2bfloat162_rn(acc[0], acc[1]);
-      hi.b = __floats2bfloat162_rn(acc[2], acc[3]);
-      const float2 ha = __bfloat1622float2(hi.a), hb = __bfloat1622float2(hi.b);
-      lo.a = __floats2bfloat162_rn(acc[0] - ha.x, acc[1] - ha.y);
-      lo.b = __floats2bfloat162_rn(acc[2] - hb.x, acc[3] - hb.y);
-      *reinterpret_cast<bf16x4*>(sA + a_tile_offset(r, 4 * lane))            = hi;
-      *reinterpret_cast<bf16x4*>(sA + a_tile_offset(r, kFin + 4 * lane))     = lo;
-      *reinterpret_cast<bf16x4*>(sA + a_tile_offset(r, 2 * kFin + 4 * lane)) = self;
+      const int col = col0 + lane;
+      if (col < f_out) {
+        const float bv      = bias ? bias[col] : 0.f;
+        const long long i0  = tile * kTileRows + lane_grp * 32;
+        float* o            = out + i0 * out_stride + col;
+#pragma unroll
+        for (int rr = 0; rr < 32; rr++)
+          if (i0 + rr < n_dst) o[(long long)rr * out_stride] = __uint_as_float(v[rr]) + bv;
+      }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+
+  long long s_cur, e_cur;
+  int id0, id1;
+  row_range((long long)blockIdx.x, s_cur, e_cur);
+  first_ids(s_cur, e_cur, id0, id1);
+  unsigned int it = 0;  // tiles this CTA has taken
+  long long prev_tile = -1;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+    const long long i = tile * kTileRows + r;
+    // the next tile's row range: in flight during this tile's gather
+    long long s_nxt, e_nxt;
+    row_range(tile + gridDim.x, s_nxt, e_nxt);
+    // the operand tile is free once the previous tile's MMAs have read it
+    if (it > 0) mbar_wait(&bars[1 + ((it - 1) & 1u)], ((it - 1) >> 1) & 1u);
+    // ---- sparse side: mean of the neighbour rows and the target row, as bf16, into the A tile -----------------------
+    {
+      float acc0[8], acc1[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++)
+        acc0[c] = acc1[c] = 0.f;
+      uint4 self0 = make_uint4(0, 0, 0, 0), self1 = self0;
+      const int deg = (int)(e_cur - s_cur);
+      if (i < n_dst) {
+        self0 = *reinterpret_cast<const uint4*>(xq + i * x_stride);
+        self1 = *reinterpret_cast<const uint4*>(xq + i * x_stride + 64);
+      }
+      int deg_max = deg;  // uniform trip count for the warp's four rows
+      deg_max = max(deg_max, __shfl_xor_sync(0xffffffffu, deg_max, 8));
+      deg_max = max(deg_max, __shfl_xor_sync(0xffffffffu, deg_max, 16));
+#pragma unroll 1
+      for (int base = 0; base < deg_max; base += 8) {
+        int mine;
+        if (base == 0) mine = id0;
+        else if (base == 8) mine = id1;
+        else mine = base + ql < deg ? (int)indices[s_cur + base + ql] : -1;
+#pragma unroll
+        for (int j = 0; j < 8; j += 4) {
+          if (base + j >= deg_max) break;  // warp-uniform
+          int nb[4];
+          uint4 lo4[4], hi4[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            nb[u] = __shfl_sync(0xffffffffu, mine, j + u, 8);
+#pragma unroll
+          for (int u = 0; u < 4; u++) {  // four neighbour rows (8 x 16 B per lane) in flight
+            lo4[u] = hi4[u] = make_uint4(0, 0, 0, 0);
+            if (nb[u] >= 0) {
+              const __nv_bfloat16* p = xq + (long long)nb[u] * x_stride;
+              lo4[u] = *reinterpret_cast<const uint4*>(p);
+              hi4[u] = *reinterpret_cast<const uint4*>(p + 64);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            acc_bf16x8(acc0, lo4[u]);
+            acc_bf16x8(acc1, hi4[u]);
+          }
+        }
+      }
+      const float inv = deg > 0 ? 1.0f / (float)deg : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        acc0[c] *= inv;
+        acc1[c] *= inv;
+      }
+      uint4 hi0, lo0, hi1, lo1;
+      split_bf16x8(acc0, hi0, lo0);
+      split_bf16x8(acc1, hi1, lo1);
+      *reinterpret_cast<uint4*>(sA + a_tile_offset(r, 8 * ql))                 = hi0;
+      *reinterpret_cast<uint4*>(sA + a_tile_offset(r, 64 + 8 * ql))            = hi1;
+      *reinterpret_cast<uint4*>(sA + a_tile_offset(r, kFin + 8 * ql))          = lo0;
+      *reinterpret_cast<uint4*>(sA + a_tile_offset(r, kFin + 64 + 8 * ql))     = lo1;
+      *reinterpret_cast<uint4*>(sA + a_tile_offset(r, 2 * kFin + 8 * ql))      = self0;
+      *reinterpret_cast<uint4*>(sA + a_tile_offset(r, 2 * kFin + 64 + 8 * ql)) = self1;
+    }
+    // the next tile's first neighbour ids: in flight during this tile's MMAs and the previous tile's epilogue
+    s_cur = s_nxt;
+    e_cur = e_nxt;
+    first_ids(s_cur, e_cur, id0, id1);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    // ---- dense side: 24 MMAs into tensor memory, issued by one thread ------------------------------------------------
+    // ---- dense side: 24 MMAs into tensor memory stage it & 1, issued by one thread ----------------------------------
     if (wid == 0) {
-      if (!w_ready) mbar_wait(&bars[0], 0);
+      if (it == 0) mbar_wait(&bars[0], 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
         int first = 1;
+        const unsigned int d_tmem = tmem + (it & 1u) * 256u;
 #pragma unroll
         for (int ab = 0; ab < kABlocks; ab++) {
           const int bb = ab < 4 ? (ab & 1) : ab - 2;  // mean_hi and mean_lo both meet W_l (B blocks 0, 1), self meets W_r (2, 3)
@@ -188,55 +314,28 @@ __global__ void __launch_bounds__(kThreads, 1) sage_tile_kernel(const __grid_con
             first                    = 0;
             // advancing 16 bf16 = 32 B along K inside the swizzled row: + 2 in the (address >> 4) field
             asm volatile(
-              "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem),
+              "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
               "l"(da + (unsigned long long)(2 * k)), "l"(db + (unsigned long long)(2 * k)), "r"(idesc), "r"(accum)
               : "memory");
           }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&bars[1])) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(&bars[1 + (it & 1u)])) : "memory");
       }
       __syncwarp();
     }
-    w_ready = true;
-    mbar_wait(&bars[1], mma_parity);
-    mma_parity ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    // ---- epilogue: accumulator -> registers -> out ----------------------------------------------------------------------
-    {
-      const int lane_grp = wid & 3, col0 = (wid >> 2) * 32;
-      if (col0 < f_out) {
-        unsigned int v[32];
-        const unsigned int taddr = tmem + ((unsigned int)(lane_grp * 32) << 16) + (unsigned int)col0;
-        asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-            "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-            "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const long long i = tile * kTileRows + lane_grp * 32 + lane;
-        if (i < n_dst) {
-          float* o = out + i * out_stride + col0;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            if (col0 + c < f_out) {  // f_out is a multiple of 16: whole groups of four
-              float4 w;
-              w.x = __uint_as_float(v[c]) + (bias ? bias[col0 + c] : 0.f);
-              w.y = __uint_as_float(v[c + 1]) + (bias ? bias[col0 + c + 1] : 0.f);
-              w.z = __uint_as_float(v[c + 2]) + (bias ? bias[col0 + c + 2] : 0.f);
-              w.w = __uint_as_float(v[c + 3]) + (bias ? bias[col0 + c + 3] : 0.f);
-              *reinterpret_cast<float4*>(o + c) = w;
-            }
-          }
-        }
-      }
+    // ---- epilogue of the PREVIOUS tile, underneath this tile's MMAs -------------------------------------------------
+    if (it > 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");  // (its MMAs were waited for before this tile's gather)
+      epilogue(prev_tile, (it - 1) & 1u);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();  // the accumulator and the A tile are free for the next tile
+    prev_tile = tile;
   }
+  if (it > 0) {
+    mbar_wait(&bars[1 + ((it - 1) & 1u)], ((it - 1) >> 1) & 1u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    epilogue(prev_tile, (it - 1) & 1u);
+  }
+  __syncthreads();
   if (wid == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
 }
 
@@ -300,7 +399,7 @@ wholememory_error_code_t wholegraph_sage_layer_forward(wholememory_tensor_t indp
     char* wp                = ptr_of(w_cat);
     float* op               = reinterpret_cast<float*>(ptr_of(out));
     const float* bp         = bias ? reinterpret_cast<const float*>(ptr_of(bias)) : nullptr;
-    WGB_EXPECTS(reinterpret_cast<unsigned long long>(xp) % 8 == 0 && xd->strides[0] % 4 == 0, "x rows must be 8-byte aligned");
+    WGB_EXPECTS(reinterpret_cast<unsigned long long>(xp) % 16 == 0 && xd->strides[0] % 8 == 0, "x rows must be 16-byte aligned");
     WGB_EXPECTS(reinterpret_cast<unsigned long long>(op) % 16 == 0 && od->strides[0] % 4 == 0, "out rows must be 16-byte aligned");
     WGB_EXPECTS(reinterpret_cast<unsigned long long>(wp) % 16 == 0 && wd->strides[0] == 2 * kFin, "W_cat must be contiguous and 16-byte aligned");
     CUtensorMap map;
@@ -312,6 +411,7 @@ wholememory_error_code_t wholegraph_sage_layer_forward(wholememory_tensor_t indp
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw cuda_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     const size_t smem = (size_t)kABlocks * kABlockBytes + (size_t)kBBlocks * f_out * 128 + 64 + 1024;
+    WGB_EXPECTS(xd->sizes[0] <= 0x7FFFFFFFLL, "the fused SAGE layer takes blocks of fewer than 2^31 source rows");
     const long long n_tiles = (n_dst + kTileRows - 1) / kTileRows;
     const int grid = (int)std::min<long long>(n_tiles, num_sms());
     cudaStream_t st = as_stream(stream);

@@ -1,7 +1,7 @@
 """Does the feature gather run underneath the sampler?  Times, with CUDA events and no host work in between:
   A  K x sampler kernels alone (begin only: fused label kernel + meta)       B  K x gather alone
   C  K x (sampler on stream 1 || gather on stream 2), launched back to back
-Perfect overlap: C = max(A, B); none: C = A + B.   argv: workload (c4 default), K"""
+Perfect overlap: C = max(A, B); none: C = A + B.   argv: workload (c4 default), K, labels per call group (comma-separated list, default 64)"""
 import os
 import sys
 import time
@@ -29,15 +29,8 @@ wm_col = wgth.create_wholememory_tensor(comm, "chunked", "cuda", [col.numel()], 
 wm_col.get_local_tensor()[0].copy_(col)
 del col
 emb = wgth.create_embedding(comm, "chunked", "cuda", torch.float32, [bench.NUM_NODES, bench.FEAT_DIM])
-labels = 64
-lo = (torch.arange(labels + 1, dtype=torch.int64) * bench.BATCH).to(dev)
-seeds = [s.to(dev) for s in bench.seed_sets(torch, K + 2, labels)]
-samplers = [wgth.MultiHopSampler() for _ in range(K + 2)]  # one object per call in flight: begin() only enqueues
-res = samplers[0].sample(wm_rp, wm_col, seeds[0], lo, bench.FANOUT, 62, int64_ids=True)
-ids = res["renumber_map"]
-x = emb.gather(ids)
+label_list = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [64]
 side = torch.cuda.Stream(device=dev)
-torch.cuda.synchronize()
 
 
 def timed(fn):
@@ -51,34 +44,44 @@ def timed(fn):
     return a.elapsed_time(b) / K
 
 
-def sampler_only():
-    pend = [samplers[k + 1].sample_async(wm_rp, wm_col, seeds[k + 1], lo, bench.FANOUT, 62 + k, int64_ids=True) for k in range(K)]
-    return pend
+for labels in label_list:
+  lo = (torch.arange(labels + 1, dtype=torch.int64) * bench.BATCH).to(dev)
+  seeds = [s.to(dev) for s in bench.seed_sets(torch, K + 2, labels)]
+  samplers = [wgth.MultiHopSampler() for _ in range(K + 2)]  # one object per call in flight: begin() only enqueues
+  res = samplers[0].sample(wm_rp, wm_col, seeds[0], lo, bench.FANOUT, 62, int64_ids=True)
+  ids = res["renumber_map"]
+  x = emb.gather(ids)
+  torch.cuda.synchronize()
 
 
-def gather_only():
-    with torch.cuda.stream(side):
-        for _ in range(K):
-            emb.gather(ids)
+  def sampler_only():
+      pend = [samplers[k + 1].sample_async(wm_rp, wm_col, seeds[k + 1], lo, bench.FANOUT, 62 + k, int64_ids=True) for k in range(K)]
+      return pend
 
 
-def both():
-    pend = []
-    for k in range(K):
-        pend.append(samplers[k + 1].sample_async(wm_rp, wm_col, seeds[k + 1], lo, bench.FANOUT, 62 + k, int64_ids=True))
-        with torch.cuda.stream(side):
-            emb.gather(ids)
-    return pend
+  def gather_only():
+      with torch.cuda.stream(side):
+          for _ in range(K):
+              emb.gather(ids)
 
 
-for name in ("warm", "run"):
-    keep = []
-    side.wait_stream(torch.cuda.current_stream())
-    A = timed(lambda: keep.append(sampler_only()))
-    [p.result() for p in keep[-1]]
-    B = timed(gather_only)
-    C = timed(lambda: keep.append(both()))
-    [p.result() for p in keep[-1]]
-    if name == "run":
-        print("bulk=%s  sampler alone %.3f ms   gather alone %.3f ms   both %.3f ms   (sum %.3f, max %.3f)  overlap efficiency %.2f" % (
-            os.environ.get("WGB_GATHER_BULK", "1"), A, B, C, A + B, max(A, B), (A + B - C) / min(A, B)))
+  def both():
+      pend = []
+      for k in range(K):
+          pend.append(samplers[k + 1].sample_async(wm_rp, wm_col, seeds[k + 1], lo, bench.FANOUT, 62 + k, int64_ids=True))
+          with torch.cuda.stream(side):
+              emb.gather(ids)
+      return pend
+
+
+  for name in ("warm", "run"):
+      keep = []
+      side.wait_stream(torch.cuda.current_stream())
+      A = timed(lambda: keep.append(sampler_only()))
+      [p.result() for p in keep[-1]]
+      B = timed(gather_only)
+      C = timed(lambda: keep.append(both()))
+      [p.result() for p in keep[-1]]
+      if name == "run":
+          print("labels=%d bulk=%s  sampler alone %.3f ms   gather alone %.3f ms   both %.3f ms   (sum %.3f, max %.3f)  overlap efficiency %.2f  | sampler us per label %.2f" % (
+              labels, os.environ.get("WGB_GATHER_BULK", "1"), A, B, C, A + B, max(A, B), (A + B - C) / min(A, B), 1e3 * A / labels))
