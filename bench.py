@@ -56,7 +56,7 @@ LABELS_PER_STEP = 148  # mini-batches per call group (the reference's `local_see
                        # then runs one CTA per label (profiles/run_r2p.sh: 3.95 us per label against 5.3 at 64 labels per call)
 SAMPLER_SEED = 62
 RMAT = (0.57, 0.19, 0.19, 0.05)
-GATHER_TRAFFIC_FILE = "r1_gather_traffic.json"     # ncu --set full captures (per-unit DRAM bytes), refreshed per round
+GATHER_TRAFFIC_FILE = {"register": "r1_gather_traffic.json", "bulk": "r2_gather_bulk_traffic.json"}  # ncu captures (per-unit DRAM bytes) per gather kernel
 SAMPLER_TRAFFIC_FILE = "r2_sampler_traffic.json"
 SCRAMBLE_MUL, SCRAMBLE_ADD = 7_919_717, 1_234_567  # multiplier coprime with every |V| used here (odd, not a multiple of 3 or 5)
 WORKLOAD = "C4 ogbn-papers100M-shape synthetic RMAT |V|=111M |E|=1.6B fanout=[25,10] feat_dim=128 fp32, sampler+renumber+gather"
@@ -480,9 +480,11 @@ def run_ours(args):
             except Exception:
                 return None, None
 
+        env_bulk = os.environ.get("WGB_GATHER_BULK", "")
+        gather_is_bulk = (env_bulk != "0") if env_bulk else world == 1  # the library's dispatch rule (gather_scatter.cu: bulk_enabled)
         rows_per_rank = tot_nodes / world
         edges_per_rank = tot_edges / world
-        traffic, traffic_src = captured(GATHER_TRAFFIC_FILE, "rows_in_launch", rows_per_rank / args.steps)
+        traffic, traffic_src = captured(GATHER_TRAFFIC_FILE["bulk" if gather_is_bulk else "register"], "rows_in_launch", rows_per_rank / args.steps)
         gather_alg_bytes = (2 * row_bytes + 8) * rows_per_rank  # per rank, all steps
         gather_achieved = gather_alg_bytes / (gather_ms * 1e-3) / 1e9
         # sampler algorithmic bytes (pylibcugraph shape = what this run returns): per sampled edge col 8 (4 read here:
@@ -524,9 +526,14 @@ def run_ours(args):
                 "nodes_gathered_per_step_per_gpu": tot_nodes / args.steps / world,
                 "sample_stage_edges_per_sec_per_gpu": tot_edges / world / (sample_ms * 1e-3),
             },
-            "roofline": {"kernel": "rows_copy_kernel (feature gather)", "bound": "hbm", "achieved": gather_achieved, "peak": hbm_peak,
+            "roofline": {"kernel": "feature gather: %s" % ("rows_bulk_gather_kernel (cp.async.bulk rings, local table)" if gather_is_bulk
+                                                             else "rows_copy_kernel (register path, striped table + hot-row replica)"),
+                         "bound": "hbm", "achieved": gather_achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": gather_achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
-                         "algorithmic_bytes_per_launch": gather_alg_bytes / args.steps, "peak_source": peak_src},
+                         "algorithmic_bytes_per_launch": gather_alg_bytes / args.steps, "peak_source": peak_src,
+                         "timed": "CUDA events on the gather's stream inside the timed region, where the next call group's sampler kernel runs beside it",
+                         "achieved_alone": gather_alg_bytes / (gather_alone_ms * 1e-3) / 1e9, "frac_alone": gather_alg_bytes / (gather_alone_ms * 1e-3) / 1e9 / hbm_peak,
+                         "alone": "the same launches in the separate synchronous pass (nothing else on the GPU)"},
             "roofline_sampler": {"kernel": "sampling + renumbering stage (all kernels of one MultiHopSampler call, synchronous pass)", "bound": "hbm",
                                  "achieved": sampler_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": sampler_achieved / hbm_peak,
                                  "traffic": s_traffic, "traffic_source": s_traffic_src,

@@ -387,18 +387,21 @@ static void launch_copy(const RowsOpArgs& a, int64_t row0, int64_t rows, unsigne
   WGB_CHECK_LAUNCH();
 }
 
-// Which same-dtype gathers go through the copy engine: those of callers that ask for it (WGB_GATHER_BULK=1; read per call).
-// Measured on C4 (profiles/r2k_*.json one GPU, profiles/r2l_*.json two GPUs): alone the bulk kernel is the faster one
-// (local table: 0.335 ms against 0.382 for 2.1 M rows of 512 B = 1.0 against 0.88 of the HBM peak; table striped over two
-// GPUs, no replica: 0.846 against 0.865 ms = 0.83 against 0.81 of the NVLink bound), but a loader runs the gather of call
-// group k beside the sampler of call group k+1, and there the register kernel is the better neighbour (step 0.642 against
-// 0.68-0.77 ms on one GPU, 0.811 against 0.900 on two): its CTAs only fit where the sampler leaves registers free, so it
-// fills the gaps of the sampler's stream, while the copy engine keeps HBM saturated and the latency-bound sampler pays.
-// So the register kernel stays the default; the bulk kernel is for gathers that have the GPU to themselves.
-static bool bulk_enabled(int /*world*/)
+// Which same-dtype gathers go through the copy engine: those of a table that is local to this GPU (world 1), unless
+// WGB_GATHER_BULK=0 / 1 says otherwise (read per call).
+// Measured on C4: alone the bulk kernel is the faster one -- local table, 148-label call groups (4.8 M rows of 512 B):
+// 0.758 ms against 0.853 = 1.0 against 0.89 of the HBM peak (profiles/r2s_bench_c4_bulk*.json); table striped over two GPUs,
+// no replica: 0.846 against 0.865 ms = 0.83 against 0.81 of the NVLink bound (profiles/r2l_*.json).  Inside a loader's
+// pipeline (gather of call group k beside the sampler of k+1) the two are within 1 % on one GPU at 148 labels per call group
+// (step 1.327 against 1.334 ms, end to end 1.411 against 1.443), while on two GPUs with the hot-row replica the register
+// kernel was the better neighbour of the sampler (0.811 against 0.900 ms per 64-label step): its CTAs only fit where the
+// sampler leaves registers free, while the copy engine keeps the memory system saturated and the latency-bound sampler pays.
+// So: local tables take the copy engine, striped tables the register kernel.
+static bool bulk_enabled(int world)
 {
   const char* e = getenv("WGB_GATHER_BULK");
-  return e && *e && atoi(e) != 0;
+  if (e && *e) return atoi(e) != 0;
+  return world == 1;
 }
 
 // Shared memory of the tile rings per CTA: 96 KB (2 warps x 3 tiles of 16 KB at 512-byte rows).  An SM that runs nothing

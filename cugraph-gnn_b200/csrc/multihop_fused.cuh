@@ -334,17 +334,29 @@ __device__ __forceinline__ void fz_sample_rows(const FzArgs& a, FzCluster& c, co
   const Affine lane_skip = affine_skip_loop((unsigned long long)g);
   int* Wg                = &c.sh->W[wib][sub * G];
   const int warps        = (int)c.size * (kFzThreads / 32);
-  for (int batch = (int)c.rank * (kFzThreads / 32) + wib; (long long)batch * 32 < n_rows; batch += warps) {
-    const int r         = batch * 32 + lane;
-    long long start_own = 0;
-    int N_own = 0, off_own = 0;
-    if (r < n_rows) {
+  // one lane per row reads the row's extent; the reads of batch k + 1 are issued before batch k is sampled, so the
+  // node -> row_ptr chain (two dependent reads, the second one random in DRAM) is off the critical path of every batch but the first
+  auto load_rows = [&](int batch, long long& start, int& N, int& off) {
+    const int r = batch * 32 + lane;
+    start       = 0;
+    N = off = 0;
+    if ((long long)batch * 32 < n_rows && r < n_rows) {
       const unsigned long long node = (unsigned long long)Fl[nbase + r];
-      start_own     = load_i64<false>(a.row_ptr, a.row_ptr_off + node);
+      start         = load_i64<false>(a.row_ptr, a.row_ptr_off + node);
       long long end = load_i64<false>(a.row_ptr, a.row_ptr_off + node + 1);
-      N_own         = (int)(end - start_own);
-      off_own       = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
+      N             = (int)(end - start);
+      off           = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
     }
+  };
+  int batch = (int)c.rank * (kFzThreads / 32) + wib;
+  long long start_nxt;
+  int N_nxt, off_nxt;
+  load_rows(batch, start_nxt, N_nxt, off_nxt);
+  for (; (long long)batch * 32 < n_rows; batch += warps) {
+    const int r               = batch * 32 + lane;
+    const long long start_own = start_nxt;
+    const int N_own = N_nxt, off_own = off_nxt;
+    load_rows(batch + warps, start_nxt, N_nxt, off_nxt);
     uniform_small_rows32<ColT, G, false>(a.col, a.col_off, M, seed, a.tab, lane_skip, Wg, lane, rowbase + r, nbase + r, start_own, N_own,
                                          off_own, sink);
   }
