@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(kBlock) rows_copy_kernel(ChunkRef table,
   }
 }
 
+#ifndef WGB_HOST_EMULATION  // the copy-engine path is PTX (cp.async.bulk, mbarrier): not part of the CPU logic check of tests/emu
 // ---- same-dtype gather as bulk-async copies (TMA) ---------------------------------------------------------
 // The register path above needs every thread slot and every register of an SM to keep ~64 KB of loads in flight
 // (256 threads x 8 CTAs x 4 x 16 B); while it runs, nothing else fits on the SM, so the sampler of the next call group
@@ -171,19 +172,22 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32) rows_bulk_gather_kernel(Ch
   unsigned long long pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 
-  auto source_of = [&](long long i, bool& ok) -> const char* {
-    long long r = i < n_rows ? (long long)idx[i] : -1;
-    ok          = r >= 0;
-    if (!ok) return nullptr;
-    if (HOT) {
-      const int hs = __ldg(hot.slot + r);
-      if (hs >= 0) return hot.rows + (unsigned long long)hs * hot.stride_bytes;
-    }
+  // Where a row comes from is a chain of dependent reads -- idx[i], then (HOT) the replica slot of that row, a random 4-byte
+  // read of a table-sized array -- before the copy can be issued.  Resolved at issue time, that chain (1.5-2 us) throttled every
+  // warp to one tile per chain: 1.06 ms against 0.76 for the same rows without the slot lookup (two GPUs, profiles/r2w_*).
+  // So the chain is software-pipelined over the ring's iterations: the tile taken by ticket in iteration k has its index read
+  // in k, its slot read in k + 1, and its copies issued in k + 2.
+  auto read_index = [&](long long tile) -> long long {
+    const long long i = tile * kBulkRows + lane;
+    return (tile < n_tiles && i < n_rows) ? (long long)idx[i] : -1;
+  };
+  auto read_slot = [&](long long r) -> int { return (HOT && r >= 0) ? __ldg(hot.slot + r) : -1; };
+  auto source_of = [&](long long r, int hs) -> const char* {
+    if (HOT && hs >= 0) return hot.rows + (unsigned long long)hs * hot.stride_bytes;
     return table.at<CHUNKED>(table_off_bytes + (unsigned long long)r * row_stride_bytes);
   };
-  auto issue_loads = [&](long long tile, int s) {
-    bool ok;
-    const char* src         = source_of(tile * kBulkRows + lane, ok);
+  auto issue_loads = [&](long long r, int hs, int s) {
+    const bool ok           = r >= 0;
     const unsigned int mask = __ballot_sync(0xffffffffu, ok);
     const unsigned int bar  = smem_u32(&bars[s]);
     if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(__popc(mask) * row_bytes) : "memory");
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32) rows_bulk_gather_kernel(Ch
     if (ok)
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                      smem_u32(ring + (size_t)s * tile_bytes + (size_t)lane * row_bytes)),
-                   "l"(src), "r"(row_bytes), "r"(bar), "l"(pol)
+                   "l"(source_of(r, hs)), "r"(row_bytes), "r"(bar), "l"(pol)
                    : "memory");
   };
 
@@ -220,17 +224,25 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32) rows_bulk_gather_kernel(Ch
       if (k == s) t = in_stage[k];
     return t;
   };
-  // prologue: stages - 1 tiles in flight
+  // prologue: stages - 1 tiles in flight (resolved on the spot), then the two look-ahead slots of the pipeline
   for (int k = 0; k < stages - 1; k++) {
     const long long t = next_tile();
     set_stage(k, t);
-    if (t < n_tiles) issue_loads(t, k);
+    if (t < n_tiles) {
+      const long long r = read_index(t);
+      issue_loads(r, read_slot(r), k);
+    }
   }
+  long long t1 = next_tile();            // its slot is read at the top of the first iteration
+  long long r1 = read_index(t1);
+  long long t2 = next_tile();            // its index is in flight
+  long long r2 = read_index(t2);
   int s = 0;
   unsigned int parity = 0;
   while (true) {
     const long long tile = get_stage(s);
     if (tile >= n_tiles) break;  // tickets are monotonic: every later stage holds nothing either
+    const int hs1 = read_slot(r1);  // in flight while this iteration waits for its tile
     // the tile's rows have landed
     const unsigned int bar = smem_u32(&bars[s]);
     asm volatile(
@@ -255,10 +267,14 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32) rows_bulk_gather_kernel(Ch
     // refill the stage the PREVIOUS tile left from: its store must have finished reading shared memory
     asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
     __syncwarp();
-    const int sp          = s == 0 ? stages - 1 : s - 1;
-    const long long ahead = next_tile();
-    set_stage(sp, ahead);
-    if (ahead < n_tiles) issue_loads(ahead, sp);
+    const int sp = s == 0 ? stages - 1 : s - 1;
+    set_stage(sp, t1);
+    if (t1 < n_tiles) issue_loads(r1, hs1, sp);
+    // rotate the look-ahead pipeline and take the next ticket
+    t1 = t2;
+    r1 = r2;
+    t2 = next_tile();
+    r2 = read_index(t2);
     if (++s == stages) {
       s = 0;
       parity ^= 1u;
@@ -266,6 +282,8 @@ __global__ void __launch_bounds__(kBulkMaxWarps * 32) rows_bulk_gather_kernel(Ch
   }
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+
+#endif  // WGB_HOST_EMULATION
 
 // ---- converting path -----------------------------------------------------------------------------
 // element conversion as the reference does it (gather_scatter_func.cuh:150-197): half / bf16 go
@@ -387,6 +405,7 @@ static void launch_copy(const RowsOpArgs& a, int64_t row0, int64_t rows, unsigne
   WGB_CHECK_LAUNCH();
 }
 
+#ifndef WGB_HOST_EMULATION
 // Which same-dtype gathers go through the copy engine: those of a table that is local to this GPU (world 1), unless
 // WGB_GATHER_BULK=0 / 1 says otherwise (read per call).
 // Measured on C4: alone the bulk kernel is the faster one -- local table, 148-label call groups (4.8 M rows of 512 B):
@@ -484,10 +503,14 @@ static bool try_bulk_gather(const RowsOpArgs& a)
   return true;
 }
 
+#endif  // WGB_HOST_EMULATION
+
 template <typename IdxT, bool SCATTER>
 static void run_copy(const RowsOpArgs& a)
 {
+#ifndef WGB_HOST_EMULATION
   if (!SCATTER && try_bulk_gather<IdxT>(a)) return;
+#endif
   size_t elt = dtype_size(a.table_desc.dtype);
   unsigned long long row_bytes = (unsigned long long)a.table_desc.sizes[1] * elt;
   unsigned long long dense_addr = reinterpret_cast<unsigned long long>(a.dense) + (unsigned long long)a.dense_desc.storage_offset * elt;

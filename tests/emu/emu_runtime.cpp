@@ -248,6 +248,9 @@ const Affine* skip_table_device()
 }
 #endif
 
+// runtime.cu drops an embedding's hot-row replica when its table is written; the emulated library has no embeddings
+void hot_rows_invalidate_for_tensor(wholememory_tensor_t) {}
+
 }  // namespace wgb
 
 extern "C" void emu_set_split_world(int w) { wgb::g_split_world = w; }
