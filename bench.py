@@ -273,8 +273,15 @@ def run_ours(args):
     # (sample_async on the second sampler object) before the host waits for the sizes of call group k.
     samplers = [sampler, wgth.MultiHopSampler()]
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def e2e_begin(k):
-        sd = host_seeds[k].to(dev, non_blocking=True)  # H2D of the step's input, from pinned memory
+        # H2D of the step's input, from pinned memory, on a copy stream of its own: it has no dependency, so it runs while the
+        # previous call group's sampler kernel is still busy instead of queueing behind it
+        with torch.cuda.stream(copy_stream):
+            sd = host_seeds[k].to(dev, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        sd.record_stream(torch.cuda.current_stream())
         return samplers[k & 1].sample_async(wm_rp, wm_col, sd, label_offsets, FANOUT, SAMPLER_SEED + 7 * k, int64_ids=True)
 
     # Feature fetch on its own stream: the next call group's sampling kernels (latency / random-access bound, little
@@ -481,7 +488,7 @@ def run_ours(args):
                 return None, None
 
         env_bulk = os.environ.get("WGB_GATHER_BULK", "")
-        gather_is_bulk = (env_bulk != "0") if env_bulk else world == 1  # the library's dispatch rule (gather_scatter.cu: bulk_enabled)
+        gather_is_bulk = env_bulk != "0"  # the library's dispatch rule (gather_scatter.cu: bulk_enabled)
         rows_per_rank = tot_nodes / world
         edges_per_rank = tot_edges / world
         traffic, traffic_src = captured(GATHER_TRAFFIC_FILE["bulk" if gather_is_bulk else "register"], "rows_in_launch", rows_per_rank / args.steps)
@@ -526,8 +533,8 @@ def run_ours(args):
                 "nodes_gathered_per_step_per_gpu": tot_nodes / args.steps / world,
                 "sample_stage_edges_per_sec_per_gpu": tot_edges / world / (sample_ms * 1e-3),
             },
-            "roofline": {"kernel": "feature gather: %s" % ("rows_bulk_gather_kernel (cp.async.bulk rings, local table)" if gather_is_bulk
-                                                             else "rows_copy_kernel (register path, striped table + hot-row replica)"),
+            "roofline": {"kernel": "feature gather: %s" % ("rows_bulk_gather_kernel (cp.async.bulk tile rings; local rows, replica rows and peer rows over NVLink)" if gather_is_bulk
+                                                             else "rows_copy_kernel (register path)"),
                          "bound": "hbm", "achieved": gather_achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": gather_achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": gather_alg_bytes / args.steps, "peak_source": peak_src,

@@ -406,21 +406,20 @@ static void launch_copy(const RowsOpArgs& a, int64_t row0, int64_t rows, unsigne
 }
 
 #ifndef WGB_HOST_EMULATION
-// Which same-dtype gathers go through the copy engine: those of a table that is local to this GPU (world 1), unless
-// WGB_GATHER_BULK=0 / 1 says otherwise (read per call).
-// Measured on C4: alone the bulk kernel is the faster one -- local table, 148-label call groups (4.8 M rows of 512 B):
-// 0.758 ms against 0.853 = 1.0 against 0.89 of the HBM peak (profiles/r2s_bench_c4_bulk*.json); table striped over two GPUs,
-// no replica: 0.846 against 0.865 ms = 0.83 against 0.81 of the NVLink bound (profiles/r2l_*.json).  Inside a loader's
-// pipeline (gather of call group k beside the sampler of k+1) the two are within 1 % on one GPU at 148 labels per call group
-// (step 1.327 against 1.334 ms, end to end 1.411 against 1.443), while on two GPUs with the hot-row replica the register
-// kernel was the better neighbour of the sampler (0.811 against 0.900 ms per 64-label step): its CTAs only fit where the
-// sampler leaves registers free, while the copy engine keeps the memory system saturated and the latency-bound sampler pays.
-// So: local tables take the copy engine, striped tables the register kernel.
-static bool bulk_enabled(int world)
+// Which same-dtype gathers go through the copy engine: all that qualify (16-byte aligned rows of at most 2 KB, >= 4096 rows),
+// unless WGB_GATHER_BULK=0 (read per call) sends them down the register path.
+// Measured on C4, 148-label call groups (4.85 M rows of 512 B per step):
+//   one GPU, local table     gather alone 0.758 ms (1.0 of the HBM peak) against 0.853 for the register kernel; pipelined step
+//                            1.327 against 1.334 ms, end to end 1.411 against 1.443                   (profiles/r2s_bench_c4_bulk*.json)
+//   two GPUs, 10 % replica   gather alone 0.986 against 1.265 ms; step 1.548 against 1.666, end to end 1.642 against 1.816
+//   two GPUs, no replica     0.83 against 0.78 of the NVLink bound                                   (profiles/r2x_bench_n2_bulk*.json)
+// (Round-2 history: with 64-label call groups and the index -> slot chain resolved at issue time the register kernel was the
+// better neighbour of the sampler on two GPUs, 0.811 against 0.900 ms per step, profiles/r2l_*.json; the software-pipelined
+// chain and one-CTA-per-label sampler calls reversed that.)
+static bool bulk_enabled(int /*world*/)
 {
   const char* e = getenv("WGB_GATHER_BULK");
-  if (e && *e) return atoi(e) != 0;
-  return world == 1;
+  return !(e && *e && atoi(e) == 0);
 }
 
 // Shared memory of the tile rings per CTA: 96 KB (2 warps x 3 tiles of 16 KB at 512-byte rows).  An SM that runs nothing

@@ -98,25 +98,65 @@ struct FzProbe {
   unsigned int v;
 };
 
-__device__ __forceinline__ void fz_load_bucket(const unsigned long long* __restrict__ tbl, unsigned int b, unsigned long long (&w)[4])
+// L2 residency.  With one label per SM the call group's scratch (~2 MB per label: tables, vertex and edge arrays) is 300 MB,
+// more than the 126 MB L2, and the random table traffic (probe, CAS, first-occurrence reads) ran at the rate of random DRAM
+// sectors: making the loops latency tolerant changed nothing (profiles/r2y_*).  The tables are what is touched at random and
+// repeatedly (0.46 MB per label at hop 2, 69 MB per call group), so every table access carries an evict-last policy and the
+// single-use random reads of the graph (col_idx) an evict-first one; the streamed scratch arrays keep the default.
+struct FzPolicy {
+  unsigned long long keep, stream;
+};
+__device__ __forceinline__ FzPolicy fz_make_policy()
 {
-  asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
-               : "l"(tbl + 4ULL * b)
-               : "memory");
+  FzPolicy p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  return p;
 }
 
-__device__ __forceinline__ FzProbe fz_probe(const unsigned long long* __restrict__ tbl, unsigned int nb, unsigned int v)
+__device__ __forceinline__ void fz_load_bucket(const unsigned long long* __restrict__ tbl, unsigned int b, unsigned long long (&w)[4],
+                                               unsigned long long pol)
+{
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+               : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3])
+               : "l"(tbl + 4ULL * b), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ unsigned long long fz_load_slot(const unsigned long long* p, unsigned long long pol)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fz_store_slot(unsigned long long* p, unsigned long long v, unsigned long long pol)
+{
+  asm volatile("st.global.L2::cache_hint.u64 [%0], %1, %2;" ::"l"(p), "l"(v), "l"(pol) : "memory");
+}
+// (atom.cas takes no cache hint -- ptxas: "Illegal modifier '.L2::cache_hint' for instruction 'atom'" -- unlike atom.add / red; the
+// sector it hits was brought in by the probe with the evict-last policy a moment earlier)
+__device__ __forceinline__ unsigned long long fz_cas_slot(unsigned long long* p, unsigned long long expect, unsigned long long desired,
+                                                          unsigned long long /*pol*/)
+{
+  return atomicCAS(p, expect, desired);
+}
+__device__ __forceinline__ void fz_min_aux(unsigned long long* slot, unsigned int v, unsigned long long pol)
+{
+  // little endian: the aux word is the low half of the slot
+  asm volatile("red.relaxed.gpu.global.min.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(reinterpret_cast<unsigned int*>(slot)), "r"(v), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ FzProbe fz_probe(const unsigned long long* __restrict__ tbl, unsigned int nb, unsigned int v, unsigned long long pol)
 {
   FzProbe p;
   p.v = v;
-  fz_load_bucket(tbl, fz_home(v, nb), p.w);
+  fz_load_bucket(tbl, fz_home(v, nb), p.w, pol);
   return p;
 }
 
 // claim-or-find `p.v` in a table of nb buckets, starting from its already loaded home bucket; the slot's aux after this
 // thread's visit is at most `mine`.  Returns the slot.
-__device__ __forceinline__ unsigned int fz_upsert(unsigned long long* __restrict__ tbl, unsigned int nb, FzProbe p, unsigned int mine)
+__device__ __forceinline__ unsigned int fz_upsert(unsigned long long* __restrict__ tbl, unsigned int nb, FzProbe p, unsigned int mine,
+                                                  unsigned long long pol)
 {
   const unsigned int v = p.v;
   unsigned int b       = fz_home(v, nb);
@@ -126,17 +166,16 @@ __device__ __forceinline__ unsigned int fz_upsert(unsigned long long* __restrict
     for (int j = 0; j < 4; j++) {
       unsigned long long cur = p.w[j];
       if (cur == kFzEmpty) {
-        cur = atomicCAS(&tbl[4ULL * b + j], kFzEmpty, fresh);
+        cur = fz_cas_slot(&tbl[4ULL * b + j], kFzEmpty, fresh, pol);
         if (cur == kFzEmpty) return 4u * b + j;
       }
       if ((unsigned int)(cur >> 32) == v) {
-        // little endian: the aux word is the low half of the slot
-        if ((unsigned int)cur > mine) atomicMin(reinterpret_cast<unsigned int*>(&tbl[4ULL * b + j]), mine);
+        if ((unsigned int)cur > mine) fz_min_aux(&tbl[4ULL * b + j], mine, pol);
         return 4u * b + j;
       }
     }
     b = b + 1 == nb ? 0u : b + 1;
-    fz_load_bucket(tbl, b, p.w);
+    fz_load_bucket(tbl, b, p.w, pol);
   }
 }
 
@@ -154,6 +193,29 @@ constexpr int kFzIlp = WGB_FZ_ILP;  // items a thread keeps in flight per stage 
 #define WGB_FZ_ILP_HASH 1
 #endif
 constexpr int kFzIlpHash = WGB_FZ_ILP_HASH;  // the same, for the three per-hop loops over the hash table (re-insert, insert, local ids)
+#ifndef WGB_FZ_ILP_SCAN
+#define WGB_FZ_ILP_SCAN 1
+#endif
+constexpr int kFzIlpScan = WGB_FZ_ILP_SCAN;  // 32-item chunks a warp keeps in flight in both passes of the ordered scans
+#ifndef WGB_FZ_INSERT_STREAM
+#define WGB_FZ_INSERT_STREAM 1  // 1: the three insert loops run lane-decoupled in a function of their own (fz_insert_stream); 0: FZ_HASH_LOOP
+#endif
+#ifndef WGB_FZ_SAMPLE_INLINE
+#define WGB_FZ_SAMPLE_INLINE 0
+#endif
+#if WGB_FZ_SAMPLE_INLINE
+#define FZ_SAMPLE_FN __forceinline__
+#else
+#define FZ_SAMPLE_FN __noinline__
+#endif
+#ifndef WGB_FZ_PIPE
+#define WGB_FZ_PIPE 1  // 1: those loops run software-pipelined (fz_for_each_pipe); 0: staged with kFzIlpHash items per thread
+#endif
+#if WGB_FZ_PIPE
+#define FZ_HASH_LOOP fz_for_each_pipe
+#else
+#define FZ_HASH_LOOP fz_for_each<kFzIlpHash>
+#endif
 
 struct FzCluster {
   FzShared* sh;
@@ -207,17 +269,18 @@ __device__ __forceinline__ unsigned int fz_ordered_scan(FzCluster& c, long long 
   const long long wbeg  = beg + wid * wlen < end ? beg + wid * wlen : end;
   const long long wend  = wbeg + wlen < end ? wbeg + wlen : end;
   unsigned int mine = 0;
-  for (long long i0 = wbeg + lane; i0 < wend; i0 += 32 * kFzIlp) {
-    decltype(sa(0LL)) A[kFzIlp];
-    decltype(sb(0LL, A[0])) Bv[kFzIlp];
+#pragma unroll 1
+  for (long long i0 = wbeg + lane; i0 < wend; i0 += 32 * kFzIlpScan) {
+    decltype(sa(0LL)) A[kFzIlpScan];
+    decltype(sb(0LL, A[0])) Bv[kFzIlpScan];
 #pragma unroll
-    for (int u = 0; u < kFzIlp; u++)
+    for (int u = 0; u < kFzIlpScan; u++)
       if (i0 + 32 * u < wend) A[u] = sa(i0 + 32 * u);
 #pragma unroll
-    for (int u = 0; u < kFzIlp; u++)
+    for (int u = 0; u < kFzIlpScan; u++)
       if (i0 + 32 * u < wend) Bv[u] = sb(i0 + 32 * u, A[u]);
 #pragma unroll
-    for (int u = 0; u < kFzIlp; u++)
+    for (int u = 0; u < kFzIlpScan; u++)
       if (i0 + 32 * u < wend) mine += sc(i0 + 32 * u, Bv[u]);
   }
 #pragma unroll
@@ -240,17 +303,27 @@ __device__ __forceinline__ unsigned int fz_ordered_scan(FzCluster& c, long long 
   const unsigned int wbase = c.sh->warp[wid];
   unsigned long long total;
   unsigned int carry = (unsigned int)c.exchange((unsigned long long)c.sh->warp[32], total) + wbase;  // (barrier: warp[] is free again)
-  for (long long i0 = wbeg; i0 < wend; i0 += 32) {
-    const long long i    = i0 + lane;
-    const unsigned int v = i < wend ? again(i) : 0u;
-    unsigned int inc     = v;
+#pragma unroll 1
+  for (long long i0 = wbeg; i0 < wend; i0 += 32 * kFzIlpScan) {
+    unsigned int vs[kFzIlpScan];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned int y = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += y;
+    for (int u = 0; u < kFzIlpScan; u++) {  // the reads of kFzIlpScan chunks are in flight together
+      const long long i = i0 + 32 * u + lane;
+      vs[u]             = i < wend ? again(i) : 0u;
     }
-    if (i < wend) out(i, carry + inc - v, v);
-    carry += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+    for (int u = 0; u < kFzIlpScan; u++) {
+      const long long i    = i0 + 32 * u + lane;
+      const unsigned int v = vs[u];
+      unsigned int inc     = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned int y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+      }
+      if (i < wend) out(i, carry + inc - v, v);
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
   }
   return (unsigned int)total;
 }
@@ -273,6 +346,93 @@ __device__ __forceinline__ void fz_for_each(const FzCluster& c, int n, StA sa, S
 #pragma unroll
     for (int u = 0; u < ILP; u++)
       if (i0 + CT * u < n) sc(i0 + CT * u, Bv[u]);
+  }
+}
+
+// The same loop, software-pipelined: while item i runs its last (longest) stage -- the compare-and-swap chain of an insert --
+// the bucket of item i + CT is already being read and the value of item i + 2 CT is on its way, so an iteration exposes one
+// round trip instead of three.  (Running two items in lock step instead, WGB_FZ_ILP_HASH = 2, did not pay: 0.358 against
+// 0.338 ms per call group; the CAS chains still ran one after the other.)  A bucket read ahead of the thread's own previous
+// insert can be stale; fz_upsert tolerates stale views by construction (a slot only ever goes from empty to one key, and a
+// failed CAS returns the slot's current contents).
+template <typename StA, typename StB, typename StC>
+__device__ __forceinline__ void fz_for_each_pipe(const FzCluster& c, int n, StA sa, StB sb, StC sc)
+{
+  const int CT = (int)c.size * kFzThreads;
+  int i        = (int)c.rank * kFzThreads + (int)threadIdx.x;
+  if (i >= n) return;
+  auto A2 = sa(i);
+  auto B0 = sb(i, A2);
+  if (i + CT < n) A2 = sa(i + CT);
+#pragma unroll 1
+  for (; i < n; i += CT) {
+    auto B1 = B0;
+    if (i + CT < n) B1 = sb(i + CT, A2);
+    if (i + 2 * CT < n) A2 = sa(i + 2 * CT);
+    sc(i, B0);
+    B0 = B1;
+  }
+}
+
+// Inserts, lane-decoupled.  A warp that runs 32 inserts in lock step pays, per round, for its SLOWEST lane -- the one whose home
+// bucket is full and who walks two or three buckets (probe + CAS round trips each) -- and at 32 lanes some lane nearly always
+// does: the insert loops spent ~6 dependent round trips per item although an item needs ~2 (phase clock: 112 us for 20 items per
+// thread; neither more items in flight, nor prefetching, nor L2 residency hints changed that, profiles/r2y_*, r2aa_*).  Here a
+// lane that has finished its item starts its next one while its neighbours are still probing: every trip of the loop is ONE
+// bucket read (+ one CAS where a slot is claimed) for every lane that still has work.
+// Not inlined, on purpose: fz_label_kernel holds ~40 values live across its phases and is capped at 64 registers, so inside the
+// inlined form of this loop every trip began with three spill reloads (LDL) in front of the bucket address -- local memory is
+// 0.7 MB per SM here, far beyond L1, so those reloads were L2 round trips on the critical path of EVERY trip, which is why no
+// latency-hiding change to the loops moved the phase times (profiles/r2y_*, r2aa_*, r2ab_*).  As a function of its own the loop's
+// state is its arguments.
+//   keys[i] -> vertex;  aux word to install / lower to = pending | i;  slot_out[i] = slot (when slot_out != nullptr)
+template <typename KeyT>
+__device__ __noinline__ void fz_insert_stream(unsigned long long* __restrict__ tbl, unsigned int nb, unsigned long long pol,
+                                              const KeyT* __restrict__ keys, int n, unsigned int pending, unsigned int* __restrict__ slot_out,
+                                              int first, int stride)
+{
+  int i        = first;
+  bool live    = i < n;
+  unsigned int v = 0, b = 0, vn = 0;
+  if (live) {
+    v = (unsigned int)keys[i];
+    b = fz_home(v, nb);
+    if (i + stride < n) vn = (unsigned int)keys[i + stride];  // the next item's key is always one item ahead
+  }
+  while (__any_sync(0xffffffffu, live)) {
+    if (live) {
+      unsigned long long w[4];
+      fz_load_bucket(tbl, b, w, pol);
+      const unsigned int m           = pending | (unsigned int)i;
+      const unsigned long long fresh = ((unsigned long long)v << 32) | m;
+      int slot                       = -1;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (slot < 0) {
+          unsigned long long cur = w[j];
+          if (cur == kFzEmpty) {
+            cur = atomicCAS(&tbl[4ULL * b + j], kFzEmpty, fresh);
+            if (cur == kFzEmpty) slot = (int)(4u * b + j);
+          }
+          if (slot < 0 && (unsigned int)(cur >> 32) == v) {
+            if ((unsigned int)cur > m) fz_min_aux(&tbl[4ULL * b + j], m, pol);
+            slot = (int)(4u * b + j);
+          }
+        }
+      }
+      if (slot >= 0) {
+        if (slot_out) slot_out[i] = (unsigned int)slot;
+        i += stride;
+        live = i < n;
+        if (live) {
+          v = vn;
+          b = fz_home(v, nb);
+          if (i + stride < n) vn = (unsigned int)keys[i + stride];
+        }
+      } else {
+        b = b + 1 == nb ? 0u : b + 1;
+      }
+    }
   }
 }
 
@@ -324,41 +484,31 @@ struct FzSink {
   __device__ __forceinline__ void val(int pos, ColT v) const { dest[pos] = v; }
 };
 
+// (not inlined, for the same reason as fz_insert_stream: the sampling loop gets a register allocation of its own)
 template <typename ColT, int G>
-__device__ __forceinline__ void fz_sample_rows(const FzArgs& a, FzCluster& c, const long long* __restrict__ Fl, const int* __restrict__ Ol,
+__device__ FZ_SAMPLE_FN void fz_sample_rows(const FzArgs& a, const FzCluster& c, const long long* __restrict__ Fl, const int* __restrict__ Ol,
                                                int nbase, int n_rows, int ebase, long long rowbase, int M, unsigned long long seed,
-                                               FzSink<ColT>& sink)
+                                               FzSink<ColT>& sink, unsigned long long col_policy)
 {
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int g = lane & (G - 1), sub = lane / G;
   const Affine lane_skip = affine_skip_loop((unsigned long long)g);
   int* Wg                = &c.sh->W[wib][sub * G];
   const int warps        = (int)c.size * (kFzThreads / 32);
-  // one lane per row reads the row's extent; the reads of batch k + 1 are issued before batch k is sampled, so the
-  // node -> row_ptr chain (two dependent reads, the second one random in DRAM) is off the critical path of every batch but the first
-  auto load_rows = [&](int batch, long long& start, int& N, int& off) {
-    const int r = batch * 32 + lane;
-    start       = 0;
-    N = off = 0;
-    if ((long long)batch * 32 < n_rows && r < n_rows) {
+  for (int batch = (int)c.rank * (kFzThreads / 32) + wib; (long long)batch * 32 < n_rows; batch += warps) {
+    const int r         = batch * 32 + lane;
+    long long start_own = 0;
+    int N_own = 0, off_own = 0;
+    if (r < n_rows) {  // one lane per row reads the row's extent
       const unsigned long long node = (unsigned long long)Fl[nbase + r];
-      start         = load_i64<false>(a.row_ptr, a.row_ptr_off + node);
+      start_own     = load_i64<false>(a.row_ptr, a.row_ptr_off + node);
       long long end = load_i64<false>(a.row_ptr, a.row_ptr_off + node + 1);
-      N             = (int)(end - start);
-      off           = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
+      N_own         = (int)(end - start_own);
+      off_own       = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
     }
-  };
-  int batch = (int)c.rank * (kFzThreads / 32) + wib;
-  long long start_nxt;
-  int N_nxt, off_nxt;
-  load_rows(batch, start_nxt, N_nxt, off_nxt);
-  for (; (long long)batch * 32 < n_rows; batch += warps) {
-    const int r               = batch * 32 + lane;
-    const long long start_own = start_nxt;
-    const int N_own = N_nxt, off_own = off_nxt;
-    load_rows(batch + warps, start_nxt, N_nxt, off_nxt);
+    // (reading the extents of batch k + 1 before batch k is sampled was measured without effect, profiles/r2s_*, and cost registers)
     uniform_small_rows32<ColT, G, false>(a.col, a.col_off, M, seed, a.tab, lane_skip, Wg, lane, rowbase + r, nbase + r, start_own, N_own,
-                                         off_own, sink);
+                                         off_own, sink, col_policy);
   }
 }
 
@@ -377,6 +527,7 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
   const unsigned int CT  = c.size * kFzThreads;        // threads of the cluster
   const unsigned int cti = c.rank * kFzThreads + tid;  // this thread's index in the cluster
   const int L            = a.L, B = a.B;
+  const FzPolicy pol     = fz_make_policy();
 
   while (true) {
     // ---- next label (tickets are handed out in label order) ------------------------------------------------
@@ -417,27 +568,31 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
     // ---- step 0: the label's distinct seeds, first occurrence first ----------------------------------------
     unsigned int nb = ((unsigned int)n_seeds >> 1) + 8u;
     for (unsigned int i = cti; i < nb * 4u; i += CT)
-      tb[i] = kFzEmpty;
+      fz_store_slot(&tb[i], kFzEmpty, pol.keep);
     c.sync();
     FZ_T(1);
-    fz_for_each(
-      c, n_seeds,
-      [&](int s) -> long long {
-        long long v = a.seed_is64 ? static_cast<const long long*>(a.seeds)[lo_l + s] : (long long)static_cast<const int*>(a.seeds)[lo_l + s];
-        if (v < 0 || (unsigned long long)v >= a.V) {  // flagged; carry on with vertex 0 so that nothing is read out of bounds
-          *a.bad_seed = 1;
-          v           = 0;
-        }
-        gidl[s] = v;  // the label's edge scratch is free until hop 0 writes it: sanitised seeds for the compaction below
-        return v;
-      },
-      [&](int, long long v) -> FzProbe { return fz_probe(tb, nb, (unsigned int)v); },
-      [&](int s, const FzProbe& pr) { auxl[s] = fz_upsert(tb, nb, pr, kFzPending | (unsigned int)s); });
+    // sanitised seeds into the label's edge scratch (free until hop 0 writes it): a seed outside [0, V) is flagged and replaced
+    // by vertex 0 so that nothing is read out of bounds
+    for (int sd = (int)cti; sd < n_seeds; sd += (int)CT) {
+      long long v = a.seed_is64 ? static_cast<const long long*>(a.seeds)[lo_l + sd] : (long long)static_cast<const int*>(a.seeds)[lo_l + sd];
+      if (v < 0 || (unsigned long long)v >= a.V) {
+        *a.bad_seed = 1;
+        v           = 0;
+      }
+      gidl[sd] = v;
+    }
+#if WGB_FZ_INSERT_STREAM
+    fz_insert_stream<long long>(tb, nb, pol.keep, gidl, n_seeds, kFzPending, auxl, (int)cti, (int)CT);  // (each thread reads back its own writes)
+#else
+    FZ_HASH_LOOP(
+      c, n_seeds, [&](int s) -> long long { return gidl[s]; }, [&](int, long long v) -> FzProbe { return fz_probe(tb, nb, (unsigned int)v, pol.keep); },
+      [&](int s, const FzProbe& pr) { auxl[s] = fz_upsert(tb, nb, pr, kFzPending | (unsigned int)s, pol.keep); });
+#endif
     c.sync();
     FZ_T(2);
     int known = (int)fz_ordered_scan(
       c, n_seeds, [&](long long s) -> unsigned int { return auxl[s]; },
-      [&](long long, unsigned int slot) -> unsigned long long { return ld_relaxed_u64(&tb[slot]); },
+      [&](long long, unsigned int slot) -> unsigned long long { return fz_load_slot(&tb[slot], pol.keep); },
       [&](long long s, unsigned long long w) -> unsigned int {
         auxl[s] = (unsigned int)w;
         return (unsigned int)w == (kFzPending | (unsigned int)s) ? 1u : 0u;
@@ -495,34 +650,42 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
       // P2: a fresh table for (everything numbered so far + this hop's edges)
       nb = (((unsigned int)known + (unsigned int)e_h) >> 1) + 8u;
       for (unsigned int i = cti; i < nb * 4u; i += CT)
-        tb[i] = kFzEmpty;
+        fz_store_slot(&tb[i], kFzEmpty, pol.keep);
       c.sync();  // table cleared, row offsets visible
       FZ_T(T0 + 1);
       // P3: the hop's rows are sampled (independent of the table); numbered vertices enter the table with their local id
       if (e_h > 0) {
         FzSink<ColT> sink{destl + ebase, majl + ebase, gidl + ebase};
         const unsigned long long hop_seed = a.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL;
-        if (M <= 8) fz_sample_rows<ColT, 8>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
-        else if (M <= 16) fz_sample_rows<ColT, 16>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
-        else fz_sample_rows<ColT, 32>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink);
+        if (M <= 8) fz_sample_rows<ColT, 8>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
+        else if (M <= 16) fz_sample_rows<ColT, 16>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
+        else fz_sample_rows<ColT, 32>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
       }
-      fz_for_each<kFzIlpHash>(
+#if WGB_FZ_INSERT_STREAM
+      fz_insert_stream<long long>(tb, nb, pol.keep, Fl, known, 0u, nullptr, (int)cti, (int)CT);
+#else
+      FZ_HASH_LOOP(
         c, known, [&](int j) -> unsigned int { return (unsigned int)Fl[j]; },
-        [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v); },
-        [&](int j, const FzProbe& pr) { fz_upsert(tb, nb, pr, (unsigned int)j); });
+        [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v, pol.keep); },
+        [&](int j, const FzProbe& pr) { fz_upsert(tb, nb, pr, (unsigned int)j, pol.keep); });
+#endif
       c.sync();  // edges written, known vertices in the table
       FZ_T(T0 + 2);
       // P4: endpoints enter the table; the smallest edge index wins a new vertex
-      fz_for_each<kFzIlpHash>(
+#if WGB_FZ_INSERT_STREAM
+      fz_insert_stream<ColT>(tb, nb, pol.keep, destl + ebase, e_h, kFzPending, auxl + ebase, (int)cti, (int)CT);
+#else
+      FZ_HASH_LOOP(
         c, e_h, [&](int i) -> unsigned int { return (unsigned int)destl[ebase + i]; },
-        [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v); },
-        [&](int i, const FzProbe& pr) { auxl[ebase + i] = fz_upsert(tb, nb, pr, kFzPending | (unsigned int)i); });
+        [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v, pol.keep); },
+        [&](int i, const FzProbe& pr) { auxl[ebase + i] = fz_upsert(tb, nb, pr, kFzPending | (unsigned int)i, pol.keep); });
+#endif
       c.sync();
       FZ_T(T0 + 3);
       // P5: first occurrences in edge order -> the next frontier, appended to the label's vertex array
       const int n_new = (int)fz_ordered_scan(
         c, e_h, [&](long long i) -> unsigned int { return auxl[ebase + i]; },
-        [&](long long, unsigned int slot) -> unsigned long long { return ld_relaxed_u64(&tb[slot]); },
+        [&](long long, unsigned int slot) -> unsigned long long { return fz_load_slot(&tb[slot], pol.keep); },
         [&](long long i, unsigned long long w) -> unsigned int {
           auxl[ebase + i] = (unsigned int)w;
           return (unsigned int)w == (kFzPending | (unsigned int)i) ? 1u : 0u;
@@ -545,7 +708,7 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
       c.sync();  // ranks visible
       FZ_T(T0 + 4);
       // P6: endpoints -> local ids
-      fz_for_each<kFzIlpHash>(
+      FZ_HASH_LOOP(
         c, e_h, [&](int i) -> unsigned int { return auxl[ebase + i]; },
         [&](int, unsigned int ax) -> unsigned int { return (ax & kFzPending) ? rankl[ebase + (ax & ~kFzPending)] : 0u; },
         [&](int i, unsigned int rk) {

@@ -18,6 +18,46 @@ __device__ __forceinline__ T load_elt(const ChunkRef& ref, unsigned long long el
   return __ldg(reinterpret_cast<const T*>(ref.at<CHUNKED>(elt * sizeof(T))));
 }
 
+#ifndef WGB_COPY_W
+#define WGB_COPY_W 4  // reads in flight per lane in the copy-row path (passes of 12 cover a fan-out-10 row in one trip but spill: no faster)
+#endif
+// read an element with an L2 cache policy (createpolicy...): single-use random reads of the graph should not push the
+// sampler's tables out of L2.  policy == 0: the plain read-only load.
+template <typename T, bool CHUNKED>
+__device__ __forceinline__ T load_elt_policy(const ChunkRef& ref, unsigned long long elt, unsigned long long policy)
+{
+#ifndef WGB_HOST_EMULATION
+  if (policy != 0ULL) {
+    const T* p = reinterpret_cast<const T*>(ref.at<CHUNKED>(elt * sizeof(T)));
+    T v;
+    if constexpr (sizeof(T) == 4) {
+      unsigned int r;
+      asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
+      v = (T)r;
+    } else {
+      unsigned long long r;
+      asm volatile("ld.global.nc.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(policy));
+      v = (T)r;
+    }
+    return v;
+  }
+#endif
+  (void)policy;
+  return load_elt<T, CHUNKED>(ref, elt);
+}
+
+// request the sector of an element into L2 (no register, no wait): used where the value is only needed much later
+template <typename T, bool CHUNKED>
+__device__ __forceinline__ void prefetch_l2(const ChunkRef& ref, unsigned long long elt)
+{
+#ifndef WGB_HOST_EMULATION
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ref.at<CHUNKED>(elt * sizeof(T))));
+#else
+  (void)ref;
+  (void)elt;
+#endif
+}
+
 #ifdef WGB_HOST_EMULATION
 // tests/emu compiles this header with g++ to check kernel LOGIC on the CPU (test infrastructure, never the product)
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
@@ -273,7 +313,7 @@ template <typename ColT, int G, bool CHUNKED, typename Sink>
 __device__ __forceinline__ void uniform_small_rows32(const ChunkRef& col, unsigned long long col_off, int M, unsigned long long seed,
                                                      const Affine* __restrict__ tab, const Affine& lane_skip, int* Wg, int lane,
                                                      long long b_own, int tag_own, long long start_own, int N_own, int off_own,
-                                                     Sink& sink)
+                                                     Sink& sink, unsigned long long col_policy = 0ULL)
 {
   constexpr int GPW = 32 / G;
   const int g = lane & (G - 1), sub = lane / G;
@@ -284,28 +324,33 @@ __device__ __forceinline__ void uniform_small_rows32(const ChunkRef& col, unsign
   // G-lane steps below, packed GPW at a time.  (Before: every row paid a full step, ~175 warp instructions per GPW rows;
   // the sampling loop was 42 % of the instructions of the fused sampler.)
   const bool sampled_own = N_own > M;
-  {
-    int n_copy = sampled_own ? 0 : N_own;
-    int n_max  = n_copy;
+  const int n_copy       = sampled_own ? 0 : N_own;
+  // (Tried and measured without effect, profiles/r2y_*: requesting the copy rows' sectors into L2 first and reading them after
+  // the sampled rows' steps.  The fused sampler is bound by the RATE of random sector accesses, not by their latency.)
+  auto store_copies = [&]() {
+    int n_max = n_copy;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const int y = __shfl_xor_sync(0xffffffffu, n_max, o);
       n_max       = y > n_max ? y : n_max;
     }
+    // every read of a pass is issued before its first store
+    constexpr int kCopyW = WGB_COPY_W;
 #pragma unroll 1
-    for (int k0 = 0; k0 < n_max; k0 += 4) {
-      ColT v[4];
+    for (int k0 = 0; k0 < n_max; k0 += kCopyW) {
+      ColT v[kCopyW];
 #pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (k0 + u < n_copy) v[u] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start_own + k0 + u));
+      for (int u = 0; u < kCopyW; u++)
+        if (k0 + u < n_copy) v[u] = load_elt_policy<ColT, CHUNKED>(col, col_off + (unsigned long long)(start_own + k0 + u), col_policy);
 #pragma unroll
-      for (int u = 0; u < 4; u++)
+      for (int u = 0; u < kCopyW; u++)
         if (k0 + u < n_copy) {
           sink.ids(off_own + k0 + u, tag_own, start_own + k0 + u);
           sink.val(off_own + k0 + u, v[u]);
         }
     }
-  }
+  };
+  store_copies();
   unsigned int rem = __ballot_sync(0xffffffffu, sampled_own);
   if (rem == 0u) return;  // warp-uniform
   Affine skip_own{1ULL, 0ULL};
@@ -349,7 +394,7 @@ __device__ __forceinline__ void uniform_small_rows32(const ChunkRef& col, unsign
       }
       const int a = resolve_chain_group<G>(x, valid, g, lane, sub, gmask, N, M, Wg);
       if (valid) {
-        val[k] = load_elt<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + a));
+        val[k] = load_elt_policy<ColT, CHUNKED>(col, col_off + (unsigned long long)(start + a), col_policy);
         sink.ids(off + g, tag, start + a);
         wmask |= 1u << k;
       }
