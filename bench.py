@@ -651,6 +651,32 @@ def run_c5(args):
     row_t = torch.tensor([0 if dt == "a" else 1 for _, dt in C5_EDGE_TYPES], device=dev)  # vertex type of the majors (CSR rows)
     col_t = torch.tensor([0 if st == "a" else 1 for st, _ in C5_EDGE_TYPES], device=dev)
 
+    # ---- parity, outside every timed region: one 4-label heterogeneous call group on THIS graph through the CPU oracle (checker
+    # only) must equal the GPU result bit for bit -- typed COO, edge ids, renumber maps, every offset array -- and the gathered rows
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        import numpy as np
+
+        oracle = _oracle()
+        h_rps = [w.get_local_tensor()[0].cpu().numpy() for w in wm_rps]
+        h_cols = [w.get_local_tensor()[0].cpu().numpy() for w in wm_cols]
+        gp = torch.Generator(device="cpu").manual_seed(99)
+        p_seeds = torch.randint(0, C5_NODES[0], (4 * BATCH,), generator=gp)
+        p_lo = (np.arange(5) * BATCH).astype(np.int64)
+        got = sampler.sample_hetero(wm_rps, wm_cols, vto, p_seeds.to(dev), torch.from_numpy(p_lo).to(dev), fan, SAMPLER_SEED, int64_ids=True)
+        exp = oracle.hetero_multihop_sample(h_rps, h_cols, np.asarray(vto, dtype=np.int64), p_seeds.numpy(), p_lo, fan, SAMPLER_SEED)
+        keys = [k for k in exp if k in got]
+        bad = [k for k in keys if not np.array_equal(got[k].cpu().numpy(), exp[k])]
+        xg = emb.gather(got["renumber_map"]).cpu().numpy()
+        ids = exp["renumber_map"].astype(np.int64)
+        want = (((ids[:, None] + np.arange(FEAT_DIM)[None, :]) & 0xFF).astype(np.float32)) / 256.0
+        if not np.array_equal(xg, want):
+            bad.append("gathered_features")
+        assert not bad and len(keys) >= 6, "GPU result differs from the oracle on the C5 graph: %s (compared %s)" % (bad, keys)
+        parity = {"ok": True, "labels": 4, "edges": int(exp["minors"].shape[0]), "nodes": int(ids.shape[0]), "compared": keys + ["gathered_features"]}
+        log("[rank 0] parity vs oracle on the C5 graph: %s" % parity)
+        del h_rps, h_cols, got, xg
+
     class Net(torch.nn.Module):
         def __init__(self):
             super().__init__()
@@ -819,6 +845,7 @@ def run_c5(args):
                        "model": "2-layer GraphSAGE %d-%d-%d (pylibwholegraph.torch.SAGEConv), %d dense parameters, %s" % (
                            FEAT_DIM, C5_HIDDEN, C5_CLASSES, n_params, "DistributedDataParallel (NCCL)" if world > 1 else "single process"),
                        "nccl_ranks": world},
+            "parity_checked": bool(parity and parity.get("ok")), "parity": parity,
             "stages_ms_per_step": {nm: v / args.steps for nm, v in zip(names, stage)},
             "aggregation_kernel_alone": {"ms": agg_ms, "algorithmic_gbs": agg_bytes / (agg_ms * 1e-3) / 1e9,
                                          "note": "csr_aggregate (mean) over the whole sampled block, 128-wide fp32 rows, rank 0's last block",
@@ -847,6 +874,10 @@ def run_loader(args):
     import torch
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
+    if NUM_EDGES > 400_000_000:
+        # the PyG stores are fed the way a user feeds them -- an int64 COO edge_index (25.6 GB on C4) and a dense feature tensor
+        # (56.8 GB) that the stores then copy -- which does not fit one GPU next to the stores' own copies on the large shapes
+        sys.exit("bench.py --loader builds PyG-style stores from whole tensors: use --workload c2 (the large shapes do not fit one GPU twice)")
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     os.environ.setdefault("LOCAL_WORLD_SIZE", "1")
