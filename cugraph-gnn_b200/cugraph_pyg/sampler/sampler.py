@@ -12,16 +12,48 @@ import torch
 
 from typing import List
 
-from cugraph_pyg._pyg_compat import SamplerOutput, HeteroSamplerOutput, NodeSamplerInput, EdgeSamplerInput, ptr2index
+from cugraph_pyg._pyg_compat import Data, SamplerOutput, HeteroSamplerOutput, NodeSamplerInput, EdgeSamplerInput, ptr2index
 from .sampler_utils import filter_cugraph_pyg_store, filter_cugraph_pyg_hetero_store, neg_sample, neg_cat
 
 
 class SampleIterator:
     """Combines sampler outputs with their features into mini-batches a GNN can consume."""
 
+    # Node features are fetched ONCE per call group -- one gather of the concatenated renumber maps, the shape the gather
+    # kernels run at full bandwidth -- and every mini-batch of the group receives a row slice of that block (the reference
+    # gathers per mini-batch, sampler.py:51-76: one small launch each).  Set to False to fetch per mini-batch.
+    prefetch_call_group_features = True
+
     def __init__(self, data, output_iter: Iterator[SamplerOutput]):
         self.__feature_store, self.__graph_store = data
         self.__output_iter = output_iter
+
+    def __homogeneous_data(self, s, col):
+        grp = getattr(s, "group", None)
+        pre = getattr(s, "edge_index", None)
+        if grp is None or not self.prefetch_call_group_features:
+            data = filter_cugraph_pyg_store(self.__feature_store, self.__graph_store, s.node, s.row, col if pre is None else pre[1], s.edge, None)
+            return data
+        blocks = grp.get("_features")
+        if blocks is None:
+            node_attrs = [a for a in self.__feature_store.get_all_tensor_attrs() if not isinstance(a.group_name, tuple)]
+            for a in node_attrs:
+                a.index = grp["map"]
+            blocks = {a.attr_name: t for a, t in zip(node_attrs, self.__feature_store.multi_get_tensor(node_attrs))} if node_attrs else {}
+            grp["_features"] = blocks
+        n0, n1 = s.node_span
+        data = Data()
+        data.edge_index = pre if pre is not None else torch.stack([s.row, col], dim=0)
+        data.num_nodes = int(s.node.numel())
+        for name, block in blocks.items():
+            data[name] = block[n0:n1]
+        edge_attrs = [a for a in self.__feature_store.get_all_tensor_attrs() if isinstance(a.group_name, tuple)]
+        if edge_attrs:
+            for a in edge_attrs:
+                a.index = s.edge
+            for a, t in zip(edge_attrs, self.__feature_store.multi_get_tensor(edge_attrs)):
+                data[a.attr_name] = t
+        return data
 
     def __next__(self):
         s = next(self.__output_iter)
@@ -29,12 +61,15 @@ class SampleIterator:
             return self.__hetero(s)
         if not isinstance(s, SamplerOutput):
             raise ValueError("Invalid output type")
-        n_edges = int(s.edge.numel())
-        if s.col.numel() == n_edges and s.metadata_is_coo:
-            col = s.col
+        if getattr(s, "edge_index", None) is not None:
+            col = None  # the reader already holds the call group's edge_index block
         else:
-            col = ptr2index(s.col, n_edges)  # CSR major offsets -> COO (what PyG layers take)
-        data = filter_cugraph_pyg_store(self.__feature_store, self.__graph_store, s.node, s.row, col, s.edge, None)
+            n_edges = int(s.edge.numel())
+            if s.col.numel() == n_edges and s.metadata_is_coo:
+                col = s.col
+            else:
+                col = ptr2index(s.col, n_edges)  # CSR major offsets -> COO (what PyG layers take)
+        data = self.__homogeneous_data(s, col)
         if "n_id" not in data:
             data.n_id = s.node
         if s.edge is not None and "e_id" not in data:
@@ -83,10 +118,13 @@ class SampleIterator:
 
 
 class _Output(SamplerOutput):
-    """SamplerOutput + two private fields used by SampleIterator."""
+    """SamplerOutput + private fields used by SampleIterator."""
 
     metadata_is_coo: bool = True
     csr = None
+    edge_index = None  # [2, E] view of the call group's edge_index block (row = source, col = destination, batch-local ids)
+    group = None      # the call group's raw sampler output (shared by its mini-batches)
+    node_span = None  # (first, last + 1) position of this mini-batch's vertices in the call group's concatenated renumber map
 
 
 class SampleReader:
@@ -158,6 +196,34 @@ class HomogeneousSampleReader(SampleReader):
         raw["_base"] = host[n_lho + B + 1:n_lho + B + 1 + (L + 1) * B].view(L + 1, B).tolist()
         raw["_edge_lho"] = host[n_lho + B + 1 + (L + 1) * B:].tolist() if "major_offsets" in raw else raw["_lho"]
         raw["_input_offsets"] = raw["input_offsets"].tolist()
+        # per-hop counts of every mini-batch as two host tensors per call group (a mini-batch takes a row)
+        el = torch.tensor(raw["_edge_lho"], dtype=torch.int64)
+        raw["_num_sampled_edges"] = (el[1:] - el[:-1]).view(B, L)
+        rm = torch.tensor(raw["_rmo"], dtype=torch.int64)
+        steps = torch.cat([torch.tensor(raw["_base"], dtype=torch.int64).view(L + 1, B), (rm[1:] - rm[:-1]).view(1, B)], dim=0)
+        raw["_num_sampled_nodes"] = (steps[1:] - steps[:-1]).t().contiguous()
+        # edge_index of every mini-batch of the call group in one block, built by a handful of launches per CALL GROUP; a
+        # mini-batch takes a column slice (the per-mini-batch form -- offsets minus base, ptr2index, stack -- was ~7 launches each)
+        minors = raw["minors"]
+        E = int(minors.numel())
+        if "major_offsets" in raw:
+            dev = minors.device
+            mo = raw["major_offsets"]
+            elho, rlho = raw["_edge_lho"], raw["_lho"]
+            e0 = torch.tensor([elho[b * L] for b in range(B)], dtype=mo.dtype).to(dev, non_blocking=True)
+            r0 = torch.tensor([rlho[b * L] for b in range(B)], dtype=torch.int64)
+            n_rows = torch.tensor([rlho[(b + 1) * L] - rlho[b * L] for b in range(B)], dtype=torch.int64)
+            n_edges = torch.tensor([elho[(b + 1) * L] - elho[b * L] for b in range(B)], dtype=torch.int64).to(dev, non_blocking=True)
+            total_rows = int(n_rows.sum())
+            # batch-local indptr of every mini-batch, boundaries duplicated: batch b at [r0_b + b, r0_b + b + rows_b]
+            bid = torch.repeat_interleave(torch.arange(B, device=dev), (n_rows + 1).to(dev, non_blocking=True), output_size=total_rows + B)
+            raw["_indptr_local"] = mo[torch.arange(total_rows + B, device=dev) - bid] - e0[bid]
+            raw["_indptr_at"] = (r0 + torch.arange(B)).tolist()
+            row_of_edge = ptr2index(mo[: total_rows + 1], E)  # row of the call group per edge
+            majors_local = row_of_edge - torch.repeat_interleave(r0.to(dev, non_blocking=True), n_edges, output_size=E)
+            raw["_edge_index"] = torch.stack([minors, majors_local.to(minors.dtype)], dim=0)
+        else:
+            raw["_edge_index"] = torch.stack([minors, raw["majors"]], dim=0)
 
     def _decode(self, raw: Dict[str, torch.Tensor], index: int):
         L, B = raw["_L"], raw["_B"]
@@ -167,16 +233,18 @@ class HomogeneousSampleReader(SampleReader):
         node = raw["map"][n0:n1]
         minors = raw["minors"][e0:e1]
         edge = raw["edge_id"][e0:e1]
-        num_sampled_edges = torch.tensor([elho[index * L + h + 1] - elho[index * L + h] for h in range(L)])
-        base = [raw["_base"][t][index] for t in range(L + 1)] + [n1 - n0]
-        num_sampled_nodes = torch.tensor([base[t + 1] - base[t] for t in range(L + 1)])
-        num_seeds = base[1]
+        num_sampled_edges = raw["_num_sampled_edges"][index]
+        num_sampled_nodes = raw["_num_sampled_nodes"][index]
+        num_seeds = raw["_base"][1][index]
         out = _Output(node=node, row=minors, col=None, edge=edge, batch=node[:num_seeds],
                       num_sampled_nodes=num_sampled_nodes, num_sampled_edges=num_sampled_edges,
                       metadata=self._seed_metadata(raw, index))
+        out.group, out.node_span = raw, (n0, n1)
+        out.edge_index = raw["_edge_index"][:, e0:e1]
         if "major_offsets" in raw:
             r0, r1 = lho[index * L], lho[(index + 1) * L]
-            out.col = raw["major_offsets"][r0:r1 + 1] - e0
+            at = raw["_indptr_at"][index]
+            out.col = raw["_indptr_local"][at:at + (r1 - r0) + 1]
             out.metadata_is_coo = False
             out.csr = (out.col, minors)
         else:

@@ -193,6 +193,51 @@ def test_plain_loaders_unchanged(stack, oracle):
         cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors=[5], input_nodes=torch.arange(4), input_time=torch.arange(4))
 
 
+def test_call_group_feature_prefetch_equals_per_batch_fetch(stack):
+    """SampleIterator fetches node features once per call group and hands every mini-batch a row slice; switched off it
+    fetches per mini-batch as the reference does (sampler.py:51-76).  Every mini-batch carries the rows of its own n_id either way,
+    and the per-call-group form asks the feature store once per call group."""
+    cugraph_pyg, FS, sampler = stack
+    from cugraph_pyg.sampler.sampler import SampleIterator
+
+    rng = np.random.default_rng(5)
+    n, e = 120, 3000
+    src, dst = torch.from_numpy(rng.integers(0, n, e)), torch.from_numpy(rng.integers(0, n, e))
+
+    class CountingFS(FS):
+        fetches = 0
+
+        def multi_get_tensor(self, attrs):
+            CountingFS.fetches += 1
+            return super().multi_get_tensor(attrs)
+
+    def run(prefetch):
+        graph_store, feature_store = cugraph_pyg.data.GraphStore(), CountingFS()
+        graph_store[("n", "to", "n"), "coo", False, (n, n)] = [src, dst]
+        feature_store["n", "x", None] = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+        feature_store["n", "y", None] = torch.arange(n, dtype=torch.int64)
+        CountingFS.fetches = 0
+        old = SampleIterator.prefetch_call_group_features
+        SampleIterator.prefetch_call_group_features = prefetch
+        try:
+            loader = cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors=[4, 2], batch_size=8, input_nodes=torch.arange(64),
+                                                       shuffle=False, local_seeds_per_call=32)
+            return [(b.n_id.clone(), b.x.clone(), b.y.clone(), b.edge_index.clone()) for b in loader], CountingFS.fetches
+        finally:
+            SampleIterator.prefetch_call_group_features = old
+
+    a, fetch_a = run(True)
+    b, fetch_b = run(False)
+    assert len(a) == len(b) == 8
+    for batches in (a, b):  # (the two loaders draw different samples: every batch is checked against the closed form of its own n_id)
+        for n_id, x, y, ei in batches:
+            assert torch.equal(x, torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)[n_id]) and torch.equal(y, n_id)
+            assert x.shape[0] == n_id.numel() and int(ei.max()) < n_id.numel()
+    for (n1, _, _, _), (n2, _, _, _) in zip(a, b):
+        assert torch.equal(n1[:8], n2[:8])  # same seeds, seeds first
+    assert fetch_a == 2 and fetch_b == 8  # 2 call groups of 4 mini-batches
+
+
 @pytest.mark.parametrize("biased", [False, True])
 def test_link_neighbor_loader_temporal_homogeneous(stack, biased):
     """tests/loader/test_neighbor_loader.py:1059-1101 of the reference (seed edge 3 -> 3 at time -1)."""
