@@ -872,7 +872,7 @@ struct wholegraph_multihop_sampler_ {
   // temporal calls only
   Buf ftime[wgb::kMaxHops + 1], eligible[wgb::kMaxHops], clipped, tdesc_dev;
   // fused per-label path (multihop_fused.cuh): label-major scratch
-  Buf fz[13];
+  Buf fz[15];
   double fz_phase_ns[32] = {};  // WGB_MH_TIMING: in-kernel phase clock of the fused path
   double fz_span_ns = 0;
   long long fz_phase_labels = 0, fz_calls = 0;

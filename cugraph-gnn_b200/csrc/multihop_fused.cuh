@@ -61,6 +61,9 @@ struct FzArgs {
   // label-major scratch (label l: vertices at lo[l] * fstride, edges at lo[l] * estride, table at fz_table_base(l))
   long long* F;           // vertices = renumber map segments
   int* Orow;              // per source row: label-local offset of its first edge
+  long long* Rstart;      // per source row: first position of its adjacency in the CSR  } written by the count phase, read by the
+  int* Rdeg;              // per source row: its degree                                   } sampling phase (coalesced; saves the
+                          //                                                               second random row_ptr read of every row)
   int* maj;               // per edge: local id of its source row
   int* mnr;               // per edge: local id of its endpoint
   long long* gid;         // per edge: position in the CSR
@@ -486,7 +489,8 @@ struct FzSink {
 
 // (not inlined, for the same reason as fz_insert_stream: the sampling loop gets a register allocation of its own)
 template <typename ColT, int G>
-__device__ FZ_SAMPLE_FN void fz_sample_rows(const FzArgs& a, const FzCluster& c, const long long* __restrict__ Fl, const int* __restrict__ Ol,
+__device__ FZ_SAMPLE_FN void fz_sample_rows(const FzArgs& a, const FzCluster& c, const long long* __restrict__ Rs, const int* __restrict__ Rd,
+                                            const int* __restrict__ Ol,
                                                int nbase, int n_rows, int ebase, long long rowbase, int M, unsigned long long seed,
                                                FzSink<ColT>& sink, unsigned long long col_policy)
 {
@@ -499,12 +503,10 @@ __device__ FZ_SAMPLE_FN void fz_sample_rows(const FzArgs& a, const FzCluster& c,
     const int r         = batch * 32 + lane;
     long long start_own = 0;
     int N_own = 0, off_own = 0;
-    if (r < n_rows) {  // one lane per row reads the row's extent
-      const unsigned long long node = (unsigned long long)Fl[nbase + r];
-      start_own     = load_i64<false>(a.row_ptr, a.row_ptr_off + node);
-      long long end = load_i64<false>(a.row_ptr, a.row_ptr_off + node + 1);
-      N_own         = (int)(end - start_own);
-      off_own       = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
+    if (r < n_rows) {  // the row's extent, as the count phase found it (coalesced reads of the label's scratch, not row_ptr again)
+      start_own = Rs[nbase + r];
+      N_own     = Rd[nbase + r];
+      off_own   = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
     }
     // (reading the extents of batch k + 1 before batch k is sampled was measured without effect, profiles/r2s_*, and cost registers)
     uniform_small_rows32<ColT, G, false>(a.col, a.col_off, M, seed, a.tab, lane_skip, Wg, lane, rowbase + r, nbase + r, start_own, N_own,
@@ -636,6 +638,8 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
         },
         [&](long long r, const Row2& x) -> unsigned int {
           long long d   = x.s1 - x.s0;
+          (a.Rstart + vbeg)[nbase + r] = x.s0;
+          (a.Rdeg + vbeg)[nbase + r]   = (int)d;
           d             = d < 0 ? 0 : (d > M ? M : d);
           Ol[nbase + r] = (int)d;
           return (unsigned int)d;
@@ -657,9 +661,9 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
       if (e_h > 0) {
         FzSink<ColT> sink{destl + ebase, majl + ebase, gidl + ebase};
         const unsigned long long hop_seed = a.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL;
-        if (M <= 8) fz_sample_rows<ColT, 8>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
-        else if (M <= 16) fz_sample_rows<ColT, 16>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
-        else fz_sample_rows<ColT, 32>(a, c, Fl, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
+        if (M <= 8) fz_sample_rows<ColT, 8>(a, c, a.Rstart + vbeg, a.Rdeg + vbeg, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
+        else if (M <= 16) fz_sample_rows<ColT, 16>(a, c, a.Rstart + vbeg, a.Rdeg + vbeg, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
+        else fz_sample_rows<ColT, 32>(a, c, a.Rstart + vbeg, a.Rdeg + vbeg, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
       }
 #if WGB_FZ_INSERT_STREAM
       fz_insert_stream<long long>(tb, nb, pol.keep, Fl, known, 0u, nullptr, (int)cti, (int)CT);
@@ -841,6 +845,8 @@ static bool multihop_begin_fused(MhCall& c)
   a.random_state = c.random_state;
   a.F       = static_cast<long long*>(ensure(sp->fz[0], nv * sizeof(long long)));
   a.Orow    = static_cast<int*>(ensure(sp->fz[1], nv * sizeof(int)));
+  a.Rstart  = static_cast<long long*>(ensure(sp->fz[13], nv * sizeof(long long)));
+  a.Rdeg    = static_cast<int*>(ensure(sp->fz[14], nv * sizeof(int)));
   a.maj     = static_cast<int*>(ensure(sp->fz[2], ne * sizeof(int)));
   a.mnr     = static_cast<int*>(ensure(sp->fz[3], ne * sizeof(int)));
   a.gid     = static_cast<long long*>(ensure(sp->fz[4], ne * sizeof(long long)));

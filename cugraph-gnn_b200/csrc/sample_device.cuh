@@ -325,32 +325,58 @@ __device__ __forceinline__ void uniform_small_rows32(const ChunkRef& col, unsign
   // the sampling loop was 42 % of the instructions of the fused sampler.)
   const bool sampled_own = N_own > M;
   const int n_copy       = sampled_own ? 0 : N_own;
-  // (Tried and measured without effect, profiles/r2y_*: requesting the copy rows' sectors into L2 first and reading them after
-  // the sampled rows' steps.  The fused sampler is bound by the RATE of random sector accesses, not by their latency.)
-  auto store_copies = [&]() {
-    int n_max = n_copy;
+  // The copy rows of the batch are walked edge by edge ACROSS the warp, not row by row per lane.  The fused sampler turned out
+  // to be bound by the number of uncoalesced memory requests an SM can issue (its insert rate per SM is the same, ~0.18 G/s,
+  // whether 16 or 148 labels are in flight: profiles/r2ag_*), and the lane-per-row form cost one request per edge for the col
+  // read and three more for the maj / gid / dest stores.  Here a lane owns an EDGE of the batch's concatenated copy rows: the
+  // stores of a pass are three coalesced requests, the col reads one request per row touched.
+  {
+    int vbeg = n_copy;  // exclusive prefix of the copy counts over the warp's 32 rows
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const int y = __shfl_xor_sync(0xffffffffu, n_max, o);
-      n_max       = y > n_max ? y : n_max;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, vbeg, o);
+      if (lane >= o) vbeg += y;
     }
-    // every read of a pass is issued before its first store
+    const int total = __shfl_sync(0xffffffffu, vbeg, 31);
+    vbeg -= n_copy;
     constexpr int kCopyW = WGB_COPY_W;
 #pragma unroll 1
-    for (int k0 = 0; k0 < n_max; k0 += kCopyW) {
+    for (int q0 = 0; q0 < total; q0 += 32 * kCopyW) {
       ColT v[kCopyW];
+      int pos[kCopyW], tag[kCopyW];
+      long long epos[kCopyW];
+#pragma unroll
+      for (int u = 0; u < kCopyW; u++) {
+        const int q = q0 + 32 * u + lane;
+        // the row that holds virtual position q: the largest r with vbeg_r <= q (rows before it with the same prefix are empty)
+        int r = 0;
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+          const int cand = r + st;
+          const int bc   = __shfl_sync(0xffffffffu, vbeg, cand & 31);
+          if (cand < 32 && bc <= q) r = cand;
+        }
+        const int vb           = __shfl_sync(0xffffffffu, vbeg, r);
+        const long long startr = __shfl_sync(0xffffffffu, start_own, r);
+        const int offr         = __shfl_sync(0xffffffffu, off_own, r);
+        const int tagr         = __shfl_sync(0xffffffffu, tag_own, r);
+        pos[u]  = -1;
+        if (q < total) {
+          const int k = q - vb;
+          pos[u]      = offr + k;
+          tag[u]      = tagr;
+          epos[u]     = startr + k;
+          v[u]        = load_elt_policy<ColT, CHUNKED>(col, col_off + (unsigned long long)epos[u], col_policy);
+        }
+      }
 #pragma unroll
       for (int u = 0; u < kCopyW; u++)
-        if (k0 + u < n_copy) v[u] = load_elt_policy<ColT, CHUNKED>(col, col_off + (unsigned long long)(start_own + k0 + u), col_policy);
-#pragma unroll
-      for (int u = 0; u < kCopyW; u++)
-        if (k0 + u < n_copy) {
-          sink.ids(off_own + k0 + u, tag_own, start_own + k0 + u);
-          sink.val(off_own + k0 + u, v[u]);
+        if (pos[u] >= 0) {
+          sink.ids(pos[u], tag[u], epos[u]);
+          sink.val(pos[u], v[u]);
         }
     }
-  };
-  store_copies();
+  }
   unsigned int rem = __ballot_sync(0xffffffffu, sampled_own);
   if (rem == 0u) return;  // warp-uniform
   Affine skip_own{1ULL, 0ULL};
