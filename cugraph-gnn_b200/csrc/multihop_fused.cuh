@@ -82,6 +82,17 @@ struct FzArgs {
   const Affine* tab;
 };
 
+// buckets (of four slots) for a table that receives at most `keys` distinct keys: two slots per key (load <= 0.5).  Measured
+// with 1.5 slots per key (WGB_FZ_SLOTS_X8 = 12, a quarter less table): clear 9.5 -> 7.1 us but insert 107 -> 118 us per label
+// (longer bucket walks), 0.558 against 0.550 ms per call group -- the smaller footprint does not pay for the extra probes.
+#ifndef WGB_FZ_SLOTS_X8
+#define WGB_FZ_SLOTS_X8 16  // slots per key, in eighths
+#endif
+__device__ __forceinline__ unsigned int fz_buckets(unsigned int keys)
+{
+  return (unsigned int)(((unsigned long long)keys * WGB_FZ_SLOTS_X8) >> 5) + 8u;
+}
+
 __device__ __forceinline__ long long fz_table_base(long long lo_l, long long fstride, int l)
 {
   return 4 * ((lo_l * fstride + 1) / 2 + 16LL * l);  // in slots; a multiple of 4 (bucket = 32-byte sector)
@@ -568,7 +579,7 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
   } while (0)
     FZ_T(0);
     // ---- step 0: the label's distinct seeds, first occurrence first ----------------------------------------
-    unsigned int nb = ((unsigned int)n_seeds >> 1) + 8u;
+    unsigned int nb = fz_buckets((unsigned int)n_seeds);
     for (unsigned int i = cti; i < nb * 4u; i += CT)
       fz_store_slot(&tb[i], kFzEmpty, pol.keep);
     c.sync();
@@ -652,7 +663,7 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
       known = nbase + n_rows;
       FZ_T(T0);
       // P2: a fresh table for (everything numbered so far + this hop's edges)
-      nb = (((unsigned int)known + (unsigned int)e_h) >> 1) + 8u;
+      nb = fz_buckets((unsigned int)known + (unsigned int)e_h);
       for (unsigned int i = cti; i < nb * 4u; i += CT)
         fz_store_slot(&tb[i], kFzEmpty, pol.keep);
       c.sync();  // table cleared, row offsets visible
@@ -850,7 +861,9 @@ static bool multihop_begin_fused(MhCall& c)
   a.maj     = static_cast<int*>(ensure(sp->fz[2], ne * sizeof(int)));
   a.mnr     = static_cast<int*>(ensure(sp->fz[3], ne * sizeof(int)));
   a.gid     = static_cast<long long*>(ensure(sp->fz[4], ne * sizeof(long long)));
-  a.dest    = ensure(sp->fz[5], ne * sizeof(ColT));
+  // a 4-byte endpoint array shares the storage of the local-id array it is turned into (phase 6 writes mnr[i] after every read
+  // of dest has happened, two barriers earlier): 4 bytes less scratch per edge
+  a.dest    = sizeof(ColT) == sizeof(int) ? static_cast<void*>(a.mnr) : ensure(sp->fz[5], ne * sizeof(ColT));
   a.aux     = static_cast<unsigned int*>(ensure(sp->fz[6], ne * sizeof(unsigned int)));
   a.rank_of = static_cast<unsigned int*>(ensure(sp->fz[7], ne * sizeof(unsigned int)));
   a.table   = static_cast<unsigned long long*>(ensure(sp->fz[8], slots * sizeof(unsigned long long)));
