@@ -12,7 +12,7 @@ import torch
 
 from typing import List
 
-from cugraph_pyg._pyg_compat import Data, SamplerOutput, HeteroSamplerOutput, NodeSamplerInput, EdgeSamplerInput, ptr2index
+from cugraph_pyg._pyg_compat import Data, HeteroData, SamplerOutput, HeteroSamplerOutput, NodeSamplerInput, EdgeSamplerInput, ptr2index
 from .sampler_utils import filter_cugraph_pyg_store, filter_cugraph_pyg_hetero_store, neg_sample, neg_cat
 
 
@@ -90,9 +90,40 @@ class SampleIterator:
             data.csr_indptr, data.csr_indices = s.csr
         return data
 
+    def __hetero_data(self, s):
+        grp = getattr(s, "group", None)
+        if grp is None or not self.prefetch_call_group_features:
+            return filter_cugraph_pyg_hetero_store(self.__feature_store, self.__graph_store, s.node, s.row, s.col, s.edge, None)
+        reader, b = s.reader, s.batch_index
+        vtypes = list(s.node.keys())
+        blocks = grp.get("_features")
+        if blocks is None:  # one gather per (vertex type, feature) for the whole call group
+            attrs = []
+            for a in self.__feature_store.get_all_tensor_attrs():
+                if not isinstance(a.group_name, tuple) and a.group_name in vtypes:
+                    a.index = reader.type_index(grp, vtypes.index(a.group_name))
+                    attrs.append(a)
+            blocks = {(a.group_name, a.attr_name): t for a, t in zip(attrs, self.__feature_store.multi_get_tensor(attrs))} if attrs else {}
+            grp["_features"] = blocks
+        data = HeteroData()
+        for et, ei in s.edge_index.items():
+            data[et].edge_index = ei
+        for nt, node in s.node.items():
+            data[nt].num_nodes = int(node.numel())
+        for (nt, name), block in blocks.items():
+            t0, t1 = grp["_type_start"][vtypes.index(nt)][b], grp["_type_start"][vtypes.index(nt)][b + 1]
+            data[nt][name] = block[t0:t1]
+        edge_attrs = [a for a in self.__feature_store.get_all_tensor_attrs() if isinstance(a.group_name, tuple) and a.group_name in s.edge]
+        if edge_attrs:
+            for a in edge_attrs:
+                a.index = s.edge[a.group_name]
+            for a, t in zip(edge_attrs, self.__feature_store.multi_get_tensor(edge_attrs)):
+                data[a.group_name][a.attr_name] = t
+        return data
+
     def __hetero(self, s: HeteroSamplerOutput):
         """sampler.py:118-163 of the reference: HeteroData with per-type n_id / e_id / counts."""
-        data = filter_cugraph_pyg_hetero_store(self.__feature_store, self.__graph_store, s.node, s.row, s.col, s.edge, None)
+        data = self.__hetero_data(s)
         for key, node in s.node.items():
             if "n_id" not in data[key]:
                 data[key].n_id = node
@@ -125,6 +156,14 @@ class _Output(SamplerOutput):
     edge_index = None  # [2, E] view of the call group's edge_index block (row = source, col = destination, batch-local ids)
     group = None      # the call group's raw sampler output (shared by its mini-batches)
     node_span = None  # (first, last + 1) position of this mini-batch's vertices in the call group's concatenated renumber map
+
+
+class _HeteroOutput(HeteroSamplerOutput):
+    """HeteroSamplerOutput + private fields used by SampleIterator."""
+
+    edge_index = None  # {edge type: [2, E] view of the call group's edge_index block}
+    group = None       # the call group's raw sampler output
+    batch_index = None  # position of this mini-batch in its call group
 
 
 class SampleReader:
@@ -283,6 +322,38 @@ class HeterogeneousSampleReader(SampleReader):
         raw["_rmo"] = host[lto.numel():lto.numel() + rmo.numel()].tolist()
         raw["_base"] = host[lto.numel() + rmo.numel():].view(L + 1, Vt, B).tolist()
         raw["_input_offsets"] = raw["input_offsets"].tolist()
+        # Everything a mini-batch needs is built per CALL GROUP by a handful of launches and sliced per mini-batch (as in the
+        # homogeneous reader): type-local vertex ids, the edge_index block, per-hop counts.
+        dev = raw["map"].device
+        n_total = int(raw["map"].numel())
+        rm = host[lto.numel():lto.numel() + rmo.numel()]
+        seg_len = rm[1:] - rm[:-1]                                   # segments [label][vertex type]
+        seg_off = torch.tensor(self.__vertex_offsets[:Vt], dtype=torch.int64).repeat(B)
+        raw["_map_local"] = raw["map"] - torch.repeat_interleave(seg_off.to(dev, non_blocking=True), seg_len.to(dev, non_blocking=True),
+                                                                 output_size=n_total)
+        raw["_edge_index"] = torch.stack([raw["minors"], raw["majors"]], dim=0)
+        steps = torch.cat([host[lto.numel() + rmo.numel():].view(L + 1, Vt, B), seg_len.view(B, Vt).t().reshape(1, Vt, B)], dim=0)
+        raw["_num_sampled_nodes"] = (steps[1:] - steps[:-1]).permute(2, 1, 0).contiguous()        # [B, Vt, L + 1]
+        lt = host[:lto.numel()]
+        raw["_num_sampled_edges"] = (lt[1:] - lt[:-1]).view(B, T, L)
+        # where the vertices of (mini-batch b, type vt) sit in the call group's per-type concatenation (feature prefetch)
+        seg = seg_len.view(B, Vt)
+        raw["_type_start"] = torch.cat([torch.zeros((1, Vt), dtype=torch.int64), seg.cumsum(0)], dim=0).t().tolist()  # [Vt][B + 1]
+
+    def type_index(self, raw, vt: int):
+        """type-local ids of every vertex of type vt in the call group, mini-batch after mini-batch (no host sync)."""
+        key = ("_type_index", vt)
+        if key not in raw:
+            Vt, B = raw["_Vt"], raw["_B"]
+            dev = raw["map"].device
+            rmo, tstart = raw["_rmo"], raw["_type_start"][vt]
+            total = tstart[B]
+            lens = torch.tensor([tstart[b + 1] - tstart[b] for b in range(B)], dtype=torch.int64)
+            shift = torch.tensor([rmo[b * Vt + vt] - tstart[b] for b in range(B)], dtype=torch.int64)
+            pos = torch.arange(total, device=dev) + torch.repeat_interleave(shift.to(dev, non_blocking=True), lens.to(dev, non_blocking=True),
+                                                                            output_size=total)
+            raw[key] = raw["_map_local"][pos]
+        return raw[key]
 
     def _decode(self, raw: Dict[str, torch.Tensor], index: int):
         T, Vt, L = raw["_T"], raw["_Vt"], raw["_L"]
@@ -290,19 +361,19 @@ class HeterogeneousSampleReader(SampleReader):
         node, num_sampled_nodes = {}, {}
         for vt, name in enumerate(self.__vertex_types):
             n0, n1 = rmo[index * Vt + vt], rmo[index * Vt + vt + 1]
-            node[name] = raw["map"][n0:n1] - self.__vertex_offsets[vt]
-            b = [base[s][vt][index] for s in range(L + 1)] + [n1 - n0]
-            num_sampled_nodes[name] = torch.tensor([b[s + 1] - b[s] for s in range(L + 1)])
-        row, col, edge, num_sampled_edges = {}, {}, {}, {}
+            node[name] = raw["_map_local"][n0:n1]
+            num_sampled_nodes[name] = raw["_num_sampled_nodes"][index, vt]
+        row, col, edge, num_sampled_edges, edge_index = {}, {}, {}, {}, {}
         for t, et in enumerate(self.__edge_types):
             g = (index * T + t) * L
             e0, e1 = lto[g], lto[g + L]
-            row[et] = raw["minors"][e0:e1]
-            col[et] = raw["majors"][e0:e1]
+            edge_index[et] = raw["_edge_index"][:, e0:e1]
+            row[et] = edge_index[et][0]
+            col[et] = edge_index[et][1]
             # edge_id is the position inside the (label, edge type) group and the group's slice of
             # edge_renumber_map starts at its first edge, so emap[edge_id] (sampler.py:334-341) is this slice
             edge[et] = raw["edge_renumber_map"][e0:e1]
-            num_sampled_edges[et] = torch.tensor([lto[g + h + 1] - lto[g + h] for h in range(L)])
+            num_sampled_edges[et] = raw["_num_sampled_edges"][index, t]
         input_type = raw["input_type"]
         if isinstance(input_type, (list, tuple)):
             input_type = tuple(input_type)
@@ -313,8 +384,11 @@ class HeterogeneousSampleReader(SampleReader):
         meta = self._seed_metadata(raw, index)
         # edge_inverse already holds ids local to (label, vertex type): no de-offsetting by the other type's count
         # (the reference subtracts `max + 1` of the lower type, sampler.py:452-461)
-        return HeteroSamplerOutput(node=node, row=row, col=col, edge=edge, batch=None, num_sampled_nodes=num_sampled_nodes,
-                                   num_sampled_edges=num_sampled_edges, metadata=((input_type, meta[0]),) + tuple(meta[1:]))
+        out = _HeteroOutput(node=node, row=row, col=col, edge=edge, batch=None, num_sampled_nodes=num_sampled_nodes,
+                            num_sampled_edges=num_sampled_edges, metadata=((input_type, meta[0]),) + tuple(meta[1:]))
+        out.edge_index, out.group, out.batch_index = edge_index, raw, index
+        out.reader = self
+        return out
 
 
 class BaseSampler:

@@ -53,15 +53,17 @@ def _torch_dtype(name):
 # ------------------------------------------------------------------------------------------------
 # G1: gather
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("memory_type", ["continuous", "chunked", "distributed"])
-@pytest.mark.parametrize("dim,stride", [(32, 32), (32, 33), (127, 127), (128, 128), (129, 129), (513, 513), (256, 256), (1, 1)])
+_DIMS = [(32, 32), (32, 33), (127, 127), (128, 128), (129, 129), (513, 513), (256, 256), (1, 1)]
+# the full width / stride sweep runs on the chunked type; the other two memory types take three shapes
+_GATHER_SHAPES = [("chunked", d, s) for d, s in _DIMS] + [(m, d, s) for m in ("continuous", "distributed") for d, s in ((32, 32), (128, 128), (32, 33))]
+
+
+@pytest.mark.parametrize("memory_type,dim,stride", _GATHER_SHAPES)
 @pytest.mark.parametrize("emb,out", [("f32", "f32"), ("f16", "f16"), ("f32", "f16"), ("f16", "f32")])
 @pytest.mark.parametrize("idx", ["i32", "i64"])
 def test_gather_matrix(wg, oracle, memory_type, dim, stride, emb, out, idx):
     import torch
 
-    if memory_type != "chunked" and (dim, stride) not in ((32, 32), (128, 128), (32, 33)):
-        pytest.skip("full dim sweep runs on the chunked type only")
     wgth, comm = wg
     rows, n = 20011, 5003
     rng = np.random.default_rng(dim * 7 + stride)

@@ -238,6 +238,49 @@ def test_call_group_feature_prefetch_equals_per_batch_fetch(stack):
     assert fetch_a == 2 and fetch_b == 8  # 2 call groups of 4 mini-batches
 
 
+@pytest.mark.parametrize("prefetch", [True, False])
+def test_hetero_loader_features_per_call_group(stack, prefetch):
+    """Heterogeneous mini-batches carry, per vertex type, the feature rows of their own n_id -- with the per-call-group feature
+    fetch (one gather per (type, feature) and call group, row slices per mini-batch) and with the per-mini-batch fetch."""
+    cugraph_pyg, FS, sampler = stack
+    from cugraph_pyg.sampler.sampler import SampleIterator
+
+    rng = np.random.default_rng(11)
+    na, nb = 50, 70
+    graph_store, feature_store = cugraph_pyg.data.GraphStore(), FS()
+    ab = torch.stack([torch.from_numpy(rng.integers(0, na, 600)), torch.from_numpy(rng.integers(0, nb, 600))])
+    ba = torch.stack([torch.from_numpy(rng.integers(0, nb, 500)), torch.from_numpy(rng.integers(0, na, 500))])
+    aa = torch.stack([torch.from_numpy(rng.integers(0, na, 400)), torch.from_numpy(rng.integers(0, na, 400))])
+    graph_store[("a", "ab", "b"), "coo", False, (na, nb)] = ab
+    graph_store[("b", "ba", "a"), "coo", False, (nb, na)] = ba
+    graph_store[("a", "aa", "a"), "coo", False, (na, na)] = aa
+    xa = torch.arange(na * 2, dtype=torch.float32).reshape(na, 2)
+    xb = 1000 + torch.arange(nb * 3, dtype=torch.float32).reshape(nb, 3)
+    feature_store["a", "x", None] = xa
+    feature_store["b", "x", None] = xb
+    feature_store["a", "y", None] = torch.arange(na)
+    old = SampleIterator.prefetch_call_group_features
+    SampleIterator.prefetch_call_group_features = prefetch
+    try:
+        loader = cugraph_pyg.loader.NeighborLoader((feature_store, graph_store), num_neighbors={("a", "ab", "b"): [3, 2], ("b", "ba", "a"): [3, 2],
+                                                                                             ("a", "aa", "a"): [2, 2]},
+                                                   input_nodes=("a", torch.arange(40)), batch_size=8, shuffle=False, local_seeds_per_call=16)
+        seen = 0
+        for i, batch in enumerate(loader):
+            assert batch["a"].n_id[:8].tolist() == list(range(8 * i, 8 * i + 8))  # seeds first
+            assert torch.equal(batch["a"].x, xa[batch["a"].n_id]) and torch.equal(batch["a"].y, batch["a"].n_id)
+            assert torch.equal(batch["b"].x, xb[batch["b"].n_id])
+            for et, full in ((("a", "ab", "b"), ab), (("b", "ba", "a"), ba), (("a", "aa", "a"), aa)):
+                ei, e_id = batch[et].edge_index, batch[et].e_id
+                assert ei.shape[1] == e_id.numel() == int(batch[et].num_sampled_edges.sum())
+                assert torch.equal(full[0][e_id], batch[et[0]].n_id[ei[0]]) and torch.equal(full[1][e_id], batch[et[2]].n_id[ei[1]])
+            assert int(batch["a"].num_sampled_nodes.sum()) == batch["a"].n_id.numel()
+            seen += 1
+        assert seen == 5
+    finally:
+        SampleIterator.prefetch_call_group_features = old
+
+
 @pytest.mark.parametrize("biased", [False, True])
 def test_link_neighbor_loader_temporal_homogeneous(stack, biased):
     """tests/loader/test_neighbor_loader.py:1059-1101 of the reference (seed edge 3 -> 3 at time -1)."""
