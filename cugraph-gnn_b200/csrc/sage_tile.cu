@@ -206,10 +206,15 @@ __global__ void __launch_bounds__(kThreads, 1) sage_tile_kernel(const __grid_con
       if (col < f_out) {
         const float bv      = bias ? bias[col] : 0.f;
         const long long i0  = tile * kTileRows + lane_grp * 32;
+        const int n_valid   = (int)(n_dst - i0 < 32 ? n_dst - i0 : 32);  // warp-uniform (<= 0: nothing to store)
         float* o            = out + i0 * out_stride + col;
+        // streaming stores (evict-first): the output is written once and never read here, and must not push the feature rows
+        // the gather re-reads out of L2 (v3 of the kernel: 33 % L2 hit rate on a block whose source rows fit L2 three times over)
 #pragma unroll
-        for (int rr = 0; rr < 32; rr++)
-          if (i0 + rr < n_dst) o[(long long)rr * out_stride] = __uint_as_float(v[rr]) + bv;
+        for (int rr = 0; rr < 32; rr++) {
+          if (rr < n_valid) __stcs(o, __uint_as_float(v[rr]) + bv);
+          o += out_stride;
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
