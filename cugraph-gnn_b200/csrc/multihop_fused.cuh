@@ -922,7 +922,12 @@ static bool multihop_begin_fused(MhCall& c)
     WGB_EXPECTS(n > 0, "the fused sampler kernel does not fit on this device");
     mc = n;
   }
-  const int clusters = std::min(B, mc);
+  int clusters = std::min(B, mc);
+  // WGB_MH_SMS=<n>: at most n SMs for this kernel (labels are taken by ticket, so fewer CTAs simply take more labels each).  A
+  // sampler CTA fills an SM's register file, so the SMs it leaves alone are where the feature gather of the previous call group
+  // runs at the same time (spatial split of the GPU between the two stages of a loader's pipeline).
+  if (const char* e = getenv("WGB_MH_SMS"))
+    if (atoi(e) > 0) clusters = std::max(1, std::min(clusters, atoi(e) / CL));
   cfg.gridDim        = dim3((unsigned int)(clusters * CL), 1, 1);
   WGB_CUDA_TRY(cudaLaunchKernelEx(&cfg, fz_label_kernel<ColT>, a));
   WGB_CHECK_LAUNCH();
