@@ -380,6 +380,8 @@ def run_ours(args):
             prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
         prime.append(torch.empty(int(n_max * 1.25), dtype=torch.int64, device=dev))
         prime += [torch.empty(int(e_max * 1.25), dtype=torch.int64, device=dev) for _ in range(3)]
+    if side is not None:  # the synchronous per-stage pass gathers on the main stream: its pool gets a feature block too
+        prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
     del prime
     torch.cuda.synchronize()
     if world > 1:
