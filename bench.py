@@ -374,13 +374,19 @@ def run_ours(args):
     # blocks 25 % above the warm-up maxima in the allocator (4 of each: up to three call groups are alive in the pipelined
     # loop -- one being built, two whose results the host has not read yet).
     prime = []
-    for _ in range(4):
+    block_bytes = int(n_max * 1.25) * FEAT_DIM * 4
+    free_bytes = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    # (the north-star shape leaves ~30 GB beside its 102 GB table: parking more feature blocks than fit makes torch's allocator
+    # release and re-request them every other step, profiles/r2aw_bench_headline_n1_e2e_debug.json)
+    n_feature_blocks = max(2, min(4, int(0.6 * free_bytes / max(block_bytes, 1))))
+    for i in range(4):
         # the feature block is allocated on the stream that runs the gather: torch keeps one pool per stream
-        with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
-            prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
+        if i < n_feature_blocks:
+            with torch.cuda.stream(side) if side is not None else contextlib.nullcontext():
+                prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
         prime.append(torch.empty(int(n_max * 1.25), dtype=torch.int64, device=dev))
         prime += [torch.empty(int(e_max * 1.25), dtype=torch.int64, device=dev) for _ in range(3)]
-    if side is not None:  # the synchronous per-stage pass gathers on the main stream: its pool gets a feature block too
+    if side is not None and n_feature_blocks == 4:  # the synchronous per-stage pass gathers on the main stream: its pool gets a block too
         prime.append(torch.empty((int(n_max * 1.25), FEAT_DIM), dtype=torch.float32, device=dev))
     del prime
     torch.cuda.synchronize()
