@@ -6,13 +6,14 @@
 // one 16 B/slot hash table for all labels (94 MB at the bench shape: beyond L2) -- measured 7x the algorithmic DRAM
 // traffic.  A label (1024 seeds -> <= 282 k vertices at fan-out [25,10], ~40 k in practice) is an independent unit of
 // work; everything it produces between its hops fits in L2 next to the other labels in flight.  So:
-//   * a cluster of CL CTAs (CL = 1..8, chosen so that labels-in-flight x CL covers the 148 SMs) takes labels by ticket
-//     and runs seeds -> [count -> sample -> dedup -> compact] x hops for its label, phases separated by cluster barriers
-//     (barrier.cluster, ~0.2 us) instead of kernel boundaries; per-CTA partial sums travel through distributed shared
-//     memory;
+//   * a cluster of CL CTAs (CL = 1..8, chosen so that labels-in-flight x CL covers the 148 SMs; call groups of >= 74
+//     labels run one CTA per label) takes labels by ticket and runs seeds -> [count -> sample -> dedup -> compact] x hops
+//     for its label, phases separated by cluster barriers (CL > 1; per-CTA partial sums travel through distributed shared
+//     memory) or by the CTA barrier (CL = 1) instead of kernel boundaries;
 //   * the label's hash table is private (no label in the key): 8-byte slots {vertex:32 | aux:32}, buckets of four = one
 //     32-byte sector read by one 256-bit load, sized from the label's true counts every hop and memset by the cluster
-//     itself, so it lives and dies in L2;
+//     itself (measured at 148 labels in flight: the call group's 325 MB of scratch does NOT stay in the 126 MB L2 -- 40 %
+//     sector hit rate -- see profiles/r2_sampler_latency_experiments.txt for what that does and does not cost);
 //   * all per-label scratch is laid out label-major (label l's vertices at lo[l] * fstride, edges at lo[l] * estride):
 //     the label's vertex array IS its renumber map (seeds first, then every hop's new vertices in first-occurrence
 //     order), its edge arrays ARE the output segments -- _finish is a segmented copy;
