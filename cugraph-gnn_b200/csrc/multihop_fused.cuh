@@ -663,13 +663,11 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
       if (c.rank == 0 && tid == 0) e_hop[h] = e_h;
       known = nbase + n_rows;
       FZ_T(T0);
-      // P2: a fresh table for (everything numbered so far + this hop's edges)
-      nb = fz_buckets((unsigned int)known + (unsigned int)e_h);
-      for (unsigned int i = cti; i < nb * 4u; i += CT)
-        fz_store_slot(&tb[i], kFzEmpty, pol.keep);
-      c.sync();  // table cleared, row offsets visible
-      FZ_T(T0 + 1);
-      // P3: the hop's rows are sampled (independent of the table); numbered vertices enter the table with their local id
+      c.sync();  // row offsets and extents visible
+      // P2: the hop's rows are sampled.  The table is not involved: it is cleared only AFTER this phase, because sampling streams
+      // ~1.6 MB of graph sectors per label through L2 (240 MB per 148-label call group) -- a table cleared before it was out in DRAM
+      // again by the time the inserts came, and they ran at the DRAM rate of random read-modify-writes (27 G/s chip-wide, what
+      // profiles/r2ay_atomic_probe.txt measures for a 283 MB table) instead of the L2 rate (40-45 G/s for tables that fit).
       if (e_h > 0) {
         FzSink<ColT> sink{destl + ebase, majl + ebase, gidl + ebase};
         const unsigned long long hop_seed = a.random_state + (unsigned long long)h * 0x9E3779B97F4A7C15ULL;
@@ -677,20 +675,24 @@ __global__ void __launch_bounds__(WGB_FZ_BOUND, 1) fz_label_kernel(const __grid_
         else if (M <= 16) fz_sample_rows<ColT, 16>(a, c, a.Rstart + vbeg, a.Rdeg + vbeg, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
         else fz_sample_rows<ColT, 32>(a, c, a.Rstart + vbeg, a.Rdeg + vbeg, Ol, nbase, n_rows, ebase, rowbase, M, hop_seed, sink, pol.stream);
       }
+      FZ_T(T0 + 1);
+      // P3: a fresh table for (everything numbered so far + this hop's edges), written by every thread as it leaves the sampling
+      // loop (no barrier in between: nothing reads the table before the one below)
+      nb = fz_buckets((unsigned int)known + (unsigned int)e_h);
+      for (unsigned int i = cti; i < nb * 4u; i += CT)
+        fz_store_slot(&tb[i], kFzEmpty, pol.keep);
+      c.sync();  // table cleared, edges written
+      FZ_T(T0 + 2);
+      // P4: numbered vertices enter the table with their local id, endpoints with their edge index (the smallest wins a new
+      // vertex); the two kinds of insert commute (the slot keeps the minimum), so they share a phase
 #if WGB_FZ_INSERT_STREAM
       fz_insert_stream<long long>(tb, nb, pol.keep, Fl, known, 0u, nullptr, (int)cti, (int)CT);
+      fz_insert_stream<ColT>(tb, nb, pol.keep, destl + ebase, e_h, kFzPending, auxl + ebase, (int)cti, (int)CT);
 #else
       FZ_HASH_LOOP(
         c, known, [&](int j) -> unsigned int { return (unsigned int)Fl[j]; },
         [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v, pol.keep); },
         [&](int j, const FzProbe& pr) { fz_upsert(tb, nb, pr, (unsigned int)j, pol.keep); });
-#endif
-      c.sync();  // edges written, known vertices in the table
-      FZ_T(T0 + 2);
-      // P4: endpoints enter the table; the smallest edge index wins a new vertex
-#if WGB_FZ_INSERT_STREAM
-      fz_insert_stream<ColT>(tb, nb, pol.keep, destl + ebase, e_h, kFzPending, auxl + ebase, (int)cti, (int)CT);
-#else
       FZ_HASH_LOOP(
         c, e_h, [&](int i) -> unsigned int { return (unsigned int)destl[ebase + i]; },
         [&](int, unsigned int v) -> FzProbe { return fz_probe(tb, nb, v, pol.keep); },
@@ -1051,7 +1053,7 @@ static void fz_print_phases(wholegraph_multihop_sampler_* sp)
 {
   if (!sp->timing || sp->fz_phase_labels == 0) return;
   static const char* seed_names[5] = {"", "seeds: clear table", "seeds: insert", "seeds: first occurrences", "seeds: local ids"};
-  static const char* hop_names[6]  = {"count + scan", "clear table", "sample + re-insert known", "insert endpoints", "first occurrences", "local ids"};
+  static const char* hop_names[6]  = {"count + scan", "sample", "clear table", "insert known + endpoints", "first occurrences", "local ids"};
   fprintf(stderr, "[wgb multihop fused] mean time of a label per phase (%lld labels), kernel span %.1f us per call\n", sp->fz_phase_labels,
           1e-3 * sp->fz_span_ns / (double)std::max<long long>(1, sp->fz_calls));
   double tot = 0;
