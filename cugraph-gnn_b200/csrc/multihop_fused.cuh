@@ -511,16 +511,27 @@ __device__ FZ_SAMPLE_FN void fz_sample_rows(const FzArgs& a, const FzCluster& c,
   const Affine lane_skip = affine_skip_loop((unsigned long long)g);
   int* Wg                = &c.sh->W[wib][sub * G];
   const int warps        = (int)c.size * (kFzThreads / 32);
-  for (int batch = (int)c.rank * (kFzThreads / 32) + wib; (long long)batch * 32 < n_rows; batch += warps) {
-    const int r         = batch * 32 + lane;
-    long long start_own = 0;
-    int N_own = 0, off_own = 0;
-    if (r < n_rows) {  // the row's extent, as the count phase found it (coalesced reads of the label's scratch, not row_ptr again)
-      start_own = Rs[nbase + r];
-      N_own     = Rd[nbase + r];
-      off_own   = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
+  // the extents of batch k + 1 are read (three coalesced loads) before batch k is sampled: with the sampling phase alone in its
+  // barrier interval the chain extents -> col read -> stores is what a warp waits for, batch after batch
+  auto load_rows = [&](int batch, long long& start, int& N, int& off) {
+    const int r = batch * 32 + lane;
+    start       = 0;
+    N = off = 0;
+    if ((long long)batch * 32 < n_rows && r < n_rows) {
+      start = Rs[nbase + r];
+      N     = Rd[nbase + r];
+      off   = Ol[nbase + r] - ebase;  // relative to the hop's first edge; the sink's arrays start there
     }
-    // (reading the extents of batch k + 1 before batch k is sampled was measured without effect, profiles/r2s_*, and cost registers)
+  };
+  int batch = (int)c.rank * (kFzThreads / 32) + wib;
+  long long start_nxt;
+  int N_nxt, off_nxt;
+  load_rows(batch, start_nxt, N_nxt, off_nxt);
+  for (; (long long)batch * 32 < n_rows; batch += warps) {
+    const int r               = batch * 32 + lane;
+    const long long start_own = start_nxt;
+    const int N_own = N_nxt, off_own = off_nxt;
+    load_rows(batch + warps, start_nxt, N_nxt, off_nxt);
     uniform_small_rows32<ColT, G, false>(a.col, a.col_off, M, seed, a.tab, lane_skip, Wg, lane, rowbase + r, nbase + r, start_own, N_own,
                                          off_own, sink, col_policy);
   }
